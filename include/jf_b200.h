@@ -1,0 +1,135 @@
+/* jf_b200.h -- C ABI of the B200-native MSM / NTT core for the mpc-jellyfish PLONK prover.
+ *
+ * The reference (100 % Rust) has no FFI seam of its own: its hot path is the set of static
+ * trait calls out of the workspace into arkworks.  Each entry point below
+ * names the call(s) it replaces.  A `jf-b200-sys` crate binds exactly these symbols
+ * (see INTEGRATION.md for the bindgen/`extern "C"` block and the patched call sites).
+ *
+ * Conventions
+ *   - Field elements: ark-ff's in-memory layout, little-endian u64 limbs (4 for BN254 Fr/Fq and
+ *     BLS12-381 Fr, 6 for BLS12-381 Fq), MONTGOMERY form unless a parameter says otherwise.
+ *     A `&[Fr]` / `&mut [Fr]` can be passed as is.
+ *   - Affine G1 point: x || y (2*L limbs).  The identity is (0, 0) plus, on output, an int
+ *     flag (ark-ec's `Affine { x: 0, y: 0, infinity: true }`).
+ *   - Every function returns a jf_status; nothing throws or aborts across the boundary.
+ *     jf_last_error() gives a human-readable reason for the last failure on that context.
+ *   - Contexts are thread-safe (rayon / tokio workers may call concurrently: calls on one
+ *     context are serialised on its stream).  Host buffers are caller-owned and only read
+ *     (scalars, points) or overwritten in place (jf_ntt) during the call; device memory is
+ *     owned by the library behind opaque handles.
+ *   - There is NO CPU fallback: without a usable CUDA device jf_ctx_create fails.
+ */
+#ifndef JF_B200_H
+#define JF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jf_ctx jf_ctx; /* one CUDA device + stream + workspace */
+typedef struct jf_srs jf_srs; /* device-resident commit key (`UnivariateProverParam::powers_of_g`) */
+
+typedef enum {
+    JF_OK = 0,
+    JF_ERR_INVALID_ARG = -1,      /* -> PCSError::InvalidParameters (primitives/src/pcs/errors.rs:17-34) */
+    JF_ERR_CUDA = -2,             /* -> PCSError::UpstreamError */
+    JF_ERR_DOMAIN_TOO_LARGE = -3, /* log_n > two-adicity -> PlonkError::DomainCreationError (plonk/src/errors.rs:16-49) */
+    JF_ERR_SCALAR_RANGE = -4,     /* a scalar was >= the group order (arkworks BigInts from into_bigint never are) */
+    JF_ERR_NOMEM = -5
+} jf_status;
+
+typedef enum { JF_BN254 = 0, JF_BLS12_381 = 1 } jf_curve;
+typedef enum { JF_BN254_FR = 0, JF_BN254_FQ = 1, JF_BLS12_381_FR = 2, JF_BLS12_381_FQ = 3 } jf_field;
+
+/* ---- context ------------------------------------------------------------------------ */
+int jf_ctx_create(int device, jf_ctx **out);
+void jf_ctx_destroy(jf_ctx *ctx);
+/* Run on an externally owned CUDA stream (a `cudaStream_t` passed as void*); NULL = the context's own. */
+int jf_ctx_set_stream(jf_ctx *ctx, void *cuda_stream);
+int jf_ctx_sync(jf_ctx *ctx);
+const char *jf_last_error(const jf_ctx *ctx);
+/* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
+uint64_t jf_ctx_launch_count(const jf_ctx *ctx);
+
+/* ---- commit key ---------------------------------------------------------------------
+ * jf_srs_load uploads `powers_of_g` once (it is immutable across proofs:
+ * plonk/src/proof_system/structs.rs:583 `ProvingKey.commit_key`).  Records are `stride_bytes`
+ * apart, each starting with x || y in Montgomery form; if `inf_flag_offset` >= 0 the byte at
+ * that offset inside a record is ark-ec's `infinity: bool`, otherwise (0,0) means identity.
+ * `window_bits` = 0 picks the signed-digit window from n; `precompute` != 0 additionally
+ * stores 2^(window_bits*t) * P_i for every window t so that all windows share one bucket set.
+ */
+int jf_srs_load(jf_ctx *ctx, int curve, const void *affine_pts, size_t n, size_t stride_bytes,
+                long inf_flag_offset, int window_bits, int precompute, jf_srs **out);
+/* `gen_srs_for_testing` (primitives/src/pcs/univariate_kzg/srs.rs:118-153) with a caller-chosen,
+ * KNOWN beta (4 canonical limbs) and g = the curve generator: powers_of_g[i] = beta^i * g. */
+int jf_srs_generate_for_testing(jf_ctx *ctx, int curve, const uint64_t *beta, size_t n, int window_bits,
+                                int precompute, jf_srs **out);
+/* Copy `count` affine points starting at `first` back to the host (x || y each). */
+int jf_srs_read(jf_ctx *ctx, const jf_srs *srs, size_t first, size_t count, uint64_t *out_xy);
+size_t jf_srs_len(const jf_srs *srs);
+int jf_srs_window_bits(const jf_srs *srs);
+void jf_srs_free(jf_ctx *ctx, jf_srs *srs);
+
+/* ---- MSM ----------------------------------------------------------------------------
+ * jf_msm == `E::G1::msm_bigint(&powers_of_g[base_offset..], scalars).into_affine()`
+ * (primitives/src/pcs/univariate_kzg/mod.rs:108-111 in `commit`, :151-155 in `open`).
+ * Uses min(n, srs_len - base_offset) pairs like arkworks.  Scalars: 4 limbs each; canonical
+ * BigInts when scalars_in_montgomery == 0 (what `into_bigint`, mod.rs:392, produces), or the
+ * polynomial's own Montgomery-form coefficients when != 0 (the conversion then happens on the
+ * GPU and `convert_to_bigints`, mod.rs:390-395, can be dropped by the caller).
+ * Result: out_xy = affine x || y (Montgomery), *out_infinity = 1 for the identity. */
+int jf_msm(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const uint64_t *scalars, size_t n,
+           int scalars_in_montgomery, uint64_t *out_xy, int *out_infinity);
+/* jf_msm_batch == `batch_commit`'s par_iter over polynomials (mod.rs:119-131) as ONE call. */
+int jf_msm_batch(jf_ctx *ctx, const jf_srs *srs, const uint64_t *const *scalars, const size_t *lens,
+                 const size_t *base_offsets, size_t batch, int scalars_in_montgomery, uint64_t *out_xy,
+                 int *out_infinity);
+/* Device-resident form: scalars already in HBM (device pointer), result left in HBM as one
+ * XYZZ point (4*L limbs: X, Y, ZZ, ZZZ; x = X/ZZ, y = Y/ZZZ; ZZ = 0 <=> identity).  This is the
+ * per-GPU partial sum of a range-sharded MSM; it is all-gathered and fed to jf_msm_combine. */
+int jf_msm_device(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n,
+                  int scalars_in_montgomery, void *d_out_xyzz);
+/* Sum `parts` XYZZ partial results (host memory) and normalise: the tail of a sharded MSM. */
+int jf_msm_combine(jf_ctx *ctx, int curve, const uint64_t *xyzz_parts, size_t parts, uint64_t *out_xy,
+                   int *out_infinity);
+
+/* ---- NTT ----------------------------------------------------------------------------
+ * In-place radix-2 transforms with `Radix2EvaluationDomain` semantics (ark-poly 0.4.2), natural
+ * order in and out, `batch` vectors `batch_stride` ELEMENTS apart, field = BN254 Fr or BLS12-381 Fr.
+ *   inverse == 0: `domain.fft_in_place` / `coset.fft` (plonk/src/proof_system/prover.rs:552-567):
+ *       the first in_len entries are coefficients (the rest is treated as zero, i.e. arkworks'
+ *       resize), out[i] = sum_j c[j] * (offset * w^i)^j.
+ *   inverse != 0: `domain.ifft_in_place` (relation/src/constraint_system.rs:1172-1257) /
+ *       `coset.ifft` (prover.rs:672): c[j] = offset^-j * n^-1 * sum_i e[i] * w^(-ij).
+ * coset_offset: NULL for the plain domain, else 4 Montgomery limbs (`get_coset(Fr::GENERATOR)`,
+ * prover.rs:545).  log_n above the field's two-adicity -> JF_ERR_DOMAIN_TOO_LARGE. */
+int jf_ntt(jf_ctx *ctx, int field, uint64_t *data, size_t in_len, unsigned log_n, int inverse,
+           const uint64_t *coset_offset, size_t batch, size_t batch_stride);
+/* Same on a device pointer (data stays in HBM; used by the device-resident prover rows). */
+int jf_ntt_device(jf_ctx *ctx, int field, void *d_data, size_t in_len, unsigned log_n, int inverse,
+                  const uint64_t *coset_offset, size_t batch, size_t batch_stride);
+
+/* ---- device buffers (plumbing for callers that keep polynomials resident) ------------ */
+int jf_dev_alloc(jf_ctx *ctx, size_t bytes, void **out);
+int jf_dev_free(jf_ctx *ctx, void *ptr);
+int jf_dev_upload(jf_ctx *ctx, void *dst, const void *src, size_t bytes);
+int jf_dev_download(jf_ctx *ctx, void *dst, const void *src, size_t bytes);
+/* Page-locked host staging buffers (what the shim crate uses for coefficient vectors). */
+int jf_host_alloc(jf_ctx *ctx, size_t bytes, void **out);
+int jf_host_free(jf_ctx *ctx, void *ptr);
+
+/* ---- element-wise field kernels (K1 parity tests and the "next" rows) ----------------
+ * op: 0 mul, 1 add, 2 sub, 3 sqr, 4 inv, 5 to_mont, 6 from_mont, 7 neg; host arrays of n elements. */
+int jf_field_op(jf_ctx *ctx, int field, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+/* out[i] = scalars[i] * G (canonical 4-limb scalars) as affine x || y: fixed-base helper used by
+ * the tests to build point sets with known discrete logs. */
+int jf_fixed_base_mul(jf_ctx *ctx, int curve, const uint64_t *scalars, size_t n, uint64_t *out_xy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JF_B200_H */

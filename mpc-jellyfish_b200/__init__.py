@@ -1,0 +1,18 @@
+"""mpc-jellyfish_b200: B200-native MSM / NTT core of the mpc-jellyfish PLONK prover.
+
+The product is `libjf_b200.so` (hand-written sm_100a CUDA behind the C ABI of
+include/jf_b200.h).  This package is the Python host side: a ctypes binding plus mirrors of
+the reference's `UnivariateKzgPCS` and `Radix2EvaluationDomain` call surfaces.  Nothing in
+here computes on the CPU; without the CUDA library every entry point raises.
+"""
+from . import _ffi
+from .context import CommitKey, Context
+from .domain import Radix2EvaluationDomain
+from .errors import DomainCreationError, InvalidParameters, PCSError, PlonkError, UpstreamError
+from .pcs import Commitment, DensePolynomial, UnivariateKzgPCS, UnivariateProverParam
+
+__all__ = [
+    "Context", "CommitKey", "Radix2EvaluationDomain", "UnivariateKzgPCS", "UnivariateProverParam",
+    "DensePolynomial", "Commitment", "PCSError", "InvalidParameters", "UpstreamError", "PlonkError",
+    "DomainCreationError",
+]

@@ -1,0 +1,88 @@
+"""ctypes binding of libjf_b200.so -- exactly the symbols include/jf_b200.h declares.
+
+There is no fallback: if the shared library is missing or a symbol is absent, importing
+anything that computes raises.  (Loading the library does not need a GPU; creating a
+context does.)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjf_b200.so")
+
+c_u64p = ctypes.POINTER(ctypes.c_uint64)
+c_void_pp = ctypes.POINTER(ctypes.c_void_p)
+
+JF_OK = 0
+JF_ERR_INVALID_ARG = -1
+JF_ERR_CUDA = -2
+JF_ERR_DOMAIN_TOO_LARGE = -3
+JF_ERR_SCALAR_RANGE = -4
+JF_ERR_NOMEM = -5
+
+CURVES = {"bn254": 0, "bls12_381": 1}
+FIELDS = {"bn254_fr": 0, "bn254_fq": 1, "bls12_381_fr": 2, "bls12_381_fq": 3}
+FIELD_LIMBS = {"bn254_fr": 4, "bn254_fq": 4, "bls12_381_fr": 4, "bls12_381_fq": 6}
+CURVE_FQ_LIMBS = {"bn254": 4, "bls12_381": 6}
+CURVE_FR = {"bn254": "bn254_fr", "bls12_381": "bls12_381_fr"}
+FIELD_OPS = {"mul": 0, "add": 1, "sub": 2, "sqr": 3, "inv": 4, "to_mont": 5, "from_mont": 6, "neg": 7}
+
+# name -> (restype, argtypes); must list every function of include/jf_b200.h
+SIGNATURES = {
+    "jf_ctx_create": (ctypes.c_int, [ctypes.c_int, c_void_pp]),
+    "jf_ctx_destroy": (None, [ctypes.c_void_p]),
+    "jf_ctx_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "jf_ctx_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "jf_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "jf_ctx_launch_count": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "jf_srs_load": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                   ctypes.c_long, ctypes.c_int, ctypes.c_int, c_void_pp]),
+    "jf_srs_generate_for_testing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64p, ctypes.c_size_t, ctypes.c_int,
+                                                   ctypes.c_int, c_void_pp]),
+    "jf_srs_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, c_u64p]),
+    "jf_srs_len": (ctypes.c_size_t, [ctypes.c_void_p]),
+    "jf_srs_window_bits": (ctypes.c_int, [ctypes.c_void_p]),
+    "jf_srs_free": (None, [ctypes.c_void_p, ctypes.c_void_p]),
+    "jf_msm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, c_u64p, ctypes.c_size_t, ctypes.c_int,
+                              c_u64p, ctypes.POINTER(ctypes.c_int)]),
+    "jf_msm_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(c_u64p),
+                                    ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t,
+                                    ctypes.c_int, c_u64p, ctypes.POINTER(ctypes.c_int)]),
+    "jf_msm_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                     ctypes.c_int, ctypes.c_void_p]),
+    "jf_msm_combine": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64p, ctypes.c_size_t, c_u64p,
+                                      ctypes.POINTER(ctypes.c_int)]),
+    "jf_ntt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64p, ctypes.c_size_t, ctypes.c_uint, ctypes.c_int, c_u64p,
+                              ctypes.c_size_t, ctypes.c_size_t]),
+    "jf_ntt_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint,
+                                     ctypes.c_int, c_u64p, ctypes.c_size_t, ctypes.c_size_t]),
+    "jf_dev_alloc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, c_void_pp]),
+    "jf_dev_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "jf_dev_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "jf_dev_download": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "jf_host_alloc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, c_void_pp]),
+    "jf_host_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "jf_field_op": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_u64p, c_u64p, c_u64p, ctypes.c_size_t]),
+    "jf_fixed_base_mul": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64p, ctypes.c_size_t, c_u64p]),
+}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load libjf_b200.so (built by `__graft_entry__.build()` / `make -C mpc-jellyfish_b200/csrc`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libjf_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                "there is no CPU fallback." % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)  # AttributeError if the symbol is missing: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib

@@ -1,0 +1,126 @@
+// common.cuh -- context, error plumbing and workspace shared by the translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/jf_b200.h"
+
+namespace jf {
+
+// A grow-only device scratch buffer.
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t cap = 0;
+};
+
+struct NttPlan;  // ntt.cu
+
+}  // namespace jf
+
+struct jf_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    std::mutex mu;
+    std::string err;
+    uint64_t launches = 0;
+    int *d_err = nullptr;  // device-side sticky error flag (scalar range), checked at sync points
+    // named scratch buffers (grow-only)
+    std::map<std::string, jf::DevBuf> scratch;
+    void *pinned = nullptr;  // small pinned staging area for results
+    size_t pinned_cap = 0;
+    // cached NTT plans keyed by (field, log_n, inverse, coset offset limbs)
+    std::map<std::string, jf::NttPlan *> ntt_plans;
+};
+
+struct jf_srs {
+    int curve = 0;
+    size_t n = 0;          // number of points
+    int limbs64 = 4;       // u64 limbs per coordinate
+    int window_bits = 16;  // c
+    int windows = 16;      // W
+    int tables = 1;        // T: 1 (no precompute) or W
+    void *d_points = nullptr;  // tables * n affine points, table-major
+};
+
+namespace jf {
+
+inline int fail(jf_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define JF_CUDA(ctx, expr)                                                                         \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            return jf::fail(ctx, e_ == cudaErrorMemoryAllocation ? JF_ERR_NOMEM : JF_ERR_CUDA,     \
+                            std::string(#expr) + ": " + cudaGetErrorString(e_));                   \
+        }                                                                                          \
+    } while (0)
+
+#define JF_TRY(expr)                \
+    do {                            \
+        int rc_ = (expr);           \
+        if (rc_ != JF_OK) return rc_; \
+    } while (0)
+
+// scratch buffer of at least `bytes`, named so that independent users do not alias
+inline int scratch(jf_ctx *ctx, const char *name, size_t bytes, void **out) {
+    DevBuf &b = ctx->scratch[name];
+    if (b.cap < bytes) {
+        if (b.ptr) {
+            JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            JF_CUDA(ctx, cudaFree(b.ptr));
+            b.ptr = nullptr;
+            b.cap = 0;
+        }
+        size_t want = bytes + bytes / 8 + 256;
+        JF_CUDA(ctx, cudaMalloc(&b.ptr, want));
+        b.cap = want;
+    }
+    *out = b.ptr;
+    return JF_OK;
+}
+
+inline int pinned(jf_ctx *ctx, size_t bytes, void **out) {
+    if (ctx->pinned_cap < bytes) {
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        ctx->pinned_cap = 0;
+        JF_CUDA(ctx, cudaMallocHost(&ctx->pinned, bytes + 4096));
+        ctx->pinned_cap = bytes + 4096;
+    }
+    *out = ctx->pinned;
+    return JF_OK;
+}
+
+#define JF_LAUNCH_CHECK(ctx)                                                            \
+    do {                                                                                \
+        (ctx)->launches++;                                                              \
+        cudaError_t e_ = cudaGetLastError();                                            \
+        if (e_ != cudaSuccess)                                                          \
+            return jf::fail(ctx, JF_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+    } while (0)
+
+// entry points implemented per translation unit
+// d_out == d_data: in place.  Otherwise the result lands in d_out and d_data is clobbered.
+int ntt_run(jf_ctx *ctx, int field, void *d_data, void *d_out, size_t in_len, unsigned log_n, int inverse,
+            const uint64_t *coset_offset, size_t batch, size_t batch_stride);
+void ntt_free_plans(jf_ctx *ctx);
+int msm_run(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n, int mont,
+            void *d_out_xyzz);
+int msm_finish_host(jf_ctx *ctx, int curve, const uint64_t *xyzz_parts, size_t parts, uint64_t *out_xy, int *out_inf);
+int srs_build(jf_ctx *ctx, int curve, const void *d_base_points /* n affine, device */, size_t n, int window_bits,
+              int precompute, jf_srs **out);
+int srs_generate(jf_ctx *ctx, int curve, const uint64_t *beta, size_t n, void *d_out_points);
+int fixed_base_mul(jf_ctx *ctx, int curve, const void *d_scalars, size_t n, void *d_out_points);
+int field_op(jf_ctx *ctx, int field, int op, const void *d_a, const void *d_b, void *d_out, size_t n);
+
+}  // namespace jf

@@ -1,0 +1,598 @@
+// msm.cu -- variable-base G1 multi-scalar multiplication (K2 of SURVEY.md §2.3).
+//
+// Replaces ark-ec 0.4.2 `VariableBaseMSM::msm_bigint` as called by `UnivariateKzgPCS::commit`
+// and `::open` (primitives/src/pcs/univariate_kzg/mod.rs:108-111,151-155), and through them
+// by every commitment of prover rounds 1, 2, 3 and 5 (plonk/src/proof_system/prover.rs:84,139,206,
+// 396-416) and of `preprocess` (plonk/src/proof_system/snark.rs:562-571).
+//
+// Pipeline (all on one stream, no host round trip until the single result point):
+//   1. digits + histogram : signed c-bit digits of every scalar, one atomic per non-zero digit
+//   2. scan               : bucket offsets and the task list offsets (a task = at most
+//                           TASK_LEN consecutive entries of one bucket -> bounded, balanced work
+//                           even when all scalars fall into one bucket)
+//   3. scatter            : counting sort of (sign | table | point index) by bucket
+//   4. accumulate         : one thread per task, XYZZ += affine mixed additions (8M + 2S),
+//                           points gathered from the resident commit key
+//   5. bucket sums        : add the task partials of each bucket
+//   6. reduce             : sum_b (b+1) * B_b by log2(#buckets) halving levels
+//                           (S_g = B_2g + B_2g+1; A_g = S_g + B_2g+1; B'_(g-1) = 2 S_g)
+//   7. window fold        : only without precomputation: Horner over the per-window sums.
+// With a precomputed commit key (tables 2^(c t) * P_i, built once in jf_srs_load) all windows
+// share ONE bucket set and step 7 disappears.
+#include <algorithm>
+#include <utility>
+#include "common.cuh"
+#include "ec.cuh"
+
+namespace jf {
+
+static constexpr int TASK_LEN_LOG = 7;
+static constexpr uint32_t TASK_LEN = 1u << TASK_LEN_LOG;  // max entries per accumulate task
+static constexpr uint32_t IDX_BITS = 26;                  // payload = sign(1) | table(5) | index(26)
+static constexpr uint32_t IDX_MASK = (1u << IDX_BITS) - 1;
+
+struct MsmGeom {
+    uint32_t n;            // pairs
+    uint32_t base_offset;  // first commit-key point used
+    uint32_t srs_n;        // points per table
+    int c, W, T, S;        // window bits, windows, tables, bucket sets
+    uint32_t NB;           // buckets per set = 2^(c-1)
+    int mont;              // scalars arrive in Montgomery form
+};
+
+// ---- 1. digits -------------------------------------------------------------------------
+template <class Fr> __device__ __forceinline__ bool load_scalar(const uint32_t *p, int mont, uint32_t (&s)[8]) {
+    Fp<Fr> a;
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 x = __ldg(q), y = __ldg(q + 1);
+    a.v[0] = x.x; a.v[1] = x.y; a.v[2] = x.z; a.v[3] = x.w;
+    a.v[4] = y.x; a.v[5] = y.y; a.v[6] = y.z; a.v[7] = y.w;
+    // canonical check: a < r  <=>  a - r borrows
+    uint32_t t[8], borrow;
+    chain_sub_p<Fr>(t, a.v, borrow);
+    if (mont) a = Fp<Fr>::from_mont(a);
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = a.v[i];
+    return borrow != 0;
+}
+
+__device__ __forceinline__ uint32_t take_bits(const uint32_t (&s)[8], int off, int c) {
+    int w = off >> 5, b = off & 31;
+    if (w >= 8) return 0;
+    uint64_t v = s[w];
+    if (w + 1 < 8) v |= (uint64_t)s[w + 1] << 32;
+    return (uint32_t)(v >> b) & ((1u << c) - 1);
+}
+
+// Calls f(window, digit) for every non-zero signed digit of s.
+template <class Fn> __device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], int c, int W, Fn f) {
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (c - 1);
+    for (int w = 0; w < W; w++) {
+        uint32_t raw = take_bits(s, w * c, c) + carry;
+        int32_t d;
+        if (raw > half) {
+            d = (int32_t)raw - (int32_t)(1u << c);
+            carry = 1;
+        } else {
+            d = (int32_t)raw;
+            carry = 0;
+        }
+        if (d != 0) f(w, d);
+    }
+}
+
+template <class Fr>
+__global__ void msm_count_kernel(const uint32_t *scalars, MsmGeom g, uint32_t *counts, int *err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    uint32_t s[8];
+    if (!load_scalar<Fr>(scalars + 8 * (size_t)i, g.mont, s)) {
+        *err = JF_ERR_SCALAR_RANGE;
+        return;
+    }
+    for_each_digit(s, g.c, g.W, [&](int w, int32_t d) {
+        uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+        uint32_t bucket = (uint32_t)(w / g.T) * g.NB + (mag - 1);
+        atomicAdd(&counts[bucket], 1u);
+    });
+}
+
+template <class Fr>
+__global__ void msm_scatter_kernel(const uint32_t *scalars, MsmGeom g, uint32_t *cursor, uint32_t *sorted) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    uint32_t s[8];
+    if (!load_scalar<Fr>(scalars + 8 * (size_t)i, g.mont, s)) return;
+    for_each_digit(s, g.c, g.W, [&](int w, int32_t d) {
+        uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+        uint32_t bucket = (uint32_t)(w / g.T) * g.NB + (mag - 1);
+        uint32_t pos = atomicAdd(&cursor[bucket], 1u);
+        sorted[pos] = (d < 0 ? 0x80000000u : 0u) | ((uint32_t)(w % g.T) << IDX_BITS) | (g.base_offset + i);
+    });
+}
+
+// ---- 2. scan -----------------------------------------------------------------------------
+// exclusive scan of (count, ceil(count / TASK_LEN)) over `total` buckets, 3 small kernels
+static constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 16, SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void scan_local_kernel(const uint32_t *counts, uint32_t total, uint32_t *off, uint32_t *toff,
+                                  uint2 *block_sums) {
+    __shared__ uint2 sh[SCAN_THREADS];
+    const uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
+    uint32_t c[SCAN_ITEMS];
+    uint2 sum = make_uint2(0, 0);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        c[k] = base + k < total ? counts[base + k] : 0;
+        sum.x += c[k];
+        sum.y += (c[k] + TASK_LEN - 1) >> TASK_LEN_LOG;
+    }
+    sh[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < SCAN_THREADS; d <<= 1) {  // Hillis-Steele inclusive scan
+        uint2 v = make_uint2(0, 0);
+        if ((int)threadIdx.x >= d) v = sh[threadIdx.x - d];
+        __syncthreads();
+        sh[threadIdx.x].x += v.x;
+        sh[threadIdx.x].y += v.y;
+        __syncthreads();
+    }
+    uint2 run = make_uint2(sh[threadIdx.x].x - sum.x, sh[threadIdx.x].y - sum.y);
+    if (threadIdx.x == SCAN_THREADS - 1) block_sums[blockIdx.x] = sh[threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < total) {
+            off[base + k] = run.x;
+            toff[base + k] = run.y;
+        }
+        run.x += c[k];
+        run.y += (c[k] + TASK_LEN - 1) >> TASK_LEN_LOG;
+    }
+}
+
+__global__ void scan_sums_kernel(uint2 *block_sums, uint32_t nblocks, uint32_t *off, uint32_t *toff, uint32_t total) {
+    // single thread block; nblocks <= 1024
+    __shared__ uint2 sh[1024];
+    uint2 mine = threadIdx.x < nblocks ? block_sums[threadIdx.x] : make_uint2(0, 0);
+    sh[threadIdx.x] = mine;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        uint2 v = make_uint2(0, 0);
+        if ((int)threadIdx.x >= d) v = sh[threadIdx.x - d];
+        __syncthreads();
+        sh[threadIdx.x].x += v.x;
+        sh[threadIdx.x].y += v.y;
+        __syncthreads();
+    }
+    if (threadIdx.x < nblocks) block_sums[threadIdx.x] = make_uint2(sh[threadIdx.x].x - mine.x, sh[threadIdx.x].y - mine.y);
+    if (threadIdx.x == 1023) {  // grand totals live one past the end
+        off[total] = sh[1023].x;
+        toff[total] = sh[1023].y;
+    }
+}
+
+__global__ void scan_add_kernel(const uint2 *block_sums, uint32_t total, uint32_t *off, uint32_t *toff, uint32_t *cursor) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    uint2 b = block_sums[i / SCAN_CHUNK];
+    uint32_t o = off[i] + b.x;
+    off[i] = o;
+    cursor[i] = o;
+    toff[i] += b.y;
+}
+
+// ---- task list ---------------------------------------------------------------------------
+// task = (start in sorted[], len-1 << 22 | bucket)
+__global__ void build_tasks_kernel(const uint32_t *off, const uint32_t *toff, uint32_t total, uint2 *tasks) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total) return;
+    uint32_t start = off[b], cnt = off[b + 1] - start, t0 = toff[b];
+    for (uint32_t k = 0; k * TASK_LEN < cnt; k++) {
+        uint32_t len = min(TASK_LEN, cnt - k * TASK_LEN);
+        tasks[t0 + k] = make_uint2(start + k * TASK_LEN, ((len - 1) << 22) | b);
+    }
+}
+
+// ---- 4. accumulate -------------------------------------------------------------------------
+template <class Fq> __device__ __forceinline__ Affine<Fq> load_affine(const Affine<Fq> *p) {
+    Affine<Fq> r;
+    constexpr int WORDS = 2 * Fq::N;  // 16 or 24 words, multiple of 4
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint32_t *o = reinterpret_cast<uint32_t *>(&r);
+#pragma unroll
+    for (int k = 0; k < WORDS / 4; k++) {
+        uint4 x = __ldg(q + k);
+        o[4 * k] = x.x; o[4 * k + 1] = x.y; o[4 * k + 2] = x.z; o[4 * k + 3] = x.w;
+    }
+    return r;
+}
+
+template <class Fq> __device__ __forceinline__ void store_xyzz(XYZZ<Fq> *p, const XYZZ<Fq> &v) {
+    constexpr int WORDS = 4 * Fq::N;
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    const uint32_t *o = reinterpret_cast<const uint32_t *>(&v);
+#pragma unroll
+    for (int k = 0; k < WORDS / 4; k++) q[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+}
+template <class Fq> __device__ __forceinline__ XYZZ<Fq> load_xyzz(const XYZZ<Fq> *p) {
+    XYZZ<Fq> r;
+    constexpr int WORDS = 4 * Fq::N;
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint32_t *o = reinterpret_cast<uint32_t *>(&r);
+#pragma unroll
+    for (int k = 0; k < WORDS / 4; k++) {
+        uint4 x = q[k];
+        o[4 * k] = x.x; o[4 * k + 1] = x.y; o[4 * k + 2] = x.z; o[4 * k + 3] = x.w;
+    }
+    return r;
+}
+
+template <class Fq>
+__global__ void __launch_bounds__(128)
+msm_accumulate_kernel(const Affine<Fq> *points, uint32_t srs_n, const uint32_t *sorted, const uint2 *tasks,
+                      const uint32_t *toff, uint32_t total_buckets, XYZZ<Fq> *partials) {
+    const uint32_t ntasks = toff[total_buckets];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntasks; t += gridDim.x * blockDim.x) {
+        const uint2 task = tasks[t];
+        const uint32_t len = (task.y >> 22) + 1;
+        const uint32_t *ent = sorted + task.x;
+        XYZZ<Fq> acc = XYZZ<Fq>::inf();
+        for (uint32_t e = 0; e < len; e++) {
+            const uint32_t pl = ent[e];
+            const Affine<Fq> *src = points + (size_t)((pl >> IDX_BITS) & 31u) * srs_n + (pl & IDX_MASK);
+            Affine<Fq> p = load_affine(src);
+            if (p.is_inf()) continue;
+            if (pl & 0x80000000u) p.y = Fp<Fq>::neg(p.y);
+            acc.add_affine(p);
+        }
+        store_xyzz(partials + t, acc);
+    }
+}
+
+// ---- 5. bucket sums ----------------------------------------------------------------------
+template <class Fq>
+__global__ void bucket_sum_kernel(const XYZZ<Fq> *partials, const uint32_t *toff, uint32_t total_buckets, XYZZ<Fq> *X) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total_buckets) return;
+    uint32_t t0 = toff[b], t1 = toff[b + 1];
+    XYZZ<Fq> acc = XYZZ<Fq>::inf();
+    for (uint32_t t = t0; t < t1; t++) acc.add(load_xyzz(partials + t));
+    store_xyzz(X + b, acc);
+}
+
+// ---- 6. weighted reduction --------------------------------------------------------------
+// One halving level over every set: X (n per set, weights 1..n), P (n per set, weight 1, absent
+// on the first level) -> Xo, Po (n/2 per set).
+template <class Fq>
+__device__ __forceinline__ void halve_one(const XYZZ<Fq> *X, const XYZZ<Fq> *P, XYZZ<Fq> *Xo, XYZZ<Fq> *Po, uint32_t n,
+                                          uint32_t g, bool has_p) {
+    XYZZ<Fq> x0 = load_xyzz(X + 2 * g), x1 = load_xyzz(X + 2 * g + 1);
+    XYZZ<Fq> s = x0;
+    s.add(x1);
+    XYZZ<Fq> a = s;
+    a.add(x1);
+    if (has_p) {
+        XYZZ<Fq> p0 = load_xyzz(P + 2 * g);
+        p0.add(load_xyzz(P + 2 * g + 1));
+        a.add(p0);
+    }
+    store_xyzz(Po + g, a);
+    if (g >= 1) store_xyzz(Xo + g - 1, s.dbl());
+    else store_xyzz(Xo + n / 2 - 1, XYZZ<Fq>::inf());
+}
+
+template <class Fq>
+__global__ void halve_kernel(const XYZZ<Fq> *X, const XYZZ<Fq> *P, XYZZ<Fq> *Xo, XYZZ<Fq> *Po, uint32_t n, int has_p) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n / 2) return;
+    size_t set = blockIdx.y;
+    halve_one<Fq>(X + set * n, P + set * n, Xo + set * (n / 2), Po + set * (n / 2), n, g, has_p != 0);
+}
+
+// Tail: one CTA per set finishes n <= 2 * blockDim levels with block barriers, leaves
+// R_set = X[0] + P[0] in out[set].  bufs: A = (X, P), B = (Xo, Po) both of capacity n per set.
+template <class Fq>
+__global__ void halve_tail_kernel(XYZZ<Fq> *XA, XYZZ<Fq> *PA, XYZZ<Fq> *XB, XYZZ<Fq> *PB, uint32_t n, uint32_t cap,
+                                  int has_p, XYZZ<Fq> *out) {
+    size_t set = blockIdx.x;
+    XYZZ<Fq> *x = XA + set * cap, *p = PA + set * cap, *xo = XB + set * cap, *po = PB + set * cap;
+    bool hp = has_p != 0;
+    while (n > 1) {
+        for (uint32_t g = threadIdx.x; g < n / 2; g += blockDim.x) halve_one<Fq>(x, p, xo, po, n, g, hp);
+        __syncthreads();
+        XYZZ<Fq> *t = x; x = xo; xo = t;
+        t = p; p = po; po = t;
+        n >>= 1;
+        hp = true;
+    }
+    if (threadIdx.x == 0) {
+        XYZZ<Fq> r = load_xyzz(x);
+        if (hp) r.add(load_xyzz(p));
+        store_xyzz(out + set, r);
+    }
+}
+
+// ---- 7. fold the per-set sums: result = sum_s 2^(shift s) R_s --------------------------
+template <class Fq> __global__ void fold_sets_kernel(const XYZZ<Fq> *R, int S, int shift, XYZZ<Fq> *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    XYZZ<Fq> acc = load_xyzz(R + (S - 1));
+    for (int s = S - 2; s >= 0; s--) {
+        for (int k = 0; k < shift; k++) acc = acc.dbl();
+        acc.add(load_xyzz(R + s));
+    }
+    store_xyzz(out, acc);
+}
+
+template <class Fq> __global__ void set_inf_kernel(XYZZ<Fq> *out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) store_xyzz(out, XYZZ<Fq>::inf());
+}
+
+// ---- driver ------------------------------------------------------------------------------
+template <class C>
+static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n_in, int mont,
+                     void *d_out) {
+    using Fq = typename C::Fq;
+    using Fr = typename C::Fr;
+    using P = XYZZ<Fq>;
+    cudaStream_t st = ctx->stream;
+    if (base_offset > srs->n) return fail(ctx, JF_ERR_INVALID_ARG, "msm: base_offset beyond the commit key");
+    size_t n = n_in < srs->n - base_offset ? n_in : srs->n - base_offset;  // arkworks: min(len(bases), len(scalars))
+    if (n == 0) {
+        set_inf_kernel<Fq><<<1, 32, 0, st>>>((P *)d_out);
+        JF_LAUNCH_CHECK(ctx);
+        return JF_OK;
+    }
+    MsmGeom g;
+    g.n = (uint32_t)n;
+    g.base_offset = (uint32_t)base_offset;
+    g.srs_n = (uint32_t)srs->n;
+    g.c = srs->window_bits;
+    g.W = srs->windows;
+    g.T = srs->tables;
+    g.S = (g.W + g.T - 1) / g.T;
+    g.NB = 1u << (g.c - 1);
+    g.mont = mont;
+    const uint32_t total = (uint32_t)g.S * g.NB;
+    const size_t max_entries = n * (size_t)g.W;
+    const size_t max_tasks = max_entries / TASK_LEN + total + 1;
+    if (max_entries >= (1ull << 32)) return fail(ctx, JF_ERR_INVALID_ARG, "msm: n * windows must stay below 2^32");
+
+    uint32_t *counts, *off, *toff, *cursor, *sorted;
+    uint2 *block_sums, *tasks;
+    P *partials, *XA, *PA, *XB, *PB, *Rs;
+    int *err;
+    void *p;
+    const uint32_t scan_blocks = (total + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    if (scan_blocks > 1024) return fail(ctx, JF_ERR_INVALID_ARG, "msm: too many buckets");
+    JF_TRY(scratch(ctx, "msm_counts", sizeof(uint32_t) * (total + 1) * 4 + sizeof(uint2) * 1024 + 64, &p));
+    counts = (uint32_t *)p;
+    off = counts + (total + 1);
+    toff = off + (total + 1);
+    cursor = toff + (total + 1);
+    block_sums = (uint2 *)(cursor + (total + 1));  // 4 * (total + 1) words: 16-byte aligned
+    JF_TRY(scratch(ctx, "msm_sorted", sizeof(uint32_t) * max_entries, &p));
+    sorted = (uint32_t *)p;
+    JF_TRY(scratch(ctx, "msm_tasks", sizeof(uint2) * max_tasks, &p));
+    tasks = (uint2 *)p;
+    JF_TRY(scratch(ctx, "msm_partials", sizeof(P) * max_tasks, &p));
+    partials = (P *)p;
+    JF_TRY(scratch(ctx, "msm_reduce", sizeof(P) * ((size_t)total * 4 + g.S + 8), &p));
+    XA = (P *)p;  // four level buffers of `total` points each (X / P ping-pong), then the per-set sums
+    XB = XA + total;
+    PA = XB + total;
+    PB = PA + total;
+    Rs = PB + total;
+    err = ctx->d_err;
+
+    const uint32_t *sc = (const uint32_t *)d_scalars;
+    JF_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (total + 1), st));
+    const unsigned nblk = (unsigned)((n + 255) / 256);
+    msm_count_kernel<Fr><<<nblk, 256, 0, st>>>(sc, g, counts, err);
+    JF_LAUNCH_CHECK(ctx);
+    scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, total, off, toff, block_sums);
+    JF_LAUNCH_CHECK(ctx);
+    scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, scan_blocks, off, toff, total);
+    JF_LAUNCH_CHECK(ctx);
+    scan_add_kernel<<<(total + 255) / 256, 256, 0, st>>>(block_sums, total, off, toff, cursor);
+    JF_LAUNCH_CHECK(ctx);
+    msm_scatter_kernel<Fr><<<nblk, 256, 0, st>>>(sc, g, cursor, sorted);
+    JF_LAUNCH_CHECK(ctx);
+    build_tasks_kernel<<<(total + 255) / 256, 256, 0, st>>>(off, toff, total, tasks);
+    JF_LAUNCH_CHECK(ctx);
+    {
+        const unsigned blocks = (unsigned)std::min<size_t>((max_tasks + 127) / 128, (size_t)ctx->sm_count * 32);
+        msm_accumulate_kernel<Fq><<<blocks, 128, 0, st>>>((const Affine<Fq> *)srs->d_points, g.srs_n, sorted, tasks, toff,
+                                                          total, partials);
+        JF_LAUNCH_CHECK(ctx);
+    }
+    bucket_sum_kernel<Fq><<<(total + 127) / 128, 128, 0, st>>>(partials, toff, total, XA);
+    JF_LAUNCH_CHECK(ctx);
+    // halving levels: big ones as grid launches, the tail inside one CTA per set
+    uint32_t nlev = g.NB;
+    P *x = XA, *pp = PA, *xo = XB, *po = PB;
+    bool has_p = false;
+    // level arrays are densely packed per set (stride = the level's n)
+    while (nlev > 512) {
+        dim3 grid((nlev / 2 + 127) / 128, g.S);
+        halve_kernel<Fq><<<grid, 128, 0, st>>>(x, pp, xo, po, nlev, has_p ? 1 : 0);
+        JF_LAUNCH_CHECK(ctx);
+        std::swap(x, xo);
+        std::swap(pp, po);
+        has_p = true;
+        nlev >>= 1;
+    }
+    halve_tail_kernel<Fq><<<g.S, 256, 0, st>>>(x, pp, xo, po, nlev, nlev, has_p ? 1 : 0, Rs);
+    JF_LAUNCH_CHECK(ctx);
+    if (g.S > 1) {
+        fold_sets_kernel<Fq><<<1, 32, 0, st>>>(Rs, g.S, g.c * g.T, (P *)d_out);
+        JF_LAUNCH_CHECK(ctx);
+    } else {
+        JF_CUDA(ctx, cudaMemcpyAsync(d_out, Rs, sizeof(P), cudaMemcpyDeviceToDevice, st));
+    }
+    return JF_OK;
+}
+
+int msm_run(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n, int mont,
+            void *d_out_xyzz) {
+    if (srs->curve == JF_BN254) return msm_run_t<Bn254G1>(ctx, srs, base_offset, d_scalars, n, mont, d_out_xyzz);
+    if (srs->curve == JF_BLS12_381) return msm_run_t<Bls12381G1>(ctx, srs, base_offset, d_scalars, n, mont, d_out_xyzz);
+    return fail(ctx, JF_ERR_INVALID_ARG, "msm: unknown curve");
+}
+
+// ---- host tail: sum partial XYZZ points and normalise (`into_affine`) ---------------------
+template <class C>
+static int msm_finish_t(const uint64_t *parts, size_t nparts, uint64_t *out_xy, int *out_inf) {
+    using Fq = typename C::Fq;
+    constexpr int L = Fq::N / 2;  // u64 limbs per coordinate
+    XYZZ<Fq> acc = XYZZ<Fq>::inf();
+    for (size_t i = 0; i < nparts; i++) {
+        XYZZ<Fq> p;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(parts + i * 4 * L);
+        for (int k = 0; k < Fq::N; k++) {
+            p.x.v[k] = w[k];
+            p.y.v[k] = w[Fq::N + k];
+            p.zz.v[k] = w[2 * Fq::N + k];
+            p.zzz.v[k] = w[3 * Fq::N + k];
+        }
+        acc.add(p);
+    }
+    Affine<Fq> a = acc.to_affine();
+    uint32_t *o = reinterpret_cast<uint32_t *>(out_xy);
+    for (int k = 0; k < Fq::N; k++) {
+        o[k] = a.x.v[k];
+        o[Fq::N + k] = a.y.v[k];
+    }
+    *out_inf = acc.is_inf() ? 1 : 0;
+    return JF_OK;
+}
+
+int msm_finish_host(jf_ctx *ctx, int curve, const uint64_t *xyzz_parts, size_t parts, uint64_t *out_xy, int *out_inf) {
+    if (curve == JF_BN254) return msm_finish_t<Bn254G1>(xyzz_parts, parts, out_xy, out_inf);
+    if (curve == JF_BLS12_381) return msm_finish_t<Bls12381G1>(xyzz_parts, parts, out_xy, out_inf);
+    return fail(ctx, JF_ERR_INVALID_ARG, "msm: unknown curve");
+}
+
+// ---- commit key construction ---------------------------------------------------------------
+// out[i] = 2^c * in[i]  (affine -> affine), the step from table t-1 to table t
+template <class Fq> __global__ void table_step_kernel(const Affine<Fq> *in, Affine<Fq> *out, uint32_t n, int c) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<Fq> p = load_affine(in + i);
+    if (p.is_inf()) {
+        out[i] = p;
+        return;
+    }
+    XYZZ<Fq> a = XYZZ<Fq>::dbl_affine(p);
+    for (int k = 1; k < c; k++) a = a.dbl();
+    out[i] = a.to_affine();
+}
+
+template <class C> __global__ void fixed_base_kernel(const uint32_t *scalars, uint32_t n, Affine<typename C::Fq> *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) k[j] = scalars[8 * (size_t)i + j];
+    XYZZ<typename C::Fq> r = scalar_mul(C::generator(), k, 8);
+    out[i] = r.to_affine();
+}
+
+// scalars[i] = beta^i as canonical integers
+template <class Fr> __global__ void beta_powers_kernel(Fp<Fr> beta_mont, uint32_t n, uint32_t *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp<Fr> e = Fp<Fr>::from_mont(Fp<Fr>::pow_u64(beta_mont, i));
+#pragma unroll
+    for (int j = 0; j < 8; j++) out[8 * (size_t)i + j] = e.v[j];
+}
+
+template <class C> static int fixed_base_t(jf_ctx *ctx, const void *d_scalars, size_t n, void *d_out) {
+    if (n == 0) return JF_OK;
+    fixed_base_kernel<C><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const uint32_t *)d_scalars, (uint32_t)n,
+                                                                            (Affine<typename C::Fq> *)d_out);
+    JF_LAUNCH_CHECK(ctx);
+    return JF_OK;
+}
+
+int fixed_base_mul(jf_ctx *ctx, int curve, const void *d_scalars, size_t n, void *d_out_points) {
+    if (curve == JF_BN254) return fixed_base_t<Bn254G1>(ctx, d_scalars, n, d_out_points);
+    if (curve == JF_BLS12_381) return fixed_base_t<Bls12381G1>(ctx, d_scalars, n, d_out_points);
+    return fail(ctx, JF_ERR_INVALID_ARG, "unknown curve");
+}
+
+template <class C> static int srs_generate_t(jf_ctx *ctx, const uint64_t *beta, size_t n, void *d_out) {
+    using Fr = typename C::Fr;
+    if (n == 0) return JF_OK;
+    Fp<Fr> b;
+    for (int i = 0; i < 4; i++) {
+        b.v[2 * i] = (uint32_t)beta[i];
+        b.v[2 * i + 1] = (uint32_t)(beta[i] >> 32);
+    }
+    b = Fp<Fr>::to_mont(b);
+    void *d_sc;
+    JF_TRY(scratch(ctx, "srs_scalars", 32 * n, &d_sc));
+    beta_powers_kernel<Fr><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(b, (uint32_t)n, (uint32_t *)d_sc);
+    JF_LAUNCH_CHECK(ctx);
+    return fixed_base_t<C>(ctx, d_sc, n, d_out);
+}
+
+int srs_generate(jf_ctx *ctx, int curve, const uint64_t *beta, size_t n, void *d_out_points) {
+    if (curve == JF_BN254) return srs_generate_t<Bn254G1>(ctx, beta, n, d_out_points);
+    if (curve == JF_BLS12_381) return srs_generate_t<Bls12381G1>(ctx, beta, n, d_out_points);
+    return fail(ctx, JF_ERR_INVALID_ARG, "unknown curve");
+}
+
+static int pick_window(size_t n) {
+    int lg = 0;
+    while (((size_t)1 << lg) < n) lg++;
+    int c = lg - 4;  // 2^20 -> 16
+    if (c < 6) c = 6;
+    if (c > 20) c = 20;
+    return c;
+}
+
+template <class C>
+static int srs_build_t(jf_ctx *ctx, int curve, const void *d_base, size_t n, int window_bits, int precompute, jf_srs **out) {
+    using Fq = typename C::Fq;
+    using Fr = typename C::Fr;
+    if (n >= (1u << IDX_BITS)) return fail(ctx, JF_ERR_INVALID_ARG, "srs: at most 2^26 - 1 points per commit key");
+    int c = window_bits > 0 ? window_bits : pick_window(n);
+    if (c < 2 || c > 22) return fail(ctx, JF_ERR_INVALID_ARG, "srs: window_bits must be in [2, 22]");
+    int W = (Fr::BITS + 1 + c - 1) / c;  // one spare bit so the top signed digit never carries out
+    if (W > 32 && precompute) return fail(ctx, JF_ERR_INVALID_ARG, "srs: too many windows for a precomputed key");
+    jf_srs *s = new jf_srs();
+    s->curve = curve;
+    s->n = n;
+    s->limbs64 = Fq::N / 2;
+    s->window_bits = c;
+    s->windows = W;
+    s->tables = precompute ? W : 1;
+    size_t bytes = sizeof(Affine<Fq>) * n * (size_t)s->tables;
+    if (bytes == 0) bytes = 64;
+    cudaError_t e = cudaMalloc(&s->d_points, bytes);
+    if (e != cudaSuccess) {
+        delete s;
+        return fail(ctx, JF_ERR_NOMEM, std::string("srs: cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    if (n) {
+        JF_CUDA(ctx, cudaMemcpyAsync(s->d_points, d_base, sizeof(Affine<Fq>) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        Affine<Fq> *tab = (Affine<Fq> *)s->d_points;
+        for (int t = 1; t < s->tables; t++) {
+            table_step_kernel<Fq><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(tab + (size_t)(t - 1) * n,
+                                                                                 tab + (size_t)t * n, (uint32_t)n, c);
+            JF_LAUNCH_CHECK(ctx);
+        }
+    }
+    JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = s;
+    return JF_OK;
+}
+
+int srs_build(jf_ctx *ctx, int curve, const void *d_base_points, size_t n, int window_bits, int precompute, jf_srs **out) {
+    if (curve == JF_BN254) return srs_build_t<Bn254G1>(ctx, curve, d_base_points, n, window_bits, precompute, out);
+    if (curve == JF_BLS12_381) return srs_build_t<Bls12381G1>(ctx, curve, d_base_points, n, window_bits, precompute, out);
+    return fail(ctx, JF_ERR_INVALID_ARG, "unknown curve");
+}
+
+}  // namespace jf
