@@ -547,7 +547,7 @@ static int pick_window(size_t n) {
     int lg = 0;
     while (((size_t)1 << lg) < n) lg++;
     int c = lg - 4;  // 2^20 -> 16
-    if (c < 6) c = 6;
+    if (c < 8) c = 8;
     if (c > 20) c = 20;
     return c;
 }
@@ -560,14 +560,13 @@ static int srs_build_t(jf_ctx *ctx, int curve, const void *d_base, size_t n, int
     int c = window_bits > 0 ? window_bits : pick_window(n);
     if (c < 2 || c > 22) return fail(ctx, JF_ERR_INVALID_ARG, "srs: window_bits must be in [2, 22]");
     int W = (Fr::BITS + 1 + c - 1) / c;  // one spare bit so the top signed digit never carries out
-    if (W > 32 && precompute) return fail(ctx, JF_ERR_INVALID_ARG, "srs: too many windows for a precomputed key");
     jf_srs *s = new jf_srs();
     s->curve = curve;
     s->n = n;
     s->limbs64 = Fq::N / 2;
     s->window_bits = c;
     s->windows = W;
-    s->tables = precompute ? W : 1;
+    s->tables = precompute ? std::min(W, 32) : 1;  // window w = set * T + table; at most 32 tables fit the payload
     size_t bytes = sizeof(Affine<Fq>) * n * (size_t)s->tables;
     if (bytes == 0) bytes = 64;
     cudaError_t e = cudaMalloc(&s->d_points, bytes);
