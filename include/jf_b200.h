@@ -65,9 +65,10 @@ uint64_t jf_ctx_launch_count(const jf_ctx *ctx);
 int jf_srs_load(jf_ctx *ctx, int curve, const void *affine_pts, size_t n, size_t stride_bytes,
                 long inf_flag_offset, int window_bits, int precompute, jf_srs **out);
 /* `gen_srs_for_testing` (primitives/src/pcs/univariate_kzg/srs.rs:118-153) with a caller-chosen,
- * KNOWN beta (4 canonical limbs) and g = the curve generator: powers_of_g[i] = beta^i * g. */
-int jf_srs_generate_for_testing(jf_ctx *ctx, int curve, const uint64_t *beta, size_t n, int window_bits,
-                                int precompute, jf_srs **out);
+ * KNOWN beta (4 canonical limbs) and g = the curve generator: key[i] = beta^(first_power + i) * g
+ * (first_power > 0 yields the slice of the key one GPU holds in a range-sharded MSM). */
+int jf_srs_generate_for_testing(jf_ctx *ctx, int curve, const uint64_t *beta, size_t first_power, size_t n,
+                                int window_bits, int precompute, jf_srs **out);
 /* Copy `count` affine points starting at `first` back to the host (x || y each). */
 int jf_srs_read(jf_ctx *ctx, const jf_srs *srs, size_t first, size_t count, uint64_t *out_xy);
 size_t jf_srs_len(const jf_srs *srs);
@@ -93,7 +94,8 @@ int jf_msm_batch(jf_ctx *ctx, const jf_srs *srs, const uint64_t *const *scalars,
  * per-GPU partial sum of a range-sharded MSM; it is all-gathered and fed to jf_msm_combine. */
 int jf_msm_device(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n,
                   int scalars_in_montgomery, void *d_out_xyzz);
-/* Sum `parts` XYZZ partial results (host memory) and normalise: the tail of a sharded MSM. */
+/* Sum `parts` XYZZ partial results (host memory) and normalise: the tail of a sharded MSM.
+ * Pure host code; ctx may be NULL. */
 int jf_msm_combine(jf_ctx *ctx, int curve, const uint64_t *xyzz_parts, size_t parts, uint64_t *out_xy,
                    int *out_infinity);
 
@@ -128,6 +130,19 @@ int jf_field_op(jf_ctx *ctx, int field, int op, const uint64_t *a, const uint64_
 /* out[i] = scalars[i] * G (canonical 4-limb scalars) as affine x || y: fixed-base helper used by
  * the tests to build point sets with known discrete logs. */
 int jf_fixed_base_mul(jf_ctx *ctx, int curve, const uint64_t *scalars, size_t n, uint64_t *out_xy);
+
+/* ---- measurement hooks (bench.py) ------------------------------------------------------
+ * Per-kernel CUDA-event timing on the context's stream.  While enabled every kernel launch is
+ * bracketed by two events; jf_profile_collect synchronises, writes one line per kernel name
+ * ("name launches total_ms\n") into buf and resets the log.  Returns the number of bytes
+ * written or a negative jf_status. */
+int jf_profile_enable(jf_ctx *ctx, int on);
+long jf_profile_collect(jf_ctx *ctx, char *buf, size_t cap);
+/* Integer-pipe micro-benchmarks that give the MSM / NTT kernels their compute roof:
+ * kind 0: independent IMAD.WIDE.U32 chains -> 32x32->64 multiply-adds per second;
+ * kind 1: dependent 256-bit Montgomery multiplications (BN254 Fq) in registers -> field muls/s.
+ * *out_rate = operations per second over the whole GPU. */
+int jf_microbench(jf_ctx *ctx, int kind, double *out_rate);
 
 #ifdef __cplusplus
 }

@@ -9,10 +9,11 @@ from . import _ffi
 from .context import CommitKey, Context
 from .domain import Radix2EvaluationDomain
 from .errors import DomainCreationError, InvalidParameters, PCSError, PlonkError, UpstreamError
+from .sharded import ShardedMsm, combine_partials, poly_owner, shard_range
 from .pcs import Commitment, DensePolynomial, UnivariateKzgPCS, UnivariateProverParam
 
 __all__ = [
     "Context", "CommitKey", "Radix2EvaluationDomain", "UnivariateKzgPCS", "UnivariateProverParam",
     "DensePolynomial", "Commitment", "PCSError", "InvalidParameters", "UpstreamError", "PlonkError",
-    "DomainCreationError",
+    "DomainCreationError", "ShardedMsm", "combine_partials", "poly_owner", "shard_range",
 ]

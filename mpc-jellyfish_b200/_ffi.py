@@ -39,8 +39,8 @@ SIGNATURES = {
     "jf_ctx_launch_count": (ctypes.c_uint64, [ctypes.c_void_p]),
     "jf_srs_load": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
                                    ctypes.c_long, ctypes.c_int, ctypes.c_int, c_void_pp]),
-    "jf_srs_generate_for_testing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64p, ctypes.c_size_t, ctypes.c_int,
-                                                   ctypes.c_int, c_void_pp]),
+    "jf_srs_generate_for_testing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64p, ctypes.c_size_t, ctypes.c_size_t,
+                                                   ctypes.c_int, ctypes.c_int, c_void_pp]),
     "jf_srs_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, c_u64p]),
     "jf_srs_len": (ctypes.c_size_t, [ctypes.c_void_p]),
     "jf_srs_window_bits": (ctypes.c_int, [ctypes.c_void_p]),
@@ -66,6 +66,9 @@ SIGNATURES = {
     "jf_host_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "jf_field_op": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_u64p, c_u64p, c_u64p, ctypes.c_size_t]),
     "jf_fixed_base_mul": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64p, ctypes.c_size_t, c_u64p]),
+    "jf_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "jf_profile_collect": (ctypes.c_long, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]),
+    "jf_microbench": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
 }
 
 _lib = None

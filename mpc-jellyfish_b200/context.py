@@ -73,11 +73,11 @@ class Context:
         return CommitKey(self, curve, h)
 
     def generate_srs_for_testing(self, curve: str, beta: int, n: int, window_bits: int = 0,
-                                 precompute: bool = True) -> "CommitKey":
-        """`gen_srs_for_testing` with a known beta: powers_of_g[i] = beta^i * G (srs.rs:118-153)."""
+                                 precompute: bool = True, first_power: int = 0) -> "CommitKey":
+        """`gen_srs_for_testing` with a known beta: key[i] = beta^(first_power + i) * G (srs.rs:118-153)."""
         b = np.array([(beta >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for k in range(4)], dtype=np.uint64)
         h = ctypes.c_void_p()
-        self._check(self._lib.jf_srs_generate_for_testing(self._h, _ffi.CURVES[curve], _u64p(b), n, window_bits,
+        self._check(self._lib.jf_srs_generate_for_testing(self._h, _ffi.CURVES[curve], _u64p(b), first_power, n, window_bits,
                                                           int(precompute), ctypes.byref(h)))
         return CommitKey(self, curve, h)
 
@@ -165,6 +165,27 @@ class Context:
         out = np.zeros((s.shape[0], 2 * L), dtype=np.uint64)
         self._check(self._lib.jf_fixed_base_mul(self._h, _ffi.CURVES[curve], _u64p(s), s.shape[0], _u64p(out)))
         return out
+
+    # -- measurement hooks ------------------------------------------------------------------------
+    def profile(self, on: bool):
+        self._check(self._lib.jf_profile_enable(self._h, int(on)))
+
+    def profile_collect(self) -> dict:
+        """{kernel name: (launches, total_ms)} since the last collect (synchronises)."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        n = self._lib.jf_profile_collect(self._h, buf, len(buf))
+        if n < 0:
+            self._check(int(n))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split()
+            out[name] = (int(cnt), float(ms))
+        return out
+
+    def microbench(self, kind: int) -> float:
+        r = ctypes.c_double(0)
+        self._check(self._lib.jf_microbench(self._h, kind, ctypes.byref(r)))
+        return r.value
 
     def dev_alloc(self, nbytes: int) -> int:
         p = ctypes.c_void_p()

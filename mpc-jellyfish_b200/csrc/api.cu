@@ -30,9 +30,8 @@ template <class F> __global__ void field_op_kernel(int op, const Fp<F> *a, const
 
 template <class F> static int field_op_t(jf_ctx *ctx, int op, const void *a, const void *b, void *out, size_t n) {
     if (n == 0) return JF_OK;
-    field_op_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(op, (const Fp<F> *)a, (const Fp<F> *)b,
-                                                                             (Fp<F> *)out, n);
-    JF_LAUNCH_CHECK(ctx);
+    JF_LAUNCH(ctx, "field_op", field_op_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(op, (const Fp<F> *)a, (const Fp<F> *)b,
+                                                                             (Fp<F> *)out, n));
     return JF_OK;
 }
 
@@ -101,6 +100,11 @@ void jf_ctx_destroy(jf_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     ntt_free_plans(ctx);
     for (auto &kv : ctx->scratch) cudaFree(kv.second.ptr);
+    for (auto &r : ctx->prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    for (auto &e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaFree(ctx->d_err);
     cudaStreamDestroy(ctx->own_stream);
@@ -154,8 +158,8 @@ int jf_srs_load(jf_ctx *ctx, int curve, const void *affine_pts, size_t n, size_t
     return srs_build(ctx, curve, d_base, n, window_bits, precompute, out);
 }
 
-int jf_srs_generate_for_testing(jf_ctx *ctx, int curve, const uint64_t *beta, size_t n, int window_bits, int precompute,
-                                jf_srs **out) {
+int jf_srs_generate_for_testing(jf_ctx *ctx, int curve, const uint64_t *beta, size_t first_power, size_t n, int window_bits,
+                                int precompute, jf_srs **out) {
     JF_GUARD(ctx);
     if (!out || !beta) return fail(ctx, JF_ERR_INVALID_ARG, "srs_generate: null argument");
     if (curve != JF_BN254 && curve != JF_BLS12_381) return fail(ctx, JF_ERR_INVALID_ARG, "srs_generate: unknown curve");
@@ -163,7 +167,7 @@ int jf_srs_generate_for_testing(jf_ctx *ctx, int curve, const uint64_t *beta, si
     const size_t rec = (size_t)curve_limbs64(curve) * 16;
     void *d_base = nullptr;
     JF_TRY(scratch(ctx, "srs_stage", rec * (n ? n : 1), &d_base));
-    JF_TRY(srs_generate(ctx, curve, beta, n, d_base));
+    JF_TRY(srs_generate(ctx, curve, beta, first_power, n, d_base));
     return srs_build(ctx, curve, d_base, n, window_bits, precompute, out);
 }
 
@@ -248,7 +252,7 @@ int jf_msm_device(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void
 }
 
 int jf_msm_combine(jf_ctx *ctx, int curve, const uint64_t *xyzz_parts, size_t parts, uint64_t *out_xy, int *out_infinity) {
-    if (!ctx) return JF_ERR_INVALID_ARG;
+    /* pure host code: ctx may be NULL (it only receives the error text) */
     if (!xyzz_parts || !out_xy || !out_infinity) return fail(ctx, JF_ERR_INVALID_ARG, "msm_combine: null argument");
     return msm_finish_host(ctx, curve, xyzz_parts, parts, out_xy, out_infinity);
 }
@@ -357,6 +361,46 @@ int jf_fixed_base_mul(jf_ctx *ctx, int curve, const uint64_t *scalars, size_t n,
     JF_CUDA(ctx, cudaMemcpyAsync(out_xy, dp, rec * n, cudaMemcpyDeviceToHost, ctx->stream));
     JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return JF_OK;
+}
+
+// ---- measurement hooks ----------------------------------------------------------------------------
+int jf_profile_enable(jf_ctx *ctx, int on) {
+    JF_GUARD(ctx);
+    ctx->prof_on = on != 0;
+    return JF_OK;
+}
+
+long jf_profile_collect(jf_ctx *ctx, char *buf, size_t cap) {
+    JF_GUARD(ctx);
+    if (!buf || cap == 0) return JF_ERR_INVALID_ARG;
+    JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::map<std::string, std::pair<long, double>> agg;
+    for (auto &r : ctx->prof) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            auto &e = agg[r.name];
+            e.first++;
+            e.second += ms;
+        }
+        ctx->event_pool.push_back(r.a);
+        ctx->event_pool.push_back(r.b);
+    }
+    ctx->prof.clear();
+    std::string s;
+    char line[160];
+    for (auto &kv : agg) {
+        snprintf(line, sizeof line, "%s %ld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        s += line;
+    }
+    if (s.size() + 1 > cap) return fail(ctx, JF_ERR_INVALID_ARG, "profile_collect: buffer too small");
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return (long)s.size();
+}
+
+int jf_microbench(jf_ctx *ctx, int kind, double *out_rate) {
+    JF_GUARD(ctx);
+    if (!out_rate || kind < 0 || kind > 1) return fail(ctx, JF_ERR_INVALID_ARG, "microbench: bad argument");
+    return microbench(ctx, kind, out_rate);
 }
 
 }  // extern "C"

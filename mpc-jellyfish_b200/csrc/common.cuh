@@ -35,6 +35,11 @@ struct jf_ctx {
     std::map<std::string, jf::DevBuf> scratch;
     void *pinned = nullptr;  // small pinned staging area for results
     size_t pinned_cap = 0;
+    // optional per-kernel event timing (jf_profile_*): (name, start, stop) per launch
+    bool prof_on = false;
+    struct ProfRec { const char *name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> event_pool;
     // cached NTT plans keyed by (field, log_n, inverse, coset offset limbs)
     std::map<std::string, jf::NttPlan *> ntt_plans;
 };
@@ -109,6 +114,36 @@ inline int pinned(jf_ctx *ctx, size_t bytes, void **out) {
             return jf::fail(ctx, JF_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
     } while (0)
 
+inline cudaEvent_t prof_event(jf_ctx *ctx) {
+    cudaEvent_t e;
+    if (!ctx->event_pool.empty()) {
+        e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return e;
+    }
+    cudaEventCreate(&e);
+    return e;
+}
+inline void prof_begin(jf_ctx *ctx, const char *name) {
+    if (!ctx->prof_on) return;
+    jf_ctx::ProfRec r{name, prof_event(ctx), prof_event(ctx)};
+    cudaEventRecord(r.a, ctx->stream);
+    ctx->prof.push_back(r);
+}
+inline void prof_end(jf_ctx *ctx) {
+    if (!ctx->prof_on) return;
+    cudaEventRecord(ctx->prof.back().b, ctx->stream);
+}
+
+// launch a kernel: optional event bracket, launch counter, launch-error check
+#define JF_LAUNCH(ctx, name, ...)   \
+    do {                            \
+        jf::prof_begin(ctx, name);  \
+        __VA_ARGS__;                \
+        jf::prof_end(ctx);          \
+        JF_LAUNCH_CHECK(ctx);       \
+    } while (0)
+
 // entry points implemented per translation unit
 // d_out == d_data: in place.  Otherwise the result lands in d_out and d_data is clobbered.
 int ntt_run(jf_ctx *ctx, int field, void *d_data, void *d_out, size_t in_len, unsigned log_n, int inverse,
@@ -119,7 +154,8 @@ int msm_run(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_sc
 int msm_finish_host(jf_ctx *ctx, int curve, const uint64_t *xyzz_parts, size_t parts, uint64_t *out_xy, int *out_inf);
 int srs_build(jf_ctx *ctx, int curve, const void *d_base_points /* n affine, device */, size_t n, int window_bits,
               int precompute, jf_srs **out);
-int srs_generate(jf_ctx *ctx, int curve, const uint64_t *beta, size_t n, void *d_out_points);
+int srs_generate(jf_ctx *ctx, int curve, const uint64_t *beta, size_t first_power, size_t n, void *d_out_points);
+int microbench(jf_ctx *ctx, int kind, double *out_rate);
 int fixed_base_mul(jf_ctx *ctx, int curve, const void *d_scalars, size_t n, void *d_out_points);
 int field_op(jf_ctx *ctx, int field, int op, const void *d_a, const void *d_b, void *d_out, size_t n);
 

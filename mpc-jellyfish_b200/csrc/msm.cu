@@ -339,8 +339,7 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     if (base_offset > srs->n) return fail(ctx, JF_ERR_INVALID_ARG, "msm: base_offset beyond the commit key");
     size_t n = n_in < srs->n - base_offset ? n_in : srs->n - base_offset;  // arkworks: min(len(bases), len(scalars))
     if (n == 0) {
-        set_inf_kernel<Fq><<<1, 32, 0, st>>>((P *)d_out);
-        JF_LAUNCH_CHECK(ctx);
+        JF_LAUNCH(ctx, "set_inf", set_inf_kernel<Fq><<<1, 32, 0, st>>>((P *)d_out));
         return JF_OK;
     }
     MsmGeom g;
@@ -388,26 +387,18 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     const uint32_t *sc = (const uint32_t *)d_scalars;
     JF_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (total + 1), st));
     const unsigned nblk = (unsigned)((n + 255) / 256);
-    msm_count_kernel<Fr><<<nblk, 256, 0, st>>>(sc, g, counts, err);
-    JF_LAUNCH_CHECK(ctx);
-    scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, total, off, toff, block_sums);
-    JF_LAUNCH_CHECK(ctx);
-    scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, scan_blocks, off, toff, total);
-    JF_LAUNCH_CHECK(ctx);
-    scan_add_kernel<<<(total + 255) / 256, 256, 0, st>>>(block_sums, total, off, toff, cursor);
-    JF_LAUNCH_CHECK(ctx);
-    msm_scatter_kernel<Fr><<<nblk, 256, 0, st>>>(sc, g, cursor, sorted);
-    JF_LAUNCH_CHECK(ctx);
-    build_tasks_kernel<<<(total + 255) / 256, 256, 0, st>>>(off, toff, total, tasks);
-    JF_LAUNCH_CHECK(ctx);
+    JF_LAUNCH(ctx, "msm_count", msm_count_kernel<Fr><<<nblk, 256, 0, st>>>(sc, g, counts, err));
+    JF_LAUNCH(ctx, "scan_local", scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, total, off, toff, block_sums));
+    JF_LAUNCH(ctx, "scan_sums", scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, scan_blocks, off, toff, total));
+    JF_LAUNCH(ctx, "scan_add", scan_add_kernel<<<(total + 255) / 256, 256, 0, st>>>(block_sums, total, off, toff, cursor));
+    JF_LAUNCH(ctx, "msm_scatter", msm_scatter_kernel<Fr><<<nblk, 256, 0, st>>>(sc, g, cursor, sorted));
+    JF_LAUNCH(ctx, "build_tasks", build_tasks_kernel<<<(total + 255) / 256, 256, 0, st>>>(off, toff, total, tasks));
     {
         const unsigned blocks = (unsigned)std::min<size_t>((max_tasks + 127) / 128, (size_t)ctx->sm_count * 32);
-        msm_accumulate_kernel<Fq><<<blocks, 128, 0, st>>>((const Affine<Fq> *)srs->d_points, g.srs_n, sorted, tasks, toff,
-                                                          total, partials);
-        JF_LAUNCH_CHECK(ctx);
+        JF_LAUNCH(ctx, "msm_accumulate", msm_accumulate_kernel<Fq><<<blocks, 128, 0, st>>>((const Affine<Fq> *)srs->d_points, g.srs_n, sorted, tasks, toff,
+                                                          total, partials));
     }
-    bucket_sum_kernel<Fq><<<(total + 127) / 128, 128, 0, st>>>(partials, toff, total, XA);
-    JF_LAUNCH_CHECK(ctx);
+    JF_LAUNCH(ctx, "bucket_sum", bucket_sum_kernel<Fq><<<(total + 127) / 128, 128, 0, st>>>(partials, toff, total, XA));
     // halving levels: big ones as grid launches, the tail inside one CTA per set
     uint32_t nlev = g.NB;
     P *x = XA, *pp = PA, *xo = XB, *po = PB;
@@ -415,18 +406,15 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     // level arrays are densely packed per set (stride = the level's n)
     while (nlev > 512) {
         dim3 grid((nlev / 2 + 127) / 128, g.S);
-        halve_kernel<Fq><<<grid, 128, 0, st>>>(x, pp, xo, po, nlev, has_p ? 1 : 0);
-        JF_LAUNCH_CHECK(ctx);
+        JF_LAUNCH(ctx, "halve", halve_kernel<Fq><<<grid, 128, 0, st>>>(x, pp, xo, po, nlev, has_p ? 1 : 0));
         std::swap(x, xo);
         std::swap(pp, po);
         has_p = true;
         nlev >>= 1;
     }
-    halve_tail_kernel<Fq><<<g.S, 256, 0, st>>>(x, pp, xo, po, nlev, nlev, has_p ? 1 : 0, Rs);
-    JF_LAUNCH_CHECK(ctx);
+    JF_LAUNCH(ctx, "halve_tail", halve_tail_kernel<Fq><<<g.S, 256, 0, st>>>(x, pp, xo, po, nlev, nlev, has_p ? 1 : 0, Rs));
     if (g.S > 1) {
-        fold_sets_kernel<Fq><<<1, 32, 0, st>>>(Rs, g.S, g.c * g.T, (P *)d_out);
-        JF_LAUNCH_CHECK(ctx);
+        JF_LAUNCH(ctx, "fold_sets", fold_sets_kernel<Fq><<<1, 32, 0, st>>>(Rs, g.S, g.c * g.T, (P *)d_out));
     } else {
         JF_CUDA(ctx, cudaMemcpyAsync(d_out, Rs, sizeof(P), cudaMemcpyDeviceToDevice, st));
     }
@@ -499,19 +487,18 @@ template <class C> __global__ void fixed_base_kernel(const uint32_t *scalars, ui
 }
 
 // scalars[i] = beta^i as canonical integers
-template <class Fr> __global__ void beta_powers_kernel(Fp<Fr> beta_mont, uint32_t n, uint32_t *out) {
+template <class Fr> __global__ void beta_powers_kernel(Fp<Fr> beta_mont, uint64_t first, uint32_t n, uint32_t *out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Fp<Fr> e = Fp<Fr>::from_mont(Fp<Fr>::pow_u64(beta_mont, i));
+    Fp<Fr> e = Fp<Fr>::from_mont(Fp<Fr>::pow_u64(beta_mont, first + i));
 #pragma unroll
     for (int j = 0; j < 8; j++) out[8 * (size_t)i + j] = e.v[j];
 }
 
 template <class C> static int fixed_base_t(jf_ctx *ctx, const void *d_scalars, size_t n, void *d_out) {
     if (n == 0) return JF_OK;
-    fixed_base_kernel<C><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const uint32_t *)d_scalars, (uint32_t)n,
-                                                                            (Affine<typename C::Fq> *)d_out);
-    JF_LAUNCH_CHECK(ctx);
+    JF_LAUNCH(ctx, "fixed_base", fixed_base_kernel<C><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const uint32_t *)d_scalars, (uint32_t)n,
+                                                                            (Affine<typename C::Fq> *)d_out));
     return JF_OK;
 }
 
@@ -521,7 +508,7 @@ int fixed_base_mul(jf_ctx *ctx, int curve, const void *d_scalars, size_t n, void
     return fail(ctx, JF_ERR_INVALID_ARG, "unknown curve");
 }
 
-template <class C> static int srs_generate_t(jf_ctx *ctx, const uint64_t *beta, size_t n, void *d_out) {
+template <class C> static int srs_generate_t(jf_ctx *ctx, const uint64_t *beta, size_t first, size_t n, void *d_out) {
     using Fr = typename C::Fr;
     if (n == 0) return JF_OK;
     Fp<Fr> b;
@@ -532,14 +519,13 @@ template <class C> static int srs_generate_t(jf_ctx *ctx, const uint64_t *beta, 
     b = Fp<Fr>::to_mont(b);
     void *d_sc;
     JF_TRY(scratch(ctx, "srs_scalars", 32 * n, &d_sc));
-    beta_powers_kernel<Fr><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(b, (uint32_t)n, (uint32_t *)d_sc);
-    JF_LAUNCH_CHECK(ctx);
+    JF_LAUNCH(ctx, "beta_powers", beta_powers_kernel<Fr><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(b, (uint64_t)first, (uint32_t)n, (uint32_t *)d_sc));
     return fixed_base_t<C>(ctx, d_sc, n, d_out);
 }
 
-int srs_generate(jf_ctx *ctx, int curve, const uint64_t *beta, size_t n, void *d_out_points) {
-    if (curve == JF_BN254) return srs_generate_t<Bn254G1>(ctx, beta, n, d_out_points);
-    if (curve == JF_BLS12_381) return srs_generate_t<Bls12381G1>(ctx, beta, n, d_out_points);
+int srs_generate(jf_ctx *ctx, int curve, const uint64_t *beta, size_t first_power, size_t n, void *d_out_points) {
+    if (curve == JF_BN254) return srs_generate_t<Bn254G1>(ctx, beta, first_power, n, d_out_points);
+    if (curve == JF_BLS12_381) return srs_generate_t<Bls12381G1>(ctx, beta, first_power, n, d_out_points);
     return fail(ctx, JF_ERR_INVALID_ARG, "unknown curve");
 }
 
@@ -578,9 +564,8 @@ static int srs_build_t(jf_ctx *ctx, int curve, const void *d_base, size_t n, int
         JF_CUDA(ctx, cudaMemcpyAsync(s->d_points, d_base, sizeof(Affine<Fq>) * n, cudaMemcpyDeviceToDevice, ctx->stream));
         Affine<Fq> *tab = (Affine<Fq> *)s->d_points;
         for (int t = 1; t < s->tables; t++) {
-            table_step_kernel<Fq><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(tab + (size_t)(t - 1) * n,
-                                                                                 tab + (size_t)t * n, (uint32_t)n, c);
-            JF_LAUNCH_CHECK(ctx);
+            JF_LAUNCH(ctx, "table_step", table_step_kernel<Fq><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(tab + (size_t)(t - 1) * n,
+                                                                                 tab + (size_t)t * n, (uint32_t)n, c));
         }
     }
     JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -592,6 +577,70 @@ int srs_build(jf_ctx *ctx, int curve, const void *d_base_points, size_t n, int w
     if (curve == JF_BN254) return srs_build_t<Bn254G1>(ctx, curve, d_base_points, n, window_bits, precompute, out);
     if (curve == JF_BLS12_381) return srs_build_t<Bls12381G1>(ctx, curve, d_base_points, n, window_bits, precompute, out);
     return fail(ctx, JF_ERR_INVALID_ARG, "unknown curve");
+}
+
+// ---- integer-pipe micro-benchmarks (jf_microbench) ----------------------------------------------
+__global__ void imad_wide_bench_kernel(uint32_t *out, uint32_t seed, int iters) {
+    // 8 independent 64-bit accumulators per thread, each step one IMAD.WIDE.U32 (32x32+64)
+    uint32_t a = seed + threadIdx.x, b = seed * 3u + blockIdx.x;
+    uint64_t acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = a + k;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = (uint64_t)(uint32_t)acc[k] * b + acc[k];
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= acc[k];
+    if (s == 0x123456789abcdefull) out[0] = (uint32_t)s;  // keep the loop alive
+}
+
+__global__ void mont_mul_bench_kernel(uint32_t *out, uint32_t seed, int iters) {
+    using E = Fp<Bn254Fq>;
+    E x[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        x[k] = E::one();
+        x[k].v[0] += seed + threadIdx.x + k;
+    }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) x[k] = E::mul(x[k], x[(k + 1) & 3]);
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) s ^= x[k].v[0] ^ x[k].v[7];
+    if (s == 0x12345678u) out[0] = s;
+}
+
+int microbench(jf_ctx *ctx, int kind, double *out_rate) {
+    void *d;
+    JF_TRY(scratch(ctx, "microbench", 64, &d));
+    cudaEvent_t a, b;
+    JF_CUDA(ctx, cudaEventCreate(&a));
+    JF_CUDA(ctx, cudaEventCreate(&b));
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    const int iters = kind == 0 ? 4096 : 256;
+    double ops = 0;
+    for (int rep = 0; rep < 3; rep++) {  // first two are warm-up
+        JF_CUDA(ctx, cudaEventRecord(a, ctx->stream));
+        if (kind == 0) {
+            JF_LAUNCH(ctx, "imad_wide_bench", imad_wide_bench_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t *)d, 7u + rep, iters));
+            ops = (double)blocks * threads * iters * 8;
+        } else {
+            JF_LAUNCH(ctx, "mont_mul_bench", mont_mul_bench_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t *)d, 7u + rep, iters));
+            ops = (double)blocks * threads * iters * 4;
+        }
+        JF_CUDA(ctx, cudaEventRecord(b, ctx->stream));
+        JF_CUDA(ctx, cudaEventSynchronize(b));
+    }
+    float ms = 0;
+    JF_CUDA(ctx, cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *out_rate = ops / (ms * 1e-3);
+    return JF_OK;
 }
 
 }  // namespace jf

@@ -282,8 +282,7 @@ template <class F> static int build_plan(jf_ctx *ctx, NttPlan *pl, const uint64_
     }
     auto table = [&](void **dptr, E base, E scale, uint64_t step, uint32_t count) -> int {
         JF_CUDA(ctx, cudaMalloc(dptr, sizeof(E) * (size_t)count));
-        pow_table_kernel<F><<<(count + 127) / 128, 128, 0, ctx->stream>>>((E *)*dptr, base, scale, step, count);
-        JF_LAUNCH_CHECK(ctx);
+        JF_LAUNCH(ctx, "pow_table", pow_table_kernel<F><<<(count + 127) / 128, 128, 0, ctx->stream>>>((E *)*dptr, base, scale, step, count));
         return JF_OK;
     };
     // the inverse transform's n^-1 rides in the low table of the output scaling (hi[0] = 1 is skipped)
@@ -349,8 +348,7 @@ template <class F, int K> static int launch_pass(jf_ctx *ctx, const PassArgs &a)
     const uint64_t total_cols = ((uint64_t)1 << (a.log_n - K)) * a.batch;
     const uint64_t blocks = (total_cols + B - 1) / B;
     if (blocks > 0x7fffffffull) return fail(ctx, JF_ERR_INVALID_ARG, "ntt: batch too large");
-    ntt_pass_kernel<F, K><<<(unsigned)blocks, 256, smem, ctx->stream>>>(a);
-    JF_LAUNCH_CHECK(ctx);
+    JF_LAUNCH(ctx, "ntt_pass", ntt_pass_kernel<F, K><<<(unsigned)blocks, 256, smem, ctx->stream>>>(a));
     return JF_OK;
 }
 
@@ -408,10 +406,9 @@ static int ntt_run_t(jf_ctx *ctx, int field, void *d_data, void *d_out, size_t i
     }
     E *data = reinterpret_cast<E *>(d_data);
     if (log_n < NTT_MIN_K) {
-        ntt_tiny_kernel<F><<<(unsigned)((batch + 63) / 64), 64, 0, ctx->stream>>>(
+        JF_LAUNCH(ctx, "ntt_tiny", ntt_tiny_kernel<F><<<(unsigned)((batch + 63) / 64), 64, 0, ctx->stream>>>(
             data, batch_stride, (uint32_t)batch, log_n, in_len, inverse, (const E *)pl->w_lo, (const E *)pl->off_lo,
-            has_off ? 1 : 0, (const E *)pl->n_inv);
-        JF_LAUNCH_CHECK(ctx);
+            has_off ? 1 : 0, (const E *)pl->n_inv));
         if (d_out != d_data)
             JF_CUDA(ctx, cudaMemcpy2DAsync(d_out, batch_stride * sizeof(E), d_data, batch_stride * sizeof(E), n * sizeof(E),
                                            batch, cudaMemcpyDeviceToDevice, ctx->stream));

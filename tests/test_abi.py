@@ -1,0 +1,88 @@
+"""CPU suite, part 2: the C-ABI library loads without a GPU and exports every symbol that
+include/jf_b200.h declares; the product path fails loudly (no CPU fallback) when CUDA is absent;
+the product never imports the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "jf_b200.h")
+PKG = os.path.join(ROOT, "mpc-jellyfish_b200")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(jf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mpc_jellyfish_b200 import _ffi
+    lib = _ffi.lib()
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "libjf_b200.so does not export %s" % n
+    assert sorted(_ffi.SIGNATURES) == names, "ctypes table and header disagree"
+
+
+def test_library_contains_sm100a_code():
+    so = os.path.join(PKG, "libjf_b200.so")
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import mpc_jellyfish_b200 as jf
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        jf.Context(0)
+    h = ctypes.c_void_p()
+    from mpc_jellyfish_b200 import _ffi
+    assert _ffi.lib().jf_ctx_create(0, ctypes.byref(h)) == _ffi.JF_ERR_CUDA and not h.value
+
+
+def test_product_never_touches_the_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        if "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.replace("the oracle", "").lower() or f == "__init__.py" and False, \
+                    "%s mentions the oracle" % os.path.join(dirpath, f)
+
+
+def test_error_mapping():
+    from mpc_jellyfish_b200 import errors, _ffi
+    with pytest.raises(errors.InvalidParameters):
+        errors.raise_for_status(_ffi.JF_ERR_INVALID_ARG, "x")
+    with pytest.raises(errors.DomainCreationError):
+        errors.raise_for_status(_ffi.JF_ERR_DOMAIN_TOO_LARGE, "x")
+    with pytest.raises(errors.UpstreamError):
+        errors.raise_for_status(_ffi.JF_ERR_CUDA, "x")
+    assert issubclass(errors.InvalidParameters, errors.PCSError)
+
+
+def test_host_mirror_logic_without_gpu():
+    """DensePolynomial strips high zeros; the low-order zero skip matches mod.rs:379-388."""
+    import numpy as np
+    from mpc_jellyfish_b200.pcs import DensePolynomial, _skip_leading_zeros
+    c = np.zeros((10, 4), dtype=np.uint64)
+    c[2, 0] = 5
+    c[6, 1] = 9
+    p = DensePolynomial(c)
+    assert len(p) == 7 and p.degree() == 6 and _skip_leading_zeros(p) == 2
+    z = DensePolynomial(np.zeros((4, 4), dtype=np.uint64))
+    assert len(z) == 0 and z.degree() == 0 and _skip_leading_zeros(z) == 0
+    from mpc_jellyfish_b200 import shard_range, poly_owner
+    for n, w in ((10, 3), (1 << 20, 8), (5, 8), (0, 2)):
+        rs = [shard_range(n, w, r) for r in range(w)]
+        assert rs[0][0] == 0 and rs[-1][1] == n and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+        assert max(e - s for s, e in rs) - min(e - s for s, e in rs) <= 1
+    assert [poly_owner(i, 4) for i in range(6)] == [0, 1, 2, 3, 0, 1]
