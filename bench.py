@@ -155,7 +155,9 @@ def run_cuda(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = 1 << LOG_N
     ctx = jf.Context(local)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream shared by torch (copies, NCCL, events) and the library's kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     # commit key slice of this rank: [beta^(rank*n + i)] G
