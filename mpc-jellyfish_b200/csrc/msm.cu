@@ -7,13 +7,13 @@
 //
 // Pipeline (all on one stream, no host round trip until the single result point):
 //   1. digits + histogram : signed c-bit digits of every scalar, one atomic per non-zero digit
-//   2. scan               : bucket offsets and the task list offsets (a task = at most
-//                           TASK_LEN consecutive entries of one bucket -> bounded, balanced work
-//                           even when all scalars fall into one bucket)
+//   2. scan               : bucket offsets
 //   3. scatter            : counting sort of (sign | table | point index) by bucket
-//   4. accumulate         : one thread per task, XYZZ += affine mixed additions (8M + 2S),
-//                           points gathered from the resident commit key
-//   5. bucket sums        : add the task partials of each bucket
+//   4. accumulate         : the sorted list is cut into equal chunks, one per thread, regardless of
+//                           bucket boundaries (perfect balance even when all scalars fall into one
+//                           bucket); XYZZ += affine mixed additions (8M + 2S), points gathered from
+//                           the resident commit key; one partial per (thread, bucket touched)
+//   5. bucket sums        : add the partials of each bucket (they sit in consecutive slots)
 //   6. reduce             : sum_b (b+1) * B_b by log2(#buckets) halving levels
 //                           (S_g = B_2g + B_2g+1; A_g = S_g + B_2g+1; B'_(g-1) = 2 S_g)
 //   7. window fold        : only without precomputation: Horner over the per-window sums.
@@ -26,8 +26,8 @@
 
 namespace jf {
 
-static constexpr int TASK_LEN_LOG = 7;
-static constexpr uint32_t TASK_LEN = 1u << TASK_LEN_LOG;  // max entries per accumulate task
+static constexpr uint32_t ACC_THREADS = 128;      // accumulate CTA size
+static constexpr uint32_t ACC_MIN_CHUNK = 16;     // never cut the list finer than this many entries per thread
 static constexpr uint32_t IDX_BITS = 26;                  // payload = sign(1) | table(5) | index(26)
 static constexpr uint32_t IDX_MASK = (1u << IDX_BITS) - 1;
 
@@ -113,85 +113,58 @@ __global__ void msm_scatter_kernel(const uint32_t *scalars, MsmGeom g, uint32_t 
 }
 
 // ---- 2. scan -----------------------------------------------------------------------------
-// exclusive scan of (count, ceil(count / TASK_LEN)) over `total` buckets, 3 small kernels
+// exclusive scan of the bucket counts, 3 small kernels; off[total] = number of sorted entries
 static constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 16, SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;
 
-__global__ void scan_local_kernel(const uint32_t *counts, uint32_t total, uint32_t *off, uint32_t *toff,
-                                  uint2 *block_sums) {
-    __shared__ uint2 sh[SCAN_THREADS];
+__global__ void scan_local_kernel(const uint32_t *counts, uint32_t total, uint32_t *off, uint32_t *block_sums) {
+    __shared__ uint32_t sh[SCAN_THREADS];
     const uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
     uint32_t c[SCAN_ITEMS];
-    uint2 sum = make_uint2(0, 0);
+    uint32_t sum = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         c[k] = base + k < total ? counts[base + k] : 0;
-        sum.x += c[k];
-        sum.y += (c[k] + TASK_LEN - 1) >> TASK_LEN_LOG;
+        sum += c[k];
     }
     sh[threadIdx.x] = sum;
     __syncthreads();
     for (int d = 1; d < SCAN_THREADS; d <<= 1) {  // Hillis-Steele inclusive scan
-        uint2 v = make_uint2(0, 0);
-        if ((int)threadIdx.x >= d) v = sh[threadIdx.x - d];
+        uint32_t v = (int)threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
         __syncthreads();
-        sh[threadIdx.x].x += v.x;
-        sh[threadIdx.x].y += v.y;
+        sh[threadIdx.x] += v;
         __syncthreads();
     }
-    uint2 run = make_uint2(sh[threadIdx.x].x - sum.x, sh[threadIdx.x].y - sum.y);
+    uint32_t run = sh[threadIdx.x] - sum;
     if (threadIdx.x == SCAN_THREADS - 1) block_sums[blockIdx.x] = sh[threadIdx.x];
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-        if (base + k < total) {
-            off[base + k] = run.x;
-            toff[base + k] = run.y;
-        }
-        run.x += c[k];
-        run.y += (c[k] + TASK_LEN - 1) >> TASK_LEN_LOG;
+        if (base + k < total) off[base + k] = run;
+        run += c[k];
     }
 }
 
-__global__ void scan_sums_kernel(uint2 *block_sums, uint32_t nblocks, uint32_t *off, uint32_t *toff, uint32_t total) {
+__global__ void scan_sums_kernel(uint32_t *block_sums, uint32_t nblocks, uint32_t *off, uint32_t total) {
     // single thread block; nblocks <= 1024
-    __shared__ uint2 sh[1024];
-    uint2 mine = threadIdx.x < nblocks ? block_sums[threadIdx.x] : make_uint2(0, 0);
+    __shared__ uint32_t sh[1024];
+    uint32_t mine = threadIdx.x < nblocks ? block_sums[threadIdx.x] : 0;
     sh[threadIdx.x] = mine;
     __syncthreads();
     for (int d = 1; d < 1024; d <<= 1) {
-        uint2 v = make_uint2(0, 0);
-        if ((int)threadIdx.x >= d) v = sh[threadIdx.x - d];
+        uint32_t v = (int)threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
         __syncthreads();
-        sh[threadIdx.x].x += v.x;
-        sh[threadIdx.x].y += v.y;
+        sh[threadIdx.x] += v;
         __syncthreads();
     }
-    if (threadIdx.x < nblocks) block_sums[threadIdx.x] = make_uint2(sh[threadIdx.x].x - mine.x, sh[threadIdx.x].y - mine.y);
-    if (threadIdx.x == 1023) {  // grand totals live one past the end
-        off[total] = sh[1023].x;
-        toff[total] = sh[1023].y;
-    }
+    if (threadIdx.x < nblocks) block_sums[threadIdx.x] = sh[threadIdx.x] - mine;
+    if (threadIdx.x == 1023) off[total] = sh[1023];  // grand total lives one past the end
 }
 
-__global__ void scan_add_kernel(const uint2 *block_sums, uint32_t total, uint32_t *off, uint32_t *toff, uint32_t *cursor) {
+__global__ void scan_add_kernel(const uint32_t *block_sums, uint32_t total, uint32_t *off, uint32_t *cursor) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    uint2 b = block_sums[i / SCAN_CHUNK];
-    uint32_t o = off[i] + b.x;
+    uint32_t o = off[i] + block_sums[i / SCAN_CHUNK];
     off[i] = o;
     cursor[i] = o;
-    toff[i] += b.y;
-}
-
-// ---- task list ---------------------------------------------------------------------------
-// task = (start in sorted[], len-1 << 22 | bucket)
-__global__ void build_tasks_kernel(const uint32_t *off, const uint32_t *toff, uint32_t total, uint2 *tasks) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= total) return;
-    uint32_t start = off[b], cnt = off[b + 1] - start, t0 = toff[b];
-    for (uint32_t k = 0; k * TASK_LEN < cnt; k++) {
-        uint32_t len = min(TASK_LEN, cnt - k * TASK_LEN);
-        tasks[t0 + k] = make_uint2(start + k * TASK_LEN, ((len - 1) << 22) | b);
-    }
 }
 
 // ---- 4. accumulate -------------------------------------------------------------------------
@@ -228,89 +201,154 @@ template <class Fq> __device__ __forceinline__ XYZZ<Fq> load_xyzz(const XYZZ<Fq>
     return r;
 }
 
+// entries per thread for this launch: the list of off[total] entries cut evenly over all threads
+__device__ __forceinline__ uint32_t chunk_len(uint32_t entries, uint32_t nthreads) {
+    uint32_t e = (entries + nthreads - 1) / nthreads;
+    return e < ACC_MIN_CHUNK ? ACC_MIN_CHUNK : e;
+}
+
+// Thread t owns sorted[t*E, (t+1)*E).  It emits one partial per bucket it touches, into slot
+// t + bucket: slots are unique (consecutive threads touch non-decreasing buckets) and the
+// partials of one bucket are consecutive, so no task list or second scan is needed.
 template <class Fq>
-__global__ void __launch_bounds__(128)
-msm_accumulate_kernel(const Affine<Fq> *points, uint32_t srs_n, const uint32_t *sorted, const uint2 *tasks,
-                      const uint32_t *toff, uint32_t total_buckets, XYZZ<Fq> *partials) {
-    const uint32_t ntasks = toff[total_buckets];
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntasks; t += gridDim.x * blockDim.x) {
-        const uint2 task = tasks[t];
-        const uint32_t len = (task.y >> 22) + 1;
-        const uint32_t *ent = sorted + task.x;
-        XYZZ<Fq> acc = XYZZ<Fq>::inf();
-        for (uint32_t e = 0; e < len; e++) {
-            const uint32_t pl = ent[e];
-            const Affine<Fq> *src = points + (size_t)((pl >> IDX_BITS) & 31u) * srs_n + (pl & IDX_MASK);
-            Affine<Fq> p = load_affine(src);
-            if (p.is_inf()) continue;
-            if (pl & 0x80000000u) p.y = Fp<Fq>::neg(p.y);
-            acc.add_affine(p);
-        }
-        store_xyzz(partials + t, acc);
+__global__ void __launch_bounds__(ACC_THREADS)
+msm_accumulate_kernel(const Affine<Fq> *points, uint32_t srs_n, const uint32_t *sorted, const uint32_t *off,
+                      uint32_t total_buckets, XYZZ<Fq> *partials) {
+    const uint32_t nthreads = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t entries = off[total_buckets];
+    const uint32_t E = chunk_len(entries, nthreads);
+    const uint64_t start64 = (uint64_t)t * E;
+    if (start64 >= entries) return;
+    const uint32_t start = (uint32_t)start64, end = min(entries, start + E);
+    // bucket containing `start`: the largest b with off[b] <= start (skips empty buckets)
+    uint32_t lo = 0, hi = total_buckets;  // invariant: off[lo] <= start < off[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= start) lo = mid;
+        else hi = mid;
     }
+    uint32_t b = lo, next = off[b + 1];
+    XYZZ<Fq> acc = XYZZ<Fq>::inf();
+    for (uint32_t pos = start; pos < end; pos++) {
+        if (pos >= next) {
+            store_xyzz(partials + (size_t)t + b, acc);
+            acc = XYZZ<Fq>::inf();
+            do {
+                b++;
+                next = off[b + 1];
+            } while (pos >= next);
+        }
+        const uint32_t pl = sorted[pos];
+        const Affine<Fq> *src = points + (size_t)((pl >> IDX_BITS) & 31u) * srs_n + (pl & IDX_MASK);
+        Affine<Fq> p = load_affine(src);
+        if (p.is_inf()) continue;
+        if (pl & 0x80000000u) p.y = Fp<Fq>::neg(p.y);
+        acc.add_affine(p);
+    }
+    store_xyzz(partials + (size_t)t + b, acc);
 }
 
 // ---- 5. bucket sums ----------------------------------------------------------------------
+// Bucket b's partials are slots [first + b, last + b], first/last = the threads owning its first
+// and last entry.  Buckets with few partials are summed by one thread; heavy ones (skewed scalars,
+// or a short top window piling onto a handful of buckets) are queued for a whole CTA each.
+static constexpr uint32_t HEAVY_PARTS = 16;
+static constexpr int HEAVY_THREADS = 128;
+
+__device__ __forceinline__ bool bucket_slots(const uint32_t *off, uint32_t b, uint32_t E, uint32_t &s0, uint32_t &s1) {
+    const uint32_t o0 = off[b], o1 = off[b + 1];
+    if (o0 == o1) return false;
+    s0 = o0 / E + b;
+    s1 = (o1 - 1) / E + b;
+    return true;
+}
+
 template <class Fq>
-__global__ void bucket_sum_kernel(const XYZZ<Fq> *partials, const uint32_t *toff, uint32_t total_buckets, XYZZ<Fq> *X) {
+__global__ void bucket_sum_kernel(const XYZZ<Fq> *partials, const uint32_t *off, uint32_t total_buckets, uint32_t acc_threads,
+                                  XYZZ<Fq> *X, uint32_t *heavy_count, uint32_t *heavy_list) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= total_buckets) return;
-    uint32_t t0 = toff[b], t1 = toff[b + 1];
+    const uint32_t E = chunk_len(off[total_buckets], acc_threads);
+    uint32_t s0, s1;
     XYZZ<Fq> acc = XYZZ<Fq>::inf();
-    for (uint32_t t = t0; t < t1; t++) acc.add(load_xyzz(partials + t));
+    if (bucket_slots(off, b, E, s0, s1)) {
+        if (s1 - s0 + 1 > HEAVY_PARTS) {
+            heavy_list[atomicAdd(heavy_count, 1u)] = b;
+            return;
+        }
+        for (uint32_t s = s0; s <= s1; s++) acc.add(load_xyzz(partials + s));
+    }
     store_xyzz(X + b, acc);
 }
 
-// ---- 6. weighted reduction --------------------------------------------------------------
-// One halving level over every set: X (n per set, weights 1..n), P (n per set, weight 1, absent
-// on the first level) -> Xo, Po (n/2 per set).
 template <class Fq>
-__device__ __forceinline__ void halve_one(const XYZZ<Fq> *X, const XYZZ<Fq> *P, XYZZ<Fq> *Xo, XYZZ<Fq> *Po, uint32_t n,
-                                          uint32_t g, bool has_p) {
-    XYZZ<Fq> x0 = load_xyzz(X + 2 * g), x1 = load_xyzz(X + 2 * g + 1);
-    XYZZ<Fq> s = x0;
-    s.add(x1);
-    XYZZ<Fq> a = s;
-    a.add(x1);
-    if (has_p) {
-        XYZZ<Fq> p0 = load_xyzz(P + 2 * g);
-        p0.add(load_xyzz(P + 2 * g + 1));
-        a.add(p0);
-    }
-    store_xyzz(Po + g, a);
-    if (g >= 1) store_xyzz(Xo + g - 1, s.dbl());
-    else store_xyzz(Xo + n / 2 - 1, XYZZ<Fq>::inf());
-}
-
-template <class Fq>
-__global__ void halve_kernel(const XYZZ<Fq> *X, const XYZZ<Fq> *P, XYZZ<Fq> *Xo, XYZZ<Fq> *Po, uint32_t n, int has_p) {
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n / 2) return;
-    size_t set = blockIdx.y;
-    halve_one<Fq>(X + set * n, P + set * n, Xo + set * (n / 2), Po + set * (n / 2), n, g, has_p != 0);
-}
-
-// Tail: one CTA per set finishes n <= 2 * blockDim levels with block barriers, leaves
-// R_set = X[0] + P[0] in out[set].  bufs: A = (X, P), B = (Xo, Po) both of capacity n per set.
-template <class Fq>
-__global__ void halve_tail_kernel(XYZZ<Fq> *XA, XYZZ<Fq> *PA, XYZZ<Fq> *XB, XYZZ<Fq> *PB, uint32_t n, uint32_t cap,
-                                  int has_p, XYZZ<Fq> *out) {
-    size_t set = blockIdx.x;
-    XYZZ<Fq> *x = XA + set * cap, *p = PA + set * cap, *xo = XB + set * cap, *po = PB + set * cap;
-    bool hp = has_p != 0;
-    while (n > 1) {
-        for (uint32_t g = threadIdx.x; g < n / 2; g += blockDim.x) halve_one<Fq>(x, p, xo, po, n, g, hp);
+__global__ void __launch_bounds__(HEAVY_THREADS)
+bucket_sum_heavy_kernel(const XYZZ<Fq> *partials, const uint32_t *off, uint32_t total_buckets, uint32_t acc_threads,
+                        XYZZ<Fq> *X, const uint32_t *heavy_count, const uint32_t *heavy_list) {
+    __shared__ XYZZ<Fq> sh[HEAVY_THREADS];
+    const uint32_t nheavy = *heavy_count;
+    const uint32_t E = chunk_len(off[total_buckets], acc_threads);
+    for (uint32_t i = blockIdx.x; i < nheavy; i += gridDim.x) {
+        const uint32_t b = heavy_list[i];
+        uint32_t s0, s1;
+        bucket_slots(off, b, E, s0, s1);
+        XYZZ<Fq> acc = XYZZ<Fq>::inf();
+        for (uint32_t s = s0 + threadIdx.x; s <= s1; s += HEAVY_THREADS) acc.add(load_xyzz(partials + s));
+        sh[threadIdx.x] = acc;
         __syncthreads();
-        XYZZ<Fq> *t = x; x = xo; xo = t;
-        t = p; p = po; po = t;
-        n >>= 1;
-        hp = true;
+        for (int d = HEAVY_THREADS / 2; d >= 1; d >>= 1) {
+            if ((int)threadIdx.x < d) {
+                acc.add(sh[threadIdx.x + d]);
+                sh[threadIdx.x] = acc;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) store_xyzz(X + b, acc);
+        __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        XYZZ<Fq> r = load_xyzz(x);
-        if (hp) r.add(load_xyzz(p));
-        store_xyzz(out + set, r);
+}
+
+// ---- 6. weighted reduction --------------------------------------------------------------
+// R = sum_b (b+1) X_b over n = 2^k buckets, in k levels of short dependent chains.  With
+// S_g = X_2g + X_2g+1:   R = sum_g (S_g + X_2g+1) + R(X'),  X'_(g-1) = 2 S_g  (g >= 1).
+// The weight-one terms S_g and X_2g+1 are not added here: they are pushed onto a pool that the
+// same launch halves by pairwise sums.  Critical path per level = one addition + one doubling.
+// Levels are grid launches of one-warp CTAs so that the few live warps spread over all SMs (a
+// lone warp already keeps its sub-core's integer pipe busy; several on one SM would queue).
+template <class Fq>
+__global__ void __launch_bounds__(128)
+reduce_level_kernel(const XYZZ<Fq> *X, XYZZ<Fq> *Xo, const XYZZ<Fq> *Pin, XYZZ<Fq> *Pout, uint32_t n, uint32_t m,
+                    uint32_t cap_x, uint32_t cap_p) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t set = blockIdx.y;
+    X += set * cap_x;
+    Xo += set * cap_x;
+    Pin += set * cap_p;
+    Pout += set * cap_p;
+    const uint32_t mh = (m + 1) / 2, xs = n >= 2 ? n / 2 : n;  // n == 1: the last bucket joins the pool
+    if (idx < xs) {
+        if (n == 1) {
+            store_xyzz(Pout + mh, load_xyzz(X));
+            return;
+        }
+        const uint32_t g = idx;
+        XYZZ<Fq> x1 = load_xyzz(X + 2 * g + 1), s = load_xyzz(X + 2 * g);
+        s.add(x1);
+        store_xyzz(Pout + mh + 2 * g, s);
+        store_xyzz(Pout + mh + 2 * g + 1, x1);
+        if (g >= 1) store_xyzz(Xo + g - 1, s.dbl());
+        else store_xyzz(Xo + n / 2 - 1, XYZZ<Fq>::inf());
+    } else if (idx - xs < mh) {
+        const uint32_t h = idx - xs;
+        XYZZ<Fq> a = load_xyzz(Pin + 2 * h);
+        if (2 * h + 1 < m) a.add(load_xyzz(Pin + 2 * h + 1));
+        store_xyzz(Pout + h, a);
     }
+}
+
+template <class Fq> __global__ void gather_sets_kernel(const XYZZ<Fq> *P, uint32_t cap_p, int S, XYZZ<Fq> *out) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) store_xyzz(out + s, load_xyzz(P + (size_t)s * cap_p));
 }
 
 // ---- 7. fold the per-set sums: result = sum_s 2^(shift s) R_s --------------------------
@@ -354,65 +392,72 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     g.mont = mont;
     const uint32_t total = (uint32_t)g.S * g.NB;
     const size_t max_entries = n * (size_t)g.W;
-    const size_t max_tasks = max_entries / TASK_LEN + total + 1;
     if (max_entries >= (1ull << 32)) return fail(ctx, JF_ERR_INVALID_ARG, "msm: n * windows must stay below 2^32");
+    // accumulate launch: one wave of resident CTAs, fewer when the list is short
+    uint32_t acc_blocks = (uint32_t)ctx->sm_count * 4;
+    {
+        const size_t want = (max_entries + (size_t)ACC_THREADS * ACC_MIN_CHUNK - 1) / ((size_t)ACC_THREADS * ACC_MIN_CHUNK);
+        if (want < acc_blocks) acc_blocks = (uint32_t)(want ? want : 1);
+    }
+    const uint32_t acc_threads = acc_blocks * ACC_THREADS;
+    const size_t max_partials = (size_t)acc_threads + total + 1;
 
-    uint32_t *counts, *off, *toff, *cursor, *sorted;
-    uint2 *block_sums, *tasks;
+    uint32_t *counts, *off, *cursor, *sorted, *block_sums;
     P *partials, *XA, *PA, *XB, *PB, *Rs;
     int *err;
     void *p;
     const uint32_t scan_blocks = (total + SCAN_CHUNK - 1) / SCAN_CHUNK;
     if (scan_blocks > 1024) return fail(ctx, JF_ERR_INVALID_ARG, "msm: too many buckets");
-    JF_TRY(scratch(ctx, "msm_counts", sizeof(uint32_t) * (total + 1) * 4 + sizeof(uint2) * 1024 + 64, &p));
+    JF_TRY(scratch(ctx, "msm_counts", sizeof(uint32_t) * ((size_t)(total + 1) * 3 + 1024) + 64, &p));
     counts = (uint32_t *)p;
     off = counts + (total + 1);
-    toff = off + (total + 1);
-    cursor = toff + (total + 1);
-    block_sums = (uint2 *)(cursor + (total + 1));  // 4 * (total + 1) words: 16-byte aligned
+    cursor = off + (total + 1);
+    block_sums = cursor + (total + 1);
     JF_TRY(scratch(ctx, "msm_sorted", sizeof(uint32_t) * max_entries, &p));
     sorted = (uint32_t *)p;
-    JF_TRY(scratch(ctx, "msm_tasks", sizeof(uint2) * max_tasks, &p));
-    tasks = (uint2 *)p;
-    JF_TRY(scratch(ctx, "msm_partials", sizeof(P) * max_tasks, &p));
+    JF_TRY(scratch(ctx, "msm_partials", sizeof(P) * max_partials, &p));
     partials = (P *)p;
-    JF_TRY(scratch(ctx, "msm_reduce", sizeof(P) * ((size_t)total * 4 + g.S + 8), &p));
-    XA = (P *)p;  // four level buffers of `total` points each (X / P ping-pong), then the per-set sums
+    const uint32_t cap_p = g.NB + 64;
+    JF_TRY(scratch(ctx, "msm_reduce", sizeof(P) * ((size_t)total * 2 + (size_t)g.S * cap_p * 2 + g.S + 8), &p));
+    XA = (P *)p;  // X ping-pong (stride NB per set), pool ping-pong (stride cap_p per set), per-set sums
     XB = XA + total;
     PA = XB + total;
-    PB = PA + total;
-    Rs = PB + total;
+    PB = PA + (size_t)g.S * cap_p;
+    Rs = PB + (size_t)g.S * cap_p;
     err = ctx->d_err;
+    uint32_t *heavy;
+    JF_TRY(scratch(ctx, "msm_heavy", sizeof(uint32_t) * ((size_t)total + 4), &p));
+    heavy = (uint32_t *)p;  // [0] = count, [1..] = bucket ids
 
     const uint32_t *sc = (const uint32_t *)d_scalars;
     JF_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (total + 1), st));
     const unsigned nblk = (unsigned)((n + 255) / 256);
     JF_LAUNCH(ctx, "msm_count", msm_count_kernel<Fr><<<nblk, 256, 0, st>>>(sc, g, counts, err));
-    JF_LAUNCH(ctx, "scan_local", scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, total, off, toff, block_sums));
-    JF_LAUNCH(ctx, "scan_sums", scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, scan_blocks, off, toff, total));
-    JF_LAUNCH(ctx, "scan_add", scan_add_kernel<<<(total + 255) / 256, 256, 0, st>>>(block_sums, total, off, toff, cursor));
+    JF_LAUNCH(ctx, "scan_local", scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, total, off, block_sums));
+    JF_LAUNCH(ctx, "scan_sums", scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, scan_blocks, off, total));
+    JF_LAUNCH(ctx, "scan_add", scan_add_kernel<<<(total + 255) / 256, 256, 0, st>>>(block_sums, total, off, cursor));
     JF_LAUNCH(ctx, "msm_scatter", msm_scatter_kernel<Fr><<<nblk, 256, 0, st>>>(sc, g, cursor, sorted));
-    JF_LAUNCH(ctx, "build_tasks", build_tasks_kernel<<<(total + 255) / 256, 256, 0, st>>>(off, toff, total, tasks));
+    JF_LAUNCH(ctx, "msm_accumulate", msm_accumulate_kernel<Fq><<<acc_blocks, ACC_THREADS, 0, st>>>(
+        (const Affine<Fq> *)srs->d_points, g.srs_n, sorted, off, total, partials));
+    JF_CUDA(ctx, cudaMemsetAsync(heavy, 0, sizeof(uint32_t), st));
+    JF_LAUNCH(ctx, "bucket_sum", bucket_sum_kernel<Fq><<<(total + 127) / 128, 128, 0, st>>>(partials, off, total, acc_threads, XA, heavy, heavy + 1));
+    JF_LAUNCH(ctx, "bucket_sum_heavy", bucket_sum_heavy_kernel<Fq><<<64, HEAVY_THREADS, 0, st>>>(partials, off, total, acc_threads, XA, heavy, heavy + 1));
     {
-        const unsigned blocks = (unsigned)std::min<size_t>((max_tasks + 127) / 128, (size_t)ctx->sm_count * 32);
-        JF_LAUNCH(ctx, "msm_accumulate", msm_accumulate_kernel<Fq><<<blocks, 128, 0, st>>>((const Affine<Fq> *)srs->d_points, g.srs_n, sorted, tasks, toff,
-                                                          total, partials));
+        uint32_t nlev = g.NB, m = 0;
+        P *x = XA, *xo = XB, *pin = PA, *pout = PB;
+        while (nlev > 0 || m > 1) {
+            const uint32_t xs = nlev >= 2 ? nlev / 2 : nlev, mh = (m + 1) / 2;
+            const uint32_t threads = xs + mh;
+            const int bs = threads > 32u * 1024u ? 128 : 32;
+            dim3 grid((threads + bs - 1) / bs, g.S);
+            JF_LAUNCH(ctx, "reduce_level", reduce_level_kernel<Fq><<<grid, bs, 0, st>>>(x, xo, pin, pout, nlev, m, g.NB, cap_p));
+            m = mh + (nlev >= 2 ? nlev : nlev);  // pairs push 2 entries each (= nlev), a lone bucket pushes 1
+            nlev = nlev >= 2 ? nlev / 2 : 0;
+            std::swap(x, xo);
+            std::swap(pin, pout);
+        }
+        JF_LAUNCH(ctx, "gather_sets", gather_sets_kernel<Fq><<<(g.S + 31) / 32, 32, 0, st>>>(pin, cap_p, g.S, Rs));
     }
-    JF_LAUNCH(ctx, "bucket_sum", bucket_sum_kernel<Fq><<<(total + 127) / 128, 128, 0, st>>>(partials, toff, total, XA));
-    // halving levels: big ones as grid launches, the tail inside one CTA per set
-    uint32_t nlev = g.NB;
-    P *x = XA, *pp = PA, *xo = XB, *po = PB;
-    bool has_p = false;
-    // level arrays are densely packed per set (stride = the level's n)
-    while (nlev > 512) {
-        dim3 grid((nlev / 2 + 127) / 128, g.S);
-        JF_LAUNCH(ctx, "halve", halve_kernel<Fq><<<grid, 128, 0, st>>>(x, pp, xo, po, nlev, has_p ? 1 : 0));
-        std::swap(x, xo);
-        std::swap(pp, po);
-        has_p = true;
-        nlev >>= 1;
-    }
-    JF_LAUNCH(ctx, "halve_tail", halve_tail_kernel<Fq><<<g.S, 256, 0, st>>>(x, pp, xo, po, nlev, nlev, has_p ? 1 : 0, Rs));
     if (g.S > 1) {
         JF_LAUNCH(ctx, "fold_sets", fold_sets_kernel<Fq><<<1, 32, 0, st>>>(Rs, g.S, g.c * g.T, (P *)d_out));
     } else {
