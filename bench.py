@@ -138,6 +138,116 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+
+# ------------------------------------------------------------------------------------------------
+NTT_FIELD, NTT_LOG_N, NTT_BATCH = "bn254_fr", 22, 16
+
+
+def ntt_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream):
+    """Second metric of BASELINE.json: "NTT 2^22 Melem/s".  One step = one batched forward COSET NTT
+    (`coset.fft`, prover.rs:552-567) of 16 polynomials of 2^22 BN254-Fr coefficients per GPU, in place,
+    natural order in and out.  N > 1: the batch is sharded by polynomial (16 per rank, no collective)."""
+    n, batch = 1 << NTT_LOG_N, NTT_BATCH
+    distinct = 4
+    host = co.random_field_elems(NTT_FIELD, n * distinct, SEED + 77 + rank, True).reshape(distinct, n, 4)
+    pinned = torch.empty((batch, n, 4), dtype=torch.int64).pin_memory()
+    for b in range(batch):
+        pinned[b].copy_(torch.from_numpy(host[b % distinct].view(np.int64)))
+    d = torch.empty((batch, n, 4), dtype=torch.int64, device="cuda")
+    d.copy_(pinned)
+    off = co.field_op(NTT_FIELD, "to_mont", np.array([[5, 0, 0, 0]], dtype=np.uint64))[0]  # Fr::GENERATOR
+    # correctness guard on this very configuration: spot-check out[i] = p(g w^i) by Horner (oracle) for poly 0
+    ctx.ntt_device(NTT_FIELD, d.data_ptr(), NTT_LOG_N, False, off, batch=batch)
+    torch.cuda.synchronize()
+    if rank == 0:
+        import pyref
+        F = pyref.BN254_FR
+        got = d[0].cpu().numpy().view(np.uint64)
+        w = pow(F.two_adic_root, 1 << (F.two_adicity - NTT_LOG_N), F.p)
+        for i in (0, 1, n // 3, n - 1):
+            xpt = (5 * pow(w, i, F.p)) % F.p
+            want = co.poly_eval(NTT_FIELD, host[0], co.ints_to_limbs([F.to_mont(xpt)], 4)[0])
+            if not np.array_equal(got[i], want):
+                raise SystemExit("bench.py: coset NTT output does not match Horner evaluation; refusing to time it")
+    steps = args.steps
+    for i in range(args.warmup):
+        ctx.ntt_device(NTT_FIELD, d.data_ptr(), NTT_LOG_N, False, off, batch=batch)
+    barrier()
+    l0 = ctx.launch_count
+    ctx.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        ctx.ntt_device(NTT_FIELD, d.data_ptr(), NTT_LOG_N, False, off, batch=batch)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+    prof = ctx.profile_collect()
+    ctx.profile(False)
+    launches = ctx.launch_count - l0
+    # end to end through jf_ntt: pinned host coefficients in, evaluations back in the same host buffer
+    e_steps = max(1, min(steps, 4))
+    arr = pinned.numpy().view(np.uint64)
+    ctx.ntt(NTT_FIELD, arr, NTT_LOG_N, False, off)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e_steps):
+        ctx.ntt(NTT_FIELD, arr, NTT_LOG_N, False, off)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e_steps)
+    if rank != 0:
+        return None
+    cnt, tot = prof.get("ntt_pass", (0, 0.0))
+    passes = cnt // max(steps, 1)
+    pass_ms = tot / max(cnt, 1)
+    mul_rate = ctx.microbench(1)
+    elems = n * batch
+    muls = elems * (NTT_LOG_N / 2.0 + 1.0)          # (n/2) log2 n butterflies + n coset scalings (SURVEY 8d)
+    peaks = _peaks()
+    cpu = None
+    if not args.no_cpu:
+        x = host[0].copy()
+        co.ntt(NTT_FIELD, x, NTT_LOG_N, False, off)   # warm the oracle's twiddle setup
+        t0 = time.perf_counter()
+        co.ntt(NTT_FIELD, x, NTT_LOG_N, False, off)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n / dt / 1e6, "unit": "Melem/s", "cores": co.max_threads(), "kind": "port",
+               "sample": "1 coset NTT of 2^%d BN254 Fr elements, OpenMP radix-2 restatement of ark-poly" % NTT_LOG_N}
+    return {
+        "metric": "NTT 2^22 Melem/s (BN254 Fr, forward coset, batch 16 per GPU, in place, natural order)",
+        "value": elems * world / (ms * 1e-3) / 1e6, "unit": "Melem/s", "ms_per_step": ms, "higher_is_better": True,
+        "passes_per_transform": passes, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "ntt_pass", "achieved": 64.0 * elems / (pass_ms * 1e-3) / 1e9,
+                     "peak": peaks[0], "unit": "GB/s", "frac": 64.0 * elems / (pass_ms * 1e-3) / 1e9 / peaks[0],
+                     "traffic": _traffic("ntt_pass"), "peak_source": peaks[1],
+                     "note": "per launch = one Stockham pass over the batch (read 32 B + write 32 B per element); a "
+                             "transform is %d passes, so the whole-transform figure is 1/%d of this" % (passes, max(passes, 1))},
+        "roofline_int": {"bound": "imad", "achieved": muls / (ms * 1e-3), "peak": mul_rate, "unit": "Montgomery mul/s",
+                         "frac": muls / (ms * 1e-3) / mul_rate,
+                         "peak_source": "jf_microbench(1): dependent 256-bit Montgomery products in registers, this run",
+                         "note": "algorithmic multiplications only ((n/2) log n + n); inter-pass twiddles are overhead"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": elems * world / (e2e_ms * 1e-3) / 1e6, "unit": "Melem/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": 32 * elems, "d2h_bytes_per_step": 32 * elems},
+    }
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic(kernel):
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 def run_cuda(args):
     import torch
@@ -249,6 +359,7 @@ def run_cuda(args):
         step_e2e(args.warmup + i)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    ntt = None if args.no_ntt else ntt_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream)
     stop.set()
     sampler.join(timeout=2)
     clocks = _clock_summary(rows)
@@ -259,14 +370,7 @@ def run_cuda(args):
         return
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    hbm_peak, peak_src = _peaks()
     dom = max(prof.items(), key=lambda kv: kv[1][1])
     dom_name, (dom_cnt, dom_ms) = dom
     dom_avg_ms = dom_ms / max(dom_cnt, 1)
@@ -280,12 +384,7 @@ def run_cuda(args):
     adds = float(n) * W                      # mixed additions in the accumulate kernel (upper bound: zero digits skip)
     limb_products = adds * 10 * 136          # 8M+2S per mixed add, 2N^2+N 32x32 products per 256-bit Montgomery product
     int_achieved = limb_products / (dom_avg_ms * 1e-3)
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(dom_name)
-    except Exception:
-        pass
+    traffic = _traffic(dom_name)
 
     # ---- CPU baseline leg (oracle restatement on this box's cores; bounded sample) ------------------
     cpu = None
@@ -327,6 +426,7 @@ def run_cuda(args):
         "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 128 * world},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "ntt": ntt,
     }
     print(json.dumps(line))
     if world > 1:
@@ -343,7 +443,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-ntt", action="store_true", help="skip the NTT 2^22 leg (second metric)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
