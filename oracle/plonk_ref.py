@@ -1,0 +1,924 @@
+"""CPU restatement of the TurboPlonk prover / verifier of mpc-jellyfish (TEST INFRASTRUCTURE ONLY).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s checker legs may import this file;
+the product (``mpc-jellyfish_b200``) never does.  PARITY UNPINNED by the reference for proofs
+(no golden proof exists and the Rust crates cannot be built here); what IS pinned:
+
+* Keccak-256 against the reference's own known-answer test
+  (``plonk/src/transcript/solidity.rs:80-96``, ``test_solidity_keccak``);
+* Merlin/STROBE-128 against the merlin crate's published ``equivalence_simple`` vector;
+* ChaCha20 against RFC 7539 / the all-zero-key keystream;
+* the proof itself through a restatement of the reference verifier (``verifier.rs``) whose final
+  pairing check e(A,[beta]_2) = e(B,[1]_2) collapses to the G1 identity beta*A == B because the
+  test SRS has a known beta (``primitives/src/pcs/univariate_kzg/srs.rs:118-153``).
+
+What follows which reference code (TurboPlonk, one instance, 5 wire types, no Plookup):
+  PlonkCircuit            relation/src/constraint_system.rs:193-225,464-501,630-666,743-778,913-1003,1150-1259
+                          relation/src/proof_linking/linkable_circuit.rs:136-230,294-314 (no link groups)
+                          relation/src/gates/arithmetic.rs, relation/src/traits.rs:140-262,640-667
+  coset representatives   relation/src/constants.rs:30-79 (ChaCha20 rng, zero seed, ark-ff Fp::rand)
+  preprocess              plonk/src/proof_system/snark.rs:529-611
+  prove                   plonk/src/proof_system/snark.rs:201-469 + prover.rs (all rounds)
+  transcripts             plonk/src/transcript/{mod,solidity,standard}.rs
+  verify                  plonk/src/proof_system/verifier.rs:57-254,317-805
+All field values in this file are canonical Python ints.
+"""
+from __future__ import annotations
+
+import struct
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+import pyref
+from pyref import BN254, Curve, Field, Radix2Domain
+
+GATE_WIDTH = 4
+NUM_WIRE_TYPES = 5
+N_SELECTORS = 13  # q_lc[4], q_mul[2], q_hash[4], q_o, q_c, q_ecc
+
+# ======================================================================================
+# Keccak-f[1600], Keccak-256 (sha3 crate `Keccak256`: original padding 0x01 .. 0x80)
+# ======================================================================================
+_RC = [0x0000000000000001, 0x0000000000008082, 0x800000000000808A, 0x8000000080008000, 0x000000000000808B,
+       0x0000000080000001, 0x8000000080008081, 0x8000000000008009, 0x000000000000008A, 0x0000000000000088,
+       0x0000000080008009, 0x000000008000000A, 0x000000008000808B, 0x800000000000008B, 0x8000000000008089,
+       0x8000000000008003, 0x8000000000008002, 0x8000000000000080, 0x000000000000800A, 0x800000008000000A,
+       0x8000000080008081, 0x8000000000008080, 0x0000000080000001, 0x8000000080008008]
+_ROT = [[0, 36, 3, 41, 18], [1, 44, 10, 45, 2], [62, 6, 43, 15, 61], [28, 55, 25, 21, 56], [27, 20, 39, 8, 14]]
+_M64 = (1 << 64) - 1
+
+
+def _rol(x, n):
+    n %= 64
+    return ((x << n) | (x >> (64 - n))) & _M64 if n else x
+
+
+def keccak_f1600(state: bytearray) -> None:
+    """In-place permutation of a 200-byte state (lanes little-endian, A[x][y] at 8*(x+5y))."""
+    A = [[int.from_bytes(state[8 * (x + 5 * y):8 * (x + 5 * y) + 8], "little") for y in range(5)] for x in range(5)]
+    for rnd in range(24):
+        C = [A[x][0] ^ A[x][1] ^ A[x][2] ^ A[x][3] ^ A[x][4] for x in range(5)]
+        D = [C[(x - 1) % 5] ^ _rol(C[(x + 1) % 5], 1) for x in range(5)]
+        A = [[A[x][y] ^ D[x] for y in range(5)] for x in range(5)]
+        B = [[0] * 5 for _ in range(5)]
+        for x in range(5):
+            for y in range(5):
+                B[y][(2 * x + 3 * y) % 5] = _rol(A[x][y], _ROT[x][y])
+        A = [[B[x][y] ^ ((~B[(x + 1) % 5][y]) & B[(x + 2) % 5][y]) for y in range(5)] for x in range(5)]
+        A[0][0] ^= _RC[rnd]
+    for x in range(5):
+        for y in range(5):
+            state[8 * (x + 5 * y):8 * (x + 5 * y) + 8] = A[x][y].to_bytes(8, "little")
+
+
+def keccak256(data: bytes) -> bytes:
+    rate = 136
+    st = bytearray(200)
+    msg = bytearray(data)
+    msg.append(0x01)
+    while len(msg) % rate:
+        msg.append(0)
+    msg[-1] |= 0x80
+    for off in range(0, len(msg), rate):
+        for i in range(rate):
+            st[i] ^= msg[off + i]
+        keccak_f1600(st)
+    return bytes(st[:32])
+
+
+# ======================================================================================
+# STROBE-128 / Merlin (merlin crate 3.x `Transcript`), as used by StandardTranscript
+# ======================================================================================
+class _Strobe128:
+    R = 166
+    I, A, C, T, M, K = 1, 2, 4, 8, 16, 32
+
+    def __init__(self, protocol_label: bytes):
+        st = bytearray(200)
+        st[0:6] = bytes([1, self.R + 2, 1, 0, 1, 96])
+        st[6:18] = b"STROBEv1.0.2"
+        keccak_f1600(st)
+        self.state, self.pos, self.pos_begin, self.cur_flags = st, 0, 0, 0
+        self.meta_ad(protocol_label, False)
+
+    def _run_f(self):
+        self.state[self.pos] ^= self.pos_begin
+        self.state[self.pos + 1] ^= 0x04
+        self.state[self.R + 1] ^= 0x80
+        keccak_f1600(self.state)
+        self.pos, self.pos_begin = 0, 0
+
+    def _absorb(self, data: bytes):
+        for b in data:
+            self.state[self.pos] ^= b
+            self.pos += 1
+            if self.pos == self.R:
+                self._run_f()
+
+    def _squeeze(self, n: int) -> bytes:
+        out = bytearray()
+        for _ in range(n):
+            out.append(self.state[self.pos])
+            self.state[self.pos] = 0
+            self.pos += 1
+            if self.pos == self.R:
+                self._run_f()
+        return bytes(out)
+
+    def _begin_op(self, flags: int, more: bool):
+        if more:
+            assert self.cur_flags == flags
+            return
+        assert flags & self.T == 0
+        old_begin = self.pos_begin
+        self.pos_begin = self.pos + 1
+        self.cur_flags = flags
+        self._absorb(bytes([old_begin, flags]))
+        if flags & (self.C | self.K) and self.pos != 0:
+            self._run_f()
+
+    def meta_ad(self, data: bytes, more: bool):
+        self._begin_op(self.M | self.A, more)
+        self._absorb(data)
+
+    def ad(self, data: bytes, more: bool):
+        self._begin_op(self.A, more)
+        self._absorb(data)
+
+    def prf(self, n: int, more: bool) -> bytes:
+        self._begin_op(self.I | self.A | self.C, more)
+        return self._squeeze(n)
+
+
+class MerlinTranscript:
+    def __init__(self, label: bytes):
+        self.strobe = _Strobe128(b"Merlin v1.0")
+        self.append_message(b"dom-sep", label)
+
+    def append_message(self, label: bytes, message: bytes):
+        self.strobe.meta_ad(label, False)
+        self.strobe.meta_ad(struct.pack("<I", len(message)), True)
+        self.strobe.ad(message, False)
+
+    def challenge_bytes(self, label: bytes, n: int) -> bytes:
+        self.strobe.meta_ad(label, False)
+        self.strobe.meta_ad(struct.pack("<I", n), True)
+        return self.strobe.prf(n, False)
+
+
+# ======================================================================================
+# ChaCha20 rng (rand_chacha 0.3 `ChaChaRng` = ChaCha20Rng) + ark-ff 0.4 `Fp::rand`
+# ======================================================================================
+def chacha20_block(key_words: Sequence[int], counter: int, stream: int = 0) -> List[int]:
+    """16 output words; state = consts | key | 64-bit counter | 64-bit stream id."""
+    M = 0xFFFFFFFF
+    st = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574] + list(key_words) + \
+         [counter & M, (counter >> 32) & M, stream & M, (stream >> 32) & M]
+    x = list(st)
+
+    def qr(a, b, c, d):
+        x[a] = (x[a] + x[b]) & M; x[d] ^= x[a]; x[d] = ((x[d] << 16) | (x[d] >> 16)) & M
+        x[c] = (x[c] + x[d]) & M; x[b] ^= x[c]; x[b] = ((x[b] << 12) | (x[b] >> 20)) & M
+        x[a] = (x[a] + x[b]) & M; x[d] ^= x[a]; x[d] = ((x[d] << 8) | (x[d] >> 24)) & M
+        x[c] = (x[c] + x[d]) & M; x[b] ^= x[c]; x[b] = ((x[b] << 7) | (x[b] >> 25)) & M
+
+    for _ in range(10):
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+    return [(a + b) & M for a, b in zip(x, st)]
+
+
+class ChaCha20Rng:
+    """`ChaChaRng::from_seed(seed)`: key = seed, counter and stream start at 0; `next_u64` takes
+    two consecutive keystream words (low word first)."""
+
+    def __init__(self, seed: bytes = bytes(32)):
+        self.key = list(struct.unpack("<8I", seed))
+        self.counter = 0
+        self.buf: List[int] = []
+
+    def next_u32(self) -> int:
+        if not self.buf:
+            self.buf = chacha20_block(self.key, self.counter)
+            self.counter += 1
+        return self.buf.pop(0)
+
+    def next_u64(self) -> int:
+        lo = self.next_u32()
+        hi = self.next_u32()
+        return lo | (hi << 32)
+
+
+def fp_rand(field: Field, rng) -> int:
+    """ark-ff 0.4 `impl Distribution<Fp> for Standard`: draw N u64 limbs, mask the top limb down to
+    the modulus bit length, reject if >= modulus; the limbs ARE the Montgomery representation.
+    Returns the canonical value."""
+    nbits = field.p.bit_length()
+    shave = 64 * field.limbs64 - nbits
+    mask = (1 << 64) - 1 if shave == 0 else ((1 << 64) - 1) >> shave
+    while True:
+        limbs = [rng.next_u64() for _ in range(field.limbs64)]
+        limbs[-1] &= mask
+        v = field.from_limbs(limbs)
+        if v < field.p:
+            return field.from_mont(v)
+
+
+def compute_coset_representatives(field: Field, num_wire_types: int, coset_size: int) -> List[int]:
+    """relation/src/constants.rs:30-79."""
+    p = field.p
+    rng = ChaCha20Rng(bytes(32))
+    ks, pows = [], []
+    for i in range(num_wire_types):
+        if i == 0:
+            ks.append(1)
+            pows.append(1)
+            continue
+        while True:
+            nxt = fp_rand(field, rng)
+            pw = pow(nxt, coset_size, p)
+            if all(pow(prev, -1, p) * pw % p != 1 for prev in pows):
+                break
+        ks.append(nxt)
+        pows.append(pw)
+    return ks
+
+
+# ======================================================================================
+# Serialization (`to_bytes!` = ark-serialize `serialize_compressed`)
+# ======================================================================================
+def ser_fr(field: Field, x: int) -> bytes:
+    return int(x % field.p).to_bytes(8 * field.limbs64, "little")
+
+
+def ser_g1(curve: Curve, P) -> bytes:
+    return curve.serialize_compressed(P)
+
+
+def from_le_bytes_mod_order(field: Field, b: bytes) -> int:
+    return int.from_bytes(b, "little") % field.p
+
+
+# ======================================================================================
+# Transcripts (plonk/src/transcript)
+# ======================================================================================
+class SolidityTranscript:
+    """solidity.rs:31-78 -- labels ignored; the byte vector is never cleared and the challenge is
+    not re-appended (the code, not its doc comment, is authoritative)."""
+
+    def __init__(self, label: bytes = b"PlonkProof"):
+        self.transcript = bytearray()
+        self.state = bytes(64)
+
+    def append_message(self, label: bytes, msg: bytes):
+        self.transcript += msg
+
+    def get_and_append_challenge(self, field: Field, label: bytes) -> int:
+        base = self.state + bytes(self.transcript)
+        self.state = keccak256(base + b"\x00") + keccak256(base + b"\x01")
+        return from_le_bytes_mod_order(field, self.state[:48])
+
+
+class StandardTranscript:
+    """standard.rs:18-46 -- Merlin; challenge = 64 PRF bytes mod r, then re-appended under the label."""
+
+    def __init__(self, label: bytes = b"PlonkProof"):
+        self.t = MerlinTranscript(label)
+
+    def append_message(self, label: bytes, msg: bytes):
+        self.t.append_message(label, msg)
+
+    def get_and_append_challenge(self, field: Field, label: bytes) -> int:
+        c = from_le_bytes_mod_order(field, self.t.challenge_bytes(label, 64))
+        self.t.append_message(label, ser_fr(field, c))
+        return c
+
+
+TRANSCRIPTS = {"solidity": SolidityTranscript, "standard": StandardTranscript}
+
+
+def append_vk_and_pub_input(tr, curve: Curve, vk: dict, pub_input: Sequence[int]):
+    """transcript/mod.rs:45-102."""
+    fr = curve.fr
+    tr.append_message(b"field size in bits", struct.pack("<I", fr.p.bit_length()))
+    tr.append_message(b"domain size", struct.pack("<Q", vk["domain_size"]))
+    tr.append_message(b"input size", struct.pack("<Q", vk["num_inputs"]))
+    for k in vk["k"]:
+        tr.append_message(b"wire subsets separators", ser_fr(fr, k))
+    for c in vk["selector_comms"]:
+        tr.append_message(b"selector commitments", ser_g1(curve, c))
+    for c in vk["sigma_comms"]:
+        tr.append_message(b"sigma commitments", ser_g1(curve, c))
+    for x in pub_input:
+        tr.append_message(b"public input", ser_fr(fr, x))
+
+
+# ======================================================================================
+# Circuit (TurboPlonk subset of `PlonkCircuit`)
+# ======================================================================================
+class Gate:
+    def __init__(self, name, q_lc=(0, 0, 0, 0), q_mul=(0, 0), q_hash=(0, 0, 0, 0), q_o=0, q_c=0, q_ecc=0):
+        self.name, self.q_lc, self.q_mul, self.q_hash, self.q_o, self.q_c, self.q_ecc = name, q_lc, q_mul, q_hash, q_o, q_c, q_ecc
+
+    def selectors(self) -> List[int]:
+        return list(self.q_lc) + list(self.q_mul) + list(self.q_hash) + [self.q_o, self.q_c, self.q_ecc]
+
+
+def ConstantGate(c): return Gate("const", q_c=c, q_o=1)
+def AdditionGate(): return Gate("add", q_lc=(1, 1, 0, 0), q_o=1)
+def SubtractionGate(p): return Gate("sub", q_lc=(1, p - 1, 0, 0), q_o=1)
+def MultiplicationGate(): return Gate("mul", q_mul=(1, 0), q_o=1)
+def EqualityGate(p): return Gate("eq", q_lc=(1, p - 1, 0, 0), q_o=1)
+def IoGate(): return Gate("io", q_o=1)
+def PaddingGate(): return Gate("pad")  # all selectors zero in this fork (relation/src/gates/mod.rs)
+
+
+class PlonkCircuit:
+    def __init__(self, field: Field = pyref.BN254_FR):
+        self.f = field
+        self.witness = [0, 1]
+        self.gates: List[Gate] = []
+        self.wire_variables: List[List[int]] = [[] for _ in range(NUM_WIRE_TYPES)]
+        self.pub_input_gate_ids: List[int] = []
+        self.n = 1  # eval domain size; 1 == not finalized
+        self.enforce_constant(0, 0)
+        self.enforce_constant(1, 1)
+
+    # -- construction ------------------------------------------------------------------------
+    def zero(self): return 0
+    def one(self): return 1
+    def num_gates(self): return len(self.gates)
+    def num_vars(self): return len(self.witness)
+    def num_inputs(self): return len(self.pub_input_gate_ids)
+
+    def create_variable(self, val: int) -> int:
+        self.witness.append(val % self.f.p)
+        return len(self.witness) - 1
+
+    def insert_gate(self, wire_vars: Sequence[int], gate: Gate):
+        assert self.n == 1 and len(wire_vars) == 5
+        for j, v in enumerate(wire_vars):
+            self.wire_variables[j].append(v)
+        self.gates.append(gate)
+
+    def set_variable_public(self, var: int):
+        self.pub_input_gate_ids.append(self.num_gates())
+        self.insert_gate([0, 0, 0, 0, var], IoGate())
+
+    def create_public_variable(self, val: int) -> int:
+        v = self.create_variable(val)
+        self.set_variable_public(v)
+        return v
+
+    def enforce_constant(self, var: int, c: int): self.insert_gate([0, 0, 0, 0, var], ConstantGate(c % self.f.p))
+    def enforce_equal(self, a: int, b: int): self.insert_gate([a, b, 0, 0, 0], EqualityGate(self.f.p))
+    def add_gate(self, a, b, c): self.insert_gate([a, b, 0, 0, c], AdditionGate())
+    def sub_gate(self, a, b, c): self.insert_gate([a, b, 0, 0, c], SubtractionGate(self.f.p))
+    def mul_gate(self, a, b, c): self.insert_gate([a, b, 0, 0, c], MultiplicationGate())
+
+    def add(self, a, b):
+        c = self.create_variable(self.witness[a] + self.witness[b])
+        self.add_gate(a, b, c)
+        return c
+
+    def sub(self, a, b):
+        c = self.create_variable(self.witness[a] - self.witness[b])
+        self.sub_gate(a, b, c)
+        return c
+
+    def mul(self, a, b):
+        c = self.create_variable(self.witness[a] * self.witness[b])
+        self.mul_gate(a, b, c)
+        return c
+
+    def public_input(self) -> List[int]:
+        return [self.witness[self.wire_variables[GATE_WIDTH][g]] for g in self.pub_input_gate_ids]
+
+    # -- finalize (TurboPlonk, no link groups) ---------------------------------------------------
+    def finalize_for_arithmetization(self):
+        if self.n != 1:
+            return
+        n = 1
+        while n < self.num_gates():  # CircuitLayout::circuit_size: next_power_of_two(n_gates)
+            n <<= 1
+        # rearrange_gates: io gates to the front (constraint_system.rs:630-645)
+        for gate_id, io_gate_id in enumerate(list(self.pub_input_gate_ids)):
+            if io_gate_id > gate_id:
+                self.gates[gate_id], self.gates[io_gate_id] = self.gates[io_gate_id], self.gates[gate_id]
+                for j in range(NUM_WIRE_TYPES):
+                    w = self.wire_variables[j]
+                    w[gate_id], w[io_gate_id] = w[io_gate_id], w[gate_id]
+                self.pub_input_gate_ids[gate_id] = gate_id
+        # pad with PaddingGate / variable 0 (linkable_circuit.rs:294-314)
+        while len(self.gates) < n:
+            self.gates.append(PaddingGate())
+            for j in range(NUM_WIRE_TYPES):
+                self.wire_variables[j].append(0)
+        self.n = n
+        self.domain = Radix2Domain(self.f, n)
+        self._compute_wire_permutation()
+        self.k = compute_coset_representatives(self.f, NUM_WIRE_TYPES, n)
+        p = self.f.p
+        g = self.domain.group_gen
+        elems = [1] * n
+        for j in range(1, n):
+            elems[j] = elems[j - 1] * g % p
+        self.extended_id_permutation = [ki * e % p for ki in self.k for e in elems]
+
+    def _compute_wire_permutation(self):
+        n = self.n
+        var_map: List[List[Tuple[int, int]]] = [[] for _ in range(self.num_vars())]
+        for wire_id in range(NUM_WIRE_TYPES):
+            for gate_id, var in enumerate(self.wire_variables[wire_id]):
+                var_map[var].append((wire_id, gate_id))
+        self.wire_permutation = [(0, 0)] * (NUM_WIRE_TYPES * n)
+        for wires in var_map:
+            if wires:
+                cyc = wires + [wires[0]]
+                for a, b in zip(cyc[:-1], cyc[1:]):
+                    self.wire_permutation[a[0] * n + a[1]] = b
+
+    # -- arithmetization inputs ----------------------------------------------------------------------
+    def selector_evals(self) -> List[List[int]]:
+        cols = [[0] * self.n for _ in range(N_SELECTORS)]
+        for i, g in enumerate(self.gates):
+            for s, v in enumerate(g.selectors()):
+                cols[s][i] = v % self.f.p
+        return cols
+
+    def extended_permutation(self) -> List[int]:
+        n = self.n
+        return [self.extended_id_permutation[w * n + g] for (w, g) in self.wire_permutation]
+
+    def wire_values(self) -> List[List[int]]:
+        return [[self.witness[v] for v in self.wire_variables[j]] for j in range(NUM_WIRE_TYPES)]
+
+    def check_satisfiability(self) -> bool:
+        p = self.f.p
+        pi = [0] * self.n
+        for g in self.pub_input_gate_ids:
+            pi[g] = self.witness[self.wire_variables[GATE_WIDTH][g]]
+        for i, g in enumerate(self.gates):
+            w = [self.witness[self.wire_variables[j][i]] for j in range(5)]
+            v = (g.q_c + pi[i] + sum(q * x for q, x in zip(g.q_lc, w)) + g.q_mul[0] * w[0] * w[1] + g.q_mul[1] * w[2] * w[3]
+                 + g.q_ecc * w[0] * w[1] * w[2] * w[3] * w[4] + sum(q * pow(x, 5, p) for q, x in zip(g.q_hash, w))
+                 - g.q_o * w[4]) % p
+            if v:
+                return False
+        return True
+
+
+def gen_circuit_for_bench(num_gates: int, field: Field = pyref.BN254_FR) -> PlonkCircuit:
+    """plonk/benches/bench.rs:29-46 (TurboPlonk)."""
+    cs = PlonkCircuit(field)
+    a = cs.zero()
+    for _ in range(num_gates - 10):
+        a = cs.add(a, cs.one())
+    cs.finalize_for_arithmetization()
+    return cs
+
+
+def gen_circuit_for_test(m: int, a0: int, field: Field = pyref.BN254_FR) -> PlonkCircuit:
+    """plonk/src/proof_system/snark.rs:681-744 (TurboPlonk branch)."""
+    cs = PlonkCircuit(field)
+    a = [cs.create_variable(i) for i in range(a0, a0 + 4 * m)]
+    b = [cs.create_public_variable(m * 2), cs.create_public_variable(a0 * 2 + m * 4 - 1)]
+    c = cs.create_public_variable((cs.witness[b[1]] + cs.witness[a[0]]) * (cs.witness[b[1]] - cs.witness[a[0]]))
+    acc = cs.zero()
+    for e in a:
+        acc = cs.add(acc, e)
+    b_mul = cs.mul(b[0], b[1])
+    cs.enforce_equal(acc, b_mul)
+    p1 = cs.add(b[1], a[0])
+    m1 = cs.sub(b[1], a[0])
+    cs.mul_gate(p1, m1, c)
+    cs.enforce_constant(b[0], m * 2)
+    cs.finalize_for_arithmetization()
+    return cs
+
+
+# ======================================================================================
+# Polynomial helpers (ark-poly DensePolynomial semantics; coefficient lists, low degree first)
+# ======================================================================================
+def _strip(c: List[int]) -> List[int]:
+    c = list(c)
+    while c and c[-1] == 0:
+        c.pop()
+    return c
+
+
+def _poly_add(p: int, a: Sequence[int], b: Sequence[int]) -> List[int]:
+    n = max(len(a), len(b))
+    return _strip([((a[i] if i < len(a) else 0) + (b[i] if i < len(b) else 0)) % p for i in range(n)])
+
+
+def _poly_scale(p: int, a: Sequence[int], s: int) -> List[int]:
+    return _strip([x * s % p for x in a])
+
+
+def _poly_eval(p: int, c: Sequence[int], x: int) -> int:
+    acc = 0
+    for v in reversed(c):
+        acc = (acc * x + v) % p
+    return acc
+
+
+def _div_linear(p: int, c: Sequence[int], z: int) -> List[int]:
+    """quotient of c(X) / (X - z), remainder dropped (ark-poly `/`)."""
+    if len(c) < 2:
+        return []
+    q = [0] * (len(c) - 1)
+    carry = 0
+    for i in range(len(c) - 1, 0, -1):
+        carry = (c[i] + carry * z) % p
+        q[i - 1] = carry
+    return _strip(q)
+
+
+class _Backend:
+    """NTT / MSM through the C oracle when present (sizes >= 2^8), else exact Python."""
+
+    def __init__(self, curve: Curve):
+        self.curve, self.fr = curve, curve.fr
+        try:
+            import coracle
+            coracle.build()
+            self.co = coracle
+        except Exception:  # pragma: no cover
+            self.co = None
+
+    def ntt(self, vals: Sequence[int], log_n: int, inverse: bool, offset: int = 1) -> List[int]:
+        n = 1 << log_n
+        f = self.fr
+        assert len(vals) <= n
+        if self.co is None or n < 64:
+            dom = Radix2Domain(f, n, offset)
+            return dom.ifft(list(vals) + [0] * (n - len(vals))) if inverse else dom.fft(list(vals))
+        co = self.co
+        R = f.R
+        arr = co.ints_to_limbs([v * R % f.p for v in vals] + [0] * (n - len(vals)), 4)
+        off = None if offset == 1 else co.ints_to_limbs([offset * R % f.p], 4)[0]
+        out = co.ntt(f.name, arr, log_n, inverse, off)
+        ri = pow(R, -1, f.p)
+        return [v * ri % f.p for v in co.limbs_to_ints(out)]
+
+    def commit(self, srs_limbs, srs_points, coeffs: Sequence[int]):
+        """UnivariateKzgPCS::commit (mod.rs:90-116): skip low-order zeros, msm_bigint, into_affine."""
+        c = list(coeffs)
+        nz = 0
+        while nz < len(c) and c[nz] == 0:
+            nz += 1
+        c = c[nz:]
+        if not c:
+            return None
+        if self.co is not None and srs_limbs is not None:
+            xy, inf = self.co.msm(self.curve.name, srs_limbs[nz:], self.co.ints_to_limbs(c, 4))
+            if inf:
+                return None
+            fq = self.curve.fq
+            x, y = self.co.limbs_to_ints(xy.reshape(2, fq.limbs64))
+            return (fq.from_mont(x), fq.from_mont(y))
+        return self.curve.msm_pippenger(c, srs_points[nz:nz + len(c)])
+
+
+# ======================================================================================
+# preprocess / prove / verify
+# ======================================================================================
+def quotient_domain_size(n: int) -> int:
+    """domain_size_ratio (plonk/src/constants.rs:18-20) then GeneralEvaluationDomain::new -> radix 2."""
+    m = 1
+    while m < n * (NUM_WIRE_TYPES + 1):
+        m <<= 1
+    return m
+
+
+def gen_srs(curve: Curve, beta: int, max_degree: int):
+    """powers_of_g = [beta^i] g, i <= max_degree (srs.rs:118-153, known beta).  Returns
+    (limb array or None, python points or None): the C oracle generates large keys."""
+    try:
+        import coracle
+        coracle.build()
+        lim = coracle.gen_srs(curve.name, coracle.ints_to_limbs([beta], 4)[0], max_degree + 1)
+        return lim, None
+    except Exception:  # pragma: no cover
+        return None, pyref.gen_srs_for_testing(curve, beta, max_degree)
+
+
+def preprocess(curve: Curve, srs, cs: PlonkCircuit) -> dict:
+    """snark.rs:529-611: selector / sigma polynomials (ifft) and their commitments."""
+    be = _Backend(curve)
+    n = cs.n
+    log_n = n.bit_length() - 1
+    srs_limbs, srs_points = srs
+    selectors = [_strip(be.ntt(col, log_n, True)) for col in cs.selector_evals()]
+    ext = cs.extended_permutation()
+    sigmas = [_strip(be.ntt(ext[i * n:(i + 1) * n], log_n, True)) for i in range(NUM_WIRE_TYPES)]
+    vk = {
+        "domain_size": n, "num_inputs": cs.num_inputs(),
+        "selector_comms": [be.commit(srs_limbs, srs_points, s) for s in selectors],
+        "sigma_comms": [be.commit(srs_limbs, srs_points, s) for s in sigmas],
+        "k": list(cs.k),
+    }
+    return {"selectors": selectors, "sigmas": sigmas, "vk": vk, "srs": srs, "n": n}
+
+
+def prove(curve: Curve, cs: PlonkCircuit, pk: dict, blinders: Sequence[int], transcript: str = "solidity",
+          extra_msg: Optional[bytes] = None) -> dict:
+    """batch_prove_internal for one TurboPlonk instance (snark.rs:201-469).  `blinders`: the 17
+    field elements the reference draws from its prng, in consumption order:
+    5 x (b0, b1) for the wire polys, (b0, b1, b2) for z, 4 split-quotient randomizers."""
+    fr, p = curve.fr, curve.fr.p
+    be = _Backend(curve)
+    n = pk["n"]
+    log_n = n.bit_length() - 1
+    m = quotient_domain_size(n)
+    log_m = m.bit_length() - 1
+    ratio = m // n
+    dom = Radix2Domain(fr, n)
+    qdom = Radix2Domain(fr, m)
+    g = dom.group_gen
+    srs_limbs, srs_points = pk["srs"]
+    vk = pk["vk"]
+    k = vk["k"]
+    bl = list(blinders)
+    assert len(bl) == 17
+
+    def commit(c):
+        return be.commit(srs_limbs, srs_points, c)
+
+    def mask(poly: List[int], hb: int) -> List[int]:
+        # mask_polynomial (prover.rs:463-486): rand(hb) * (X^n - 1) + poly
+        r = [bl.pop(0) for _ in range(hb + 1)]
+        out = list(poly) + [0] * (n + hb + 1 - len(poly))
+        for i, b in enumerate(r):
+            out[i] = (out[i] - b) % p
+            out[n + i] = (out[n + i] + b) % p
+        return _strip(out)
+
+    tr = TRANSCRIPTS[transcript](b"PlonkProof")
+    if extra_msg is not None:
+        tr.append_message(b"extra info", extra_msg)
+    pub_input = cs.public_input()
+    append_vk_and_pub_input(tr, curve, vk, pub_input)
+
+    # ---- round 1 ---------------------------------------------------------------------------------
+    wvals = cs.wire_values()
+    wire_polys = [mask(_strip(be.ntt(w, log_n, True)), 1) for w in wvals]
+    wires_comms = [commit(wp) for wp in wire_polys]
+    pi_vec = [0] * n
+    for gid in cs.pub_input_gate_ids:
+        pi_vec[gid] = cs.witness[cs.wire_variables[GATE_WIDTH][gid]]
+    pi_poly = _strip(be.ntt(pi_vec, log_n, True))
+    for c in wires_comms:
+        tr.append_message(b"witness_poly_comms", ser_g1(curve, c))
+    tau = tr.get_and_append_challenge(fr, b"tau")  # noqa: F841  (squeezed even without Plookup)
+
+    # ---- round 2 ---------------------------------------------------------------------------------
+    beta = tr.get_and_append_challenge(fr, b"beta")
+    gamma = tr.get_and_append_challenge(fr, b"gamma")
+    ext_id, wperm = cs.extended_id_permutation, cs.wire_permutation
+    prod = [1]
+    for j in range(n - 1):
+        a = b = 1
+        for i in range(NUM_WIRE_TYPES):
+            tmp = (wvals[i][j] + gamma) % p
+            a = a * (tmp + beta * ext_id[i * n + j]) % p
+            pi_, pj_ = wperm[i * n + j]
+            b = b * (tmp + beta * ext_id[pi_ * n + pj_]) % p
+        prod.append(prod[-1] * a % p * pow(b, -1, p) % p)
+    z_poly = mask(_strip(be.ntt(prod, log_n, True)), 2)
+    z_comm = commit(z_poly)
+    tr.append_message(b"perm_poly_comms", ser_g1(curve, z_comm))
+
+    # ---- round 3 ---------------------------------------------------------------------------------
+    alpha = tr.get_and_append_challenge(fr, b"alpha")
+    G = fr.generator
+    z_h_inv = [pow((pow(G * qdom.element(i) % p, n, p) - 1) % p, -1, p) for i in range(ratio)]
+    cfft = lambda poly: be.ntt(poly, log_m, False, G)  # noqa: E731  coset.fft
+    sel_c = [cfft(s) for s in pk["selectors"]]
+    sig_c = [cfft(s) for s in pk["sigmas"]]
+    w_c = [cfft(wp) for wp in wire_polys]
+    z_c = cfft(z_poly)
+    pi_c = cfft(pi_poly)
+    alpha2 = alpha * alpha % p
+    n_f = n % p
+    quot = [0] * m
+    wq = qdom.group_gen
+    x = G  # eval point g * w_m^i
+    for i in range(m):
+        w = [w_c[j][i] for j in range(5)]
+        q = [sel_c[s][i] for s in range(N_SELECTORS)]
+        t_circ = (q[11] + pi_c[i] + q[0] * w[0] + q[1] * w[1] + q[2] * w[2] + q[3] * w[3]
+                  + q[4] * w[0] * w[1] + q[5] * w[2] * w[3] + q[12] * w[0] * w[1] * w[2] * w[3] * w[4]
+                  + q[6] * pow(w[0], 5, p) + q[7] * pow(w[1], 5, p) + q[8] * pow(w[2], 5, p) + q[9] * pow(w[3], 5, p)
+                  - q[10] * w[4]) % p
+        zx, zxw = z_c[i], z_c[(i + ratio) % m]
+        r1 = zx
+        r2 = zxw
+        for j in range(5):
+            r1 = r1 * (w[j] + k[j] * x % p * beta + gamma) % p
+            r2 = r2 * (w[j] + sig_c[j][i] * beta + gamma) % p
+        t_perm1 = alpha * (r1 - r2) % p
+        t_perm2 = alpha2 * (zx - 1) % p * pow(n_f * (x - 1) % p, -1, p) % p
+        quot[i] = ((t_circ + t_perm1) * z_h_inv[i % ratio] + t_perm2) % p
+        x = x * wq % p
+    quot_poly = _strip(be.ntt(quot, log_m, True, G))
+    expected_degree = NUM_WIRE_TYPES * (n + 1) + 2
+    if len(quot_poly) - 1 != expected_degree:
+        raise ValueError("WrongQuotientPolyDegree(%d, %d)" % (len(quot_poly) - 1, expected_degree))
+    split = []
+    for i in range(NUM_WIRE_TYPES):
+        end = (i + 1) * (n + 2) if i < NUM_WIRE_TYPES - 1 else len(quot_poly)
+        split.append(_strip(quot_poly[i * (n + 2):end]))
+    last = 0
+    for i in range(NUM_WIRE_TYPES - 1):
+        now = bl.pop(0)
+        split[i][0] = (split[i][0] - last) % p
+        assert len(split[i]) == n + 2
+        split[i].append(now)
+        last = now
+    split[-1][0] = (split[-1][0] - last) % p
+    split_comms = [commit(s) for s in split]
+    for c in split_comms:
+        tr.append_message(b"quot_poly_comms", ser_g1(curve, c))
+
+    # ---- round 4 ---------------------------------------------------------------------------------
+    zeta = tr.get_and_append_challenge(fr, b"zeta")
+    wires_evals = [_poly_eval(p, wp, zeta) for wp in wire_polys]
+    sigma_evals = [_poly_eval(p, s, zeta) for s in pk["sigmas"][:NUM_WIRE_TYPES - 1]]
+    perm_next_eval = _poly_eval(p, z_poly, zeta * g % p)
+    for e in wires_evals:
+        tr.append_message(b"wire_evals", ser_fr(fr, e))
+    for e in sigma_evals:
+        tr.append_message(b"wire_sigma_evals", ser_fr(fr, e))
+    tr.append_message(b"perm_next_eval", ser_fr(fr, perm_next_eval))
+
+    # linearization polynomial (snark.rs:419-440; prover.rs:339-360,963-1034)
+    vanish = (pow(zeta, n, p) - 1) % p
+    zeta_n2 = (vanish + 1) * zeta % p * zeta % p
+    r_quot = list(split[0])
+    coeff = 1
+    for sp in split[1:]:
+        coeff = coeff * zeta_n2 % p
+        r_quot = _poly_add(p, r_quot, _poly_scale(p, sp, coeff))
+    lin = _poly_scale(p, r_quot, (-vanish) % p)
+    we = wires_evals
+    sel = pk["selectors"]
+    r_circ = []
+    for s_idx, sc in ((0, we[0]), (1, we[1]), (2, we[2]), (3, we[3]), (4, we[0] * we[1]), (5, we[2] * we[3]),
+                      (6, pow(we[0], 5, p)), (7, pow(we[1], 5, p)), (8, pow(we[2], 5, p)), (9, pow(we[3], 5, p)),
+                      (12, we[0] * we[1] * we[2] * we[3] * we[4]), (10, -we[4])):
+        r_circ = _poly_add(p, r_circ, _poly_scale(p, sel[s_idx], sc % p))
+    r_circ = _poly_add(p, r_circ, sel[11])
+    lagrange_1 = vanish * pow(n_f * (zeta - 1) % p, -1, p) % p
+    c1 = alpha
+    for j in range(5):
+        c1 = c1 * (we[j] + beta * k[j] % p * zeta + gamma) % p
+    c1 = (c1 + alpha2 * lagrange_1) % p
+    r_perm = _poly_scale(p, z_poly, c1)
+    c2 = alpha * beta % p * perm_next_eval % p
+    for j in range(4):
+        c2 = c2 * (we[j] + beta * sigma_evals[j] + gamma) % p
+    r_perm = _poly_add(p, r_perm, _poly_scale(p, pk["sigmas"][4], (-c2) % p))
+    lin = _poly_add(p, lin, _poly_scale(p, _poly_add(p, r_circ, r_perm), 1))  # alpha_base = 1
+
+    # ---- round 5 ---------------------------------------------------------------------------------
+    v = tr.get_and_append_challenge(fr, b"v")
+
+    def batched_witness(polys, r, point):
+        acc, coeff = [], 1
+        for poly in polys:
+            acc = _poly_add(p, acc, _poly_scale(p, poly, coeff))
+            coeff = coeff * r % p
+        return commit(_div_linear(p, acc, point))
+
+    opening = batched_witness([lin] + wire_polys + pk["sigmas"][:4], v, zeta)
+    shifted = batched_witness([z_poly], v, g * zeta % p)
+    return {
+        "wires_poly_comms": wires_comms, "prod_perm_poly_comm": z_comm, "split_quot_poly_comms": split_comms,
+        "opening_proof": opening, "shifted_opening_proof": shifted,
+        "wires_evals": wires_evals, "wire_sigma_evals": sigma_evals, "perm_next_eval": perm_next_eval,
+        "challenges": {"beta": beta, "gamma": gamma, "alpha": alpha, "zeta": zeta, "v": v},
+    }
+
+
+def serialize_proof(curve: Curve, proof: dict) -> bytes:
+    """`Proof<E>` CanonicalSerialize (compressed), field order of structs.rs:62-84."""
+    fr = curve.fr
+    out = bytearray()
+    out += struct.pack("<Q", len(proof["wires_poly_comms"]))
+    for c in proof["wires_poly_comms"]:
+        out += ser_g1(curve, c)
+    out += ser_g1(curve, proof["prod_perm_poly_comm"])
+    out += struct.pack("<Q", len(proof["split_quot_poly_comms"]))
+    for c in proof["split_quot_poly_comms"]:
+        out += ser_g1(curve, c)
+    out += ser_g1(curve, proof["opening_proof"])
+    out += ser_g1(curve, proof["shifted_opening_proof"])
+    out += struct.pack("<Q", len(proof["wires_evals"]))
+    for e in proof["wires_evals"]:
+        out += ser_fr(fr, e)
+    out += struct.pack("<Q", len(proof["wire_sigma_evals"]))
+    for e in proof["wire_sigma_evals"]:
+        out += ser_fr(fr, e)
+    out += ser_fr(fr, proof["perm_next_eval"])
+    out += b"\x00"  # plookup_proof: None
+    return bytes(out)
+
+
+def verify(curve: Curve, vk: dict, pub_input: Sequence[int], proof: dict, beta_srs: int, transcript: str = "solidity",
+           extra_msg: Optional[bytes] = None) -> bool:
+    """verifier.rs (prepare_pcs_info + batch_verify_opening_proofs for one proof); the pairing check
+    e(A,[x]_2) == e(B,[1]_2) is evaluated as x*A == B with the known trapdoor x = beta_srs."""
+    fr, p = curve.fr, curve.fr.p
+    n = vk["domain_size"]
+    dom = Radix2Domain(fr, n)
+    g = dom.group_gen
+    k = vk["k"]
+    if len(pub_input) != vk["num_inputs"]:
+        return False
+    # compute_challenges (verifier.rs:257-318)
+    tr = TRANSCRIPTS[transcript](b"PlonkProof")
+    if extra_msg is not None:
+        tr.append_message(b"extra info", extra_msg)
+    append_vk_and_pub_input(tr, curve, vk, pub_input)
+    for c in proof["wires_poly_comms"]:
+        tr.append_message(b"witness_poly_comms", ser_g1(curve, c))
+    tr.get_and_append_challenge(fr, b"tau")
+    beta = tr.get_and_append_challenge(fr, b"beta")
+    gamma = tr.get_and_append_challenge(fr, b"gamma")
+    tr.append_message(b"perm_poly_comms", ser_g1(curve, proof["prod_perm_poly_comm"]))
+    alpha = tr.get_and_append_challenge(fr, b"alpha")
+    for c in proof["split_quot_poly_comms"]:
+        tr.append_message(b"quot_poly_comms", ser_g1(curve, c))
+    zeta = tr.get_and_append_challenge(fr, b"zeta")
+    for e in proof["wires_evals"]:
+        tr.append_message(b"wire_evals", ser_fr(fr, e))
+    for e in proof["wire_sigma_evals"]:
+        tr.append_message(b"wire_sigma_evals", ser_fr(fr, e))
+    tr.append_message(b"perm_next_eval", ser_fr(fr, proof["perm_next_eval"]))
+    v = tr.get_and_append_challenge(fr, b"v")
+    tr.append_message(b"open_proof", ser_g1(curve, proof["opening_proof"]))
+    tr.append_message(b"shifted_open_proof", ser_g1(curve, proof["shifted_opening_proof"]))
+    u = tr.get_and_append_challenge(fr, b"u")
+
+    alpha2 = alpha * alpha % p
+    vanish = (pow(zeta, n, p) - 1) % p
+    n_f = n % p
+    lagrange_1 = vanish * pow(n_f * (zeta - 1) % p, -1, p) % p
+    we, se, pne = proof["wires_evals"], proof["wire_sigma_evals"], proof["perm_next_eval"]
+    # evaluate_pi_poly (verifier.rs:765-805)
+    pi_eval = 0
+    if vanish:
+        vdn = pow(n_f, -1, p) * vanish % p
+        for i, val in enumerate(pub_input):
+            e = dom.element(i)
+            pi_eval = (pi_eval + vdn * e % p * pow((zeta - e) % p, -1, p) % p * val) % p
+    # compute_lin_poly_constant_term
+    tmp = (pi_eval - alpha2 * lagrange_1) % p
+    acc = alpha * pne % p * ((gamma + we[4]) % p) % p
+    for j in range(4):
+        acc = acc * ((gamma + we[j] + beta * se[j]) % p) % p
+    lin_const = (tmp - acc) % p
+    # linearization_scalars_and_bases
+    sb: List[Tuple[int, object]] = []
+    coeff = alpha2 * lagrange_1 % p
+    c = alpha
+    for j in range(5):
+        c = c * ((beta * k[j] % p * zeta + gamma + we[j]) % p) % p
+    sb.append(((coeff + c) % p, proof["prod_perm_poly_comm"]))
+    c = alpha * beta % p * pne % p
+    for j in range(4):
+        c = c * ((beta * se[j] + gamma + we[j]) % p) % p
+    sb.append(((-c) % p, vk["sigma_comms"][4]))
+    qs = [we[0], we[1], we[2], we[3], we[0] * we[1] % p, we[2] * we[3] % p, pow(we[0], 5, p), pow(we[1], 5, p),
+          pow(we[2], 5, p), pow(we[3], 5, p), (-we[4]) % p, 1, we[0] * we[1] * we[2] * we[3] * we[4] % p]
+    for s, cm in zip(qs, vk["selector_comms"]):
+        sb.append((s, cm))
+    zeta_n2 = (1 + vanish) * zeta % p * zeta % p
+    coeff = (-vanish) % p
+    sb.append((coeff, proof["split_quot_poly_comms"][0]))
+    for cm in proof["split_quot_poly_comms"][1:]:
+        coeff = coeff * zeta_n2 % p
+        sb.append((coeff, cm))
+    # aggregate_poly_commitments / aggregate_evaluations
+    v_base, uv_base = v, u
+    buf = []
+    for cm in proof["wires_poly_comms"]:
+        buf.append(v_base); sb.append((v_base, cm)); v_base = v_base * v % p
+    for cm in vk["sigma_comms"][:4]:
+        buf.append(v_base); sb.append((v_base, cm)); v_base = v_base * v % p
+    buf.append(uv_base); sb.append((uv_base, proof["prod_perm_poly_comm"])); uv_base = uv_base * v % p
+    ev = (-lin_const) % p
+    for b_, e in zip(buf, list(we) + list(se) + [pne]):
+        ev = (ev + e * b_) % p
+    # batch_verify_opening_proofs with one instance (r = 1)
+    A = curve.add(proof["opening_proof"], curve.mul(u, proof["shifted_opening_proof"]))
+    B = None
+    for s, cm in sb:
+        B = curve.add(B, curve.mul(s % p, cm))
+    B = curve.add(B, curve.mul(zeta, proof["opening_proof"]))
+    B = curve.add(B, curve.mul(u * (zeta * g % p) % p, proof["shifted_opening_proof"]))
+    B = curve.add(B, curve.mul((-ev) % p, curve.gen))
+    return curve.mul(beta_srs % p, A) == B

@@ -1,0 +1,91 @@
+"""CPU suite: pin the prover oracle (oracle/plonk_ref.py).  Keccak-256 against the reference's own
+KAT, Merlin / ChaCha20 / coset representatives against published vectors (tests/golden/
+transcript_vectors.json), then prover <-> verifier consistency: the prover restated from prover.rs /
+snark.rs must satisfy the verifier restated from verifier.rs (known-beta G1 form of the pairing check)."""
+import json
+import os
+import random
+import struct
+
+import pytest
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "transcript_vectors.json")))
+
+
+@pytest.fixture(scope="module")
+def P():
+    import plonk_ref
+    return plonk_ref
+
+
+def test_keccak256_reference_kat(P):
+    g = GOLD["keccak256"]
+    assert P.keccak256(g["message"].encode()).hex() == g["digest"]
+    assert P.keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+
+
+def test_merlin_published_vector(P):
+    g = GOLD["merlin"]
+    t = P.MerlinTranscript(g["protocol"].encode())
+    t.append_message(g["label"].encode(), g["data"].encode())
+    assert t.challenge_bytes(g["challenge_label"].encode(), 32).hex() == g["challenge"]
+
+
+def test_chacha20_and_coset_representatives(P, py):
+    assert struct.pack("<16I", *P.chacha20_block([0] * 8, 0)).hex() == GOLD["chacha20_zero_key_block0"]
+    want = [int(x, 16) for x in GOLD["coset_k_bn254"]]
+    for n in (1 << 5, 1 << 10, 1 << 20):
+        assert P.compute_coset_representatives(py.BN254_FR, 5, n) == want
+
+
+def test_solidity_transcript_follows_the_code_not_the_doc(P, py):
+    # state <- keccak(state|transcript|0) || keccak(state|transcript|1); the transcript is NOT cleared
+    t = P.SolidityTranscript()
+    t.append_message(b"ignored", b"abc")
+    c1 = t.get_and_append_challenge(py.BN254_FR, b"x")
+    s1 = P.keccak256(bytes(64) + b"abc\x00") + P.keccak256(bytes(64) + b"abc\x01")
+    assert c1 == int.from_bytes(s1[:48], "little") % py.BN254_FR.p
+    t.append_message(b"ignored", b"de")
+    c2 = t.get_and_append_challenge(py.BN254_FR, b"y")
+    s2 = P.keccak256(s1 + b"abcde\x00") + P.keccak256(s1 + b"abcde\x01")
+    assert c2 == int.from_bytes(s2[:48], "little") % py.BN254_FR.p
+
+
+@pytest.mark.parametrize("kind", ["solidity", "standard"])
+@pytest.mark.parametrize("which", ["test_m2", "bench_64", "test_m20"])
+def test_oracle_prover_satisfies_oracle_verifier(P, py, kind, which):
+    cv = py.BN254
+    cs = {"test_m2": lambda: P.gen_circuit_for_test(2, 3), "bench_64": lambda: P.gen_circuit_for_bench(64),
+          "test_m20": lambda: P.gen_circuit_for_test(20, 1)}[which]()
+    assert cs.check_satisfiability()
+    beta = 0x1234567890ABCDEF1234567890ABCDEF % cv.fr.p
+    pk = P.preprocess(cv, P.gen_srs(cv, beta, cs.n + 2), cs)
+    rnd = random.Random(3)
+    bl = [rnd.randrange(cv.fr.p) for _ in range(17)]
+    proof = P.prove(cv, cs, pk, bl, kind)
+    assert P.verify(cv, pk["vk"], cs.public_input(), proof, beta, kind)
+    assert len(P.serialize_proof(cv, proof)) == 8 * 4 + 32 * 13 + 32 * 10 + 1
+    # soundness smoke: any tampering is rejected, and so is the wrong transcript or public input
+    bad = dict(proof)
+    bad["wires_evals"] = [proof["wires_evals"][0] ^ 1] + proof["wires_evals"][1:]
+    assert not P.verify(cv, pk["vk"], cs.public_input(), bad, beta, kind)
+    other = "standard" if kind == "solidity" else "solidity"
+    assert not P.verify(cv, pk["vk"], cs.public_input(), proof, beta, other)
+    if cs.num_inputs():
+        pi = cs.public_input()
+        pi[0] = (pi[0] + 1) % cv.fr.p
+        assert not P.verify(cv, pk["vk"], pi, proof, beta, kind)
+    # different blinders, different proof, still accepted (zero-knowledge masking is live)
+    proof2 = P.prove(cv, cs, pk, [b + 1 for b in bl], kind)
+    assert proof2["wires_poly_comms"] != proof["wires_poly_comms"]
+    assert P.verify(cv, pk["vk"], cs.public_input(), proof2, beta, kind)
+
+
+def test_unsatisfied_witness_fails_quotient_degree(P, py):
+    cv = py.BN254
+    cs = P.gen_circuit_for_test(2, 3)
+    pk = P.preprocess(cv, P.gen_srs(cv, 77, cs.n + 2), cs)
+    cs.witness[5] = (cs.witness[5] + 1) % cv.fr.p  # break a gate
+    assert not cs.check_satisfiability()
+    with pytest.raises(ValueError, match="WrongQuotientPolyDegree"):
+        P.prove(cv, cs, pk, list(range(1, 18)), "solidity")
