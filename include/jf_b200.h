@@ -31,6 +31,7 @@ extern "C" {
 
 typedef struct jf_ctx jf_ctx; /* one CUDA device + stream + workspace */
 typedef struct jf_srs jf_srs; /* device-resident commit key (`UnivariateProverParam::powers_of_g`) */
+typedef struct jf_plonk_pk jf_plonk_pk; /* device-resident `ProvingKey` + per-proof workspace */
 
 typedef enum {
     JF_OK = 0,
@@ -38,7 +39,8 @@ typedef enum {
     JF_ERR_CUDA = -2,             /* -> PCSError::UpstreamError */
     JF_ERR_DOMAIN_TOO_LARGE = -3, /* log_n > two-adicity -> PlonkError::DomainCreationError (plonk/src/errors.rs:16-49) */
     JF_ERR_SCALAR_RANGE = -4,     /* a scalar was >= the group order (arkworks BigInts from into_bigint never are) */
-    JF_ERR_NOMEM = -5
+    JF_ERR_NOMEM = -5,
+    JF_ERR_QUOTIENT_DEGREE = -6   /* -> SnarkError::WrongQuotientPolyDegree (prover.rs:916-919): witness does not satisfy the circuit */
 } jf_status;
 
 typedef enum { JF_BN254 = 0, JF_BLS12_381 = 1 } jf_curve;
@@ -114,6 +116,65 @@ int jf_ntt(jf_ctx *ctx, int field, uint64_t *data, size_t in_len, unsigned log_n
 /* Same on a device pointer (data stays in HBM; used by the device-resident prover rows). */
 int jf_ntt_device(jf_ctx *ctx, int field, void *d_data, size_t in_len, unsigned log_n, int inverse,
                   const uint64_t *coset_offset, size_t batch, size_t batch_stride);
+
+/* ---- TurboPlonk prover rounds around the two kernels -----------------
+ * One TurboPlonk instance, 5 wire types, no Plookup.  Circuit construction stays with the caller
+ * (relation/src/constraint_system.rs): it passes the selector columns `all_selectors()` (13 x n, order
+ * q_lc0-3, q_mul0-1, q_hash0-3, q_o, q_c, q_ecc; :890-905), the extended permutation
+ * `compute_extended_permutation()` (5 x n; :929-953), the coset representatives k (relation/src/constants.rs:30-79),
+ * the wire -> variable map `wire_variables` (5 x n) and the io gate ids.  All field elements are 4-limb
+ * Montgomery.
+ *
+ * jf_plonk_preprocess == `PlonkKzgSnark::preprocess` (plonk/src/proof_system/snark.rs:529-611): 18 iNTTs,
+ * 18 commitments; the selector / sigma polynomials stay resident (the `ProvingKey`).  flags & 1: also
+ * keep their 8n coset evaluations resident (18 of the 25 coset NTTs of round 3 then happen once per
+ * key instead of once per proof; +4.5 GiB at n = 2^20).  `srs` must outlive the key and hold >= n + 3 points. */
+int jf_plonk_preprocess(jf_ctx *ctx, const jf_srs *srs, unsigned log_n, const uint64_t *selector_evals,
+                        const uint64_t *sigma_evals, const uint64_t *k, const uint32_t *wire_variables, size_t num_vars,
+                        const uint32_t *pub_input_gate_ids, size_t num_inputs, int flags, jf_plonk_pk **out);
+/* selector_comms (13) then sigma_comms (5) of the `VerifyingKey`: affine x || y each, plus infinity flags */
+int jf_plonk_vk_commitments(jf_ctx *ctx, const jf_plonk_pk *pk, uint64_t *out_xy, int *out_inf);
+void jf_plonk_pk_free(jf_ctx *ctx, jf_plonk_pk *pk);
+
+/* `Proof<E>` (plonk/src/proof_system/structs.rs:62-84); points are x || y with 2*L limbs each, packed. */
+typedef struct {
+    int curve;
+    uint64_t wires_poly_comms[5 * 12];
+    int wires_inf[5];
+    uint64_t prod_perm_poly_comm[12];
+    int prod_perm_inf;
+    uint64_t split_quot_poly_comms[5 * 12];
+    int split_inf[5];
+    uint64_t opening_proof[12];
+    int opening_inf;
+    uint64_t shifted_opening_proof[12];
+    int shifted_opening_inf;
+    uint64_t wires_evals[5 * 4];       /* ProofEvaluations, Montgomery */
+    uint64_t wire_sigma_evals[4 * 4];
+    uint64_t perm_next_eval[4];
+    uint64_t challenges[5 * 4];        /* beta, gamma, alpha, zeta, v (Montgomery): diagnostics */
+} jf_plonk_proof;
+
+/* jf_plonk_prove == `PlonkKzgSnark::prove` -> `batch_prove_internal` for one instance (snark.rs:201-469)
+ * with all five `Prover` rounds (prover.rs).  witness: num_vars Montgomery elements (`cs.witness`).
+ * blinders: the 17 field elements the reference draws from its prng, in its consumption order
+ * (5 x 2 wire masks, 3 for the permutation product, 4 split-quotient randomizers; prover.rs:463-486,946-957):
+ * the caller keeps control of the randomness, which is also what makes proofs comparable byte for byte.
+ * transcript_kind: 0 `SolidityTranscript` (Keccak-256), 1 `StandardTranscript` (Merlin).
+ * extra_msg: `extra_transcript_init_msg` or NULL.  Fails with JF_ERR_QUOTIENT_DEGREE when the witness does
+ * not satisfy the circuit (the reference's WrongQuotientPolyDegree). */
+int jf_plonk_prove(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *witness, const uint64_t *blinders, int transcript_kind,
+                   const uint8_t *extra_msg, size_t extra_len, jf_plonk_proof *out);
+/* ark-serialize `serialize_compressed` of the proof; returns the byte count (769 for BN254) or < 0. */
+long jf_plonk_proof_serialize(const jf_plonk_proof *proof, uint8_t *out, size_t cap);
+
+/* Host-only pieces of the transcripts (no GPU needed): sha3 `Keccak256`, and `PlonkTranscript`
+ * new / append_message / get_and_append_challenge (plonk/src/transcript/{solidity,standard}.rs). */
+void jf_keccak256(const uint8_t *data, size_t len, uint8_t out[32]);
+void *jf_transcript_new(int kind, const char *label);
+void jf_transcript_free(void *t);
+void jf_transcript_append(void *t, const char *label, const uint8_t *msg, size_t len);
+int jf_transcript_challenge(void *t, int field, const char *label, uint64_t *out_montgomery);
 
 /* ---- device buffers (plumbing for callers that keep polynomials resident) ------------ */
 int jf_dev_alloc(jf_ctx *ctx, size_t bytes, void **out);

@@ -8,12 +8,15 @@ here computes on the CPU; without the CUDA library every entry point raises.
 from . import _ffi
 from .context import CommitKey, Context
 from .domain import Radix2EvaluationDomain
-from .errors import DomainCreationError, InvalidParameters, PCSError, PlonkError, UpstreamError
+from .errors import (DomainCreationError, InvalidParameters, PCSError, PlonkError, UpstreamError,
+                     WrongQuotientPolyDegree)
+from .plonk import PlonkKzgSnark, Proof, ProvingKey, Transcript, keccak256
 from .sharded import ShardedMsm, combine_partials, poly_owner, shard_range
 from .pcs import Commitment, DensePolynomial, UnivariateKzgPCS, UnivariateProverParam
 
 __all__ = [
     "Context", "CommitKey", "Radix2EvaluationDomain", "UnivariateKzgPCS", "UnivariateProverParam",
     "DensePolynomial", "Commitment", "PCSError", "InvalidParameters", "UpstreamError", "PlonkError",
-    "DomainCreationError", "ShardedMsm", "combine_partials", "poly_owner", "shard_range",
+    "DomainCreationError", "WrongQuotientPolyDegree", "PlonkKzgSnark", "Proof", "ProvingKey", "Transcript", "keccak256",
+    "ShardedMsm", "combine_partials", "poly_owner", "shard_range",
 ]

@@ -21,6 +21,7 @@ JF_ERR_CUDA = -2
 JF_ERR_DOMAIN_TOO_LARGE = -3
 JF_ERR_SCALAR_RANGE = -4
 JF_ERR_NOMEM = -5
+JF_ERR_QUOTIENT_DEGREE = -6
 
 CURVES = {"bn254": 0, "bls12_381": 1}
 FIELDS = {"bn254_fr": 0, "bn254_fq": 1, "bls12_381_fr": 2, "bls12_381_fq": 3}
@@ -28,6 +29,24 @@ FIELD_LIMBS = {"bn254_fr": 4, "bn254_fq": 4, "bls12_381_fr": 4, "bls12_381_fq": 
 CURVE_FQ_LIMBS = {"bn254": 4, "bls12_381": 6}
 CURVE_FR = {"bn254": "bn254_fr", "bls12_381": "bls12_381_fr"}
 FIELD_OPS = {"mul": 0, "add": 1, "sub": 2, "sqr": 3, "inv": 4, "to_mont": 5, "from_mont": 6, "neg": 7}
+
+c_u32p = ctypes.POINTER(ctypes.c_uint32)
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+class PlonkProofStruct(ctypes.Structure):
+    """`jf_plonk_proof` of include/jf_b200.h."""
+    _fields_ = [
+        ("curve", ctypes.c_int),
+        ("wires_poly_comms", ctypes.c_uint64 * 60), ("wires_inf", ctypes.c_int * 5),
+        ("prod_perm_poly_comm", ctypes.c_uint64 * 12), ("prod_perm_inf", ctypes.c_int),
+        ("split_quot_poly_comms", ctypes.c_uint64 * 60), ("split_inf", ctypes.c_int * 5),
+        ("opening_proof", ctypes.c_uint64 * 12), ("opening_inf", ctypes.c_int),
+        ("shifted_opening_proof", ctypes.c_uint64 * 12), ("shifted_opening_inf", ctypes.c_int),
+        ("wires_evals", ctypes.c_uint64 * 20), ("wire_sigma_evals", ctypes.c_uint64 * 16),
+        ("perm_next_eval", ctypes.c_uint64 * 4), ("challenges", ctypes.c_uint64 * 20),
+    ]
+
 
 # name -> (restype, argtypes); must list every function of include/jf_b200.h
 SIGNATURES = {
@@ -69,6 +88,18 @@ SIGNATURES = {
     "jf_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "jf_profile_collect": (ctypes.c_long, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]),
     "jf_microbench": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
+    "jf_plonk_preprocess": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint, c_u64p, c_u64p, c_u64p, c_u32p,
+                                           ctypes.c_size_t, c_u32p, ctypes.c_size_t, ctypes.c_int, c_void_pp]),
+    "jf_plonk_vk_commitments": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64p, ctypes.POINTER(ctypes.c_int)]),
+    "jf_plonk_pk_free": (None, [ctypes.c_void_p, ctypes.c_void_p]),
+    "jf_plonk_prove": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64p, c_u64p, ctypes.c_int, ctypes.c_char_p,
+                                      ctypes.c_size_t, ctypes.POINTER(PlonkProofStruct)]),
+    "jf_plonk_proof_serialize": (ctypes.c_long, [ctypes.POINTER(PlonkProofStruct), ctypes.c_char_p, ctypes.c_size_t]),
+    "jf_keccak256": (None, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]),
+    "jf_transcript_new": (ctypes.c_void_p, [ctypes.c_int, ctypes.c_char_p]),
+    "jf_transcript_free": (None, [ctypes.c_void_p]),
+    "jf_transcript_append": (None, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]),
+    "jf_transcript_challenge": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, c_u64p]),
 }
 
 _lib = None

@@ -1,0 +1,1083 @@
+// plonk.cu -- device-resident TurboPlonk prover rounds around the MSM / NTT kernels
+// (the "next" rows either side of the hot path).
+//
+// Replaces, for one TurboPlonk instance with 5 wire types and no Plookup:
+//   PlonkKzgSnark::preprocess              plonk/src/proof_system/snark.rs:529-611
+//   PlonkKzgSnark::batch_prove_internal    plonk/src/proof_system/snark.rs:201-469
+//   Prover::run_1st..3rd_round, compute_evaluations, compute_(non_)quotient_component_for_lin_poly,
+//   compute_opening_proofs, mask_polynomial, split_quotient_polynomial, compute_quotient_polynomial
+//                                          plonk/src/proof_system/prover.rs:72-87,125-141,192-235,302-419,463-673,902-1034
+//   PlonkCircuit::compute_{wire,pub_input,prod_permutation,selector,extended_permutation}_polynomial(s)
+//                                          relation/src/constraint_system.rs:1162-1259
+// Circuit construction (gates, variables, the wire permutation) stays with the caller: it hands over
+// the selector columns, the extended permutation sigma*(i) = k_w * g^j, the wire -> variable map and,
+// per proof, the witness.  Everything between the witness upload and the 13 commitments + 10
+// evaluations of the proof stays in HBM; the host only runs the Fiat-Shamir transcript (5 round
+// trips of a few hundred bytes).
+//
+// Polynomial algebra on the device (all exact field arithmetic, so results are bit-identical to the
+// reference's serial loops whatever the evaluation order):
+//   grand product      z = prefix-product(a) * suffix-product(b) / prod(b): two parallel scans and ONE
+//                      inversion instead of n divisions (constraint_system.rs:1197-1223)
+//   quotient           one fused pointwise kernel over the 8n coset (prover.rs:605-663,677-759),
+//                      1/(n (x - 1)) from a table built once per proving key
+//   evaluation         blocked Horner + tree sum (prover.rs:216-235)
+//   lin. combination   one kernel over up to 32 (scalar, polynomial) pairs (prover.rs:339-360,490-502,963-1034)
+//   p / (X - z)        q_j = z^-(j+1) * sum_{i>j} p_i z^i: power scaling + one additive suffix scan
+//                      (prover.rs:504-506; ark-poly's `/` drops the remainder)
+#include <string.h>
+#include <algorithm>
+#include "common.cuh"
+#include "ec.cuh"
+#include "transcript.hpp"
+
+namespace jf {
+
+static constexpr int NW = 5;      // wire types (GATE_WIDTH + 1)
+static constexpr int NSEL = 13;   // q_lc[4], q_mul[2], q_hash[4], q_o, q_c, q_ecc
+static constexpr int NBLIND = 17; // 5 x 2 (wires) + 3 (z) + 4 (split quotient)
+static constexpr int PAD = 8;     // room above n for the masking coefficients
+
+template <class F> __device__ __forceinline__ Fp<F> ldf(const Fp<F> *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = q[0], b = q[1];
+    Fp<F> r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+template <class F> __device__ __forceinline__ void stf(Fp<F> *p, const Fp<F> &r) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+// a^e for a small exponent (only the set bits of e are walked)
+template <class F> __host__ __device__ __forceinline__ Fp<F> pow_small(const Fp<F> &a, uint64_t e) {
+    Fp<F> acc = Fp<F>::one();
+    int top = 63;
+    while (top >= 0 && !((e >> top) & 1)) top--;
+    for (int i = top; i >= 0; i--) {
+        acc = Fp<F>::sqr(acc);
+        if ((e >> i) & 1) acc = Fp<F>::mul(acc, a);
+    }
+    return acc;
+}
+
+// ---- parallel scans over field elements ------------------------------------------------------
+struct OpMul {
+    template <class T> static __device__ __forceinline__ T apply(const T &a, const T &b) { return T::mul(a, b); }
+    template <class T> static __device__ __forceinline__ T identity() { return T::one(); }
+};
+struct OpAdd {
+    template <class T> static __device__ __forceinline__ T apply(const T &a, const T &b) { return T::add(a, b); }
+    template <class T> static __device__ __forceinline__ T identity() { return T::zero(); }
+};
+static constexpr int FS_T = 256, FS_I = 4, FS_TILE = FS_T * FS_I;
+
+template <class F> __device__ __forceinline__ Fp<F> shfl_up_f(const Fp<F> &x, int d) {
+    Fp<F> r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_up_sync(0xffffffffu, x.v[i], d);
+    return r;
+}
+
+// Inclusive scan of one tile per CTA (logical order reversed when REV); totals[b] = tile sum.
+template <class F, class Op, bool REV>
+__global__ void __launch_bounds__(FS_T) fscan_local_kernel(const Fp<F> *in, Fp<F> *out, Fp<F> *totals, size_t n) {
+    using E = Fp<F>;
+    __shared__ E wt[FS_T / 32];
+    const size_t base = (size_t)blockIdx.x * FS_TILE + (size_t)threadIdx.x * FS_I;
+    E v[FS_I];
+#pragma unroll
+    for (int k = 0; k < FS_I; k++) {
+        const size_t L = base + k;
+        v[k] = L < n ? ldf(in + (REV ? n - 1 - L : L)) : Op::template identity<E>();
+        if (k) v[k] = Op::apply(v[k - 1], v[k]);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    E tot = v[FS_I - 1];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        E o = shfl_up_f(tot, d);
+        if (lane >= d) tot = Op::apply(o, tot);
+    }
+    if (lane == 31) wt[warp] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        E acc = Op::template identity<E>();
+        for (int w = 0; w < FS_T / 32; w++) {
+            E t = wt[w];
+            wt[w] = acc;
+            acc = Op::apply(acc, t);
+        }
+        if (totals) stf(totals + blockIdx.x, acc);
+    }
+    __syncthreads();
+    E excl = shfl_up_f(tot, 1);
+    if (lane == 0) excl = Op::template identity<E>();
+    excl = Op::apply(wt[warp], excl);
+#pragma unroll
+    for (int k = 0; k < FS_I; k++) {
+        const size_t L = base + k;
+        if (L < n) stf(out + (REV ? n - 1 - L : L), Op::apply(excl, v[k]));
+    }
+}
+
+// out[L] = op(scanned_totals[tile(L) - 1], out[L]) for every tile but the first
+template <class F, class Op, bool REV>
+__global__ void fscan_apply_kernel(Fp<F> *out, const Fp<F> *scanned_totals, size_t n) {
+    const size_t L = (size_t)blockIdx.x * blockDim.x + threadIdx.x + FS_TILE;
+    if (L >= n) return;
+    const size_t tile = L / FS_TILE;
+    Fp<F> *p = out + (REV ? n - 1 - L : L);
+    stf(p, Op::apply(ldf(scanned_totals + tile - 1), ldf(p)));
+}
+
+// Inclusive scan (forward, or reverse = suffix scan) of n elements; `tmp` holds >= n/512 + 64 elements.
+template <class F, class Op, bool REV>
+static int fscan(jf_ctx *ctx, const Fp<F> *in, Fp<F> *out, size_t n, Fp<F> *tmp) {
+    if (n == 0) return JF_OK;
+    const size_t tiles = (n + FS_TILE - 1) / FS_TILE;
+    if (tiles == 1) {
+        JF_LAUNCH(ctx, "fscan_local", fscan_local_kernel<F, Op, REV><<<1, FS_T, 0, ctx->stream>>>(in, out, nullptr, n));
+        return JF_OK;
+    }
+    JF_LAUNCH(ctx, "fscan_local", fscan_local_kernel<F, Op, REV><<<(unsigned)tiles, FS_T, 0, ctx->stream>>>(in, out, tmp, n));
+    // totals are in logical tile order: always a forward scan
+    JF_TRY((fscan<F, Op, false>(ctx, tmp, tmp, tiles, tmp + tiles)));
+    const size_t rest = n - FS_TILE;
+    JF_LAUNCH(ctx, "fscan_apply", fscan_apply_kernel<F, Op, REV><<<(unsigned)((rest + 255) / 256), 256, 0, ctx->stream>>>(out, tmp, n));
+    return JF_OK;
+}
+
+// ---- small element-wise kernels ------------------------------------------------------------------
+// wire value columns: wv[j*n + i] = witness[wire_vars[j*n + i]]; pi[i] = witness of the io gates' output wire
+template <class F>
+__global__ void gather_wires_kernel(const Fp<F> *witness, const uint32_t *wire_vars, size_t total, Fp<F> *wv) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) stf(wv + i, ldf(witness + wire_vars[i]));
+}
+template <class F>
+__global__ void pub_input_kernel(const Fp<F> *witness, const uint32_t *wire_vars_out, const uint32_t *gate_ids, uint32_t num,
+                                 Fp<F> *pi) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < num) stf(pi + gate_ids[i], ldf(witness + wire_vars_out[gate_ids[i]]));
+}
+// mask_polynomial (prover.rs:463-486): poly += (b_0 + .. + b_hb X^hb) (X^n - 1); entries n.. are zero on entry
+template <class F> __global__ void blind_kernel(Fp<F> *poly, size_t n, const Fp<F> *b, int count) {
+    int i = threadIdx.x;
+    if (i >= count) return;
+    Fp<F> bi = ldf(b + i);
+    stf(poly + i, Fp<F>::sub(ldf(poly + i), bi));
+    stf(poly + n + i, bi);
+}
+// copy with row strides (vectors of `len` elements); rows beyond are untouched
+template <class F>
+__global__ void copy_rows_kernel(const Fp<F> *src, size_t src_stride, Fp<F> *dst, size_t dst_stride, size_t len, size_t zero_to) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t row = blockIdx.y;
+    if (i < len) stf(dst + row * dst_stride + i, ldf(src + row * src_stride + i));
+    else if (i < zero_to) stf(dst + row * dst_stride + i, Fp<F>::zero());
+}
+
+// ---- round 2: numerators / denominators of the grand product ---------------------------------------
+template <class F> struct PermArgs {
+    const Fp<F> *wv;       // NW x n wire values
+    const Fp<F> *sigma;    // NW x n extended permutation values
+    Fp<F> beta_k[NW];      // beta * k_j
+    Fp<F> beta, gamma, omega;
+    Fp<F> *a, *b;          // n each
+    uint32_t n;
+};
+static constexpr int PERM_I = 8;
+template <class F> __global__ void perm_ab_kernel(const __grid_constant__ PermArgs<F> p) {
+    using E = Fp<F>;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t start = (uint64_t)t * PERM_I;
+    if (start >= p.n) return;
+    E x = pow_small(p.omega, start);
+    for (int k = 0; k < PERM_I; k++) {
+        const uint64_t j = start + k;
+        if (j >= p.n) break;
+        E a = E::one(), b = E::one();
+        if (j < p.n - 1) {
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                E tmp = E::add(ldf(p.wv + (size_t)w * p.n + j), p.gamma);
+                a = E::mul(a, E::add(tmp, E::mul(p.beta_k[w], x)));
+                b = E::mul(b, E::add(tmp, E::mul(p.beta, ldf(p.sigma + (size_t)w * p.n + j))));
+            }
+        }
+        stf(p.a + j, a);
+        stf(p.b + j, b);
+        x = E::mul(x, p.omega);
+    }
+}
+template <class F> __global__ void inv_one_kernel(const Fp<F> *in, Fp<F> *out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) stf(out, Fp<F>::inv(ldf(in)));
+}
+// z[i] = (prod_{j<i} a_j) * (prod_{j>=i} b_j) / prod(b)
+template <class F>
+__global__ void z_combine_kernel(const Fp<F> *pa, const Fp<F> *sb, const Fp<F> *binv, Fp<F> *z, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp<F> v = Fp<F>::mul(ldf(sb + i), ldf(binv));
+    if (i) v = Fp<F>::mul(v, ldf(pa + i - 1));
+    stf(z + i, v);
+}
+// batch inversion from prefix / suffix products: out[i] = P[i-1] * S[i+1] / total
+template <class F>
+__global__ void inv_combine_kernel(const Fp<F> *pp, const Fp<F> *sp, const Fp<F> *tinv, Fp<F> *out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp<F> v = ldf(tinv);
+    if (i) v = Fp<F>::mul(v, ldf(pp + i - 1));
+    if (i + 1 < n) v = Fp<F>::mul(v, ldf(sp + i + 1));
+    stf(out + i, v);
+}
+// d[i] = scale * (x_i - 1),  x_i = hi[i >> lo_bits] * lo[i & mask]
+template <class F>
+__global__ void xm1_kernel(const Fp<F> *lo, const Fp<F> *hi, int lo_bits, Fp<F> scale, Fp<F> *d, size_t m) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    Fp<F> x = Fp<F>::mul(ldf(lo + (i & (((size_t)1 << lo_bits) - 1))), ldf(hi + (i >> lo_bits)));
+    stf(d + i, Fp<F>::mul(scale, Fp<F>::sub(x, Fp<F>::one())));
+}
+// table[i] = scale * base^(i * step)
+template <class F> __global__ void pow_tab_kernel(Fp<F> *table, Fp<F> base, Fp<F> scale, uint64_t step, uint32_t count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) stf(table + i, Fp<F>::mul(scale, pow_small(base, (uint64_t)i * step)));
+}
+
+// ---- round 3: the quotient on the 8n coset -----------------------------------------------------------
+template <class F> struct QuotArgs {
+    const Fp<F> *sel;    // NSEL x m coset evaluations
+    const Fp<F> *sig;    // NW x m
+    const Fp<F> *w;      // NW x m
+    const Fp<F> *z, *pi; // m each
+    const Fp<F> *inv_nx1;  // 1 / (n (x_i - 1))
+    const Fp<F> *x_lo, *x_hi;
+    int lo_bits;
+    Fp<F> beta_k[NW], beta, gamma, alpha, alpha2;
+    Fp<F> zh_inv[8];
+    Fp<F> *out;
+    uint32_t m, ratio;
+};
+template <class F> __device__ __forceinline__ Fp<F> pow5(const Fp<F> &x) {
+    Fp<F> x2 = Fp<F>::sqr(x);
+    return Fp<F>::mul(x, Fp<F>::sqr(x2));
+}
+template <class F> __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ QuotArgs<F> q) {
+    using E = Fp<F>;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q.m) return;
+    const size_t m = q.m;
+    E w[NW];
+#pragma unroll
+    for (int j = 0; j < NW; j++) w[j] = ldf(q.w + j * m + i);
+    auto S = [&](int s) { return ldf(q.sel + s * m + i); };
+    // circuit part (prover.rs:696-708); selector order q_lc 0-3, q_mul 4-5, q_hash 6-9, q_o 10, q_c 11, q_ecc 12
+    E w01 = E::mul(w[0], w[1]), w23 = E::mul(w[2], w[3]);
+    E t = E::add(S(11), ldf(q.pi + i));
+    t = E::add(t, E::mul(S(0), w[0]));
+    t = E::add(t, E::mul(S(1), w[1]));
+    t = E::add(t, E::mul(S(2), w[2]));
+    t = E::add(t, E::mul(S(3), w[3]));
+    t = E::add(t, E::mul(S(4), w01));
+    t = E::add(t, E::mul(S(5), w23));
+    t = E::add(t, E::mul(S(12), E::mul(E::mul(w01, w23), w[4])));
+    t = E::add(t, E::mul(S(6), pow5(w[0])));
+    t = E::add(t, E::mul(S(7), pow5(w[1])));
+    t = E::add(t, E::mul(S(8), pow5(w[2])));
+    t = E::add(t, E::mul(S(9), pow5(w[3])));
+    t = E::sub(t, E::mul(S(10), w[4]));
+    // copy constraints (prover.rs:743-756)
+    const E x = E::mul(ldf(q.x_lo + (i & ((1u << q.lo_bits) - 1))), ldf(q.x_hi + (i >> q.lo_bits)));
+    const E zx = ldf(q.z + i);
+    uint32_t inext = i + q.ratio;
+    if (inext >= q.m) inext -= q.m;
+    E r1 = zx, r2 = ldf(q.z + inext);
+#pragma unroll
+    for (int j = 0; j < NW; j++) {
+        E wg = E::add(w[j], q.gamma);
+        r1 = E::mul(r1, E::add(wg, E::mul(q.beta_k[j], x)));
+        r2 = E::mul(r2, E::add(wg, E::mul(q.beta, ldf(q.sig + j * m + i))));
+    }
+    t = E::add(t, E::mul(q.alpha, E::sub(r1, r2)));
+    E t2 = E::mul(E::mul(q.alpha2, E::sub(zx, E::one())), ldf(q.inv_nx1 + i));
+    stf(q.out + i, E::add(E::mul(t, q.zh_inv[i % q.ratio]), t2));
+}
+// WrongQuotientPolyDegree (prover.rs:916-919): coefficient `deg` must be non-zero, all above zero
+template <class F> __global__ void degree_check_kernel(const Fp<F> *c, size_t deg, size_t m, int *err) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x + deg;
+    if (i >= m) return;
+    const bool z = ldf(c + i).is_zero();
+    if ((i == deg) == z) *err = JF_ERR_QUOTIENT_DEGREE;
+}
+// split_quotient_polynomial (prover.rs:902-960): part i = t[i (n+2) .. ] with the masking edits
+template <class F>
+__global__ void split_kernel(const Fp<F> *t, size_t n, size_t total_len, const Fp<F> *b, Fp<F> *parts, size_t stride) {
+    const int part = blockIdx.y;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t start = (size_t)part * (n + 2);
+    const size_t len = part < NW - 1 ? n + 2 : total_len - start;
+    Fp<F> v = Fp<F>::zero();
+    if (i < len) v = ldf(t + start + i);
+    if (i == 0 && part > 0) v = Fp<F>::sub(v, ldf(b + part - 1));
+    if (i == n + 2 && part < NW - 1) v = ldf(b + part);
+    if (i < stride) stf(parts + part * stride + i, v);
+}
+
+// ---- round 4: evaluation -------------------------------------------------------------------------------
+static constexpr int EV_T = 256, EV_I = 8;
+template <class F> __global__ void __launch_bounds__(EV_T) eval_partial_kernel(const Fp<F> *c, size_t len, Fp<F> x, Fp<F> *partials) {
+    using E = Fp<F>;
+    __shared__ E sh[EV_T];
+    const size_t start = ((size_t)blockIdx.x * EV_T + threadIdx.x) * EV_I;
+    E acc = E::zero();
+    if (start < len) {
+        const int cnt = (int)(len - start < (size_t)EV_I ? len - start : EV_I);
+        for (int k = cnt - 1; k >= 0; k--) acc = E::add(E::mul(acc, x), ldf(c + start + k));
+        acc = E::mul(acc, pow_small(x, start));
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = EV_T / 2; d >= 1; d >>= 1) {
+        if ((int)threadIdx.x < d) sh[threadIdx.x] = E::add(sh[threadIdx.x], sh[threadIdx.x + d]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) stf(partials + blockIdx.x, sh[0]);
+}
+template <class F> __global__ void __launch_bounds__(EV_T) sum_kernel(const Fp<F> *in, size_t count, Fp<F> *out) {
+    using E = Fp<F>;
+    __shared__ E sh[EV_T];
+    E acc = E::zero();
+    for (size_t i = threadIdx.x; i < count; i += EV_T) acc = E::add(acc, ldf(in + i));
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = EV_T / 2; d >= 1; d >>= 1) {
+        if ((int)threadIdx.x < d) sh[threadIdx.x] = E::add(sh[threadIdx.x], sh[threadIdx.x + d]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) stf(out, sh[0]);
+}
+
+// ---- round 5: linear combination, division by a linear factor ------------------------------------------
+static constexpr int LC_MAX = 32;
+template <class F> struct LinArgs {
+    const Fp<F> *p[LC_MAX];
+    uint32_t len[LC_MAX];
+    Fp<F> s[LC_MAX];
+    int count;
+    Fp<F> *out;
+    uint32_t out_len;
+};
+template <class F> __global__ void lincomb_kernel(const __grid_constant__ LinArgs<F> a) {
+    using E = Fp<F>;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.out_len) return;
+    E acc = E::zero();
+    for (int k = 0; k < a.count; k++)
+        if (i < a.len[k]) acc = E::add(acc, E::mul(a.s[k], ldf(a.p[k] + i)));
+    stf(a.out + i, acc);
+}
+// out[j] = in[j + shift] * base^(j + e0), j < len
+static constexpr int MP_I = 8;
+template <class F>
+__global__ void mulpow_kernel(const Fp<F> *in, Fp<F> *out, size_t len, uint32_t shift, uint32_t e0, Fp<F> base) {
+    using E = Fp<F>;
+    const size_t start = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * MP_I;
+    if (start >= len) return;
+    E pw = pow_small(base, start + e0);
+    for (int k = 0; k < MP_I && start + k < len; k++) {
+        stf(out + start + k, E::mul(ldf(in + start + k + shift), pw));
+        pw = E::mul(pw, base);
+    }
+}
+
+}  // namespace jf
+
+// ================================================================================================
+// host side
+// ================================================================================================
+using namespace jf;
+
+struct jf_plonk_pk {
+    int curve = JF_BN254;
+    const jf_srs *srs = nullptr;
+    unsigned log_n = 0, log_m = 0;
+    size_t n = 0, m = 0, np = 0;  // np = n + PAD: stride of the n-sized polynomial buffers
+    size_t num_vars = 0;
+    uint32_t num_inputs = 0;
+    int cache_coset = 0;
+    std::vector<uint32_t> pub_vars;  // variable index of every public input, in io-gate order
+    // device, persistent
+    void *d_sel = nullptr, *d_sig = nullptr, *d_sig_evals = nullptr;  // NSEL x n, NW x n coefficients; NW x n values
+    uint32_t *d_wire_vars = nullptr, *d_gate_ids = nullptr;
+    void *d_xlo = nullptr, *d_xhi = nullptr, *d_inv_nx1 = nullptr;
+    void *d_cached = nullptr;  // (NSEL + NW) x m coset evaluations when cache_coset
+    int lo_bits = 0;
+    // device, per-proof workspace
+    void *d_wit = nullptr, *d_bl = nullptr, *d_wv = nullptr, *d_w = nullptr /* (NW+1) x np: wires + PI */, *d_z = nullptr;
+    void *d_a = nullptr, *d_b = nullptr, *d_tmp = nullptr, *d_e = nullptr, *d_q = nullptr, *d_split = nullptr;
+    void *d_bp = nullptr, *d_t = nullptr, *d_s = nullptr, *d_wz = nullptr, *d_small = nullptr, *d_res = nullptr;
+    // host constants (Montgomery)
+    uint32_t k[NW][8], omega_n[8], omega_m[8], gen[8], zh_inv[8][8];
+    uint64_t gen_limbs[4];
+    // verifying-key commitments (affine Montgomery x || y) and their transcript serialisation
+    std::vector<uint64_t> vk_xy;
+    std::vector<int> vk_inf;
+    std::vector<uint8_t> vk_transcript_prefix;  // everything append_vk_and_pub_input adds before the public inputs
+    std::vector<void *> allocs;
+};
+
+namespace jf {
+
+template <class C> struct HostCurve {
+    using Fq = typename C::Fq;
+    using Fr = typename C::Fr;
+    using Er = Fp<Fr>;
+    using Eq = Fp<Fq>;
+    static constexpr int L = Fq::N / 2;  // u64 limbs per base-field element
+
+    static Er fr_from_limbs(const uint64_t *l) {
+        Er r;
+        for (int i = 0; i < 4; i++) {
+            r.v[2 * i] = (uint32_t)l[i];
+            r.v[2 * i + 1] = (uint32_t)(l[i] >> 32);
+        }
+        return r;
+    }
+    static void fr_to_limbs(const Er &a, uint64_t *l) {
+        for (int i = 0; i < 4; i++) l[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+    }
+    // canonical little-endian bytes of a Montgomery-form element (`serialize_compressed` of a field element)
+    static void fr_bytes(const Er &a, uint8_t out[32]) {
+        Er c = Er::from_mont(a);
+        memcpy(out, c.v, 32);
+    }
+    // `from_le_bytes_mod_order` of up to 64 bytes -> Montgomery form
+    static Er fr_from_le_bytes_mod_order(const uint8_t *b, size_t n) {
+        uint8_t buf[64] = {0};
+        memcpy(buf, b, n);
+        Er chunk[2];
+        for (int c = 0; c < 2; c++) {
+            memcpy(chunk[c].v, buf + 32 * c, 32);
+            for (int it = 0; it < 8; it++) {  // 2^256 < 8 p for every field here
+                uint32_t t[8], borrow;
+                chain_sub_p<Fr>(t, chunk[c].v, borrow);
+                if (borrow) break;
+                memcpy(chunk[c].v, t, 32);
+            }
+            chunk[c] = Er::to_mont(chunk[c]);
+        }
+        // value = lo + hi * 2^256; the element 2^256 has Montgomery form R^2 mod p
+        return Er::add(chunk[0], Er::mul(chunk[1], Er::r_squared()));
+    }
+    // ark-serialize 0.4 compressed SW point: x LE, bit 7 of the last byte = y > -y, bit 6 = infinity
+    static void g1_bytes(const uint64_t *xy, int inf, uint8_t *out) {
+        const int nb = 8 * L;
+        memset(out, 0, nb);
+        if (inf) {
+            out[nb - 1] |= 0x40;
+            return;
+        }
+        Eq x, y;
+        memcpy(x.v, xy, nb);
+        memcpy(y.v, xy + L, nb);
+        Eq xc = Eq::from_mont(x), yc = Eq::from_mont(y), ny = Eq::from_mont(Eq::neg(y));
+        memcpy(out, xc.v, nb);
+        bool greater = false;
+        for (int i = Fq::N - 1; i >= 0; i--) {
+            if (yc.v[i] != ny.v[i]) {
+                greater = yc.v[i] > ny.v[i];
+                break;
+            }
+        }
+        if (greater) out[nb - 1] |= 0x80;
+    }
+};
+
+static int dalloc(jf_ctx *ctx, jf_plonk_pk *pk, size_t bytes, void **out) {
+    JF_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 64));
+    pk->allocs.push_back(*out);
+    return JF_OK;
+}
+
+template <class C> struct Plonk {
+    using Fr = typename C::Fr;
+    using Fq = typename C::Fq;
+    using E = Fp<Fr>;
+    using H = HostCurve<C>;
+    static constexpr int L = H::L;
+    static constexpr size_t PT = sizeof(XYZZ<Fq>);
+
+    static E kf(const jf_plonk_pk *pk, int j) {
+        E r;
+        memcpy(r.v, pk->k[j], 32);
+        return r;
+    }
+    static E lf(const uint32_t *w) {
+        E r;
+        memcpy(r.v, w, 32);
+        return r;
+    }
+
+    // d_out[n.. ] untouched; in-place inverse NTT over the size-n domain of `batch` vectors `stride` apart
+    static int intt_n(jf_ctx *ctx, const jf_plonk_pk *pk, void *d, size_t batch, size_t stride) {
+        return ntt_run(ctx, C::FR_ID, d, d, pk->n, pk->log_n, 1, nullptr, batch, stride);
+    }
+
+    // commitments of `count` device polynomials (Montgomery coefficients) -> d_res[slot..]
+    static int commit_dev(jf_ctx *ctx, const jf_plonk_pk *pk, const void *d_poly, size_t len, int slot) {
+        return msm_run(ctx, pk->srs, 0, d_poly, len, 1, (char *)pk->d_res + PT * slot);
+    }
+    // bring `count` XYZZ results back and normalise (into_affine)
+    static int fetch_commits(jf_ctx *ctx, const jf_plonk_pk *pk, int slot, int count, uint64_t *xy, int *inf) {
+        void *h;
+        JF_TRY(pinned(ctx, PT * count + 64, &h));
+        JF_CUDA(ctx, cudaMemcpyAsync(h, (char *)pk->d_res + PT * slot, PT * count, cudaMemcpyDeviceToHost, ctx->stream));
+        int herr[2] = {0, 0};
+        JF_CUDA(ctx, cudaMemcpyAsync(herr, ctx->d_err, sizeof herr, cudaMemcpyDeviceToHost, ctx->stream));
+        JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (herr[0] || herr[1]) {
+            cudaMemsetAsync(ctx->d_err, 0, sizeof herr, ctx->stream);
+            if (herr[1]) return fail(ctx, herr[1], "prove: WrongQuotientPolyDegree (the witness does not satisfy the circuit)");
+            return fail(ctx, herr[0], "prove: a scalar is not below the group order");
+        }
+        for (int i = 0; i < count; i++)
+            JF_TRY(msm_finish_host(ctx, pk->curve, (const uint64_t *)((const char *)h + PT * i), 1, xy + (size_t)2 * L * i, inf + i));
+        return JF_OK;
+    }
+
+    static int eval_dev(jf_ctx *ctx, const jf_plonk_pk *pk, const E *poly, size_t len, const E &x, E *d_out) {
+        const size_t per = (size_t)EV_T * EV_I;
+        const unsigned blocks = (unsigned)((len + per - 1) / per);
+        E *partials = (E *)pk->d_tmp;
+        JF_LAUNCH(ctx, "eval_partial", eval_partial_kernel<Fr><<<blocks ? blocks : 1, EV_T, 0, ctx->stream>>>(poly, len, x, partials));
+        JF_LAUNCH(ctx, "eval_sum", sum_kernel<Fr><<<1, EV_T, 0, ctx->stream>>>(partials, blocks ? blocks : 1, d_out));
+        return JF_OK;
+    }
+
+    // out (len-1 coefficients) = p / (X - z), remainder dropped
+    static int div_linear_dev(jf_ctx *ctx, const jf_plonk_pk *pk, const E *p, size_t len, const E &z, E *out) {
+        if (len < 2) return fail(ctx, JF_ERR_INVALID_ARG, "prove: degenerate opening polynomial");
+        if (z.is_zero()) return fail(ctx, JF_ERR_INVALID_ARG, "prove: zero evaluation point");
+        E *t = (E *)pk->d_t, *s = (E *)pk->d_s;
+        const unsigned b1 = (unsigned)((len + 256 * MP_I - 1) / (256 * MP_I));
+        JF_LAUNCH(ctx, "mulpow", mulpow_kernel<Fr><<<b1, 256, 0, ctx->stream>>>(p, t, len, 0, 0, z));
+        JF_TRY((fscan<Fr, OpAdd, true>(ctx, t, s, len, (E *)pk->d_tmp)));
+        const E zinv = E::inv(z);
+        JF_LAUNCH(ctx, "mulpow", mulpow_kernel<Fr><<<b1, 256, 0, ctx->stream>>>(s, out, len - 1, 1, 1, zinv));
+        return JF_OK;
+    }
+
+    static void tr_fr(Transcript &tr, const char *label, const E &a) {
+        uint8_t b[32];
+        H::fr_bytes(a, b);
+        tr.append_message(label, b, 32);
+    }
+    static void tr_g1(Transcript &tr, const char *label, const uint64_t *xy, int inf) {
+        uint8_t b[8 * L];
+        H::g1_bytes(xy, inf, b);
+        tr.append_message(label, b, 8 * L);
+    }
+    static E challenge(Transcript &tr, const char *label) {
+        uint8_t buf[64];
+        size_t n = tr.challenge_bytes(label, buf);
+        E c = H::fr_from_le_bytes_mod_order(buf, n);
+        uint8_t cb[32];
+        H::fr_bytes(c, cb);
+        tr.challenge_done(label, cb, 32);
+        return c;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    static int preprocess(jf_ctx *ctx, const jf_srs *srs, unsigned log_n, const uint64_t *selector_evals,
+                          const uint64_t *sigma_evals, const uint64_t *k, const uint32_t *wire_variables, size_t num_vars,
+                          const uint32_t *pub_gate_ids, size_t num_inputs, int flags, jf_plonk_pk **out) {
+        if (log_n < 3 || log_n + 3 > (unsigned)Fr::TWO_ADICITY || log_n > 26)
+            return fail(ctx, JF_ERR_DOMAIN_TOO_LARGE, "preprocess: unsupported domain size");
+        const size_t n = (size_t)1 << log_n, m = n * 8, np = n + PAD;
+        if (srs->n < n + 3) return fail(ctx, JF_ERR_INVALID_ARG, "preprocess: the commit key needs n + 3 points (srs_size = n + 2)");
+        jf_plonk_pk *pk = new jf_plonk_pk();
+        pk->curve = srs->curve;
+        pk->srs = srs;
+        pk->log_n = log_n;
+        pk->log_m = log_n + 3;
+        pk->n = n;
+        pk->m = m;
+        pk->np = np;
+        pk->num_vars = num_vars;
+        pk->num_inputs = (uint32_t)num_inputs;
+        pk->cache_coset = flags & 1;
+        int rc = preprocess_inner(ctx, pk, selector_evals, sigma_evals, k, wire_variables, pub_gate_ids);
+        if (rc != JF_OK) {
+            cudaStreamSynchronize(ctx->stream);
+            for (void *p : pk->allocs) cudaFree(p);
+            delete pk;
+            return rc;
+        }
+        *out = pk;
+        return JF_OK;
+    }
+
+    static int preprocess_inner(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *selector_evals, const uint64_t *sigma_evals,
+                                const uint64_t *k, const uint32_t *wire_variables, const uint32_t *pub_gate_ids) {
+        const size_t n = pk->n, m = pk->m, np = pk->np;
+        cudaStream_t st = ctx->stream;
+        for (size_t i = 0; i < (size_t)NW * n; i++)
+            if (wire_variables[i] >= pk->num_vars) return fail(ctx, JF_ERR_INVALID_ARG, "preprocess: wire variable out of range");
+        for (size_t i = 0; i < pk->num_inputs; i++) {
+            if (pub_gate_ids[i] >= n) return fail(ctx, JF_ERR_INVALID_ARG, "preprocess: io gate id out of range");
+            pk->pub_vars.push_back(wire_variables[(size_t)(NW - 1) * n + pub_gate_ids[i]]);
+        }
+        // ---- host constants ----
+        for (int j = 0; j < NW; j++) {
+            E kj = H::fr_from_limbs(k + 4 * j);
+            memcpy(pk->k[j], kj.v, 32);
+        }
+        E g = E::from_u32(Fr::GENERATOR);
+        memcpy(pk->gen, g.v, 32);
+        H::fr_to_limbs(g, pk->gen_limbs);
+        // two-adic root: GENERATOR^((p-1)/2^s), then squared down to the n- and m-th roots
+        uint32_t e[8];
+        Limbs<Fr>::p(e);
+        e[0] -= 1;
+        for (int s = 0; s < Fr::TWO_ADICITY; s++)
+            for (int i = 0; i < 8; i++) e[i] = (e[i] >> 1) | (i < 7 ? e[i + 1] << 31 : 0);
+        E root = E::pow(g, e, 8);
+        E wm = root;
+        for (unsigned s = 0; s < Fr::TWO_ADICITY - pk->log_m; s++) wm = E::sqr(wm);
+        E wn = wm;
+        for (int s = 0; s < 3; s++) wn = E::sqr(wn);
+        memcpy(pk->omega_m, wm.v, 32);
+        memcpy(pk->omega_n, wn.v, 32);
+        for (int r = 0; r < 8; r++) {  // 1 / ((g w_m^r)^n - 1)   (prover.rs:530-537)
+            E x = E::mul(g, pow_small(wm, r));
+            E zh = E::sub(pow_small(x, n), E::one());
+            zh = E::inv(zh);
+            memcpy(pk->zh_inv[r], zh.v, 32);
+        }
+        // ---- device buffers ----
+        const size_t fe = sizeof(E);
+        JF_TRY(dalloc(ctx, pk, fe * NSEL * n, &pk->d_sel));
+        JF_TRY(dalloc(ctx, pk, fe * NW * n, &pk->d_sig));
+        JF_TRY(dalloc(ctx, pk, fe * NW * n, &pk->d_sig_evals));
+        JF_TRY(dalloc(ctx, pk, sizeof(uint32_t) * NW * n, (void **)&pk->d_wire_vars));
+        JF_TRY(dalloc(ctx, pk, sizeof(uint32_t) * (pk->num_inputs + 1), (void **)&pk->d_gate_ids));
+        pk->lo_bits = (pk->log_m + 1) / 2;
+        const uint32_t lo_n = 1u << pk->lo_bits, hi_n = 1u << (pk->log_m - pk->lo_bits);
+        JF_TRY(dalloc(ctx, pk, fe * lo_n, &pk->d_xlo));
+        JF_TRY(dalloc(ctx, pk, fe * hi_n, &pk->d_xhi));
+        JF_TRY(dalloc(ctx, pk, fe * m, &pk->d_inv_nx1));
+        JF_TRY(dalloc(ctx, pk, fe * (pk->num_vars + 1), &pk->d_wit));
+        JF_TRY(dalloc(ctx, pk, fe * NBLIND, &pk->d_bl));
+        JF_TRY(dalloc(ctx, pk, fe * NW * n, &pk->d_wv));
+        JF_TRY(dalloc(ctx, pk, fe * (NW + 1) * np, &pk->d_w));
+        JF_TRY(dalloc(ctx, pk, fe * np, &pk->d_z));
+        JF_TRY(dalloc(ctx, pk, fe * m, &pk->d_a));   // scan inputs / outputs (m-sized for the inversion table)
+        JF_TRY(dalloc(ctx, pk, fe * m, &pk->d_b));
+        JF_TRY(dalloc(ctx, pk, fe * (m / 256 + 4096), &pk->d_tmp));
+        const int ne = pk->cache_coset ? NW + 2 : NSEL + 2 * NW + 2;
+        JF_TRY(dalloc(ctx, pk, fe * (size_t)ne * m, &pk->d_e));
+        JF_TRY(dalloc(ctx, pk, fe * m, &pk->d_q));
+        JF_TRY(dalloc(ctx, pk, fe * NW * np, &pk->d_split));
+        JF_TRY(dalloc(ctx, pk, fe * np, &pk->d_bp));
+        JF_TRY(dalloc(ctx, pk, fe * np, &pk->d_t));
+        JF_TRY(dalloc(ctx, pk, fe * np, &pk->d_s));
+        JF_TRY(dalloc(ctx, pk, fe * np, &pk->d_wz));
+        JF_TRY(dalloc(ctx, pk, fe * 64, &pk->d_small));
+        JF_TRY(dalloc(ctx, pk, PT * 32, &pk->d_res));
+        if (pk->cache_coset) JF_TRY(dalloc(ctx, pk, fe * (size_t)(NSEL + NW) * m, &pk->d_cached));
+        JF_CUDA(ctx, cudaMemcpyAsync(pk->d_sel, selector_evals, fe * NSEL * n, cudaMemcpyHostToDevice, st));
+        JF_CUDA(ctx, cudaMemcpyAsync(pk->d_sig, sigma_evals, fe * NW * n, cudaMemcpyHostToDevice, st));
+        JF_CUDA(ctx, cudaMemcpyAsync(pk->d_sig_evals, sigma_evals, fe * NW * n, cudaMemcpyHostToDevice, st));
+        JF_CUDA(ctx, cudaMemcpyAsync(pk->d_wire_vars, wire_variables, sizeof(uint32_t) * NW * n, cudaMemcpyHostToDevice, st));
+        if (pk->num_inputs)
+            JF_CUDA(ctx, cudaMemcpyAsync(pk->d_gate_ids, pub_gate_ids, sizeof(uint32_t) * pk->num_inputs, cudaMemcpyHostToDevice, st));
+        // x_i = g w_m^i tables and 1 / (n (x_i - 1)) by one batch inversion
+        JF_LAUNCH(ctx, "pow_tab", pow_tab_kernel<Fr><<<(lo_n + 127) / 128, 128, 0, st>>>((E *)pk->d_xlo, wm, E::one(), 1, lo_n));
+        JF_LAUNCH(ctx, "pow_tab", pow_tab_kernel<Fr><<<(hi_n + 127) / 128, 128, 0, st>>>((E *)pk->d_xhi, wm, g, lo_n, hi_n));
+        {
+            E nf = E::from_u32((uint32_t)n);
+            E *d = (E *)pk->d_q, *pp = (E *)pk->d_a, *sp = (E *)pk->d_b, *small = (E *)pk->d_small;
+            JF_LAUNCH(ctx, "xm1", xm1_kernel<Fr><<<(unsigned)((m + 255) / 256), 256, 0, st>>>((const E *)pk->d_xlo, (const E *)pk->d_xhi,
+                                                                                       pk->lo_bits, nf, d, m));
+            JF_TRY((fscan<Fr, OpMul, false>(ctx, d, pp, m, (E *)pk->d_tmp)));
+            JF_TRY((fscan<Fr, OpMul, true>(ctx, d, sp, m, (E *)pk->d_tmp)));
+            JF_LAUNCH(ctx, "inv_one", inv_one_kernel<Fr><<<1, 32, 0, st>>>(sp, small));
+            JF_LAUNCH(ctx, "inv_combine", inv_combine_kernel<Fr><<<(unsigned)((m + 255) / 256), 256, 0, st>>>(pp, sp, small, (E *)pk->d_inv_nx1, m));
+        }
+        // selector / sigma polynomials (ifft) and the 18 verifying-key commitments
+        JF_TRY(intt_n(ctx, pk, pk->d_sel, NSEL, n));
+        JF_TRY(intt_n(ctx, pk, pk->d_sig, NW, n));
+        for (int i = 0; i < NSEL; i++) JF_TRY(commit_dev(ctx, pk, (E *)pk->d_sel + (size_t)i * n, n, i));
+        for (int i = 0; i < NW; i++) JF_TRY(commit_dev(ctx, pk, (E *)pk->d_sig + (size_t)i * n, n, NSEL + i));
+        pk->vk_xy.resize((size_t)(NSEL + NW) * 2 * L);
+        pk->vk_inf.resize(NSEL + NW);
+        JF_TRY(fetch_commits(ctx, pk, 0, NSEL + NW, pk->vk_xy.data(), pk->vk_inf.data()));
+        if (pk->cache_coset) {
+            JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sel, n, n, NSEL, (E *)pk->d_cached));
+            JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sig, n, n, NW, (E *)pk->d_cached + (size_t)NSEL * m));
+        }
+        // transcript prefix (transcript/mod.rs:45-88): sizes, k, selector and sigma commitments
+        JF_CUDA(ctx, cudaStreamSynchronize(st));
+        return JF_OK;
+    }
+
+    // rows of coefficients (`len` valid, `stride` apart) -> rows of m coset evaluations in `dst`
+    static int coset_fft_rows(jf_ctx *ctx, const jf_plonk_pk *pk, const E *src, size_t stride, size_t len, int rows, E *dst) {
+        const size_t m = pk->m, in_len = pk->n + 3;
+        dim3 grid((unsigned)((in_len + 255) / 256), rows);
+        JF_LAUNCH(ctx, "copy_rows", copy_rows_kernel<Fr><<<grid, 256, 0, ctx->stream>>>(src, stride, dst, m, len, in_len));
+        for (int r = 0; r < rows; r += 5) {
+            const int b = std::min(5, rows - r);
+            JF_TRY(ntt_run(ctx, C::FR_ID, dst + (size_t)r * m, dst + (size_t)r * m, in_len, pk->log_m, 0, pk->gen_limbs, b, m));
+        }
+        return JF_OK;
+    }
+
+    static void append_vk_and_pub_input(Transcript &tr, const jf_plonk_pk *pk, const E *pub, size_t npub) {
+        const uint32_t bits = Fr::BITS;
+        const uint64_t dom = pk->n, nin = pk->num_inputs;
+        tr.append_message("field size in bits", (const uint8_t *)&bits, 4);
+        tr.append_message("domain size", (const uint8_t *)&dom, 8);
+        tr.append_message("input size", (const uint8_t *)&nin, 8);
+        for (int j = 0; j < NW; j++) tr_fr(tr, "wire subsets separators", kf(pk, j));
+        for (int i = 0; i < NSEL; i++) tr_g1(tr, "selector commitments", pk->vk_xy.data() + (size_t)2 * L * i, pk->vk_inf[i]);
+        for (int i = 0; i < NW; i++)
+            tr_g1(tr, "sigma commitments", pk->vk_xy.data() + (size_t)2 * L * (NSEL + i), pk->vk_inf[NSEL + i]);
+        for (size_t i = 0; i < npub; i++) tr_fr(tr, "public input", pub[i]);
+    }
+
+    // ------------------------------------------------------------------------------------------
+    static int prove(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *witness, const uint64_t *blinders, int kind,
+                     const uint8_t *extra, size_t extra_len, jf_plonk_proof *out) {
+        const size_t n = pk->n, m = pk->m, np = pk->np;
+        const size_t fe = sizeof(E);
+        cudaStream_t st = ctx->stream;
+        E *W = (E *)pk->d_w, *PI = W + (size_t)NW * np, *Z = (E *)pk->d_z, *WV = (E *)pk->d_wv;
+        E *bl = (E *)pk->d_bl, *small = (E *)pk->d_small;
+        memset(out, 0, sizeof *out);
+
+        JF_CUDA(ctx, cudaMemcpyAsync(pk->d_wit, witness, fe * pk->num_vars, cudaMemcpyHostToDevice, st));
+        JF_CUDA(ctx, cudaMemcpyAsync(bl, blinders, fe * NBLIND, cudaMemcpyHostToDevice, st));
+        Transcript tr(kind, "PlonkProof");
+        if (extra) tr.append_message("extra info", extra, extra_len);
+        {
+            std::vector<E> pub(pk->num_inputs);
+            for (size_t i = 0; i < pk->num_inputs; i++) pub[i] = H::fr_from_limbs(witness + 4 * (size_t)pk->pub_vars[i]);
+            append_vk_and_pub_input(tr, pk, pub.data(), pub.size());
+        }
+        // ---- round 1 (prover.rs:72-87): wire polynomials, masking, 5 commitments, PI polynomial ----
+        JF_LAUNCH(ctx, "gather_wires", gather_wires_kernel<Fr><<<(unsigned)((NW * n + 255) / 256), 256, 0, st>>>(
+            (const E *)pk->d_wit, pk->d_wire_vars, (size_t)NW * n, WV));
+        JF_CUDA(ctx, cudaMemsetAsync(W, 0, fe * (NW + 1) * np, st));
+        JF_CUDA(ctx, cudaMemcpy2DAsync(W, fe * np, WV, fe * n, fe * n, NW, cudaMemcpyDeviceToDevice, st));
+        if (pk->num_inputs)
+            JF_LAUNCH(ctx, "pub_input", pub_input_kernel<Fr><<<(pk->num_inputs + 127) / 128, 128, 0, st>>>(
+                (const E *)pk->d_wit, pk->d_wire_vars + (size_t)(NW - 1) * n, pk->d_gate_ids, pk->num_inputs, PI));
+        JF_TRY(intt_n(ctx, pk, W, NW + 1, np));
+        for (int j = 0; j < NW; j++) JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(W + (size_t)j * np, n, bl + 2 * j, 2));
+        for (int j = 0; j < NW; j++) JF_TRY(commit_dev(ctx, pk, W + (size_t)j * np, n + 2, j));
+        JF_TRY(fetch_commits(ctx, pk, 0, NW, out->wires_poly_comms, out->wires_inf));
+        for (int j = 0; j < NW; j++) tr_g1(tr, "witness_poly_comms", out->wires_poly_comms + 2 * L * j, out->wires_inf[j]);
+        (void)challenge(tr, "tau");  // squeezed even without Plookup (snark.rs:293)
+        // ---- round 2 (prover.rs:125-141; constraint_system.rs:1197-1223) ----
+        const E beta = challenge(tr, "beta"), gamma = challenge(tr, "gamma");
+        {
+            PermArgs<Fr> pa;
+            pa.wv = WV;
+            pa.sigma = (const E *)pk->d_sig_evals;
+            for (int j = 0; j < NW; j++) pa.beta_k[j] = E::mul(beta, kf(pk, j));
+            pa.beta = beta;
+            pa.gamma = gamma;
+            pa.omega = lf(pk->omega_n);
+            pa.a = (E *)pk->d_a;
+            pa.b = (E *)pk->d_b;
+            pa.n = (uint32_t)n;
+            const unsigned threads = (unsigned)((n + PERM_I - 1) / PERM_I);
+            JF_LAUNCH(ctx, "perm_ab", perm_ab_kernel<Fr><<<(threads + 127) / 128, 128, 0, st>>>(pa));
+            E *PA = (E *)pk->d_t, *SB = (E *)pk->d_s;
+            JF_TRY((fscan<Fr, OpMul, false>(ctx, pa.a, PA, n, (E *)pk->d_tmp)));
+            JF_TRY((fscan<Fr, OpMul, true>(ctx, pa.b, SB, n, (E *)pk->d_tmp)));
+            JF_LAUNCH(ctx, "inv_one", inv_one_kernel<Fr><<<1, 32, 0, st>>>(SB, small));
+            JF_CUDA(ctx, cudaMemsetAsync(Z, 0, fe * np, st));
+            JF_LAUNCH(ctx, "z_combine", z_combine_kernel<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(PA, SB, small, Z, (uint32_t)n));
+            JF_TRY(intt_n(ctx, pk, Z, 1, np));
+            JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(Z, n, bl + 10, 3));
+            JF_TRY(commit_dev(ctx, pk, Z, n + 3, 0));
+            JF_TRY(fetch_commits(ctx, pk, 0, 1, out->prod_perm_poly_comm, &out->prod_perm_inf));
+            tr_g1(tr, "perm_poly_comms", out->prod_perm_poly_comm, out->prod_perm_inf);
+        }
+        // ---- round 3 (prover.rs:192-209, 512-673, 902-960) ----
+        const E alpha = challenge(tr, "alpha");
+        {
+            E *Ev = (E *)pk->d_e;
+            const E *sel_c, *sig_c;
+            E *w_c, *z_c, *pi_c;
+            if (pk->cache_coset) {
+                sel_c = (const E *)pk->d_cached;
+                sig_c = sel_c + (size_t)NSEL * m;
+                w_c = Ev;
+            } else {
+                JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sel, n, n, NSEL, Ev));
+                JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sig, n, n, NW, Ev + (size_t)NSEL * m));
+                sel_c = Ev;
+                sig_c = Ev + (size_t)NSEL * m;
+                w_c = Ev + (size_t)(NSEL + NW) * m;
+            }
+            z_c = w_c + (size_t)NW * m;
+            pi_c = z_c + m;
+            JF_TRY(coset_fft_rows(ctx, pk, W, np, n + 2, NW, w_c));
+            JF_TRY(coset_fft_rows(ctx, pk, Z, np, n + 3, 1, z_c));
+            JF_TRY(coset_fft_rows(ctx, pk, PI, np, n, 1, pi_c));
+            QuotArgs<Fr> q;
+            q.sel = sel_c;
+            q.sig = sig_c;
+            q.w = w_c;
+            q.z = z_c;
+            q.pi = pi_c;
+            q.inv_nx1 = (const E *)pk->d_inv_nx1;
+            q.x_lo = (const E *)pk->d_xlo;
+            q.x_hi = (const E *)pk->d_xhi;
+            q.lo_bits = pk->lo_bits;
+            for (int j = 0; j < NW; j++) q.beta_k[j] = E::mul(beta, kf(pk, j));
+            q.beta = beta;
+            q.gamma = gamma;
+            q.alpha = alpha;
+            q.alpha2 = E::sqr(alpha);
+            for (int r = 0; r < 8; r++) q.zh_inv[r] = lf(pk->zh_inv[r]);
+            q.out = (E *)pk->d_q;
+            q.m = (uint32_t)m;
+            q.ratio = 8;
+            JF_LAUNCH(ctx, "quotient", quotient_kernel<Fr><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(q));
+            JF_TRY(ntt_run(ctx, C::FR_ID, pk->d_q, pk->d_q, m, pk->log_m, 1, pk->gen_limbs, 1, m));
+            const size_t deg = NW * (n + 1) + 2;  // quotient_polynomial_degree (prover.rs:1126-1128)
+            JF_LAUNCH(ctx, "degree_check", degree_check_kernel<Fr><<<(unsigned)((m - deg + 255) / 256), 256, 0, st>>>(
+                (const E *)pk->d_q, deg, m, ctx->d_err + 1));
+            dim3 grid((unsigned)((np + 255) / 256), NW);
+            JF_LAUNCH(ctx, "split", split_kernel<Fr><<<grid, 256, 0, st>>>((const E *)pk->d_q, n, deg + 1, bl + 13, (E *)pk->d_split, np));
+            for (int i = 0; i < NW; i++) {
+                const size_t len = i < NW - 1 ? n + 3 : deg + 1 - (size_t)(NW - 1) * (n + 2);
+                JF_TRY(commit_dev(ctx, pk, (E *)pk->d_split + (size_t)i * np, len, i));
+            }
+            JF_TRY(fetch_commits(ctx, pk, 0, NW, out->split_quot_poly_comms, out->split_inf));
+            for (int i = 0; i < NW; i++) tr_g1(tr, "quot_poly_comms", out->split_quot_poly_comms + 2 * L * i, out->split_inf[i]);
+        }
+        // ---- round 4 (prover.rs:216-235) ----
+        const E zeta = challenge(tr, "zeta");
+        const E omega = lf(pk->omega_n);
+        const E zeta_w = E::mul(zeta, omega);
+        E ev[10];
+        {
+            for (int j = 0; j < NW; j++) JF_TRY(eval_dev(ctx, pk, W + (size_t)j * np, n + 2, zeta, small + j));
+            for (int j = 0; j < NW - 1; j++) JF_TRY(eval_dev(ctx, pk, (const E *)pk->d_sig + (size_t)j * n, n, zeta, small + NW + j));
+            JF_TRY(eval_dev(ctx, pk, Z, n + 3, zeta_w, small + 9));
+            JF_CUDA(ctx, cudaMemcpyAsync(ev, small, fe * 10, cudaMemcpyDeviceToHost, st));
+            JF_CUDA(ctx, cudaStreamSynchronize(st));
+            for (int j = 0; j < NW; j++) tr_fr(tr, "wire_evals", ev[j]);
+            for (int j = 0; j < NW - 1; j++) tr_fr(tr, "wire_sigma_evals", ev[NW + j]);
+            tr_fr(tr, "perm_next_eval", ev[9]);
+        }
+        // ---- round 5 (snark.rs:419-449; prover.rs:302-360, 362-419, 490-509, 963-1034) ----
+        const E v = challenge(tr, "v");
+        {
+            const E *we = ev, *se = ev + NW;
+            const E pne = ev[9];
+            const E one = E::one();
+            const E vanish = E::sub(pow_small(zeta, n), one);
+            const E zeta_n2 = E::mul(E::mul(E::add(vanish, one), zeta), zeta);
+            const E alpha2 = E::sqr(alpha);
+            const E nf = E::from_u32((uint32_t)n);
+            const E lagrange_1 = E::mul(vanish, E::inv(E::mul(nf, E::sub(zeta, one))));
+            LinArgs<Fr> la;
+            int c = 0;
+            auto push = [&](const E *p, size_t len, const E &s) {
+                la.p[c] = p;
+                la.len[c] = (uint32_t)len;
+                la.s[c] = s;
+                c++;
+            };
+            // quotient part: -Z_H(zeta) * sum_i zeta^(i (n+2)) t_i
+            E coeff = E::neg(vanish);
+            for (int i = 0; i < NW; i++) {
+                const size_t len = i < NW - 1 ? n + 3 : NW * (n + 1) + 3 - (size_t)(NW - 1) * (n + 2);
+                push((const E *)pk->d_split + (size_t)i * np, len, coeff);
+                coeff = E::mul(coeff, zeta_n2);
+            }
+            // circuit part
+            const E *sel = (const E *)pk->d_sel;
+            const E w01 = E::mul(we[0], we[1]), w23 = E::mul(we[2], we[3]);
+            const E qs[NSEL] = {we[0], we[1], we[2], we[3], w01, w23, pow_small(we[0], 5), pow_small(we[1], 5), pow_small(we[2], 5),
+                                pow_small(we[3], 5), E::neg(we[4]), one, E::mul(E::mul(w01, w23), we[4])};
+            for (int s = 0; s < NSEL; s++) push(sel + (size_t)s * n, n, qs[s]);
+            // permutation part
+            E c1 = alpha;
+            for (int j = 0; j < NW; j++) c1 = E::mul(c1, E::add(E::add(we[j], E::mul(E::mul(beta, kf(pk, j)), zeta)), gamma));
+            c1 = E::add(c1, E::mul(alpha2, lagrange_1));
+            E c2 = E::mul(E::mul(alpha, beta), pne);
+            for (int j = 0; j < NW - 1; j++) c2 = E::mul(c2, E::add(E::add(we[j], E::mul(beta, se[j])), gamma));
+            // the opening batch: lin + v w_0 + .. + v^5 w_4 + v^6 sigma_0 + .. + v^9 sigma_3; z appears in lin only
+            push(Z, n + 3, c1);
+            E vp = v;
+            for (int j = 0; j < NW; j++) {
+                push(W + (size_t)j * np, n + 2, vp);
+                vp = E::mul(vp, v);
+            }
+            const E *sig = (const E *)pk->d_sig;
+            for (int j = 0; j < NW - 1; j++) {
+                push(sig + (size_t)j * n, n, vp);
+                vp = E::mul(vp, v);
+            }
+            push(sig + (size_t)(NW - 1) * n, n, E::neg(c2));
+            la.count = c;
+            la.out = (E *)pk->d_bp;
+            la.out_len = (uint32_t)(n + 3);
+            JF_LAUNCH(ctx, "lincomb", lincomb_kernel<Fr><<<(unsigned)((n + 3 + 127) / 128), 128, 0, st>>>(la));
+            E *WZ = (E *)pk->d_wz;
+            JF_TRY(div_linear_dev(ctx, pk, (const E *)pk->d_bp, n + 3, zeta, WZ));
+            JF_TRY(commit_dev(ctx, pk, WZ, n + 2, 0));
+            JF_TRY(div_linear_dev(ctx, pk, Z, n + 3, zeta_w, WZ));
+            JF_TRY(commit_dev(ctx, pk, WZ, n + 2, 1));
+            uint64_t xy[2 * 2 * 6];
+            int inf[2];
+            JF_TRY(fetch_commits(ctx, pk, 0, 2, xy, inf));
+            memcpy(out->opening_proof, xy, sizeof(uint64_t) * 2 * L);
+            memcpy(out->shifted_opening_proof, xy + 2 * L, sizeof(uint64_t) * 2 * L);
+            out->opening_inf = inf[0];
+            out->shifted_opening_inf = inf[1];
+        }
+        for (int j = 0; j < NW; j++) H::fr_to_limbs(ev[j], out->wires_evals + 4 * j);
+        for (int j = 0; j < NW - 1; j++) H::fr_to_limbs(ev[NW + j], out->wire_sigma_evals + 4 * j);
+        H::fr_to_limbs(ev[9], out->perm_next_eval);
+        H::fr_to_limbs(beta, out->challenges + 0);
+        H::fr_to_limbs(gamma, out->challenges + 4);
+        H::fr_to_limbs(alpha, out->challenges + 8);
+        H::fr_to_limbs(zeta, out->challenges + 12);
+        H::fr_to_limbs(v, out->challenges + 16);
+        out->curve = pk->curve;
+        return JF_OK;
+    }
+
+    // `Proof<E>` CanonicalSerialize, compressed (structs.rs:62-84)
+    static size_t serialize(const jf_plonk_proof *p, uint8_t *out) {
+        uint8_t *o = out;
+        auto u64 = [&](uint64_t v) { memcpy(o, &v, 8); o += 8; };
+        auto g1 = [&](const uint64_t *xy, int inf) { H::g1_bytes(xy, inf, o); o += 8 * L; };
+        auto fr = [&](const uint64_t *l) { H::fr_bytes(H::fr_from_limbs(l), o); o += 32; };
+        u64(NW);
+        for (int j = 0; j < NW; j++) g1(p->wires_poly_comms + 2 * L * j, p->wires_inf[j]);
+        g1(p->prod_perm_poly_comm, p->prod_perm_inf);
+        u64(NW);
+        for (int j = 0; j < NW; j++) g1(p->split_quot_poly_comms + 2 * L * j, p->split_inf[j]);
+        g1(p->opening_proof, p->opening_inf);
+        g1(p->shifted_opening_proof, p->shifted_opening_inf);
+        u64(NW);
+        for (int j = 0; j < NW; j++) fr(p->wires_evals + 4 * j);
+        u64(NW - 1);
+        for (int j = 0; j < NW - 1; j++) fr(p->wire_sigma_evals + 4 * j);
+        fr(p->perm_next_eval);
+        *o++ = 0;  // plookup_proof: None
+        return (size_t)(o - out);
+    }
+};
+
+struct Bn254Plonk : Bn254G1 {
+    static constexpr int FR_ID = JF_BN254_FR;
+};
+struct Bls12381Plonk : Bls12381G1 {
+    static constexpr int FR_ID = JF_BLS12_381_FR;
+};
+
+}  // namespace jf
+
+#define JF_GUARD(ctx)                             \
+    if (!(ctx)) return JF_ERR_INVALID_ARG;        \
+    std::lock_guard<std::mutex> lock_((ctx)->mu); \
+    cudaSetDevice((ctx)->device)
+
+extern "C" {
+
+int jf_plonk_preprocess(jf_ctx *ctx, const jf_srs *srs, unsigned log_n, const uint64_t *selector_evals, const uint64_t *sigma_evals,
+                        const uint64_t *k, const uint32_t *wire_variables, size_t num_vars, const uint32_t *pub_input_gate_ids,
+                        size_t num_inputs, int flags, jf_plonk_pk **out) {
+    JF_GUARD(ctx);
+    if (!srs || !selector_evals || !sigma_evals || !k || !wire_variables || !out || (num_inputs && !pub_input_gate_ids))
+        return fail(ctx, JF_ERR_INVALID_ARG, "plonk_preprocess: null argument");
+    *out = nullptr;
+    if (srs->curve == JF_BN254)
+        return Plonk<Bn254Plonk>::preprocess(ctx, srs, log_n, selector_evals, sigma_evals, k, wire_variables, num_vars,
+                                             pub_input_gate_ids, num_inputs, flags, out);
+    return Plonk<Bls12381Plonk>::preprocess(ctx, srs, log_n, selector_evals, sigma_evals, k, wire_variables, num_vars,
+                                            pub_input_gate_ids, num_inputs, flags, out);
+}
+
+int jf_plonk_vk_commitments(jf_ctx *ctx, const jf_plonk_pk *pk, uint64_t *out_xy, int *out_inf) {
+    JF_GUARD(ctx);
+    if (!pk || !out_xy || !out_inf) return fail(ctx, JF_ERR_INVALID_ARG, "plonk_vk_commitments: null argument");
+    memcpy(out_xy, pk->vk_xy.data(), pk->vk_xy.size() * sizeof(uint64_t));
+    memcpy(out_inf, pk->vk_inf.data(), pk->vk_inf.size() * sizeof(int));
+    return JF_OK;
+}
+
+void jf_plonk_pk_free(jf_ctx *ctx, jf_plonk_pk *pk) {
+    if (!pk) return;
+    if (ctx) {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        for (void *p : pk->allocs) cudaFree(p);
+    } else {
+        for (void *p : pk->allocs) cudaFree(p);
+    }
+    delete pk;
+}
+
+int jf_plonk_prove(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *witness, const uint64_t *blinders, int transcript_kind,
+                   const uint8_t *extra_msg, size_t extra_len, jf_plonk_proof *out) {
+    JF_GUARD(ctx);
+    if (!pk || !witness || !blinders || !out) return fail(ctx, JF_ERR_INVALID_ARG, "plonk_prove: null argument");
+    if (transcript_kind != 0 && transcript_kind != 1) return fail(ctx, JF_ERR_INVALID_ARG, "plonk_prove: unknown transcript");
+    if (pk->curve == JF_BN254) return Plonk<Bn254Plonk>::prove(ctx, pk, witness, blinders, transcript_kind, extra_msg, extra_len, out);
+    return Plonk<Bls12381Plonk>::prove(ctx, pk, witness, blinders, transcript_kind, extra_msg, extra_len, out);
+}
+
+long jf_plonk_proof_serialize(const jf_plonk_proof *proof, uint8_t *out, size_t cap) {
+    if (!proof || !out) return JF_ERR_INVALID_ARG;
+    const size_t need = proof->curve == JF_BN254 ? 769 : 8 * 4 + 48 * 13 + 32 * 10 + 1;
+    if (cap < need) return JF_ERR_INVALID_ARG;
+    if (proof->curve == JF_BN254) return (long)Plonk<Bn254Plonk>::serialize(proof, out);
+    return (long)Plonk<Bls12381Plonk>::serialize(proof, out);
+}
+
+// ---- host-only transcript entry points (no GPU needed; exercised by the CPU test-suite) ----------
+void jf_keccak256(const uint8_t *data, size_t len, uint8_t out[32]) { keccak256(data, len, out); }
+
+void *jf_transcript_new(int kind, const char *label) {
+    if (kind != 0 && kind != 1) return nullptr;
+    return new Transcript(kind, label ? label : "");
+}
+void jf_transcript_free(void *t) { delete static_cast<Transcript *>(t); }
+void jf_transcript_append(void *t, const char *label, const uint8_t *msg, size_t len) {
+    static_cast<Transcript *>(t)->append_message(label, msg, len);
+}
+/* field: JF_BN254_FR or JF_BLS12_381_FR; out = the challenge, 4 Montgomery limbs */
+int jf_transcript_challenge(void *t, int field, const char *label, uint64_t *out) {
+    if (!t || !out) return JF_ERR_INVALID_ARG;
+    Transcript &tr = *static_cast<Transcript *>(t);
+    if (field == JF_BN254_FR) {
+        auto c = Plonk<Bn254Plonk>::challenge(tr, label);
+        HostCurve<Bn254Plonk>::fr_to_limbs(c, out);
+        return JF_OK;
+    }
+    if (field == JF_BLS12_381_FR) {
+        auto c = Plonk<Bls12381Plonk>::challenge(tr, label);
+        HostCurve<Bls12381Plonk>::fr_to_limbs(c, out);
+        return JF_OK;
+    }
+    return JF_ERR_INVALID_ARG;
+}
+
+}  // extern "C"

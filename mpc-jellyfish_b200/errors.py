@@ -22,6 +22,10 @@ class DomainCreationError(PlonkError):
     """`PlonkError::DomainCreationError` -- domain size exceeds the field's two-adicity."""
 
 
+class WrongQuotientPolyDegree(PlonkError):
+    """`SnarkError::WrongQuotientPolyDegree` (prover.rs:916-919): the witness does not satisfy the circuit."""
+
+
 def raise_for_status(rc: int, msg: str):
     from . import _ffi
     if rc == _ffi.JF_OK:
@@ -30,4 +34,6 @@ def raise_for_status(rc: int, msg: str):
         raise InvalidParameters(msg)
     if rc == _ffi.JF_ERR_DOMAIN_TOO_LARGE:
         raise DomainCreationError(msg)
+    if rc == _ffi.JF_ERR_QUOTIENT_DEGREE:
+        raise WrongQuotientPolyDegree(msg)
     raise UpstreamError("%s (status %d)" % (msg, rc))

@@ -1,0 +1,172 @@
+"""Host-side mirror of `PlonkKzgSnark::{preprocess, prove}` for one TurboPlonk instance
+(plonk/src/proof_system/snark.rs:529-611, 613-640 -> 201-469) and of the `PlonkTranscript`
+implementations (plonk/src/transcript/{solidity,standard}.rs).  Everything here is a thin ctypes
+wrapper: the five prover rounds, the polynomial algebra, the MSMs / NTTs and the Fiat-Shamir
+transcript all run inside libjf_b200.so (csrc/plonk.cu, csrc/transcript.hpp).
+
+The caller hands over what `relation::PlonkCircuit` produces after `finalize_for_arithmetization`:
+selector columns, the extended permutation, the coset representatives k, the wire -> variable map and
+the io gate ids; per proof, the witness and the 17 masking scalars.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from .context import CommitKey, Context
+from .errors import InvalidParameters
+
+TRANSCRIPT_KINDS = {"solidity": 0, "standard": 1}
+NUM_WIRE_TYPES = 5
+NUM_SELECTORS = 13
+NUM_BLINDERS = 17
+
+
+def keccak256(data: bytes) -> bytes:
+    """sha3 crate `Keccak256` (host code of the library; no GPU needed)."""
+    out = ctypes.create_string_buffer(32)
+    _ffi.lib().jf_keccak256(data, len(data), out)
+    return out.raw
+
+
+class Transcript:
+    """`SolidityTranscript` / `StandardTranscript` (host code of the library; no GPU needed)."""
+
+    def __init__(self, kind: str, label: bytes = b"PlonkProof"):
+        self._lib = _ffi.lib()
+        self._h = self._lib.jf_transcript_new(TRANSCRIPT_KINDS[kind], label)
+        if not self._h:
+            raise InvalidParameters("unknown transcript kind %r" % kind)
+
+    def append_message(self, label: bytes, msg: bytes):
+        self._lib.jf_transcript_append(self._h, label, msg, len(msg))
+
+    def get_and_append_challenge(self, field: str, label: bytes) -> np.ndarray:
+        """-> 4 Montgomery limbs of the challenge."""
+        out = np.zeros(4, dtype=np.uint64)
+        rc = self._lib.jf_transcript_challenge(self._h, _ffi.FIELDS[field], label, out.ctypes.data_as(_ffi.c_u64p))
+        if rc != _ffi.JF_OK:
+            raise InvalidParameters("transcript challenge failed (%d)" % rc)
+        return out
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.jf_transcript_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+@dataclass
+class Proof:
+    """`Proof<E>` (structs.rs:62-84).  Points: (count, 2L) Montgomery x || y + infinity flags;
+    evaluations: (count, 4) Montgomery limbs."""
+    curve: str
+    wires_poly_comms: np.ndarray
+    wires_inf: List[bool]
+    prod_perm_poly_comm: np.ndarray
+    prod_perm_inf: bool
+    split_quot_poly_comms: np.ndarray
+    split_inf: List[bool]
+    opening_proof: np.ndarray
+    opening_inf: bool
+    shifted_opening_proof: np.ndarray
+    shifted_opening_inf: bool
+    wires_evals: np.ndarray
+    wire_sigma_evals: np.ndarray
+    perm_next_eval: np.ndarray
+    challenges: np.ndarray  # beta, gamma, alpha, zeta, v
+    _raw: object = None
+
+    def serialize_compressed(self) -> bytes:
+        buf = ctypes.create_string_buffer(1024)
+        n = _ffi.lib().jf_plonk_proof_serialize(ctypes.byref(self._raw), buf, len(buf))
+        if n < 0:
+            raise InvalidParameters("proof serialization failed (%d)" % n)
+        return buf.raw[:n]
+
+
+class ProvingKey:
+    """`ProvingKey<E>` resident on the GPU (selector / sigma polynomials, commit key, vk commitments)."""
+
+    def __init__(self, ctx: Context, key: CommitKey, handle, n: int, num_vars: int, num_inputs: int, k: np.ndarray):
+        self.ctx, self.key, self._h, self.n, self.num_vars, self.num_inputs, self.k = ctx, key, handle, n, num_vars, num_inputs, k
+        L = _ffi.CURVE_FQ_LIMBS[key.curve]
+        xy = np.zeros((NUM_SELECTORS + NUM_WIRE_TYPES, 2 * L), dtype=np.uint64)
+        inf = (ctypes.c_int * (NUM_SELECTORS + NUM_WIRE_TYPES))()
+        ctx._check(ctx._lib.jf_plonk_vk_commitments(ctx._h, handle, xy.ctypes.data_as(_ffi.c_u64p), inf))
+        self.selector_comms, self.sigma_comms = xy[:NUM_SELECTORS], xy[NUM_SELECTORS:]
+        self.selector_inf = [bool(v) for v in inf[:NUM_SELECTORS]]
+        self.sigma_inf = [bool(v) for v in inf[NUM_SELECTORS:]]
+
+    def free(self):
+        if self._h is not None and self.ctx._h:
+            self.ctx._lib.jf_plonk_pk_free(self.ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PlonkKzgSnark:
+    @staticmethod
+    def preprocess(ctx: Context, key: CommitKey, selector_evals: np.ndarray, sigma_evals: np.ndarray, k: np.ndarray,
+                   wire_variables: np.ndarray, num_vars: int, pub_input_gate_ids: Sequence[int] = (),
+                   cache_coset_evals: bool = False) -> ProvingKey:
+        """selector_evals (13, n, 4), sigma_evals (5, n, 4) = the extended permutation, k (5, 4):
+        Montgomery limbs; wire_variables (5, n) uint32."""
+        sel = np.ascontiguousarray(selector_evals, dtype=np.uint64)
+        sig = np.ascontiguousarray(sigma_evals, dtype=np.uint64)
+        kk = np.ascontiguousarray(k, dtype=np.uint64)
+        wv = np.ascontiguousarray(wire_variables, dtype=np.uint32)
+        if sel.ndim != 3 or sel.shape[0] != NUM_SELECTORS or sel.shape[2] != 4:
+            raise InvalidParameters("selector_evals must be (13, n, 4)")
+        n = sel.shape[1]
+        if n & (n - 1) or sig.shape != (NUM_WIRE_TYPES, n, 4) or kk.shape != (NUM_WIRE_TYPES, 4) or wv.shape != (NUM_WIRE_TYPES, n):
+            raise InvalidParameters("inconsistent proving-key shapes")
+        gids = np.ascontiguousarray(list(pub_input_gate_ids), dtype=np.uint32)
+        h = ctypes.c_void_p()
+        ctx._check(ctx._lib.jf_plonk_preprocess(
+            ctx._h, key._h, n.bit_length() - 1, sel.ctypes.data_as(_ffi.c_u64p), sig.ctypes.data_as(_ffi.c_u64p),
+            kk.ctypes.data_as(_ffi.c_u64p), wv.ctypes.data_as(_ffi.c_u32p), num_vars,
+            gids.ctypes.data_as(_ffi.c_u32p) if len(gids) else None, len(gids), int(cache_coset_evals), ctypes.byref(h)))
+        return ProvingKey(ctx, key, h, n, num_vars, len(gids), kk)
+
+    @staticmethod
+    def prove(pk: ProvingKey, witness: np.ndarray, blinders: np.ndarray, transcript: str = "solidity",
+              extra_transcript_init_msg: Optional[bytes] = None) -> Proof:
+        """witness (num_vars, 4), blinders (17, 4): Montgomery limbs."""
+        ctx = pk.ctx
+        w = np.ascontiguousarray(witness, dtype=np.uint64)
+        b = np.ascontiguousarray(blinders, dtype=np.uint64)
+        if w.shape != (pk.num_vars, 4) or b.shape != (NUM_BLINDERS, 4):
+            raise InvalidParameters("witness must be (num_vars, 4) and blinders (17, 4)")
+        raw = _ffi.PlonkProofStruct()
+        ctx._check(ctx._lib.jf_plonk_prove(ctx._h, pk._h, w.ctypes.data_as(_ffi.c_u64p), b.ctypes.data_as(_ffi.c_u64p),
+                                           TRANSCRIPT_KINDS[transcript], extra_transcript_init_msg,
+                                           len(extra_transcript_init_msg) if extra_transcript_init_msg else 0,
+                                           ctypes.byref(raw)))
+        L = _ffi.CURVE_FQ_LIMBS[pk.key.curve]
+
+        def pts(arr, count):
+            return np.array(arr[: count * 2 * L], dtype=np.uint64).reshape(count, 2 * L)
+
+        return Proof(
+            curve=pk.key.curve,
+            wires_poly_comms=pts(raw.wires_poly_comms, 5), wires_inf=[bool(v) for v in raw.wires_inf],
+            prod_perm_poly_comm=pts(raw.prod_perm_poly_comm, 1)[0], prod_perm_inf=bool(raw.prod_perm_inf),
+            split_quot_poly_comms=pts(raw.split_quot_poly_comms, 5), split_inf=[bool(v) for v in raw.split_inf],
+            opening_proof=pts(raw.opening_proof, 1)[0], opening_inf=bool(raw.opening_inf),
+            shifted_opening_proof=pts(raw.shifted_opening_proof, 1)[0], shifted_opening_inf=bool(raw.shifted_opening_inf),
+            wires_evals=np.array(raw.wires_evals, dtype=np.uint64).reshape(5, 4),
+            wire_sigma_evals=np.array(raw.wire_sigma_evals, dtype=np.uint64).reshape(4, 4),
+            perm_next_eval=np.array(raw.perm_next_eval, dtype=np.uint64),
+            challenges=np.array(raw.challenges, dtype=np.uint64).reshape(5, 4), _raw=raw)

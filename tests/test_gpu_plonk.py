@@ -1,0 +1,157 @@
+"""Prover rows: the device-resident TurboPlonk prover behind jf_plonk_preprocess /
+jf_plonk_prove against the CPU restatement (oracle/plonk_ref.py) on the same circuit, witness,
+masking scalars and transcript: identical verifying-key commitments and byte-identical serialized
+proofs, which the restated jellyfish verifier accepts.  At sizes the Python prover cannot reach the
+proof is checked by that verifier alone (size-independent)."""
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+pytestmark = pytest.mark.gpu
+
+BETA = 0x1D3C7A5B9E8F60412B7A6C5D4E3F20198A7B6C5D4E3F2A1B0C9D8E7F6A5B4C3
+
+
+@pytest.fixture(scope="module")
+def P():
+    import plonk_ref
+    return plonk_ref
+
+
+def _blinders(co, fr, seed):
+    rnd = random.Random(seed)
+    ints = [rnd.randrange(fr.p) for _ in range(17)]
+    return ints, co.ints_to_limbs([fr.to_mont(v) for v in ints], 4)
+
+
+CIRCUITS = {
+    "test_m2": lambda P: P.gen_circuit_for_test(2, 3),
+    "bench_64": lambda P: P.gen_circuit_for_bench(64),
+    "test_m20": lambda P: P.gen_circuit_for_test(20, 1),
+    "bench_2^10": lambda P: P.gen_circuit_for_bench(1 << 10),
+    "test_m300": lambda P: P.gen_circuit_for_test(300, 7),
+}
+
+
+@pytest.mark.parametrize("name", list(CIRCUITS))
+def test_proof_bytes_match_the_cpu_restatement(ctx, co, py, P, name):
+    import mpc_jellyfish_b200 as jf
+    import plonk_util as U
+    cv, fr = py.BN254, py.BN254_FR
+    cs = CIRCUITS[name](P)
+    n = cs.n
+    beta = BETA % fr.p
+    arr = U.arrays_from_oracle_circuit(co, py, cs)
+    key = ctx.generate_srs_for_testing("bn254", beta, n + 3)
+    pk = jf.PlonkKzgSnark.preprocess(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"],
+                                     arr["pub_gate_ids"])
+    opk = P.preprocess(cv, P.gen_srs(cv, beta, n + 2), cs)
+    vk = U.vk_from_product(co, cv, pk, cs.k)
+    assert vk["selector_comms"] == opk["vk"]["selector_comms"]
+    assert vk["sigma_comms"] == opk["vk"]["sigma_comms"]
+    for kind in ("solidity", "standard"):
+        ints, bl = _blinders(co, fr, 11)
+        proof = jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, kind)
+        want = P.prove(cv, cs, opk, ints, kind)
+        got = U.proof_to_oracle(co, cv, proof)
+        for f in ("wires_poly_comms", "prod_perm_poly_comm", "split_quot_poly_comms", "wires_evals", "wire_sigma_evals",
+                  "perm_next_eval", "opening_proof", "shifted_opening_proof"):
+            assert got[f] == want[f], (kind, f)
+        assert proof.serialize_compressed() == P.serialize_proof(cv, want)
+        assert P.verify(cv, opk["vk"], cs.public_input(), got, beta, kind)
+        ch = [fr.from_mont(v) for v in co.limbs_to_ints(proof.challenges)]
+        assert ch == [want["challenges"][c] for c in ("beta", "gamma", "alpha", "zeta", "v")]
+    # extra transcript message (snark.rs:263-266) changes every challenge, on both sides alike
+    ints, bl = _blinders(co, fr, 12)
+    p2 = jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, "solidity", b"extra transcript init msg")
+    w2 = P.prove(cv, cs, opk, ints, "solidity", b"extra transcript init msg")
+    assert p2.serialize_compressed() == P.serialize_proof(cv, w2)
+    pk.free()
+    key.free()
+
+
+def test_cached_coset_evaluations_give_the_same_proof(ctx, co, py, P):
+    import mpc_jellyfish_b200 as jf
+    import plonk_util as U
+    fr = py.BN254_FR
+    cs = P.gen_circuit_for_test(40, 2)
+    arr = U.arrays_from_oracle_circuit(co, py, cs)
+    key = ctx.generate_srs_for_testing("bn254", BETA % fr.p, cs.n + 3)
+    _, bl = _blinders(co, fr, 5)
+    outs = []
+    for cache in (False, True):
+        pk = jf.PlonkKzgSnark.preprocess(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"],
+                                         arr["pub_gate_ids"], cache_coset_evals=cache)
+        outs.append(jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, "standard").serialize_compressed())
+        # the key is reusable: a second proof with other masks differs but has the same evaluations' count
+        outs.append(jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, "standard").serialize_compressed())
+        pk.free()
+    assert outs[0] == outs[1] == outs[2] == outs[3]
+    key.free()
+
+
+def test_unsatisfied_witness_is_rejected_like_the_reference(ctx, co, py, P):
+    """prover.rs:916-919 WrongQuotientPolyDegree; the context stays usable afterwards."""
+    import mpc_jellyfish_b200 as jf
+    import plonk_util as U
+    fr = py.BN254_FR
+    cs = P.gen_circuit_for_test(2, 3)
+    arr = U.arrays_from_oracle_circuit(co, py, cs)
+    key = ctx.generate_srs_for_testing("bn254", 77, cs.n + 3)
+    pk = jf.PlonkKzgSnark.preprocess(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"],
+                                     arr["pub_gate_ids"])
+    _, bl = _blinders(co, fr, 1)
+    bad = arr["witness"].copy()
+    bad[5] = co.ints_to_limbs([fr.to_mont(cs.witness[5] + 1)], 4)[0]
+    with pytest.raises(jf.WrongQuotientPolyDegree):
+        jf.PlonkKzgSnark.prove(pk, bad, bl, "solidity")
+    good = jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, "solidity")
+    opk = P.preprocess(py.BN254, P.gen_srs(py.BN254, 77, cs.n + 2), cs)
+    assert P.verify(py.BN254, opk["vk"], cs.public_input(), U.proof_to_oracle(co, py.BN254, good), 77, "solidity")
+    with pytest.raises(jf.InvalidParameters):  # commit key too short for n + 3 coefficients
+        short = ctx.generate_srs_for_testing("bn254", 77, cs.n)
+        jf.PlonkKzgSnark.preprocess(ctx, short, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"],
+                                    arr["pub_gate_ids"])
+    pk.free()
+    key.free()
+
+
+def test_numpy_circuit_builder_matches_the_restated_circuit(ctx, co, py, P):
+    import bench_circuit as B
+    import plonk_util as U
+    cs = P.gen_circuit_for_bench(1 << 8)
+    want = U.arrays_from_oracle_circuit(co, py, cs)
+    got = B.bench_circuit_arrays(ctx, 8)
+    assert cs.k == B.BN254_K
+    for f in ("selectors", "sigmas", "k", "witness"):
+        assert np.array_equal(got[f], want[f]), f
+    assert np.array_equal(got["wire_vars"], want["wire_vars"]) and got["num_vars"] == want["num_vars"]
+
+
+@pytest.mark.parametrize("log_n,kind", [(14, "solidity"), (16, "standard"), (18, "solidity")])
+def test_large_proofs_are_accepted_by_the_restated_verifier(ctx, co, py, P, log_n, kind):
+    """BASELINE config 4 shape (the bench circuit); the verifier check is size independent."""
+    import mpc_jellyfish_b200 as jf
+    import bench_circuit as B
+    import plonk_util as U
+    cv, fr = py.BN254, py.BN254_FR
+    arr = B.bench_circuit_arrays(ctx, log_n)
+    beta = BETA % fr.p
+    key = ctx.generate_srs_for_testing("bn254", beta, arr["n"] + 3)
+    pk = jf.PlonkKzgSnark.preprocess(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"], [])
+    _, bl = _blinders(co, fr, log_n)
+    proof = jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, kind)
+    got = U.proof_to_oracle(co, cv, proof)
+    vk = U.vk_from_product(co, cv, pk, B.BN254_K)
+    assert P.verify(cv, vk, [], got, beta, kind)
+    tampered = dict(got)
+    tampered["perm_next_eval"] = (got["perm_next_eval"] + 1) % fr.p
+    assert not P.verify(cv, vk, [], tampered, beta, kind)
+    pk.free()
+    key.free()
