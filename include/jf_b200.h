@@ -91,6 +91,15 @@ int jf_msm(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const uint64_t *s
 int jf_msm_batch(jf_ctx *ctx, const jf_srs *srs, const uint64_t *const *scalars, const size_t *lens,
                  const size_t *base_offsets, size_t batch, int scalars_in_montgomery, uint64_t *out_xy,
                  int *out_infinity);
+/* jf_kzg_open == `UnivariateKzgPCS::open` (mod.rs:135-161) for `batch` (polynomial, point) pairs in one call:
+ * the witness polynomial p / (X - z) (remainder dropped, as ark-poly's `/`), its commitment and p(z) are
+ * computed on the GPU (division = power scaling + one suffix scan; evaluation = blocked Horner).
+ * polys[i]: lens[i] Montgomery coefficients, low degree first; points: batch x 4 Montgomery limbs.
+ * Outputs: affine proofs (x || y each), infinity flags, evaluations (batch x 4 Montgomery limbs).  With the
+ * share and the MAC polynomial of an authenticated share as a batch of two this is also the local part of
+ * `MultiproverKZG::open` (plonk/src/multiprover/primitives/multiprover_kzg.rs:171-197). */
+int jf_kzg_open(jf_ctx *ctx, const jf_srs *srs, const uint64_t *const *polys, const size_t *lens, size_t batch,
+                const uint64_t *points, uint64_t *out_proof_xy, int *out_infinity, uint64_t *out_evals);
 /* Device-resident form: scalars already in HBM (device pointer), result left in HBM as one
  * XYZZ point (4*L limbs: X, Y, ZZ, ZZZ; x = X/ZZ, y = Y/ZZZ; ZZ = 0 <=> identity).  This is the
  * per-GPU partial sum of a range-sharded MSM; it is all-gathered and fed to jf_msm_combine. */

@@ -10,6 +10,8 @@ from .context import CommitKey, Context
 from .domain import Radix2EvaluationDomain
 from .errors import (DomainCreationError, InvalidParameters, PCSError, PlonkError, UpstreamError,
                      WrongQuotientPolyDegree)
+from .multiprover import (AuthenticatedDensePoly, AuthenticatedPointShare, MultiproverKZG, fft_with_domain,
+                          ifft_with_domain)
 from .plonk import PlonkKzgSnark, Proof, ProvingKey, Transcript, keccak256
 from .sharded import ShardedMsm, combine_partials, poly_owner, shard_range
 from .pcs import Commitment, DensePolynomial, UnivariateKzgPCS, UnivariateProverParam
@@ -18,5 +20,6 @@ __all__ = [
     "Context", "CommitKey", "Radix2EvaluationDomain", "UnivariateKzgPCS", "UnivariateProverParam",
     "DensePolynomial", "Commitment", "PCSError", "InvalidParameters", "UpstreamError", "PlonkError",
     "DomainCreationError", "WrongQuotientPolyDegree", "PlonkKzgSnark", "Proof", "ProvingKey", "Transcript", "keccak256",
+    "MultiproverKZG", "AuthenticatedDensePoly", "AuthenticatedPointShare", "fft_with_domain", "ifft_with_domain",
     "ShardedMsm", "combine_partials", "poly_owner", "shard_range",
 ]

@@ -69,6 +69,8 @@ SIGNATURES = {
     "jf_msm_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(c_u64p),
                                     ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t,
                                     ctypes.c_int, c_u64p, ctypes.POINTER(ctypes.c_int)]),
+    "jf_kzg_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(c_u64p), ctypes.POINTER(ctypes.c_size_t),
+                                   ctypes.c_size_t, c_u64p, c_u64p, ctypes.POINTER(ctypes.c_int), c_u64p]),
     "jf_msm_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
                                      ctypes.c_int, ctypes.c_void_p]),
     "jf_msm_combine": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64p, ctypes.c_size_t, c_u64p,

@@ -105,6 +105,23 @@ class Context:
         self._check(self._lib.jf_msm_batch(self._h, key._h, ptrs, lens, offs, B, int(montgomery), _u64p(out), inf))
         return out, [bool(x) for x in inf]
 
+    def kzg_open(self, key: "CommitKey", polys: Sequence[np.ndarray], points: np.ndarray):
+        """`UnivariateKzgPCS::open` for a batch: polys[i] (len_i, 4) Montgomery coefficients, points (batch, 4)
+        Montgomery -> (proofs (batch, 2L), infinity flags, evaluations (batch, 4) Montgomery)."""
+        L = _ffi.CURVE_FQ_LIMBS[key.curve]
+        vecs = [_as_u64(np.asarray(p).reshape(-1, 4), 4) for p in polys]
+        B = len(vecs)
+        pts = _as_u64(np.asarray(points).reshape(-1, 4), 4)
+        if pts.shape[0] != B:
+            raise InvalidParameters("poly length %d is different from points length %d" % (B, pts.shape[0]))
+        ptrs = (_ffi.c_u64p * B)(*[_u64p(v) for v in vecs])
+        lens = (ctypes.c_size_t * B)(*[v.shape[0] for v in vecs])
+        out = np.zeros((B, 2 * L), dtype=np.uint64)
+        inf = (ctypes.c_int * B)()
+        evals = np.zeros((B, 4), dtype=np.uint64)
+        self._check(self._lib.jf_kzg_open(self._h, key._h, ptrs, lens, B, _u64p(pts), _u64p(out), inf, _u64p(evals)))
+        return out, [bool(x) for x in inf], evals
+
     def msm_device(self, key: "CommitKey", d_scalars: int, n: int, d_out_xyzz: int, base_offset: int = 0,
                    montgomery: bool = False):
         """Scalars and the XYZZ result stay in HBM (raw device pointers); asynchronous on the stream."""

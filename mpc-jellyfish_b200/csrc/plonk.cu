@@ -551,9 +551,12 @@ template <class C> struct Plonk {
     }
 
     static int eval_dev(jf_ctx *ctx, const jf_plonk_pk *pk, const E *poly, size_t len, const E &x, E *d_out) {
+        return eval_dev(ctx, (E *)pk->d_tmp, poly, len, x, d_out);
+    }
+    // d_out = poly(x); `partials` holds >= len / 2048 + 1 elements
+    static int eval_dev(jf_ctx *ctx, E *partials, const E *poly, size_t len, const E &x, E *d_out) {
         const size_t per = (size_t)EV_T * EV_I;
         const unsigned blocks = (unsigned)((len + per - 1) / per);
-        E *partials = (E *)pk->d_tmp;
         JF_LAUNCH(ctx, "eval_partial", eval_partial_kernel<Fr><<<blocks ? blocks : 1, EV_T, 0, ctx->stream>>>(poly, len, x, partials));
         JF_LAUNCH(ctx, "eval_sum", sum_kernel<Fr><<<1, EV_T, 0, ctx->stream>>>(partials, blocks ? blocks : 1, d_out));
         return JF_OK;
@@ -561,12 +564,18 @@ template <class C> struct Plonk {
 
     // out (len-1 coefficients) = p / (X - z), remainder dropped
     static int div_linear_dev(jf_ctx *ctx, const jf_plonk_pk *pk, const E *p, size_t len, const E &z, E *out) {
-        if (len < 2) return fail(ctx, JF_ERR_INVALID_ARG, "prove: degenerate opening polynomial");
-        if (z.is_zero()) return fail(ctx, JF_ERR_INVALID_ARG, "prove: zero evaluation point");
-        E *t = (E *)pk->d_t, *s = (E *)pk->d_s;
+        return div_linear_dev(ctx, (E *)pk->d_t, (E *)pk->d_s, (E *)pk->d_tmp, p, len, z, out);
+    }
+    // t, s: len elements each; tmp: len / 512 + 64 elements
+    static int div_linear_dev(jf_ctx *ctx, E *t, E *s, E *tmp, const E *p, size_t len, const E &z, E *out) {
+        if (len < 2) return fail(ctx, JF_ERR_INVALID_ARG, "degenerate polynomial: nothing to divide");
+        if (z.is_zero()) {  // p / X: drop the constant term
+            JF_CUDA(ctx, cudaMemcpyAsync(out, p + 1, sizeof(E) * (len - 1), cudaMemcpyDeviceToDevice, ctx->stream));
+            return JF_OK;
+        }
         const unsigned b1 = (unsigned)((len + 256 * MP_I - 1) / (256 * MP_I));
         JF_LAUNCH(ctx, "mulpow", mulpow_kernel<Fr><<<b1, 256, 0, ctx->stream>>>(p, t, len, 0, 0, z));
-        JF_TRY((fscan<Fr, OpAdd, true>(ctx, t, s, len, (E *)pk->d_tmp)));
+        JF_TRY((fscan<Fr, OpAdd, true>(ctx, t, s, len, tmp)));
         const E zinv = E::inv(z);
         JF_LAUNCH(ctx, "mulpow", mulpow_kernel<Fr><<<b1, 256, 0, ctx->stream>>>(s, out, len - 1, 1, 1, zinv));
         return JF_OK;
@@ -961,6 +970,54 @@ template <class C> struct Plonk {
         return JF_OK;
     }
 
+    // `UnivariateKzgPCS::open` (primitives/src/pcs/univariate_kzg/mod.rs:135-161) for `batch` polynomials:
+    // witness polynomial p / (X - z), its commitment, and p(z); everything on the device.
+    static int kzg_open(jf_ctx *ctx, const jf_srs *srs, const uint64_t *const *polys, const size_t *lens, size_t batch,
+                        const uint64_t *points, uint64_t *out_xy, int *out_inf, uint64_t *out_evals) {
+        size_t max_len = 1;
+        for (size_t i = 0; i < batch; i++) max_len = std::max(max_len, lens[i]);
+        void *dp, *dt, *ds, *dw, *dtmp, *dres;
+        const size_t fe = sizeof(E);
+        JF_TRY(scratch(ctx, "open_p", fe * max_len, &dp));
+        JF_TRY(scratch(ctx, "open_t", fe * max_len, &dt));
+        JF_TRY(scratch(ctx, "open_s", fe * max_len, &ds));
+        JF_TRY(scratch(ctx, "open_w", fe * max_len, &dw));
+        JF_TRY(scratch(ctx, "open_tmp", fe * (max_len / 256 + 4096), &dtmp));
+        JF_TRY(scratch(ctx, "open_res", (PT + fe) * (batch ? batch : 1), &dres));
+        E *d_ev = (E *)((char *)dres + PT * batch);
+        for (size_t i = 0; i < batch; i++) {
+            // DensePolynomial semantics: trailing (high-degree) zero coefficients do not count
+            size_t len = lens[i];
+            while (len && !(polys[i][4 * (len - 1)] | polys[i][4 * (len - 1) + 1] | polys[i][4 * (len - 1) + 2] | polys[i][4 * (len - 1) + 3])) len--;
+            if (len > srs->n + 1) return fail(ctx, JF_ERR_INVALID_ARG, "open: polynomial degree exceeds the commit key");
+            const E z = H::fr_from_limbs(points + 4 * i);
+            XYZZ<Fq> *res = (XYZZ<Fq> *)((char *)dres + PT * i);
+            if (len) JF_CUDA(ctx, cudaMemcpyAsync(dp, polys[i], fe * len, cudaMemcpyHostToDevice, ctx->stream));
+            if (len == 0) JF_CUDA(ctx, cudaMemsetAsync(d_ev + i, 0, fe, ctx->stream));
+            else JF_TRY(eval_dev(ctx, (E *)dtmp, (const E *)dp, len, z, d_ev + i));
+            if (len < 2) {
+                JF_TRY(msm_run(ctx, srs, 0, dp, 0, 1, res));  // constant / zero polynomial: identity proof
+            } else {
+                JF_TRY(div_linear_dev(ctx, (E *)dt, (E *)ds, (E *)dtmp, (const E *)dp, len, z, (E *)dw));
+                JF_TRY(msm_run(ctx, srs, 0, dw, len - 1, 1, res));
+            }
+        }
+        void *h;
+        JF_TRY(pinned(ctx, (PT + fe) * batch + 64, &h));
+        JF_CUDA(ctx, cudaMemcpyAsync(h, dres, (PT + fe) * batch, cudaMemcpyDeviceToHost, ctx->stream));
+        int herr = 0;
+        JF_CUDA(ctx, cudaMemcpyAsync(&herr, ctx->d_err, sizeof herr, cudaMemcpyDeviceToHost, ctx->stream));
+        JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (herr) {
+            cudaMemsetAsync(ctx->d_err, 0, sizeof herr, ctx->stream);
+            return fail(ctx, herr, "open: a coefficient is not a reduced field element");
+        }
+        for (size_t i = 0; i < batch; i++)
+            JF_TRY(msm_finish_host(ctx, srs->curve, (const uint64_t *)((const char *)h + PT * i), 1, out_xy + (size_t)2 * L * i, out_inf + i));
+        memcpy(out_evals, (const char *)h + PT * batch, fe * batch);
+        return JF_OK;
+    }
+
     // `Proof<E>` CanonicalSerialize, compressed (structs.rs:62-84)
     static size_t serialize(const jf_plonk_proof *p, uint8_t *out) {
         uint8_t *o = out;
@@ -1042,6 +1099,18 @@ int jf_plonk_prove(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *witness, const 
     if (transcript_kind != 0 && transcript_kind != 1) return fail(ctx, JF_ERR_INVALID_ARG, "plonk_prove: unknown transcript");
     if (pk->curve == JF_BN254) return Plonk<Bn254Plonk>::prove(ctx, pk, witness, blinders, transcript_kind, extra_msg, extra_len, out);
     return Plonk<Bls12381Plonk>::prove(ctx, pk, witness, blinders, transcript_kind, extra_msg, extra_len, out);
+}
+
+int jf_kzg_open(jf_ctx *ctx, const jf_srs *srs, const uint64_t *const *polys, const size_t *lens, size_t batch,
+                const uint64_t *points, uint64_t *out_proof_xy, int *out_infinity, uint64_t *out_evals) {
+    JF_GUARD(ctx);
+    if (!srs || !out_proof_xy || !out_infinity || !out_evals || (batch && (!polys || !lens || !points)))
+        return fail(ctx, JF_ERR_INVALID_ARG, "kzg_open: null argument");
+    for (size_t i = 0; i < batch; i++)
+        if (lens[i] && !polys[i]) return fail(ctx, JF_ERR_INVALID_ARG, "kzg_open: null polynomial");
+    if (batch == 0) return JF_OK;
+    if (srs->curve == JF_BN254) return Plonk<Bn254Plonk>::kzg_open(ctx, srs, polys, lens, batch, points, out_proof_xy, out_infinity, out_evals);
+    return Plonk<Bls12381Plonk>::kzg_open(ctx, srs, polys, lens, batch, points, out_proof_xy, out_infinity, out_evals);
 }
 
 long jf_plonk_proof_serialize(const jf_plonk_proof *proof, uint8_t *out, size_t cap) {

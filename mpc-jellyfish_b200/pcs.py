@@ -88,20 +88,20 @@ class UnivariateKzgPCS:
     @staticmethod
     def open(prover_param: UnivariateProverParam, polynomial: DensePolynomial, point: int):
         """-> (proof commitment, evaluation as a canonical int).  `point` is a canonical int.
-        Witness polynomial p/(X - z) and the Horner evaluation stay on the host, as in the
-        reference (mod.rs:142-157); only the MSM is on the GPU."""
+        Witness polynomial p / (X - z), its commitment and the evaluation all run on the GPU
+        (`jf_kzg_open`; mod.rs:135-161)."""
         field = CURVE_FR[prover_param.key.curve]
-        p = MODULUS[field]
-        c = [from_mont(field, v) for v in array_to_ints(polynomial.coeffs)]
-        q = [0] * max(len(c) - 1, 0)
-        carry = 0
-        for i in range(len(c) - 1, 0, -1):
-            carry = (c[i] + carry * point) % p
-            q[i - 1] = carry
-        ev = 0
-        for v in reversed(c):
-            ev = (ev * point + v) % p
-        w = DensePolynomial(ints_to_array([to_mont(field, v) for v in q], 4) if q else np.zeros((0, 4), np.uint64))
-        nz = _skip_leading_zeros(w)
-        xy, inf = prover_param.ctx.msm(prover_param.key, w.coeffs[nz:], base_offset=nz, montgomery=True)
-        return Commitment.from_raw(xy, inf), ev
+        z = ints_to_array([to_mont(field, point % MODULUS[field])], 4)
+        xy, inf, ev = prover_param.ctx.kzg_open(prover_param.key, [polynomial.coeffs], z)
+        return Commitment.from_raw(xy[0], inf[0]), from_mont(field, array_to_ints(ev)[0])
+
+    @staticmethod
+    def batch_open(prover_param: UnivariateProverParam, polynomials: Sequence[DensePolynomial], points: Sequence[int]):
+        """`batch_open` (mod.rs:165-194): one opening per (polynomial, point) pair; one library call."""
+        if len(polynomials) != len(points):  # mod.rs:171-177
+            raise InvalidParameters("poly length %d is different from points length %d" % (len(polynomials), len(points)))
+        field = CURVE_FR[prover_param.key.curve]
+        z = ints_to_array([to_mont(field, pt % MODULUS[field]) for pt in points], 4)
+        xy, inf, ev = prover_param.ctx.kzg_open(prover_param.key, [p.coeffs for p in polynomials], z)
+        return ([Commitment.from_raw(xy[i], inf[i]) for i in range(len(points))],
+                [from_mont(field, v) for v in array_to_ints(ev)])
