@@ -41,6 +41,11 @@ struct NttPlan {
     void *off_lo = nullptr, *off_hi = nullptr;  // powers of offset (fwd) / offset^-1 scaled by n^-1 (inv)
     void *tw[NTT_MAX_K + 1] = {nullptr};        // tw[k][i] = w_{2^k}^i, i < 2^(k-1)
     void *n_inv = nullptr;                      // single element n^-1 (plain inverse)
+    // inter-pass twiddles, one multiplication per element: ptw[i][(r << log_ns) | k] = w^((k r) n / (Ns R)),
+    // times n^-1 on the last pass of a plain inverse transform (the scaling rides along for free)
+    std::vector<void *> ptw;
+    void *off_full = nullptr;                   // offset^j (fwd) / n^-1 offset^-j (inv), j < n; built on first dense use
+    bool ninv_folded = false;
 };
 
 template <class F> struct El {  // 32-byte element as two 16-byte halves for vector loads
@@ -92,6 +97,8 @@ struct PassArgs {
     int coset_in;      // on first pass: multiply input j by off table
     int split;
     const void *w_lo, *w_hi, *off_lo, *off_hi, *tw, *n_inv;
+    const void *ptw;       // this pass' inter-pass twiddle table (passes > 0)
+    const void *off_full;  // full offset power table or NULL (then the two-level tables are used)
 };
 
 template <int K> __device__ __forceinline__ uint32_t bitrev_k(uint32_t x) { return __brev(x) >> (32 - K); }
@@ -112,11 +119,10 @@ template <class F, int K> __global__ void __launch_bounds__(256, 2) ntt_pass_ker
     const uint32_t q = t >> LOGB;  // < R/8
     const uint32_t log_cols = a.log_n - K;
     const uint64_t cols = 1ull << log_cols;
-    const uint64_t cidx = (uint64_t)blockIdx.x * B + b;
-    const uint64_t total_cols = cols * a.batch;
-    const bool valid = cidx < total_cols;
-    const uint64_t bid = cidx >> log_cols;
-    const uint64_t j = cidx & (cols - 1);
+    // consecutive CTAs work on the same column tile of different vectors: they share the twiddle tile in L2
+    const uint64_t bid = blockIdx.x % a.batch;
+    const uint64_t j = (uint64_t)(blockIdx.x / a.batch) * B + b;
+    const bool valid = j < cols;
     const E *src = reinterpret_cast<const E *>(a.src) + bid * a.stride;
     E *dst = reinterpret_cast<E *>(a.dst) + bid * a.stride;
     const E *tw = reinterpret_cast<const E *>(a.tw);
@@ -126,7 +132,6 @@ template <class F, int K> __global__ void __launch_bounds__(256, 2) ntt_pass_ker
     {
         constexpr int S0 = K - 3;
         const uint64_t k = j & ((1ull << a.log_ns) - 1);
-        const uint32_t tw_shift = a.log_n - a.log_ns - K;  // exponent scale n / (Ns R)
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const uint32_t r = ((uint32_t)e << S0) | q;
@@ -135,9 +140,10 @@ template <class F, int K> __global__ void __launch_bounds__(256, 2) ntt_pass_ker
                 v[e] = ld_el(src + idx);
                 if (a.first) {
                     if (a.coset_in)
-                        v[e] = E::mul(v[e], pow2l((const E *)a.off_lo, (const E *)a.off_hi, idx, a.split));
-                } else if (k != 0 && r != 0) {
-                    v[e] = E::mul(v[e], pow2l((const E *)a.w_lo, (const E *)a.w_hi, (k * r) << tw_shift, a.split));
+                        v[e] = E::mul(v[e], a.off_full ? ldg_el((const E *)a.off_full + idx)
+                                                       : pow2l((const E *)a.off_lo, (const E *)a.off_hi, idx, a.split));
+                } else {
+                    v[e] = E::mul(v[e], ldg_el((const E *)a.ptw + (((uint64_t)r << a.log_ns) | k)));
                 }
             } else {
                 v[e] = E::zero();
@@ -207,7 +213,8 @@ template <class F, int K> __global__ void __launch_bounds__(256, 2) ntt_pass_ker
             if (a.last) {
                 if (a.scale_mode == 1) o = E::mul(o, ldg_el(ninv));
                 else if (a.scale_mode == 2)
-                    o = E::mul(o, pow2l((const E *)a.off_lo, (const E *)a.off_hi, idx, a.split));
+                    o = E::mul(o, a.off_full ? ldg_el((const E *)a.off_full + idx)
+                                             : pow2l((const E *)a.off_lo, (const E *)a.off_hi, idx, a.split));
             }
             st_el(dst + idx, o);
         }
@@ -245,6 +252,24 @@ __global__ void pow_table_kernel(Fp<F> *table, Fp<F> base, Fp<F> scale, uint64_t
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     table[i] = Fp<F>::mul(scale, Fp<F>::pow_u64(base, (uint64_t)i * step_mul));
+}
+
+// ptw[(r << log_ns) | k] = scale * w^((k r) << tw_shift), from the two-level power tables
+template <class F>
+__global__ void pass_table_kernel(Fp<F> *out, const Fp<F> *w_lo, const Fp<F> *w_hi, int split, uint32_t log_ns, uint32_t k_bits,
+                                  uint32_t tw_shift, Fp<F> scale, int use_scale) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >> (log_ns + k_bits)) return;
+    const uint64_t k = i & ((1ull << log_ns) - 1), r = i >> log_ns;
+    Fp<F> t = pow2l(w_lo, w_hi, (k * r) << tw_shift, split);
+    if (use_scale) t = Fp<F>::mul(t, scale);
+    st_el(out + i, t);
+}
+// full[i] = lo[i & mask] * hi[i >> split]  (lo already carries any constant factor)
+template <class F>
+__global__ void full_table_kernel(Fp<F> *out, const Fp<F> *lo, const Fp<F> *hi, int split, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_el(out + i, pow2l(lo, hi, i, split));
 }
 
 // ---- host-side field helpers (serial, a handful of operations per plan) -----------------------
@@ -309,6 +334,18 @@ template <class F> static int build_plan(jf_ctx *ctx, NttPlan *pl, const uint64_
             JF_TRY(table(&pl->off_lo, off, out_scale, 1, lo_n));
             JF_TRY(table(&pl->off_hi, off, E::one(), lo_n, hi_n));
         }
+        const int npass = (int)pl->passes.size();
+        pl->ptw.assign(npass, nullptr);
+        pl->ninv_folded = pl->inverse && !pl->has_offset && npass >= 2;
+        for (int i = 1; i < npass; i++) {
+            const NttPass &ps = pl->passes[i];
+            const uint64_t count = 1ull << (ps.log_ns + ps.k);
+            JF_CUDA(ctx, cudaMalloc(&pl->ptw[i], sizeof(E) * count));
+            const bool fold = pl->ninv_folded && i == npass - 1;
+            JF_LAUNCH(ctx, "pass_table", pass_table_kernel<F><<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(
+                (E *)pl->ptw[i], (const E *)pl->w_lo, (const E *)pl->w_hi, pl->split, (uint32_t)ps.log_ns, (uint32_t)ps.k,
+                (uint32_t)(log_n - ps.log_ns - ps.k), ninv, fold ? 1 : 0));
+        }
         for (auto &ps : pl->passes) {
             if (pl->tw[ps.k]) continue;
             // w_{2^k}^i = w^(i * n / 2^k)
@@ -327,6 +364,8 @@ static void free_plan(NttPlan *pl) {
     cudaFree(pl->off_lo);
     cudaFree(pl->off_hi);
     cudaFree(pl->n_inv);
+    cudaFree(pl->off_full);
+    for (auto &t : pl->ptw) cudaFree(t);
     for (auto &t : pl->tw) cudaFree(t);
     delete pl;
 }
@@ -345,8 +384,8 @@ template <class F, int K> static int launch_pass(jf_ctx *ctx, const PassArgs &a)
         JF_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel<F, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    const uint64_t total_cols = ((uint64_t)1 << (a.log_n - K)) * a.batch;
-    const uint64_t blocks = (total_cols + B - 1) / B;
+    const uint64_t cols = (uint64_t)1 << (a.log_n - K);
+    const uint64_t blocks = ((cols + B - 1) / B) * a.batch;
     if (blocks > 0x7fffffffull) return fail(ctx, JF_ERR_INVALID_ARG, "ntt: batch too large");
     JF_LAUNCH(ctx, "ntt_pass", ntt_pass_kernel<F, K><<<(unsigned)blocks, 256, smem, ctx->stream>>>(a));
     return JF_OK;
@@ -440,6 +479,12 @@ static int ntt_run_t(jf_ctx *ctx, int field, void *d_data, void *d_out, size_t i
         JF_TRY(scratch(ctx, "ntt_t1", span * sizeof(E), &t1));
         for (int i = 1; i < np; i++) hop[i] = (i % 2 == 1) ? t1 : d_data;
     }
+    // dense coset input / coset output scaling: one multiplication per element from a full table
+    if (has_off && !pl->off_full && (inverse || in_len > n / 4)) {
+        JF_CUDA(ctx, cudaMalloc(&pl->off_full, sizeof(E) * n));
+        JF_LAUNCH(ctx, "full_table", full_table_kernel<F><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+            (E *)pl->off_full, (const E *)pl->off_lo, (const E *)pl->off_hi, pl->split, (uint64_t)n));
+    }
     for (int i = 0; i < np; i++) {
         PassArgs a;
         a.src = hop[i];
@@ -452,7 +497,9 @@ static int ntt_run_t(jf_ctx *ctx, int field, void *d_data, void *d_out, size_t i
         a.first = i == 0;
         a.last = i == np - 1;
         a.coset_in = (!inverse && has_off) ? 1 : 0;
-        a.scale_mode = inverse ? (has_off ? 2 : 1) : 0;
+        a.scale_mode = inverse ? (has_off ? 2 : (pl->ninv_folded ? 0 : 1)) : 0;
+        a.ptw = pl->ptw[i];
+        a.off_full = (inverse || in_len > n / 4) ? pl->off_full : nullptr;
         a.split = pl->split;
         a.w_lo = pl->w_lo;
         a.w_hi = pl->w_hi;
