@@ -229,7 +229,17 @@ msm_accumulate_kernel(const Affine<Fq> *points, uint32_t srs_n, const uint32_t *
     }
     uint32_t b = lo, next = off[b + 1];
     XYZZ<Fq> acc = XYZZ<Fq>::inf();
+    // software pipeline: the gather of entry pos + 1 (a random 64-byte read, ~1 us from HBM) is in flight
+    // while entry pos is being added
+    uint32_t pl = sorted[start];
+    Affine<Fq> p = load_affine(points + (size_t)((pl >> IDX_BITS) & 31u) * srs_n + (pl & IDX_MASK));
     for (uint32_t pos = start; pos < end; pos++) {
+        const uint32_t cur_pl = pl;
+        Affine<Fq> cur = p;
+        if (pos + 1 < end) {
+            pl = sorted[pos + 1];
+            p = load_affine(points + (size_t)((pl >> IDX_BITS) & 31u) * srs_n + (pl & IDX_MASK));
+        }
         if (pos >= next) {
             store_xyzz(partials + (size_t)t + b, acc);
             acc = XYZZ<Fq>::inf();
@@ -238,12 +248,9 @@ msm_accumulate_kernel(const Affine<Fq> *points, uint32_t srs_n, const uint32_t *
                 next = off[b + 1];
             } while (pos >= next);
         }
-        const uint32_t pl = sorted[pos];
-        const Affine<Fq> *src = points + (size_t)((pl >> IDX_BITS) & 31u) * srs_n + (pl & IDX_MASK);
-        Affine<Fq> p = load_affine(src);
-        if (p.is_inf()) continue;
-        if (pl & 0x80000000u) p.y = Fp<Fq>::neg(p.y);
-        acc.add_affine(p);
+        if (cur.is_inf()) continue;
+        if (cur_pl & 0x80000000u) cur.y = Fp<Fq>::neg(cur.y);
+        acc.add_affine(cur);
     }
     store_xyzz(partials + (size_t)t + b, acc);
 }
