@@ -137,7 +137,9 @@ int jf_ntt_device(jf_ctx *ctx, int field, void *d_data, size_t in_len, unsigned 
  * jf_plonk_preprocess == `PlonkKzgSnark::preprocess` (plonk/src/proof_system/snark.rs:529-611): 18 iNTTs,
  * 18 commitments; the selector / sigma polynomials stay resident (the `ProvingKey`).  flags & 1: also
  * keep their 8n coset evaluations resident (18 of the 25 coset NTTs of round 3 then happen once per
- * key instead of once per proof; +4.5 GiB at n = 2^20).  `srs` must outlive the key and hold >= n + 3 points. */
+ * key instead of once per proof; +4.5 GiB at n = 2^20).  flags & 2: selector columns that are identically
+ * zero (e.g. q_hash / q_ecc in circuits without Rescue or ECC gates) are recognised once and their coset NTTs and
+ * quotient terms are skipped; the proof is unchanged.  `srs` must outlive the key and hold >= n + 3 points. */
 int jf_plonk_preprocess(jf_ctx *ctx, const jf_srs *srs, unsigned log_n, const uint64_t *selector_evals,
                         const uint64_t *sigma_evals, const uint64_t *k, const uint32_t *wire_variables, size_t num_vars,
                         const uint32_t *pub_input_gate_ids, size_t num_inputs, int flags, jf_plonk_pk **out);

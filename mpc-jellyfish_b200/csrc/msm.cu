@@ -82,6 +82,21 @@ template <class Fn> __device__ __forceinline__ void for_each_digit(const uint32_
     }
 }
 
+// The top window of a scalar holds only (BITS + 1) - (W - 1) c bits; when that is a handful of bits,
+// every scalar lands in the same few buckets there and plain atomics serialise.  Lanes of a warp that
+// hit the same bucket are therefore merged (one atomic per distinct bucket per warp) in that window.
+static constexpr int AGG_TOP_BITS = 10;
+
+__device__ __forceinline__ uint32_t agg_atomic_add(uint32_t *ctr, uint32_t bucket) {
+    const uint32_t active = __activemask();
+    const uint32_t peers = __match_any_sync(active, bucket);
+    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&ctr[bucket], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1));
+}
+
 template <class Fr>
 __global__ void msm_count_kernel(const uint32_t *scalars, MsmGeom g, uint32_t *counts, int *err) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,10 +106,12 @@ __global__ void msm_count_kernel(const uint32_t *scalars, MsmGeom g, uint32_t *c
         *err = JF_ERR_SCALAR_RANGE;
         return;
     }
+    const bool agg_top = Fr::BITS + 1 - (g.W - 1) * g.c <= AGG_TOP_BITS;
     for_each_digit(s, g.c, g.W, [&](int w, int32_t d) {
         uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
         uint32_t bucket = (uint32_t)(w / g.T) * g.NB + (mag - 1);
-        atomicAdd(&counts[bucket], 1u);
+        if (agg_top && w == g.W - 1) agg_atomic_add(counts, bucket);
+        else atomicAdd(&counts[bucket], 1u);
     });
 }
 
@@ -104,10 +121,11 @@ __global__ void msm_scatter_kernel(const uint32_t *scalars, MsmGeom g, uint32_t 
     if (i >= g.n) return;
     uint32_t s[8];
     if (!load_scalar<Fr>(scalars + 8 * (size_t)i, g.mont, s)) return;
+    const bool agg_top = Fr::BITS + 1 - (g.W - 1) * g.c <= AGG_TOP_BITS;
     for_each_digit(s, g.c, g.W, [&](int w, int32_t d) {
         uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
         uint32_t bucket = (uint32_t)(w / g.T) * g.NB + (mag - 1);
-        uint32_t pos = atomicAdd(&cursor[bucket], 1u);
+        uint32_t pos = (agg_top && w == g.W - 1) ? agg_atomic_add(cursor, bucket) : atomicAdd(&cursor[bucket], 1u);
         sorted[pos] = (d < 0 ? 0x80000000u : 0u) | ((uint32_t)(w % g.T) << IDX_BITS) | (g.base_offset + i);
     });
 }
@@ -448,7 +466,7 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
         (const Affine<Fq> *)srs->d_points, g.srs_n, sorted, off, total, partials));
     JF_CUDA(ctx, cudaMemsetAsync(heavy, 0, sizeof(uint32_t), st));
     JF_LAUNCH(ctx, "bucket_sum", bucket_sum_kernel<Fq><<<(total + 127) / 128, 128, 0, st>>>(partials, off, total, acc_threads, XA, heavy, heavy + 1));
-    JF_LAUNCH(ctx, "bucket_sum_heavy", bucket_sum_heavy_kernel<Fq><<<64, HEAVY_THREADS, 0, st>>>(partials, off, total, acc_threads, XA, heavy, heavy + 1));
+    JF_LAUNCH(ctx, "bucket_sum_heavy", bucket_sum_heavy_kernel<Fq><<<(unsigned)ctx->sm_count * 4, HEAVY_THREADS, 0, st>>>(partials, off, total, acc_threads, XA, heavy, heavy + 1));
     {
         uint32_t nlev = g.NB, m = 0;
         P *x = XA, *xo = XB, *pin = PA, *pout = PB;
@@ -581,12 +599,19 @@ int srs_generate(jf_ctx *ctx, int curve, const uint64_t *beta, size_t first_powe
     return fail(ctx, JF_ERR_INVALID_ARG, "unknown curve");
 }
 
+// Window bits by size, from a sweep on B200 (tools/sweep_c.py; precomputed tables): the accumulate work falls
+// with c, the bucket reduction is latency bound (~20 us per level) and grows with it.
 static int pick_window(size_t n) {
+    if (n > ((size_t)1 << 23) + 64) return 21;
+    if (n > ((size_t)1 << 21) + 64) return 20;
+    if (n > ((size_t)1 << 18) + 64) return 17;
     int lg = 0;
     while (((size_t)1 << lg) < n) lg++;
-    int c = lg - 4;  // 2^20 -> 16
+    if (n > ((size_t)1 << 16) + 64) return 17;
+    int c = lg - 1;
+    if (n <= ((size_t)1 << lg) / 2 + 64 && lg > 0) c = lg - 2;  // just above a power of two: do not round up
     if (c < 8) c = 8;
-    if (c > 20) c = 20;
+    if (c > 15) c = 15;
     return c;
 }
 

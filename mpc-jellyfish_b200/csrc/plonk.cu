@@ -262,6 +262,7 @@ template <class F> struct QuotArgs {
     Fp<F> zh_inv[8];
     Fp<F> *out;
     uint32_t m, ratio;
+    uint32_t zero_sel;  // bit s set: selector s is the zero polynomial (its term and its loads are skipped)
 };
 template <class F> __device__ __forceinline__ Fp<F> pow5(const Fp<F> &x) {
     Fp<F> x2 = Fp<F>::sqr(x);
@@ -277,20 +278,22 @@ template <class F> __global__ void __launch_bounds__(128) quotient_kernel(const 
     for (int j = 0; j < NW; j++) w[j] = ldf(q.w + j * m + i);
     auto S = [&](int s) { return ldf(q.sel + s * m + i); };
     // circuit part (prover.rs:696-708); selector order q_lc 0-3, q_mul 4-5, q_hash 6-9, q_o 10, q_c 11, q_ecc 12
+    auto on = [&](int s) { return !((q.zero_sel >> s) & 1u); };  // uniform across the grid
     E w01 = E::mul(w[0], w[1]), w23 = E::mul(w[2], w[3]);
-    E t = E::add(S(11), ldf(q.pi + i));
-    t = E::add(t, E::mul(S(0), w[0]));
-    t = E::add(t, E::mul(S(1), w[1]));
-    t = E::add(t, E::mul(S(2), w[2]));
-    t = E::add(t, E::mul(S(3), w[3]));
-    t = E::add(t, E::mul(S(4), w01));
-    t = E::add(t, E::mul(S(5), w23));
-    t = E::add(t, E::mul(S(12), E::mul(E::mul(w01, w23), w[4])));
-    t = E::add(t, E::mul(S(6), pow5(w[0])));
-    t = E::add(t, E::mul(S(7), pow5(w[1])));
-    t = E::add(t, E::mul(S(8), pow5(w[2])));
-    t = E::add(t, E::mul(S(9), pow5(w[3])));
-    t = E::sub(t, E::mul(S(10), w[4]));
+    E t = ldf(q.pi + i);
+    if (on(11)) t = E::add(t, S(11));
+    if (on(0)) t = E::add(t, E::mul(S(0), w[0]));
+    if (on(1)) t = E::add(t, E::mul(S(1), w[1]));
+    if (on(2)) t = E::add(t, E::mul(S(2), w[2]));
+    if (on(3)) t = E::add(t, E::mul(S(3), w[3]));
+    if (on(4)) t = E::add(t, E::mul(S(4), w01));
+    if (on(5)) t = E::add(t, E::mul(S(5), w23));
+    if (on(12)) t = E::add(t, E::mul(S(12), E::mul(E::mul(w01, w23), w[4])));
+    if (on(6)) t = E::add(t, E::mul(S(6), pow5(w[0])));
+    if (on(7)) t = E::add(t, E::mul(S(7), pow5(w[1])));
+    if (on(8)) t = E::add(t, E::mul(S(8), pow5(w[2])));
+    if (on(9)) t = E::add(t, E::mul(S(9), pow5(w[3])));
+    if (on(10)) t = E::sub(t, E::mul(S(10), w[4]));
     // copy constraints (prover.rs:743-756)
     const E x = E::mul(ldf(q.x_lo + (i & ((1u << q.lo_bits) - 1))), ldf(q.x_hi + (i >> q.lo_bits)));
     const E zx = ldf(q.z + i);
@@ -410,6 +413,7 @@ struct jf_plonk_pk {
     size_t num_vars = 0;
     uint32_t num_inputs = 0;
     int cache_coset = 0;
+    uint32_t zero_sel = 0;  // selectors that are identically zero (flags & 2)
     std::vector<uint32_t> pub_vars;  // variable index of every public input, in io-gate order
     // device, persistent
     void *d_sel = nullptr, *d_sig = nullptr, *d_sig_evals = nullptr;  // NSEL x n, NW x n coefficients; NW x n values
@@ -620,6 +624,14 @@ template <class C> struct Plonk {
         pk->num_vars = num_vars;
         pk->num_inputs = (uint32_t)num_inputs;
         pk->cache_coset = flags & 1;
+        if (flags & 2) {
+            for (int sel = 0; sel < NSEL; sel++) {
+                const uint64_t *col = selector_evals + (size_t)sel * 4 * n;
+                uint64_t acc = 0;
+                for (size_t i = 0; i < 4 * n; i++) acc |= col[i];
+                if (!acc) pk->zero_sel |= 1u << sel;
+            }
+        }
         int rc = preprocess_inner(ctx, pk, selector_evals, sigma_evals, k, wire_variables, pub_gate_ids);
         if (rc != JF_OK) {
             cudaStreamSynchronize(ctx->stream);
@@ -727,7 +739,7 @@ template <class C> struct Plonk {
         pk->vk_inf.resize(NSEL + NW);
         JF_TRY(fetch_commits(ctx, pk, 0, NSEL + NW, pk->vk_xy.data(), pk->vk_inf.data()));
         if (pk->cache_coset) {
-            JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sel, n, n, NSEL, (E *)pk->d_cached));
+            JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sel, n, n, NSEL, (E *)pk->d_cached, pk->zero_sel));
             JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sig, n, n, NW, (E *)pk->d_cached + (size_t)NSEL * m));
         }
         // transcript prefix (transcript/mod.rs:45-88): sizes, k, selector and sigma commitments
@@ -736,13 +748,22 @@ template <class C> struct Plonk {
     }
 
     // rows of coefficients (`len` valid, `stride` apart) -> rows of m coset evaluations in `dst`
-    static int coset_fft_rows(jf_ctx *ctx, const jf_plonk_pk *pk, const E *src, size_t stride, size_t len, int rows, E *dst) {
+    // Rows whose bit is set in `skip` are zero polynomials: their (all-zero) evaluations are never read.
+    static int coset_fft_rows(jf_ctx *ctx, const jf_plonk_pk *pk, const E *src, size_t stride, size_t len, int rows, E *dst,
+                              uint32_t skip = 0) {
         const size_t m = pk->m, in_len = pk->n + 3;
         dim3 grid((unsigned)((in_len + 255) / 256), rows);
         JF_LAUNCH(ctx, "copy_rows", copy_rows_kernel<Fr><<<grid, 256, 0, ctx->stream>>>(src, stride, dst, m, len, in_len));
-        for (int r = 0; r < rows; r += 5) {
-            const int b = std::min(5, rows - r);
+        int r = 0;
+        while (r < rows) {
+            if ((skip >> r) & 1u) {
+                r++;
+                continue;
+            }
+            int b = 1;
+            while (b < 5 && r + b < rows && !((skip >> (r + b)) & 1u)) b++;
             JF_TRY(ntt_run(ctx, C::FR_ID, dst + (size_t)r * m, dst + (size_t)r * m, in_len, pk->log_m, 0, pk->gen_limbs, b, m));
+            r += b;
         }
         return JF_OK;
     }
@@ -831,7 +852,7 @@ template <class C> struct Plonk {
                 sig_c = sel_c + (size_t)NSEL * m;
                 w_c = Ev;
             } else {
-                JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sel, n, n, NSEL, Ev));
+                JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sel, n, n, NSEL, Ev, pk->zero_sel));
                 JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sig, n, n, NW, Ev + (size_t)NSEL * m));
                 sel_c = Ev;
                 sig_c = Ev + (size_t)NSEL * m;
@@ -861,6 +882,7 @@ template <class C> struct Plonk {
             q.out = (E *)pk->d_q;
             q.m = (uint32_t)m;
             q.ratio = 8;
+            q.zero_sel = pk->zero_sel;
             JF_LAUNCH(ctx, "quotient", quotient_kernel<Fr><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(q));
             JF_TRY(ntt_run(ctx, C::FR_ID, pk->d_q, pk->d_q, m, pk->log_m, 1, pk->gen_limbs, 1, m));
             const size_t deg = NW * (n + 1) + 2;  // quotient_polynomial_degree (prover.rs:1126-1128)
@@ -921,7 +943,8 @@ template <class C> struct Plonk {
             const E w01 = E::mul(we[0], we[1]), w23 = E::mul(we[2], we[3]);
             const E qs[NSEL] = {we[0], we[1], we[2], we[3], w01, w23, pow_small(we[0], 5), pow_small(we[1], 5), pow_small(we[2], 5),
                                 pow_small(we[3], 5), E::neg(we[4]), one, E::mul(E::mul(w01, w23), we[4])};
-            for (int s = 0; s < NSEL; s++) push(sel + (size_t)s * n, n, qs[s]);
+            for (int s = 0; s < NSEL; s++)
+                if (!((pk->zero_sel >> s) & 1u)) push(sel + (size_t)s * n, n, qs[s]);
             // permutation part
             E c1 = alpha;
             for (int j = 0; j < NW; j++) c1 = E::mul(c1, E::add(E::add(we[j], E::mul(E::mul(beta, kf(pk, j)), zeta)), gamma));

@@ -76,7 +76,7 @@ def test_proof_bytes_match_the_cpu_restatement(ctx, co, py, P, name):
     key.free()
 
 
-def test_cached_coset_evaluations_give_the_same_proof(ctx, co, py, P):
+def test_cached_coset_evaluations_and_zero_selector_skip_give_the_same_proof(ctx, co, py, P):
     import mpc_jellyfish_b200 as jf
     import plonk_util as U
     fr = py.BN254_FR
@@ -85,14 +85,14 @@ def test_cached_coset_evaluations_give_the_same_proof(ctx, co, py, P):
     key = ctx.generate_srs_for_testing("bn254", BETA % fr.p, cs.n + 3)
     _, bl = _blinders(co, fr, 5)
     outs = []
-    for cache in (False, True):
+    for cache, skip in ((False, False), (True, False), (False, True), (True, True)):
         pk = jf.PlonkKzgSnark.preprocess(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"],
-                                         arr["pub_gate_ids"], cache_coset_evals=cache)
+                                         arr["pub_gate_ids"], cache_coset_evals=cache, skip_zero_selectors=skip)
         outs.append(jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, "standard").serialize_compressed())
         # the key is reusable: a second proof with other masks differs but has the same evaluations' count
         outs.append(jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, "standard").serialize_compressed())
         pk.free()
-    assert outs[0] == outs[1] == outs[2] == outs[3]
+    assert len(set(outs)) == 1 and len(outs) == 8
     key.free()
 
 
