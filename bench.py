@@ -362,7 +362,7 @@ def run_cuda(args):
     n = 1 << LOG_N
     ctx = jf.Context(local)
     # a real (non-default) stream shared by torch (copies, NCCL, events) and the library's kernels
-    stream = torch.cuda.Stream()
+    stream = torch.cuda.Stream(priority=-1)  # high priority: the library's side streams only fill its idle slots
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 

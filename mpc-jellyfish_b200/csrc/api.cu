@@ -84,7 +84,10 @@ int jf_ctx_create(int device, jf_ctx **out) {
         return JF_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // highest priority: the library's own side streams (lowest) only fill what this stream leaves idle
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
         cudaMalloc((void **)&ctx->d_err, 64) != cudaSuccess || cudaMemset(ctx->d_err, 0, 64) != cudaSuccess) {
         delete ctx;
         return JF_ERR_CUDA;

@@ -27,6 +27,7 @@ struct jf_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
+    int lane = 0;  // 1 while work is being issued on a secondary stream: scratch buffers are kept apart per lane
     std::mutex mu;
     std::string err;
     uint64_t launches = 0;
@@ -78,7 +79,7 @@ inline int fail(jf_ctx *ctx, int code, const std::string &msg) {
 
 // scratch buffer of at least `bytes`, named so that independent users do not alias
 inline int scratch(jf_ctx *ctx, const char *name, size_t bytes, void **out) {
-    DevBuf &b = ctx->scratch[name];
+    DevBuf &b = ctx->scratch[ctx->lane ? std::string(name) + "#1" : std::string(name)];
     if (b.cap < bytes) {
         if (b.ptr) {
             JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

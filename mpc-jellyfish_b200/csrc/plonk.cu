@@ -433,6 +433,9 @@ struct jf_plonk_pk {
     std::vector<int> vk_inf;
     std::vector<uint8_t> vk_transcript_prefix;  // everything append_vk_and_pub_input adds before the public inputs
     std::vector<void *> allocs;
+    // secondary stream: coset NTTs that do not depend on the next challenge run beside the commitments
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr;
 };
 
 namespace jf {
@@ -632,6 +635,14 @@ template <class C> struct Plonk {
                 if (!acc) pk->zero_sel |= 1u << sel;
             }
         }
+        int prio_least = 0, prio_greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+        if (cudaStreamCreateWithPriority(&pk->side, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+            cudaEventCreateWithFlags(&pk->ev_main, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&pk->ev_side, cudaEventDisableTiming) != cudaSuccess) {
+            delete pk;
+            return fail(ctx, JF_ERR_CUDA, "preprocess: cannot create the side stream");
+        }
         int rc = preprocess_inner(ctx, pk, selector_evals, sigma_evals, k, wire_variables, pub_gate_ids);
         if (rc != JF_OK) {
             cudaStreamSynchronize(ctx->stream);
@@ -768,6 +779,25 @@ template <class C> struct Plonk {
         return JF_OK;
     }
 
+    // Issue `body` on the side stream, ordered after everything issued on the main stream so far.
+    template <class Fn> static int on_side(jf_ctx *ctx, jf_plonk_pk *pk, Fn body) {
+        cudaStream_t main_stream = ctx->stream;
+        JF_CUDA(ctx, cudaEventRecord(pk->ev_main, main_stream));
+        JF_CUDA(ctx, cudaStreamWaitEvent(pk->side, pk->ev_main, 0));
+        ctx->stream = pk->side;
+        ctx->lane = 1;
+        int rc = body();
+        ctx->stream = main_stream;
+        ctx->lane = 0;
+        return rc;
+    }
+    // the main stream waits for everything issued on the side stream so far
+    static int join_side(jf_ctx *ctx, jf_plonk_pk *pk) {
+        JF_CUDA(ctx, cudaEventRecord(pk->ev_side, pk->side));
+        JF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pk->ev_side, 0));
+        return JF_OK;
+    }
+
     static void append_vk_and_pub_input(Transcript &tr, const jf_plonk_pk *pk, const E *pub, size_t npub) {
         const uint32_t bits = Fr::BITS;
         const uint64_t dom = pk->n, nin = pk->num_inputs;
@@ -793,6 +823,26 @@ template <class C> struct Plonk {
 
         JF_CUDA(ctx, cudaMemcpyAsync(pk->d_wit, witness, fe * pk->num_vars, cudaMemcpyHostToDevice, st));
         JF_CUDA(ctx, cudaMemcpyAsync(bl, blinders, fe * NBLIND, cudaMemcpyHostToDevice, st));
+        // coset-evaluation slots (8n each): selectors, sigmas (or the resident copies), wires, z, PI
+        E *Ev = (E *)pk->d_e;
+        const E *sel_c, *sig_c;
+        E *w_c, *z_c, *pi_c;
+        if (pk->cache_coset) {
+            sel_c = (const E *)pk->d_cached;
+            sig_c = sel_c + (size_t)NSEL * m;
+            w_c = Ev;
+        } else {
+            sel_c = Ev;
+            sig_c = Ev + (size_t)NSEL * m;
+            w_c = Ev + (size_t)(NSEL + NW) * m;
+            // independent of this proof's challenges: runs on the side stream beside rounds 1 and 2
+            JF_TRY(on_side(ctx, pk, [&]() -> int {
+                JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sel, n, n, NSEL, Ev, pk->zero_sel));
+                return coset_fft_rows(ctx, pk, (const E *)pk->d_sig, n, n, NW, Ev + (size_t)NSEL * m);
+            }));
+        }
+        z_c = w_c + (size_t)NW * m;
+        pi_c = z_c + m;
         Transcript tr(kind, "PlonkProof");
         if (extra) tr.append_message("extra info", extra, extra_len);
         {
@@ -810,6 +860,11 @@ template <class C> struct Plonk {
                 (const E *)pk->d_wit, pk->d_wire_vars + (size_t)(NW - 1) * n, pk->d_gate_ids, pk->num_inputs, PI));
         JF_TRY(intt_n(ctx, pk, W, NW + 1, np));
         for (int j = 0; j < NW; j++) JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(W + (size_t)j * np, n, bl + 2 * j, 2));
+        // the wire / PI polynomials are final: their coset NTTs run beside the commitments
+        JF_TRY(on_side(ctx, pk, [&]() -> int {
+            JF_TRY(coset_fft_rows(ctx, pk, W, np, n + 2, NW, w_c));
+            return coset_fft_rows(ctx, pk, PI, np, n, 1, pi_c);
+        }));
         for (int j = 0; j < NW; j++) JF_TRY(commit_dev(ctx, pk, W + (size_t)j * np, n + 2, j));
         JF_TRY(fetch_commits(ctx, pk, 0, NW, out->wires_poly_comms, out->wires_inf));
         for (int j = 0; j < NW; j++) tr_g1(tr, "witness_poly_comms", out->wires_poly_comms + 2 * L * j, out->wires_inf[j]);
@@ -837,6 +892,7 @@ template <class C> struct Plonk {
             JF_LAUNCH(ctx, "z_combine", z_combine_kernel<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(PA, SB, small, Z, (uint32_t)n));
             JF_TRY(intt_n(ctx, pk, Z, 1, np));
             JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(Z, n, bl + 10, 3));
+            JF_TRY(on_side(ctx, pk, [&]() -> int { return coset_fft_rows(ctx, pk, Z, np, n + 3, 1, z_c); }));
             JF_TRY(commit_dev(ctx, pk, Z, n + 3, 0));
             JF_TRY(fetch_commits(ctx, pk, 0, 1, out->prod_perm_poly_comm, &out->prod_perm_inf));
             tr_g1(tr, "perm_poly_comms", out->prod_perm_poly_comm, out->prod_perm_inf);
@@ -844,25 +900,7 @@ template <class C> struct Plonk {
         // ---- round 3 (prover.rs:192-209, 512-673, 902-960) ----
         const E alpha = challenge(tr, "alpha");
         {
-            E *Ev = (E *)pk->d_e;
-            const E *sel_c, *sig_c;
-            E *w_c, *z_c, *pi_c;
-            if (pk->cache_coset) {
-                sel_c = (const E *)pk->d_cached;
-                sig_c = sel_c + (size_t)NSEL * m;
-                w_c = Ev;
-            } else {
-                JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sel, n, n, NSEL, Ev, pk->zero_sel));
-                JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sig, n, n, NW, Ev + (size_t)NSEL * m));
-                sel_c = Ev;
-                sig_c = Ev + (size_t)NSEL * m;
-                w_c = Ev + (size_t)(NSEL + NW) * m;
-            }
-            z_c = w_c + (size_t)NW * m;
-            pi_c = z_c + m;
-            JF_TRY(coset_fft_rows(ctx, pk, W, np, n + 2, NW, w_c));
-            JF_TRY(coset_fft_rows(ctx, pk, Z, np, n + 3, 1, z_c));
-            JF_TRY(coset_fft_rows(ctx, pk, PI, np, n, 1, pi_c));
+            JF_TRY(join_side(ctx, pk));  // all 25 coset evaluation vectors are in place
             QuotArgs<Fr> q;
             q.sel = sel_c;
             q.sig = sig_c;
@@ -1108,10 +1146,14 @@ void jf_plonk_pk_free(jf_ctx *ctx, jf_plonk_pk *pk) {
         std::lock_guard<std::mutex> lock(ctx->mu);
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
+        if (pk->side) cudaStreamSynchronize(pk->side);
         for (void *p : pk->allocs) cudaFree(p);
     } else {
         for (void *p : pk->allocs) cudaFree(p);
     }
+    if (pk->ev_main) cudaEventDestroy(pk->ev_main);
+    if (pk->ev_side) cudaEventDestroy(pk->ev_side);
+    if (pk->side) cudaStreamDestroy(pk->side);
     delete pk;
 }
 
