@@ -135,7 +135,7 @@ def run_reference(args):
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 
@@ -538,7 +538,7 @@ def run_cuda(args):
         "ntt": ntt,
         "prove": prove,
     }
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -547,7 +547,21 @@ def co_modulus():
     return 21888242871839275222246405745257275088548364400416034343698204186575808495617
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version banner,
+    make output of the oracle build, ...) has been routed to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

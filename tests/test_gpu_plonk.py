@@ -76,6 +76,31 @@ def test_proof_bytes_match_the_cpu_restatement(ctx, co, py, P, name):
     key.free()
 
 
+@pytest.mark.parametrize("name,kind", [("test_m2", "standard"), ("test_m20", "solidity")])
+def test_bls12_381_proofs_match_the_cpu_restatement(ctx, co, py, P, name, kind):
+    """The same prover over BLS12-381 (48-byte compressed points, 255-bit Fr, GENERATOR 7, its own k)."""
+    import mpc_jellyfish_b200 as jf
+    import plonk_util as U
+    cv, fr = py.BLS12_381, py.BLS12_381_FR
+    cs = {"test_m2": lambda: P.gen_circuit_for_test(2, 3, fr), "test_m20": lambda: P.gen_circuit_for_test(20, 1, fr)}[name]()
+    beta = BETA % fr.p
+    arr = U.arrays_from_oracle_circuit(co, py, cs)
+    key = ctx.generate_srs_for_testing("bls12_381", beta, cs.n + 3)
+    pk = jf.PlonkKzgSnark.preprocess(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"],
+                                     arr["pub_gate_ids"], skip_zero_selectors=True)
+    opk = P.preprocess(cv, P.gen_srs(cv, beta, cs.n + 2), cs)
+    vk = U.vk_from_product(co, cv, pk, cs.k)
+    assert vk["selector_comms"] == opk["vk"]["selector_comms"] and vk["sigma_comms"] == opk["vk"]["sigma_comms"]
+    ints, bl = _blinders(co, fr, 21)
+    proof = jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, kind)
+    want = P.prove(cv, cs, opk, ints, kind)
+    ser = proof.serialize_compressed()
+    assert len(ser) == 8 * 4 + 48 * 13 + 32 * 10 + 1 and ser == P.serialize_proof(cv, want)
+    assert P.verify(cv, opk["vk"], cs.public_input(), U.proof_to_oracle(co, cv, proof), beta, kind)
+    pk.free()
+    key.free()
+
+
 def test_cached_coset_evaluations_and_zero_selector_skip_give_the_same_proof(ctx, co, py, P):
     import mpc_jellyfish_b200 as jf
     import plonk_util as U
