@@ -425,6 +425,7 @@ struct jf_plonk_pk {
     void *d_wit = nullptr, *d_bl = nullptr, *d_wv = nullptr, *d_w = nullptr /* (NW+1) x np: wires + PI */, *d_z = nullptr;
     void *d_a = nullptr, *d_b = nullptr, *d_tmp = nullptr, *d_e = nullptr, *d_q = nullptr, *d_split = nullptr;
     void *d_bp = nullptr, *d_t = nullptr, *d_s = nullptr, *d_wz = nullptr, *d_small = nullptr, *d_res = nullptr;
+    void *d_side = nullptr;  // scratch of the side stream's division (3 np + scan temporaries)
     // host constants (Montgomery)
     uint32_t k[NW][8], omega_n[8], omega_m[8], gen[8], zh_inv[8][8];
     uint64_t gen_limbs[4];
@@ -538,6 +539,27 @@ template <class C> struct Plonk {
     // commitments of `count` device polynomials (Montgomery coefficients) -> d_res[slot..]
     static int commit_dev(jf_ctx *ctx, const jf_plonk_pk *pk, const void *d_poly, size_t len, int slot) {
         return msm_run(ctx, pk->srs, 0, d_poly, len, 1, (char *)pk->d_res + PT * slot);
+    }
+    // `count` commitments, alternating between the main and the side stream: the latency-bound phases of one
+    // MSM (digit sort, bucket reduction) overlap the bucket accumulation of the next.  The side stream must
+    // be idle-able here (no queued NTT work the caller still waits for).
+    struct CommitJob { const void *poly; size_t len; int slot; };
+    static int commit_many(jf_ctx *ctx, jf_plonk_pk *pk, const CommitJob *jobs, int count) {
+        cudaStream_t main_stream = ctx->stream;
+        JF_CUDA(ctx, cudaEventRecord(pk->ev_main, main_stream));
+        JF_CUDA(ctx, cudaStreamWaitEvent(pk->side, pk->ev_main, 0));
+        int rc = JF_OK;
+        for (int i = 0; i < count && rc == JF_OK; i++) {
+            if (i & 1) {
+                ctx->stream = pk->side;
+                ctx->lane = 1;
+            }
+            rc = commit_dev(ctx, pk, jobs[i].poly, jobs[i].len, jobs[i].slot);
+            ctx->stream = main_stream;
+            ctx->lane = 0;
+        }
+        JF_TRY(rc);
+        return join_side(ctx, pk);
     }
     // bring `count` XYZZ results back and normalise (into_affine)
     static int fetch_commits(jf_ctx *ctx, const jf_plonk_pk *pk, int slot, int count, uint64_t *xy, int *inf) {
@@ -719,6 +741,7 @@ template <class C> struct Plonk {
         JF_TRY(dalloc(ctx, pk, fe * np, &pk->d_t));
         JF_TRY(dalloc(ctx, pk, fe * np, &pk->d_s));
         JF_TRY(dalloc(ctx, pk, fe * np, &pk->d_wz));
+        JF_TRY(dalloc(ctx, pk, fe * (3 * np + np / 256 + 4096), &pk->d_side));
         JF_TRY(dalloc(ctx, pk, fe * 64, &pk->d_small));
         JF_TRY(dalloc(ctx, pk, PT * 32, &pk->d_res));
         if (pk->cache_coset) JF_TRY(dalloc(ctx, pk, fe * (size_t)(NSEL + NW) * m, &pk->d_cached));
@@ -744,8 +767,12 @@ template <class C> struct Plonk {
         // selector / sigma polynomials (ifft) and the 18 verifying-key commitments
         JF_TRY(intt_n(ctx, pk, pk->d_sel, NSEL, n));
         JF_TRY(intt_n(ctx, pk, pk->d_sig, NW, n));
-        for (int i = 0; i < NSEL; i++) JF_TRY(commit_dev(ctx, pk, (E *)pk->d_sel + (size_t)i * n, n, i));
-        for (int i = 0; i < NW; i++) JF_TRY(commit_dev(ctx, pk, (E *)pk->d_sig + (size_t)i * n, n, NSEL + i));
+        {
+            CommitJob jobs[NSEL + NW];
+            for (int i = 0; i < NSEL; i++) jobs[i] = {(E *)pk->d_sel + (size_t)i * n, n, i};
+            for (int i = 0; i < NW; i++) jobs[NSEL + i] = {(E *)pk->d_sig + (size_t)i * n, n, NSEL + i};
+            JF_TRY(commit_many(ctx, pk, jobs, NSEL + NW));
+        }
         pk->vk_xy.resize((size_t)(NSEL + NW) * 2 * L);
         pk->vk_inf.resize(NSEL + NW);
         JF_TRY(fetch_commits(ctx, pk, 0, NSEL + NW, pk->vk_xy.data(), pk->vk_inf.data()));
@@ -928,10 +955,10 @@ template <class C> struct Plonk {
                 (const E *)pk->d_q, deg, m, ctx->d_err + 1));
             dim3 grid((unsigned)((np + 255) / 256), NW);
             JF_LAUNCH(ctx, "split", split_kernel<Fr><<<grid, 256, 0, st>>>((const E *)pk->d_q, n, deg + 1, bl + 13, (E *)pk->d_split, np));
-            for (int i = 0; i < NW; i++) {
-                const size_t len = i < NW - 1 ? n + 3 : deg + 1 - (size_t)(NW - 1) * (n + 2);
-                JF_TRY(commit_dev(ctx, pk, (E *)pk->d_split + (size_t)i * np, len, i));
-            }
+            CommitJob jobs[NW];
+            for (int i = 0; i < NW; i++)
+                jobs[i] = {(E *)pk->d_split + (size_t)i * np, i < NW - 1 ? n + 3 : deg + 1 - (size_t)(NW - 1) * (n + 2), i};
+            JF_TRY(commit_many(ctx, pk, jobs, NW));
             JF_TRY(fetch_commits(ctx, pk, 0, NW, out->split_quot_poly_comms, out->split_inf));
             for (int i = 0; i < NW; i++) tr_g1(tr, "quot_poly_comms", out->split_quot_poly_comms + 2 * L * i, out->split_inf[i]);
         }
@@ -1006,11 +1033,16 @@ template <class C> struct Plonk {
             la.out = (E *)pk->d_bp;
             la.out_len = (uint32_t)(n + 3);
             JF_LAUNCH(ctx, "lincomb", lincomb_kernel<Fr><<<(unsigned)((n + 3 + 127) / 128), 128, 0, st>>>(la));
+            // the shifted opening z / (X - zeta w) is independent of the batch polynomial: side stream, own scratch
+            E *side_buf = (E *)pk->d_side;  // t, s, quotient (np each), scan temporaries
+            JF_TRY(on_side(ctx, pk, [&]() -> int {
+                JF_TRY(div_linear_dev(ctx, side_buf, side_buf + np, side_buf + 3 * np, Z, n + 3, zeta_w, side_buf + 2 * np));
+                return commit_dev(ctx, pk, side_buf + 2 * np, n + 2, 1);
+            }));
             E *WZ = (E *)pk->d_wz;
             JF_TRY(div_linear_dev(ctx, pk, (const E *)pk->d_bp, n + 3, zeta, WZ));
             JF_TRY(commit_dev(ctx, pk, WZ, n + 2, 0));
-            JF_TRY(div_linear_dev(ctx, pk, Z, n + 3, zeta_w, WZ));
-            JF_TRY(commit_dev(ctx, pk, WZ, n + 2, 1));
+            JF_TRY(join_side(ctx, pk));
             uint64_t xy[2 * 2 * 6];
             int inf[2];
             JF_TRY(fetch_commits(ctx, pk, 0, 2, xy, inf));
