@@ -219,7 +219,7 @@ def ntt_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream):
         "passes_per_transform": passes, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "ntt_pass", "achieved": 64.0 * elems / (pass_ms * 1e-3) / 1e9,
                      "peak": peaks[0], "unit": "GB/s", "frac": 64.0 * elems / (pass_ms * 1e-3) / 1e9 / peaks[0],
-                     "traffic": _traffic("ntt_pass"), "peak_source": peaks[1],
+                     "traffic": (_traffic("ntt_pass_bytes_per_element") or 0) * elems or None, "peak_source": peaks[1],
                      "note": "per launch = one Stockham pass over the batch (read 32 B + write 32 B per element); a "
                              "transform is %d passes, so the whole-transform figure is 1/%d of this" % (passes, max(passes, 1))},
         "roofline_int": {"bound": "imad", "achieved": muls / (ms * 1e-3), "peak": mul_rate, "unit": "Montgomery mul/s",
