@@ -1,0 +1,97 @@
+//! Raw bindings of `include/jf_b200.h`.  One declaration per exported symbol; see the header for the
+//! contract of each call and the reference call site it replaces.
+#![allow(non_camel_case_types)]
+use core::ffi::{c_char, c_int, c_long, c_uint, c_void};
+
+#[repr(C)] pub struct jf_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct jf_srs { _p: [u8; 0] }
+#[repr(C)] pub struct jf_plonk_pk { _p: [u8; 0] }
+
+pub const JF_OK: c_int = 0;
+pub const JF_ERR_INVALID_ARG: c_int = -1;
+pub const JF_ERR_CUDA: c_int = -2;
+pub const JF_ERR_DOMAIN_TOO_LARGE: c_int = -3;
+pub const JF_ERR_SCALAR_RANGE: c_int = -4;
+pub const JF_ERR_NOMEM: c_int = -5;
+pub const JF_ERR_QUOTIENT_DEGREE: c_int = -6;
+pub const JF_BN254: c_int = 0;
+pub const JF_BLS12_381: c_int = 1;
+pub const JF_BN254_FR: c_int = 0;
+pub const JF_BLS12_381_FR: c_int = 2;
+
+/// `jf_plonk_proof`: points are x || y with 2 L limbs each, packed (L = 4 BN254, 6 BLS12-381).
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct jf_plonk_proof {
+    pub curve: c_int,
+    pub wires_poly_comms: [u64; 60], pub wires_inf: [c_int; 5],
+    pub prod_perm_poly_comm: [u64; 12], pub prod_perm_inf: c_int,
+    pub split_quot_poly_comms: [u64; 60], pub split_inf: [c_int; 5],
+    pub opening_proof: [u64; 12], pub opening_inf: c_int,
+    pub shifted_opening_proof: [u64; 12], pub shifted_opening_inf: c_int,
+    pub wires_evals: [u64; 20], pub wire_sigma_evals: [u64; 16], pub perm_next_eval: [u64; 4],
+    pub challenges: [u64; 20],
+}
+
+extern "C" {
+    pub fn jf_ctx_create(device: c_int, out: *mut *mut jf_ctx) -> c_int;
+    pub fn jf_ctx_destroy(ctx: *mut jf_ctx);
+    pub fn jf_ctx_set_stream(ctx: *mut jf_ctx, cuda_stream: *mut c_void) -> c_int;
+    pub fn jf_ctx_sync(ctx: *mut jf_ctx) -> c_int;
+    pub fn jf_last_error(ctx: *const jf_ctx) -> *const c_char;
+    pub fn jf_ctx_launch_count(ctx: *const jf_ctx) -> u64;
+
+    pub fn jf_srs_load(ctx: *mut jf_ctx, curve: c_int, affine_pts: *const c_void, n: usize, stride_bytes: usize,
+                       inf_flag_offset: c_long, window_bits: c_int, precompute: c_int, out: *mut *mut jf_srs) -> c_int;
+    pub fn jf_srs_generate_for_testing(ctx: *mut jf_ctx, curve: c_int, beta: *const u64, first_power: usize, n: usize,
+                                       window_bits: c_int, precompute: c_int, out: *mut *mut jf_srs) -> c_int;
+    pub fn jf_srs_read(ctx: *mut jf_ctx, srs: *const jf_srs, first: usize, count: usize, out_xy: *mut u64) -> c_int;
+    pub fn jf_srs_len(srs: *const jf_srs) -> usize;
+    pub fn jf_srs_window_bits(srs: *const jf_srs) -> c_int;
+    pub fn jf_srs_free(ctx: *mut jf_ctx, srs: *mut jf_srs);
+
+    pub fn jf_msm(ctx: *mut jf_ctx, srs: *const jf_srs, base_offset: usize, scalars: *const u64, n: usize,
+                  scalars_in_montgomery: c_int, out_xy: *mut u64, out_infinity: *mut c_int) -> c_int;
+    pub fn jf_msm_batch(ctx: *mut jf_ctx, srs: *const jf_srs, scalars: *const *const u64, lens: *const usize,
+                        base_offsets: *const usize, batch: usize, scalars_in_montgomery: c_int, out_xy: *mut u64,
+                        out_infinity: *mut c_int) -> c_int;
+    pub fn jf_kzg_open(ctx: *mut jf_ctx, srs: *const jf_srs, polys: *const *const u64, lens: *const usize, batch: usize,
+                       points: *const u64, out_proof_xy: *mut u64, out_infinity: *mut c_int, out_evals: *mut u64) -> c_int;
+    pub fn jf_msm_device(ctx: *mut jf_ctx, srs: *const jf_srs, base_offset: usize, d_scalars: *const c_void, n: usize,
+                         scalars_in_montgomery: c_int, d_out_xyzz: *mut c_void) -> c_int;
+    pub fn jf_msm_combine(ctx: *mut jf_ctx, curve: c_int, xyzz_parts: *const u64, parts: usize, out_xy: *mut u64,
+                          out_infinity: *mut c_int) -> c_int;
+
+    pub fn jf_ntt(ctx: *mut jf_ctx, field: c_int, data: *mut u64, in_len: usize, log_n: c_uint, inverse: c_int,
+                  coset_offset: *const u64, batch: usize, batch_stride: usize) -> c_int;
+    pub fn jf_ntt_device(ctx: *mut jf_ctx, field: c_int, d_data: *mut c_void, in_len: usize, log_n: c_uint, inverse: c_int,
+                         coset_offset: *const u64, batch: usize, batch_stride: usize) -> c_int;
+
+    pub fn jf_plonk_preprocess(ctx: *mut jf_ctx, srs: *const jf_srs, log_n: c_uint, selector_evals: *const u64,
+                               sigma_evals: *const u64, k: *const u64, wire_variables: *const u32, num_vars: usize,
+                               pub_input_gate_ids: *const u32, num_inputs: usize, flags: c_int,
+                               out: *mut *mut jf_plonk_pk) -> c_int;
+    pub fn jf_plonk_vk_commitments(ctx: *mut jf_ctx, pk: *const jf_plonk_pk, out_xy: *mut u64, out_inf: *mut c_int) -> c_int;
+    pub fn jf_plonk_pk_free(ctx: *mut jf_ctx, pk: *mut jf_plonk_pk);
+    pub fn jf_plonk_prove(ctx: *mut jf_ctx, pk: *mut jf_plonk_pk, witness: *const u64, blinders: *const u64,
+                          transcript_kind: c_int, extra_msg: *const u8, extra_len: usize, out: *mut jf_plonk_proof) -> c_int;
+    pub fn jf_plonk_proof_serialize(proof: *const jf_plonk_proof, out: *mut u8, cap: usize) -> c_long;
+
+    pub fn jf_keccak256(data: *const u8, len: usize, out: *mut u8);
+    pub fn jf_transcript_new(kind: c_int, label: *const c_char) -> *mut c_void;
+    pub fn jf_transcript_free(t: *mut c_void);
+    pub fn jf_transcript_append(t: *mut c_void, label: *const c_char, msg: *const u8, len: usize);
+    pub fn jf_transcript_challenge(t: *mut c_void, field: c_int, label: *const c_char, out_montgomery: *mut u64) -> c_int;
+
+    pub fn jf_dev_alloc(ctx: *mut jf_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn jf_dev_free(ctx: *mut jf_ctx, ptr: *mut c_void) -> c_int;
+    pub fn jf_dev_upload(ctx: *mut jf_ctx, dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
+    pub fn jf_dev_download(ctx: *mut jf_ctx, dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
+    pub fn jf_host_alloc(ctx: *mut jf_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn jf_host_free(ctx: *mut jf_ctx, ptr: *mut c_void) -> c_int;
+    pub fn jf_field_op(ctx: *mut jf_ctx, field: c_int, op: c_int, a: *const u64, b: *const u64, out: *mut u64, n: usize) -> c_int;
+    pub fn jf_fixed_base_mul(ctx: *mut jf_ctx, curve: c_int, scalars: *const u64, n: usize, out_xy: *mut u64) -> c_int;
+    pub fn jf_profile_enable(ctx: *mut jf_ctx, on: c_int) -> c_int;
+    pub fn jf_profile_collect(ctx: *mut jf_ctx, buf: *mut c_char, cap: usize) -> c_long;
+    pub fn jf_microbench(ctx: *mut jf_ctx, kind: c_int, out_rate: *mut f64) -> c_int;
+}

@@ -29,6 +29,13 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_ffi.SIGNATURES) == names, "ctypes table and header disagree"
 
 
+def test_rust_sys_crate_declares_every_symbol():
+    """rust/jf-b200-sys (source only: no Rust toolchain in this image) must bind exactly the header's symbols."""
+    src = open(os.path.join(ROOT, "rust", "jf-b200-sys", "src", "lib.rs")).read()
+    rust = sorted(set(re.findall(r"pub fn (jf_[a-z0-9_]+)\s*\(", src)))
+    assert rust == _declared()
+
+
 def test_library_contains_sm100a_code():
     so = os.path.join(PKG, "libjf_b200.so")
     out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
