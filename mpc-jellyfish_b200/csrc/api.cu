@@ -108,6 +108,9 @@ void jf_ctx_destroy(jf_ctx *ctx) {
         cudaEventDestroy(r.b);
     }
     for (auto &e : ctx->event_pool) cudaEventDestroy(e);
+    for (auto &e : ctx->sync_events) cudaEventDestroy(e);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaFree(ctx->d_err);
     cudaStreamDestroy(ctx->own_stream);
@@ -219,13 +222,36 @@ static int msm_batch_locked(jf_ctx *ctx, const jf_srs *srs, const uint64_t *cons
     JF_TRY(scratch(ctx, "msm_scalars1", 32 * (max_len ? max_len : 1), &d_sc[1]));
     JF_TRY(scratch(ctx, "msm_results", pt * batch, &d_res));
     JF_TRY(pinned(ctx, pt * batch, &h_res));
+    // uploads run on their own stream: the scalars of vector i+1 cross PCIe while vector i is being summed
+    const bool piped = batch > 1;
+    if (piped) {
+        if (!ctx->copy_in) {
+            JF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+            JF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        }
+        while (ctx->sync_events.size() < 5) {
+            cudaEvent_t e;
+            JF_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->sync_events.push_back(e);
+        }
+        JF_CUDA(ctx, cudaEventRecord(ctx->sync_events[4], ctx->stream));
+        JF_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->sync_events[4], 0));
+    }
     for (size_t i = 0; i < batch; i++) {
         const size_t off = base_offsets ? base_offsets[i] : 0;
         if (off > srs->n) return fail(ctx, JF_ERR_INVALID_ARG, "msm: base_offset beyond the commit key");
         size_t n = lens[i] < srs->n - off ? lens[i] : srs->n - off;
         void *d = d_sc[i & 1];
-        if (n) JF_CUDA(ctx, cudaMemcpyAsync(d, scalars[i], 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+        cudaEvent_t ev_up = piped ? ctx->sync_events[i & 1] : nullptr, ev_done = piped ? ctx->sync_events[2 + (i & 1)] : nullptr;
+        cudaStream_t up = piped ? ctx->copy_in : ctx->stream;
+        if (piped && i >= 2) JF_CUDA(ctx, cudaStreamWaitEvent(up, ev_done, 0));  // buffer i & 1 was read by MSM i - 2
+        if (n) JF_CUDA(ctx, cudaMemcpyAsync(d, scalars[i], 32 * n, cudaMemcpyHostToDevice, up));
+        if (piped) {
+            JF_CUDA(ctx, cudaEventRecord(ev_up, up));
+            JF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_up, 0));
+        }
         JF_TRY(msm_run(ctx, srs, off, d, n, mont, (char *)d_res + pt * i));
+        if (piped) JF_CUDA(ctx, cudaEventRecord(ev_done, ctx->stream));
     }
     JF_CUDA(ctx, cudaMemcpyAsync(h_res, d_res, pt * batch, cudaMemcpyDeviceToHost, ctx->stream));
     JF_TRY(check_dev_err(ctx));  // synchronises
@@ -285,12 +311,51 @@ int jf_ntt(jf_ctx *ctx, int field, uint64_t *data, size_t in_len, unsigned log_n
     void *d_in = nullptr, *d_out = nullptr;
     JF_TRY(scratch(ctx, "ntt_in", 32 * n * batch, &d_in));
     JF_TRY(scratch(ctx, "ntt_out", 32 * n * batch, &d_out));
-    // only the first in_len entries are read by the kernels: upload just those
-    if (in_len)
-        JF_CUDA(ctx, cudaMemcpy2DAsync(d_in, 32 * n, data, 32 * batch_stride, 32 * in_len, batch, cudaMemcpyHostToDevice,
-                                       ctx->stream));
-    JF_TRY(ntt_run(ctx, field, d_in, d_out, in_len, log_n, inverse, coset_offset, batch, n));
-    JF_CUDA(ctx, cudaMemcpy2DAsync(data, 32 * batch_stride, d_out, 32 * n, 32 * n, batch, cudaMemcpyDeviceToHost, ctx->stream));
+    // Large batches are pipelined: the upload of group g+1 and the download of group g-1 run on their own
+    // streams beside the kernels of group g (PCIe is full duplex), so the call costs about one direction
+    // of the transfer instead of both plus the transform.
+    size_t groups = 1;
+    if (batch > 1 && 32 * n * batch >= ((size_t)64 << 20)) {
+        groups = batch < 16 ? batch : 16;
+        while (batch % groups) groups--;
+    }
+    if (groups == 1) {
+        // only the first in_len entries are read by the kernels: upload just those
+        if (in_len)
+            JF_CUDA(ctx, cudaMemcpy2DAsync(d_in, 32 * n, data, 32 * batch_stride, 32 * in_len, batch, cudaMemcpyHostToDevice,
+                                           ctx->stream));
+        JF_TRY(ntt_run(ctx, field, d_in, d_out, in_len, log_n, inverse, coset_offset, batch, n));
+        JF_CUDA(ctx, cudaMemcpy2DAsync(data, 32 * batch_stride, d_out, 32 * n, 32 * n, batch, cudaMemcpyDeviceToHost, ctx->stream));
+        JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return JF_OK;
+    }
+    if (!ctx->copy_in) {
+        JF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        JF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    }
+    while (ctx->sync_events.size() < 2 * groups + 1) {
+        cudaEvent_t e;
+        JF_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->sync_events.push_back(e);
+    }
+    const size_t per = batch / groups;
+    // the copy streams start after whatever is already queued on the compute stream
+    JF_CUDA(ctx, cudaEventRecord(ctx->sync_events[2 * groups], ctx->stream));
+    JF_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->sync_events[2 * groups], 0));
+    JF_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->sync_events[2 * groups], 0));
+    for (size_t g = 0; g < groups; g++) {
+        char *di = (char *)d_in + 32 * n * per * g, *d_o = (char *)d_out + 32 * n * per * g;
+        uint64_t *h = data + 4 * batch_stride * per * g;
+        if (in_len)
+            JF_CUDA(ctx, cudaMemcpy2DAsync(di, 32 * n, h, 32 * batch_stride, 32 * in_len, per, cudaMemcpyHostToDevice, ctx->copy_in));
+        JF_CUDA(ctx, cudaEventRecord(ctx->sync_events[2 * g], ctx->copy_in));
+        JF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->sync_events[2 * g], 0));
+        JF_TRY(ntt_run(ctx, field, di, d_o, in_len, log_n, inverse, coset_offset, per, n));
+        JF_CUDA(ctx, cudaEventRecord(ctx->sync_events[2 * g + 1], ctx->stream));
+        JF_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->sync_events[2 * g + 1], 0));
+        JF_CUDA(ctx, cudaMemcpy2DAsync(h, 32 * batch_stride, d_o, 32 * n, 32 * n, per, cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    JF_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
     JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return JF_OK;
 }

@@ -27,6 +27,8 @@ struct jf_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // lazily created: host<->device copies beside the kernels
+    std::vector<cudaEvent_t> sync_events;                // event pool for the copy pipeline
     int lane = 0;  // 1 while work is being issued on a secondary stream: scratch buffers are kept apart per lane
     std::mutex mu;
     std::string err;
