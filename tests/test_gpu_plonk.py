@@ -159,7 +159,7 @@ def test_numpy_circuit_builder_matches_the_restated_circuit(ctx, co, py, P):
     assert np.array_equal(got["wire_vars"], want["wire_vars"]) and got["num_vars"] == want["num_vars"]
 
 
-@pytest.mark.parametrize("log_n,kind", [(14, "solidity"), (16, "standard"), (18, "solidity")])
+@pytest.mark.parametrize("log_n,kind", [(14, "solidity"), (16, "standard"), (18, "solidity"), (20, "standard")])
 def test_large_proofs_are_accepted_by_the_restated_verifier(ctx, co, py, P, log_n, kind):
     """BASELINE config 4 shape (the bench circuit); the verifier check is size independent."""
     import mpc_jellyfish_b200 as jf
