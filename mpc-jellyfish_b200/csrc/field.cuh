@@ -41,6 +41,7 @@ namespace jf {
      F::pfx##8, F::pfx##9, F::pfx##10, F::pfx##11}
 
 struct Bn254Fr {
+    static constexpr bool P_OPAQUE = false;
     static constexpr int N = 8;
     static constexpr int BITS = 254;
     static constexpr int TWO_ADICITY = 28;
@@ -52,6 +53,7 @@ struct Bn254Fr {
 };
 
 struct Bn254Fq {
+    static constexpr bool P_OPAQUE = false;
     static constexpr int N = 8;
     static constexpr int BITS = 254;
     static constexpr uint32_t INV = 0xe4866389u;
@@ -61,6 +63,7 @@ struct Bn254Fq {
 };
 
 struct Bls12381Fr {
+    static constexpr bool P_OPAQUE = true;  // INV = 0xffffffff must stay opaque to ptxas: see mont_inv()
     static constexpr int N = 8;
     static constexpr int BITS = 255;
     static constexpr int TWO_ADICITY = 32;
@@ -72,6 +75,7 @@ struct Bls12381Fr {
 };
 
 struct Bls12381Fq {
+    static constexpr bool P_OPAQUE = false;
     static constexpr int N = 12;
     static constexpr int BITS = 381;
     static constexpr uint32_t INV = 0xfffcfffdu;
@@ -96,6 +100,23 @@ template <class F> struct Limbs<F, 12> {
     static JF_HD void r(uint32_t (&o)[12]) { const uint32_t t[12] = JF_ARR12(F, R); for (int i = 0; i < 12; i++) o[i] = t[i]; }
     static JF_HD void rr(uint32_t (&o)[12]) { const uint32_t t[12] = JF_ARR12(F, RR); for (int i = 0; i < 12; i++) o[i] = t[i]; }
 };
+
+#ifdef __CUDACC__
+static __constant__ uint32_t jf_c_bls12381_fr_inv = Bls12381Fr::INV;
+#endif
+// -p^-1 mod 2^32.  For Bls12381Fr it is 0xffffffff: as an immediate ptxas rewrites m = x * INV into a
+// negation, pushes the sign through the m * p products and no longer fuses their (lo, hi) pairs into
+// IMAD.WIDE.  Reading the constant from constant memory keeps m an ordinary product.
+template <class F> JF_HD uint32_t mont_inv() {
+#ifdef __CUDA_ARCH__
+    if constexpr (F::P_OPAQUE) return jf_c_bls12381_fr_inv;
+#endif
+    return F::INV;
+}
+template <class F> JF_HD void mad_p_pair(uint32_t (&odd_acc)[F::N], uint32_t (&even_acc)[F::N], uint32_t m) {
+    chain_mad_odd_p<F>(odd_acc, m);
+    chain_mad_even_p<F>(even_acc, m, odd_acc[F::N - 1]);
+}
 
 // ---- the field element -------------------------------------------------------------------
 template <class F> struct Fp {
@@ -187,9 +208,8 @@ template <class F> struct Fp {
             y[j + 1] = (uint32_t)(o >> 32);
         }
         {
-            uint32_t m = x[0] * F::INV;
-            chain_mad_odd_p<F>(y, m);
-            chain_mad_even_p<F>(x, m, y[N - 1]);
+            uint32_t m = x[0] * mont_inv<F>();
+            mad_p_pair<F>(y, x, m);
         }
 #pragma unroll
         for (int i = 1; i < N; i += 2) {
@@ -210,9 +230,8 @@ template <class F> struct Fp {
     static JF_HD void row(uint32_t (&prev_e)[N], uint32_t (&prev_o)[N], const uint32_t (&a)[N], uint32_t bi) {
         chain_shift_mad_odd(prev_e, prev_o[0], a, bi);
         chain_mad_even(prev_o, a, bi, prev_e[N - 1]);
-        uint32_t m = prev_o[0] * F::INV;
-        chain_mad_odd_p<F>(prev_e, m);
-        chain_mad_even_p<F>(prev_o, m, prev_e[N - 1]);
+        uint32_t m = prev_o[0] * mont_inv<F>();
+        mad_p_pair<F>(prev_e, prev_o, m);
     }
 
     static JF_HD Fp to_mont(const Fp &a) { return mul(a, r_squared()); }
