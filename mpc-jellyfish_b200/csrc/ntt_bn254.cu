@@ -1,0 +1,11 @@
+// ntt_bn254.cu -- the NTT kernels of ntt_impl.cuh instantiated for Bn254Fr.
+#include "ntt_impl.cuh"
+
+namespace jf {
+
+int ntt_run_bn254(jf_ctx *ctx, int field, void *d_data, void *d_out, size_t in_len, unsigned log_n, int inverse,
+               const uint64_t *coset_offset, size_t batch, size_t batch_stride) {
+    return ntt_run_t<Bn254Fr>(ctx, field, d_data, d_out, in_len, log_n, inverse, coset_offset, batch, batch_stride);
+}
+
+}  // namespace jf
