@@ -377,6 +377,9 @@ reduce_level_kernel(const XYZZ<Fq> *X, XYZZ<Fq> *Xo, const XYZZ<Fq> *Pin, XYZZ<F
                     uint32_t cap_x, uint32_t cap_p) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const size_t set = blockIdx.y;
+    // launched with programmatic stream serialisation: this level's launch overlaps the previous level's
+    // tail; wait here until the previous level's results are visible
+    cudaGridDependencySynchronize();
     X += set * cap_x;
     Xo += set * cap_x;
     Pin += set * cap_p;
@@ -506,7 +509,19 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
             const uint32_t threads = xs + mh;
             const int bs = threads > 32u * 1024u ? 128 : 32;
             dim3 grid((threads + bs - 1) / bs, g.S);
-            JF_LAUNCH(ctx, "reduce_level", reduce_level_kernel<Fq><<<grid, bs, 0, st>>>(x, xo, pin, pout, nlev, m, g.NB, cap_p));
+            {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = grid;
+                cfg.blockDim = dim3(bs);
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                const XYZZ<Fq> *cx = x, *cpin = pin;
+                JF_LAUNCH(ctx, "reduce_level", cudaLaunchKernelEx(&cfg, reduce_level_kernel<Fq>, cx, xo, cpin, pout, nlev, m, g.NB, cap_p));
+            }
             m = mh + (nlev >= 2 ? nlev : nlev);  // pairs push 2 entries each (= nlev), a lone bucket pushes 1
             nlev = nlev >= 2 ? nlev / 2 : 0;
             std::swap(x, xo);
