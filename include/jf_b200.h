@@ -139,7 +139,8 @@ int jf_ntt_device(jf_ctx *ctx, int field, void *d_data, size_t in_len, unsigned 
  * keep their 8n coset evaluations resident (18 of the 25 coset NTTs of round 3 then happen once per
  * key instead of once per proof; +4.5 GiB at n = 2^20).  flags & 2: selector columns that are identically
  * zero (e.g. q_hash / q_ecc in circuits without Rescue or ECC gates) are recognised once and their coset NTTs and
- * quotient terms are skipped; the proof is unchanged.  `srs` must outlive the key and hold >= n + 3 points. */
+ * quotient terms are skipped; the proof is unchanged.  `srs` must outlive the key and hold >= n + 3 points.  2 <= log_n and
+ * log_n + 3 <= two-adicity (JF_ERR_DOMAIN_TOO_LARGE otherwise: `Prover::new`, prover.rs:54-62). */
 int jf_plonk_preprocess(jf_ctx *ctx, const jf_srs *srs, unsigned log_n, const uint64_t *selector_evals,
                         const uint64_t *sigma_evals, const uint64_t *k, const uint32_t *wire_variables, size_t num_vars,
                         const uint32_t *pub_input_gate_ids, size_t num_inputs, int flags, jf_plonk_pk **out);

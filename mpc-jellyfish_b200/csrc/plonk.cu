@@ -634,7 +634,7 @@ template <class C> struct Plonk {
     static int preprocess(jf_ctx *ctx, const jf_srs *srs, unsigned log_n, const uint64_t *selector_evals,
                           const uint64_t *sigma_evals, const uint64_t *k, const uint32_t *wire_variables, size_t num_vars,
                           const uint32_t *pub_gate_ids, size_t num_inputs, int flags, jf_plonk_pk **out) {
-        if (log_n < 3 || log_n + 3 > (unsigned)Fr::TWO_ADICITY || log_n > 26)
+        if (log_n < 2 || log_n + 3 > (unsigned)Fr::TWO_ADICITY || log_n > 26)  // n = 2: the quotient (degree 17) does not fit 8n
             return fail(ctx, JF_ERR_DOMAIN_TOO_LARGE, "preprocess: unsupported domain size");
         const size_t n = (size_t)1 << log_n, m = n * 8, np = n + PAD;
         if (srs->n < n + 3) return fail(ctx, JF_ERR_INVALID_ARG, "preprocess: the commit key needs n + 3 points (srs_size = n + 2)");

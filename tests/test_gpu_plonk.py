@@ -30,7 +30,18 @@ def _blinders(co, fr, seed):
     return ints, co.ints_to_limbs([fr.to_mont(v) for v in ints], 4)
 
 
+def _tiny(P, adds):
+    cs = P.PlonkCircuit()
+    a = cs.create_public_variable(5) if adds == 1 else cs.create_variable(5)
+    for _ in range(adds):
+        a = cs.add(a, cs.one())
+    cs.finalize_for_arithmetization()
+    return cs
+
+
 CIRCUITS = {
+    "tiny_n4": lambda P: _tiny(P, 1),      # 2 constant gates + io gate + 1 addition -> n = 4, quotient domain 32
+    "tiny_n8": lambda P: _tiny(P, 4),
     "test_m2": lambda P: P.gen_circuit_for_test(2, 3),
     "bench_64": lambda P: P.gen_circuit_for_bench(64),
     "test_m20": lambda P: P.gen_circuit_for_test(20, 1),
