@@ -341,6 +341,58 @@ def jf_mod():
     return jf
 
 
+# ------------------------------------------------------------------------------------------------
+def mpc_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream):
+    """BASELINE config 5 shape: one party's local share-wise work in the collaborative prover at n = 2^18
+    (plonk/src/multiprover/primitives/multiprover_kzg.rs:128-143, multiprover/proof_system/prover.rs:373-388):
+    `MultiproverKZG::batch_commit` of the 5 authenticated wire polynomials (share + MAC vectors = 10 MSMs of
+    n + 2 scalars through jf_msm_batch, host buffers) and the share-wise coset NTT of the same 5 polynomials to
+    the 8n domain (10 vectors, device resident).  N > 1: one party per GPU (no collective on this path)."""
+    n = 1 << 18
+    rng = np.random.default_rng(7 + rank)
+    key = ctx.generate_srs_for_testing("bn254", BETA % co_modulus(), n + 3)
+    pp = jf_mod().UnivariateProverParam(key)
+    polys = [jf_mod().AuthenticatedDensePoly(rng.integers(0, 1 << 60, size=(n + 2, 4), dtype=np.uint64),
+                                             rng.integers(0, 1 << 60, size=(n + 2, 4), dtype=np.uint64)) for _ in range(5)]
+    steps = max(1, min(args.steps, 5))
+    for _ in range(2):
+        jf_mod().MultiproverKZG.batch_commit(pp, polys)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        jf_mod().MultiproverKZG.batch_commit(pp, polys)
+    commit_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+    m = 8 * n
+    d = torch.zeros((10, m, 4), dtype=torch.int64, device="cuda")
+    for i, pl in enumerate(polys):
+        d[2 * i, : n + 2].copy_(torch.from_numpy(pl.share.view(np.int64)))
+        d[2 * i + 1, : n + 2].copy_(torch.from_numpy(pl.mac.view(np.int64)))
+    base = d.clone()
+    off = np.array([0x1b0d0ef99fffffe6, 0xeaba68a3a32a913f, 0x47d8eb76d8dd0689, 0x15d0085520f5bbc3], dtype=np.uint64)  # 5 R mod r
+    for _ in range(2):
+        d.copy_(base)
+        ctx.ntt_device("bn254_fr", d.data_ptr(), 21, False, off, in_len=n + 2, batch=10)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot = 0.0
+    for _ in range(steps):
+        d.copy_(base)
+        e0.record(stream)
+        ctx.ntt_device("bn254_fr", d.data_ptr(), 21, False, off, in_len=n + 2, batch=10)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    ntt_ms = max_over_ranks(tot / steps)
+    key.free()
+    if rank != 0:
+        return None
+    return {"workload": "one party, n = 2^18: batch_commit of 5 authenticated wire polynomials (10 MSMs, host scalars) and "
+                        "their share-wise coset NTT to 8n (10 vectors, device resident)",
+            "batch_commit_ms": commit_ms, "msm_per_s": 10 * world / (commit_ms * 1e-3),
+            "sharewise_coset_ntt_ms": ntt_ms, "ntt_melem_per_s": 10 * m * world / (ntt_ms * 1e-3) / 1e6,
+            "parties": world}
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -481,6 +533,7 @@ def run_cuda(args):
             cpu_msm_ms = (time.perf_counter() - t0) * 1e3 * (n / ns)
             cpu_ntt = ntt["cpu_baseline"]["value"] if ntt and ntt.get("cpu_baseline") else None
         prove = prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream, cpu_msm_ms, cpu_ntt)
+    mpc = None if args.no_mpc else mpc_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream)
     stop.set()
     sampler.join(timeout=2)
     clocks = _clock_summary(rows)
@@ -550,6 +603,7 @@ def run_cuda(args):
         "clocks": clocks,
         "ntt": ntt,
         "prove": prove,
+        "mpc": mpc,
     }
     _emit(line)
     if world > 1:
@@ -582,6 +636,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-ntt", action="store_true", help="skip the NTT 2^22 leg (second metric)")
+    ap.add_argument("--no-mpc", action="store_true", help="skip the collaborative-prover share-wise leg (config 5 shape)")
     ap.add_argument("--no-prove", action="store_true", help="skip the 2^20-gate prove leg (first metric)")
     args = ap.parse_args()
     if args.warmup < 3:
