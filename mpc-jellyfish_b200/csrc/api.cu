@@ -109,6 +109,7 @@ void jf_ctx_destroy(jf_ctx *ctx) {
     }
     for (auto &e : ctx->event_pool) cudaEventDestroy(e);
     for (auto &e : ctx->sync_events) cudaEventDestroy(e);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -222,37 +223,72 @@ static int msm_batch_locked(jf_ctx *ctx, const jf_srs *srs, const uint64_t *cons
     JF_TRY(scratch(ctx, "msm_scalars1", 32 * (max_len ? max_len : 1), &d_sc[1]));
     JF_TRY(scratch(ctx, "msm_results", pt * batch, &d_res));
     JF_TRY(pinned(ctx, pt * batch, &h_res));
-    // uploads run on their own stream: the scalars of vector i+1 cross PCIe while vector i is being summed
+    // A batch is pipelined over three streams: uploads on the copy stream (the scalars of vector i+1 cross PCIe
+    // while vector i is being summed), the bulk phases of every MSM (digits, sort, bucket accumulation) in order
+    // on the low-priority side stream, and the latency-bound bucket reductions on the caller's (high-priority)
+    // stream, where they overlap the bulk phases of the next MSM.  Workspaces alternate between two lanes.
     const bool piped = batch > 1;
+    cudaStream_t main_stream = ctx->stream;
+    enum { EV_UP = 0, EV_A = 2, EV_B = 4, EV_MID = 6, EV_START = 8, EV_COUNT = 9 };
     if (piped) {
         if (!ctx->copy_in) {
             JF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
             JF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
         }
-        while (ctx->sync_events.size() < 5) {
+        if (!ctx->side) {
+            int prio_least = 0, prio_greatest = 0;
+            cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+            JF_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_least));
+        }
+        while (ctx->sync_events.size() < EV_COUNT) {
             cudaEvent_t e;
             JF_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             ctx->sync_events.push_back(e);
         }
-        JF_CUDA(ctx, cudaEventRecord(ctx->sync_events[4], ctx->stream));
-        JF_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->sync_events[4], 0));
+        JF_CUDA(ctx, cudaEventRecord(ctx->sync_events[EV_START], main_stream));
+        JF_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->sync_events[EV_START], 0));
+        JF_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->sync_events[EV_START], 0));
     }
-    for (size_t i = 0; i < batch; i++) {
+    int rc = JF_OK;
+    for (size_t i = 0; i < batch && rc == JF_OK; i++) {
         const size_t off = base_offsets ? base_offsets[i] : 0;
-        if (off > srs->n) return fail(ctx, JF_ERR_INVALID_ARG, "msm: base_offset beyond the commit key");
-        size_t n = lens[i] < srs->n - off ? lens[i] : srs->n - off;
-        void *d = d_sc[i & 1];
-        cudaEvent_t ev_up = piped ? ctx->sync_events[i & 1] : nullptr, ev_done = piped ? ctx->sync_events[2 + (i & 1)] : nullptr;
-        cudaStream_t up = piped ? ctx->copy_in : ctx->stream;
-        if (piped && i >= 2) JF_CUDA(ctx, cudaStreamWaitEvent(up, ev_done, 0));  // buffer i & 1 was read by MSM i - 2
-        if (n) JF_CUDA(ctx, cudaMemcpyAsync(d, scalars[i], 32 * n, cudaMemcpyHostToDevice, up));
-        if (piped) {
-            JF_CUDA(ctx, cudaEventRecord(ev_up, up));
-            JF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_up, 0));
+        if (off > srs->n) {
+            rc = fail(ctx, JF_ERR_INVALID_ARG, "msm: base_offset beyond the commit key");
+            break;
         }
-        JF_TRY(msm_run(ctx, srs, off, d, n, mont, (char *)d_res + pt * i));
-        if (piped) JF_CUDA(ctx, cudaEventRecord(ev_done, ctx->stream));
+        size_t n = lens[i] < srs->n - off ? lens[i] : srs->n - off;
+        const int slot = (int)(i & 1);
+        void *d = d_sc[slot];
+        if (!piped) {
+            if (n) JF_CUDA(ctx, cudaMemcpyAsync(d, scalars[i], 32 * n, cudaMemcpyHostToDevice, main_stream));
+            rc = msm_run(ctx, srs, off, d, n, mont, (char *)d_res + pt * i);
+            break;
+        }
+        cudaEvent_t *ev = ctx->sync_events.data();
+        cudaError_t ce = cudaSuccess;
+        if (i >= 2) ce = cudaStreamWaitEvent(ctx->copy_in, ev[EV_A + slot], 0);  // MSM i-2 has read this scalar buffer
+        if (ce == cudaSuccess && n) ce = cudaMemcpyAsync(d, scalars[i], 32 * n, cudaMemcpyHostToDevice, ctx->copy_in);
+        if (ce == cudaSuccess) ce = cudaEventRecord(ev[EV_UP + slot], ctx->copy_in);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->side, ev[EV_UP + slot], 0);
+        if (ce == cudaSuccess && i >= 2) ce = cudaStreamWaitEvent(ctx->side, ev[EV_B + slot], 0);  // its reduction is done
+        if (ce != cudaSuccess) {
+            rc = fail(ctx, JF_ERR_CUDA, std::string("msm_batch: ") + cudaGetErrorString(ce));
+            break;
+        }
+        ctx->stream = ctx->side;
+        ctx->lane = slot;
+        rc = msm_run_split(ctx, srs, off, d, n, mont, (char *)d_res + pt * i, main_stream, ev[EV_MID + slot]);
+        ctx->stream = main_stream;
+        ctx->lane = 0;
+        if (rc == JF_OK && (cudaEventRecord(ev[EV_A + slot], ctx->side) != cudaSuccess ||
+                            cudaEventRecord(ev[EV_B + slot], main_stream) != cudaSuccess))
+            rc = fail(ctx, JF_ERR_CUDA, "msm_batch: event record");
     }
+    if (piped) {  // results are complete on the main stream once the side stream's last bulk phase has been joined
+        cudaEventRecord(ctx->sync_events[EV_START], ctx->side);
+        cudaStreamWaitEvent(main_stream, ctx->sync_events[EV_START], 0);
+    }
+    JF_TRY(rc);
     JF_CUDA(ctx, cudaMemcpyAsync(h_res, d_res, pt * batch, cudaMemcpyDeviceToHost, ctx->stream));
     JF_TRY(check_dev_err(ctx));  // synchronises
     for (size_t i = 0; i < batch; i++)

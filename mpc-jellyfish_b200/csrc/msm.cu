@@ -260,7 +260,9 @@ __device__ __forceinline__ uint32_t chunk_len(uint32_t entries, uint32_t nthread
 // t + bucket: slots are unique (consecutive threads touch non-decreasing buckets) and the
 // partials of one bucket are consecutive, so no task list or second scan is needed.
 template <class Fq>
-__global__ void __launch_bounds__(ACC_THREADS)
+// 112 registers: four CTAs per SM leave ~7 K registers free, so the one-warp kernels of another stream (bucket
+// reduction of the previous MSM of a batch) can run beside a resident accumulate wave
+__global__ void __maxnreg__(112)
 msm_accumulate_kernel(const Affine<Fq> *points, uint32_t srs_n, const uint32_t *sorted, const uint32_t *off,
                       uint32_t total_buckets, XYZZ<Fq> *partials) {
     const uint32_t nthreads = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -428,7 +430,7 @@ template <class Fq> __global__ void set_inf_kernel(XYZZ<Fq> *out) {
 // ---- driver ------------------------------------------------------------------------------
 template <class C>
 static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n_in, int mont,
-                     void *d_out) {
+                     void *d_out, cudaStream_t tail_stream, cudaEvent_t ev_mid) {
     using Fq = typename C::Fq;
     using Fr = typename C::Fr;
     using P = XYZZ<Fq>;
@@ -436,7 +438,7 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     if (base_offset > srs->n) return fail(ctx, JF_ERR_INVALID_ARG, "msm: base_offset beyond the commit key");
     size_t n = n_in < srs->n - base_offset ? n_in : srs->n - base_offset;  // arkworks: min(len(bases), len(scalars))
     if (n == 0) {
-        JF_LAUNCH(ctx, "set_inf", set_inf_kernel<Fq><<<1, 32, 0, st>>>((P *)d_out));
+        JF_LAUNCH(ctx, "set_inf", set_inf_kernel<Fq><<<1, 32, 0, tail_stream ? tail_stream : st>>>((P *)d_out));
         return JF_OK;
     }
     MsmGeom g;
@@ -502,6 +504,13 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     JF_CUDA(ctx, cudaMemsetAsync(heavy, 0, sizeof(uint32_t), st));
     JF_LAUNCH(ctx, "bucket_sum", bucket_sum_kernel<Fq><<<(total + 127) / 128, 128, 0, st>>>(partials, off, total, acc_threads, XA, heavy, heavy + 1));
     JF_LAUNCH(ctx, "bucket_sum_heavy", bucket_sum_heavy_kernel<Fq><<<(unsigned)ctx->sm_count * 4, HEAVY_THREADS, 0, st>>>(partials, off, total, acc_threads, XA, heavy, heavy + 1));
+    if (tail_stream) {
+        // split form: the bulk phases above ran on ctx->stream, the latency-bound bucket reduction continues on
+        // `tail_stream` (a higher-priority stream) so that it overlaps the bulk phases of the caller's next MSM
+        JF_CUDA(ctx, cudaEventRecord(ev_mid, st));
+        JF_CUDA(ctx, cudaStreamWaitEvent(tail_stream, ev_mid, 0));
+        st = tail_stream;
+    }
     {
         uint32_t nlev = g.NB, m = 0;
         P *x = XA, *xo = XB, *pin = PA, *pout = PB;
@@ -538,11 +547,17 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     return JF_OK;
 }
 
+int msm_run_split(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n, int mont,
+                  void *d_out_xyzz, cudaStream_t tail_stream, cudaEvent_t ev_mid) {
+    if (srs->curve == JF_BN254) return msm_run_t<Bn254G1>(ctx, srs, base_offset, d_scalars, n, mont, d_out_xyzz, tail_stream, ev_mid);
+    if (srs->curve == JF_BLS12_381)
+        return msm_run_t<Bls12381G1>(ctx, srs, base_offset, d_scalars, n, mont, d_out_xyzz, tail_stream, ev_mid);
+    return fail(ctx, JF_ERR_INVALID_ARG, "msm: unknown curve");
+}
+
 int msm_run(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n, int mont,
             void *d_out_xyzz) {
-    if (srs->curve == JF_BN254) return msm_run_t<Bn254G1>(ctx, srs, base_offset, d_scalars, n, mont, d_out_xyzz);
-    if (srs->curve == JF_BLS12_381) return msm_run_t<Bls12381G1>(ctx, srs, base_offset, d_scalars, n, mont, d_out_xyzz);
-    return fail(ctx, JF_ERR_INVALID_ARG, "msm: unknown curve");
+    return msm_run_split(ctx, srs, base_offset, d_scalars, n, mont, d_out_xyzz, nullptr, nullptr);
 }
 
 // ---- host tail: sum partial XYZZ points and normalise (`into_affine`) ---------------------

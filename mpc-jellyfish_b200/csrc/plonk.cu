@@ -436,7 +436,7 @@ struct jf_plonk_pk {
     std::vector<void *> allocs;
     // secondary stream: coset NTTs that do not depend on the next challenge run beside the commitments
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_mid[2] = {nullptr, nullptr}, ev_tail[2] = {nullptr, nullptr};
 };
 
 namespace jf {
@@ -540,9 +540,10 @@ template <class C> struct Plonk {
     static int commit_dev(jf_ctx *ctx, const jf_plonk_pk *pk, const void *d_poly, size_t len, int slot) {
         return msm_run(ctx, pk->srs, 0, d_poly, len, 1, (char *)pk->d_res + PT * slot);
     }
-    // `count` commitments, alternating between the main and the side stream: the latency-bound phases of one
-    // MSM (digit sort, bucket reduction) overlap the bucket accumulation of the next.  The side stream must
-    // be idle-able here (no queued NTT work the caller still waits for).
+    // `count` commitments as a pipeline: the bulk phases of every MSM (digits, sort, bucket accumulation) run in
+    // order on the low-priority side stream, the latency-bound bucket reductions on the main (high-priority)
+    // stream, where they overlap the bulk phases of the next MSM; workspaces alternate between two lanes.
+    // The side stream must be idle-able here (no queued NTT work the caller still waits for).
     struct CommitJob { const void *poly; size_t len; int slot; };
     static int commit_many(jf_ctx *ctx, jf_plonk_pk *pk, const CommitJob *jobs, int count) {
         cudaStream_t main_stream = ctx->stream;
@@ -550,13 +551,15 @@ template <class C> struct Plonk {
         JF_CUDA(ctx, cudaStreamWaitEvent(pk->side, pk->ev_main, 0));
         int rc = JF_OK;
         for (int i = 0; i < count && rc == JF_OK; i++) {
-            if (i & 1) {
-                ctx->stream = pk->side;
-                ctx->lane = 1;
-            }
-            rc = commit_dev(ctx, pk, jobs[i].poly, jobs[i].len, jobs[i].slot);
+            const int lane = i & 1;
+            if (i >= 2) JF_CUDA(ctx, cudaStreamWaitEvent(pk->side, pk->ev_tail[lane], 0));  // lane's last reduction is done
+            ctx->stream = pk->side;
+            ctx->lane = lane;
+            rc = msm_run_split(ctx, pk->srs, 0, jobs[i].poly, jobs[i].len, 1, (char *)pk->d_res + PT * jobs[i].slot, main_stream,
+                               pk->ev_mid[lane]);
             ctx->stream = main_stream;
             ctx->lane = 0;
+            if (rc == JF_OK) JF_CUDA(ctx, cudaEventRecord(pk->ev_tail[lane], main_stream));
         }
         JF_TRY(rc);
         return join_side(ctx, pk);
@@ -661,7 +664,11 @@ template <class C> struct Plonk {
         cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
         if (cudaStreamCreateWithPriority(&pk->side, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
             cudaEventCreateWithFlags(&pk->ev_main, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&pk->ev_side, cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&pk->ev_side, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&pk->ev_mid[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&pk->ev_mid[1], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&pk->ev_tail[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&pk->ev_tail[1], cudaEventDisableTiming) != cudaSuccess) {
             delete pk;
             return fail(ctx, JF_ERR_CUDA, "preprocess: cannot create the side stream");
         }
@@ -1185,6 +1192,10 @@ void jf_plonk_pk_free(jf_ctx *ctx, jf_plonk_pk *pk) {
     }
     if (pk->ev_main) cudaEventDestroy(pk->ev_main);
     if (pk->ev_side) cudaEventDestroy(pk->ev_side);
+    for (int i = 0; i < 2; i++) {
+        if (pk->ev_mid[i]) cudaEventDestroy(pk->ev_mid[i]);
+        if (pk->ev_tail[i]) cudaEventDestroy(pk->ev_tail[i]);
+    }
     if (pk->side) cudaStreamDestroy(pk->side);
     delete pk;
 }
