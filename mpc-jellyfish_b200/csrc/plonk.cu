@@ -280,7 +280,7 @@ template <class F> __global__ void __launch_bounds__(128) quotient_kernel(const 
     // circuit part (prover.rs:696-708); selector order q_lc 0-3, q_mul 4-5, q_hash 6-9, q_o 10, q_c 11, q_ecc 12
     auto on = [&](int s) { return !((q.zero_sel >> s) & 1u); };  // uniform across the grid
     E w01 = E::mul(w[0], w[1]), w23 = E::mul(w[2], w[3]);
-    E t = ldf(q.pi + i);
+    E t = q.pi ? ldf(q.pi + i) : E::zero();  // no public inputs: the PI polynomial is zero (flags & 2)
     if (on(11)) t = E::add(t, S(11));
     if (on(0)) t = E::add(t, E::mul(S(0), w[0]));
     if (on(1)) t = E::add(t, E::mul(S(1), w[1]));
@@ -414,6 +414,7 @@ struct jf_plonk_pk {
     uint32_t num_inputs = 0;
     int cache_coset = 0;
     uint32_t zero_sel = 0;  // selectors that are identically zero (flags & 2)
+    int skip_zero = 0;      // flags & 2: zero polynomials (such selectors; PI without public inputs) are not transformed
     std::vector<uint32_t> pub_vars;  // variable index of every public input, in io-gate order
     // device, persistent
     void *d_sel = nullptr, *d_sig = nullptr, *d_sig_evals = nullptr;  // NSEL x n, NW x n coefficients; NW x n values
@@ -652,6 +653,7 @@ template <class C> struct Plonk {
         pk->num_vars = num_vars;
         pk->num_inputs = (uint32_t)num_inputs;
         pk->cache_coset = flags & 1;
+        pk->skip_zero = (flags & 2) ? 1 : 0;
         if (flags & 2) {
             for (int sel = 0; sel < NSEL; sel++) {
                 const uint64_t *col = selector_evals + (size_t)sel * 4 * n;
@@ -897,6 +899,7 @@ template <class C> struct Plonk {
         // the wire / PI polynomials are final: their coset NTTs run beside the commitments
         JF_TRY(on_side(ctx, pk, [&]() -> int {
             JF_TRY(coset_fft_rows(ctx, pk, W, np, n + 2, NW, w_c));
+            if (pk->num_inputs == 0 && pk->skip_zero) return JF_OK;  // PI(X) = 0: nothing to transform
             return coset_fft_rows(ctx, pk, PI, np, n, 1, pi_c);
         }));
         for (int j = 0; j < NW; j++) JF_TRY(commit_dev(ctx, pk, W + (size_t)j * np, n + 2, j));
@@ -940,7 +943,7 @@ template <class C> struct Plonk {
             q.sig = sig_c;
             q.w = w_c;
             q.z = z_c;
-            q.pi = pi_c;
+            q.pi = (pk->num_inputs == 0 && pk->skip_zero) ? nullptr : pi_c;
             q.inv_nx1 = (const E *)pk->d_inv_nx1;
             q.x_lo = (const E *)pk->d_xlo;
             q.x_hi = (const E *)pk->d_xhi;
