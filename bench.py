@@ -307,6 +307,20 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
                       "kernels_ms": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}}
         pk.free()
     key.free()
+    # BASELINE configs[0] shape (2^16 gates, the size the reference's own bench can run): one data point
+    arr16 = B.bench_circuit_arrays(ctx, 16)
+    key16 = ctx.generate_srs_for_testing("bn254", BETA % co_modulus(), (1 << 16) + 3)
+    pk16 = jf_mod().PlonkKzgSnark.preprocess(ctx, key16, arr16["selectors"], arr16["sigmas"], arr16["k"], arr16["wire_vars"],
+                                             arr16["num_vars"], [])
+    for _ in range(2):
+        jf_mod().PlonkKzgSnark.prove(pk16, arr16["witness"], bl, "solidity")
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        jf_mod().PlonkKzgSnark.prove(pk16, arr16["witness"], bl, "solidity")
+    prove16_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+    pk16.free()
+    key16.free()
     if rank != 0:
         return None
     cpu = None
@@ -329,6 +343,7 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
                                        "quotient terms are skipped; same proof bytes (tests/test_gpu_plonk.py)"),
         "with_cached_selector_sigma_coset_evals": alt((True, True), "additionally the selector / sigma coset evaluations stay "
                                                       "resident (+4.5 GiB): only 7 coset NTTs per proof; same proof bytes"),
+        "prove_2^16_gates_ms": prove16_ms,
         "cpu_baseline": cpu,
         "e2e": {"value": base["wall_ms"], "unit": "ms", "h2d_bytes_per_step": int(arr["witness"].nbytes + 17 * 32),
                 "d2h_bytes_per_step": 13 * 128 + 10 * 32},
