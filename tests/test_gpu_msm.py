@@ -185,3 +185,17 @@ def test_msm_large_known_beta_identity(ctx, co, py, log_n):
     S = cv.add(P1, P2)
     assert S == tuple(fq.from_mont(v) for v in co.limbs_to_ints(xy.reshape(2, 4)))
     key.free()
+
+
+def test_msm_2_20_random_points_vs_oracle_pippenger(ctx, co):
+    """BASELINE config-2 size with random (non-KZG) points: the GPU result against the C restatement of
+    ark-ec's Pippenger on all 2^20 + 3 pairs (the known-beta identity above only covers KZG-shaped keys)."""
+    n = (1 << 20) + 3
+    ks = co.random_field_elems("bn254_fr", n, 777, False)
+    pts = ctx.fixed_base_mul("bn254", ks)
+    s = co.random_field_elems("bn254_fr", n, 778, False)
+    key = ctx.load_srs("bn254", pts)
+    xy, inf = ctx.msm(key, s)
+    key.free()
+    wxy, winf = co.msm("bn254", pts, s)
+    assert inf == winf and np.array_equal(xy, wxy)

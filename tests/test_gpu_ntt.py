@@ -113,3 +113,14 @@ def test_domain_mirror(ctx, co, py, fname):
     assert [f.from_mont(v) for v in co.limbs_to_ints(ev)] == ref.fft(vals)
     back = coset.ifft(ev)
     assert np.array_equal(back[:700], c) and not back[700:].any()
+
+
+@pytest.mark.parametrize("fname,log_n,inverse", [("bn254_fr", 22, False), ("bls12_381_fr", 22, True), ("bn254_fr", 21, True)])
+def test_full_size_output_equals_the_oracle(ctx, co, py, fname, log_n, inverse):
+    """BASELINE config-3 sizes: every one of the 2^22 outputs against the C restatement (coset domain)."""
+    f = py.FIELDS[fname]
+    n = 1 << log_n
+    x = co.random_field_elems(fname, n, 4242 + log_n, True)
+    off = co.ints_to_limbs([f.to_mont(f.generator)], 4)[0]
+    got = ctx.ntt(fname, x.copy(), log_n, inverse, off)
+    assert np.array_equal(got, co.ntt(fname, x, log_n, inverse, off))
