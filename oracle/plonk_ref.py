@@ -469,6 +469,38 @@ class PlonkCircuit:
         return True
 
 
+def gen_circuit_all_selectors(m: int, field: Field = pyref.BN254_FR) -> PlonkCircuit:
+    """A satisfiable circuit that drives every one of the 13 selector columns (q_lc0-3, q_mul0-1, q_hash0-3,
+    q_o, q_c, q_ecc) with non-trivial values, so that every term of the quotient / linearisation formulas
+    (prover.rs:696-708, 963-1003) is exercised.  Gates are generic `insert_gate` calls with the selector
+    values of the reference's gate types (relation/src/gates/arithmetic.rs: LinCombGate, MulAddGate,
+    FifthRootGate, and an ecc-style degree-5 product gate)."""
+    p = field.p
+    cs = PlonkCircuit(field)
+    pub = cs.create_public_variable(11)
+    v = [cs.create_variable(3 + 2 * i) for i in range(4 * m)]
+    for i in range(m):
+        a, b, c, d = v[4 * i:4 * i + 4]
+        wa, wb, wc, wd = (cs.witness[x] for x in (a, b, c, d))
+        # LinCombGate: q_lc = (2, 3, 5, 7), q_o = 1
+        e = cs.create_variable(2 * wa + 3 * wb + 5 * wc + 7 * wd)
+        cs.insert_gate([a, b, c, d, e], Gate("lincomb", q_lc=(2, 3, 5, 7), q_o=1))
+        # MulAddGate: q_mul = (4, 9), q_o = 1
+        f = cs.create_variable(4 * wa * wb + 9 * wc * wd)
+        cs.insert_gate([a, b, c, d, f], Gate("muladd", q_mul=(4, 9), q_o=1))
+        # hash-style gate: q_hash = (1, 2, 3, 4), q_c = 6, q_o = 1
+        h = cs.create_variable(pow(wa, 5, p) + 2 * pow(wb, 5, p) + 3 * pow(wc, 5, p) + 4 * pow(wd, 5, p) + 6)
+        cs.insert_gate([a, b, c, d, h], Gate("hash", q_hash=(1, 2, 3, 4), q_c=6, q_o=1))
+        # ecc-style gate: q_ecc * w0 w1 w2 w3 w4 + q_lc0 w0 + q_c = q_o w4 with q_o = 0:  the product is pinned
+        # by the constant: choose w4 = e, q_ecc = 5, q_c = -(5 a b c d e + 8 a)
+        we = cs.witness[e]
+        cs.insert_gate([a, b, c, d, e], Gate("ecc", q_lc=(8, 0, 0, 0), q_ecc=5, q_c=(-(5 * wa * wb * wc * wd * we + 8 * wa)) % p))
+    s2 = cs.add(pub, v[0])
+    cs.mul_gate(s2, v[1], cs.create_variable(cs.witness[s2] * cs.witness[v[1]]))
+    cs.finalize_for_arithmetization()
+    return cs
+
+
 def gen_circuit_for_bench(num_gates: int, field: Field = pyref.BN254_FR) -> PlonkCircuit:
     """plonk/benches/bench.rs:29-46 (TurboPlonk)."""
     cs = PlonkCircuit(field)

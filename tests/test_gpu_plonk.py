@@ -47,6 +47,8 @@ CIRCUITS = {
     "test_m20": lambda P: P.gen_circuit_for_test(20, 1),
     "bench_2^10": lambda P: P.gen_circuit_for_bench(1 << 10),
     "test_m300": lambda P: P.gen_circuit_for_test(300, 7),
+    "all_selectors_m9": lambda P: P.gen_circuit_all_selectors(9),      # every selector column non-zero
+    "all_selectors_m100": lambda P: P.gen_circuit_all_selectors(100),
 }
 
 

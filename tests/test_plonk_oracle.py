@@ -52,11 +52,13 @@ def test_solidity_transcript_follows_the_code_not_the_doc(P, py):
 
 
 @pytest.mark.parametrize("kind", ["solidity", "standard"])
-@pytest.mark.parametrize("which", ["test_m2", "bench_64", "test_m20"])
+@pytest.mark.parametrize("which", ["test_m2", "bench_64", "test_m20", "all_sel"])
 def test_oracle_prover_satisfies_oracle_verifier(P, py, kind, which):
     cv = py.BN254
     cs = {"test_m2": lambda: P.gen_circuit_for_test(2, 3), "bench_64": lambda: P.gen_circuit_for_bench(64),
-          "test_m20": lambda: P.gen_circuit_for_test(20, 1)}[which]()
+          "test_m20": lambda: P.gen_circuit_for_test(20, 1), "all_sel": lambda: P.gen_circuit_all_selectors(5)}[which]()
+    if which == "all_sel":
+        assert all(any(col) for col in cs.selector_evals()), "every selector column must be exercised"
     assert cs.check_satisfiability()
     beta = 0x1234567890ABCDEF1234567890ABCDEF % cv.fr.p
     pk = P.preprocess(cv, P.gen_srs(cv, beta, cs.n + 2), cs)
