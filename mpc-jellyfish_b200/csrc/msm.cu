@@ -6,9 +6,10 @@
 // 396-416) and of `preprocess` (plonk/src/proof_system/snark.rs:562-571).
 //
 // Pipeline (all on one stream, no host round trip until the single result point):
-//   1. digits + histogram : signed c-bit digits of every scalar, one atomic per non-zero digit
-//   2. scan               : bucket offsets
-//   3. scatter            : counting sort of (sign | table | point index) by bucket
+//   1-3. sort by bucket   : direct form (uniform digits): every bucket owns fixed slots, ONE pass writes
+//                           (sign | table | point index) at the bucket's running count, then a scan of the counts;
+//                           compact form (narrow top window, or a bucket overflowed its slots -- decided on the
+//                           device): digits + histogram, scan, counting-sort scatter
 //   4. accumulate         : the sorted list is cut into equal chunks, one per thread, regardless of
 //                           bucket boundaries (perfect balance even when all scalars fall into one
 //                           bucket); XYZZ += affine mixed additions (8M + 2S), points gathered from
@@ -119,9 +120,10 @@ __global__ void msm_count_kernel(const uint32_t *scalars, MsmGeom g, uint32_t *c
 // that a thread has eight L2 round trips in flight instead of one.
 template <class Fr>
 __global__ void msm_scatter_kernel(const uint32_t *__restrict__ scalars, MsmGeom g, uint32_t *__restrict__ cursor,
-                                   uint32_t *__restrict__ sorted) {
+                                   uint32_t *__restrict__ sorted, const int *only_if) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
+    if (only_if && !*only_if) return;  // fallback launch of the direct path: nothing overflowed
     uint32_t s[8];
     if (!load_scalar<Fr>(scalars + 8 * (size_t)i, g.mont, s)) return;
     const bool agg_top = Fr::BITS + 1 - (g.W - 1) * g.c <= AGG_TOP_BITS;
@@ -158,6 +160,58 @@ __global__ void msm_scatter_kernel(const uint32_t *__restrict__ scalars, MsmGeom
 #pragma unroll
         for (int k = 0; k < 8; k++)
             if (on[k]) sorted[pos[k]] = payload[k];
+    }
+}
+
+// Direct form (no counting pass): every bucket owns `1 << cap_log` slots, the running count of a bucket is its
+// cursor.  counts[] ends up exact even when a bucket overflows its slots; the overflow flag then routes the MSM
+// through the compact (count / scan / scatter) path, whose counting pass this kernel has already done.
+template <class Fr>
+__global__ void msm_scatter_direct_kernel(const uint32_t *__restrict__ scalars, MsmGeom g, uint32_t *__restrict__ counts,
+                                          uint32_t *__restrict__ slots, uint32_t cap_log, int *overflow, int *err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    uint32_t s[8];
+    if (!load_scalar<Fr>(scalars + 8 * (size_t)i, g.mont, s)) {
+        *err = JF_ERR_SCALAR_RANGE;
+        return;
+    }
+    const uint32_t half = 1u << (g.c - 1), cap = 1u << cap_log;
+    uint32_t carry = 0;
+    for (int w0 = 0; w0 < g.W; w0 += 8) {
+        uint32_t bucket[8], payload[8], pos[8];
+        bool on[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int w = w0 + k;
+            on[k] = false;
+            if (w < g.W) {
+                uint32_t raw = take_bits(s, w * g.c, g.c) + carry;
+                int32_t d;
+                if (raw > half) {
+                    d = (int32_t)raw - (int32_t)(1u << g.c);
+                    carry = 1;
+                } else {
+                    d = (int32_t)raw;
+                    carry = 0;
+                }
+                if (d != 0) {
+                    const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+                    on[k] = true;
+                    bucket[k] = (uint32_t)(w / g.T) * g.NB + (mag - 1);
+                    payload[k] = (d < 0 ? 0x80000000u : 0u) | ((uint32_t)(w % g.T) << IDX_BITS) | (g.base_offset + i);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (on[k]) pos[k] = atomicAdd(&counts[bucket[k]], 1u);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (on[k]) {
+                if (pos[k] < cap) slots[((size_t)bucket[k] << cap_log) + pos[k]] = payload[k];
+                else *overflow = 1;
+            }
     }
 }
 
@@ -256,15 +310,18 @@ __device__ __forceinline__ uint32_t chunk_len(uint32_t entries, uint32_t nthread
     return e < ACC_MIN_CHUNK ? ACC_MIN_CHUNK : e;
 }
 
-// Thread t owns sorted[t*E, (t+1)*E).  It emits one partial per bucket it touches, into slot
-// t + bucket: slots are unique (consecutive threads touch non-decreasing buckets) and the
-// partials of one bucket are consecutive, so no task list or second scan is needed.
-template <class Fq>
+// Thread t owns entries [t*E, (t+1)*E) of the bucket-ordered list.  It emits one partial per bucket it touches,
+// into slot t + bucket: slots are unique (consecutive threads touch non-decreasing buckets) and the partials of
+// one bucket are consecutive, so no task list or second scan is needed.
+// The list is either compact (`cap_log` == 0: entry pos at list[pos]) or slotted (entry k of bucket b at
+// list[(b << cap_log) + k]); `flag` / `run_if_set` select which of the two launches of an MSM does the work.
+template <class Fq, bool SLOTTED>
 // 112 registers: four CTAs per SM leave ~7 K registers free, so the one-warp kernels of another stream (bucket
 // reduction of the previous MSM of a batch) can run beside a resident accumulate wave
 __global__ void __maxnreg__(112)
-msm_accumulate_kernel(const Affine<Fq> *points, uint32_t srs_n, const uint32_t *sorted, const uint32_t *off,
-                      uint32_t total_buckets, XYZZ<Fq> *partials) {
+msm_accumulate_kernel(const Affine<Fq> *points, uint32_t srs_n, const uint32_t *list, uint32_t cap_log, const uint32_t *off,
+                      uint32_t total_buckets, XYZZ<Fq> *partials, const int *flag, int run_if_set) {
+    if (flag && ((*flag != 0) != (run_if_set != 0))) return;
     const uint32_t nthreads = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t entries = off[total_buckets];
     const uint32_t E = chunk_len(entries, nthreads);
@@ -278,26 +335,33 @@ msm_accumulate_kernel(const Affine<Fq> *points, uint32_t srs_n, const uint32_t *
         if (off[mid] <= start) lo = mid;
         else hi = mid;
     }
-    uint32_t b = lo, next = off[b + 1];
+    // fetch cursor: bucket fb holds entries [foff, fnext)
+    uint32_t fb = lo, foff = off[lo], fnext = off[lo + 1];
+    auto fetch = [&](uint32_t pos) -> uint32_t {
+        while (pos >= fnext) {
+            fb++;
+            foff = fnext;
+            fnext = off[fb + 1];
+        }
+        return SLOTTED ? list[((size_t)fb << cap_log) + (pos - foff)] : list[pos];
+    };
     XYZZ<Fq> acc = XYZZ<Fq>::inf();
     // software pipeline: the gather of entry pos + 1 (a random 64-byte read, ~1 us from HBM) is in flight
     // while entry pos is being added
-    uint32_t pl = sorted[start];
+    uint32_t pl = fetch(start);
+    uint32_t b = fb;
     Affine<Fq> p = load_affine(points + (size_t)((pl >> IDX_BITS) & 31u) * srs_n + (pl & IDX_MASK));
     for (uint32_t pos = start; pos < end; pos++) {
-        const uint32_t cur_pl = pl;
+        const uint32_t cur_pl = pl, cur_b = fb;
         Affine<Fq> cur = p;
         if (pos + 1 < end) {
-            pl = sorted[pos + 1];
+            pl = fetch(pos + 1);
             p = load_affine(points + (size_t)((pl >> IDX_BITS) & 31u) * srs_n + (pl & IDX_MASK));
         }
-        if (pos >= next) {
+        if (cur_b != b) {
             store_xyzz(partials + (size_t)t + b, acc);
             acc = XYZZ<Fq>::inf();
-            do {
-                b++;
-                next = off[b + 1];
-            } while (pos >= next);
+            b = cur_b;
         }
         if (cur.is_inf()) continue;
         if (cur_pl & 0x80000000u) cur.y = Fp<Fq>::neg(cur.y);
@@ -488,19 +552,49 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     Rs = PB + (size_t)g.S * cap_p;
     err = ctx->d_err;
     uint32_t *heavy;
-    JF_TRY(scratch(ctx, "msm_heavy", sizeof(uint32_t) * ((size_t)total + 4), &p));
+    JF_TRY(scratch(ctx, "msm_heavy", sizeof(uint32_t) * ((size_t)total + 8), &p));
     heavy = (uint32_t *)p;  // [0] = count, [1..] = bucket ids
 
     const uint32_t *sc = (const uint32_t *)d_scalars;
     JF_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (total + 1), st));
     const unsigned nblk = (unsigned)((n + 255) / 256);
-    JF_LAUNCH(ctx, "msm_count", msm_count_kernel<Fr><<<nblk, 256, 0, st>>>(sc, g, counts, err));
-    JF_LAUNCH(ctx, "scan_local", scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, total, off, block_sums));
-    JF_LAUNCH(ctx, "scan_sums", scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, scan_blocks, off, total));
-    JF_LAUNCH(ctx, "scan_add", scan_add_kernel<<<(total + 255) / 256, 256, 0, st>>>(block_sums, total, off, cursor));
-    JF_LAUNCH(ctx, "msm_scatter", msm_scatter_kernel<Fr><<<nblk, 256, 0, st>>>(sc, g, cursor, sorted));
-    JF_LAUNCH(ctx, "msm_accumulate", msm_accumulate_kernel<Fq><<<acc_blocks, ACC_THREADS, 0, st>>>(
-        (const Affine<Fq> *)srs->d_points, g.srs_n, sorted, off, total, partials));
+    // Direct sort when every bucket is expected to stay far below its slot capacity (uniform digits, no narrow
+    // top window): one pass over the scalars instead of two.  A bucket that overflows anyway (skewed scalars)
+    // raises a device-side flag and the compact path below takes over; no host round trip either way.
+    const int top_bits = Fr::BITS + 1 - (g.W - 1) * g.c;
+    uint32_t cap_log = 0;
+    {
+        const size_t lam = max_entries / total + 1;  // expected entries per bucket
+        size_t cap = 64;
+        while (cap < 2 * lam + 64) cap <<= 1;
+        while (((size_t)1 << cap_log) < cap) cap_log++;
+        if (top_bits < g.c - 1 || (size_t)total * cap > 8 * max_entries + ((size_t)1 << 22)) cap_log = 0;  // not worth the slots
+    }
+    int *flag = (int *)(heavy + total + 2);
+    if (cap_log) {
+        uint32_t *slots;
+        JF_TRY(scratch(ctx, "msm_slots", sizeof(uint32_t) * ((size_t)total << cap_log), &p));
+        slots = (uint32_t *)p;
+        JF_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), st));
+        JF_LAUNCH(ctx, "msm_scatter_direct", msm_scatter_direct_kernel<Fr><<<nblk, 256, 0, st>>>(sc, g, counts, slots, cap_log, flag, err));
+        JF_LAUNCH(ctx, "scan_local", scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, total, off, block_sums));
+        JF_LAUNCH(ctx, "scan_sums", scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, scan_blocks, off, total));
+        JF_LAUNCH(ctx, "scan_add", scan_add_kernel<<<(total + 255) / 256, 256, 0, st>>>(block_sums, total, off, cursor));
+        JF_LAUNCH(ctx, "msm_accumulate", msm_accumulate_kernel<Fq, true><<<acc_blocks, ACC_THREADS, 0, st>>>(
+            (const Affine<Fq> *)srs->d_points, g.srs_n, slots, cap_log, off, total, partials, flag, 0));
+        // fallback (both launches return at once unless the flag is set)
+        JF_LAUNCH(ctx, "msm_scatter", msm_scatter_kernel<Fr><<<nblk, 256, 0, st>>>(sc, g, cursor, sorted, flag));
+        JF_LAUNCH(ctx, "msm_accumulate_fallback", msm_accumulate_kernel<Fq, false><<<acc_blocks, ACC_THREADS, 0, st>>>(
+            (const Affine<Fq> *)srs->d_points, g.srs_n, sorted, 0u, off, total, partials, flag, 1));
+    } else {
+        JF_LAUNCH(ctx, "msm_count", msm_count_kernel<Fr><<<nblk, 256, 0, st>>>(sc, g, counts, err));
+        JF_LAUNCH(ctx, "scan_local", scan_local_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, total, off, block_sums));
+        JF_LAUNCH(ctx, "scan_sums", scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, scan_blocks, off, total));
+        JF_LAUNCH(ctx, "scan_add", scan_add_kernel<<<(total + 255) / 256, 256, 0, st>>>(block_sums, total, off, cursor));
+        JF_LAUNCH(ctx, "msm_scatter", msm_scatter_kernel<Fr><<<nblk, 256, 0, st>>>(sc, g, cursor, sorted, (const int *)nullptr));
+        JF_LAUNCH(ctx, "msm_accumulate", msm_accumulate_kernel<Fq, false><<<acc_blocks, ACC_THREADS, 0, st>>>(
+            (const Affine<Fq> *)srs->d_points, g.srs_n, sorted, 0u, off, total, partials, (const int *)nullptr, 0));
+    }
     JF_CUDA(ctx, cudaMemsetAsync(heavy, 0, sizeof(uint32_t), st));
     JF_LAUNCH(ctx, "bucket_sum", bucket_sum_kernel<Fq><<<(total + 127) / 128, 128, 0, st>>>(partials, off, total, acc_threads, XA, heavy, heavy + 1));
     JF_LAUNCH(ctx, "bucket_sum_heavy", bucket_sum_heavy_kernel<Fq><<<(unsigned)ctx->sm_count * 4, HEAVY_THREADS, 0, st>>>(partials, off, total, acc_threads, XA, heavy, heavy + 1));
