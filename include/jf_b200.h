@@ -125,6 +125,17 @@ int jf_ntt(jf_ctx *ctx, int field, uint64_t *data, size_t in_len, unsigned log_n
 /* Same on a device pointer (data stays in HBM; used by the device-resident prover rows). */
 int jf_ntt_device(jf_ctx *ctx, int field, void *d_data, size_t in_len, unsigned log_n, int inverse,
                   const uint64_t *coset_offset, size_t batch, size_t batch_stride);
+/* Several cosets of the size-2^log_n domain in one batch.  The 8n-point quotient coset g<w_8n> of the prover
+ * (plonk/src/proof_system/prover.rs:545,552-567) is the union of the cosets (g w_8n^r)<w_n>, r < 8, and the
+ * quotient (degree 5n + 7, prover.rs:1126-1128) is already determined by six of them, so round 3 evaluates its
+ * 25 polynomials on rows of n points instead of one 8n-point transform each.
+ *   inverse == 0: `polys` coefficient vectors of in_len <= 2n entries, in_stride ELEMENTS apart, are read from
+ *       polys_in; out[(p * rows + r) * n + i] = poly_p(offsets[r] * w_n^i)   (`get_coset(offsets[r]).fft`).
+ *   inverse != 0: polys_in is ignored; `out` holds polys x rows rows of n values on those cosets and is
+ *       overwritten in place by the n coefficients of each row's interpolant (`get_coset(offsets[r]).ifft`).
+ * offsets: rows x 4 Montgomery limbs, 1 <= rows <= 16; 3 <= log_n <= two-adicity. */
+int jf_ntt_cosets(jf_ctx *ctx, int field, const uint64_t *polys_in, size_t in_len, size_t in_stride, size_t polys,
+                  unsigned log_n, int inverse, const uint64_t *offsets, int rows, uint64_t *out);
 
 /* ---- TurboPlonk prover rounds around the two kernels -----------------
  * One TurboPlonk instance, 5 wire types, no Plookup.  Circuit construction stays with the caller
@@ -139,7 +150,11 @@ int jf_ntt_device(jf_ctx *ctx, int field, void *d_data, size_t in_len, unsigned 
  * keep their 8n coset evaluations resident (18 of the 25 coset NTTs of round 3 then happen once per
  * key instead of once per proof; +4.5 GiB at n = 2^20).  flags & 2: selector columns that are identically
  * zero (e.g. q_hash / q_ecc in circuits without Rescue or ECC gates) are recognised once and their coset NTTs and
- * quotient terms are skipped; the proof is unchanged.  `srs` must outlive the key and hold >= n + 3 points.  2 <= log_n and
+ * quotient terms are skipped; the proof is unchanged.  Round 3 evaluates the quotient on six sub-cosets
+ * (g w_8n^r)<w_n>, r < 6, of the reference's 8n-point coset (6n points determine a polynomial of degree 5n + 7;
+ * the coefficients follow from six size-n inverse transforms and a 6 x 6 Vandermonde solve per index), which
+ * yields the same quotient polynomial with 29 % less transform work; flags & 4 keeps the reference's form (one
+ * 8n-point coset transform per polynomial, prover.rs:552-567,672), as do domains below 8.  `srs` must outlive the key and hold >= n + 3 points.  2 <= log_n and
  * log_n + 3 <= two-adicity (JF_ERR_DOMAIN_TOO_LARGE otherwise: `Prover::new`, prover.rs:54-62). */
 int jf_plonk_preprocess(jf_ctx *ctx, const jf_srs *srs, unsigned log_n, const uint64_t *selector_evals,
                         const uint64_t *sigma_evals, const uint64_t *k, const uint32_t *wire_variables, size_t num_vars,

@@ -79,6 +79,8 @@ SIGNATURES = {
                               ctypes.c_size_t, ctypes.c_size_t]),
     "jf_ntt_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint,
                                      ctypes.c_int, c_u64p, ctypes.c_size_t, ctypes.c_size_t]),
+    "jf_ntt_cosets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t,
+                                     ctypes.c_uint, ctypes.c_int, c_u64p, ctypes.c_int, c_u64p]),
     "jf_dev_alloc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, c_void_pp]),
     "jf_dev_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "jf_dev_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),

@@ -155,6 +155,29 @@ class Context:
                                      int(inverse), _u64p(off) if off is not None else None, batch, data.shape[-2]))
         return data
 
+    def ntt_cosets(self, field: str, polys: np.ndarray, log_n: int, offsets: np.ndarray) -> np.ndarray:
+        """`get_coset(offsets[r]).fft` of every row of `polys` ((p, in_len, 4), in_len <= 2n) -> (p, rows, n, 4)."""
+        polys = np.ascontiguousarray(polys, dtype=np.uint64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64).reshape(-1, 4)
+        if polys.ndim != 3 or polys.shape[-1] != 4:
+            raise InvalidParameters("ntt_cosets wants a (polys, in_len, 4) uint64 array")
+        n = 1 << log_n if log_n < 63 else 0
+        out = np.zeros((polys.shape[0], offsets.shape[0], n, 4), dtype=np.uint64)
+        self._check(self._lib.jf_ntt_cosets(self._h, _ffi.FIELDS[field], _u64p(polys), polys.shape[1], polys.shape[1],
+                                            polys.shape[0], log_n, 0, _u64p(offsets), offsets.shape[0], _u64p(out)))
+        return out
+
+    def intt_cosets(self, field: str, rows: np.ndarray, log_n: int, offsets: np.ndarray) -> np.ndarray:
+        """`get_coset(offsets[r]).ifft` in place on `rows` ((p, rows, n, 4)); returns `rows`."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64).reshape(-1, 4)
+        n = 1 << log_n if log_n < 63 else 0
+        if (rows.dtype != np.uint64 or not rows.flags["C_CONTIGUOUS"] or not rows.flags["WRITEABLE"] or rows.ndim != 4
+                or rows.shape[1:] != (offsets.shape[0], n, 4)):
+            raise InvalidParameters("intt_cosets wants a writable C-contiguous (polys, rows, n, 4) uint64 array")
+        self._check(self._lib.jf_ntt_cosets(self._h, _ffi.FIELDS[field], None, n, n, rows.shape[0], log_n, 1, _u64p(offsets),
+                                            offsets.shape[0], _u64p(rows)))
+        return rows
+
     def ntt_device(self, field: str, d_data: int, log_n: int, inverse: bool = False,
                    coset_offset: Optional[np.ndarray] = None, in_len: Optional[int] = None, batch: int = 1,
                    batch_stride: Optional[int] = None):

@@ -396,6 +396,37 @@ int jf_ntt(jf_ctx *ctx, int field, uint64_t *data, size_t in_len, unsigned log_n
     return JF_OK;
 }
 
+int jf_ntt_cosets(jf_ctx *ctx, int field, const uint64_t *polys_in, size_t in_len, size_t in_stride, size_t polys,
+                  unsigned log_n, int inverse, const uint64_t *offsets, int rows, uint64_t *out) {
+    JF_GUARD(ctx);
+    if (!out || !offsets || (!inverse && !polys_in)) return fail(ctx, JF_ERR_INVALID_ARG, "ntt_cosets: null argument");
+    if (field != JF_BN254_FR && field != JF_BLS12_381_FR)
+        return fail(ctx, JF_ERR_INVALID_ARG, "ntt: field must be BN254 Fr or BLS12-381 Fr");
+    if (log_n > (field == JF_BN254_FR ? 28u : 32u))
+        return fail(ctx, JF_ERR_DOMAIN_TOO_LARGE, "ntt: log_n exceeds the field's two-adicity");
+    if (log_n > 30) return fail(ctx, JF_ERR_NOMEM, "ntt: log_n > 30 is not supported");
+    if (rows < 1 || rows > 16) return fail(ctx, JF_ERR_INVALID_ARG, "ntt_cosets: 1..16 cosets");
+    if (polys == 0) return JF_OK;
+    const size_t n = (size_t)1 << log_n, total = polys * (size_t)rows;
+    if (!inverse && (in_len > 2 * n || in_stride < in_len)) return fail(ctx, JF_ERR_INVALID_ARG, "ntt_cosets: in_len > 2 n or in_stride < in_len");
+    void *d_in = nullptr, *d_out = nullptr;
+    JF_TRY(scratch(ctx, "nttc_out", 32 * n * total, &d_out));
+    if (!inverse) {
+        const size_t dstride = in_len ? in_len : 1;
+        JF_TRY(scratch(ctx, "nttc_in", 32 * dstride * polys, &d_in));
+        if (in_len)
+            JF_CUDA(ctx, cudaMemcpy2DAsync(d_in, 32 * dstride, polys_in, 32 * in_stride, 32 * in_len, polys, cudaMemcpyHostToDevice,
+                                           ctx->stream));
+        JF_TRY(ntt_run_cosets(ctx, field, d_in, dstride, in_len, d_out, log_n, 0, offsets, rows, polys));
+    } else {
+        JF_CUDA(ctx, cudaMemcpyAsync(d_out, out, 32 * n * total, cudaMemcpyHostToDevice, ctx->stream));
+        JF_TRY(ntt_run_cosets(ctx, field, d_out, n, n, d_out, log_n, 1, offsets, rows, polys));
+    }
+    JF_CUDA(ctx, cudaMemcpyAsync(out, d_out, 32 * n * total, cudaMemcpyDeviceToHost, ctx->stream));
+    JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JF_OK;
+}
+
 // ---- device buffers -----------------------------------------------------------------------------
 int jf_dev_alloc(jf_ctx *ctx, size_t bytes, void **out) {
     JF_GUARD(ctx);

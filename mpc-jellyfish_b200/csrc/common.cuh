@@ -152,6 +152,9 @@ inline void prof_end(jf_ctx *ctx) {
 // d_out == d_data: in place.  Otherwise the result lands in d_out and d_data is clobbered.
 int ntt_run(jf_ctx *ctx, int field, void *d_data, void *d_out, size_t in_len, unsigned log_n, int inverse,
             const uint64_t *coset_offset, size_t batch, size_t batch_stride);
+// `rows` cosets offsets[r] * <w_n> of `polys` vectors in one batch (ntt_impl.cuh: ntt_run_cosets_t)
+int ntt_run_cosets(jf_ctx *ctx, int field, const void *d_src, size_t src_stride, size_t in_len, void *d_dst, unsigned log_n,
+                   int inverse, const uint64_t *offsets, int rows, size_t polys);
 void ntt_free_plans(jf_ctx *ctx);
 int msm_run(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n, int mont,
             void *d_out_xyzz);

@@ -47,6 +47,9 @@ struct NttPlan {
     std::vector<void *> ptw;
     void *off_full = nullptr;                   // offset^j (fwd) / n^-1 offset^-j (inv), j < n; built on first dense use
     bool ninv_folded = false;
+    // ntt_run_cosets: `rows` offset tables of n entries in off_full, X^n on each coset in fold_c
+    int rows = 0;
+    void *fold_c = nullptr;
 };
 
 inline void free_plan(NttPlan *pl) {
@@ -56,6 +59,7 @@ inline void free_plan(NttPlan *pl) {
     cudaFree(pl->off_hi);
     cudaFree(pl->n_inv);
     cudaFree(pl->off_full);
+    cudaFree(pl->fold_c);
     for (auto &t : pl->ptw) cudaFree(t);
     for (auto &t : pl->tw) cudaFree(t);
     delete pl;
@@ -112,6 +116,12 @@ struct PassArgs {
     const void *w_lo, *w_hi, *off_lo, *off_hi, *tw, *n_inv;
     const void *ptw;       // this pass' inter-pass twiddle table (passes > 0)
     const void *off_full;  // full offset power table or NULL (then the two-level tables are used)
+    // several cosets of one polynomial (ntt_run_cosets): batch entry `bid` is coset row bid % off_rows, whose
+    // offset powers are off_full + row * n; on the first pass src_group consecutive entries read the same
+    // source vector, and coefficients n.. are folded in with X^n = fold_c[row] (reduction mod X^n - c)
+    size_t src_stride;
+    uint32_t src_group, off_rows;
+    const void *fold_c;
 };
 
 template <int K> __device__ __forceinline__ uint32_t bitrev_k(uint32_t x) { return __brev(x) >> (32 - K); }
@@ -138,9 +148,16 @@ template <class F, int K, bool FIRST, bool LAST> __global__ void __launch_bounds
     const uint64_t bid = blockIdx.x % a.batch;
     const uint64_t j = (uint64_t)(blockIdx.x / a.batch) * B + b;
     const bool valid = j < cols;
-    const E *src = reinterpret_cast<const E *>(a.src) + bid * a.stride;
+    const E *src = reinterpret_cast<const E *>(a.src) + (FIRST ? (bid / a.src_group) * a.src_stride : bid * a.stride);
     E *dst = reinterpret_cast<E *>(a.dst) + bid * a.stride;
     const E *tw = reinterpret_cast<const E *>(a.tw);
+    // this entry's offset table (only the first / last pass of a coset transform touches it)
+    const E *off_full = reinterpret_cast<const E *>(a.off_full);
+    uint32_t orow = 0;
+    if ((FIRST || LAST) && a.off_rows > 1) {
+        orow = (uint32_t)(bid % a.off_rows);
+        off_full += (size_t)orow << a.log_n;
+    }
 
     E v[8];
     // ---- gather (group 0 mapping: row = e << (K-3) | q) ------------------------------------
@@ -154,8 +171,10 @@ template <class F, int K, bool FIRST, bool LAST> __global__ void __launch_bounds
             if (valid && (!FIRST || idx < a.in_len)) {
                 v[e] = ld_el(src + idx);
                 if (FIRST) {
+                    if (a.fold_c && idx + (1ull << a.log_n) < a.in_len)
+                        v[e] = E::add(v[e], E::mul(ld_el(src + idx + (1ull << a.log_n)), ldg_el((const E *)a.fold_c + orow)));
                     if (a.coset_in)
-                        v[e] = E::mul(v[e], a.off_full ? ldg_el((const E *)a.off_full + idx)
+                        v[e] = E::mul(v[e], a.off_full ? ldg_el(off_full + idx)
                                                        : pow2l((const E *)a.off_lo, (const E *)a.off_hi, idx, a.split));
                 } else {
                     v[e] = E::mul(v[e], ldg_el((const E *)a.ptw + (((uint64_t)r << a.log_ns) | k)));
@@ -228,7 +247,7 @@ template <class F, int K, bool FIRST, bool LAST> __global__ void __launch_bounds
             if (LAST) {
                 if (a.scale_mode == 1) o = E::mul(o, ldg_el(ninv));
                 else if (a.scale_mode == 2)
-                    o = E::mul(o, ldg_el((const E *)a.off_full + idx));  // ntt_run always builds it for inverses
+                    o = E::mul(o, ldg_el(off_full + idx));  // ntt_run always builds it for inverses
             }
             st_el(dst + idx, o);
         }
@@ -408,18 +427,10 @@ template <class F> static int launch_pass_k(jf_ctx *ctx, int k, const PassArgs &
     return fail(ctx, JF_ERR_INVALID_ARG, "ntt: bad radix");
 }
 
+// cached plan of (field, log n, direction, offset); an offset equal to one is the plain domain
 template <class F>
-static int ntt_run_t(jf_ctx *ctx, int field, void *d_data, void *d_out, size_t in_len, unsigned log_n, int inverse,
-                     const uint64_t *coset_offset, size_t batch, size_t batch_stride) {
+static int get_plan(jf_ctx *ctx, int field, unsigned log_n, int inverse, const uint64_t *coset_offset, NttPlan **out, bool *out_has_off) {
     using E = Fp<F>;
-    if (log_n > (unsigned)F::TWO_ADICITY) return fail(ctx, JF_ERR_DOMAIN_TOO_LARGE, "ntt: log_n exceeds the field's two-adicity");
-    if (log_n > 30) return fail(ctx, JF_ERR_NOMEM, "ntt: log_n > 30 is not supported");
-    const size_t n = (size_t)1 << log_n;
-    if (in_len > n) return fail(ctx, JF_ERR_INVALID_ARG, "ntt: in_len > domain size");
-    if (batch == 0) return JF_OK;
-    if (batch > 1 && batch_stride < n) return fail(ctx, JF_ERR_INVALID_ARG, "ntt: batch_stride < domain size");
-    if (batch >= (1u << 30)) return fail(ctx, JF_ERR_INVALID_ARG, "ntt: batch too large");
-    // is the offset the Montgomery one?  then it is the plain domain
     bool has_off = false;
     if (coset_offset) {
         E one = E::one();
@@ -447,6 +458,25 @@ static int ntt_run_t(jf_ctx *ctx, int field, void *d_data, void *d_out, size_t i
     } else {
         pl = it->second;
     }
+    *out = pl;
+    *out_has_off = has_off;
+    return JF_OK;
+}
+
+template <class F>
+static int ntt_run_t(jf_ctx *ctx, int field, void *d_data, void *d_out, size_t in_len, unsigned log_n, int inverse,
+                     const uint64_t *coset_offset, size_t batch, size_t batch_stride) {
+    using E = Fp<F>;
+    if (log_n > (unsigned)F::TWO_ADICITY) return fail(ctx, JF_ERR_DOMAIN_TOO_LARGE, "ntt: log_n exceeds the field's two-adicity");
+    if (log_n > 30) return fail(ctx, JF_ERR_NOMEM, "ntt: log_n > 30 is not supported");
+    const size_t n = (size_t)1 << log_n;
+    if (in_len > n) return fail(ctx, JF_ERR_INVALID_ARG, "ntt: in_len > domain size");
+    if (batch == 0) return JF_OK;
+    if (batch > 1 && batch_stride < n) return fail(ctx, JF_ERR_INVALID_ARG, "ntt: batch_stride < domain size");
+    if (batch >= (1u << 30)) return fail(ctx, JF_ERR_INVALID_ARG, "ntt: batch too large");
+    NttPlan *pl;
+    bool has_off;
+    JF_TRY(get_plan<F>(ctx, field, log_n, inverse, coset_offset, &pl, &has_off));
     E *data = reinterpret_cast<E *>(d_data);
     if (log_n < NTT_MIN_K) {
         JF_LAUNCH(ctx, "ntt_tiny", ntt_tiny_kernel<F><<<(unsigned)((batch + 63) / 64), 64, 0, ctx->stream>>>(
@@ -511,11 +541,128 @@ static int ntt_run_t(jf_ctx *ctx, int field, void *d_data, void *d_out, size_t i
         a.off_hi = pl->off_hi;
         a.tw = pl->tw[pl->passes[i].k];
         a.n_inv = pl->n_inv;
+        a.src_stride = batch_stride;
+        a.src_group = 1;
+        a.off_rows = 1;
+        a.fold_c = nullptr;
         JF_TRY(launch_pass_k<F>(ctx, pl->passes[i].k, a));
     }
     if (in_place && np == 1)
         JF_CUDA(ctx, cudaMemcpy2DAsync(d_data, batch_stride * sizeof(E), t1, batch_stride * sizeof(E), n * sizeof(E), batch,
                                        cudaMemcpyDeviceToDevice, ctx->stream));
+    return JF_OK;
+}
+
+// Several cosets of the same size-n domain in one batch (the quotient domain of the prover taken coset by coset:
+// the 8n-point coset g<w_8n> is the union of the eight cosets (g w_8n^r)<w_n>, and a polynomial of degree < 2n
+// is evaluated on one of them by reducing it mod X^n - (g w_8n^r)^n and transforming n coefficients).
+//   forward: polynomial p at d_src + p * src_stride (in_len <= 2n coefficients)
+//            -> d_dst[(p * rows + r) * n + i] = poly(offsets[r] * w_n^i)
+//   inverse: in place on d_dst: row (p * rows + r) holds values on coset r and becomes the n coefficients of
+//            the interpolant of degree < n
+// All rows share the twiddle tables of the plain size-n plan; each coset has its own table of offset powers.
+template <class F>
+static int ntt_run_cosets_t(jf_ctx *ctx, int field, const void *d_src, size_t src_stride, size_t in_len, void *d_dst, unsigned log_n,
+                            int inverse, const uint64_t *offsets, int rows, size_t polys) {
+    using E = Fp<F>;
+    if (log_n > (unsigned)F::TWO_ADICITY) return fail(ctx, JF_ERR_DOMAIN_TOO_LARGE, "ntt: log_n exceeds the field's two-adicity");
+    if (log_n > 30) return fail(ctx, JF_ERR_NOMEM, "ntt: log_n > 30 is not supported");
+    if (log_n < (unsigned)NTT_MIN_K) return fail(ctx, JF_ERR_INVALID_ARG, "ntt_cosets: domain smaller than 8");
+    if (rows < 1 || rows > 16 || !offsets) return fail(ctx, JF_ERR_INVALID_ARG, "ntt_cosets: 1..16 cosets");
+    const size_t n = (size_t)1 << log_n;
+    if (!inverse && in_len > 2 * n) return fail(ctx, JF_ERR_INVALID_ARG, "ntt_cosets: in_len > 2 n");
+    if (polys == 0) return JF_OK;
+    const size_t total = polys * (size_t)rows;
+    if (total >= (1u << 30)) return fail(ctx, JF_ERR_INVALID_ARG, "ntt: batch too large");
+    NttPlan *base;
+    bool unused;
+    JF_TRY(get_plan<F>(ctx, field, log_n, inverse, nullptr, &base, &unused));
+    std::string key = "cosets/" + std::to_string(field) + "/" + std::to_string(log_n) + "/" + std::to_string(inverse ? 1 : 0) + "/";
+    for (int i = 0; i < 4 * rows; i++) {
+        char h[20];
+        snprintf(h, sizeof h, "%016llx", (unsigned long long)offsets[i]);
+        key += h;
+    }
+    NttPlan *pl;
+    auto it = ctx->ntt_plans.find(key);
+    if (it == ctx->ntt_plans.end()) {
+        pl = new NttPlan();
+        pl->field = field;
+        pl->log_n = log_n;
+        pl->inverse = inverse != 0;
+        pl->has_offset = true;
+        pl->rows = rows;
+        ctx->ntt_plans[key] = pl;  // owned by the cache from here on (freed with the context)
+        E ninv = E::one();
+        if (inverse && !base->ninv_folded) {
+            E half = E::inv(E::from_u32(2));
+            for (unsigned i = 0; i < log_n; i++) ninv = E::mul(ninv, half);
+        }
+        JF_CUDA(ctx, cudaMalloc(&pl->off_full, sizeof(E) * n * rows));
+        JF_CUDA(ctx, cudaMalloc(&pl->fold_c, sizeof(E) * rows));
+        std::vector<E> c(rows);
+        for (int r = 0; r < rows; r++) {
+            E off;
+            for (int i = 0; i < 4; i++) {
+                off.v[2 * i] = (uint32_t)offsets[4 * r + i];
+                off.v[2 * i + 1] = (uint32_t)(offsets[4 * r + i] >> 32);
+            }
+            c[r] = off;
+            for (unsigned i = 0; i < log_n; i++) c[r] = E::sqr(c[r]);
+            if (inverse) off = E::inv(off);
+            JF_LAUNCH(ctx, "pow_table", pow_table_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(
+                (E *)pl->off_full + (size_t)r * n, off, ninv, 1, (uint32_t)n));
+        }
+        JF_CUDA(ctx, cudaMemcpyAsync(pl->fold_c, c.data(), sizeof(E) * rows, cudaMemcpyHostToDevice, ctx->stream));
+        JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // c is a local
+    } else {
+        pl = it->second;
+    }
+    const int np = (int)base->passes.size();
+    void *t1 = nullptr, *t2 = nullptr;
+    std::vector<const void *> hop(np + 1);
+    hop[np] = d_dst;
+    if (!inverse) {
+        if (np >= 2) JF_TRY(scratch(ctx, "ntt_c1", total * n * sizeof(E), &t1));
+        hop[0] = d_src;
+        for (int i = np - 1; i >= 1; i--) hop[i] = ((np - i) % 2 == 1) ? t1 : d_dst;
+    } else {
+        JF_TRY(scratch(ctx, "ntt_c1", total * n * sizeof(E), &t1));
+        if (np % 2 == 1 && np >= 3) JF_TRY(scratch(ctx, "ntt_c2", total * n * sizeof(E), &t2));
+        hop[0] = d_dst;
+        if (np == 1) hop[1] = t1;
+        for (int i = 1; i < np; i++) hop[i] = (i % 2 == 1) ? t1 : (np % 2 == 0 ? (const void *)d_dst : (const void *)t2);
+    }
+    for (int i = 0; i < np; i++) {
+        PassArgs a;
+        a.src = hop[i];
+        a.dst = const_cast<void *>(hop[i + 1]);
+        a.stride = n;
+        a.in_len = inverse ? n : in_len;
+        a.batch = (uint32_t)total;
+        a.log_n = log_n;
+        a.log_ns = base->passes[i].log_ns;
+        a.first = i == 0;
+        a.last = i == np - 1;
+        a.coset_in = inverse ? 0 : 1;
+        a.scale_mode = inverse ? 2 : 0;
+        a.ptw = base->ptw[i];
+        a.off_full = pl->off_full;
+        a.split = base->split;
+        a.w_lo = base->w_lo;
+        a.w_hi = base->w_hi;
+        a.off_lo = nullptr;
+        a.off_hi = nullptr;
+        a.tw = base->tw[base->passes[i].k];
+        a.n_inv = base->n_inv;
+        a.src_stride = inverse ? n : src_stride;
+        a.src_group = inverse ? 1u : (uint32_t)rows;
+        a.off_rows = (uint32_t)rows;
+        a.fold_c = (!inverse && in_len > n) ? pl->fold_c : nullptr;
+        JF_TRY(launch_pass_k<F>(ctx, base->passes[i].k, a));
+    }
+    if (inverse && np == 1)
+        JF_CUDA(ctx, cudaMemcpyAsync(d_dst, t1, total * n * sizeof(E), cudaMemcpyDeviceToDevice, ctx->stream));
     return JF_OK;
 }
 

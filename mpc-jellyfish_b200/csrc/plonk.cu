@@ -236,12 +236,15 @@ __global__ void inv_combine_kernel(const Fp<F> *pp, const Fp<F> *sp, const Fp<F>
     stf(out + i, v);
 }
 // d[i] = scale * (x_i - 1),  x_i = hi[i >> lo_bits] * lo[i & mask]
+// sub != 0: position i = r n + j holds the point of index 8 j + r (sub-coset r of the 8n coset, see QuotArgs)
 template <class F>
-__global__ void xm1_kernel(const Fp<F> *lo, const Fp<F> *hi, int lo_bits, Fp<F> scale, Fp<F> *d, size_t m) {
+__global__ void xm1_kernel(const Fp<F> *lo, const Fp<F> *hi, int lo_bits, Fp<F> scale, Fp<F> *d, size_t m, int sub, uint32_t log_n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
+    const size_t pos = i;
+    if (sub) i = ((i & (((size_t)1 << log_n) - 1)) << 3) | (i >> log_n);
     Fp<F> x = Fp<F>::mul(ldf(lo + (i & (((size_t)1 << lo_bits) - 1))), ldf(hi + (i >> lo_bits)));
-    stf(d + i, Fp<F>::mul(scale, Fp<F>::sub(x, Fp<F>::one())));
+    stf(d + pos, Fp<F>::mul(scale, Fp<F>::sub(x, Fp<F>::one())));
 }
 // table[i] = scale * base^(i * step)
 template <class F> __global__ void pow_tab_kernel(Fp<F> *table, Fp<F> base, Fp<F> scale, uint64_t step, uint32_t count) {
@@ -261,8 +264,11 @@ template <class F> struct QuotArgs {
     Fp<F> beta_k[NW], beta, gamma, alpha, alpha2;
     Fp<F> zh_inv[8];
     Fp<F> *out;
-    uint32_t m, ratio;
+    uint32_t m, ratio;  // m: evaluation points per polynomial (8n, or 6n by sub-cosets)
     uint32_t zero_sel;  // bit s set: selector s is the zero polynomial (its term and its loads are skipped)
+    // sub != 0: the evaluations are laid out by sub-coset, position r n + j <-> the point g w_8n^(8 j + r), r < sub.
+    // Within a row the domain generator w_n is a shift by one, and X^n - 1 is the constant 1 / zh_inv[r].
+    uint32_t sub, log_n;
 };
 template <class F> __device__ __forceinline__ Fp<F> pow5(const Fp<F> &x) {
     Fp<F> x2 = Fp<F>::sqr(x);
@@ -295,10 +301,18 @@ template <class F> __global__ void __launch_bounds__(128) quotient_kernel(const 
     if (on(9)) t = E::add(t, E::mul(S(9), pow5(w[3])));
     if (on(10)) t = E::sub(t, E::mul(S(10), w[4]));
     // copy constraints (prover.rs:743-756)
-    const E x = E::mul(ldf(q.x_lo + (i & ((1u << q.lo_bits) - 1))), ldf(q.x_hi + (i >> q.lo_bits)));
+    uint32_t xi = i, inext = i + q.ratio, row = 0;
+    if (q.sub) {
+        const uint32_t nmask = (1u << q.log_n) - 1, jj = i & nmask;
+        row = i >> q.log_n;
+        xi = (jj << 3) | row;
+        inext = (i & ~nmask) | ((jj + 1) & nmask);
+    } else {
+        if (inext >= q.m) inext -= q.m;
+        row = i % q.ratio;
+    }
+    const E x = E::mul(ldf(q.x_lo + (xi & ((1u << q.lo_bits) - 1))), ldf(q.x_hi + (xi >> q.lo_bits)));
     const E zx = ldf(q.z + i);
-    uint32_t inext = i + q.ratio;
-    if (inext >= q.m) inext -= q.m;
     E r1 = zx, r2 = ldf(q.z + inext);
 #pragma unroll
     for (int j = 0; j < NW; j++) {
@@ -308,7 +322,7 @@ template <class F> __global__ void __launch_bounds__(128) quotient_kernel(const 
     }
     t = E::add(t, E::mul(q.alpha, E::sub(r1, r2)));
     E t2 = E::mul(E::mul(q.alpha2, E::sub(zx, E::one())), ldf(q.inv_nx1 + i));
-    stf(q.out + i, E::add(E::mul(t, q.zh_inv[i % q.ratio]), t2));
+    stf(q.out + i, E::add(E::mul(t, q.zh_inv[row]), t2));
 }
 // WrongQuotientPolyDegree (prover.rs:916-919): coefficient `deg` must be non-zero, all above zero
 template <class F> __global__ void degree_check_kernel(const Fp<F> *c, size_t deg, size_t m, int *err) {
@@ -316,6 +330,31 @@ template <class F> __global__ void degree_check_kernel(const Fp<F> *c, size_t de
     if (i >= m) return;
     const bool z = ldf(c + i).is_zero();
     if ((i == deg) == z) *err = JF_ERR_QUOTIENT_DEGREE;
+}
+// Quotient coefficients from its interpolants on the sub-cosets: with t = sum_k X^(k n) t_k (deg t_k < n) and
+// X^n = c_r on coset r, the interpolant there is T_r = sum_k c_r^k t_k, so t_k[j] = sum_r Vinv[k][r] T_r[j] where
+// V[r][k] = c_r^k is a SUB x SUB Vandermonde matrix (inverted once per proving key on the host).
+static constexpr int SUB = 6;  // 6 n points determine the quotient (degree 5 n + 7) for every n >= 8
+template <class F> struct SolveArgs {
+    const Fp<F> *T;  // SUB rows of n
+    Fp<F> *t;        // SUB * n coefficients
+    uint32_t n;
+    Fp<F> vinv[SUB][SUB];
+};
+template <class F> __global__ void __launch_bounds__(128) subcoset_solve_kernel(const __grid_constant__ SolveArgs<F> a) {
+    using E = Fp<F>;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.n) return;
+    E T[SUB];
+#pragma unroll
+    for (int r = 0; r < SUB; r++) T[r] = ldf(a.T + (size_t)r * a.n + j);
+#pragma unroll
+    for (int k = 0; k < SUB; k++) {
+        E acc = E::mul(a.vinv[k][0], T[0]);
+#pragma unroll
+        for (int r = 1; r < SUB; r++) acc = E::add(acc, E::mul(a.vinv[k][r], T[r]));
+        stf(a.t + (size_t)k * a.n + j, acc);
+    }
 }
 // split_quotient_polynomial (prover.rs:902-960): part i = t[i (n+2) .. ] with the masking edits
 template <class F>
@@ -410,6 +449,10 @@ struct jf_plonk_pk {
     const jf_srs *srs = nullptr;
     unsigned log_n = 0, log_m = 0;
     size_t n = 0, m = 0, np = 0;  // np = n + PAD: stride of the n-sized polynomial buffers
+    int sub = 0;                  // SUB: the quotient is evaluated on 6 of the 8 sub-cosets (n points each); 0: all 8n points
+    size_t mq = 0;                // evaluation points per polynomial: sub ? sub * n : m
+    uint64_t sub_off[6 * 4];      // offsets g w_8n^r of the sub-cosets (Montgomery limbs)
+    uint32_t vinv[6][6][8];       // inverse Vandermonde matrix of subcoset_solve_kernel
     size_t num_vars = 0;
     uint32_t num_inputs = 0;
     int cache_coset = 0;
@@ -654,6 +697,8 @@ template <class C> struct Plonk {
         pk->num_inputs = (uint32_t)num_inputs;
         pk->cache_coset = flags & 1;
         pk->skip_zero = (flags & 2) ? 1 : 0;
+        pk->sub = (log_n >= 3 && !(flags & 4)) ? SUB : 0;  // 6 n >= 5 n + 8 coefficients needs n >= 8
+        pk->mq = pk->sub ? (size_t)pk->sub * n : m;
         if (flags & 2) {
             for (int sel = 0; sel < NSEL; sel++) {
                 const uint64_t *col = selector_evals + (size_t)sel * 4 * n;
@@ -687,7 +732,7 @@ template <class C> struct Plonk {
 
     static int preprocess_inner(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *selector_evals, const uint64_t *sigma_evals,
                                 const uint64_t *k, const uint32_t *wire_variables, const uint32_t *pub_gate_ids) {
-        const size_t n = pk->n, m = pk->m, np = pk->np;
+        const size_t n = pk->n, m = pk->m, np = pk->np, mq = pk->mq;
         cudaStream_t st = ctx->stream;
         for (size_t i = 0; i < (size_t)NW * n; i++)
             if (wire_variables[i] >= pk->num_vars) return fail(ctx, JF_ERR_INVALID_ARG, "preprocess: wire variable out of range");
@@ -722,6 +767,36 @@ template <class C> struct Plonk {
             zh = E::inv(zh);
             memcpy(pk->zh_inv[r], zh.v, 32);
         }
+        if (pk->sub) {
+            // sub-coset offsets and the inverse of V[r][k] = c_r^k, c_r = (g w_m^r)^n, by Gauss-Jordan elimination
+            E V[SUB][2 * SUB];
+            for (int r = 0; r < SUB; r++) {
+                E off = E::mul(g, pow_small(wm, r));
+                H::fr_to_limbs(off, pk->sub_off + 4 * r);
+                const E c = pow_small(off, n);
+                E pw = E::one();
+                for (int kk = 0; kk < SUB; kk++) {
+                    V[r][kk] = pw;
+                    pw = E::mul(pw, c);
+                    V[r][SUB + kk] = kk == r ? E::one() : E::zero();
+                }
+            }
+            for (int col = 0; col < SUB; col++) {
+                int piv = col;
+                while (piv < SUB && V[piv][col].is_zero()) piv++;
+                if (piv == SUB) return fail(ctx, JF_ERR_INVALID_ARG, "preprocess: singular sub-coset matrix");
+                for (int kk = 0; kk < 2 * SUB; kk++) std::swap(V[piv][kk], V[col][kk]);
+                const E inv = E::inv(V[col][col]);
+                for (int kk = 0; kk < 2 * SUB; kk++) V[col][kk] = E::mul(V[col][kk], inv);
+                for (int r = 0; r < SUB; r++) {
+                    if (r == col || V[r][col].is_zero()) continue;
+                    const E f = V[r][col];
+                    for (int kk = 0; kk < 2 * SUB; kk++) V[r][kk] = E::sub(V[r][kk], E::mul(f, V[col][kk]));
+                }
+            }
+            for (int r = 0; r < SUB; r++)
+                for (int kk = 0; kk < SUB; kk++) memcpy(pk->vinv[r][kk], V[r][SUB + kk].v, 32);
+        }
         // ---- device buffers ----
         const size_t fe = sizeof(E);
         JF_TRY(dalloc(ctx, pk, fe * NSEL * n, &pk->d_sel));
@@ -733,7 +808,7 @@ template <class C> struct Plonk {
         const uint32_t lo_n = 1u << pk->lo_bits, hi_n = 1u << (pk->log_m - pk->lo_bits);
         JF_TRY(dalloc(ctx, pk, fe * lo_n, &pk->d_xlo));
         JF_TRY(dalloc(ctx, pk, fe * hi_n, &pk->d_xhi));
-        JF_TRY(dalloc(ctx, pk, fe * m, &pk->d_inv_nx1));
+        JF_TRY(dalloc(ctx, pk, fe * mq, &pk->d_inv_nx1));
         JF_TRY(dalloc(ctx, pk, fe * (pk->num_vars + 1), &pk->d_wit));
         JF_TRY(dalloc(ctx, pk, fe * NBLIND, &pk->d_bl));
         JF_TRY(dalloc(ctx, pk, fe * NW * n, &pk->d_wv));
@@ -743,7 +818,7 @@ template <class C> struct Plonk {
         JF_TRY(dalloc(ctx, pk, fe * m, &pk->d_b));
         JF_TRY(dalloc(ctx, pk, fe * (m / 256 + 4096), &pk->d_tmp));
         const int ne = pk->cache_coset ? NW + 2 : NSEL + 2 * NW + 2;
-        JF_TRY(dalloc(ctx, pk, fe * (size_t)ne * m, &pk->d_e));
+        JF_TRY(dalloc(ctx, pk, fe * (size_t)ne * mq, &pk->d_e));
         JF_TRY(dalloc(ctx, pk, fe * m, &pk->d_q));
         JF_TRY(dalloc(ctx, pk, fe * NW * np, &pk->d_split));
         JF_TRY(dalloc(ctx, pk, fe * np, &pk->d_bp));
@@ -753,7 +828,7 @@ template <class C> struct Plonk {
         JF_TRY(dalloc(ctx, pk, fe * (3 * np + np / 256 + 4096), &pk->d_side));
         JF_TRY(dalloc(ctx, pk, fe * 64, &pk->d_small));
         JF_TRY(dalloc(ctx, pk, PT * 32, &pk->d_res));
-        if (pk->cache_coset) JF_TRY(dalloc(ctx, pk, fe * (size_t)(NSEL + NW) * m, &pk->d_cached));
+        if (pk->cache_coset) JF_TRY(dalloc(ctx, pk, fe * (size_t)(NSEL + NW) * mq, &pk->d_cached));
         JF_CUDA(ctx, cudaMemcpyAsync(pk->d_sel, selector_evals, fe * NSEL * n, cudaMemcpyHostToDevice, st));
         JF_CUDA(ctx, cudaMemcpyAsync(pk->d_sig, sigma_evals, fe * NW * n, cudaMemcpyHostToDevice, st));
         JF_CUDA(ctx, cudaMemcpyAsync(pk->d_sig_evals, sigma_evals, fe * NW * n, cudaMemcpyHostToDevice, st));
@@ -766,12 +841,12 @@ template <class C> struct Plonk {
         {
             E nf = E::from_u32((uint32_t)n);
             E *d = (E *)pk->d_q, *pp = (E *)pk->d_a, *sp = (E *)pk->d_b, *small = (E *)pk->d_small;
-            JF_LAUNCH(ctx, "xm1", xm1_kernel<Fr><<<(unsigned)((m + 255) / 256), 256, 0, st>>>((const E *)pk->d_xlo, (const E *)pk->d_xhi,
-                                                                                       pk->lo_bits, nf, d, m));
-            JF_TRY((fscan<Fr, OpMul, false>(ctx, d, pp, m, (E *)pk->d_tmp)));
-            JF_TRY((fscan<Fr, OpMul, true>(ctx, d, sp, m, (E *)pk->d_tmp)));
+            JF_LAUNCH(ctx, "xm1", xm1_kernel<Fr><<<(unsigned)((mq + 255) / 256), 256, 0, st>>>(
+                (const E *)pk->d_xlo, (const E *)pk->d_xhi, pk->lo_bits, nf, d, mq, pk->sub, (uint32_t)pk->log_n));
+            JF_TRY((fscan<Fr, OpMul, false>(ctx, d, pp, mq, (E *)pk->d_tmp)));
+            JF_TRY((fscan<Fr, OpMul, true>(ctx, d, sp, mq, (E *)pk->d_tmp)));
             JF_LAUNCH(ctx, "inv_one", inv_one_kernel<Fr><<<1, 32, 0, st>>>(sp, small));
-            JF_LAUNCH(ctx, "inv_combine", inv_combine_kernel<Fr><<<(unsigned)((m + 255) / 256), 256, 0, st>>>(pp, sp, small, (E *)pk->d_inv_nx1, m));
+            JF_LAUNCH(ctx, "inv_combine", inv_combine_kernel<Fr><<<(unsigned)((mq + 255) / 256), 256, 0, st>>>(pp, sp, small, (E *)pk->d_inv_nx1, mq));
         }
         // selector / sigma polynomials (ifft) and the 18 verifying-key commitments
         JF_TRY(intt_n(ctx, pk, pk->d_sel, NSEL, n));
@@ -787,7 +862,7 @@ template <class C> struct Plonk {
         JF_TRY(fetch_commits(ctx, pk, 0, NSEL + NW, pk->vk_xy.data(), pk->vk_inf.data()));
         if (pk->cache_coset) {
             JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sel, n, n, NSEL, (E *)pk->d_cached, pk->zero_sel));
-            JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sig, n, n, NW, (E *)pk->d_cached + (size_t)NSEL * m));
+            JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sig, n, n, NW, (E *)pk->d_cached + (size_t)NSEL * mq));
         }
         // transcript prefix (transcript/mod.rs:45-88): sizes, k, selector and sigma commitments
         JF_CUDA(ctx, cudaStreamSynchronize(st));
@@ -799,6 +874,23 @@ template <class C> struct Plonk {
     static int coset_fft_rows(jf_ctx *ctx, const jf_plonk_pk *pk, const E *src, size_t stride, size_t len, int rows, E *dst,
                               uint32_t skip = 0) {
         const size_t m = pk->m, in_len = pk->n + 3;
+        if (pk->sub) {
+            // sub-coset form: row r of the result holds the polynomial on the cosets (g w_m^s) <w_n>, s < sub, n points each;
+            // the transform reads the coefficients where they are (reduced mod X^n - c_s on the way in)
+            int r = 0;
+            while (r < rows) {
+                if ((skip >> r) & 1u) {
+                    r++;
+                    continue;
+                }
+                int b = 1;
+                while (b < 5 && r + b < rows && !((skip >> (r + b)) & 1u)) b++;
+                JF_TRY(ntt_run_cosets(ctx, C::FR_ID, src + (size_t)r * stride, stride, len, dst + (size_t)r * pk->mq, pk->log_n, 0,
+                                      pk->sub_off, pk->sub, b));
+                r += b;
+            }
+            return JF_OK;
+        }
         dim3 grid((unsigned)((in_len + 255) / 256), rows);
         JF_LAUNCH(ctx, "copy_rows", copy_rows_kernel<Fr><<<grid, 256, 0, ctx->stream>>>(src, stride, dst, m, len, in_len));
         int r = 0;
@@ -850,7 +942,7 @@ template <class C> struct Plonk {
     // ------------------------------------------------------------------------------------------
     static int prove(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *witness, const uint64_t *blinders, int kind,
                      const uint8_t *extra, size_t extra_len, jf_plonk_proof *out) {
-        const size_t n = pk->n, m = pk->m, np = pk->np;
+        const size_t n = pk->n, m = pk->mq, np = pk->np;  // m: evaluation points per polynomial in round 3
         const size_t fe = sizeof(E);
         cudaStream_t st = ctx->stream;
         E *W = (E *)pk->d_w, *PI = W + (size_t)NW * np, *Z = (E *)pk->d_z, *WV = (E *)pk->d_wv;
@@ -958,13 +1050,26 @@ template <class C> struct Plonk {
             q.m = (uint32_t)m;
             q.ratio = 8;
             q.zero_sel = pk->zero_sel;
+            q.sub = (uint32_t)pk->sub;
+            q.log_n = pk->log_n;
             JF_LAUNCH(ctx, "quotient", quotient_kernel<Fr><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(q));
-            JF_TRY(ntt_run(ctx, C::FR_ID, pk->d_q, pk->d_q, m, pk->log_m, 1, pk->gen_limbs, 1, m));
+            const E *T = (const E *)pk->d_q;  // quotient coefficients
+            if (pk->sub) {
+                JF_TRY(ntt_run_cosets(ctx, C::FR_ID, pk->d_q, n, n, pk->d_q, pk->log_n, 1, pk->sub_off, pk->sub, 1));
+                SolveArgs<Fr> sa;
+                sa.T = (const E *)pk->d_q;
+                sa.t = (E *)pk->d_a;  // free since round 2
+                sa.n = (uint32_t)n;
+                memcpy(sa.vinv, pk->vinv, sizeof sa.vinv);
+                JF_LAUNCH(ctx, "subcoset_solve", subcoset_solve_kernel<Fr><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sa));
+                T = (const E *)pk->d_a;
+            } else {
+                JF_TRY(ntt_run(ctx, C::FR_ID, pk->d_q, pk->d_q, m, pk->log_m, 1, pk->gen_limbs, 1, m));
+            }
             const size_t deg = NW * (n + 1) + 2;  // quotient_polynomial_degree (prover.rs:1126-1128)
-            JF_LAUNCH(ctx, "degree_check", degree_check_kernel<Fr><<<(unsigned)((m - deg + 255) / 256), 256, 0, st>>>(
-                (const E *)pk->d_q, deg, m, ctx->d_err + 1));
+            JF_LAUNCH(ctx, "degree_check", degree_check_kernel<Fr><<<(unsigned)((m - deg + 255) / 256), 256, 0, st>>>(T, deg, m, ctx->d_err + 1));
             dim3 grid((unsigned)((np + 255) / 256), NW);
-            JF_LAUNCH(ctx, "split", split_kernel<Fr><<<grid, 256, 0, st>>>((const E *)pk->d_q, n, deg + 1, bl + 13, (E *)pk->d_split, np));
+            JF_LAUNCH(ctx, "split", split_kernel<Fr><<<grid, 256, 0, st>>>(T, n, deg + 1, bl + 13, (E *)pk->d_split, np));
             CommitJob jobs[NW];
             for (int i = 0; i < NW; i++)
                 jobs[i] = {(E *)pk->d_split + (size_t)i * np, i < NW - 1 ? n + 3 : deg + 1 - (size_t)(NW - 1) * (n + 2), i};

@@ -120,7 +120,8 @@ class PlonkKzgSnark:
     @staticmethod
     def preprocess(ctx: Context, key: CommitKey, selector_evals: np.ndarray, sigma_evals: np.ndarray, k: np.ndarray,
                    wire_variables: np.ndarray, num_vars: int, pub_input_gate_ids: Sequence[int] = (),
-                   cache_coset_evals: bool = False, skip_zero_selectors: bool = False) -> ProvingKey:
+                   cache_coset_evals: bool = False, skip_zero_selectors: bool = False,
+                   full_quotient_coset: bool = False) -> ProvingKey:
         """selector_evals (13, n, 4), sigma_evals (5, n, 4) = the extended permutation, k (5, 4):
         Montgomery limbs; wire_variables (5, n) uint32."""
         sel = np.ascontiguousarray(selector_evals, dtype=np.uint64)
@@ -137,7 +138,7 @@ class PlonkKzgSnark:
         ctx._check(ctx._lib.jf_plonk_preprocess(
             ctx._h, key._h, n.bit_length() - 1, sel.ctypes.data_as(_ffi.c_u64p), sig.ctypes.data_as(_ffi.c_u64p),
             kk.ctypes.data_as(_ffi.c_u64p), wv.ctypes.data_as(_ffi.c_u32p), num_vars,
-            gids.ctypes.data_as(_ffi.c_u32p) if len(gids) else None, len(gids), int(cache_coset_evals) | (2 if skip_zero_selectors else 0), ctypes.byref(h)))
+            gids.ctypes.data_as(_ffi.c_u32p) if len(gids) else None, len(gids), int(cache_coset_evals) | (2 if skip_zero_selectors else 0) | (4 if full_quotient_coset else 0), ctypes.byref(h)))
         return ProvingKey(ctx, key, h, n, num_vars, len(gids), kk)
 
     @staticmethod

@@ -66,6 +66,8 @@ extern "C" {
                   coset_offset: *const u64, batch: usize, batch_stride: usize) -> c_int;
     pub fn jf_ntt_device(ctx: *mut jf_ctx, field: c_int, d_data: *mut c_void, in_len: usize, log_n: c_uint, inverse: c_int,
                          coset_offset: *const u64, batch: usize, batch_stride: usize) -> c_int;
+    pub fn jf_ntt_cosets(ctx: *mut jf_ctx, field: c_int, polys_in: *const u64, in_len: usize, in_stride: usize, polys: usize,
+                         log_n: c_uint, inverse: c_int, offsets: *const u64, rows: c_int, out: *mut u64) -> c_int;
 
     pub fn jf_plonk_preprocess(ctx: *mut jf_ctx, srs: *const jf_srs, log_n: c_uint, selector_evals: *const u64,
                                sigma_evals: *const u64, k: *const u64, wire_variables: *const u32, num_vars: usize,

@@ -124,3 +124,75 @@ def test_full_size_output_equals_the_oracle(ctx, co, py, fname, log_n, inverse):
     off = co.ints_to_limbs([f.to_mont(f.generator)], 4)[0]
     got = ctx.ntt(fname, x.copy(), log_n, inverse, off)
     assert np.array_equal(got, co.ntt(fname, x, log_n, inverse, off))
+
+
+def _sub_offsets(py, co, fname, log_n, rows):
+    """g * w_8n^r, r < rows: the sub-cosets of the prover's quotient coset g<w_8n> (prover.rs:545)."""
+    f = py.FIELDS[fname]
+    w8n = py.Radix2Domain(f, 8 << log_n).group_gen
+    offs = [f.generator * pow(w8n, r, f.p) % f.p for r in range(rows)]
+    return offs, co.ints_to_limbs([f.to_mont(o) for o in offs], 4)
+
+
+@pytest.mark.parametrize("fname", FIELDS)
+@pytest.mark.parametrize("log_n,in_len", [(3, 8), (3, 11), (5, 35), (9, 515), (10, 1024), (12, 4099), (14, 3), (18, (1 << 18) + 3)])
+def test_ntt_cosets_vs_oracle(ctx, co, py, fname, log_n, in_len):
+    """jf_ntt_cosets forward: each row is `get_coset(g w_8n^r).fft` of the polynomial reduced mod X^n - (g w_8n^r)^n."""
+    f = py.FIELDS[fname]
+    n = 1 << log_n
+    rows, polys = 6, 3
+    offs, off_limbs = _sub_offsets(py, co, fname, log_n, rows)
+    x = co.random_field_elems(fname, polys * in_len, 900 + log_n, True).reshape(polys, in_len, 4)
+    got = ctx.ntt_cosets(fname, x, log_n, off_limbs)
+    assert got.shape == (polys, rows, n, 4)
+    for p in range(polys):
+        for r in range(rows):
+            folded = np.zeros((n, 4), dtype=np.uint64)
+            folded[:min(n, in_len)] = x[p, :n]
+            if in_len > n:
+                c = co.ints_to_limbs([f.to_mont(pow(offs[r], n, f.p))], 4)
+                hi = x[p, n:]
+                cc = np.repeat(c, hi.shape[0], axis=0)
+                folded[:in_len - n] = co.field_op(fname, "add", folded[:in_len - n], co.field_op(fname, "mul", hi, cc))
+            want = co.ntt(fname, folded, log_n, False, off_limbs[r])
+            assert np.array_equal(got[p, r], want), (fname, log_n, p, r)
+
+
+@pytest.mark.parametrize("fname", FIELDS)
+@pytest.mark.parametrize("log_n", [3, 4, 8, 9, 10, 13, 18])
+def test_intt_cosets_vs_oracle(ctx, co, py, fname, log_n):
+    n = 1 << log_n
+    rows, polys = 6, 2
+    _, off_limbs = _sub_offsets(py, co, fname, log_n, rows)
+    x = co.random_field_elems(fname, polys * rows * n, 77 + log_n, True).reshape(polys, rows, n, 4)
+    got = ctx.intt_cosets(fname, x.copy(), log_n, off_limbs)
+    for p in range(polys):
+        for r in range(rows):
+            assert np.array_equal(got[p, r], co.ntt(fname, x[p, r], log_n, True, off_limbs[r])), (fname, log_n, p, r)
+
+
+@pytest.mark.parametrize("fname,log_n", [("bn254_fr", 12), ("bls12_381_fr", 10), ("bn254_fr", 19)])
+def test_ntt_cosets_tile_the_8n_coset(ctx, co, py, fname, log_n):
+    """The reference's own call: `quot_domain.get_coset(GENERATOR).fft` over 8n points (prover.rs:552-567).
+    Row r of the sub-coset form is its outputs r, r + 8, r + 16, ..."""
+    n = 1 << log_n
+    in_len = n + 3
+    x = co.random_field_elems(fname, in_len, 5151, True)
+    _, off_limbs = _sub_offsets(py, co, fname, log_n, 8)
+    rows = ctx.ntt_cosets(fname, x[None], log_n, off_limbs)[0]
+    big = np.zeros((8 * n, 4), dtype=np.uint64)
+    big[:in_len] = x
+    full = ctx.ntt(fname, big, log_n + 3, False, _offset(py, co, fname), in_len=in_len)
+    for r in range(8):
+        assert np.array_equal(rows[r], full[r::8]), r
+
+
+def test_ntt_cosets_bad_args(ctx):
+    import mpc_jellyfish_b200 as jf
+    one = np.zeros((1, 4), dtype=np.uint64)
+    with pytest.raises(jf.InvalidParameters):
+        ctx.ntt_cosets("bn254_fr", np.zeros((1, 17, 4), dtype=np.uint64), 3, one)   # in_len > 2n
+    with pytest.raises(jf.InvalidParameters):
+        ctx.ntt_cosets("bn254_fr", np.zeros((1, 4, 4), dtype=np.uint64), 2, one)    # domain below 8
+    with pytest.raises(jf.DomainCreationError):
+        ctx.ntt_cosets("bn254_fr", np.zeros((1, 4, 4), dtype=np.uint64), 29, one)

@@ -123,14 +123,18 @@ def test_cached_coset_evaluations_and_zero_selector_skip_give_the_same_proof(ctx
     key = ctx.generate_srs_for_testing("bn254", BETA % fr.p, cs.n + 3)
     _, bl = _blinders(co, fr, 5)
     outs = []
-    for cache, skip in ((False, False), (True, False), (False, True), (True, True)):
+    for cache, skip, full in ((False, False, False), (True, False, False), (False, True, False), (True, True, False),
+                              (False, False, True), (True, True, True)):
+        # full: all 8n points of the quotient coset in one transform per polynomial, as the reference does
+        # (prover.rs:552-567), instead of six sub-cosets of n points
         pk = jf.PlonkKzgSnark.preprocess(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"],
-                                         arr["pub_gate_ids"], cache_coset_evals=cache, skip_zero_selectors=skip)
+                                         arr["pub_gate_ids"], cache_coset_evals=cache, skip_zero_selectors=skip,
+                                         full_quotient_coset=full)
         outs.append(jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, "standard").serialize_compressed())
         # the key is reusable: a second proof with other masks differs but has the same evaluations' count
         outs.append(jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, "standard").serialize_compressed())
         pk.free()
-    assert len(set(outs)) == 1 and len(outs) == 8
+    assert len(set(outs)) == 1 and len(outs) == 12
     key.free()
 
 
