@@ -341,10 +341,10 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
         "kernels_ms_per_proof": base["kernels_ms"], "setup_s": round(t_setup, 2), "preprocess_s": base["preprocess_s"],
         "with_full_8n_quotient_coset": alt((False, False, True), "round 3 in the reference's literal form: one 8n-point coset NTT per "
                                            "polynomial (prover.rs:552-567) instead of six sub-cosets of n points; same proof bytes"),
-        "with_zero_selector_skip": alt((False, True, False), ""selector columns that are identically zero (9 of 13 in this circuit: "
+        "with_zero_selector_skip": alt((False, True, False), "selector columns that are identically zero (9 of 13 in this circuit: "
                                        "q_lc2-3, q_mul, q_hash, q_ecc) are recognised at preprocess; their coset NTTs and "
                                        "quotient terms are skipped; same proof bytes (tests/test_gpu_plonk.py)"),
-        "with_cached_selector_sigma_coset_evals": alt((True, True, False), ""additionally the selector / sigma coset evaluations stay "
+        "with_cached_selector_sigma_coset_evals": alt((True, True, False), "additionally the selector / sigma coset evaluations stay "
                                                       "resident (+3.4 GiB): only 7 polynomials are transformed per proof; same proof bytes"),
         "prove_2^16_gates_ms": prove16_ms,
         "cpu_baseline": cpu,
