@@ -129,7 +129,8 @@ template <int K> __device__ __forceinline__ uint32_t bitrev_k(uint32_t x) { retu
 // One Stockham pass of radix 2^K.  blockDim = 256 = (R/8) * B.
 // FIRST / LAST are compile-time so that every instantiation carries only the twiddle / scaling code it uses
 // (the fully unrolled kernel otherwise overflows the instruction cache: 11 % no-instruction stalls in ncu).
-template <class F, int K, bool FIRST, bool LAST> __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(PassArgs a) {
+// MULTI: a batch of several cosets per polynomial (ntt_run_cosets); the plain transforms compile without that code.
+template <class F, int K, bool FIRST, bool LAST, bool MULTI> __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(PassArgs a) {
     using E = Fp<F>;
     constexpr int R = 1 << K;
     constexpr int LOGB = NTT_TILE_LOG - K;
@@ -148,15 +149,18 @@ template <class F, int K, bool FIRST, bool LAST> __global__ void __launch_bounds
     const uint64_t bid = blockIdx.x % a.batch;
     const uint64_t j = (uint64_t)(blockIdx.x / a.batch) * B + b;
     const bool valid = j < cols;
-    const E *src = reinterpret_cast<const E *>(a.src) + (FIRST ? (bid / a.src_group) * a.src_stride : bid * a.stride);
+    const E *src = reinterpret_cast<const E *>(a.src) + bid * a.stride;
     E *dst = reinterpret_cast<E *>(a.dst) + bid * a.stride;
     const E *tw = reinterpret_cast<const E *>(a.tw);
-    // this entry's offset table (only the first / last pass of a coset transform touches it)
+    // several cosets of one polynomial (only the first / last pass of such a transform takes this branch):
+    // this entry's offset table and, on the first pass, the source vector its group shares
     const E *off_full = reinterpret_cast<const E *>(a.off_full);
     uint32_t orow = 0;
-    if ((FIRST || LAST) && a.off_rows > 1) {
-        orow = (uint32_t)(bid % a.off_rows);
+    if (MULTI) {
+        const uint32_t bid32 = (uint32_t)bid;
+        orow = bid32 % a.off_rows;
         off_full += (size_t)orow << a.log_n;
+        if (FIRST) src = reinterpret_cast<const E *>(a.src) + (size_t)(bid32 / a.src_group) * a.src_stride;
     }
 
     E v[8];
@@ -171,7 +175,7 @@ template <class F, int K, bool FIRST, bool LAST> __global__ void __launch_bounds
             if (valid && (!FIRST || idx < a.in_len)) {
                 v[e] = ld_el(src + idx);
                 if (FIRST) {
-                    if (a.fold_c && idx + (1ull << a.log_n) < a.in_len)
+                    if (MULTI && a.fold_c && idx + (1ull << a.log_n) < a.in_len)
                         v[e] = E::add(v[e], E::mul(ld_el(src + idx + (1ull << a.log_n)), ldg_el((const E *)a.fold_c + orow)));
                     if (a.coset_in)
                         v[e] = E::mul(v[e], a.off_full ? ldg_el(off_full + idx)
@@ -391,27 +395,32 @@ template <class F> static int build_plan(jf_ctx *ctx, NttPlan *pl, const uint64_
     return JF_OK;
 }
 
-template <class F, int K, bool FIRST, bool LAST> static int launch_pass_fl(jf_ctx *ctx, const PassArgs &a) {
+template <class F, int K, bool FIRST, bool LAST, bool MULTI> static int launch_pass_fl(jf_ctx *ctx, const PassArgs &a) {
     constexpr int R = 1 << K;
     constexpr int B = 1 << (NTT_TILE_LOG - K);
     constexpr size_t smem = (size_t)2 * (R + R / 8) * B * sizeof(uint4);
     static bool configured = false;
     if (!configured) {
-        JF_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel<F, K, FIRST, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        JF_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel<F, K, FIRST, LAST, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     const uint64_t cols = (uint64_t)1 << (a.log_n - K);
     const uint64_t blocks = ((cols + B - 1) / B) * a.batch;
     if (blocks > 0x7fffffffull) return fail(ctx, JF_ERR_INVALID_ARG, "ntt: batch too large");
-    JF_LAUNCH(ctx, "ntt_pass", ntt_pass_kernel<F, K, FIRST, LAST><<<(unsigned)blocks, 256, smem, ctx->stream>>>(a));
+    JF_LAUNCH(ctx, "ntt_pass", ntt_pass_kernel<F, K, FIRST, LAST, MULTI><<<(unsigned)blocks, 256, smem, ctx->stream>>>(a));
     return JF_OK;
 }
 
 template <class F, int K> static int launch_pass(jf_ctx *ctx, const PassArgs &a) {
-    if (a.first && a.last) return launch_pass_fl<F, K, true, true>(ctx, a);
-    if (a.first) return launch_pass_fl<F, K, true, false>(ctx, a);
-    if (a.last) return launch_pass_fl<F, K, false, true>(ctx, a);
-    return launch_pass_fl<F, K, false, false>(ctx, a);
+    if (a.off_rows != 0) {  // only the first and last pass differ for a multi-coset batch
+        if (a.first && a.last) return launch_pass_fl<F, K, true, true, true>(ctx, a);
+        if (a.first) return launch_pass_fl<F, K, true, false, true>(ctx, a);
+        if (a.last) return launch_pass_fl<F, K, false, true, true>(ctx, a);
+    }
+    if (a.first && a.last) return launch_pass_fl<F, K, true, true, false>(ctx, a);
+    if (a.first) return launch_pass_fl<F, K, true, false, false>(ctx, a);
+    if (a.last) return launch_pass_fl<F, K, false, true, false>(ctx, a);
+    return launch_pass_fl<F, K, false, false, false>(ctx, a);
 }
 
 template <class F> static int launch_pass_k(jf_ctx *ctx, int k, const PassArgs &a) {
@@ -543,7 +552,7 @@ static int ntt_run_t(jf_ctx *ctx, int field, void *d_data, void *d_out, size_t i
         a.n_inv = pl->n_inv;
         a.src_stride = batch_stride;
         a.src_group = 1;
-        a.off_rows = 1;
+        a.off_rows = 0;  // not a multi-coset batch
         a.fold_c = nullptr;
         JF_TRY(launch_pass_k<F>(ctx, pl->passes[i].k, a));
     }
