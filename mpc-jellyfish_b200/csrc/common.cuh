@@ -158,6 +158,16 @@ int ntt_run_cosets(jf_ctx *ctx, int field, const void *d_src, size_t src_stride,
 void ntt_free_plans(jf_ctx *ctx);
 int msm_run(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n, int mont,
             void *d_out_xyzz);
+// A group of MSMs over the same commit key on ctx->stream: the bulk phases run one after the other, the bucket
+// reduction (latency-bound: ~20 dependent levels whatever the number of bucket sets) once for all of them.
+struct MsmJob {
+    size_t base_offset;
+    const void *d_scalars;
+    size_t n;
+    int mont;
+    void *d_out_xyzz;
+};
+int msm_run_many(jf_ctx *ctx, const jf_srs *srs, const MsmJob *jobs, int count);
 // Bulk phases (digits, sort, accumulate, bucket sums) on ctx->stream, then -- after `ev_mid` -- the bucket reduction
 // on `tail_stream`.  The caller orders the reuse of the per-lane workspace across calls.
 int msm_run_split(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n, int mont,

@@ -493,15 +493,18 @@ template <class Fq> __global__ void set_inf_kernel(XYZZ<Fq> *out) {
 
 // ---- driver ------------------------------------------------------------------------------
 template <class C>
+// ji / jc: this call is MSM `ji` of a group of `jc` over the same commit key (msm_run_many).  Every member runs its
+// bulk phases into its own bucket array; the bucket reduction, whose cost is the latency of its ~20 dependent levels
+// whatever the number of bucket sets, runs once for the whole group after the last member (d_outs: jc results).
 static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n_in, int mont,
-                     void *d_out, cudaStream_t tail_stream, cudaEvent_t ev_mid) {
+                     void *d_out, cudaStream_t tail_stream, cudaEvent_t ev_mid, int ji = 0, int jc = 1, void *const *d_outs = nullptr) {
     using Fq = typename C::Fq;
     using Fr = typename C::Fr;
     using P = XYZZ<Fq>;
     cudaStream_t st = ctx->stream;
     if (base_offset > srs->n) return fail(ctx, JF_ERR_INVALID_ARG, "msm: base_offset beyond the commit key");
     size_t n = n_in < srs->n - base_offset ? n_in : srs->n - base_offset;  // arkworks: min(len(bases), len(scalars))
-    if (n == 0) {
+    if (n == 0 && jc == 1) {
         JF_LAUNCH(ctx, "set_inf", set_inf_kernel<Fq><<<1, 32, 0, tail_stream ? tail_stream : st>>>((P *)d_out));
         return JF_OK;
     }
@@ -544,19 +547,28 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     JF_TRY(scratch(ctx, "msm_partials", sizeof(P) * max_partials, &p));
     partials = (P *)p;
     const uint32_t cap_p = g.NB + 64;
-    JF_TRY(scratch(ctx, "msm_reduce", sizeof(P) * ((size_t)total * 2 + (size_t)g.S * cap_p * 2 + g.S + 8), &p));
+    const uint32_t sets = (uint32_t)jc * g.S;  // bucket sets the reduction handles at once
+    JF_TRY(scratch(ctx, "msm_reduce", sizeof(P) * ((size_t)jc * total * 2 + (size_t)sets * cap_p * 2 + sets + 8), &p));
     XA = (P *)p;  // X ping-pong (stride NB per set), pool ping-pong (stride cap_p per set), per-set sums
-    XB = XA + total;
-    PA = XB + total;
-    PB = PA + (size_t)g.S * cap_p;
-    Rs = PB + (size_t)g.S * cap_p;
+    XB = XA + (size_t)jc * total;
+    PA = XB + (size_t)jc * total;
+    PB = PA + (size_t)sets * cap_p;
+    Rs = PB + (size_t)sets * cap_p;
+    P *const XA0 = XA;
+    XA += (size_t)ji * total;  // this member's buckets
     err = ctx->d_err;
     uint32_t *heavy;
     JF_TRY(scratch(ctx, "msm_heavy", sizeof(uint32_t) * ((size_t)total + 8), &p));
     heavy = (uint32_t *)p;  // [0] = count, [1..] = bucket ids
 
+    if (n == 0) {  // empty member of a group: all buckets are the identity (all-zero words)
+        JF_CUDA(ctx, cudaMemsetAsync(XA, 0, sizeof(P) * total, st));
+        if (ji + 1 < jc) return JF_OK;
+    }
+    const bool bulk = n != 0;
     const uint32_t *sc = (const uint32_t *)d_scalars;
-    JF_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (total + 1), st));
+    if (bulk) JF_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (total + 1), st));
+    if (bulk) {
     const unsigned nblk = (unsigned)((n + 255) / 256);
     // Direct sort when every bucket is expected to stay far below its slot capacity (uniform digits, no narrow
     // top window): one pass over the scalars instead of two.  A bucket that overflows anyway (skewed scalars)
@@ -598,6 +610,8 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     JF_CUDA(ctx, cudaMemsetAsync(heavy, 0, sizeof(uint32_t), st));
     JF_LAUNCH(ctx, "bucket_sum", bucket_sum_kernel<Fq><<<(total + 127) / 128, 128, 0, st>>>(partials, off, total, acc_threads, XA, heavy, heavy + 1));
     JF_LAUNCH(ctx, "bucket_sum_heavy", bucket_sum_heavy_kernel<Fq><<<(unsigned)ctx->sm_count * 4, HEAVY_THREADS, 0, st>>>(partials, off, total, acc_threads, XA, heavy, heavy + 1));
+    }  // bulk
+    if (ji + 1 < jc) return JF_OK;  // the group's last member reduces every member's buckets
     if (tail_stream) {
         // split form: the bulk phases above ran on ctx->stream, the latency-bound bucket reduction continues on
         // `tail_stream` (a higher-priority stream) so that it overlaps the bulk phases of the caller's next MSM
@@ -607,12 +621,12 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     }
     {
         uint32_t nlev = g.NB, m = 0;
-        P *x = XA, *xo = XB, *pin = PA, *pout = PB;
+        P *x = XA0, *xo = XB, *pin = PA, *pout = PB;
         while (nlev > 0 || m > 1) {
             const uint32_t xs = nlev >= 2 ? nlev / 2 : nlev, mh = (m + 1) / 2;
             const uint32_t threads = xs + mh;
             const int bs = threads > 32u * 1024u ? 128 : 32;
-            dim3 grid((threads + bs - 1) / bs, g.S);
+            dim3 grid((threads + bs - 1) / bs, sets);
             {
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = grid;
@@ -631,12 +645,15 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
             std::swap(x, xo);
             std::swap(pin, pout);
         }
-        JF_LAUNCH(ctx, "gather_sets", gather_sets_kernel<Fq><<<(g.S + 31) / 32, 32, 0, st>>>(pin, cap_p, g.S, Rs));
+        JF_LAUNCH(ctx, "gather_sets", gather_sets_kernel<Fq><<<(sets + 31) / 32, 32, 0, st>>>(pin, cap_p, (int)sets, Rs));
     }
-    if (g.S > 1) {
-        JF_LAUNCH(ctx, "fold_sets", fold_sets_kernel<Fq><<<1, 32, 0, st>>>(Rs, g.S, g.c * g.T, (P *)d_out));
-    } else {
-        JF_CUDA(ctx, cudaMemcpyAsync(d_out, Rs, sizeof(P), cudaMemcpyDeviceToDevice, st));
+    for (int j = 0; j < jc; j++) {
+        void *out = jc == 1 ? d_out : d_outs[j];
+        if (g.S > 1) {
+            JF_LAUNCH(ctx, "fold_sets", fold_sets_kernel<Fq><<<1, 32, 0, st>>>(Rs + (size_t)j * g.S, g.S, g.c * g.T, (P *)out));
+        } else {
+            JF_CUDA(ctx, cudaMemcpyAsync(out, Rs + j, sizeof(P), cudaMemcpyDeviceToDevice, st));
+        }
     }
     return JF_OK;
 }
@@ -647,6 +664,24 @@ int msm_run_split(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void
     if (srs->curve == JF_BLS12_381)
         return msm_run_t<Bls12381G1>(ctx, srs, base_offset, d_scalars, n, mont, d_out_xyzz, tail_stream, ev_mid);
     return fail(ctx, JF_ERR_INVALID_ARG, "msm: unknown curve");
+}
+
+int msm_run_many(jf_ctx *ctx, const jf_srs *srs, const MsmJob *jobs, int count) {
+    if (count <= 0) return JF_OK;
+    if (count > 64) return fail(ctx, JF_ERR_INVALID_ARG, "msm: at most 64 MSMs per group");
+    void *outs[64];
+    for (int i = 0; i < count; i++) outs[i] = jobs[i].d_out_xyzz;
+    for (int i = 0; i < count; i++) {
+        int rc;
+        if (srs->curve == JF_BN254)
+            rc = msm_run_t<Bn254G1>(ctx, srs, jobs[i].base_offset, jobs[i].d_scalars, jobs[i].n, jobs[i].mont, outs[i], nullptr, nullptr, i, count, outs);
+        else if (srs->curve == JF_BLS12_381)
+            rc = msm_run_t<Bls12381G1>(ctx, srs, jobs[i].base_offset, jobs[i].d_scalars, jobs[i].n, jobs[i].mont, outs[i], nullptr, nullptr, i, count, outs);
+        else
+            return fail(ctx, JF_ERR_INVALID_ARG, "msm: unknown curve");
+        JF_TRY(rc);
+    }
+    return JF_OK;
 }
 
 int msm_run(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n, int mont,

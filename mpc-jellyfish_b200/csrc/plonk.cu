@@ -584,29 +584,14 @@ template <class C> struct Plonk {
     static int commit_dev(jf_ctx *ctx, const jf_plonk_pk *pk, const void *d_poly, size_t len, int slot) {
         return msm_run(ctx, pk->srs, 0, d_poly, len, 1, (char *)pk->d_res + PT * slot);
     }
-    // `count` commitments as a pipeline: the bulk phases of every MSM (digits, sort, bucket accumulation) run in
-    // order on the low-priority side stream, the latency-bound bucket reductions on the main (high-priority)
-    // stream, where they overlap the bulk phases of the next MSM; workspaces alternate between two lanes.
-    // The side stream must be idle-able here (no queued NTT work the caller still waits for).
+    // `count` commitments on the main stream: every MSM runs its bulk phases (digits, sort, bucket accumulation) into
+    // its own bucket array, then ONE bucket reduction handles all of them (its ~20 dependent levels cost the same
+    // latency for 1 or 18 bucket sets).
     struct CommitJob { const void *poly; size_t len; int slot; };
     static int commit_many(jf_ctx *ctx, jf_plonk_pk *pk, const CommitJob *jobs, int count) {
-        cudaStream_t main_stream = ctx->stream;
-        JF_CUDA(ctx, cudaEventRecord(pk->ev_main, main_stream));
-        JF_CUDA(ctx, cudaStreamWaitEvent(pk->side, pk->ev_main, 0));
-        int rc = JF_OK;
-        for (int i = 0; i < count && rc == JF_OK; i++) {
-            const int lane = i & 1;
-            if (i >= 2) JF_CUDA(ctx, cudaStreamWaitEvent(pk->side, pk->ev_tail[lane], 0));  // lane's last reduction is done
-            ctx->stream = pk->side;
-            ctx->lane = lane;
-            rc = msm_run_split(ctx, pk->srs, 0, jobs[i].poly, jobs[i].len, 1, (char *)pk->d_res + PT * jobs[i].slot, main_stream,
-                               pk->ev_mid[lane]);
-            ctx->stream = main_stream;
-            ctx->lane = 0;
-            if (rc == JF_OK) JF_CUDA(ctx, cudaEventRecord(pk->ev_tail[lane], main_stream));
-        }
-        JF_TRY(rc);
-        return join_side(ctx, pk);
+        MsmJob mj[NSEL + NW];
+        for (int i = 0; i < count; i++) mj[i] = MsmJob{0, jobs[i].poly, jobs[i].len, 1, (char *)pk->d_res + PT * jobs[i].slot};
+        return msm_run_many(ctx, pk->srs, mj, count);
     }
     // bring `count` XYZZ results back and normalise (into_affine)
     static int fetch_commits(jf_ctx *ctx, const jf_plonk_pk *pk, int slot, int count, uint64_t *xy, int *inf) {
@@ -994,7 +979,11 @@ template <class C> struct Plonk {
             if (pk->num_inputs == 0 && pk->skip_zero) return JF_OK;  // PI(X) = 0: nothing to transform
             return coset_fft_rows(ctx, pk, PI, np, n, 1, pi_c);
         }));
-        for (int j = 0; j < NW; j++) JF_TRY(commit_dev(ctx, pk, W + (size_t)j * np, n + 2, j));
+        {
+            CommitJob jobs[NW];
+            for (int j = 0; j < NW; j++) jobs[j] = {W + (size_t)j * np, n + 2, j};
+            JF_TRY(commit_many(ctx, pk, jobs, NW));
+        }
         JF_TRY(fetch_commits(ctx, pk, 0, NW, out->wires_poly_comms, out->wires_inf));
         for (int j = 0; j < NW; j++) tr_g1(tr, "witness_poly_comms", out->wires_poly_comms + 2 * L * j, out->wires_inf[j]);
         (void)challenge(tr, "tau");  // squeezed even without Plookup (snark.rs:293)
