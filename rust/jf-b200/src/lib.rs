@@ -106,6 +106,18 @@ pub fn ntt(gpu: &Gpu, data: &mut [Fr], in_len: usize, log_n: u32, inverse: bool,
     })
 }
 
+/// `polys` coefficient vectors (`in_len` <= 2n each, contiguous) evaluated on the cosets `offsets[r] * <w_n>`:
+/// `out[(p * rows + r) * n + i] = poly_p(offsets[r] * w_n^i)`.  With `offsets[r] = g * w_8n^r` the rows are the residue
+/// classes mod 8 of the 8n-point `coset.fft` of prover.rs:552-567; six rows determine the quotient polynomial.
+pub fn ntt_cosets(gpu: &Gpu, polys: &[Fr], in_len: usize, log_n: u32, offsets: &[Fr], out: &mut [Fr]) -> Result<(), GpuError> {
+    let (n, count) = (1usize << log_n, polys.len() / in_len.max(1));
+    assert!(polys.len() == count * in_len && out.len() >= count * offsets.len() * n);
+    gpu.check(unsafe {
+        sys::jf_ntt_cosets(gpu.ctx, sys::JF_BN254_FR, polys.as_ptr() as *const u64, in_len, in_len, count, log_n, 0,
+                           offsets.as_ptr() as *const u64, offsets.len() as c_int, out.as_mut_ptr() as *mut u64)
+    })
+}
+
 /// `ProvingKey` resident on the GPU; `prove` == `PlonkKzgSnark::prove` for one TurboPlonk instance.
 pub struct GpuProvingKey<'g> { gpu: &'g Gpu, pk: *mut sys::jf_plonk_pk }
 impl<'g> GpuProvingKey<'g> {

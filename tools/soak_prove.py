@@ -11,9 +11,10 @@ arr = B.bench_circuit_arrays(ctx, 20)
 key = ctx.generate_srs_for_testing("bn254", 0x1234567 + (7 << 200), arr["n"] + 3)
 bl = np.random.default_rng(1).integers(0, 1 << 60, size=(17, 4), dtype=np.uint64)
 seen = set()
-for cache, skip in ((False, False), (False, True), (True, True)):
+for cache, skip, full in ((False, False, False), (False, True, False), (True, True, False), (False, False, True)):
+    # full: round 3 on the reference's literal 8n coset instead of six sub-cosets -- same quotient, same bytes
     pk = jf.PlonkKzgSnark.preprocess(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"], [],
-                                     cache_coset_evals=cache, skip_zero_selectors=skip)
+                                     cache_coset_evals=cache, skip_zero_selectors=skip, full_quotient_coset=full)
     for i in range(40):
         seen.add(jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, "standard" if i % 2 else "solidity").serialize_compressed())
     pk.free()
