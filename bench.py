@@ -373,13 +373,21 @@ def mpc_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream):
     polys = [jf_mod().AuthenticatedDensePoly(rng.integers(0, 1 << 60, size=(n + 2, 4), dtype=np.uint64),
                                              rng.integers(0, 1 << 60, size=(n + 2, 4), dtype=np.uint64)) for _ in range(5)]
     steps = max(1, min(args.steps, 5))
-    for _ in range(2):
-        jf_mod().MultiproverKZG.batch_commit(pp, polys)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        jf_mod().MultiproverKZG.batch_commit(pp, polys)
-    commit_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+
+    def timed_commit(ps):
+        for _ in range(2):
+            jf_mod().MultiproverKZG.batch_commit(pp, ps)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            jf_mod().MultiproverKZG.batch_commit(pp, ps)
+        return max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+
+    pageable_ms = timed_commit(polys)
+    # the same vectors in page-locked memory (what jf_host_alloc hands the shim crate for coefficient vectors)
+    pin = lambda a: torch.from_numpy(a.view(np.int64)).pin_memory().numpy().view(np.uint64)  # noqa: E731
+    pinned_polys = [jf_mod().AuthenticatedDensePoly(pin(pl.share), pin(pl.mac)) for pl in polys]
+    commit_ms = timed_commit(pinned_polys)
     m = 8 * n
     d = torch.zeros((10, m, 4), dtype=torch.int64, device="cuda")
     for i, pl in enumerate(polys):
@@ -406,7 +414,8 @@ def mpc_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream):
         return None
     return {"workload": "one party, n = 2^18: batch_commit of 5 authenticated wire polynomials (10 MSMs, host scalars) and "
                         "their share-wise coset NTT to 8n (10 vectors, device resident)",
-            "batch_commit_ms": commit_ms, "msm_per_s": 10 * world / (commit_ms * 1e-3),
+            "batch_commit_ms": commit_ms, "batch_commit_pageable_host_ms": pageable_ms, "msm_per_s": 10 * world / (commit_ms * 1e-3),
+            "note": "batch_commit_ms: scalars in page-locked host memory; pageable: plain numpy arrays (the driver stages them)",
             "sharewise_coset_ntt_ms": ntt_ms, "ntt_melem_per_s": 10 * m * world / (ntt_ms * 1e-3) / 1e6,
             "parties": world}
 

@@ -217,76 +217,71 @@ static int msm_batch_locked(jf_ctx *ctx, const jf_srs *srs, const uint64_t *cons
         max_len = lens[i] > max_len ? lens[i] : max_len;
     }
     if (batch == 0) return JF_OK;
-    // two staging buffers so that the upload of vector i+1 overlaps the kernels of vector i
-    void *d_sc[2], *d_res, *h_res;
-    JF_TRY(scratch(ctx, "msm_scalars0", 32 * (max_len ? max_len : 1), &d_sc[0]));
-    JF_TRY(scratch(ctx, "msm_scalars1", 32 * (max_len ? max_len : 1), &d_sc[1]));
+    // A batch runs in groups of up to GROUP MSMs (msm_run_many): the scalars of vector i+1 cross PCIe on the copy stream
+    // while vector i goes through its bulk phases (digits, sort, bucket accumulation), and the latency-bound bucket
+    // reduction runs once per group over all its bucket sets.  One staging buffer per group member.
+    constexpr int GROUP = 8;
+    const int G = batch < (size_t)GROUP ? (int)batch : GROUP;
+    void *d_sc[GROUP], *d_res, *h_res;
+    for (int k = 0; k < G; k++) {
+        char name[32];
+        snprintf(name, sizeof name, "msm_scalars%d", k);
+        JF_TRY(scratch(ctx, name, 32 * (max_len ? max_len : 1), &d_sc[k]));
+    }
     JF_TRY(scratch(ctx, "msm_results", pt * batch, &d_res));
     JF_TRY(pinned(ctx, pt * batch, &h_res));
-    // A batch is pipelined over three streams: uploads on the copy stream (the scalars of vector i+1 cross PCIe
-    // while vector i is being summed), the bulk phases of every MSM (digits, sort, bucket accumulation) in order
-    // on the low-priority side stream, and the latency-bound bucket reductions on the caller's (high-priority)
-    // stream, where they overlap the bulk phases of the next MSM.  Workspaces alternate between two lanes.
     const bool piped = batch > 1;
     cudaStream_t main_stream = ctx->stream;
-    enum { EV_UP = 0, EV_A = 2, EV_B = 4, EV_MID = 6, EV_START = 8, EV_COUNT = 9 };
+    enum { EV_READY = 0, EV_DONE = GROUP, EV_START = 2 * GROUP, EV_COUNT = 2 * GROUP + 1 };
     if (piped) {
         if (!ctx->copy_in) {
             JF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
             JF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
-        }
-        if (!ctx->side) {
-            int prio_least = 0, prio_greatest = 0;
-            cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-            JF_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_least));
         }
         while (ctx->sync_events.size() < EV_COUNT) {
             cudaEvent_t e;
             JF_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             ctx->sync_events.push_back(e);
         }
+        // the copy stream starts after whatever already reads the staging buffers on the compute stream
         JF_CUDA(ctx, cudaEventRecord(ctx->sync_events[EV_START], main_stream));
         JF_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->sync_events[EV_START], 0));
-        JF_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->sync_events[EV_START], 0));
     }
     int rc = JF_OK;
-    for (size_t i = 0; i < batch && rc == JF_OK; i++) {
-        const size_t off = base_offsets ? base_offsets[i] : 0;
-        if (off > srs->n) {
-            rc = fail(ctx, JF_ERR_INVALID_ARG, "msm: base_offset beyond the commit key");
-            break;
-        }
-        size_t n = lens[i] < srs->n - off ? lens[i] : srs->n - off;
-        const int slot = (int)(i & 1);
-        void *d = d_sc[slot];
-        if (!piped) {
-            if (n) JF_CUDA(ctx, cudaMemcpyAsync(d, scalars[i], 32 * n, cudaMemcpyHostToDevice, main_stream));
-            rc = msm_run(ctx, srs, off, d, n, mont, (char *)d_res + pt * i);
-            break;
-        }
-        cudaEvent_t *ev = ctx->sync_events.data();
-        cudaError_t ce = cudaSuccess;
-        if (i >= 2) ce = cudaStreamWaitEvent(ctx->copy_in, ev[EV_A + slot], 0);  // MSM i-2 has read this scalar buffer
-        if (ce == cudaSuccess && n) ce = cudaMemcpyAsync(d, scalars[i], 32 * n, cudaMemcpyHostToDevice, ctx->copy_in);
-        if (ce == cudaSuccess) ce = cudaEventRecord(ev[EV_UP + slot], ctx->copy_in);
-        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->side, ev[EV_UP + slot], 0);
-        if (ce == cudaSuccess && i >= 2) ce = cudaStreamWaitEvent(ctx->side, ev[EV_B + slot], 0);  // its reduction is done
-        if (ce != cudaSuccess) {
-            rc = fail(ctx, JF_ERR_CUDA, std::string("msm_batch: ") + cudaGetErrorString(ce));
-            break;
-        }
-        ctx->stream = ctx->side;
-        ctx->lane = slot;
-        rc = msm_run_split(ctx, srs, off, d, n, mont, (char *)d_res + pt * i, main_stream, ev[EV_MID + slot]);
-        ctx->stream = main_stream;
-        ctx->lane = 0;
-        if (rc == JF_OK && (cudaEventRecord(ev[EV_A + slot], ctx->side) != cudaSuccess ||
-                            cudaEventRecord(ev[EV_B + slot], main_stream) != cudaSuccess))
-            rc = fail(ctx, JF_ERR_CUDA, "msm_batch: event record");
+    if (!piped) {
+        const size_t off = base_offsets ? base_offsets[0] : 0;
+        if (off > srs->n) return fail(ctx, JF_ERR_INVALID_ARG, "msm: base_offset beyond the commit key");
+        const size_t n = lens[0] < srs->n - off ? lens[0] : srs->n - off;
+        if (n) JF_CUDA(ctx, cudaMemcpyAsync(d_sc[0], scalars[0], 32 * n, cudaMemcpyHostToDevice, main_stream));
+        rc = msm_run(ctx, srs, off, d_sc[0], n, mont, d_res);
     }
-    if (piped) {  // results are complete on the main stream once the side stream's last bulk phase has been joined
-        cudaEventRecord(ctx->sync_events[EV_START], ctx->side);
-        cudaStreamWaitEvent(main_stream, ctx->sync_events[EV_START], 0);
+    for (size_t g0 = 0; piped && g0 < batch && rc == JF_OK; g0 += G) {
+        const int cnt = batch - g0 < (size_t)G ? (int)(batch - g0) : G;
+        MsmJob jobs[GROUP];
+        cudaEvent_t *ev = ctx->sync_events.data();
+        for (int k = 0; k < cnt && rc == JF_OK; k++) {
+            const size_t i = g0 + k, off = base_offsets ? base_offsets[i] : 0;
+            if (off > srs->n) {
+                rc = fail(ctx, JF_ERR_INVALID_ARG, "msm: base_offset beyond the commit key");
+                break;
+            }
+            const size_t n = lens[i] < srs->n - off ? lens[i] : srs->n - off;
+            jobs[k] = MsmJob{off, d_sc[k], n, mont, (char *)d_res + pt * i, ev[EV_READY + k], ev[EV_DONE + k]};
+        }
+        // member k's upload is issued right before its kernels are enqueued: the kernels of the members before it are
+        // then already running while the host stages a pageable source buffer
+        struct Up { jf_ctx *ctx; const MsmJob *jobs; const uint64_t *const *src; bool wait_done; } up{ctx, jobs, scalars + g0, g0 > 0};
+        auto prepare = [](void *user, int k) -> int {
+            Up *u = (Up *)user;
+            const MsmJob &j = u->jobs[k];
+            cudaError_t ce = cudaSuccess;
+            if (u->wait_done) ce = cudaStreamWaitEvent(u->ctx->copy_in, j.done, 0);  // the previous group's member k has read this buffer
+            if (ce == cudaSuccess && j.n) ce = cudaMemcpyAsync(const_cast<void *>(j.d_scalars), u->src[k], 32 * j.n, cudaMemcpyHostToDevice, u->ctx->copy_in);
+            if (ce == cudaSuccess) ce = cudaEventRecord(j.ready, u->ctx->copy_in);
+            if (ce != cudaSuccess) return fail(u->ctx, JF_ERR_CUDA, std::string("msm_batch: ") + cudaGetErrorString(ce));
+            return JF_OK;
+        };
+        if (rc == JF_OK) rc = msm_run_many(ctx, srs, jobs, cnt, prepare, &up);
     }
     JF_TRY(rc);
     JF_CUDA(ctx, cudaMemcpyAsync(h_res, d_res, pt * batch, cudaMemcpyDeviceToHost, ctx->stream));

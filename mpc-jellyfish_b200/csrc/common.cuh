@@ -166,8 +166,13 @@ struct MsmJob {
     size_t n;
     int mont;
     void *d_out_xyzz;
+    cudaEvent_t ready = nullptr;  // optional: the scalars are complete once this event has fired (upload on another stream)
+    cudaEvent_t done = nullptr;   // optional: recorded on ctx->stream once this member no longer reads its scalars
 };
-int msm_run_many(jf_ctx *ctx, const jf_srs *srs, const MsmJob *jobs, int count);
+// prepare(user, i), when given, is called right before member i is enqueued (e.g. to issue the upload its `ready`
+// event follows: a copy from pageable memory blocks the host, so it must not delay the kernels of members < i).
+int msm_run_many(jf_ctx *ctx, const jf_srs *srs, const MsmJob *jobs, int count, int (*prepare)(void *user, int i) = nullptr,
+                 void *user = nullptr);
 // Bulk phases (digits, sort, accumulate, bucket sums) on ctx->stream, then -- after `ev_mid` -- the bucket reduction
 // on `tail_stream`.  The caller orders the reuse of the per-lane workspace across calls.
 int msm_run_split(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n, int mont,

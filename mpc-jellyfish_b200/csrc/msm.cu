@@ -666,13 +666,15 @@ int msm_run_split(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void
     return fail(ctx, JF_ERR_INVALID_ARG, "msm: unknown curve");
 }
 
-int msm_run_many(jf_ctx *ctx, const jf_srs *srs, const MsmJob *jobs, int count) {
+int msm_run_many(jf_ctx *ctx, const jf_srs *srs, const MsmJob *jobs, int count, int (*prepare)(void *user, int i), void *user) {
     if (count <= 0) return JF_OK;
     if (count > 64) return fail(ctx, JF_ERR_INVALID_ARG, "msm: at most 64 MSMs per group");
     void *outs[64];
     for (int i = 0; i < count; i++) outs[i] = jobs[i].d_out_xyzz;
     for (int i = 0; i < count; i++) {
         int rc;
+        if (prepare) JF_TRY(prepare(user, i));
+        if (jobs[i].ready) JF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, jobs[i].ready, 0));
         if (srs->curve == JF_BN254)
             rc = msm_run_t<Bn254G1>(ctx, srs, jobs[i].base_offset, jobs[i].d_scalars, jobs[i].n, jobs[i].mont, outs[i], nullptr, nullptr, i, count, outs);
         else if (srs->curve == JF_BLS12_381)
@@ -680,6 +682,7 @@ int msm_run_many(jf_ctx *ctx, const jf_srs *srs, const MsmJob *jobs, int count) 
         else
             return fail(ctx, JF_ERR_INVALID_ARG, "msm: unknown curve");
         JF_TRY(rc);
+        if (jobs[i].done) JF_CUDA(ctx, cudaEventRecord(jobs[i].done, ctx->stream));
     }
     return JF_OK;
 }
