@@ -145,6 +145,26 @@ def test_msm_batch_matches_single(ctx, co):
     key.free()
 
 
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("precompute", [True, False])
+def test_msm_batch_spanning_several_groups(ctx, co, curve, precompute):
+    """jf_msm_batch runs in groups of 8 that share one bucket reduction (one bucket set per member and window set):
+    19 ragged vectors incl. empty ones at the group boundaries, all-equal scalars and a single-element vector."""
+    fr = "bn254_fr" if curve == "bn254" else "bls12_381_fr"
+    _, pts = _points(ctx, co, curve, 300, 9)
+    key = ctx.load_srs(curve, pts, window_bits=6, precompute=precompute)
+    lens = [0, 300, 1, 17, 299, 0, 64, 300, 0, 5, 300, 33, 0, 0, 128, 2, 300, 7, 0]
+    vecs = [co.random_field_elems(fr, m, 700 + i, False) for i, m in enumerate(lens)]
+    vecs[4][:] = vecs[4][0]  # every scalar equal: one bucket per window takes everything
+    offs = [0, 0, 299, 5, 1, 0, 100, 0, 7, 295, 0, 20, 300, 0, 172, 298, 0, 50, 0]
+    out, infs = ctx.msm_batch(key, vecs, offs)
+    width = out.shape[1]
+    for i, (v, o) in enumerate(zip(vecs, offs)):
+        wxy, winf = co.msm(curve, pts[o:], v) if len(v) else (np.zeros(width, np.uint64), True)
+        assert infs[i] == winf and np.array_equal(out[i], wxy), i
+    key.free()
+
+
 @pytest.mark.parametrize("curve,log_n", [("bn254", 16), ("bls12_381", 14)])
 def test_msm_medium_vs_oracle_pippenger(ctx, co, curve, log_n):
     fr = "bn254_fr" if curve == "bn254" else "bls12_381_fr"
