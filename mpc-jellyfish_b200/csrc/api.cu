@@ -109,7 +109,6 @@ void jf_ctx_destroy(jf_ctx *ctx) {
     }
     for (auto &e : ctx->event_pool) cudaEventDestroy(e);
     for (auto &e : ctx->sync_events) cudaEventDestroy(e);
-    if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

@@ -27,7 +27,6 @@ struct jf_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
-    cudaStream_t side = nullptr;                         // lazily created: second lane for independent MSMs of a batch
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // lazily created: host<->device copies beside the kernels
     std::vector<cudaEvent_t> sync_events;                // event pool for the copy pipeline
     int lane = 0;  // 1 while work is being issued on a secondary stream: scratch buffers are kept apart per lane
@@ -173,10 +172,6 @@ struct MsmJob {
 // event follows: a copy from pageable memory blocks the host, so it must not delay the kernels of members < i).
 int msm_run_many(jf_ctx *ctx, const jf_srs *srs, const MsmJob *jobs, int count, int (*prepare)(void *user, int i) = nullptr,
                  void *user = nullptr);
-// Bulk phases (digits, sort, accumulate, bucket sums) on ctx->stream, then -- after `ev_mid` -- the bucket reduction
-// on `tail_stream`.  The caller orders the reuse of the per-lane workspace across calls.
-int msm_run_split(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n, int mont,
-                  void *d_out_xyzz, cudaStream_t tail_stream, cudaEvent_t ev_mid);
 int msm_finish_host(jf_ctx *ctx, int curve, const uint64_t *xyzz_parts, size_t parts, uint64_t *out_xy, int *out_inf);
 int srs_build(jf_ctx *ctx, int curve, const void *d_base_points /* n affine, device */, size_t n, int window_bits,
               int precompute, jf_srs **out);

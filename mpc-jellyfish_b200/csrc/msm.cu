@@ -316,9 +316,7 @@ __device__ __forceinline__ uint32_t chunk_len(uint32_t entries, uint32_t nthread
 // The list is either compact (`cap_log` == 0: entry pos at list[pos]) or slotted (entry k of bucket b at
 // list[(b << cap_log) + k]); `flag` / `run_if_set` select which of the two launches of an MSM does the work.
 template <class Fq, bool SLOTTED>
-// 112 registers: four CTAs per SM leave ~7 K registers free, so the one-warp kernels of another stream (bucket
-// reduction of the previous MSM of a batch) can run beside a resident accumulate wave
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(128, 4)
 msm_accumulate_kernel(const Affine<Fq> *points, uint32_t srs_n, const uint32_t *list, uint32_t cap_log, const uint32_t *off,
                       uint32_t total_buckets, XYZZ<Fq> *partials, const int *flag, int run_if_set) {
     if (flag && ((*flag != 0) != (run_if_set != 0))) return;
@@ -497,7 +495,7 @@ template <class C>
 // bulk phases into its own bucket array; the bucket reduction, whose cost is the latency of its ~20 dependent levels
 // whatever the number of bucket sets, runs once for the whole group after the last member (d_outs: jc results).
 static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n_in, int mont,
-                     void *d_out, cudaStream_t tail_stream, cudaEvent_t ev_mid, int ji = 0, int jc = 1, void *const *d_outs = nullptr) {
+                     void *d_out, int ji = 0, int jc = 1, void *const *d_outs = nullptr) {
     using Fq = typename C::Fq;
     using Fr = typename C::Fr;
     using P = XYZZ<Fq>;
@@ -505,7 +503,7 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     if (base_offset > srs->n) return fail(ctx, JF_ERR_INVALID_ARG, "msm: base_offset beyond the commit key");
     size_t n = n_in < srs->n - base_offset ? n_in : srs->n - base_offset;  // arkworks: min(len(bases), len(scalars))
     if (n == 0 && jc == 1) {
-        JF_LAUNCH(ctx, "set_inf", set_inf_kernel<Fq><<<1, 32, 0, tail_stream ? tail_stream : st>>>((P *)d_out));
+        JF_LAUNCH(ctx, "set_inf", set_inf_kernel<Fq><<<1, 32, 0, st>>>((P *)d_out));
         return JF_OK;
     }
     MsmGeom g;
@@ -612,13 +610,6 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     JF_LAUNCH(ctx, "bucket_sum_heavy", bucket_sum_heavy_kernel<Fq><<<(unsigned)ctx->sm_count * 4, HEAVY_THREADS, 0, st>>>(partials, off, total, acc_threads, XA, heavy, heavy + 1));
     }  // bulk
     if (ji + 1 < jc) return JF_OK;  // the group's last member reduces every member's buckets
-    if (tail_stream) {
-        // split form: the bulk phases above ran on ctx->stream, the latency-bound bucket reduction continues on
-        // `tail_stream` (a higher-priority stream) so that it overlaps the bulk phases of the caller's next MSM
-        JF_CUDA(ctx, cudaEventRecord(ev_mid, st));
-        JF_CUDA(ctx, cudaStreamWaitEvent(tail_stream, ev_mid, 0));
-        st = tail_stream;
-    }
     {
         uint32_t nlev = g.NB, m = 0;
         P *x = XA0, *xo = XB, *pin = PA, *pout = PB;
@@ -658,14 +649,6 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     return JF_OK;
 }
 
-int msm_run_split(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n, int mont,
-                  void *d_out_xyzz, cudaStream_t tail_stream, cudaEvent_t ev_mid) {
-    if (srs->curve == JF_BN254) return msm_run_t<Bn254G1>(ctx, srs, base_offset, d_scalars, n, mont, d_out_xyzz, tail_stream, ev_mid);
-    if (srs->curve == JF_BLS12_381)
-        return msm_run_t<Bls12381G1>(ctx, srs, base_offset, d_scalars, n, mont, d_out_xyzz, tail_stream, ev_mid);
-    return fail(ctx, JF_ERR_INVALID_ARG, "msm: unknown curve");
-}
-
 int msm_run_many(jf_ctx *ctx, const jf_srs *srs, const MsmJob *jobs, int count, int (*prepare)(void *user, int i), void *user) {
     if (count <= 0) return JF_OK;
     if (count > 64) return fail(ctx, JF_ERR_INVALID_ARG, "msm: at most 64 MSMs per group");
@@ -676,9 +659,9 @@ int msm_run_many(jf_ctx *ctx, const jf_srs *srs, const MsmJob *jobs, int count, 
         if (prepare) JF_TRY(prepare(user, i));
         if (jobs[i].ready) JF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, jobs[i].ready, 0));
         if (srs->curve == JF_BN254)
-            rc = msm_run_t<Bn254G1>(ctx, srs, jobs[i].base_offset, jobs[i].d_scalars, jobs[i].n, jobs[i].mont, outs[i], nullptr, nullptr, i, count, outs);
+            rc = msm_run_t<Bn254G1>(ctx, srs, jobs[i].base_offset, jobs[i].d_scalars, jobs[i].n, jobs[i].mont, outs[i], i, count, outs);
         else if (srs->curve == JF_BLS12_381)
-            rc = msm_run_t<Bls12381G1>(ctx, srs, jobs[i].base_offset, jobs[i].d_scalars, jobs[i].n, jobs[i].mont, outs[i], nullptr, nullptr, i, count, outs);
+            rc = msm_run_t<Bls12381G1>(ctx, srs, jobs[i].base_offset, jobs[i].d_scalars, jobs[i].n, jobs[i].mont, outs[i], i, count, outs);
         else
             return fail(ctx, JF_ERR_INVALID_ARG, "msm: unknown curve");
         JF_TRY(rc);
@@ -689,7 +672,9 @@ int msm_run_many(jf_ctx *ctx, const jf_srs *srs, const MsmJob *jobs, int count, 
 
 int msm_run(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void *d_scalars, size_t n, int mont,
             void *d_out_xyzz) {
-    return msm_run_split(ctx, srs, base_offset, d_scalars, n, mont, d_out_xyzz, nullptr, nullptr);
+    if (srs->curve == JF_BN254) return msm_run_t<Bn254G1>(ctx, srs, base_offset, d_scalars, n, mont, d_out_xyzz);
+    if (srs->curve == JF_BLS12_381) return msm_run_t<Bls12381G1>(ctx, srs, base_offset, d_scalars, n, mont, d_out_xyzz);
+    return fail(ctx, JF_ERR_INVALID_ARG, "msm: unknown curve");
 }
 
 // ---- host tail: sum partial XYZZ points and normalise (`into_affine`) ---------------------

@@ -480,7 +480,7 @@ struct jf_plonk_pk {
     std::vector<void *> allocs;
     // secondary stream: coset NTTs that do not depend on the next challenge run beside the commitments
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_mid[2] = {nullptr, nullptr}, ev_tail[2] = {nullptr, nullptr};
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr;
 };
 
 namespace jf {
@@ -696,11 +696,7 @@ template <class C> struct Plonk {
         cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
         if (cudaStreamCreateWithPriority(&pk->side, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
             cudaEventCreateWithFlags(&pk->ev_main, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&pk->ev_side, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&pk->ev_mid[0], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&pk->ev_mid[1], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&pk->ev_tail[0], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&pk->ev_tail[1], cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&pk->ev_side, cudaEventDisableTiming) != cudaSuccess) {
             delete pk;
             return fail(ctx, JF_ERR_CUDA, "preprocess: cannot create the side stream");
         }
@@ -1289,10 +1285,6 @@ void jf_plonk_pk_free(jf_ctx *ctx, jf_plonk_pk *pk) {
     }
     if (pk->ev_main) cudaEventDestroy(pk->ev_main);
     if (pk->ev_side) cudaEventDestroy(pk->ev_side);
-    for (int i = 0; i < 2; i++) {
-        if (pk->ev_mid[i]) cudaEventDestroy(pk->ev_mid[i]);
-        if (pk->ev_tail[i]) cudaEventDestroy(pk->ev_tail[i]);
-    }
     if (pk->side) cudaStreamDestroy(pk->side);
     delete pk;
 }
