@@ -174,7 +174,7 @@ def ntt_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream):
         ctx.ntt_device(NTT_FIELD, d.data_ptr(), NTT_LOG_N, False, off, batch=batch)
     barrier()
     l0 = ctx.launch_count
-    ctx.profile(True)
+    ctx.profile(True, dominant_only=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(steps):
@@ -524,7 +524,9 @@ def run_cuda(args):
     sampler.start()
     time.sleep(0.25)
     launches0 = ctx.launch_count
-    ctx.profile(True)
+    # only the dominant kernel is bracketed by events inside the timed region: events around all ~30 dependent launches
+    # of an MSM cost ~0.2 ms per step (the full per-kernel breakdown comes from a separate instrumented pass below)
+    ctx.profile(True, dominant_only=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -533,10 +535,17 @@ def run_cuda(args):
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    prof = ctx.profile_collect()
+    prof_dom = ctx.profile_collect()
     ctx.profile(False)
     launches = ctx.launch_count - launches0
     ms_step = max_over_ranks(ms_total / args.steps)
+    # instrumented pass (not timed as a step): every launch bracketed, for the per-kernel breakdown
+    ctx.profile(True)
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+    barrier()
+    prof = ctx.profile_collect()
+    ctx.profile(False)
 
     # ---- end-to-end region (host buffers, copies inside) -------------------------------------------
     for i in range(min(args.warmup, 3)):
@@ -572,7 +581,7 @@ def run_cuda(args):
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------
     hbm_peak, peak_src = _peaks()
-    dom = max(prof.items(), key=lambda kv: kv[1][1])
+    dom = max(prof_dom.items(), key=lambda kv: kv[1][1])  # measured inside the timed region
     dom_name, (dom_cnt, dom_ms) = dom
     dom_avg_ms = dom_ms / max(dom_cnt, 1)
     kernel_ms_step = sum(v[1] for v in prof.values()) / args.steps
@@ -622,8 +631,11 @@ def run_cuda(args):
                          "peak_source": "max of jf_microbench(0) (independent IMAD.WIDE.U32 chains, %.3e/s) and 136 x jf_microbench(1) "
                                         "(dependent Montgomery products in registers), both measured in this run" % imad_rate,
                          "mont_mul_peak_per_s": mul_rate, "mont_mul_achieved_per_s": adds * 10 / (dom_avg_ms * 1e-3),
-                         "kernel_ms": dom_avg_ms, "kernel_share_of_step": dom_ms / args.steps / kernel_ms_step},
+                         "kernel_ms": dom_avg_ms, "kernel_share_of_step": dom_ms / args.steps / ms_step,
+                         "kernel_share_of_kernel_time": dom_ms / args.steps / kernel_ms_step},
         "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+        "kernels_ms_note": "from a separate pass with every launch bracketed by events (that pass is ~0.2 ms slower per step "
+                           "than the timed region, where only the dominant kernel is bracketed)",
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 128 * world},
         "gpu_launches": int(launches),

@@ -207,8 +207,9 @@ class Context:
         return out
 
     # -- measurement hooks ------------------------------------------------------------------------
-    def profile(self, on: bool):
-        self._check(self._lib.jf_profile_enable(self._h, int(on)))
+    def profile(self, on, dominant_only: bool = False):
+        """Per-kernel event timing; dominant_only brackets msm_accumulate / ntt_pass launches only (no cost to the step)."""
+        self._check(self._lib.jf_profile_enable(self._h, 2 if (on and dominant_only) else int(bool(on))))
 
     def profile_collect(self) -> dict:
         """{kernel name: (launches, total_ms)} since the last collect (synchronises)."""

@@ -496,6 +496,7 @@ int jf_fixed_base_mul(jf_ctx *ctx, int curve, const uint64_t *scalars, size_t n,
 int jf_profile_enable(jf_ctx *ctx, int on) {
     JF_GUARD(ctx);
     ctx->prof_on = on != 0;
+    ctx->prof_dominant_only = on == 2;
     return JF_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -40,6 +41,8 @@ struct jf_ctx {
     size_t pinned_cap = 0;
     // optional per-kernel event timing (jf_profile_*): (name, start, stop) per launch
     bool prof_on = false;
+    bool prof_dominant_only = false;  // jf_profile_enable(ctx, 2): only msm_accumulate / ntt_pass launches are bracketed
+    bool prof_open = false;           // the current launch has a start event
     struct ProfRec { const char *name; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> event_pool;
@@ -128,13 +131,16 @@ inline cudaEvent_t prof_event(jf_ctx *ctx) {
     return e;
 }
 inline void prof_begin(jf_ctx *ctx, const char *name) {
+    ctx->prof_open = false;
     if (!ctx->prof_on) return;
+    if (ctx->prof_dominant_only && strcmp(name, "msm_accumulate") != 0 && strcmp(name, "ntt_pass") != 0) return;
+    ctx->prof_open = true;
     jf_ctx::ProfRec r{name, prof_event(ctx), prof_event(ctx)};
     cudaEventRecord(r.a, ctx->stream);
     ctx->prof.push_back(r);
 }
 inline void prof_end(jf_ctx *ctx) {
-    if (!ctx->prof_on) return;
+    if (!ctx->prof_open) return;
     cudaEventRecord(ctx->prof.back().b, ctx->stream);
 }
 
