@@ -1178,22 +1178,44 @@ template <class C> struct Plonk {
         JF_TRY(scratch(ctx, "open_tmp", fe * (max_len / 256 + 4096), &dtmp));
         JF_TRY(scratch(ctx, "open_res", (PT + fe) * (batch ? batch : 1), &dres));
         E *d_ev = (E *)((char *)dres + PT * batch);
+        // The witness-polynomial commitments form MSM groups (one bucket reduction per group); the upload, evaluation
+        // and division of polynomial i are enqueued right before its MSM, so one set of buffers serves the whole batch.
+        struct Open {
+            jf_ctx *ctx;
+            const uint64_t *const *polys;
+            const uint64_t *points;
+            const size_t *len;  // trimmed lengths
+            E *dp, *dt, *ds, *dw, *dtmp, *d_ev;
+            size_t first;
+        };
+        std::vector<size_t> tl(batch);
         for (size_t i = 0; i < batch; i++) {
             // DensePolynomial semantics: trailing (high-degree) zero coefficients do not count
             size_t len = lens[i];
             while (len && !(polys[i][4 * (len - 1)] | polys[i][4 * (len - 1) + 1] | polys[i][4 * (len - 1) + 2] | polys[i][4 * (len - 1) + 3])) len--;
             if (len > srs->n + 1) return fail(ctx, JF_ERR_INVALID_ARG, "open: polynomial degree exceeds the commit key");
-            const E z = H::fr_from_limbs(points + 4 * i);
-            XYZZ<Fq> *res = (XYZZ<Fq> *)((char *)dres + PT * i);
-            if (len) JF_CUDA(ctx, cudaMemcpyAsync(dp, polys[i], fe * len, cudaMemcpyHostToDevice, ctx->stream));
-            if (len == 0) JF_CUDA(ctx, cudaMemsetAsync(d_ev + i, 0, fe, ctx->stream));
-            else JF_TRY(eval_dev(ctx, (E *)dtmp, (const E *)dp, len, z, d_ev + i));
-            if (len < 2) {
-                JF_TRY(msm_run(ctx, srs, 0, dp, 0, 1, res));  // constant / zero polynomial: identity proof
-            } else {
-                JF_TRY(div_linear_dev(ctx, (E *)dt, (E *)ds, (E *)dtmp, (const E *)dp, len, z, (E *)dw));
-                JF_TRY(msm_run(ctx, srs, 0, dw, len - 1, 1, res));
-            }
+            tl[i] = len;
+        }
+        auto prepare = [](void *user, int k) -> int {
+            Open *o = (Open *)user;
+            jf_ctx *ctx = o->ctx;
+            const size_t i = o->first + k, len = o->len[i];
+            const size_t fe = sizeof(E);
+            const E z = H::fr_from_limbs(o->points + 4 * i);
+            if (len) JF_CUDA(ctx, cudaMemcpyAsync(o->dp, o->polys[i], fe * len, cudaMemcpyHostToDevice, ctx->stream));
+            if (len == 0) JF_CUDA(ctx, cudaMemsetAsync(o->d_ev + i, 0, fe, ctx->stream));
+            else JF_TRY(eval_dev(ctx, o->dtmp, (const E *)o->dp, len, z, o->d_ev + i));
+            if (len >= 2) JF_TRY(div_linear_dev(ctx, o->dt, o->ds, o->dtmp, (const E *)o->dp, len, z, o->dw));
+            return JF_OK;
+        };
+        constexpr size_t GROUP = 16;
+        for (size_t g0 = 0; g0 < batch; g0 += GROUP) {
+            const int cnt = (int)std::min(GROUP, batch - g0);
+            MsmJob jobs[GROUP];
+            for (int k = 0; k < cnt; k++)  // constant / zero polynomial: empty MSM, identity proof
+                jobs[k] = MsmJob{0, dw, tl[g0 + k] >= 2 ? tl[g0 + k] - 1 : 0, 1, (char *)dres + PT * (g0 + k)};
+            Open o{ctx, polys, points, tl.data(), (E *)dp, (E *)dt, (E *)ds, (E *)dw, (E *)dtmp, d_ev, g0};
+            JF_TRY(msm_run_many(ctx, srs, jobs, cnt, prepare, &o));
         }
         void *h;
         JF_TRY(pinned(ctx, (PT + fe) * batch + 64, &h));

@@ -19,6 +19,7 @@ for log_n in (22,):
 n = (1 << 24) + 3
 key = ctx.generate_srs_for_testing("bn254", beta, n)
 coeffs = np.random.default_rng(2).integers(0, 1 << 60, size=(n, 4), dtype=np.uint64)
+ctx.msm(key, coeffs, montgomery=True)  # first call: grows the workspaces (cudaMalloc of several GB)
 t0 = time.time(); xy, inf = ctx.msm(key, coeffs, montgomery=True); t1 = time.time()
 ev = co.poly_eval("bn254_fr", coeffs, co.ints_to_limbs([fr.to_mont(beta)], 4)[0])
 want = co.fixed_base_mul("bn254", co.field_op("bn254_fr", "from_mont", ev[None, :]))[0]
