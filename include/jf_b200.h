@@ -154,7 +154,8 @@ int jf_ntt_cosets(jf_ctx *ctx, int field, const uint64_t *polys_in, size_t in_le
  * (g w_8n^r)<w_n>, r < 6, of the reference's 8n-point coset (6n points determine a polynomial of degree 5n + 7;
  * the coefficients follow from six size-n inverse transforms and a 6 x 6 Vandermonde solve per index), which
  * yields the same quotient polynomial with 29 % less transform work; flags & 4 keeps the reference's form (one
- * 8n-point coset transform per polynomial, prover.rs:552-567,672), as do domains below 8.  `srs` must outlive the key and hold >= n + 3 points.  2 <= log_n and
+ * 8n-point coset transform per polynomial, prover.rs:552-567,672), as do domains below 16 (at n = 8 six rows hold
+ * exactly the quotient's 48 coefficients and nothing would be left for the WrongQuotientPolyDegree check).  `srs` must outlive the key and hold >= n + 3 points.  2 <= log_n and
  * log_n + 3 <= two-adicity (JF_ERR_DOMAIN_TOO_LARGE otherwise: `Prover::new`, prover.rs:54-62). */
 int jf_plonk_preprocess(jf_ctx *ctx, const jf_srs *srs, unsigned log_n, const uint64_t *selector_evals,
                         const uint64_t *sigma_evals, const uint64_t *k, const uint32_t *wire_variables, size_t num_vars,

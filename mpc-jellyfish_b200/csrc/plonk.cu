@@ -334,7 +334,7 @@ template <class F> __global__ void degree_check_kernel(const Fp<F> *c, size_t de
 // Quotient coefficients from its interpolants on the sub-cosets: with t = sum_k X^(k n) t_k (deg t_k < n) and
 // X^n = c_r on coset r, the interpolant there is T_r = sum_k c_r^k t_k, so t_k[j] = sum_r Vinv[k][r] T_r[j] where
 // V[r][k] = c_r^k is a SUB x SUB Vandermonde matrix (inverted once per proving key on the host).
-static constexpr int SUB = 6;  // 6 n points determine the quotient (degree 5 n + 7) for every n >= 8
+static constexpr int SUB = 6;  // 6 n points determine the quotient (degree 5 n + 7) for every n >= 8 (used from n = 16)
 template <class F> struct SolveArgs {
     const Fp<F> *T;  // SUB rows of n
     Fp<F> *t;        // SUB * n coefficients
@@ -682,7 +682,9 @@ template <class C> struct Plonk {
         pk->num_inputs = (uint32_t)num_inputs;
         pk->cache_coset = flags & 1;
         pk->skip_zero = (flags & 2) ? 1 : 0;
-        pk->sub = (log_n >= 3 && !(flags & 4)) ? SUB : 0;  // 6 n >= 5 n + 8 coefficients needs n >= 8
+        // 6 n >= 5 n + 8 coefficients needs n >= 8; n >= 16 also leaves n - 8 >= 8 coefficients above the quotient's degree
+        // for the WrongQuotientPolyDegree check (at n = 8 the six-row interpolant has no coefficient above degree 47 at all)
+        pk->sub = (log_n >= 4 && !(flags & 4)) ? SUB : 0;
         pk->mq = pk->sub ? (size_t)pk->sub * n : m;
         if (flags & 2) {
             for (int sel = 0; sel < NSEL; sel++) {

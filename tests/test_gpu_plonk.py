@@ -164,6 +164,36 @@ def test_unsatisfied_witness_is_rejected_like_the_reference(ctx, co, py, P):
     key.free()
 
 
+@pytest.mark.parametrize("adds,form", [(4, "8n coset (n = 8)"), (12, "six sub-cosets (n = 16, the smallest)"), (20, "six sub-cosets (n = 32)")])
+def test_unsatisfied_witness_is_rejected_at_the_boundary_between_the_two_round_3_forms(ctx, co, py, P, adds, form):
+    """n = 8 keeps the reference's 8n coset: six rows would hold exactly the quotient's 48 coefficients and leave nothing
+    for the degree check.  From n = 16 on the six-row interpolant has n - 8 coefficients above the degree to betray a
+    witness that does not satisfy the circuit (tests/test_subcoset_identity.py states the same in big-int terms)."""
+    import mpc_jellyfish_b200 as jf
+    import plonk_util as U
+    fr = py.BN254_FR
+    cs = P.PlonkCircuit()
+    a = cs.create_variable(5)
+    for _ in range(adds):
+        a = cs.add(a, cs.one())
+    cs.finalize_for_arithmetization()
+    arr = U.arrays_from_oracle_circuit(co, py, cs)
+    key = ctx.generate_srs_for_testing("bn254", 99, cs.n + 3)
+    pk = jf.PlonkKzgSnark.preprocess(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"],
+                                     arr["pub_gate_ids"])
+    ints, bl = _blinders(co, fr, 8)
+    for victim in (len(cs.witness) - 1, 2):  # the last sum (one gate breaks) / the input variable (its gate and the copy constraints)
+        bad = arr["witness"].copy()
+        bad[victim] = co.ints_to_limbs([fr.to_mont((cs.witness[victim] + 7) % fr.p)], 4)[0]
+        with pytest.raises(jf.WrongQuotientPolyDegree):
+            jf.PlonkKzgSnark.prove(pk, bad, bl, "solidity")
+    good = jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, "standard")
+    opk = P.preprocess(py.BN254, P.gen_srs(py.BN254, 99, cs.n + 2), cs)
+    assert good.serialize_compressed() == P.serialize_proof(py.BN254, P.prove(py.BN254, cs, opk, ints, "standard")), form
+    pk.free()
+    key.free()
+
+
 def test_numpy_circuit_builder_matches_the_restated_circuit(ctx, co, py, P):
     import bench_circuit as B
     import plonk_util as U
