@@ -1,5 +1,6 @@
+"""Exploration: jf_msm at 2^24 + 3 pairs, end to end with pageable host scalars, and its kernel breakdown."""
 import os, sys, time
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import mpc_jellyfish_b200 as jf
 ctx = jf.Context(0)
