@@ -97,6 +97,8 @@ class Chain:
             else:
                 raise ValueError(o)
         host.append("    (void)cc; (void)t_;")
+        if not self.ops:
+            return "__host__ __device__ __forceinline__ void %s(%s) {}\n" % (self.name, self.params)
         t = "template <class F> " if self.tparams else ""
         s = "%s__host__ __device__ __forceinline__ void %s(%s) {\n" % (t, self.name, self.params)
         s += "#ifdef __CUDA_ARCH__\n" + dev + "#else\n" + "\n".join(host) + "\n#endif\n}\n"
@@ -137,6 +139,41 @@ def gen(N):
         c.op("madc.lo.cc", "x[%d]" % k, "a[%d]" % j, "b", lo_add)
         c.op("madc.hi.cc" if j != N - 1 else "madc.hi", "x[%d]" % (k + 1), "a[%d]" % j, "b", hi_add)
     out.append(c.emit())
+
+    # Squaring rows (Fp::sqr): row I of a square only takes the products with j >= I (the others were added, doubled,
+    # by the rows before it).  Same chains as above with the skipped products replaced by the carry propagation alone
+    # (odd chain: the 64-bit shift still has to happen) or dropped (even chain: nothing to add below the first product).
+    for I in range(1, N):
+        c = Chain("chain_shift_mad_odd_from%d" % I, (arr % "x") + ", uint32_t &e0, " + (carr % "a") + ", uint32_t b")
+        c.op("add.cc", "e0", "e0", "x[1]")
+        for j in range(1, N, 2):
+            k = j - 1
+            lo_add = "x[%d]" % (k + 2) if k + 2 < N else 0
+            hi_add = "x[%d]" % (k + 3) if k + 3 < N else 0
+            if j >= I:
+                c.op("madc.lo.cc", "x[%d]" % k, "a[%d]" % j, "b", lo_add)
+                c.op("madc.hi.cc" if j != N - 1 else "madc.hi", "x[%d]" % (k + 1), "a[%d]" % j, "b", hi_add)
+            else:
+                c.op("addc.cc", "x[%d]" % k, lo_add, 0)
+                c.op("addc.cc", "x[%d]" % (k + 1), hi_add, 0)
+        out.append(c.emit())
+        c = Chain("chain_mad_even_from%d" % I, (arr % "acc") + ", " + (carr % "a") + ", uint32_t b, uint32_t &ci")
+        first = True
+        for j in range(0, N, 2):
+            if j < I:
+                continue
+            c.op("mad.lo.cc" if first else "madc.lo.cc", "acc[%d]" % j, "a[%d]" % j, "b", "acc[%d]" % j)
+            c.op("madc.hi.cc", "acc[%d]" % (j + 1), "a[%d]" % j, "b", "acc[%d]" % (j + 1))
+            first = False
+        if not first:
+            c.op("addc", "ci", "ci", 0)
+        out.append(c.emit())
+    disp = []
+    for nm, params, args in (("chain_shift_mad_odd_from", (arr % "x") + ", uint32_t &e0, " + (carr % "a") + ", uint32_t b", "x, e0, a, b"),
+                             ("chain_mad_even_from", (arr % "acc") + ", " + (carr % "a") + ", uint32_t b, uint32_t &ci", "acc, a, b, ci")):
+        body = " else ".join("if constexpr (I == %d) %s%d(%s);" % (I, nm, I, args) for I in range(1, N))
+        disp.append("template <int I> __host__ __device__ __forceinline__ void %s(%s) {\n    %s\n}\n" % (nm, params, body))
+    out.append("\n".join(disp))
 
     # r = (e >> 32) + o
     c = Chain("chain_merge", (arr % "r") + ", " + (carr % "e") + ", " + (carr % "o"))

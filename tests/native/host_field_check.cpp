@@ -35,6 +35,10 @@ template <class F> static int run(const std::string &op, int count) {
         std::cin >> sa >> sb;
         Fp<F> a = parse<F>(sa), b = parse<F>(sb), r;
         if (op == "mul") r = Fp<F>::mul(a, b);
+        else if (op == "sqr") {  // the dedicated squaring where the field has the headroom for it, else what sqr() does
+            if constexpr (Fp<F>::SQR_OK) r = Fp<F>::sqr_dedicated(a);
+            else r = Fp<F>::sqr(a);
+        }
         else if (op == "add") r = Fp<F>::add(a, b);
         else if (op == "sub") r = Fp<F>::sub(a, b);
         else if (op == "neg") r = Fp<F>::neg(a);

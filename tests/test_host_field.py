@@ -39,6 +39,12 @@ def test_device_field_algorithm_on_host(py, hfc, fname):
     pairs = [(a, b) for a in edge for b in edge] + [(rnd.choice(vals), rnd.choice(vals)) for _ in range(1500)]
     ri = pow(f.R, -1, f.p)
     assert hfc(fname, "mul", pairs) == [a * b * ri % f.p for a, b in pairs]
+    # dedicated squaring (36 / 78 wide products; the doubled operand needs two spare bits in the top limb): operands
+    # with saturated limbs exercise every carry the skipped products leave behind
+    n32 = (f.bits + 31) // 32
+    sat = [sum(((0xFFFFFFFF if rnd.random() < 0.8 else rnd.getrandbits(32)) << (32 * i)) for i in range(n32)) % f.p for _ in range(600)]
+    sq = [(a, 0) for a in vals + sat + [rnd.randrange(f.p) for _ in range(3000)]]
+    assert hfc(fname, "sqr", sq) == [a * a * ri % f.p for a, _ in sq]
     assert hfc(fname, "add", pairs) == [(a + b) % f.p for a, b in pairs]
     assert hfc(fname, "sub", pairs) == [(a - b) % f.p for a, b in pairs]
     assert hfc(fname, "neg", pairs) == [(-a) % f.p for a, _ in pairs]
