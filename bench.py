@@ -632,7 +632,9 @@ def run_cuda(args):
                                         "(dependent Montgomery products in registers), both measured in this run" % imad_rate,
                          "mont_mul_peak_per_s": mul_rate, "mont_mul_achieved_per_s": adds * 10 / (dom_avg_ms * 1e-3),
                          "kernel_ms": dom_avg_ms, "kernel_share_of_step": dom_ms / args.steps / ms_step,
-                         "kernel_share_of_kernel_time": dom_ms / args.steps / kernel_ms_step},
+                         "kernel_share_of_kernel_time": dom_ms / args.steps / kernel_ms_step,
+                         "note": "achieved = ALGORITHMIC limb products (N W mixed additions x 10 Fq products x 136, SURVEY 8d) / kernel time; "
+                                 "the kernel itself issues fewer: its 2 squarings per addition take 108 wide products each"},
         "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
         "kernels_ms_note": "from a separate pass with every launch bracketed by events (that pass is ~0.2 ms slower per step "
                            "than the timed region, where only the dominant kernel is bracketed)",
