@@ -38,7 +38,7 @@ template <class Fq> struct XYZZ {
         F xx = F::sqr(p.x);
         F m = F::add(F::dbl(xx), xx);
         r.x = F::sub(F::sqr(m), F::dbl(s));
-        r.y = F::sub(F::mul(m, F::sub(s, r.x)), F::mul(w, p.y));
+        r.y = F::mul_sub(m, F::sub(s, r.x), w, p.y);
         r.zz = v;
         r.zzz = w;
         return r;
@@ -55,7 +55,7 @@ template <class Fq> struct XYZZ {
         F xx = F::sqr(x);
         F m = F::add(F::dbl(xx), xx);
         r.x = F::sub(F::sqr(m), F::dbl(s));
-        r.y = F::sub(F::mul(m, F::sub(s, r.x)), F::mul(w, y));
+        r.y = F::mul_sub(m, F::sub(s, r.x), w, y);
         r.zz = F::mul(v, zz);
         r.zzz = F::mul(w, zzz);
         return r;
@@ -80,7 +80,7 @@ template <class Fq> struct XYZZ {
         F ppp = F::mul(p, pp);
         F q1 = F::mul(x, pp);
         F x3 = F::sub(F::sub(F::sqr(r), ppp), F::dbl(q1));
-        F y3 = F::sub(F::mul(r, F::sub(q1, x3)), F::mul(y, ppp));
+        F y3 = F::mul_sub(r, F::sub(q1, x3), y, ppp);
         x = x3;
         y = y3;
         zz = F::mul(zz, pp);
@@ -106,7 +106,7 @@ template <class Fq> struct XYZZ {
         F ppp = F::mul(p, pp);
         F q1 = F::mul(u1, pp);
         F x3 = F::sub(F::sub(F::sqr(r), ppp), F::dbl(q1));
-        F y3 = F::sub(F::mul(r, F::sub(q1, x3)), F::mul(s1, ppp));
+        F y3 = F::mul_sub(r, F::sub(q1, x3), s1, ppp);
         x = x3;
         y = y3;
         zz = F::mul(F::mul(zz, o.zz), pp);

@@ -237,6 +237,55 @@ template <class F> struct Fp {
 #endif
         return mul(a, a);
     }
+    // a b + c d with ONE Montgomery reduction: every row adds both partial products before its reduction row, 2 x 64 + 72
+    // wide products instead of 2 x (64 + 72).  (a b + c d + M p) / R < 1.5 p for p < R / 4, so one conditional subtraction
+    // still fully reduces; like the squaring this needs the two spare top bits (SQR_OK; tests/test_field_model.py).
+    // y3 = r (q - x3) - y ppp of the point formulas has this shape (ec.cuh, behind JF_FUSED_MULSUB: host-verified, not yet
+    // run on a GPU, so the Makefile leaves it off).
+    static JF_HD Fp mul_add(const Fp &a, const Fp &b, const Fp &c, const Fp &d) {
+        if constexpr (!SQR_OK) return add(mul(a, b), mul(c, d));
+        uint32_t x[N], y[N];
+#pragma unroll
+        for (int j = 0; j < N; j += 2) {
+            uint64_t e = (uint64_t)a.v[j] * b.v[0];
+            uint64_t o = (uint64_t)a.v[j + 1] * b.v[0];
+            x[j] = (uint32_t)e;
+            x[j + 1] = (uint32_t)(e >> 32);
+            y[j] = (uint32_t)o;
+            y[j + 1] = (uint32_t)(o >> 32);
+        }
+        chain_mad_odd(y, c.v, d.v[0]);
+        chain_mad_even(x, c.v, d.v[0], y[N - 1]);
+        {
+            uint32_t m = x[0] * mont_inv<F>();
+            mad_p_pair<F>(y, x, m);
+        }
+#pragma unroll
+        for (int i = 1; i < N; i += 2) {
+            row2(x, y, a.v, b.v[i], c.v, d.v[i]);
+            if (i + 1 < N) row2(y, x, a.v, b.v[i + 1], c.v, d.v[i + 1]);
+        }
+        Fp r;
+        chain_merge(r.v, y, x);
+        reduce_once(r);
+        return r;
+    }
+    // a b - c d
+    static JF_HD Fp mul_sub(const Fp &a, const Fp &b, const Fp &c, const Fp &d) {
+#ifdef JF_FUSED_MULSUB
+        if constexpr (SQR_OK) return mul_add(a, b, c, neg(d));
+#endif
+        return sub(mul(a, b), mul(c, d));
+    }
+    static JF_HD void row2(uint32_t (&prev_e)[N], uint32_t (&prev_o)[N], const uint32_t (&a)[N], uint32_t bi, const uint32_t (&c)[N],
+                           uint32_t di) {
+        chain_shift_mad_odd(prev_e, prev_o[0], a, bi);
+        chain_mad_even(prev_o, a, bi, prev_e[N - 1]);
+        chain_mad_odd(prev_e, c, di);
+        chain_mad_even(prev_o, c, di, prev_e[N - 1]);
+        uint32_t m = prev_o[0] * mont_inv<F>();
+        mad_p_pair<F>(prev_e, prev_o, m);
+    }
     template <int I> static JF_HD void sqr_rows(uint32_t (&even)[N], uint32_t (&odd)[N], const uint32_t (&a)[N], const uint32_t (&a2)[N]) {
         if constexpr (I < N) {
             uint32_t d[N];

@@ -35,6 +35,7 @@ template <class F> static int run(const std::string &op, int count) {
         std::cin >> sa >> sb;
         Fp<F> a = parse<F>(sa), b = parse<F>(sb), r;
         if (op == "mul") r = Fp<F>::mul(a, b);
+        else if (op == "madd") r = Fp<F>::mul_add(a, b, Fp<F>::add(a, b), Fp<F>::sub(a, b));  // a b + (a + b)(a - b), one reduction
         else if (op == "sqr") {  // the dedicated squaring where the field has the headroom for it, else what sqr() does
             if constexpr (Fp<F>::SQR_OK) r = Fp<F>::sqr_dedicated(a);
             else r = Fp<F>::sqr(a);

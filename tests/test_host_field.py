@@ -45,6 +45,9 @@ def test_device_field_algorithm_on_host(py, hfc, fname):
     sat = [sum(((0xFFFFFFFF if rnd.random() < 0.8 else rnd.getrandbits(32)) << (32 * i)) for i in range(n32)) % f.p for _ in range(600)]
     sq = [(a, 0) for a in vals + sat + [rnd.randrange(f.p) for _ in range(3000)]]
     assert hfc(fname, "sqr", sq) == [a * a * ri % f.p for a, _ in sq]
+    # a b + c d under one reduction (mul_add; c = a + b, d = a - b derived in the harness)
+    mp = pairs + [(a, rnd.choice(sat)) for a in sat]
+    assert hfc(fname, "madd", mp) == [(a * b + ((a + b) % f.p) * ((a - b) % f.p)) * ri % f.p for a, b in mp]
     assert hfc(fname, "add", pairs) == [(a + b) % f.p for a, b in pairs]
     assert hfc(fname, "sub", pairs) == [(a - b) % f.p for a, b in pairs]
     assert hfc(fname, "neg", pairs) == [(-a) % f.p for a, _ in pairs]
