@@ -138,3 +138,59 @@ def test_squaring_rows_overflow_with_one_spare_bit():
     with pytest.raises(Ovf):
         for a in _operands(p, N, 200, 3):
             mont(limbs(a, N), sqr_rows(limbs(a, N), N), p_l, inv, N)
+
+
+def mont2(rowsA, rowsB, p_l, inv, N):
+    """(a b + c d) / R as Fp::mul_add computes it: every row adds both partial products, then one reduction row."""
+    x = [0] * N
+    y = [0] * N
+    d, b, _ = rowsA[0]
+    for j in range(0, N, 2):
+        e = d[j] * b
+        o = d[j + 1] * b
+        x[j], x[j + 1], y[j], y[j + 1] = e & M32, e >> 32, o & M32, o >> 32
+
+    def add_products(odd_acc, even_acc, d, b):
+        mad_odd(odd_acc, d, b, N)
+        h = [odd_acc[N - 1]]
+        mad_even(even_acc, d, b, h, N)
+        odd_acc[N - 1] = h[0]
+
+    d2, b2, _ = rowsB[0]
+    add_products(y, x, d2, b2)
+    add_products(y, x, p_l, (x[0] * inv) & M32)
+
+    def row(prev_e, prev_o, ra, rb):
+        shift_mad_odd(prev_e, prev_o, ra[0], ra[1], N)
+        h = [prev_e[N - 1]]
+        mad_even(prev_o, ra[0], ra[1], h, N)
+        prev_e[N - 1] = h[0]
+        add_products(prev_e, prev_o, rb[0], rb[1])
+        add_products(prev_e, prev_o, p_l, (prev_o[0] * inv) & M32)
+        assert prev_o[0] == 0
+
+    for i in range(1, N):
+        if i % 2 == 1:
+            row(x, y, rowsA[i], rowsB[i])
+        else:
+            row(y, x, rowsA[i], rowsB[i])
+    r = (val(y) >> 32) + val(x)
+    if r >> (32 * N):
+        raise Ovf("merge overflow")
+    p = val(p_l)
+    if r >= p:
+        r -= p
+    if r >= p:
+        raise Ovf("not reduced after one subtraction")
+    return r
+
+
+@pytest.mark.parametrize("name", ["bn254_fq", "bn254_fr", "bls12_381_fq"])
+def test_two_products_under_one_reduction_are_exact_with_two_spare_bits(name):
+    p, N, p_l, inv, rinv = _params(name)
+    ops = _operands(p, N, 1200, 4)
+    rnd = random.Random(9)
+    quads = [(p - 1, p - 1, p - 1, p - 1)] + [tuple(rnd.choice(ops) for _ in range(4)) for _ in range(1200)]
+    for a, b, c, d in quads:
+        got = mont2(mul_rows(limbs(a, N), limbs(b, N), N), mul_rows(limbs(c, N), limbs(d, N), N), p_l, inv, N)
+        assert got == (a * b + c * d) * rinv % p
