@@ -87,7 +87,9 @@ void jf_srs_free(jf_ctx *ctx, jf_srs *srs);
  * Result: out_xy = affine x || y (Montgomery), *out_infinity = 1 for the identity. */
 int jf_msm(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const uint64_t *scalars, size_t n,
            int scalars_in_montgomery, uint64_t *out_xy, int *out_infinity);
-/* jf_msm_batch == `batch_commit`'s par_iter over polynomials (mod.rs:119-131) as ONE call. */
+/* jf_msm_batch == `batch_commit`'s par_iter over polynomials (mod.rs:119-131) as ONE call: the vectors are uploaded on a
+ * copy stream while their predecessors are being sorted and accumulated, and groups of up to 8 MSMs share one bucket
+ * reduction (its ~20 dependent levels cost the same latency for one bucket set or many).  Empty vectors give the identity. */
 int jf_msm_batch(jf_ctx *ctx, const jf_srs *srs, const uint64_t *const *scalars, const size_t *lens,
                  const size_t *base_offsets, size_t batch, int scalars_in_montgomery, uint64_t *out_xy,
                  int *out_infinity);
