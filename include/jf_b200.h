@@ -32,6 +32,9 @@ extern "C" {
 typedef struct jf_ctx jf_ctx; /* one CUDA device + stream + workspace */
 typedef struct jf_srs jf_srs; /* device-resident commit key (`UnivariateProverParam::powers_of_g`) */
 typedef struct jf_plonk_pk jf_plonk_pk; /* device-resident `ProvingKey` + per-proof workspace */
+typedef struct jf_comm jf_comm;   /* this rank's end of a one-process-per-GPU group (range-sharded MSM) */
+typedef struct jf_group jf_group; /* several GPUs driven by ONE process: contexts + peer access */
+typedef struct jf_group_srs jf_group_srs; /* a commit key split by point range over the GPUs of a jf_group */
 
 typedef enum {
     JF_OK = 0,
@@ -40,7 +43,8 @@ typedef enum {
     JF_ERR_DOMAIN_TOO_LARGE = -3, /* log_n > two-adicity -> PlonkError::DomainCreationError (plonk/src/errors.rs:16-49) */
     JF_ERR_SCALAR_RANGE = -4,     /* a scalar was >= the group order (arkworks BigInts from into_bigint never are) */
     JF_ERR_NOMEM = -5,
-    JF_ERR_QUOTIENT_DEGREE = -6   /* -> SnarkError::WrongQuotientPolyDegree (prover.rs:916-919): witness does not satisfy the circuit */
+    JF_ERR_QUOTIENT_DEGREE = -6,  /* -> SnarkError::WrongQuotientPolyDegree (prover.rs:916-919): witness does not satisfy the circuit */
+    JF_ERR_COMM = -7              /* NCCL unavailable / failed, or a peer did not deliver its partial sum in time -> PCSError::UpstreamError */
 } jf_status;
 
 typedef enum { JF_BN254 = 0, JF_BLS12_381 = 1 } jf_curve;
@@ -111,6 +115,54 @@ int jf_msm_device(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const void
  * Pure host code; ctx may be NULL. */
 int jf_msm_combine(jf_ctx *ctx, int curve, const uint64_t *xyzz_parts, size_t parts, uint64_t *out_xy,
                    int *out_infinity);
+
+/* ---- multi-GPU MSM, sharded by point range ------------------------------------
+ * `commit` is a sum over (coefficient, key point) pairs (mod.rs:106-111), so GPU g can hold key[start_g, end_g) resident and
+ * receive the matching scalar slice; the partial sums (one XYZZ point = 128 B BN254 / 192 B BLS12-381 per GPU) are joined by
+ * ONE exchange step.  Two forms:
+ *
+ * (1) one process per GPU (torchrun / MPI style; what bench.py --gpus N runs).  Rank 0 calls jf_comm_unique_id and hands the
+ *     128 bytes to the other ranks by whatever channel the caller has; every rank then calls jf_comm_init (collective).
+ *     NCCL (libnccl.so.2, loaded at run time: single-GPU users need not have it) bootstraps the group and is one of the two
+ *     transports.  transport: 1 = `ncclAllGather` of the partials; 2 = peer-memory mailboxes: every rank maps the other
+ *     ranks' mailbox through CUDA IPC, and ONE kernel at the tail of the MSM stores its partial into all peers' HBM over
+ *     NVLink and waits for theirs (no collective launch; the wait gives up after 2 s with JF_ERR_COMM); 0 = 2 when all peers
+ *     are reachable, else 1 (env JF_COMM_TRANSPORT=nccl|p2p overrides).
+ *     jf_msm_sharded(_device) are collective: every rank calls them in the same order with its own key slice and scalar
+ *     slice and obtains the same result.  The final G-1 additions and the `into_affine` inversion run on the host (a lone
+ *     GPU thread needs ~0.2 ms for a Fermat inversion, a CPU core ~20 us). */
+#define JF_COMM_ID_BYTES 128
+int jf_comm_unique_id(uint8_t id[JF_COMM_ID_BYTES]);
+int jf_comm_init(jf_ctx *ctx, int rank, int nranks, const uint8_t id[JF_COMM_ID_BYTES], int transport, jf_comm **out);
+void jf_comm_destroy(jf_comm *comm);
+int jf_comm_transport(const jf_comm *comm); /* 1 nccl, 2 p2p */
+/* scalars: this rank's slice in host memory; out_xy / out_infinity as jf_msm */
+int jf_msm_sharded(jf_ctx *ctx, jf_comm *comm, const jf_srs *key_slice, size_t base_offset, const uint64_t *scalars,
+                   size_t n_local, int scalars_in_montgomery, uint64_t *out_xy, int *out_infinity);
+/* device form: scalars in HBM; leaves all `nranks` XYZZ partials (rank order, 4*L limbs each) in d_out_parts on every rank;
+ * asynchronous on the context's stream.  jf_msm_combine finishes on the host. */
+int jf_msm_sharded_device(jf_ctx *ctx, jf_comm *comm, const jf_srs *key_slice, size_t base_offset, const void *d_scalars,
+                          size_t n_local, int scalars_in_montgomery, void *d_out_parts);
+/* (2) ONE process driving several GPUs -- the drop-in for a Rust prover process (rayon threads, one address space).  The
+ *     group owns one context per device and enables peer access; the key is split by point range at load time; jf_group_msm
+ *     uploads each GPU's scalar slice, runs the slices concurrently and joins the partials with event-ordered peer reads (no
+ *     NCCL, no spinning kernel).  The same device may be listed more than once (used by the single-GPU tests). */
+int jf_group_create(const int *devices, int n_dev, jf_group **out);
+void jf_group_destroy(jf_group *g);
+int jf_group_size(const jf_group *g);
+jf_ctx *jf_group_ctx(jf_group *g, int i);
+const char *jf_group_last_error(const jf_group *g);
+int jf_group_srs_load(jf_group *g, int curve, const void *affine_pts, size_t n, size_t stride_bytes, long inf_flag_offset,
+                      int window_bits, int precompute, jf_group_srs **out);
+int jf_group_srs_generate_for_testing(jf_group *g, int curve, const uint64_t *beta, size_t n, int window_bits, int precompute,
+                                      jf_group_srs **out);
+void jf_group_srs_free(jf_group *g, jf_group_srs *srs);
+/* == jf_msm over the whole key: `msm_bigint(&powers_of_g[base_offset..], scalars).into_affine()` */
+int jf_group_msm(jf_group *g, const jf_group_srs *srs, size_t base_offset, const uint64_t *scalars, size_t n,
+                 int scalars_in_montgomery, uint64_t *out_xy, int *out_infinity);
+/* batched transforms sharded by polynomial (vector b runs on GPU b mod size; no exchange step): == jf_ntt */
+int jf_group_ntt(jf_group *g, int field, uint64_t *data, size_t in_len, unsigned log_n, int inverse,
+                 const uint64_t *coset_offset, size_t batch, size_t batch_stride);
 
 /* ---- NTT ----------------------------------------------------------------------------
  * In-place radix-2 transforms with `Radix2EvaluationDomain` semantics (ark-poly 0.4.2), natural

@@ -13,7 +13,7 @@ from .errors import (DomainCreationError, InvalidParameters, PCSError, PlonkErro
 from .multiprover import (AuthenticatedDensePoly, AuthenticatedPointShare, MultiproverKZG, fft_with_domain,
                           ifft_with_domain)
 from .plonk import PlonkKzgSnark, Proof, ProvingKey, Transcript, keccak256
-from .sharded import ShardedMsm, combine_partials, poly_owner, shard_range
+from .sharded import Comm, Group, GroupKey, ShardedMsm, combine_partials, poly_owner, shard_range
 from .pcs import Commitment, DensePolynomial, UnivariateKzgPCS, UnivariateProverParam
 
 __all__ = [
@@ -21,5 +21,5 @@ __all__ = [
     "DensePolynomial", "Commitment", "PCSError", "InvalidParameters", "UpstreamError", "PlonkError",
     "DomainCreationError", "WrongQuotientPolyDegree", "PlonkKzgSnark", "Proof", "ProvingKey", "Transcript", "keccak256",
     "MultiproverKZG", "AuthenticatedDensePoly", "AuthenticatedPointShare", "fft_with_domain", "ifft_with_domain",
-    "ShardedMsm", "combine_partials", "poly_owner", "shard_range",
+    "ShardedMsm", "Comm", "Group", "GroupKey", "combine_partials", "poly_owner", "shard_range",
 ]

@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjf_b200.so")
+# JF_B200_LIB selects another build of the same library (A/B timing of a compile-time variant: csrc/Makefile VARIANT=...)
+LIB_PATH = os.environ.get("JF_B200_LIB") or os.path.join(_HERE, "libjf_b200.so")
 
 c_u64p = ctypes.POINTER(ctypes.c_uint64)
 c_void_pp = ctypes.POINTER(ctypes.c_void_p)
@@ -22,6 +23,8 @@ JF_ERR_DOMAIN_TOO_LARGE = -3
 JF_ERR_SCALAR_RANGE = -4
 JF_ERR_NOMEM = -5
 JF_ERR_QUOTIENT_DEGREE = -6
+JF_ERR_COMM = -7
+JF_COMM_ID_BYTES = 128
 
 CURVES = {"bn254": 0, "bls12_381": 1}
 FIELDS = {"bn254_fr": 0, "bn254_fq": 1, "bls12_381_fr": 2, "bls12_381_fq": 3}
@@ -75,6 +78,28 @@ SIGNATURES = {
                                      ctypes.c_int, ctypes.c_void_p]),
     "jf_msm_combine": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64p, ctypes.c_size_t, c_u64p,
                                       ctypes.POINTER(ctypes.c_int)]),
+    "jf_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
+    "jf_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, c_void_pp]),
+    "jf_comm_destroy": (None, [ctypes.c_void_p]),
+    "jf_comm_transport": (ctypes.c_int, [ctypes.c_void_p]),
+    "jf_msm_sharded": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, c_u64p, ctypes.c_size_t,
+                                      ctypes.c_int, c_u64p, ctypes.POINTER(ctypes.c_int)]),
+    "jf_msm_sharded_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                             ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "jf_group_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int, c_void_pp]),
+    "jf_group_destroy": (None, [ctypes.c_void_p]),
+    "jf_group_size": (ctypes.c_int, [ctypes.c_void_p]),
+    "jf_group_ctx": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int]),
+    "jf_group_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "jf_group_srs_load": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                         ctypes.c_long, ctypes.c_int, ctypes.c_int, c_void_pp]),
+    "jf_group_srs_generate_for_testing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64p, ctypes.c_size_t, ctypes.c_int,
+                                                         ctypes.c_int, c_void_pp]),
+    "jf_group_srs_free": (None, [ctypes.c_void_p, ctypes.c_void_p]),
+    "jf_group_msm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, c_u64p, ctypes.c_size_t, ctypes.c_int,
+                                    c_u64p, ctypes.POINTER(ctypes.c_int)]),
+    "jf_group_ntt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64p, ctypes.c_size_t, ctypes.c_uint, ctypes.c_int, c_u64p,
+                                    ctypes.c_size_t, ctypes.c_size_t]),
     "jf_ntt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64p, ctypes.c_size_t, ctypes.c_uint, ctypes.c_int, c_u64p,
                               ctypes.c_size_t, ctypes.c_size_t]),
     "jf_ntt_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint,

@@ -50,14 +50,29 @@ static int field_limbs64(int field) { return field == JF_BLS12_381_FQ ? 6 : 4; }
 static int curve_limbs64(int curve) { return curve == JF_BLS12_381 ? 6 : 4; }
 
 // surface a sticky device-side error (scalar out of range) after a synchronisation point
-static int check_dev_err(jf_ctx *ctx) {
+int check_dev_err(jf_ctx *ctx) {
     int h = 0;
     JF_CUDA(ctx, cudaMemcpyAsync(&h, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (h != 0) {
         cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream);
+        if (h == JF_ERR_COMM) return fail(ctx, h, "msm_sharded: a peer did not deliver its partial sum within 2 s");
         return fail(ctx, h, "msm: a scalar is not below the group order (expected canonical BigInts / reduced field elements)");
     }
+    return JF_OK;
+}
+
+// rows of `width` bytes between pitched buffers; cudaMemcpy2DAsync refuses pitches of 2 GiB and more (a batch of
+// 2^24-element vectors dealt out over 8 GPUs is 4 GiB apart on the host), so those go row by row
+int copy_rows(jf_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows, cudaMemcpyKind kind,
+              cudaStream_t st) {
+    if (rows == 0 || width == 0) return JF_OK;
+    if (dpitch < ((size_t)1 << 31) && spitch < ((size_t)1 << 31)) {
+        JF_CUDA(ctx, cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st));
+        return JF_OK;
+    }
+    for (size_t r = 0; r < rows; r++)
+        JF_CUDA(ctx, cudaMemcpyAsync((char *)dst + r * dpitch, (const char *)src + r * spitch, width, kind, st));
     return JF_OK;
 }
 
@@ -352,10 +367,10 @@ int jf_ntt(jf_ctx *ctx, int field, uint64_t *data, size_t in_len, unsigned log_n
     if (groups == 1) {
         // only the first in_len entries are read by the kernels: upload just those
         if (in_len)
-            JF_CUDA(ctx, cudaMemcpy2DAsync(d_in, 32 * n, data, 32 * batch_stride, 32 * in_len, batch, cudaMemcpyHostToDevice,
+            JF_TRY(copy_rows(ctx, d_in, 32 * n, data, 32 * batch_stride, 32 * in_len, batch, cudaMemcpyHostToDevice,
                                            ctx->stream));
         JF_TRY(ntt_run(ctx, field, d_in, d_out, in_len, log_n, inverse, coset_offset, batch, n));
-        JF_CUDA(ctx, cudaMemcpy2DAsync(data, 32 * batch_stride, d_out, 32 * n, 32 * n, batch, cudaMemcpyDeviceToHost, ctx->stream));
+        JF_TRY(copy_rows(ctx, data, 32 * batch_stride, d_out, 32 * n, 32 * n, batch, cudaMemcpyDeviceToHost, ctx->stream));
         JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return JF_OK;
     }
@@ -377,13 +392,13 @@ int jf_ntt(jf_ctx *ctx, int field, uint64_t *data, size_t in_len, unsigned log_n
         char *di = (char *)d_in + 32 * n * per * g, *d_o = (char *)d_out + 32 * n * per * g;
         uint64_t *h = data + 4 * batch_stride * per * g;
         if (in_len)
-            JF_CUDA(ctx, cudaMemcpy2DAsync(di, 32 * n, h, 32 * batch_stride, 32 * in_len, per, cudaMemcpyHostToDevice, ctx->copy_in));
+            JF_TRY(copy_rows(ctx, di, 32 * n, h, 32 * batch_stride, 32 * in_len, per, cudaMemcpyHostToDevice, ctx->copy_in));
         JF_CUDA(ctx, cudaEventRecord(ctx->sync_events[2 * g], ctx->copy_in));
         JF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->sync_events[2 * g], 0));
         JF_TRY(ntt_run(ctx, field, di, d_o, in_len, log_n, inverse, coset_offset, per, n));
         JF_CUDA(ctx, cudaEventRecord(ctx->sync_events[2 * g + 1], ctx->stream));
         JF_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->sync_events[2 * g + 1], 0));
-        JF_CUDA(ctx, cudaMemcpy2DAsync(h, 32 * batch_stride, d_o, 32 * n, 32 * n, per, cudaMemcpyDeviceToHost, ctx->copy_out));
+        JF_TRY(copy_rows(ctx, h, 32 * batch_stride, d_o, 32 * n, 32 * n, per, cudaMemcpyDeviceToHost, ctx->copy_out));
     }
     JF_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
     JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -409,7 +424,7 @@ int jf_ntt_cosets(jf_ctx *ctx, int field, const uint64_t *polys_in, size_t in_le
         const size_t dstride = in_len ? in_len : 1;
         JF_TRY(scratch(ctx, "nttc_in", 32 * dstride * polys, &d_in));
         if (in_len)
-            JF_CUDA(ctx, cudaMemcpy2DAsync(d_in, 32 * dstride, polys_in, 32 * in_stride, 32 * in_len, polys, cudaMemcpyHostToDevice,
+            JF_TRY(copy_rows(ctx, d_in, 32 * dstride, polys_in, 32 * in_stride, 32 * in_len, polys, cudaMemcpyHostToDevice,
                                            ctx->stream));
         JF_TRY(ntt_run_cosets(ctx, field, d_in, dstride, in_len, d_out, log_n, 0, offsets, rows, polys));
     } else {

@@ -185,5 +185,9 @@ int srs_generate(jf_ctx *ctx, int curve, const uint64_t *beta, size_t first_powe
 int microbench(jf_ctx *ctx, int kind, double *out_rate);
 int fixed_base_mul(jf_ctx *ctx, int curve, const void *d_scalars, size_t n, void *d_out_points);
 int field_op(jf_ctx *ctx, int field, int op, const void *d_a, const void *d_b, void *d_out, size_t n);
+// copies the sticky device-side error flag back (synchronises the stream) and turns it into a status
+int check_dev_err(jf_ctx *ctx);
+int copy_rows(jf_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows, cudaMemcpyKind kind,
+              cudaStream_t st);
 
 }  // namespace jf

@@ -11,7 +11,7 @@ class InvalidParameters(PCSError):
 
 
 class UpstreamError(PCSError):
-    """`PCSError::UpstreamError` -- here: a CUDA failure surfaced through the C ABI."""
+    """`PCSError::UpstreamError` -- here: a CUDA / NCCL failure surfaced through the C ABI."""
 
 
 class PlonkError(Exception):

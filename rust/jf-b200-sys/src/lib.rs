@@ -6,6 +6,9 @@ use core::ffi::{c_char, c_int, c_long, c_uint, c_void};
 #[repr(C)] pub struct jf_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct jf_srs { _p: [u8; 0] }
 #[repr(C)] pub struct jf_plonk_pk { _p: [u8; 0] }
+#[repr(C)] pub struct jf_comm { _p: [u8; 0] }
+#[repr(C)] pub struct jf_group { _p: [u8; 0] }
+#[repr(C)] pub struct jf_group_srs { _p: [u8; 0] }
 
 pub const JF_OK: c_int = 0;
 pub const JF_ERR_INVALID_ARG: c_int = -1;
@@ -14,6 +17,8 @@ pub const JF_ERR_DOMAIN_TOO_LARGE: c_int = -3;
 pub const JF_ERR_SCALAR_RANGE: c_int = -4;
 pub const JF_ERR_NOMEM: c_int = -5;
 pub const JF_ERR_QUOTIENT_DEGREE: c_int = -6;
+pub const JF_ERR_COMM: c_int = -7;
+pub const JF_COMM_ID_BYTES: usize = 128;
 pub const JF_BN254: c_int = 0;
 pub const JF_BLS12_381: c_int = 1;
 pub const JF_BN254_FR: c_int = 0;
@@ -61,6 +66,32 @@ extern "C" {
                          scalars_in_montgomery: c_int, d_out_xyzz: *mut c_void) -> c_int;
     pub fn jf_msm_combine(ctx: *mut jf_ctx, curve: c_int, xyzz_parts: *const u64, parts: usize, out_xy: *mut u64,
                           out_infinity: *mut c_int) -> c_int;
+
+    // multi-GPU, one process per GPU
+    pub fn jf_comm_unique_id(id: *mut u8) -> c_int;
+    pub fn jf_comm_init(ctx: *mut jf_ctx, rank: c_int, nranks: c_int, id: *const u8, transport: c_int, out: *mut *mut jf_comm) -> c_int;
+    pub fn jf_comm_destroy(comm: *mut jf_comm);
+    pub fn jf_comm_transport(comm: *const jf_comm) -> c_int;
+    pub fn jf_msm_sharded(ctx: *mut jf_ctx, comm: *mut jf_comm, key_slice: *const jf_srs, base_offset: usize, scalars: *const u64,
+                          n_local: usize, scalars_in_montgomery: c_int, out_xy: *mut u64, out_infinity: *mut c_int) -> c_int;
+    pub fn jf_msm_sharded_device(ctx: *mut jf_ctx, comm: *mut jf_comm, key_slice: *const jf_srs, base_offset: usize,
+                                 d_scalars: *const c_void, n_local: usize, scalars_in_montgomery: c_int,
+                                 d_out_parts: *mut c_void) -> c_int;
+    // multi-GPU, one process driving several GPUs
+    pub fn jf_group_create(devices: *const c_int, n_dev: c_int, out: *mut *mut jf_group) -> c_int;
+    pub fn jf_group_destroy(g: *mut jf_group);
+    pub fn jf_group_size(g: *const jf_group) -> c_int;
+    pub fn jf_group_ctx(g: *mut jf_group, i: c_int) -> *mut jf_ctx;
+    pub fn jf_group_last_error(g: *const jf_group) -> *const c_char;
+    pub fn jf_group_srs_load(g: *mut jf_group, curve: c_int, affine_pts: *const c_void, n: usize, stride_bytes: usize,
+                             inf_flag_offset: c_long, window_bits: c_int, precompute: c_int, out: *mut *mut jf_group_srs) -> c_int;
+    pub fn jf_group_srs_generate_for_testing(g: *mut jf_group, curve: c_int, beta: *const u64, n: usize, window_bits: c_int,
+                                             precompute: c_int, out: *mut *mut jf_group_srs) -> c_int;
+    pub fn jf_group_srs_free(g: *mut jf_group, srs: *mut jf_group_srs);
+    pub fn jf_group_msm(g: *mut jf_group, srs: *const jf_group_srs, base_offset: usize, scalars: *const u64, n: usize,
+                        scalars_in_montgomery: c_int, out_xy: *mut u64, out_infinity: *mut c_int) -> c_int;
+    pub fn jf_group_ntt(g: *mut jf_group, field: c_int, data: *mut u64, in_len: usize, log_n: c_uint, inverse: c_int,
+                        coset_offset: *const u64, batch: usize, batch_stride: usize) -> c_int;
 
     pub fn jf_ntt(ctx: *mut jf_ctx, field: c_int, data: *mut u64, in_len: usize, log_n: c_uint, inverse: c_int,
                   coset_offset: *const u64, batch: usize, batch_stride: usize) -> c_int;
