@@ -15,8 +15,12 @@ configs[1], the configuration `metric` "MSM 2^20 G1 ms" is quoted on).  The comm
           region; for N > 1 it includes the NCCL all-gather of the per-GPU partial sums and
           the final combine.
   N > 1   weak scaling: the job is ONE MSM of N * 2^20 pairs, sharded by point range (rank r
-          holds key[r*2^20, (r+1)*2^20) and the matching scalars); one 128-byte-per-rank NCCL
-          all-gather joins the partial sums.  `value` is the time of that whole step.
+          holds key[r*2^20, (r+1)*2^20) and the matching scalars) through the library's own
+          `jf_msm_sharded`: the 128-byte partial sums are exchanged over peer memory (or
+          `ncclAllGather`) right behind the MSM kernels.  `value` is the time of that whole step;
+          the combined result is checked against commit(p) == p(beta) G at every N.
+  also    `msm_strong`: ONE 2^20 and ONE 2^24 MSM split over the N GPUs (strong scaling);
+          `msm_sweep` / `ntt.sweep`: every size of BASELINE configs[1] / configs[2] (N = 1).
 
 Inputs are larger than L2: the step rotates through 8 distinct scalar vectors (256 MB) and
 gathers from 1 GiB of window tables.
@@ -43,6 +47,24 @@ LOG_N = 20
 N_SETS = 8
 BETA = 0x1D3C7A5B9E8F60412B7A6C5D4E3F20198A7B6C5D4E3F2A1B0C9D8E7F6A5B4C3  # fixed, known
 SEED = 0x6A656C6C79666973
+
+
+def _cpu_threads():
+    """Host threads for the CPU arm: every core this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its
+    workers; the CPU legs pass the count explicitly (`num_threads(T)` in the oracle) so that does not throttle them."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def workload_config(world):
+    """`config` of BOTH arms (identical by construction: the driver compares them)."""
+    n = 1 << LOG_N
+    return {"workload": "KZG commit MSM (msm_bigint + into_affine), BN254 G1, one MSM of N_gpus x 2^20 uniform canonical "
+                        "scalars against key = [beta^i]G (BASELINE configs[1])",
+            "pairs_total": n * world, "pairs_per_gpu": n,
+            "sharding": "point range per GPU, one exchange of the 128-byte partial sums" if world > 1 else "none"}
 
 
 def _clock_sampler(stop, rows, dev):
@@ -84,76 +106,149 @@ def _clock_summary(rows):
 
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """CPU arm: the oracle's restatement of ark-ec 0.4.2 msm_bigint (signed-digit Pippenger,
-    parallel across windows only, like rayon in the reference) on the host cores.  The Rust
-    reference cannot be compiled in this image, so kind = "port" ("Oracle")."""
+    """CPU arm: the oracle's restatement of ark-ec 0.4.2 msm_bigint (signed-digit Pippenger, parallel across windows
+    only, like rayon in the reference) on ALL host cores this process may use, for the same job as the CUDA arm at this
+    N: one MSM of N x 2^20 pairs.  The Rust reference cannot be compiled in this image, so kind = "port" (DESIGN.md §2)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     import coracle as co
     co.build()
-    threads = co.max_threads()
-    windows = co.msm_windows(1 << LOG_N, 254)
-    # bounded sample: find a size whose (steps + warmup) MSMs fit in ~150 s
+    threads = _cpu_threads()
+    target = (1 << LOG_N) * world
+    log_t = target.bit_length() - 1
+    # bounded sample: the largest power of two <= target whose (steps + warmup) MSMs fit in ~150 s
     n0 = 1 << 14
     ks = co.random_field_elems("bn254_fr", n0, SEED, False)
-    pts0 = co.fixed_base_mul("bn254", ks)
+    pts0 = co.fixed_base_mul("bn254", ks, threads)
     s0 = co.random_field_elems("bn254_fr", n0, SEED + 1, False)
     t = time.perf_counter()
-    co.msm("bn254", pts0, s0)
+    co.msm("bn254", pts0, s0, threads)
     t14 = time.perf_counter() - t
     budget = 150.0 / max(args.steps + args.warmup, 1)
     log_s = 14
-    while log_s < LOG_N and t14 * (2 ** (log_s + 1 - 14)) * 0.8 < budget:
+    while log_s < log_t and t14 * (2 ** (log_s + 1 - 14)) * 0.8 < budget:
         log_s += 1
     n = 1 << log_s
-    # points: tile the 2^14 known points (the bucket method's cost does not depend on which
-    # points they are), scalars: fresh uniform values
+    # points: tile the 2^14 known points (the bucket method's cost does not depend on which points they are); scalars: fresh
     pts = np.ascontiguousarray(np.tile(pts0, (n // n0, 1)))
     times = []
     for i in range(args.warmup + args.steps):
-        s = co.random_field_elems("bn254_fr", n, SEED + 10 + i, False)
+        sc = co.random_field_elems("bn254_fr", n, SEED + 10 + i, False)
         t = time.perf_counter()
-        co.msm("bn254", pts, s)
+        co.msm("bn254", pts, sc, threads)
         dt = time.perf_counter() - t
         if i >= args.warmup:
             times.append(dt)
     ms_sample = 1e3 * float(np.mean(times))
-    scale = (1 << LOG_N) / n
+    # scale to the target size by pairs x windows (ark-ec's window count shrinks slowly with the size)
+    w_s, w_t = co.msm_windows(n, 254), co.msm_windows(target, 254)
+    scale = (target / n) * (w_t / w_s)
     ms = ms_sample * scale
-    sample = ("%d MSM(s) of 2^%d pairs per step, %d threads (ark-ec parallelises over its %d windows only)%s"
-              % (1, log_s, threads, co.msm_windows(n, 254),
-                 "" if log_s == LOG_N else "; scaled linearly x%d to 2^%d" % (int(scale), LOG_N)))
+    used = min(threads, w_s)
+    sample = ("1 MSM of 2^%d pairs per step, %d OpenMP threads requested (ark-ec parallelises over its %d windows only, so %d run)%s"
+              % (log_s, threads, w_s, used,
+                 "" if n == target else "; scaled x%.2f to %d x 2^20 pairs (pairs x windows %d/%d)" % (scale, world, w_t, w_s)))
     line = {
         "impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64x4 Montgomery (CPU, __int128)", "data": "synthetic",
-        "config": {"workload": "KZG commit MSM, BN254 G1, N=2^20 uniform canonical scalars, CPU restatement of "
-                               "ark-ec msm_bigint", "windows_at_2^20": windows},
-        "cpu_baseline": {"value": ms, "unit": "ms", "cores": min(threads, co.msm_windows(n, 254)), "kind": "port",
-                         "sample": sample},
+        "config": workload_config(world),
+        "cpu_baseline": {"value": ms, "unit": "ms", "cores": used, "kind": "port", "sample": sample},
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     _emit(line)
 
 
-
 # ------------------------------------------------------------------------------------------------
 NTT_FIELD, NTT_LOG_N, NTT_BATCH = "bn254_fr", 22, 16
 
 
-def ntt_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream):
+BLS_FR_P = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+BLS_OFF = np.array([0x0000000efffffff1, 0x17e363d300189c0f, 0xff9c57876f8457b0, 0x351332208fc5a8c4], dtype=np.uint64)  # 7 R mod r
+NTT_MODES = (("forward_coset", False, True), ("inverse_coset", True, True), ("inverse_plain", True, False))
+
+
+def _ntt_products(log_n, elems, coset, inverse):
+    """Algorithmic Montgomery products of a transform: (n/2) log2 n butterflies per vector, + n for the coset
+    scaling, + n for the 1/n of an inverse (the two fold into one per element when both apply: offset^-j / n)."""
+    return elems * (log_n / 2.0 + (1.0 if (coset or inverse) else 0.0))
+
+
+def ntt_sweep(env, d_buf, pinned):
+    """BASELINE configs[2]: batched coset NTT / iNTT, BLS12-381 Fr, 2^18 ... 2^24, 16 polynomials, in place, natural order.
+    Parity at every size before timing: Horner spot checks of the forward transform (oracle) and inverse(forward(x)) == x.
+    N > 1: the 16 polynomials are dealt out over the GPUs (strong scaling, no exchange step)."""
+    torch, co, ctx = env.torch, env.co, env.ctx
+    import pyref
+    F = pyref.BLS12_381_FR
+    mul_rate = ctx.microbench(1)
+    out = {}
+    mine = [p for p in range(NTT_BATCH) if p % env.world == env.rank]   # poly_owner: p mod world
+    for log_n in (18, 20, 22, 24):
+        n = 1 << log_n
+        per = len(mine)
+        if per == 0:
+            continue
+        # distinct coefficients per polynomial would need 8 GiB of host data at 2^24: 2 distinct vectors, tiled
+        src = co.random_field_elems("bls12_381_fr", 2 * n, SEED + 900 + log_n + 31 * env.rank, True).reshape(2, n, 4)
+        d = d_buf[: per * n * 4].view(per, n, 4)
+        dsrc = torch.from_numpy(src.view(np.int64)).cuda()
+        for b in range(per):
+            d[b].copy_(dsrc[b % 2])
+        ctx.ntt_device("bls12_381_fr", d.data_ptr(), log_n, False, BLS_OFF, batch=per)
+        env.torch.cuda.synchronize()
+        got = d[0].cpu().numpy().view(np.uint64)
+        w = pow(F.two_adic_root, 1 << (F.two_adicity - log_n), F.p)
+        for i in (1, n // 3):
+            want = co.poly_eval("bls12_381_fr", src[0], co.ints_to_limbs([F.to_mont((7 * pow(w, i, F.p)) % F.p)], 4)[0])
+            if not np.array_equal(got[i], want):
+                raise SystemExit("bench.py: BLS12-381 coset NTT 2^%d does not match Horner evaluation; refusing to time it" % log_n)
+        ctx.ntt_device("bls12_381_fr", d.data_ptr(), log_n, True, BLS_OFF, batch=per)
+        if not torch.equal(d[per - 1], dsrc[(per - 1) % 2]) or not torch.equal(d[0], dsrc[0]):
+            raise SystemExit("bench.py: inverse(forward(x)) != x at 2^%d" % log_n)
+        row = {}
+        steps = 3 if log_n >= 24 else 5
+        for name, inverse, coset in NTT_MODES:
+            off = BLS_OFF if coset else None
+            ms = env.device_ms(lambda i: ctx.ntt_device("bls12_381_fr", d.data_ptr(), log_n, inverse, off, batch=per), steps, warmup=2)
+            elems = NTT_BATCH * n
+            row[name] = {"ms": ms, "Melem_per_s": elems / (ms * 1e-3) / 1e6,
+                         "frac_of_mont_mul_rate": _ntt_products(log_n, elems, coset, inverse) / (ms * 1e-3) / (mul_rate * env.world),
+                         "hbm_GBps_algorithmic": 64.0 * elems / (ms * 1e-3) / 1e9}
+        # end to end through jf_ntt (pinned host memory, both copies inside); the pinned buffer holds 2^26 elements
+        eb = min(per, max(1, (pinned.numel() // 4) // n))
+        arr = pinned.view(-1)[: eb * n * 4].view(eb, n, 4).numpy().view(np.uint64)
+        for b in range(eb):
+            arr[b] = src[b % 2]
+        e2e = env.wall_ms(lambda i: ctx.ntt("bls12_381_fr", arr, log_n, False, BLS_OFF), 2, warmup=1)
+        row["forward_coset"]["e2e_ms"] = e2e
+        row["forward_coset"]["e2e_Melem_per_s"] = eb * env.world * n / (e2e * 1e-3) / 1e6
+        row["forward_coset"]["e2e_batch_per_gpu"] = eb
+        row["parity"] = "Horner spot checks + inverse(forward(x)) == x"
+        out["2^%d" % log_n] = row
+        del dsrc
+    return out
+
+
+def ntt_leg(env):
     """Second metric of BASELINE.json: "NTT 2^22 Melem/s".  One step = one batched forward COSET NTT
     (`coset.fft`, prover.rs:552-567) of 16 polynomials of 2^22 BN254-Fr coefficients per GPU, in place,
-    natural order in and out.  N > 1: the batch is sharded by polynomial (16 per rank, no collective)."""
+    natural order in and out.  N > 1: 16 per rank, no collective (weak); `sweep` deals 16 out over the ranks (strong)."""
+    ctx, co, torch, args, world, rank = env.ctx, env.co, env.torch, env.args, env.world, env.rank
+    barrier, max_over_ranks, stream = env.barrier, env.max_over_ranks, env.stream
     n, batch = 1 << NTT_LOG_N, NTT_BATCH
     distinct = 4
     host = co.random_field_elems(NTT_FIELD, n * distinct, SEED + 77 + rank, True).reshape(distinct, n, 4)
     pinned = torch.empty((batch, n, 4), dtype=torch.int64).pin_memory()
     for b in range(batch):
         pinned[b].copy_(torch.from_numpy(host[b % distinct].view(np.int64)))
-    d = torch.empty((batch, n, 4), dtype=torch.int64, device="cuda")
+    big = not args.no_sweep
+    per24 = len([p for p in range(NTT_BATCH) if p % world == rank])
+    d_buf = torch.empty((max(batch * n, per24 << 24 if big else 0) * 4,), dtype=torch.int64, device="cuda")
+    d = d_buf[: batch * n * 4].view(batch, n, 4)
     d.copy_(pinned)
     off = co.field_op(NTT_FIELD, "to_mont", np.array([[5, 0, 0, 0]], dtype=np.uint64))[0]  # Fr::GENERATOR
     # correctness guard on this very configuration: spot-check out[i] = p(g w^i) by Horner (oracle) for poly 0
@@ -185,18 +280,6 @@ def ntt_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream):
     prof = ctx.profile_collect()
     ctx.profile(False)
     launches = ctx.launch_count - l0
-    # config 3's field (BLS12-381 Fr, GENERATOR 7) on the same buffers, device-timed only
-    off_bls = np.array([0x0000000efffffff1, 0x17e363d300189c0f, 0xff9c57876f8457b0, 0x351332208fc5a8c4], dtype=np.uint64)  # 7 R mod r
-    for i in range(3):
-        ctx.ntt_device("bls12_381_fr", d.data_ptr(), NTT_LOG_N, False, off_bls, batch=batch)
-    barrier()
-    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    b0.record(stream)
-    for i in range(steps):
-        ctx.ntt_device("bls12_381_fr", d.data_ptr(), NTT_LOG_N, False, off_bls, batch=batch)
-    b1.record(stream)
-    barrier()
-    ms_bls = max_over_ranks(b0.elapsed_time(b1) / steps)
     # end to end through jf_ntt: pinned host coefficients in, evaluations back in the same host buffer
     e_steps = max(1, min(steps, 4))
     arr = pinned.numpy().view(np.uint64)
@@ -207,41 +290,48 @@ def ntt_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream):
         ctx.ntt(NTT_FIELD, arr, NTT_LOG_N, False, off)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e_steps)
+    sweep = ntt_sweep(env, d_buf, pinned) if big else None
     if rank != 0:
         return None
     cnt, tot = prof.get("ntt_pass", (0, 0.0))
     passes = cnt // max(steps, 1)
     pass_ms = tot / max(cnt, 1)
     mul_rate = ctx.microbench(1)
+    int_peak, int_src = _int_peak(ctx)
     elems = n * batch
-    muls = elems * (NTT_LOG_N / 2.0 + 1.0)          # (n/2) log2 n butterflies + n coset scalings
+    muls = _ntt_products(NTT_LOG_N, elems, True, False)
     peaks = _peaks()
     cpu = None
     if not args.no_cpu:
         x = host[0].copy()
-        co.ntt(NTT_FIELD, x, NTT_LOG_N, False, off)   # warm the oracle's twiddle setup
+        co.ntt(NTT_FIELD, x, NTT_LOG_N, False, off, threads=env.threads)   # warm the oracle's twiddle setup
         t0 = time.perf_counter()
-        co.ntt(NTT_FIELD, x, NTT_LOG_N, False, off)
+        co.ntt(NTT_FIELD, x, NTT_LOG_N, False, off, threads=env.threads)
         dt = time.perf_counter() - t0
-        cpu = {"value": n / dt / 1e6, "unit": "Melem/s", "cores": co.max_threads(), "kind": "port",
-               "sample": "1 coset NTT of 2^%d BN254 Fr elements, OpenMP radix-2 restatement of ark-poly" % NTT_LOG_N}
+        cpu = {"value": n / dt / 1e6, "unit": "Melem/s", "cores": env.threads, "kind": "port",
+               "sample": "1 coset NTT of 2^%d BN254 Fr elements, %d OpenMP threads, radix-2 restatement of ark-poly" % (NTT_LOG_N, env.threads)}
     return {
         "metric": "NTT 2^22 Melem/s (BN254 Fr, forward coset, batch 16 per GPU, in place, natural order)",
         "value": elems * world / (ms * 1e-3) / 1e6, "unit": "Melem/s", "ms_per_step": ms, "higher_is_better": True,
         "passes_per_transform": passes, "gpu_launches": int(launches),
-        "bls12_381_fr_melem_per_s": elems * world / (ms_bls * 1e-3) / 1e6,
-        "roofline": {"bound": "hbm", "kernel": "ntt_pass", "achieved": 64.0 * elems / (pass_ms * 1e-3) / 1e9,
-                     "peak": peaks[0], "unit": "GB/s", "frac": 64.0 * elems / (pass_ms * 1e-3) / 1e9 / peaks[0],
-                     "traffic": (_traffic("ntt_pass_bytes_per_element") or 0) * elems or None, "peak_source": peaks[1],
-                     "note": "per launch = one Stockham pass over the batch (read 32 B + write 32 B per element); a "
-                             "transform is %d passes, so the whole-transform figure is 1/%d of this" % (passes, max(passes, 1))},
-        "roofline_int": {"bound": "imad", "achieved": muls / (ms * 1e-3), "peak": mul_rate, "unit": "Montgomery mul/s",
-                         "frac": muls / (ms * 1e-3) / mul_rate,
-                         "peak_source": "jf_microbench(1): dependent 256-bit Montgomery products in registers, this run",
-                         "note": "algorithmic multiplications only ((n/2) log n + n); inter-pass twiddles are overhead"},
+        "roofline": {"bound": "imad", "kernel": "ntt_pass", "achieved": muls * PRODUCTS_PER_MUL / (ms * 1e-3), "peak": int_peak,
+                     "unit": "32x32->64 limb products/s", "frac": muls * PRODUCTS_PER_MUL / (ms * 1e-3) / int_peak,
+                     "peak_source": int_src, "traffic": (_traffic("ntt_pass_bytes_per_element") or 0) * elems or None,
+                     "microbench": {"mont_mul_per_s": mul_rate, "frac_of_mont_mul_rate": muls / (ms * 1e-3) / mul_rate},
+                     "note": "whole transform (%d passes = launches); algorithmic multiplications only ((n/2) log n + n per vector, x 136 "
+                             "limb products); the inter-pass twiddle products the kernel also performs are not counted" % passes},
+        "roofline_hbm": {"bound": "hbm", "kernel": "ntt_pass", "achieved": 64.0 * elems / (pass_ms * 1e-3) / 1e9,
+                         "peak": peaks[0], "unit": "GB/s", "frac": 64.0 * elems / (pass_ms * 1e-3) / 1e9 / peaks[0],
+                         "peak_source": peaks[1],
+                         "note": "per launch = one Stockham pass over the batch (read 32 B + write 32 B per element); a transform is "
+                                 "%d passes, so the whole-transform figure is 1/%d of this; secondary roof" % (passes, max(passes, 1))},
         "cpu_baseline": cpu,
         "e2e": {"value": elems * world / (e2e_ms * 1e-3) / 1e6, "unit": "Melem/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 32 * elems, "d2h_bytes_per_step": 32 * elems},
+                "h2d_bytes_per_step": 32 * elems, "d2h_bytes_per_step": 32 * elems,
+                "note": "PCIe bound: keep polynomials resident (jf_ntt_device / the prover entry points) wherever the caller can"},
+        "sweep": sweep,
+        "sweep_note": "BASELINE configs[2]: BLS12-381 Fr, 16 polynomials%s; ms is the max over ranks" %
+                      (" dealt out over %d GPUs by polynomial (strong scaling, no exchange)" % world if world > 1 else ""),
     }
 
 
@@ -327,7 +417,7 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
     cpu = None
     if cpu_msm_ms is not None and cpu_ntt_melems is not None:
         est = 13 * cpu_msm_ms + (26 * 8 * n + 7 * n) / (cpu_ntt_melems * 1e6) * 1e3
-        cpu = {"value": est, "unit": "ms", "cores": co.max_threads(), "kind": "port",
+        cpu = {"value": est, "unit": "ms", "cores": _cpu_threads(), "kind": "port",
                "sample": "component sum of the CPU restatement timed in this run: 13 MSM(2^20) + 26 coset NTT(2^23) + "
                          "7 iNTT(2^20) (App. A workload); pointwise / Horner / division terms not included. The reference's "
                          "only published figure extrapolates to ~24 s on a 5900X (bench.md:17, 2^15 gates x 32)"}
@@ -437,26 +527,149 @@ def _traffic(kernel):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_cuda(args):
-    import torch
-    import torch.distributed as dist
-    import mpc_jellyfish_b200 as jf
-    import coracle as co  # input generation + the cpu_baseline leg only
+IMAD_LANES_PER_SM_CLK = 32   # IMAD.WIDE.U32 lanes per SM and clock on the fmaheavy pipe (tools/micro/pipes.cu, profiles/int_peaks.json)
+PRODUCTS_PER_MUL = 136       # 32x32->64 products of one 256-bit Montgomery multiplication (2 N^2 + N, N = 8)
+MULS_PER_MIXED_ADD = 10      # XYZZ += affine: 8 M + 2 S
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; this framework has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+def _int_peak(ctx):
+    """Integer-multiply roof of this GPU: SMs x 32 IMAD.WIDE lanes x the driver-recorded max SM clock (MEASURED_PEAKS.json),
+    i.e. every lane-clock of the pipe counted -- the strictest denominator.  The library's own micro-benchmarks (measured
+    in this run) are reported beside it."""
+    mhz, src = 1965.0, "fallback 1965 MHz"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            mhz, src = float(json.load(f)["sm_max_mhz"]), "sm_max_mhz of MEASURED_PEAKS.json"
+    except Exception:
+        pass
+    import torch
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    peak = sms * IMAD_LANES_PER_SM_CLK * mhz * 1e6
+    return peak, "%d SMs x %d IMAD.WIDE.U32 lanes/clk x %s (%.0f MHz)" % (sms, IMAD_LANES_PER_SM_CLK, src, mhz)
+
+
+def _known_beta_commitment(co, scalars_canonical, beta):
+    """p(beta) * G for the coefficient vector `scalars_canonical` (oracle: Horner + one fixed-base multiplication)."""
+    beta_m = co.field_op("bn254_fr", "to_mont", co.ints_to_limbs([beta % co_modulus()], 4))[0]
+    ev = co.poly_eval("bn254_fr", co.field_op("bn254_fr", "to_mont", scalars_canonical), beta_m)
+    return co.fixed_base_mul("bn254", co.field_op("bn254_fr", "from_mont", ev[None, :]))[0]
+
+
+class _Env:
+    """What every leg needs: the context, torch, the process group and the timing helpers."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import mpc_jellyfish_b200 as jf
+        import coracle as co  # input generation, guards and the cpu_baseline legs only
+        self.torch, self.dist, self.jf, self.co, self.args = torch, dist, jf, co, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; this framework has no CPU path (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.ctx = jf.Context(self.local)
+        # a real (non-default) stream shared by torch (copies, events) and the library's kernels
+        self.stream = torch.cuda.Stream(priority=-1)  # high priority: the library's side streams only fill its idle slots
+        torch.cuda.set_stream(self.stream)
+        self.ctx.set_stream(self.stream.cuda_stream)
+        self.comm = jf.Comm.from_torch_distributed(self.ctx, transport=args.transport) if self.world > 1 else None
+        self.threads = _cpu_threads()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.world == 1:
+            return ms
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def device_ms(self, fn, steps, warmup=3):
+        """max over ranks of the CUDA-event time of `steps` back-to-back calls of fn(i), after `warmup` calls"""
+        for i in range(warmup):
+            fn(i)
+        self.barrier()
+        e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record(self.stream)
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1) / steps)
+
+    def wall_ms(self, fn, steps, warmup=2):
+        for i in range(warmup):
+            fn(i)
+        self.barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            fn(warmup + i)
+        self.barrier()
+        return self.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+
+
+def msm_one_size(env, log_total, steps, check=True):
+    """ONE MSM of 2^log_total pairs over all ranks (strong scaling; at N = 1 a plain single-GPU MSM): device-timed with
+    resident scalars, end to end from pinned host scalars, and checked against the known-beta identity."""
+    torch, co, ctx, jf = env.torch, env.co, env.ctx, env.jf
+    total = 1 << log_total
+    a, b = jf.shard_range(total, env.world, env.rank)
+    nl = b - a
+    t0 = time.time()
+    key = ctx.generate_srs_for_testing("bn254", BETA, nl, first_power=a)
+    t_key = time.time() - t0
+    sets = 2 if log_total >= 24 else 4
+    full = [co.random_field_elems("bn254_fr", total, SEED + 555 + 16 * log_total + k, False) for k in range(1 if env.world > 1 else sets)]
+    if env.world > 1:   # the other sets only matter for cache behaviour: rotate slices of independent vectors
+        mine = [full[0][a:b]] + [co.random_field_elems("bn254_fr", nl, SEED + 7777 + 16 * log_total + 100 * env.rank + k, False)
+                                 for k in range(1, sets)]
+    else:
+        mine = full
+    pinned = torch.empty((sets, nl, 4), dtype=torch.int64).pin_memory()
+    for k in range(sets):
+        pinned[k].copy_(torch.from_numpy(np.ascontiguousarray(mine[k]).view(np.int64)))
+    d_sets = pinned.cuda()
+    d_parts = torch.zeros((max(env.world, 1), 16), dtype=torch.int64, device="cuda")
+    host = [pinned[k].numpy().view(np.uint64) for k in range(sets)]
+
+    if env.world == 1:
+        dev = lambda i: ctx.msm_device(key, d_sets[i % sets].data_ptr(), nl, d_parts.data_ptr())  # noqa: E731
+        e2e = lambda i: ctx.msm(key, host[i % sets])  # noqa: E731
+    else:
+        dev = lambda i: env.comm.msm_device(key, d_sets[i % sets].data_ptr(), nl, d_parts.data_ptr())  # noqa: E731
+        e2e = lambda i: env.comm.msm(key, host[i % sets])  # noqa: E731
+    xy, inf = e2e(0)
+    ok = None
+    if check and env.rank == 0:
+        want = _known_beta_commitment(co, full[0], BETA)
+        ok = bool((not inf) and np.array_equal(xy, want))
+        if not ok:
+            raise SystemExit("bench.py: 2^%d MSM over %d GPU(s) does not match the known-beta identity; refusing to time it"
+                             % (log_total, env.world))
+    ms = env.device_ms(dev, steps)
+    e2e_ms = env.wall_ms(e2e, steps)
+    c = key.window_bits
+    W = (254 + 1 + c - 1) // c
+    key.free()
+    del d_sets, pinned
+    return {"pairs": total, "pairs_per_gpu": nl, "ms": ms, "e2e_ms": e2e_ms, "window_bits": c, "windows": W,
+            "Mpairs_per_s": total / (ms * 1e-3) / 1e6, "known_beta_identity": ok, "key_build_s": round(t_key, 3)}
+
+
+def run_cuda(args):
+    env = _Env(args)
+    torch, dist, jf, co, ctx = env.torch, env.dist, env.jf, env.co, env.ctx
+    world, rank, local, stream = env.world, env.rank, env.local, env.stream
+    barrier, max_over_ranks = env.barrier, env.max_over_ranks
     n = 1 << LOG_N
-    ctx = jf.Context(local)
-    # a real (non-default) stream shared by torch (copies, NCCL, events) and the library's kernels
-    stream = torch.cuda.Stream(priority=-1)  # high priority: the library's side streams only fill its idle slots
-    torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
 
     # commit key slice of this rank: [beta^(rank*n + i)] G
     t0 = time.time()
@@ -464,56 +677,40 @@ def run_cuda(args):
     t_key = time.time() - t0
 
     # scalars: N_SETS distinct uniform vectors per rank, canonical BigInts like `into_bigint` yields
-    host_sets = []
-    for k in range(N_SETS):
-        host_sets.append(co.random_field_elems("bn254_fr", n, SEED + 1000 * rank + k, False))
+    host_sets = [co.random_field_elems("bn254_fr", n, SEED + 1000 * rank + k, False) for k in range(N_SETS)]
     d_sets = torch.empty((N_SETS, n, 4), dtype=torch.int64, device="cuda")
     pinned = torch.empty((N_SETS, n, 4), dtype=torch.int64).pin_memory()
     for k in range(N_SETS):
         pinned[k].copy_(torch.from_numpy(host_sets[k].view(np.int64)))
     d_sets.copy_(pinned, non_blocking=False)
-    d_out = torch.zeros((16,), dtype=torch.int64, device="cuda")          # one XYZZ point (128 B)
-    gathered = torch.zeros((world, 16), dtype=torch.int64, device="cuda")
-    res_host = torch.zeros((world, 16), dtype=torch.int64).pin_memory()
+    d_parts = torch.zeros((world, 16), dtype=torch.int64, device="cuda")   # XYZZ partial(s), 128 B each
+    host_views = [pinned[k].numpy().view(np.uint64) for k in range(N_SETS)]
 
     def step_device(i):
         k = i % N_SETS
-        ctx.msm_device(key, d_sets[k].data_ptr(), n, d_out.data_ptr())
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), d_out)
+        if world == 1:
+            ctx.msm_device(key, d_sets[k].data_ptr(), n, d_parts.data_ptr())
+        else:   # kernels + the exchange of the partial sums, all on the library's stream
+            env.comm.msm_device(key, d_sets[k].data_ptr(), n, d_parts.data_ptr())
 
     def step_e2e(i):
+        # the C-ABI call a user makes: host scalars in, affine point out (jf_msm / jf_msm_sharded)
         k = i % N_SETS
-        if world == 1:
-            # the C-ABI call a user makes: host scalars in, affine point out
-            return ctx.msm(key, pinned[k].numpy().view(np.uint64))
-        d_sets[k].copy_(pinned[k], non_blocking=True)
-        ctx.msm_device(key, d_sets[k].data_ptr(), n, d_out.data_ptr())
-        dist.all_gather_into_tensor(gathered.view(-1), d_out)
-        res_host.copy_(gathered, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return ctx.msm_combine("bn254", res_host.numpy().view(np.uint64))
+        return ctx.msm(key, host_views[k]) if world == 1 else env.comm.msm(key, host_views[k])
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- correctness guard: the commitment equals p(beta') * G for the known beta ----------------
+    # ---- correctness guard at EVERY N: the combined commitment equals p(beta) * G over all N * 2^20 coefficients -------
     xy, inf = step_e2e(0)
-    if rank == 0 and world == 1:
-        ev = co.poly_eval("bn254_fr", co.field_op("bn254_fr", "to_mont", host_sets[0]),
-                          co.field_op("bn254_fr", "to_mont", co.ints_to_limbs([BETA % co_modulus()], 4))[0])
-        want = co.fixed_base_mul("bn254", co.field_op("bn254_fr", "from_mont", ev[None, :]))[0]
+    if rank == 0:
+        allc = np.concatenate([host_sets[0]] + [co.random_field_elems("bn254_fr", n, SEED + 1000 * r, False) for r in range(1, world)])
+        want = _known_beta_commitment(co, allc, BETA)
         if inf or not np.array_equal(xy, want):
-            raise SystemExit("bench.py: MSM result does not match the known-beta identity; refusing to time a wrong kernel")
+            raise SystemExit("bench.py: MSM result over %d GPU(s) does not match the known-beta identity; refusing to time a wrong kernel" % world)
+        del allc
+    step_device(0)
+    parts = d_parts.cpu().numpy().view(np.uint64)
+    dxy, dinf = ctx.msm_combine("bn254", parts)
+    if dinf or not np.array_equal(dxy, xy):
+        raise SystemExit("bench.py: device-resident form disagrees with the host form on rank %d" % rank)
 
     # ---- device-timed region ---------------------------------------------------------------------
     for i in range(args.warmup):
@@ -556,7 +753,36 @@ def run_cuda(args):
         step_e2e(args.warmup + i)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
-    ntt = None if args.no_ntt else ntt_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream)
+
+    # ---- where the end-to-end time goes (each piece timed on its own, max over ranks) -------------------------------
+    def h2d(i):
+        d_sets[i % N_SETS].copy_(pinned[i % N_SETS], non_blocking=True)
+    bd = {"h2d_ms": env.device_ms(h2d, 10), "kernels_ms": ms_step}
+    if world > 1:
+        bd["exchange_ms"] = env.device_ms(lambda i: env.comm.msm_device(key, 0, 0, d_parts.data_ptr()), 20)
+        bd["exchange_note"] = "an empty slice through jf_msm_sharded_device: one trivial kernel + the %s exchange" % env.comm.transport
+    hp = np.zeros((world, 16), dtype=np.uint64)
+
+    def tail(i):
+        ctx.dev_download(hp, d_parts.data_ptr())
+        ctx.msm_combine("bn254", hp)
+    bd["d2h_and_host_combine_ms"] = env.wall_ms(tail, 20)
+    bd["sum_ms"] = bd["h2d_ms"] + bd["kernels_ms"] + bd["d2h_and_host_combine_ms"]
+    bd["e2e_ms"] = e2e_ms
+    bd["unaccounted_ms"] = e2e_ms - bd["sum_ms"]
+    bd["note"] = ("kernels_ms is the device-timed step (includes the exchange at N > 1); unaccounted = call overhead, "
+                  "stream synchronisation latency and, at N > 1, the skew between ranks")
+
+    # ---- the other sizes and shardings ----------------------------------------------------------------------------------
+    sweep = strong = None
+    if not args.no_sweep:
+        sw_steps = max(3, min(args.steps, 10))
+        if world == 1:
+            sweep = {"2^%d" % lg: msm_one_size(env, lg, sw_steps) for lg in (16, 18, 20, 22, 24)}
+            strong = {k: sweep[k] for k in ("2^20", "2^24")}
+        else:
+            strong = {"2^%d" % lg: msm_one_size(env, lg, sw_steps) for lg in (20, 24)}
+    ntt = None if args.no_ntt else ntt_leg(env)
     prove = None
     if not args.no_prove:
         cpu_msm_ms = cpu_ntt = None
@@ -565,7 +791,7 @@ def run_cuda(args):
             ns = 1 << 16
             pts16 = key.read(0, ns)
             t0 = time.perf_counter()
-            co.msm("bn254", pts16, host_sets[0][:ns])
+            co.msm("bn254", pts16, host_sets[0][:ns], env.threads)
             cpu_msm_ms = (time.perf_counter() - t0) * 1e3 * (n / ns)
             cpu_ntt = ntt["cpu_baseline"]["value"] if ntt and ntt.get("cpu_baseline") else None
         prove = prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream, cpu_msm_ms, cpu_ntt)
@@ -576,10 +802,11 @@ def run_cuda(args):
 
     if rank != 0:
         if world > 1:
+            env.comm.close()
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel -------------------------------------------------------------
+    # ---- roofline of the dominant kernel: the integer-multiply pipe is the binding roof ---------------------
     hbm_peak, peak_src = _peaks()
     dom = max(prof_dom.items(), key=lambda kv: kv[1][1])  # measured inside the timed region
     dom_name, (dom_cnt, dom_ms) = dom
@@ -587,67 +814,74 @@ def run_cuda(args):
     kernel_ms_step = sum(v[1] for v in prof.values()) / args.steps
     alg_bytes = 96.0 * n  # 32 B scalar + 64 B affine point per pair
     achieved_gbs = alg_bytes / (dom_avg_ms * 1e-3) / 1e9
-    # integer roof: measured by the library's own micro-benchmarks on this GPU, right now
+    int_peak, int_src = _int_peak(ctx)
     imad_rate = ctx.microbench(0)
     mul_rate = ctx.microbench(1)
     W = (254 + 1 + key.window_bits - 1) // key.window_bits
     adds = float(n) * W                      # mixed additions in the accumulate kernel (upper bound: zero digits skip)
-    limb_products = adds * 10 * 136          # 8M+2S per mixed add, 2N^2+N 32x32 products per 256-bit Montgomery product
+    limb_products = adds * MULS_PER_MIXED_ADD * PRODUCTS_PER_MUL
     int_achieved = limb_products / (dom_avg_ms * 1e-3)
     traffic = _traffic(dom_name)
 
     # ---- CPU baseline leg (oracle restatement on this box's cores; bounded sample) ------------------
     cpu = None
     if not args.no_cpu:
-        threads = co.max_threads()
         log_s = 18
         ns = 1 << log_s
         pts = key.read(0, ns)
         t0 = time.perf_counter()
-        co.msm("bn254", pts, host_sets[0][:ns])
+        co.msm("bn254", pts, host_sets[0][:ns], env.threads)
         dt = time.perf_counter() - t0
-        cpu = {"value": dt * 1e3 * (n / ns), "unit": "ms", "cores": min(threads, co.msm_windows(ns, 254)), "kind": "port",
-               "sample": "1 MSM of 2^%d pairs (same key and scalars), %d OpenMP threads, ark-ec-style window parallelism; "
-                         "scaled linearly x%d to 2^20" % (log_s, threads, n // ns)}
+        w_s, w_t = co.msm_windows(ns, 254), co.msm_windows(n * world, 254)
+        scale = (n * world / ns) * (w_t / w_s)
+        cpu = {"value": dt * 1e3 * scale, "unit": "ms", "cores": min(env.threads, w_s), "kind": "port",
+               "sample": "1 MSM of 2^%d pairs (same key and scalars), %d OpenMP threads requested (ark-ec-style parallelism over its %d "
+                         "windows); scaled x%.2f to %d x 2^20 pairs (pairs x windows %d/%d)" % (log_s, env.threads, w_s, scale, world, w_t, w_s)}
 
+    cfg = workload_config(world)
     line = {
         "metric": METRIC, "value": ms_step, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 limbs (8-limb Montgomery mod 254-bit p, IMAD pipe)", "data": "synthetic",
-        "config": {
-            "workload": "KZG commit MSM (msm_bigint), BN254 G1, 2^20 uniform canonical scalars per GPU, key = [beta^i]G "
-                        "resident with precomputed window tables (c=%d, %d windows, 1 bucket set)" % (key.window_bits, W),
-            "pairs_total": n * world, "sharding": "point range per rank + 1 NCCL all-gather (128 B/rank)" if world > 1 else "none",
-            "l2": "inputs larger than L2: rotates %d scalar vectors (%d MB) and gathers from %d MB of tables"
-                  % (N_SETS, N_SETS * 32, (W * n * 64) >> 20),
-            "key_build_s": round(t_key, 3),
-        },
+        "config": cfg,
+        "setup": {"window_bits": key.window_bits, "windows": W, "bucket_sets": 1, "key_build_s": round(t_key, 3),
+                  "transport": env.comm.transport if world > 1 else None,
+                  "l2": "inputs larger than L2: rotates %d scalar vectors (%d MB) and gathers from %d MB of window tables"
+                        % (N_SETS, N_SETS * 32, (W * n * 64) >> 20)},
         "pairs_per_s": n * world / (ms_step * 1e-3),
-        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                     "note": "MSM is integer-multiply bound, not HBM bound (SURVEY 8d); see roofline_int"},
-        "roofline_int": {"bound": "imad", "kernel": dom_name, "achieved": int_achieved, "peak": max(imad_rate, 136.0 * mul_rate),
-                         "unit": "32x32->64 limb products/s", "frac": int_achieved / max(imad_rate, 136.0 * mul_rate),
-                         "peak_source": "max of jf_microbench(0) (independent IMAD.WIDE.U32 chains, %.3e/s) and 136 x jf_microbench(1) "
-                                        "(dependent Montgomery products in registers), both measured in this run" % imad_rate,
-                         "mont_mul_peak_per_s": mul_rate, "mont_mul_achieved_per_s": adds * 10 / (dom_avg_ms * 1e-3),
-                         "kernel_ms": dom_avg_ms, "kernel_share_of_step": dom_ms / args.steps / ms_step,
-                         "kernel_share_of_kernel_time": dom_ms / args.steps / kernel_ms_step,
-                         "note": "achieved = ALGORITHMIC limb products (N W mixed additions x 10 Fq products x 136, SURVEY 8d) / kernel time; "
-                                 "the kernel itself issues fewer: its 2 squarings per addition take 108 wide products each"},
+        "roofline": {"bound": "imad", "kernel": dom_name, "achieved": int_achieved, "peak": int_peak,
+                     "unit": "32x32->64 limb products/s", "frac": int_achieved / int_peak,
+                     "frac_whole_step": limb_products / (ms_step * 1e-3) / int_peak, "traffic": traffic,
+                     "peak_source": int_src,
+                     "kernel_ms": dom_avg_ms, "kernel_share_of_step": dom_ms / args.steps / ms_step,
+                     "kernel_share_of_kernel_time": dom_ms / args.steps / kernel_ms_step,
+                     "microbench": {"imad_wide_per_s": imad_rate, "mont_mul_per_s": mul_rate,
+                                    "frac_of_mont_mul_rate": adds * MULS_PER_MIXED_ADD / (dom_avg_ms * 1e-3) / mul_rate,
+                                    "note": "jf_microbench(0): independent IMAD.WIDE.U32 chains; (1): dependent 256-bit Montgomery "
+                                            "products in registers; both measured in this run (tracked copy: profiles/int_peaks.json)"},
+                     "note": "achieved = ALGORITHMIC limb products (N W mixed additions x 10 Fq products x 136, SURVEY 8d) / kernel "
+                             "time; the kernel issues fewer (dedicated squaring, fused y3), so frac understates nothing; traffic = "
+                             "DRAM bytes per launch from ncu (profiles/traffic.json)"},
+        "roofline_hbm": {"bound": "hbm", "kernel": dom_name, "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "note": "secondary roof: 96 algorithmic bytes per pair; the MSM is integer-multiply bound (SURVEY 8d)"},
         "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
         "kernels_ms_note": "from a separate pass with every launch bracketed by events (that pass is ~0.2 ms slower per step "
                            "than the timed region, where only the dominant kernel is bracketed)",
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 128 * world},
+        "e2e_breakdown": bd,
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "msm_sweep": sweep,
+        "msm_strong": strong,
         "ntt": ntt,
         "prove": prove,
         "mpc": mpc,
     }
     _emit(line)
     if world > 1:
+        env.comm.close()
         dist.destroy_process_group()
 
 
@@ -679,6 +913,8 @@ def main():
     ap.add_argument("--no-ntt", action="store_true", help="skip the NTT 2^22 leg (second metric)")
     ap.add_argument("--no-mpc", action="store_true", help="skip the collaborative-prover share-wise leg (config 5 shape)")
     ap.add_argument("--no-prove", action="store_true", help="skip the 2^20-gate prove leg (first metric)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the size sweeps / strong-scaling legs (configs[1], configs[2])")
+    ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "p2p"], help="exchange of the partial sums at N > 1")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -39,7 +39,9 @@ static NcclApi *nccl_api() {
     static NcclApi api;
     static std::once_flag once;
     std::call_once(once, [] {
-        // RTLD_NOLOAD first: inside a process that already carries an NCCL (e.g. torch's bundled one) use that very copy
+        // JF_NCCL_LIB names a specific copy.  Otherwise RTLD_NOLOAD first: inside a process that already carries an NCCL
+        // (e.g. torch's bundled one) use that very copy -- a process holds one library per SONAME.
+        if (const char *path = getenv("JF_NCCL_LIB")) api.handle = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
         const char *names[] = {"libnccl.so.2", "libnccl.so"};
         for (const char *n : names)
             if (!api.handle) api.handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);

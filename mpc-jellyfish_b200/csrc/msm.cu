@@ -435,19 +435,10 @@ bucket_sum_heavy_kernel(const XYZZ<Fq> *partials, const uint32_t *off, uint32_t 
 // same launch halves by pairwise sums.  Critical path per level = one addition + one doubling.
 // Levels are grid launches of one-warp CTAs so that the few live warps spread over all SMs (a
 // lone warp already keeps its sub-core's integer pipe busy; several on one SM would queue).
+// one work item of a level: idx < xs pairs two buckets, the rest halve the pool
 template <class Fq>
-__global__ void __launch_bounds__(128)
-reduce_level_kernel(const XYZZ<Fq> *X, XYZZ<Fq> *Xo, const XYZZ<Fq> *Pin, XYZZ<Fq> *Pout, uint32_t n, uint32_t m,
-                    uint32_t cap_x, uint32_t cap_p) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t set = blockIdx.y;
-    // launched with programmatic stream serialisation: this level's launch overlaps the previous level's
-    // tail; wait here until the previous level's results are visible
-    cudaGridDependencySynchronize();
-    X += set * cap_x;
-    Xo += set * cap_x;
-    Pin += set * cap_p;
-    Pout += set * cap_p;
+__device__ __forceinline__ void reduce_level_item(const XYZZ<Fq> *X, XYZZ<Fq> *Xo, const XYZZ<Fq> *Pin, XYZZ<Fq> *Pout, uint32_t n,
+                                                  uint32_t m, uint32_t idx) {
     const uint32_t mh = (m + 1) / 2, xs = n >= 2 ? n / 2 : n;  // n == 1: the last bucket joins the pool
     if (idx < xs) {
         if (n == 1) {
@@ -467,6 +458,18 @@ reduce_level_kernel(const XYZZ<Fq> *X, XYZZ<Fq> *Xo, const XYZZ<Fq> *Pin, XYZZ<F
         if (2 * h + 1 < m) a.add(load_xyzz(Pin + 2 * h + 1));
         store_xyzz(Pout + h, a);
     }
+}
+
+template <class Fq>
+__global__ void __launch_bounds__(128)
+reduce_level_kernel(const XYZZ<Fq> *X, XYZZ<Fq> *Xo, const XYZZ<Fq> *Pin, XYZZ<Fq> *Pout, uint32_t n, uint32_t m,
+                    uint32_t cap_x, uint32_t cap_p) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t set = blockIdx.y;
+    // launched with programmatic stream serialisation: this level's launch overlaps the previous level's
+    // tail; wait here until the previous level's results are visible
+    cudaGridDependencySynchronize();
+    reduce_level_item<Fq>(X + set * cap_x, Xo + set * cap_x, Pin + set * cap_p, Pout + set * cap_p, n, m, idx);
 }
 
 template <class Fq> __global__ void gather_sets_kernel(const XYZZ<Fq> *P, uint32_t cap_p, int S, XYZZ<Fq> *out) {

@@ -17,6 +17,7 @@
 // first pass' loads, zero padding (in_len < n) costs no reads, and the inverse transform's
 // n^-1 * g^-j scaling is fused into the last pass' stores.
 #pragma once
+#include <atomic>
 #include "common.cuh"
 #include "field.cuh"
 
@@ -399,10 +400,12 @@ template <class F, int K, bool FIRST, bool LAST, bool MULTI> static int launch_p
     constexpr int R = 1 << K;
     constexpr int B = 1 << (NTT_TILE_LOG - K);
     constexpr size_t smem = (size_t)2 * (R + R / 8) * B * sizeof(uint4);
-    static bool configured = false;
-    if (!configured) {
+    // the attribute is per device: one bit per device, set after the (idempotent) call so that concurrent first calls are harmless
+    static std::atomic<uint64_t> configured{0};
+    const uint64_t bit = (uint64_t)1 << (ctx->device & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
         JF_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel<F, K, FIRST, LAST, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.fetch_or(bit, std::memory_order_release);
     }
     const uint64_t cols = (uint64_t)1 << (a.log_n - K);
     const uint64_t blocks = ((cols + B - 1) / B) * a.batch;

@@ -60,6 +60,27 @@ def all_gather_partials(local_xyzz, group=None):
 TRANSPORTS = {"auto": 0, "nccl": 1, "p2p": 2}
 
 
+def _preload_nccl():
+    """The library binds NCCL at run time by SONAME (`libnccl.so.2`).  A process holds ONE library per SONAME, so if the
+    system copy were loaded first and torch (which needs the newer copy it bundles) imported later, torch would fail to
+    resolve its symbols.  In a Python process that has the bundled copy, load that one first; everywhere else (a Rust
+    prover process) the library finds the system's."""
+    import importlib.util
+    import os
+    import sys
+    if "torch" in sys.modules:
+        return
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (spec.submodule_search_locations if spec else []):
+            path = os.path.join(root, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
+
+
 class Comm:
     """This rank's end of a one-process-per-GPU group (`jf_comm`)."""
 
@@ -67,12 +88,14 @@ class Comm:
         if len(unique_id) != _ffi.JF_COMM_ID_BYTES:
             raise InvalidParameters("unique_id must be %d bytes" % _ffi.JF_COMM_ID_BYTES)
         self.ctx, self.rank, self.nranks = ctx, rank, nranks
+        _preload_nccl()
         h = ctypes.c_void_p()
         ctx._check(ctx._lib.jf_comm_init(ctx._h, rank, nranks, unique_id, TRANSPORTS[transport], ctypes.byref(h)))
         self._h = h
 
     @staticmethod
     def unique_id() -> bytes:
+        _preload_nccl()
         buf = ctypes.create_string_buffer(_ffi.JF_COMM_ID_BYTES)
         raise_for_status(_ffi.lib().jf_comm_unique_id(buf), "jf_comm_unique_id failed (is libnccl.so.2 loadable?)")
         return buf.raw
