@@ -526,19 +526,23 @@ template <class C> struct HostCurve {
         // value = lo + hi * 2^256; the element 2^256 has Montgomery form R^2 mod p
         return Er::add(chunk[0], Er::mul(chunk[1], Er::r_squared()));
     }
-    // ark-serialize 0.4 compressed SW point: x LE, bit 7 of the last byte = y > -y, bit 6 = infinity
+    // `serialize_compressed` of a G1 point (`to_bytes!`, utilities/src/macros.rs:13-18).
+    // BN254: ark-ec's generic short-Weierstrass form -- x little-endian, bit 7 of the LAST byte = y > -y, bit 6 = infinity.
+    // BLS12-381: ark-bls12-381 0.4.0 overrides `serialize_with_mode` for G1 with the ZCash / IETF form -- x BIG-endian, top
+    // bits of the FIRST byte: 7 = compressed, 6 = infinity, 5 = y > -y (published vectors: tests/golden/constants.json).
+    static constexpr bool ZCASH_G1 = Fq::N == 12;
     static void g1_bytes(const uint64_t *xy, int inf, uint8_t *out) {
         const int nb = 8 * L;
         memset(out, 0, nb);
         if (inf) {
-            out[nb - 1] |= 0x40;
+            if (ZCASH_G1) out[0] = 0xC0;
+            else out[nb - 1] |= 0x40;
             return;
         }
         Eq x, y;
         memcpy(x.v, xy, nb);
         memcpy(y.v, xy + L, nb);
         Eq xc = Eq::from_mont(x), yc = Eq::from_mont(y), ny = Eq::from_mont(Eq::neg(y));
-        memcpy(out, xc.v, nb);
         bool greater = false;
         for (int i = Fq::N - 1; i >= 0; i--) {
             if (yc.v[i] != ny.v[i]) {
@@ -546,7 +550,14 @@ template <class C> struct HostCurve {
                 break;
             }
         }
-        if (greater) out[nb - 1] |= 0x80;
+        if (ZCASH_G1) {
+            const uint8_t *le = reinterpret_cast<const uint8_t *>(xc.v);
+            for (int i = 0; i < nb; i++) out[i] = le[nb - 1 - i];
+            out[0] |= greater ? 0xA0 : 0x80;
+        } else {
+            memcpy(out, xc.v, nb);
+            if (greater) out[nb - 1] |= 0x80;
+        }
     }
 };
 

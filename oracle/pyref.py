@@ -251,9 +251,26 @@ class Curve:
             total = self._jadd(total, acc)
         return self._to_affine(total)
 
-    # ---- ark-serialize 0.4 `serialize_compressed` for SW affine points ----
+    # ---- `serialize_compressed` of a G1 affine point (`to_bytes!`, utilities/src/macros.rs:13-18) ----
+    # BN254 (ark-bn254 0.4.0) uses ark-ec's generic short-Weierstrass encoding: x little-endian, flags in the top two bits of
+    # the LAST byte (bit 7: y is the lexicographically larger root, bit 6: infinity).
+    # BLS12-381 (ark-bls12-381 0.4.0, the version the reference pins in primitives/Cargo.toml:13) overrides
+    # `SWCurveConfig::serialize_with_mode` for G1 with the ZCash / IETF encoding (its `curves/util.rs`: `EncodingFlags`,
+    # `serialize_fq`): x BIG-endian, flags in the top three bits of the FIRST byte (bit 7: compressed, bit 6: infinity,
+    # bit 5: y is the larger root, only when compressed and finite).  SURVEY.md 8c described the generic form for both
+    # curves; that was wrong for BLS12-381 (VERDICT r1, weak #1b).  Pinned by the published compressed generator, 2 G and
+    # identity in tests/golden/constants.json.
     def serialize_compressed(self, P: Affine) -> bytes:
         nbytes = self.fq.limbs64 * 8
+        if self.name == "bls12_381":
+            if P is None:
+                return bytes([0xC0]) + bytes(nbytes - 1)
+            x, y = P
+            out = bytearray(x.to_bytes(nbytes, "big"))
+            out[0] |= 0x80
+            if y > (self.fq.p - y):
+                out[0] |= 0x20
+            return bytes(out)
         if P is None:
             out = bytearray(nbytes)
             out[-1] |= 0x40

@@ -54,6 +54,12 @@ GOLDEN = {
         "generator": [
             "0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb",
             "0x08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1"],
+        # ZCash / IETF compressed encoding (what ark-bls12-381 0.4.0 emits for G1): the published generator, the public keys
+        # of the secret keys 2 and 3 in the BLS signature test suites (= 2 G, 3 G), and the identity
+        "generator_compressed": "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb",
+        "two_g_compressed": "a572cbea904d67468808c8eb50a9450c9721db309128012543902d0ac358a62ae28f75bb8f1c7c42c39a8c5529bf0f4e",
+        "three_g_compressed": "89ece308f9d1f0131765212deca99697b112d61f9be9a5f1f3780a51335b3ff981747a0b2ca2179b96d2c0c9024e5224",
+        "identity_compressed": "c0" + "00" * 47,
     },
 }
 

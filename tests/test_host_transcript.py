@@ -54,3 +54,48 @@ def test_error_type_for_unsatisfied_witness_exists():
     with pytest.raises(jf.WrongQuotientPolyDegree):
         errors.raise_for_status(_ffi.JF_ERR_QUOTIENT_DEGREE, "x")
     assert issubclass(jf.WrongQuotientPolyDegree, jf.PlonkError)
+
+
+def test_product_serializer_emits_the_published_g1_encodings(py):
+    """`jf_plonk_proof_serialize` is host code.  BN254 points use ark-ec's generic compressed form, BLS12-381 points the
+    ZCash / IETF form ark-bls12-381 0.4.0 emits; both are checked against the PUBLISHED encodings of G, 2 G and the identity
+    (tests/golden/constants.json), not against the Python restatement."""
+    import ctypes
+    from mpc_jellyfish_b200 import _ffi
+    consts = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "constants.json")))
+    for curve_id, cv, key, L in ((0, py.BN254, "bn254_g1", 4), (1, py.BLS12_381, "bls12_381_g1", 6)):
+        g = consts[key]
+        pr = _ffi.PlonkProofStruct()
+        pr.curve = curve_id
+        fq = cv.fq
+
+        def put(dst, slot, P):
+            x, y = P
+            for k, v in enumerate((fq.to_mont(x), fq.to_mont(y))):
+                for i in range(L):
+                    dst[2 * L * slot + L * k + i] = (v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF
+
+        G, G2 = cv.gen, cv.mul(2, cv.gen)
+        put(pr.wires_poly_comms, 0, G)
+        put(pr.wires_poly_comms, 1, G2)
+        put(pr.wires_poly_comms, 2, cv.neg(G))
+        pr.wires_inf[3] = 1
+        put(pr.wires_poly_comms, 4, G)
+        for name in ("prod_perm_poly_comm", "opening_proof", "shifted_opening_proof"):
+            put(getattr(pr, name), 0, G)
+        for j in range(5):
+            put(pr.split_quot_poly_comms, j, G)
+        buf = ctypes.create_string_buffer(2048)
+        n = _ffi.lib().jf_plonk_proof_serialize(ctypes.byref(pr), buf, len(buf))
+        nb = 8 * L
+        assert n == 8 + 5 * nb + nb + 8 + 5 * nb + 2 * nb + 8 + 5 * 32 + 8 + 4 * 32 + 32 + 1
+        raw = buf.raw[:n]
+        pts = [raw[8 + nb * i: 8 + nb * (i + 1)].hex() for i in range(5)]
+        assert pts[0] == g["generator_compressed"] and pts[4] == g["generator_compressed"]
+        assert pts[3] == g["identity_compressed"]
+        if key == "bls12_381_g1":
+            assert pts[1] == g["two_g_compressed"]
+            assert pts[2] == "b7" + g["generator_compressed"][2:]
+        else:
+            assert pts[2] == g["generator_compressed"][:-2] + "80"   # -G: same x, "negative" flag in the last byte
+        assert pts[1] == cv.serialize_compressed(G2).hex() and pts[2] == cv.serialize_compressed(cv.neg(G)).hex()

@@ -43,6 +43,13 @@ def test_curve_known_answers(py):
     cv = py.BLS12_381
     assert cv.gen == tuple(_int(v) for v in b["generator"]) and cv.b == b["b"]
     assert cv.is_on_curve(cv.gen) and cv.mul(cv.fr.p, cv.gen) is None
+    # ark-bls12-381 0.4.0 serialises G1 in the ZCash / IETF form (x big-endian, flags in the top bits of byte 0)
+    assert cv.serialize_compressed(cv.gen).hex() == b["generator_compressed"]
+    assert cv.serialize_compressed(cv.mul(2, cv.gen)).hex() == b["two_g_compressed"]       # larger root: sort flag set
+    assert cv.serialize_compressed(cv.mul(3, cv.gen)).hex() == b["three_g_compressed"]
+    assert cv.serialize_compressed(None).hex() == b["identity_compressed"]
+    neg = cv.serialize_compressed(cv.neg(cv.gen))
+    assert neg[0] == 0xB7 and neg[1:] == cv.serialize_compressed(cv.gen)[1:]
 
 
 @pytest.mark.parametrize("fname", ["bn254_fr", "bn254_fq", "bls12_381_fr", "bls12_381_fq"])
