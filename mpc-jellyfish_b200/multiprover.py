@@ -6,15 +6,18 @@
   AuthenticatedScalarResult::ifft               plonk/src/multiprover/proof_system/constraint_system.rs:930,955,978
 
 An authenticated value is an additive share plus an additive share of its MAC (ark-mpc
-`AuthenticatedScalarResult { share, mac, .. }`).  MSM and NTT are linear, so each party applies them
-to its share vector and to its MAC vector locally -- here as one batch of two on the GPU -- and the
-results are valid shares of the plain result.  Opening shares (the network exchange of ark-mpc) is
-not on this path; `open_shares` below is the arithmetic the reference's tests use to check results.
+`AuthenticatedScalarResult { share, mac, public_modifier }`; the reference builds shares as `ScalarShare::new(share, mac)`,
+multiprover/proof_system/prover.rs:985-1013).  ark-mpc is an unpinned git dependency (Cargo.toml:16): revisions that carry
+the third component -- the public modifier, the running sum of public constants folded into the value, which the MAC check
+needs -- push it through `msm_authenticated` / `fft_with_domain` as a third vector.  MSM and NTT are linear, so each party
+applies them to every component vector locally -- here as ONE batch of two or three on the GPU -- and the results are
+valid shares of the plain result.  Opening shares (the network exchange of ark-mpc) is not on this path; the tests add
+the parties' results, which is the arithmetic the reference's own tests use (`open_authenticated`).
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -26,27 +29,49 @@ from .pcs import UnivariateProverParam
 
 @dataclass
 class AuthenticatedDensePoly:
-    """`AuthenticatedDensePoly`: coefficient shares and their MAC shares, (n, 4) Montgomery limbs each."""
+    """`AuthenticatedDensePoly`: coefficient shares, their MAC shares and (optionally: the three-component form of
+    ark-mpc's authenticated scalars) their public modifiers, (n, 4) Montgomery limbs each."""
     share: np.ndarray
     mac: np.ndarray
+    public_modifier: Optional[np.ndarray] = None
 
     def __post_init__(self):
         self.share = np.ascontiguousarray(self.share, dtype=np.uint64).reshape(-1, 4)
         self.mac = np.ascontiguousarray(self.mac, dtype=np.uint64).reshape(-1, 4)
         if self.share.shape != self.mac.shape:
             raise InvalidParameters("share and MAC vectors differ in length")
+        if self.public_modifier is not None:
+            self.public_modifier = np.ascontiguousarray(self.public_modifier, dtype=np.uint64).reshape(-1, 4)
+            if self.public_modifier.shape != self.share.shape:
+                raise InvalidParameters("share and public-modifier vectors differ in length")
 
     def degree(self) -> int:
         return max(len(self.share) - 1, 0)
 
+    def components(self) -> List[np.ndarray]:
+        """the vectors every linear operation is applied to, in ark-mpc's field order"""
+        return [self.share, self.mac] + ([self.public_modifier] if self.public_modifier is not None else [])
+
 
 @dataclass
 class AuthenticatedPointShare:
-    """One party's share of a commitment / opening proof: (share point, MAC point), affine x || y."""
+    """One party's share of a commitment / opening proof: (share point, MAC point[, public-modifier point]), affine x || y."""
     share: np.ndarray
     share_inf: bool
     mac: np.ndarray
     mac_inf: bool
+    public_modifier: Optional[np.ndarray] = None
+    public_modifier_inf: bool = True
+
+
+def _point_shares(polys: Sequence[AuthenticatedDensePoly], out: np.ndarray, inf: Sequence[bool]) -> List[AuthenticatedPointShare]:
+    res, i = [], 0
+    for p in polys:
+        k = len(p.components())
+        res.append(AuthenticatedPointShare(out[i], inf[i], out[i + 1], inf[i + 1], out[i + 2] if k == 3 else None,
+                                           inf[i + 2] if k == 3 else True))
+        i += k
+    return res
 
 
 class MultiproverKZG:
@@ -62,9 +87,11 @@ class MultiproverKZG:
                 raise InvalidParameters("Polynomial degree exceeds supported degree")
         vecs = []
         for p in polys:
-            vecs += [p.share, p.mac]
+            vecs += p.components()
+        # one call for every component of every polynomial (the reference loops over `commit`, and each `commit` rebuilds the
+        # key as `Vec<CurvePoint>`, multiprover_kzg.rs:232-234; here the key stays resident)
         out, inf = prover_params.ctx.msm_batch(prover_params.key, vecs, None, montgomery=True)
-        return [AuthenticatedPointShare(out[2 * i], inf[2 * i], out[2 * i + 1], inf[2 * i + 1]) for i in range(len(polys))]
+        return _point_shares(polys, out, inf)
 
     @staticmethod
     def open(prover_params: UnivariateProverParam, poly: AuthenticatedDensePoly, point: np.ndarray
@@ -72,21 +99,45 @@ class MultiproverKZG:
         """`point` is public (4 Montgomery limbs).  -> (proof share, (evaluation share, evaluation MAC share))."""
         if poly.degree() - 1 > len(prover_params.key):  # multiprover_kzg.rs:176-181
             raise InvalidParameters("Polynomial degree exceeds supported degree")
-        z = np.ascontiguousarray(point, dtype=np.uint64).reshape(1, 4)
-        xy, inf, ev = prover_params.ctx.kzg_open(prover_params.key, [poly.share, poly.mac], np.repeat(z, 2, axis=0))
-        return AuthenticatedPointShare(xy[0], inf[0], xy[1], inf[1]), (ev[0], ev[1])
+        proofs, evals = MultiproverKZG.batch_open(prover_params, [poly], [point])
+        return proofs[0], evals[0]
+
+    @staticmethod
+    def batch_open(prover_params: UnivariateProverParam, polys: Sequence[AuthenticatedDensePoly], points: Sequence[np.ndarray]
+                   ) -> Tuple[List[AuthenticatedPointShare], List[Tuple[np.ndarray, ...]]]:
+        """`MultiproverKZG::batch_open` (multiprover_kzg.rs:199-229): every (polynomial, public point) pair, all components,
+        in one `jf_kzg_open` call.  -> (proof shares, per polynomial the evaluation of each component)."""
+        if len(polys) != len(points):
+            raise InvalidParameters("poly length %d is different from points length %d" % (len(polys), len(points)))
+        vecs, zs = [], []
+        for poly, point in zip(polys, points):
+            if poly.degree() - 1 > len(prover_params.key):  # multiprover_kzg.rs:176-181
+                raise InvalidParameters("Polynomial degree exceeds supported degree")
+            z = np.ascontiguousarray(point, dtype=np.uint64).reshape(1, 4)
+            comps = poly.components()
+            vecs += comps
+            zs += [z] * len(comps)
+        xy, inf, ev = prover_params.ctx.kzg_open(prover_params.key, vecs, np.concatenate(zs, axis=0))
+        proofs = _point_shares(polys, xy, inf)
+        evals, i = [], 0
+        for poly in polys:
+            k = len(poly.components())
+            evals.append(tuple(ev[i + j] for j in range(k)))
+            i += k
+        return proofs, evals
 
 
 def fft_with_domain(domain: Radix2EvaluationDomain, poly: AuthenticatedDensePoly, inverse: bool = False) -> AuthenticatedDensePoly:
-    """Share-wise (coset) NTT / iNTT of an authenticated vector: one batch of two on the GPU."""
+    """Share-wise (coset) NTT / iNTT of an authenticated vector: one batch of two (three) on the GPU."""
     n = domain.size
     if len(poly.share) > n:
         raise InvalidParameters("input of length %d exceeds the domain size %d" % (len(poly.share), n))
-    buf = np.zeros((2, n, 4), dtype=np.uint64)
-    buf[0, : len(poly.share)] = poly.share
-    buf[1, : len(poly.mac)] = poly.mac
+    comps = poly.components()
+    buf = np.zeros((len(comps), n, 4), dtype=np.uint64)
+    for i, c in enumerate(comps):
+        buf[i, : len(c)] = c
     out = domain.batch_fft(buf, inverse=inverse, in_len=len(poly.share))
-    return AuthenticatedDensePoly(out[0], out[1])
+    return AuthenticatedDensePoly(out[0], out[1], out[2] if len(comps) == 3 else None)
 
 
 def ifft_with_domain(domain: Radix2EvaluationDomain, evals: AuthenticatedDensePoly) -> AuthenticatedDensePoly:

@@ -114,3 +114,79 @@ def test_kzg_batch_open_and_edge_polynomials(ctx, co, py):
     with pytest.raises(jf.InvalidParameters):
         jf.UnivariateKzgPCS.batch_open(pp, polys, pts[:-1])
     pp.key.free()
+
+
+def _fast_shares(co, field, vals_m, key_m, seed, with_modifier):
+    """two parties' (share, mac[, public modifier]) vectors of `vals_m` (Montgomery limbs), built with the C oracle so that
+    2^18-element vectors take milliseconds: share_1 random, share_0 = v - share_1; likewise for mac = key * (v + modifier)."""
+    n = len(vals_m)
+    r1 = co.random_field_elems(field, n, seed, True)
+    r2 = co.random_field_elems(field, n, seed + 1, True)
+    mod = co.random_field_elems(field, n, seed + 2, True) if with_modifier else None
+    base = co.field_op(field, "add", vals_m, mod) if with_modifier else vals_m
+    mac = co.field_op(field, "mul", base, np.repeat(key_m[None, :], n, axis=0))
+    parties = []
+    for who in range(2):
+        share = r1 if who == 1 else co.field_op(field, "sub", vals_m, r1)
+        m = r2 if who == 1 else co.field_op(field, "sub", mac, r2)
+        parties.append((share, m, mod))          # the public modifier is public: both parties hold the same vector
+    return parties, mac, mod
+
+
+@pytest.mark.parametrize("three", [False, True], ids=["share+mac", "share+mac+modifier"])
+def test_config5_size_commit_and_sharewise_coset_ntt(ctx, co, py, three):
+    """BASELINE configs[4]: the collaborative prover at n = 2^18 (BN254).  `MultiproverKZG::batch_commit` of authenticated
+    polynomials of n + 2 coefficients and their share-wise coset NTT to the 8n quotient domain: the parties' results, added
+    (= opened), equal the single prover's (multiprover/proof_system/prover.rs:1316-1438 assert the same per round), the MAC
+    shares open to key * result, and the optional third component goes through the same linear map."""
+    import mpc_jellyfish_b200 as jf
+    cv, fr, field = py.BN254, py.BN254_FR, "bn254_fr"
+    n = 1 << 18
+    beta, mac_key = 0x5EEDBEEFCAFE1234567, 0x246813579BDF
+    key_m = co.ints_to_limbs([fr.to_mont(mac_key)], 4)[0]
+    pp = jf.UnivariateProverParam(ctx.generate_srs_for_testing("bn254", beta, n + 3))
+    polys = [co.random_field_elems(field, n + 2, 700 + i, True) for i in range(2)]
+    shared = [_fast_shares(co, field, v, key_m, 800 + 10 * i, three) for i, v in enumerate(polys)]
+    beta_m = co.ints_to_limbs([fr.to_mont(beta)], 4)[0]
+
+    def commit_of(vec_m):  # known-beta identity: commit(p) = p(beta) G
+        ev = co.poly_eval(field, vec_m, beta_m)
+        xy = co.fixed_base_mul("bn254", co.field_op(field, "from_mont", ev[None, :]))[0]
+        return _pt(co, cv, xy, not xy.any())
+
+    per_party = [jf.MultiproverKZG.batch_commit(pp, [jf.AuthenticatedDensePoly(*sh[0][who]) for sh in shared]) for who in range(2)]
+    single = jf.UnivariateKzgPCS.batch_commit(pp, [jf.DensePolynomial(v) for v in polys])
+    for i, v in enumerate(polys):
+        a, b = per_party[0][i], per_party[1][i]
+        opened = cv.add(_pt(co, cv, a.share, a.share_inf), _pt(co, cv, b.share, b.share_inf))
+        assert opened == _pt(co, cv, np.array(single[i].xy, dtype=np.uint64), single[i].infinity) == commit_of(v)
+        opened_mac = cv.add(_pt(co, cv, a.mac, a.mac_inf), _pt(co, cv, b.mac, b.mac_inf))
+        assert opened_mac == commit_of(shared[i][1])
+        if three:
+            want_mod = commit_of(shared[i][2])
+            assert _pt(co, cv, a.public_modifier, a.public_modifier_inf) == want_mod
+            assert opened_mac == cv.mul(mac_key, cv.add(opened, want_mod))   # mac = key * (value + modifier)
+        else:
+            assert a.public_modifier is None and opened_mac == cv.mul(mac_key, opened)
+    # share-wise coset NTT to the quotient domain (prover.rs:373-388): opened evaluations == the plain transform
+    dom8 = jf.Radix2EvaluationDomain(ctx, field, 8 * n).get_coset(fr.generator)
+    v = polys[0]
+    want = dom8.fft(v)
+    outs = [jf.fft_with_domain(dom8, jf.AuthenticatedDensePoly(*shared[0][0][who])) for who in range(2)]
+    assert np.array_equal(co.field_op(field, "add", outs[0].share, outs[1].share), want)
+    mac_want = dom8.fft(shared[0][1])
+    assert np.array_equal(co.field_op(field, "add", outs[0].mac, outs[1].mac), mac_want)
+    if three:
+        assert np.array_equal(outs[0].public_modifier, dom8.fft(shared[0][2]))
+    # ... and back: the coset iNTT of the opened evaluations returns the coefficients (prover.rs:418)
+    back = jf.ifft_with_domain(dom8, outs[1])
+    assert np.array_equal(back.share[: n + 2], shared[0][0][1][0]) and not back.share[n + 2:].any()
+    # batch_open on shares at size (multiprover_kzg.rs:199-229)
+    z = co.ints_to_limbs([fr.to_mont(0x1234567890ABCDEF1234567890)], 4)[0]
+    pr = [jf.MultiproverKZG.batch_open(pp, [jf.AuthenticatedDensePoly(*shared[0][0][who])], [z]) for who in range(2)]
+    proof_single, ev_single = jf.UnivariateKzgPCS.open(pp, jf.DensePolynomial(v), 0x1234567890ABCDEF1234567890)
+    opened_proof = cv.add(_pt(co, cv, pr[0][0][0].share, pr[0][0][0].share_inf), _pt(co, cv, pr[1][0][0].share, pr[1][0][0].share_inf))
+    assert opened_proof == _pt(co, cv, np.array(proof_single.xy, dtype=np.uint64), proof_single.infinity)
+    ev = co.field_op(field, "add", pr[0][1][0][0][None, :], pr[1][1][0][0][None, :])[0]
+    assert fr.from_mont(co.limbs_to_ints(ev[None, :])[0]) == ev_single
+    pp.key.free()
