@@ -24,6 +24,9 @@ use std::{
     sync::{Arc, Mutex, OnceLock},
 };
 
+#[cfg(feature = "ark-mpc")]
+pub mod mpc;
+
 #[derive(Debug)]
 pub enum GpuError { InvalidParameters(String), Upstream(String), DomainCreation, WrongQuotientPolyDegree }
 
