@@ -3,6 +3,7 @@
 // Host buffers in, host buffers out; every call stages through device memory owned by the
 // context.  No CPU fallback exists: if CUDA is unusable jf_ctx_create fails and nothing else
 // can be called.
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "field.cuh"
@@ -75,6 +76,25 @@ int copy_rows(jf_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spi
         JF_CUDA(ctx, cudaMemcpyAsync((char *)dst + r * dpitch, (const char *)src + r * spitch, width, kind, st));
     return JF_OK;
 }
+
+bool zero_copy_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("JF_MSM_ZEROCOPY");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+// device-visible alias of a page-locked host buffer, nullptr for pageable memory
+const void *pinned_device_view(const void *host) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return at.devicePointer;
+}
+
 
 }  // namespace jf
 
@@ -266,8 +286,15 @@ static int msm_batch_locked(jf_ctx *ctx, const jf_srs *srs, const uint64_t *cons
         const size_t off = base_offsets ? base_offsets[0] : 0;
         if (off > srs->n) return fail(ctx, JF_ERR_INVALID_ARG, "msm: base_offset beyond the commit key");
         const size_t n = lens[0] < srs->n - off ? lens[0] : srs->n - off;
-        if (n) JF_CUDA(ctx, cudaMemcpyAsync(d_sc[0], scalars[0], 32 * n, cudaMemcpyHostToDevice, main_stream));
-        rc = msm_run(ctx, srs, off, d_sc[0], n, mont, d_res);
+        // Page-locked scalars (jf_host_alloc / cudaHostRegister) that the sort reads exactly once are read by the sort kernel
+        // straight from host memory: the PCIe transfer and the sort become one step instead of two (JF_MSM_ZEROCOPY=0: copy).
+        const void *src = d_sc[0];
+        if (n && zero_copy_enabled() && msm_reads_scalars_once(srs, n) && (src = pinned_device_view(scalars[0])) != nullptr) {
+        } else {
+            src = d_sc[0];
+            if (n) JF_CUDA(ctx, cudaMemcpyAsync(d_sc[0], scalars[0], 32 * n, cudaMemcpyHostToDevice, main_stream));
+        }
+        rc = msm_run(ctx, srs, off, src, n, mont, d_res);
     }
     for (size_t g0 = 0; piped && g0 < batch && rc == JF_OK; g0 += G) {
         const int cnt = batch - g0 < (size_t)G ? (int)(batch - g0) : G;

@@ -401,8 +401,13 @@ int jf_msm_sharded(jf_ctx *ctx, jf_comm *c, const jf_srs *srs, size_t base_offse
     void *d_sc, *h_res;
     JF_TRY(scratch(ctx, "msm_scalars0", 32 * (n ? n : 1), &d_sc));
     JF_TRY(pinned(ctx, pt * c->nranks, &h_res));
-    if (n) JF_CUDA(ctx, cudaMemcpyAsync(d_sc, scalars, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
-    JF_TRY(msm_run(ctx, srs, base_offset, d_sc, n, mont, c->d_part));
+    const void *src = nullptr;
+    if (n && zero_copy_enabled() && msm_reads_scalars_once(srs, n)) src = pinned_device_view(scalars);  // see jf_msm
+    if (!src) {
+        src = d_sc;
+        if (n) JF_CUDA(ctx, cudaMemcpyAsync(d_sc, scalars, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    JF_TRY(msm_run(ctx, srs, base_offset, src, n, mont, c->d_part));
     JF_TRY(comm_exchange(ctx, c, pt, c->d_parts));
     JF_CUDA(ctx, cudaMemcpyAsync(h_res, c->d_parts, pt * c->nranks, cudaMemcpyDeviceToHost, ctx->stream));
     JF_TRY(check_dev_err(ctx));  // synchronises

@@ -178,6 +178,10 @@ struct MsmJob {
 // event follows: a copy from pageable memory blocks the host, so it must not delay the kernels of members < i).
 int msm_run_many(jf_ctx *ctx, const jf_srs *srs, const MsmJob *jobs, int count, int (*prepare)(void *user, int i) = nullptr,
                  void *user = nullptr);
+// true when an MSM of n pairs over this key sorts in ONE pass over the scalars (then they may be read straight from pinned host memory)
+bool msm_reads_scalars_once(const jf_srs *srs, size_t n);
+bool zero_copy_enabled();                          // JF_MSM_ZEROCOPY != 0
+const void *pinned_device_view(const void *host);  // device-visible alias of a page-locked host buffer, nullptr for pageable memory
 int msm_finish_host(jf_ctx *ctx, int curve, const uint64_t *xyzz_parts, size_t parts, uint64_t *out_xy, int *out_inf);
 int srs_build(jf_ctx *ctx, int curve, const void *d_base_points /* n affine, device */, size_t n, int window_bits,
               int precompute, jf_srs **out);

@@ -493,6 +493,25 @@ template <class Fq> __global__ void set_inf_kernel(XYZZ<Fq> *out) {
 }
 
 // ---- driver ------------------------------------------------------------------------------
+// Direct (single-pass) sort geometry: slot capacity per bucket as a power of two, 0 = use the compact two-pass form.
+static uint32_t direct_cap_log(int bits, int c, int W, uint32_t total, size_t max_entries) {
+    const int top_bits = bits + 1 - (W - 1) * c;
+    const size_t lam = max_entries / total + 1;  // expected entries per bucket
+    size_t cap = 64;
+    uint32_t cap_log = 0;
+    while (cap < 2 * lam + 64) cap <<= 1;
+    while (((size_t)1 << cap_log) < cap) cap_log++;
+    if (top_bits < c - 1 || (size_t)total * cap > 8 * max_entries + ((size_t)1 << 22)) cap_log = 0;  // not worth the slots
+    return cap_log;
+}
+
+bool msm_reads_scalars_once(const jf_srs *srs, size_t n) {
+    const int bits = srs->curve == JF_BLS12_381 ? 255 : 254;
+    const int S = (srs->windows + srs->tables - 1) / srs->tables;
+    const uint32_t total = (uint32_t)S << (srs->window_bits - 1);
+    return n != 0 && direct_cap_log(bits, srs->window_bits, srs->windows, total, n * (size_t)srs->windows) != 0;
+}
+
 template <class C>
 // ji / jc: this call is MSM `ji` of a group of `jc` over the same commit key (msm_run_many).  Every member runs its
 // bulk phases into its own bucket array; the bucket reduction, whose cost is the latency of its ~20 dependent levels
@@ -574,15 +593,7 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     // Direct sort when every bucket is expected to stay far below its slot capacity (uniform digits, no narrow
     // top window): one pass over the scalars instead of two.  A bucket that overflows anyway (skewed scalars)
     // raises a device-side flag and the compact path below takes over; no host round trip either way.
-    const int top_bits = Fr::BITS + 1 - (g.W - 1) * g.c;
-    uint32_t cap_log = 0;
-    {
-        const size_t lam = max_entries / total + 1;  // expected entries per bucket
-        size_t cap = 64;
-        while (cap < 2 * lam + 64) cap <<= 1;
-        while (((size_t)1 << cap_log) < cap) cap_log++;
-        if (top_bits < g.c - 1 || (size_t)total * cap > 8 * max_entries + ((size_t)1 << 22)) cap_log = 0;  // not worth the slots
-    }
+    const uint32_t cap_log = direct_cap_log(Fr::BITS, g.c, g.W, total, max_entries);
     int *flag = (int *)(heavy + total + 2);
     if (cap_log) {
         uint32_t *slots;
