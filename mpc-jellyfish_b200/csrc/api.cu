@@ -164,7 +164,16 @@ int jf_ctx_sync(jf_ctx *ctx) {
     return check_dev_err(ctx);
 }
 
-const char *jf_last_error(const jf_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+const char *jf_last_error(const jf_ctx *ctx) {
+    // the text is rewritten by whichever thread fails next: hand every caller its own copy, taken under the lock
+    static thread_local std::string mine;
+    if (!ctx) return "null context";
+    {
+        std::lock_guard<std::mutex> lock(const_cast<jf_ctx *>(ctx)->mu);
+        mine = ctx->err;
+    }
+    return mine.c_str();
+}
 
 uint64_t jf_ctx_launch_count(const jf_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
@@ -415,17 +424,26 @@ int jf_ntt(jf_ctx *ctx, int field, uint64_t *data, size_t in_len, unsigned log_n
     JF_CUDA(ctx, cudaEventRecord(ctx->sync_events[2 * groups], ctx->stream));
     JF_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->sync_events[2 * groups], 0));
     JF_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->sync_events[2 * groups], 0));
-    for (size_t g = 0; g < groups; g++) {
-        char *di = (char *)d_in + 32 * n * per * g, *d_o = (char *)d_out + 32 * n * per * g;
-        uint64_t *h = data + 4 * batch_stride * per * g;
-        if (in_len)
-            JF_TRY(copy_rows(ctx, di, 32 * n, h, 32 * batch_stride, 32 * in_len, per, cudaMemcpyHostToDevice, ctx->copy_in));
-        JF_CUDA(ctx, cudaEventRecord(ctx->sync_events[2 * g], ctx->copy_in));
-        JF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->sync_events[2 * g], 0));
-        JF_TRY(ntt_run(ctx, field, di, d_o, in_len, log_n, inverse, coset_offset, per, n));
-        JF_CUDA(ctx, cudaEventRecord(ctx->sync_events[2 * g + 1], ctx->stream));
-        JF_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->sync_events[2 * g + 1], 0));
-        JF_TRY(copy_rows(ctx, h, 32 * batch_stride, d_o, 32 * n, 32 * n, per, cudaMemcpyDeviceToHost, ctx->copy_out));
+    const int prc = [&]() -> int {
+        for (size_t g = 0; g < groups; g++) {
+            char *di = (char *)d_in + 32 * n * per * g, *d_o = (char *)d_out + 32 * n * per * g;
+            uint64_t *h = data + 4 * batch_stride * per * g;
+            if (in_len)
+                JF_TRY(copy_rows(ctx, di, 32 * n, h, 32 * batch_stride, 32 * in_len, per, cudaMemcpyHostToDevice, ctx->copy_in));
+            JF_CUDA(ctx, cudaEventRecord(ctx->sync_events[2 * g], ctx->copy_in));
+            JF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->sync_events[2 * g], 0));
+            JF_TRY(ntt_run(ctx, field, di, d_o, in_len, log_n, inverse, coset_offset, per, n));
+            JF_CUDA(ctx, cudaEventRecord(ctx->sync_events[2 * g + 1], ctx->stream));
+            JF_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->sync_events[2 * g + 1], 0));
+            JF_TRY(copy_rows(ctx, h, 32 * batch_stride, d_o, 32 * n, 32 * n, per, cudaMemcpyDeviceToHost, ctx->copy_out));
+        }
+        return JF_OK;
+    }();
+    if (prc != JF_OK) {  // copies may still be queued against the caller's buffer: drain all three streams before reporting
+        cudaStreamSynchronize(ctx->copy_in);
+        cudaStreamSynchronize(ctx->copy_out);
+        cudaStreamSynchronize(ctx->stream);
+        return prc;
     }
     JF_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
     JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -48,6 +48,7 @@ struct jf_ctx {
     std::vector<cudaEvent_t> event_pool;
     // cached NTT plans keyed by (field, log_n, inverse, coset offset limbs)
     std::map<std::string, jf::NttPlan *> ntt_plans;
+    uint64_t ntt_plan_clock = 0;  // LRU clock of the plan cache (ntt_impl.cuh: plan_cache_insert)
 };
 
 struct jf_srs {

@@ -830,15 +830,24 @@ static int srs_build_t(jf_ctx *ctx, int curve, const void *d_base, size_t n, int
         delete s;
         return fail(ctx, JF_ERR_NOMEM, std::string("srs: cudaMalloc: ") + cudaGetErrorString(e));
     }
-    if (n) {
-        JF_CUDA(ctx, cudaMemcpyAsync(s->d_points, d_base, sizeof(Affine<Fq>) * n, cudaMemcpyDeviceToDevice, ctx->stream));
-        Affine<Fq> *tab = (Affine<Fq> *)s->d_points;
-        for (int t = 1; t < s->tables; t++) {
-            JF_LAUNCH(ctx, "table_step", table_step_kernel<Fq><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(tab + (size_t)(t - 1) * n,
-                                                                                 tab + (size_t)t * n, (uint32_t)n, c));
+    const int rc = [&]() -> int {
+        if (n) {
+            JF_CUDA(ctx, cudaMemcpyAsync(s->d_points, d_base, sizeof(Affine<Fq>) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+            Affine<Fq> *tab = (Affine<Fq> *)s->d_points;
+            for (int t = 1; t < s->tables; t++) {
+                JF_LAUNCH(ctx, "table_step", table_step_kernel<Fq><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(
+                    tab + (size_t)(t - 1) * n, tab + (size_t)t * n, (uint32_t)n, c));
+            }
         }
+        JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return JF_OK;
+    }();
+    if (rc != JF_OK) {  // do not leak the half-built key
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(s->d_points);
+        delete s;
+        return rc;
     }
-    JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = s;
     return JF_OK;
 }

@@ -51,6 +51,7 @@ struct NttPlan {
     // ntt_run_cosets: `rows` offset tables of n entries in off_full, X^n on each coset in fold_c
     int rows = 0;
     void *fold_c = nullptr;
+    uint64_t last_use = 0;  // cache clock of the last call that used this plan (LRU eviction)
 };
 
 inline void free_plan(NttPlan *pl) {
@@ -64,6 +65,30 @@ inline void free_plan(NttPlan *pl) {
     for (auto &t : pl->ptw) cudaFree(t);
     for (auto &t : pl->tw) cudaFree(t);
     delete pl;
+}
+
+// The cache is keyed by the coset offset as well, so a caller that varies the offset per call would otherwise grow it
+// without bound: beyond NTT_PLAN_CAP plans the least recently used ones are dropped (after a device synchronisation:
+// kernels of any lane may still read their tables).  `keep` is never dropped.
+static constexpr size_t NTT_PLAN_CAP = 48;
+inline NttPlan *plan_touch(jf_ctx *ctx, NttPlan *pl) {
+    pl->last_use = ++ctx->ntt_plan_clock;
+    return pl;
+}
+inline void plan_cache_insert(jf_ctx *ctx, const std::string &key, NttPlan *pl, const NttPlan *keep = nullptr) {
+    plan_touch(ctx, pl);
+    ctx->ntt_plans[key] = pl;
+    if (ctx->ntt_plans.size() <= NTT_PLAN_CAP) return;
+    cudaDeviceSynchronize();
+    while (ctx->ntt_plans.size() > NTT_PLAN_CAP * 3 / 4) {
+        auto victim = ctx->ntt_plans.end();
+        for (auto it = ctx->ntt_plans.begin(); it != ctx->ntt_plans.end(); ++it)
+            if (it->second != pl && it->second != keep && (victim == ctx->ntt_plans.end() || it->second->last_use < victim->second->last_use))
+                victim = it;
+        if (victim == ctx->ntt_plans.end()) break;
+        free_plan(victim->second);
+        ctx->ntt_plans.erase(victim);
+    }
 }
 
 template <class F> struct El {  // 32-byte element as two 16-byte halves for vector loads
@@ -466,9 +491,9 @@ static int get_plan(jf_ctx *ctx, int field, unsigned log_n, int inverse, const u
             free_plan(pl);
             return rc;
         }
-        ctx->ntt_plans[key] = pl;
+        plan_cache_insert(ctx, key, pl);
     } else {
-        pl = it->second;
+        pl = plan_touch(ctx, it->second);
     }
     *out = pl;
     *out_has_off = has_off;
@@ -530,6 +555,8 @@ static int ntt_run_t(jf_ctx *ctx, int field, void *d_data, void *d_out, size_t i
         JF_CUDA(ctx, cudaMalloc(&pl->off_full, sizeof(E) * n));
         JF_LAUNCH(ctx, "full_table", full_table_kernel<F><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
             (E *)pl->off_full, (const E *)pl->off_lo, (const E *)pl->off_hi, pl->split, (uint64_t)n));
+        // the plan is shared by every lane (stream) of the context: complete the table before anyone else can see the pointer
+        JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     for (int i = 0; i < np; i++) {
         PassArgs a;
@@ -604,31 +631,38 @@ static int ntt_run_cosets_t(jf_ctx *ctx, int field, const void *d_src, size_t sr
         pl->inverse = inverse != 0;
         pl->has_offset = true;
         pl->rows = rows;
-        ctx->ntt_plans[key] = pl;  // owned by the cache from here on (freed with the context)
-        E ninv = E::one();
-        if (inverse && !base->ninv_folded) {
-            E half = E::inv(E::from_u32(2));
-            for (unsigned i = 0; i < log_n; i++) ninv = E::mul(ninv, half);
-        }
-        JF_CUDA(ctx, cudaMalloc(&pl->off_full, sizeof(E) * n * rows));
-        JF_CUDA(ctx, cudaMalloc(&pl->fold_c, sizeof(E) * rows));
-        std::vector<E> c(rows);
-        for (int r = 0; r < rows; r++) {
-            E off;
-            for (int i = 0; i < 4; i++) {
-                off.v[2 * i] = (uint32_t)offsets[4 * r + i];
-                off.v[2 * i + 1] = (uint32_t)(offsets[4 * r + i] >> 32);
+        const int brc = [&]() -> int {
+            E ninv = E::one();
+            if (inverse && !base->ninv_folded) {
+                E half = E::inv(E::from_u32(2));
+                for (unsigned i = 0; i < log_n; i++) ninv = E::mul(ninv, half);
             }
-            c[r] = off;
-            for (unsigned i = 0; i < log_n; i++) c[r] = E::sqr(c[r]);
-            if (inverse) off = E::inv(off);
-            JF_LAUNCH(ctx, "pow_table", pow_table_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(
-                (E *)pl->off_full + (size_t)r * n, off, ninv, 1, (uint32_t)n));
+            JF_CUDA(ctx, cudaMalloc(&pl->off_full, sizeof(E) * n * rows));
+            JF_CUDA(ctx, cudaMalloc(&pl->fold_c, sizeof(E) * rows));
+            std::vector<E> c(rows);
+            for (int r = 0; r < rows; r++) {
+                E off;
+                for (int i = 0; i < 4; i++) {
+                    off.v[2 * i] = (uint32_t)offsets[4 * r + i];
+                    off.v[2 * i + 1] = (uint32_t)(offsets[4 * r + i] >> 32);
+                }
+                c[r] = off;
+                for (unsigned i = 0; i < log_n; i++) c[r] = E::sqr(c[r]);
+                if (inverse) off = E::inv(off);
+                JF_LAUNCH(ctx, "pow_table", pow_table_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(
+                    (E *)pl->off_full + (size_t)r * n, off, ninv, 1, (uint32_t)n));
+            }
+            JF_CUDA(ctx, cudaMemcpyAsync(pl->fold_c, c.data(), sizeof(E) * rows, cudaMemcpyHostToDevice, ctx->stream));
+            JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // c is a local
+            return JF_OK;
+        }();
+        if (brc != JF_OK) {
+            free_plan(pl);
+            return brc;
         }
-        JF_CUDA(ctx, cudaMemcpyAsync(pl->fold_c, c.data(), sizeof(E) * rows, cudaMemcpyHostToDevice, ctx->stream));
-        JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // c is a local
+        plan_cache_insert(ctx, key, pl, base);  // owned by the cache from here on (freed with the context)
     } else {
-        pl = it->second;
+        pl = plan_touch(ctx, it->second);
     }
     const int np = (int)base->passes.size();
     void *t1 = nullptr, *t2 = nullptr;

@@ -561,6 +561,15 @@ template <class C> struct HostCurve {
     }
 };
 
+// frees everything a (possibly half-built) proving key owns; the caller has synchronised the streams that used it
+static void release_pk(jf_plonk_pk *pk) {
+    for (void *p : pk->allocs) cudaFree(p);
+    if (pk->ev_main) cudaEventDestroy(pk->ev_main);
+    if (pk->ev_side) cudaEventDestroy(pk->ev_side);
+    if (pk->side) cudaStreamDestroy(pk->side);
+    delete pk;
+}
+
 static int dalloc(jf_ctx *ctx, jf_plonk_pk *pk, size_t bytes, void **out) {
     JF_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 64));
     pk->allocs.push_back(*out);
@@ -710,14 +719,14 @@ template <class C> struct Plonk {
         if (cudaStreamCreateWithPriority(&pk->side, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
             cudaEventCreateWithFlags(&pk->ev_main, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&pk->ev_side, cudaEventDisableTiming) != cudaSuccess) {
-            delete pk;
+            release_pk(pk);
             return fail(ctx, JF_ERR_CUDA, "preprocess: cannot create the side stream");
         }
         int rc = preprocess_inner(ctx, pk, selector_evals, sigma_evals, k, wire_variables, pub_gate_ids);
         if (rc != JF_OK) {
             cudaStreamSynchronize(ctx->stream);
-            for (void *p : pk->allocs) cudaFree(p);
-            delete pk;
+            cudaStreamSynchronize(pk->side);
+            release_pk(pk);
             return rc;
         }
         *out = pk;
@@ -1314,14 +1323,8 @@ void jf_plonk_pk_free(jf_ctx *ctx, jf_plonk_pk *pk) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         if (pk->side) cudaStreamSynchronize(pk->side);
-        for (void *p : pk->allocs) cudaFree(p);
-    } else {
-        for (void *p : pk->allocs) cudaFree(p);
     }
-    if (pk->ev_main) cudaEventDestroy(pk->ev_main);
-    if (pk->ev_side) cudaEventDestroy(pk->ev_side);
-    if (pk->side) cudaStreamDestroy(pk->side);
-    delete pk;
+    release_pk(pk);
 }
 
 int jf_plonk_prove(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *witness, const uint64_t *blinders, int transcript_kind,
@@ -1329,8 +1332,16 @@ int jf_plonk_prove(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *witness, const 
     JF_GUARD(ctx);
     if (!pk || !witness || !blinders || !out) return fail(ctx, JF_ERR_INVALID_ARG, "plonk_prove: null argument");
     if (transcript_kind != 0 && transcript_kind != 1) return fail(ctx, JF_ERR_INVALID_ARG, "plonk_prove: unknown transcript");
-    if (pk->curve == JF_BN254) return Plonk<Bn254Plonk>::prove(ctx, pk, witness, blinders, transcript_kind, extra_msg, extra_len, out);
-    return Plonk<Bls12381Plonk>::prove(ctx, pk, witness, blinders, transcript_kind, extra_msg, extra_len, out);
+    const int rc = pk->curve == JF_BN254
+                       ? Plonk<Bn254Plonk>::prove(ctx, pk, witness, blinders, transcript_kind, extra_msg, extra_len, out)
+                       : Plonk<Bls12381Plonk>::prove(ctx, pk, witness, blinders, transcript_kind, extra_msg, extra_len, out);
+    if (rc != JF_OK) {
+        // an early return may leave kernels and copies queued against the key's scratch and the caller's buffers:
+        // drain both streams so the next call starts clean (the context keeps its stream and lane)
+        cudaStreamSynchronize(ctx->stream);
+        if (pk->side) cudaStreamSynchronize(pk->side);
+    }
+    return rc;
 }
 
 int jf_kzg_open(jf_ctx *ctx, const jf_srs *srs, const uint64_t *const *polys, const size_t *lens, size_t batch,
