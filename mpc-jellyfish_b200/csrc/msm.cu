@@ -278,7 +278,15 @@ template <class Fq> __device__ __forceinline__ Affine<Fq> load_affine(const Affi
     uint32_t *o = reinterpret_cast<uint32_t *>(&r);
 #pragma unroll
     for (int k = 0; k < WORDS / 4; k++) {
-        uint4 x = __ldg(q + k);
+        // A gathered table point is 64 (96) bytes at a random place of a ~1 GB table and nothing next to it is wanted: ask L2
+        // for 64-byte fills instead of the default 128.  Same kernel time, DRAM reads 2.05 -> 1.12 GB per 2^20 MSM
+        // (profiles/r2f_msm_kernels_full.md), which matters when the prover runs NTT passes beside the accumulation.
+        uint4 x;
+#ifdef __CUDA_ARCH__
+        asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "l"(q + k));
+#else
+        x = q[k];
+#endif
         o[4 * k] = x.x; o[4 * k + 1] = x.y; o[4 * k + 2] = x.z; o[4 * k + 3] = x.w;
     }
     return r;
