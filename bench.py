@@ -304,10 +304,12 @@ def ntt_leg(env):
     cpu = None
     if not args.no_cpu:
         x = host[0].copy()
+        env.cpu_leg()
         co.ntt(NTT_FIELD, x, NTT_LOG_N, False, off, threads=env.threads)   # warm the oracle's twiddle setup
         t0 = time.perf_counter()
         co.ntt(NTT_FIELD, x, NTT_LOG_N, False, off, threads=env.threads)
         dt = time.perf_counter() - t0
+        env.gpu_leg()
         cpu = {"value": n / dt / 1e6, "unit": "Melem/s", "cores": env.threads, "kind": "port",
                "sample": "1 coset NTT of 2^%d BN254 Fr elements, %d OpenMP threads, radix-2 restatement of ark-poly" % (NTT_LOG_N, env.threads)}
     return {
@@ -555,10 +557,36 @@ def _known_beta_commitment(co, scalars_canonical, beta):
     return co.fixed_base_mul("bn254", co.field_op("bn254_fr", "from_mont", ev[None, :]))[0]
 
 
+def _bind_to_gpu_numa_node(local):
+    """Pin this rank to the CPU cores next to its GPU (NVML's affinity mask) BEFORE it allocates page-locked memory, so that the
+    host side of every H2D transfer is NUMA-local: with 8 ranks reading their scalars at once, remote-socket buffers make the
+    upload (0.6 ms alone) the step that limits end-to-end scaling.  Returns (all cores this process may use, note)."""
+    try:
+        all_cores = sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None, "sched_getaffinity unavailable"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(all_cores) // 64) + 1)
+        near = [c for c in all_cores if (words[c // 64] >> (c % 64)) & 1]
+        if near:
+            os.sched_setaffinity(0, near)
+            _bind_to_gpu_numa_node.near = near
+            return all_cores, "bound to %d of %d cores near GPU %d (NVML affinity)" % (len(near), len(all_cores), local)
+        return all_cores, "NVML affinity mask empty: not bound"
+    except Exception as e:   # no NVML: stay unbound
+        return all_cores, "not bound (%s)" % type(e).__name__
+
+
 class _Env:
     """What every leg needs: the context, torch, the process group and the timing helpers."""
 
     def __init__(self, args):
+        self.all_cores, self.affinity_note = (None, "single rank: not bound")
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not args.no_bind:
+            self.all_cores, self.affinity_note = _bind_to_gpu_numa_node(int(os.environ.get("LOCAL_RANK", "0")))
         import torch
         import torch.distributed as dist
         import mpc_jellyfish_b200 as jf
@@ -578,7 +606,23 @@ class _Env:
         torch.cuda.set_stream(self.stream)
         self.ctx.set_stream(self.stream.cuda_stream)
         self.comm = jf.Comm.from_torch_distributed(self.ctx, transport=args.transport) if self.world > 1 else None
-        self.threads = _cpu_threads()
+        self.threads = len(self.all_cores) if self.all_cores else _cpu_threads()
+
+    def cpu_leg(self):
+        """the CPU baseline legs use every core of the box again (rank 0 only runs them, after the GPU legs)"""
+        if self.all_cores:
+            try:
+                os.sched_setaffinity(0, self.all_cores)
+            except Exception:
+                pass
+
+    def gpu_leg(self):
+        near = getattr(_bind_to_gpu_numa_node, "near", None)
+        if near:
+            try:
+                os.sched_setaffinity(0, near)
+            except Exception:
+                pass
 
     def barrier(self):
         if self.world > 1:
@@ -790,9 +834,11 @@ def run_cuda(args):
             # bounded CPU samples for the prove leg's component-sum baseline
             ns = 1 << 16
             pts16 = key.read(0, ns)
+            env.cpu_leg()
             t0 = time.perf_counter()
             co.msm("bn254", pts16, host_sets[0][:ns], env.threads)
             cpu_msm_ms = (time.perf_counter() - t0) * 1e3 * (n / ns)
+            env.gpu_leg()
             cpu_ntt = ntt["cpu_baseline"]["value"] if ntt and ntt.get("cpu_baseline") else None
         prove = prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream, cpu_msm_ms, cpu_ntt)
     mpc = None if args.no_mpc else mpc_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream)
@@ -826,6 +872,7 @@ def run_cuda(args):
     # ---- CPU baseline leg (oracle restatement on this box's cores; bounded sample) ------------------
     cpu = None
     if not args.no_cpu:
+        env.cpu_leg()
         log_s = 18
         ns = 1 << log_s
         pts = key.read(0, ns)
@@ -845,7 +892,7 @@ def run_cuda(args):
         "dtype": "u32 limbs (8-limb Montgomery mod 254-bit p, IMAD pipe)", "data": "synthetic",
         "config": cfg,
         "setup": {"window_bits": key.window_bits, "windows": W, "bucket_sets": 1, "key_build_s": round(t_key, 3),
-                  "transport": env.comm.transport if world > 1 else None,
+                  "transport": env.comm.transport if world > 1 else None, "cpu_affinity": env.affinity_note,
                   "l2": "inputs larger than L2: rotates %d scalar vectors (%d MB) and gathers from %d MB of window tables"
                         % (N_SETS, N_SETS * 32, (W * n * 64) >> 20)},
         "pairs_per_s": n * world / (ms_step * 1e-3),
@@ -914,6 +961,7 @@ def main():
     ap.add_argument("--no-mpc", action="store_true", help="skip the collaborative-prover share-wise leg (config 5 shape)")
     ap.add_argument("--no-prove", action="store_true", help="skip the 2^20-gate prove leg (first metric)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the size sweeps / strong-scaling legs (configs[1], configs[2])")
+    ap.add_argument("--no-bind", action="store_true", help="N > 1: do not bind each rank to the cores next to its GPU")
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "p2p"], help="exchange of the partial sums at N > 1")
     args = ap.parse_args()
     if args.warmup < 3:
