@@ -318,8 +318,11 @@ def append_vk_and_pub_input(tr, curve: Curve, vk: dict, pub_input: Sequence[int]
 # Circuit (TurboPlonk subset of `PlonkCircuit`)
 # ======================================================================================
 class Gate:
-    def __init__(self, name, q_lc=(0, 0, 0, 0), q_mul=(0, 0), q_hash=(0, 0, 0, 0), q_o=0, q_c=0, q_ecc=0):
+    def __init__(self, name, q_lc=(0, 0, 0, 0), q_mul=(0, 0), q_hash=(0, 0, 0, 0), q_o=0, q_c=0, q_ecc=0,
+                 q_lookup=0, q_dom_sep=0, table_key=0, table_dom_sep=0):
         self.name, self.q_lc, self.q_mul, self.q_hash, self.q_o, self.q_c, self.q_ecc = name, q_lc, q_mul, q_hash, q_o, q_c, q_ecc
+        # UltraPlonk (relation/src/gates/lookup.rs): lookup selector, domain separators and the table key of a LookupGate
+        self.q_lookup, self.q_dom_sep, self.table_key, self.table_dom_sep = q_lookup, q_dom_sep, table_key, table_dom_sep
 
     def selectors(self) -> List[int]:
         return list(self.q_lc) + list(self.q_mul) + list(self.q_hash) + [self.q_o, self.q_c, self.q_ecc]
@@ -331,19 +334,58 @@ def SubtractionGate(p): return Gate("sub", q_lc=(1, p - 1, 0, 0), q_o=1)
 def MultiplicationGate(): return Gate("mul", q_mul=(1, 0), q_o=1)
 def EqualityGate(p): return Gate("eq", q_lc=(1, p - 1, 0, 0), q_o=1)
 def IoGate(): return Gate("io", q_o=1)
+def ConstantAdditionGate(c): return Gate("const_add", q_lc=(1, 0, 0, 0), q_c=c, q_o=1)
+def LookupGate(q_dom_sep, table_dom_sep, table_key):
+    return Gate("lookup", q_lookup=1, q_dom_sep=q_dom_sep, table_dom_sep=table_dom_sep, table_key=table_key)
 def PaddingGate(): return Gate("pad")  # all selectors zero in this fork (relation/src/gates/mod.rs)
 
 
+RANGE_WIRE_ID = 5  # relation/src/constraint_system.rs:77-85
+
+
 class PlonkCircuit:
-    def __init__(self, field: Field = pyref.BN254_FR):
+    def __init__(self, field: Field = pyref.BN254_FR, range_bit_len: Optional[int] = None):
+        """`new_turbo_plonk()`; with `range_bit_len`: `new_ultra_plonk(range_bit_len)` (constraint_system.rs:193-240):
+        a sixth wire type (the range / lookup wire), the q_lookup selector, the range table {0..2^bits-1} and
+        key-value tables inserted with `create_table_and_lookup_variables`."""
         self.f = field
+        self.range_bit_len = range_bit_len
+        self.ultra = range_bit_len is not None
+        self.nw = NUM_WIRE_TYPES + (1 if self.ultra else 0)
         self.witness = [0, 1]
         self.gates: List[Gate] = []
-        self.wire_variables: List[List[int]] = [[] for _ in range(NUM_WIRE_TYPES)]
+        self.wire_variables: List[List[int]] = [[] for _ in range(NUM_WIRE_TYPES + 1)]
         self.pub_input_gate_ids: List[int] = []
+        self.num_table_elems = 0
+        self.table_gate_ids: List[Tuple[int, int]] = []
         self.n = 1  # eval domain size; 1 == not finalized
         self.enforce_constant(0, 0)
         self.enforce_constant(1, 1)
+
+    # -- UltraPlonk construction -----------------------------------------------------------------------
+    def range_size(self) -> int:
+        return 1 << self.range_bit_len
+
+    def add_range_check_variable(self, var: int):
+        assert self.ultra and self.n == 1
+        self.wire_variables[RANGE_WIRE_ID].append(var)
+
+    def add_constant(self, x: int, c: int) -> int:
+        y = self.create_variable(self.witness[x] + c)
+        self.insert_gate([x, 1, 0, 0, y], ConstantAdditionGate(c % self.f.p))
+        return y
+
+    def create_table_and_lookup_variables(self, lookup_vars, table_vars):
+        """relation/src/gadgets/ultraplonk/lookup_table.rs:21-57"""
+        assert self.ultra
+        cnt = max(len(lookup_vars), len(table_vars))
+        self.table_gate_ids.append((self.num_gates(), cnt))
+        table_ctr = len(self.table_gate_ids)
+        for i in range(cnt):
+            q_dom_sep, key, v0, v1 = (table_ctr,) + tuple(lookup_vars[i]) if i < len(lookup_vars) else (0, 0, 0, 0)
+            t_dom_sep, t_key, t0, t1 = (table_ctr, i) + tuple(table_vars[i]) if i < len(table_vars) else (0, 0, 0, 0)
+            self.insert_gate([key, v0, v1, t0, t1], LookupGate(q_dom_sep, t_dom_sep, t_key))
+        self.num_table_elems += cnt
 
     # -- construction ------------------------------------------------------------------------
     def zero(self): return 0
@@ -395,13 +437,25 @@ class PlonkCircuit:
     def public_input(self) -> List[int]:
         return [self.witness[self.wire_variables[GATE_WIDTH][g]] for g in self.pub_input_gate_ids]
 
-    # -- finalize (TurboPlonk, no link groups) ---------------------------------------------------
+    # -- finalize (TurboPlonk without link groups; UltraPlonk) ------------------------------------------
     def finalize_for_arithmetization(self):
         if self.n != 1:
             return
+        if not self.ultra:
+            n_gates = self.num_gates()  # CircuitLayout::circuit_size: next_power_of_two(n_gates)
+        else:  # range gates and lookup gates need separate slots (constraint_system.rs:981-987)
+            n_gates = max(self.num_gates(),
+                          max(self.range_size(), len(self.wire_variables[RANGE_WIRE_ID])) + self.num_table_elems + 1)
         n = 1
-        while n < self.num_gates():  # CircuitLayout::circuit_size: next_power_of_two(n_gates)
+        while n < n_gates:
             n <<= 1
+        if self.ultra:
+            # pad (:675-686) first, then rearrange (:630-666)
+            while len(self.gates) < n:
+                self.gates.append(PaddingGate())
+            for j in range(self.nw):
+                w = self.wire_variables[j]
+                w.extend([0] * (n - len(w)))
         # rearrange_gates: io gates to the front (constraint_system.rs:630-645)
         for gate_id, io_gate_id in enumerate(list(self.pub_input_gate_ids)):
             if io_gate_id > gate_id:
@@ -410,15 +464,27 @@ class PlonkCircuit:
                     w = self.wire_variables[j]
                     w[gate_id], w[io_gate_id] = w[io_gate_id], w[gate_id]
                 self.pub_input_gate_ids[gate_id] = gate_id
-        # pad with PaddingGate / variable 0 (linkable_circuit.rs:294-314)
-        while len(self.gates) < n:
-            self.gates.append(PaddingGate())
-            for j in range(NUM_WIRE_TYPES):
-                self.wire_variables[j].append(0)
+        if self.ultra:
+            # lookup gates to the rear, relative order kept, never the very last slot (:647-664)
+            cur = n - 2
+            for table_gate_id, table_size in reversed(self.table_gate_ids):
+                for gate_id in reversed(range(table_gate_id, table_gate_id + table_size)):
+                    if gate_id < cur:
+                        self.gates[gate_id], self.gates[cur] = self.gates[cur], self.gates[gate_id]
+                        for j in range(NUM_WIRE_TYPES):
+                            w = self.wire_variables[j]
+                            w[gate_id], w[cur] = w[cur], w[gate_id]
+                        cur -= 1
+        else:
+            # pad with PaddingGate / variable 0 (linkable_circuit.rs:294-314)
+            while len(self.gates) < n:
+                self.gates.append(PaddingGate())
+                for j in range(NUM_WIRE_TYPES):
+                    self.wire_variables[j].append(0)
         self.n = n
         self.domain = Radix2Domain(self.f, n)
         self._compute_wire_permutation()
-        self.k = compute_coset_representatives(self.f, NUM_WIRE_TYPES, n)
+        self.k = compute_coset_representatives(self.f, self.nw, n)
         p = self.f.p
         g = self.domain.group_gen
         elems = [1] * n
@@ -429,10 +495,10 @@ class PlonkCircuit:
     def _compute_wire_permutation(self):
         n = self.n
         var_map: List[List[Tuple[int, int]]] = [[] for _ in range(self.num_vars())]
-        for wire_id in range(NUM_WIRE_TYPES):
+        for wire_id in range(self.nw):
             for gate_id, var in enumerate(self.wire_variables[wire_id]):
                 var_map[var].append((wire_id, gate_id))
-        self.wire_permutation = [(0, 0)] * (NUM_WIRE_TYPES * n)
+        self.wire_permutation = [(0, 0)] * (self.nw * n)
         for wires in var_map:
             if wires:
                 cyc = wires + [wires[0]]
@@ -441,18 +507,78 @@ class PlonkCircuit:
 
     # -- arithmetization inputs ----------------------------------------------------------------------
     def selector_evals(self) -> List[List[int]]:
-        cols = [[0] * self.n for _ in range(N_SELECTORS)]
+        """all_selectors (constraint_system.rs:890-905): the 13 TurboPlonk columns, then q_lookup when lookups are supported"""
+        cols = [[0] * self.n for _ in range(N_SELECTORS + (1 if self.ultra else 0))]
         for i, g in enumerate(self.gates):
             for s, v in enumerate(g.selectors()):
                 cols[s][i] = v % self.f.p
+            if self.ultra:
+                cols[N_SELECTORS][i] = g.q_lookup % self.f.p
         return cols
+
+    # -- Plookup arithmetization (constraint_system.rs:1261-1492) ------------------------------------------
+    def q_lookup(self): return [g.q_lookup % self.f.p for g in self.gates]
+    def q_dom_sep(self): return [g.q_dom_sep % self.f.p for g in self.gates]
+    def table_key_vec(self): return [g.table_key % self.f.p for g in self.gates]
+    def table_dom_sep_vec(self): return [g.table_dom_sep % self.f.p for g in self.gates]
+
+    def range_table(self) -> List[int]:
+        assert self.n >= self.range_size(), "Domain size < range size"
+        return list(range(self.range_size())) + [0] * (self.n - self.range_size())
+
+    def _wit(self, wire: int, i: int) -> int:
+        return self.witness[self.wire_variables[wire][i]]
+
+    def merged_lookup_table(self, tau: int) -> List[int]:
+        p = self.f.p
+        rt, tk, td, ql = self.range_table(), self.table_key_vec(), self.table_dom_sep_vec(), self.q_lookup()
+        return [(rt[i] + ql[i] * tau % p * ((td[i] + tau * ((tk[i] + tau * ((self._wit(3, i) + tau * self._wit(4, i)) % p)) % p)) % p)) % p
+                for i in range(self.n)]
+
+    def merged_lookup_wire_value(self, tau: int, i: int, ql, qd) -> int:
+        p = self.f.p
+        return (self._wit(RANGE_WIRE_ID, i)
+                + ql[i] * tau % p * ((qd[i] + tau * ((self._wit(0, i) + tau * ((self._wit(1, i) + tau * self._wit(2, i)) % p)) % p)) % p)) % p
+
+    def lookup_sorted_vec(self, tau: int, merged_table: Sequence[int]) -> List[int]:
+        """compute_lookup_sorted_vec_polynomials (:1370-1418): the lookup values merged into the table, in table order."""
+        n = self.n
+        ql, qd = self.q_lookup(), self.q_dom_sep()
+        counts: dict = {}
+        for i in range(n - 1):
+            e = self.merged_lookup_wire_value(tau, i, ql, qd)
+            counts[e] = counts.get(e, 0) + 1
+        out = []
+        for e in merged_table:
+            if e in counts:
+                out.extend([e] * (1 + counts.pop(e)))
+            else:
+                out.append(e)
+        if len(out) != 2 * n - 1:
+            raise ValueError("The sorted vector has wrong length, some lookup variables might be outside the table")
+        return out
+
+    def lookup_prod_vec(self, tau: int, beta: int, gamma: int, merged_table: Sequence[int], sorted_vec: Sequence[int]) -> List[int]:
+        """compute_lookup_prod_polynomial (:1311-1368), evaluations on the domain"""
+        p, n = self.f.p, self.n
+        ql, qd = self.q_lookup(), self.q_dom_sep()
+        bp1 = (1 + beta) % p
+        gb = gamma * bp1 % p
+        prod = [1]
+        for j in range(n - 2):
+            lw = self.merged_lookup_wire_value(tau, j, ql, qd)
+            a = bp1 * ((gamma + lw) % p) % p * ((gb + merged_table[j] + beta * merged_table[j + 1]) % p) % p
+            b = (gb + sorted_vec[j] + beta * sorted_vec[j + 1]) % p * ((gb + sorted_vec[n - 1 + j] + beta * sorted_vec[n + j]) % p) % p
+            prod.append(prod[-1] * a % p * pow(b, -1, p) % p)
+        prod.append(1)
+        return prod
 
     def extended_permutation(self) -> List[int]:
         n = self.n
         return [self.extended_id_permutation[w * n + g] for (w, g) in self.wire_permutation]
 
     def wire_values(self) -> List[List[int]]:
-        return [[self.witness[v] for v in self.wire_variables[j]] for j in range(NUM_WIRE_TYPES)]
+        return [[self.witness[v] for v in self.wire_variables[j]] for j in range(self.nw)]
 
     def check_satisfiability(self) -> bool:
         p = self.f.p
@@ -466,6 +592,17 @@ class PlonkCircuit:
                  - g.q_o * w[4]) % p
             if v:
                 return False
+        if self.ultra:  # constraint_system.rs:405-449
+            nrange = len(self.wire_variables[RANGE_WIRE_ID])
+            if any(self._wit(RANGE_WIRE_ID, i) >= self.range_size() for i in range(nrange)):
+                return False
+            table = {(0, 0, 0, 0)}
+            for i, g in enumerate(self.gates):
+                if g.q_lookup:
+                    table.add((g.table_dom_sep % p, g.table_key % p, self._wit(3, i), self._wit(4, i)))
+            for i, g in enumerate(self.gates):
+                if g.q_lookup and (g.q_dom_sep % p, self._wit(0, i), self._wit(1, i), self._wit(2, i)) not in table:
+                    return False
         return True
 
 
@@ -501,9 +638,9 @@ def gen_circuit_all_selectors(m: int, field: Field = pyref.BN254_FR) -> PlonkCir
     return cs
 
 
-def gen_circuit_for_bench(num_gates: int, field: Field = pyref.BN254_FR) -> PlonkCircuit:
-    """plonk/benches/bench.rs:29-46 (TurboPlonk)."""
-    cs = PlonkCircuit(field)
+def gen_circuit_for_bench(num_gates: int, field: Field = pyref.BN254_FR, ultra: bool = False) -> PlonkCircuit:
+    """plonk/benches/bench.rs:29-46 (`new_turbo_plonk()` / `new_ultra_plonk(RANGE_BIT_LEN = 8)`)."""
+    cs = PlonkCircuit(field, 8 if ultra else None)
     a = cs.zero()
     for _ in range(num_gates - 10):
         a = cs.add(a, cs.one())
@@ -511,9 +648,9 @@ def gen_circuit_for_bench(num_gates: int, field: Field = pyref.BN254_FR) -> Plon
     return cs
 
 
-def gen_circuit_for_test(m: int, a0: int, field: Field = pyref.BN254_FR) -> PlonkCircuit:
-    """plonk/src/proof_system/snark.rs:681-744 (TurboPlonk branch)."""
-    cs = PlonkCircuit(field)
+def gen_circuit_for_test(m: int, a0: int, field: Field = pyref.BN254_FR, ultra: bool = False) -> PlonkCircuit:
+    """plonk/src/proof_system/snark.rs:681-744 (both branches; UltraPlonk: range_bit_len = 5, a0 <= m + 1)."""
+    cs = PlonkCircuit(field, 5 if ultra else None)
     a = [cs.create_variable(i) for i in range(a0, a0 + 4 * m)]
     b = [cs.create_public_variable(m * 2), cs.create_public_variable(a0 * 2 + m * 4 - 1)]
     c = cs.create_public_variable((cs.witness[b[1]] + cs.witness[a[0]]) * (cs.witness[b[1]] - cs.witness[a[0]]))
@@ -526,6 +663,18 @@ def gen_circuit_for_test(m: int, a0: int, field: Field = pyref.BN254_FR) -> Plon
     m1 = cs.sub(b[1], a[0])
     cs.mul_gate(p1, m1, c)
     cs.enforce_constant(b[0], m * 2)
+    if ultra:
+        # range gates: a_i in {0..31} for i < m, b0 in the table; one key-value table with two lookups (:722-738)
+        for var in a[:m]:
+            cs.add_range_check_variable(var)
+        cs.add_range_check_variable(b[0])
+        table_vars = [(a[0], a[2]), (a[1], a[3]), (b[0], a[0])]
+        key0 = cs.one()
+        key1 = cs.create_variable(2)
+        two_m = cs.create_public_variable(m * 2)
+        a1 = cs.add_constant(a[0], 1)
+        a3 = cs.add_constant(a[0], 3)
+        cs.create_table_and_lookup_variables([(key0, a1, a3), (key1, two_m, a[0])], table_vars)
     cs.finalize_for_arithmetization()
     return cs
 
@@ -617,10 +766,11 @@ class _Backend:
 # ======================================================================================
 # preprocess / prove / verify
 # ======================================================================================
-def quotient_domain_size(n: int) -> int:
-    """domain_size_ratio (plonk/src/constants.rs:18-20) then GeneralEvaluationDomain::new -> radix 2."""
+def quotient_domain_size(n: int, num_wire_types: int = NUM_WIRE_TYPES) -> int:
+    """domain_size_ratio (plonk/src/constants.rs:18-20) then GeneralEvaluationDomain::new -> radix 2 (prover.rs:54-62)."""
+    ratio = (num_wire_types * (n + 1) + 2) // n + 1
     m = 1
-    while m < n * (NUM_WIRE_TYPES + 1):
+    while m < n * ratio:
         m <<= 1
     return m
 
@@ -638,43 +788,96 @@ def gen_srs(curve: Curve, beta: int, max_degree: int):
 
 
 def preprocess(curve: Curve, srs, cs: PlonkCircuit) -> dict:
-    """snark.rs:529-611: selector / sigma polynomials (ifft) and their commitments."""
+    """snark.rs:529-611: selector / sigma (and, for UltraPlonk, the four Plookup table) polynomials (ifft) and their commitments."""
     be = _Backend(curve)
     n = cs.n
     log_n = n.bit_length() - 1
     srs_limbs, srs_points = srs
     selectors = [_strip(be.ntt(col, log_n, True)) for col in cs.selector_evals()]
     ext = cs.extended_permutation()
-    sigmas = [_strip(be.ntt(ext[i * n:(i + 1) * n], log_n, True)) for i in range(NUM_WIRE_TYPES)]
+    sigmas = [_strip(be.ntt(ext[i * n:(i + 1) * n], log_n, True)) for i in range(cs.nw)]
     vk = {
         "domain_size": n, "num_inputs": cs.num_inputs(),
         "selector_comms": [be.commit(srs_limbs, srs_points, s) for s in selectors],
         "sigma_comms": [be.commit(srs_limbs, srs_points, s) for s in sigmas],
-        "k": list(cs.k),
+        "k": list(cs.k), "plookup": None,
     }
-    return {"selectors": selectors, "sigmas": sigmas, "vk": vk, "srs": srs, "n": n}
+    pk = {"selectors": selectors, "sigmas": sigmas, "vk": vk, "srs": srs, "n": n, "plookup": None}
+    if cs.ultra:
+        lk = {"range_table_poly": _strip(be.ntt(cs.range_table(), log_n, True)),
+              "key_table_poly": _strip(be.ntt(cs.table_key_vec(), log_n, True)),
+              "table_dom_sep_poly": _strip(be.ntt(cs.table_dom_sep_vec(), log_n, True)),
+              "q_dom_sep_poly": _strip(be.ntt(cs.q_dom_sep(), log_n, True))}
+        pk["plookup"] = lk
+        vk["plookup"] = {"range_table_comm": be.commit(srs_limbs, srs_points, lk["range_table_poly"]),
+                         "key_table_comm": be.commit(srs_limbs, srs_points, lk["key_table_poly"]),
+                         "table_dom_sep_comm": be.commit(srs_limbs, srs_points, lk["table_dom_sep_poly"]),
+                         "q_dom_sep_comm": be.commit(srs_limbs, srs_points, lk["q_dom_sep_poly"])}
+    return pk
+
+
+def num_blinders(cs_or_nw, ultra: Optional[bool] = None) -> int:
+    """field elements `prove` draws from the prng: 2 per wire polynomial, 3 for z, nw - 1 split-quotient randomizers and, for
+    UltraPlonk, 3 each for h1, h2 and the lookup product (17 / 29)."""
+    nw = cs_or_nw if isinstance(cs_or_nw, int) else cs_or_nw.nw
+    ultra = (nw == 6) if ultra is None else ultra
+    return 2 * nw + 3 + (nw - 1) + (9 if ultra else 0)
+
+
+def _merged_table(p, tau, rng, key, ql, w3, w4, tds):
+    """eval_merged_table (structs.rs:926-939)"""
+    return (rng + ql * tau % p * ((tds + tau * ((key + tau * ((w3 + tau * w4) % p)) % p)) % p)) % p
+
+
+def _merged_lookup(p, tau, wr, w0, w1, w2, ql, qds):
+    """eval_merged_lookup_witness (structs.rs:943-956)"""
+    return (wr + ql * tau % p * ((qds + tau * ((w0 + tau * ((w1 + tau * w2) % p)) % p)) % p)) % p
+
+
+PLOOKUP_EVAL_FIELDS = ["range_table_eval", "key_table_eval", "table_dom_sep_eval", "q_dom_sep_eval", "h_1_eval", "q_lookup_eval",
+                       "prod_next_eval", "range_table_next_eval", "key_table_next_eval", "table_dom_sep_next_eval", "h_1_next_eval",
+                       "h_2_next_eval", "q_lookup_next_eval", "w_3_next_eval", "w_4_next_eval"]  # structs.rs:496-541, declaration order
+
+
+def _plookup_evals_vec(e):       # structs.rs:545-554
+    return [e["range_table_eval"], e["key_table_eval"], e["h_1_eval"], e["q_lookup_eval"], e["table_dom_sep_eval"], e["q_dom_sep_eval"]]
+
+
+def _plookup_next_evals_vec(e):  # structs.rs:557-569
+    return [e["prod_next_eval"], e["range_table_next_eval"], e["key_table_next_eval"], e["h_1_next_eval"], e["h_2_next_eval"],
+            e["q_lookup_next_eval"], e["w_3_next_eval"], e["w_4_next_eval"], e["table_dom_sep_next_eval"]]
+
+
+def _append_plookup_evals(tr, fr, e):
+    """transcript/mod.rs:168-201: only six of the fifteen evaluations enter the transcript"""
+    for label, key in ((b"lookup_table_eval", "range_table_eval"), (b"h_1_eval", "h_1_eval"), (b"prod_next_eval", "prod_next_eval"),
+                       (b"lookup_table_next_eval", "range_table_next_eval"), (b"h_1_next_eval", "h_1_next_eval"),
+                       (b"h_2_next_eval", "h_2_next_eval")):
+        tr.append_message(label, ser_fr(fr, e[key]))
 
 
 def prove(curve: Curve, cs: PlonkCircuit, pk: dict, blinders: Sequence[int], transcript: str = "solidity",
           extra_msg: Optional[bytes] = None) -> dict:
-    """batch_prove_internal for one TurboPlonk instance (snark.rs:201-469).  `blinders`: the 17
-    field elements the reference draws from its prng, in consumption order:
-    5 x (b0, b1) for the wire polys, (b0, b1, b2) for z, 4 split-quotient randomizers."""
+    """batch_prove_internal for ONE instance (snark.rs:201-469), TurboPlonk or UltraPlonk.  `blinders`: the field elements the
+    reference draws from its prng, in consumption order: nw x (b0, b1) for the wire polynomials, [3 for h1,
+    3 for h2,] 3 for z, [3 for the lookup product,] nw - 1 split-quotient randomizers: 17 for TurboPlonk, 29 for UltraPlonk."""
     fr, p = curve.fr, curve.fr.p
     be = _Backend(curve)
     n = pk["n"]
+    nw, ultra = cs.nw, cs.ultra
     log_n = n.bit_length() - 1
-    m = quotient_domain_size(n)
+    m = quotient_domain_size(n, nw)
     log_m = m.bit_length() - 1
     ratio = m // n
     dom = Radix2Domain(fr, n)
     qdom = Radix2Domain(fr, m)
     g = dom.group_gen
+    g_inv = pow(g, -1, p)
     srs_limbs, srs_points = pk["srs"]
     vk = pk["vk"]
     k = vk["k"]
     bl = list(blinders)
-    assert len(bl) == 17
+    assert len(bl) == num_blinders(nw, ultra)
 
     def commit(c):
         return be.commit(srs_limbs, srs_points, c)
@@ -704,7 +907,16 @@ def prove(curve: Curve, cs: PlonkCircuit, pk: dict, blinders: Sequence[int], tra
     pi_poly = _strip(be.ntt(pi_vec, log_n, True))
     for c in wires_comms:
         tr.append_message(b"witness_poly_comms", ser_g1(curve, c))
-    tau = tr.get_and_append_challenge(fr, b"tau")  # noqa: F841  (squeezed even without Plookup)
+
+    # ---- round 1.5 (Plookup; the challenge is squeezed even without it) -------------------------------
+    tau = tr.get_and_append_challenge(fr, b"tau")
+    if ultra:
+        merged_table = cs.merged_lookup_table(tau)
+        sorted_vec = cs.lookup_sorted_vec(tau, merged_table)
+        h_polys = [mask(_strip(be.ntt(sorted_vec[:n], log_n, True)), 2), mask(_strip(be.ntt(sorted_vec[n - 1:], log_n, True)), 2)]
+        h_comms = [commit(h) for h in h_polys]
+        for c in h_comms:
+            tr.append_message(b"h_poly_comms", ser_g1(curve, c))
 
     # ---- round 2 ---------------------------------------------------------------------------------
     beta = tr.get_and_append_challenge(fr, b"beta")
@@ -713,7 +925,7 @@ def prove(curve: Curve, cs: PlonkCircuit, pk: dict, blinders: Sequence[int], tra
     prod = [1]
     for j in range(n - 1):
         a = b = 1
-        for i in range(NUM_WIRE_TYPES):
+        for i in range(nw):
             tmp = (wvals[i][j] + gamma) % p
             a = a * (tmp + beta * ext_id[i * n + j]) % p
             pi_, pj_ = wperm[i * n + j]
@@ -722,6 +934,12 @@ def prove(curve: Curve, cs: PlonkCircuit, pk: dict, blinders: Sequence[int], tra
     z_poly = mask(_strip(be.ntt(prod, log_n, True)), 2)
     z_comm = commit(z_poly)
     tr.append_message(b"perm_poly_comms", ser_g1(curve, z_comm))
+
+    # ---- round 2.5 (Plookup product) -------------------------------------------------------------------
+    if ultra:
+        pl_poly = mask(_strip(be.ntt(cs.lookup_prod_vec(tau, beta, gamma, merged_table, sorted_vec), log_n, True)), 2)
+        pl_comm = commit(pl_poly)
+        tr.append_message(b"plookup_poly_comms", ser_g1(curve, pl_comm))
 
     # ---- round 3 ---------------------------------------------------------------------------------
     alpha = tr.get_and_append_challenge(fr, b"alpha")
@@ -733,60 +951,100 @@ def prove(curve: Curve, cs: PlonkCircuit, pk: dict, blinders: Sequence[int], tra
     w_c = [cfft(wp) for wp in wire_polys]
     z_c = cfft(z_poly)
     pi_c = cfft(pi_poly)
+    if ultra:
+        lk = pk["plookup"]
+        tds_c, qds_c = cfft(lk["table_dom_sep_poly"]), cfft(lk["q_dom_sep_poly"])
+        rng_c, key_c = cfft(lk["range_table_poly"]), cfft(lk["key_table_poly"])
+        h1_c, h2_c, pl_c = cfft(h_polys[0]), cfft(h_polys[1]), cfft(pl_poly)
+        ql_c = sel_c[N_SELECTORS]
     alpha2 = alpha * alpha % p
+    alpha3 = alpha2 * alpha % p
     n_f = n % p
+    bp1 = (1 + beta) % p
+    gb = gamma * bp1 % p
     quot = [0] * m
     wq = qdom.group_gen
     x = G  # eval point g * w_m^i
     for i in range(m):
-        w = [w_c[j][i] for j in range(5)]
+        inx = (i + ratio) % m
+        w = [w_c[j][i] for j in range(nw)]
         q = [sel_c[s][i] for s in range(N_SELECTORS)]
         t_circ = (q[11] + pi_c[i] + q[0] * w[0] + q[1] * w[1] + q[2] * w[2] + q[3] * w[3]
                   + q[4] * w[0] * w[1] + q[5] * w[2] * w[3] + q[12] * w[0] * w[1] * w[2] * w[3] * w[4]
                   + q[6] * pow(w[0], 5, p) + q[7] * pow(w[1], 5, p) + q[8] * pow(w[2], 5, p) + q[9] * pow(w[3], 5, p)
                   - q[10] * w[4]) % p
-        zx, zxw = z_c[i], z_c[(i + ratio) % m]
+        zx, zxw = z_c[i], z_c[inx]
         r1 = zx
         r2 = zxw
-        for j in range(5):
+        for j in range(nw):
             r1 = r1 * (w[j] + k[j] * x % p * beta + gamma) % p
             r2 = r2 * (w[j] + sig_c[j][i] * beta + gamma) % p
-        t_perm1 = alpha * (r1 - r2) % p
-        t_perm2 = alpha2 * (zx - 1) % p * pow(n_f * (x - 1) % p, -1, p) % p
-        quot[i] = ((t_circ + t_perm1) * z_h_inv[i % ratio] + t_perm2) % p
+        t1 = (t_circ + alpha * (r1 - r2)) % p
+        t2 = alpha2 * (zx - 1) % p * pow(n_f * (x - 1) % p, -1, p) % p
+        if ultra:  # compute_quotient_plookup_contribution (prover.rs:773-888)
+            lag_n = g_inv * pow(n_f * (x - g_inv) % p, -1, p) % p
+            lag_1 = pow(n_f * (x - 1) % p, -1, p)
+            mt_x = _merged_table(p, tau, rng_c[i], key_c[i], ql_c[i], w[3], w[4], tds_c[i])
+            mt_xw = _merged_table(p, tau, rng_c[inx], key_c[inx], ql_c[inx], w_c[3][inx], w_c[4][inx], tds_c[inx])
+            ml_x = _merged_lookup(p, tau, w[5], w[0], w[1], w[2], ql_c[i], qds_c[i])
+            ap = alpha3
+            t2 = (t2 + ap * ((h1_c[i] - h2_c[inx]) * lag_n % p)) % p
+            ap = ap * alpha % p
+            t2 = (t2 + ap * ((pl_c[i] - 1) * lag_1 % p)) % p
+            ap = ap * alpha % p
+            t2 = (t2 + ap * ((pl_c[i] - 1) * lag_n % p)) % p
+            ap = ap * alpha % p
+            term = (x - g_inv) * (pl_c[i] * bp1 % p * ((gamma + ml_x) % p) % p * ((gb + mt_x + beta * mt_xw) % p)
+                                  - pl_c[inx] * ((gb + h1_c[i] + beta * h1_c[inx]) % p) % p * ((gb + h2_c[i] + beta * h2_c[inx]) % p)) % p
+            t1 = (t1 + ap * term) % p
+        quot[i] = (t1 * z_h_inv[i % ratio] + t2) % p
         x = x * wq % p
     quot_poly = _strip(be.ntt(quot, log_m, True, G))
-    expected_degree = NUM_WIRE_TYPES * (n + 1) + 2
+    expected_degree = nw * (n + 1) + 2
     if len(quot_poly) - 1 != expected_degree:
         raise ValueError("WrongQuotientPolyDegree(%d, %d)" % (len(quot_poly) - 1, expected_degree))
     split = []
-    for i in range(NUM_WIRE_TYPES):
-        end = (i + 1) * (n + 2) if i < NUM_WIRE_TYPES - 1 else len(quot_poly)
+    for i in range(nw):
+        end = (i + 1) * (n + 2) if i < nw - 1 else len(quot_poly)
         split.append(_strip(quot_poly[i * (n + 2):end]))
     last = 0
-    for i in range(NUM_WIRE_TYPES - 1):
+    for i in range(nw - 1):
         now = bl.pop(0)
         split[i][0] = (split[i][0] - last) % p
         assert len(split[i]) == n + 2
         split[i].append(now)
         last = now
     split[-1][0] = (split[-1][0] - last) % p
-    split_comms = [commit(s) for s in split]
+    split_comms = [commit(sp) for sp in split]
     for c in split_comms:
         tr.append_message(b"quot_poly_comms", ser_g1(curve, c))
 
     # ---- round 4 ---------------------------------------------------------------------------------
     zeta = tr.get_and_append_challenge(fr, b"zeta")
+    zg = zeta * g % p
     wires_evals = [_poly_eval(p, wp, zeta) for wp in wire_polys]
-    sigma_evals = [_poly_eval(p, s, zeta) for s in pk["sigmas"][:NUM_WIRE_TYPES - 1]]
-    perm_next_eval = _poly_eval(p, z_poly, zeta * g % p)
+    sigma_evals = [_poly_eval(p, sg, zeta) for sg in pk["sigmas"][:nw - 1]]
+    perm_next_eval = _poly_eval(p, z_poly, zg)
     for e in wires_evals:
         tr.append_message(b"wire_evals", ser_fr(fr, e))
     for e in sigma_evals:
         tr.append_message(b"wire_sigma_evals", ser_fr(fr, e))
     tr.append_message(b"perm_next_eval", ser_fr(fr, perm_next_eval))
+    plookup_evals = None
+    if ultra:  # round 4.5: compute_plookup_evaluations (prover.rs:239-297)
+        qlp = pk["selectors"][N_SELECTORS]
+        plookup_evals = {
+            "range_table_eval": _poly_eval(p, lk["range_table_poly"], zeta), "key_table_eval": _poly_eval(p, lk["key_table_poly"], zeta),
+            "h_1_eval": _poly_eval(p, h_polys[0], zeta), "q_lookup_eval": _poly_eval(p, qlp, zeta),
+            "table_dom_sep_eval": _poly_eval(p, lk["table_dom_sep_poly"], zeta), "q_dom_sep_eval": _poly_eval(p, lk["q_dom_sep_poly"], zeta),
+            "prod_next_eval": _poly_eval(p, pl_poly, zg), "range_table_next_eval": _poly_eval(p, lk["range_table_poly"], zg),
+            "key_table_next_eval": _poly_eval(p, lk["key_table_poly"], zg), "h_1_next_eval": _poly_eval(p, h_polys[0], zg),
+            "h_2_next_eval": _poly_eval(p, h_polys[1], zg), "q_lookup_next_eval": _poly_eval(p, qlp, zg),
+            "w_3_next_eval": _poly_eval(p, wire_polys[3], zg), "w_4_next_eval": _poly_eval(p, wire_polys[4], zg),
+            "table_dom_sep_next_eval": _poly_eval(p, lk["table_dom_sep_poly"], zg)}
+        _append_plookup_evals(tr, fr, plookup_evals)
 
-    # linearization polynomial (snark.rs:419-440; prover.rs:339-360,963-1034)
+    # linearization polynomial (snark.rs:419-440; prover.rs:302-360,963-1113)
     vanish = (pow(zeta, n, p) - 1) % p
     zeta_n2 = (vanish + 1) * zeta % p * zeta % p
     r_quot = list(split[0])
@@ -805,15 +1063,32 @@ def prove(curve: Curve, cs: PlonkCircuit, pk: dict, blinders: Sequence[int], tra
     r_circ = _poly_add(p, r_circ, sel[11])
     lagrange_1 = vanish * pow(n_f * (zeta - 1) % p, -1, p) % p
     c1 = alpha
-    for j in range(5):
+    for j in range(nw):
         c1 = c1 * (we[j] + beta * k[j] % p * zeta + gamma) % p
     c1 = (c1 + alpha2 * lagrange_1) % p
     r_perm = _poly_scale(p, z_poly, c1)
     c2 = alpha * beta % p * perm_next_eval % p
-    for j in range(4):
+    for j in range(nw - 1):
         c2 = c2 * (we[j] + beta * sigma_evals[j] + gamma) % p
-    r_perm = _poly_add(p, r_perm, _poly_scale(p, pk["sigmas"][4], (-c2) % p))
-    lin = _poly_add(p, lin, _poly_scale(p, _poly_add(p, r_circ, r_perm), 1))  # alpha_base = 1
+    r_perm = _poly_add(p, r_perm, _poly_scale(p, pk["sigmas"][nw - 1], (-c2) % p))
+    non_quot = _poly_add(p, r_circ, r_perm)
+    if ultra:  # compute_lin_poly_plookup_contribution (prover.rs:1037-1113)
+        pe = plookup_evals
+        alpha4 = alpha2 * alpha2 % p
+        alpha5, alpha6 = alpha4 * alpha % p, alpha4 * alpha2 % p
+        lagrange_n = vanish * g_inv % p * pow(n_f * (zeta - g_inv) % p, -1, p) % p
+        mt = _merged_table(p, tau, pe["range_table_eval"], pe["key_table_eval"], pe["q_lookup_eval"], we[3], we[4], pe["table_dom_sep_eval"])
+        mtn = _merged_table(p, tau, pe["range_table_next_eval"], pe["key_table_next_eval"], pe["q_lookup_next_eval"], pe["w_3_next_eval"],
+                            pe["w_4_next_eval"], pe["table_dom_sep_next_eval"])
+        ml = _merged_lookup(p, tau, we[5], we[0], we[1], we[2], pe["q_lookup_eval"], pe["q_dom_sep_eval"])
+        zmg = (zeta - g_inv) % p
+        cpl = (alpha4 * lagrange_1 + alpha5 * lagrange_n
+               + alpha6 * zmg % p * bp1 % p * ((gamma + ml) % p) % p * ((gb + mt + beta * mtn) % p)) % p
+        r_lookup = _poly_scale(p, pl_poly, cpl)
+        ch2 = (-alpha6) % p * zmg % p * pe["prod_next_eval"] % p * ((gb + pe["h_1_eval"] + beta * pe["h_1_next_eval"]) % p) % p
+        r_lookup = _poly_add(p, r_lookup, _poly_scale(p, h_polys[1], ch2))
+        non_quot = _poly_add(p, non_quot, r_lookup)
+    lin = _poly_add(p, lin, _poly_scale(p, non_quot, 1))  # alpha_base = 1 for the first (only) instance
 
     # ---- round 5 ---------------------------------------------------------------------------------
     v = tr.get_and_append_challenge(fr, b"v")
@@ -825,14 +1100,25 @@ def prove(curve: Curve, cs: PlonkCircuit, pk: dict, blinders: Sequence[int], tra
             coeff = coeff * r % p
         return commit(_div_linear(p, acc, point))
 
-    opening = batched_witness([lin] + wire_polys + pk["sigmas"][:4], v, zeta)
-    shifted = batched_witness([z_poly], v, g * zeta % p)
-    return {
+    open_polys = [lin] + wire_polys + pk["sigmas"][:nw - 1]
+    shifted_polys = [z_poly]
+    if ultra:  # plookup_open_polys_ref / plookup_shifted_open_polys_ref (prover.rs:427-460)
+        open_polys += [lk["range_table_poly"], lk["key_table_poly"], h_polys[0], pk["selectors"][N_SELECTORS], lk["table_dom_sep_poly"],
+                       lk["q_dom_sep_poly"]]
+        shifted_polys += [pl_poly, lk["range_table_poly"], lk["key_table_poly"], h_polys[0], h_polys[1], pk["selectors"][N_SELECTORS],
+                          wire_polys[3], wire_polys[4], lk["table_dom_sep_poly"]]
+    opening = batched_witness(open_polys, v, zeta)
+    shifted = batched_witness(shifted_polys, v, zg)
+    proof = {
         "wires_poly_comms": wires_comms, "prod_perm_poly_comm": z_comm, "split_quot_poly_comms": split_comms,
         "opening_proof": opening, "shifted_opening_proof": shifted,
         "wires_evals": wires_evals, "wire_sigma_evals": sigma_evals, "perm_next_eval": perm_next_eval,
-        "challenges": {"beta": beta, "gamma": gamma, "alpha": alpha, "zeta": zeta, "v": v},
+        "plookup_proof": None,
+        "challenges": {"tau": tau, "beta": beta, "gamma": gamma, "alpha": alpha, "zeta": zeta, "v": v},
     }
+    if ultra:
+        proof["plookup_proof"] = {"h_poly_comms": h_comms, "prod_lookup_poly_comm": pl_comm, "poly_evals": plookup_evals}
+    return proof
 
 
 def serialize_proof(curve: Curve, proof: dict) -> bytes:
@@ -855,20 +1141,35 @@ def serialize_proof(curve: Curve, proof: dict) -> bytes:
     for e in proof["wire_sigma_evals"]:
         out += ser_fr(fr, e)
     out += ser_fr(fr, proof["perm_next_eval"])
-    out += b"\x00"  # plookup_proof: None
+    lp = proof.get("plookup_proof")
+    if lp is None:
+        out += b"\x00"  # plookup_proof: None
+    else:               # Some(PlookupProof { h_poly_comms: Vec, prod_lookup_poly_comm, poly_evals }) (structs.rs:255-265,496-541)
+        out += b"\x01"
+        out += struct.pack("<Q", len(lp["h_poly_comms"]))
+        for c in lp["h_poly_comms"]:
+            out += ser_g1(curve, c)
+        out += ser_g1(curve, lp["prod_lookup_poly_comm"])
+        for name in PLOOKUP_EVAL_FIELDS:
+            out += ser_fr(fr, lp["poly_evals"][name])
     return bytes(out)
 
 
 def verify(curve: Curve, vk: dict, pub_input: Sequence[int], proof: dict, beta_srs: int, transcript: str = "solidity",
            extra_msg: Optional[bytes] = None) -> bool:
-    """verifier.rs (prepare_pcs_info + batch_verify_opening_proofs for one proof); the pairing check
+    """verifier.rs (prepare_pcs_info + batch_verify_opening_proofs for one proof, TurboPlonk or UltraPlonk); the pairing check
     e(A,[x]_2) == e(B,[1]_2) is evaluated as x*A == B with the known trapdoor x = beta_srs."""
     fr, p = curve.fr, curve.fr.p
     n = vk["domain_size"]
     dom = Radix2Domain(fr, n)
     g = dom.group_gen
+    g_inv = pow(g, -1, p)
     k = vk["k"]
-    if len(pub_input) != vk["num_inputs"]:
+    lp = proof.get("plookup_proof")
+    if (vk.get("plookup") is not None) != (lp is not None):   # verifier.rs:97
+        return False
+    nw = len(proof["wires_poly_comms"])
+    if len(pub_input) != vk["num_inputs"] or nw != len(k):
         return False
     # compute_challenges (verifier.rs:257-318)
     tr = TRANSCRIPTS[transcript](b"PlonkProof")
@@ -877,10 +1178,15 @@ def verify(curve: Curve, vk: dict, pub_input: Sequence[int], proof: dict, beta_s
     append_vk_and_pub_input(tr, curve, vk, pub_input)
     for c in proof["wires_poly_comms"]:
         tr.append_message(b"witness_poly_comms", ser_g1(curve, c))
-    tr.get_and_append_challenge(fr, b"tau")
+    tau = tr.get_and_append_challenge(fr, b"tau")
+    if lp is not None:
+        for c in lp["h_poly_comms"]:
+            tr.append_message(b"h_poly_comms", ser_g1(curve, c))
     beta = tr.get_and_append_challenge(fr, b"beta")
     gamma = tr.get_and_append_challenge(fr, b"gamma")
     tr.append_message(b"perm_poly_comms", ser_g1(curve, proof["prod_perm_poly_comm"]))
+    if lp is not None:
+        tr.append_message(b"plookup_poly_comms", ser_g1(curve, lp["prod_lookup_poly_comm"]))
     alpha = tr.get_and_append_challenge(fr, b"alpha")
     for c in proof["split_quot_poly_comms"]:
         tr.append_message(b"quot_poly_comms", ser_g1(curve, c))
@@ -890,15 +1196,22 @@ def verify(curve: Curve, vk: dict, pub_input: Sequence[int], proof: dict, beta_s
     for e in proof["wire_sigma_evals"]:
         tr.append_message(b"wire_sigma_evals", ser_fr(fr, e))
     tr.append_message(b"perm_next_eval", ser_fr(fr, proof["perm_next_eval"]))
+    if lp is not None:
+        _append_plookup_evals(tr, fr, lp["poly_evals"])
     v = tr.get_and_append_challenge(fr, b"v")
     tr.append_message(b"open_proof", ser_g1(curve, proof["opening_proof"]))
     tr.append_message(b"shifted_open_proof", ser_g1(curve, proof["shifted_opening_proof"]))
     u = tr.get_and_append_challenge(fr, b"u")
 
     alpha2 = alpha * alpha % p
+    alpha3, alpha4 = alpha2 * alpha % p, alpha2 * alpha2 % p
+    alpha5, alpha6 = alpha4 * alpha % p, alpha4 * alpha2 % p
     vanish = (pow(zeta, n, p) - 1) % p
     n_f = n % p
     lagrange_1 = vanish * pow(n_f * (zeta - 1) % p, -1, p) % p
+    lagrange_n = vanish * g_inv % p * pow(n_f * (zeta - g_inv) % p, -1, p) % p
+    bp1 = (1 + beta) % p
+    gb = gamma * bp1 % p
     we, se, pne = proof["wires_evals"], proof["wire_sigma_evals"], proof["perm_next_eval"]
     # evaluate_pi_poly (verifier.rs:765-805)
     pi_eval = 0
@@ -907,49 +1220,77 @@ def verify(curve: Curve, vk: dict, pub_input: Sequence[int], proof: dict, beta_s
         for i, val in enumerate(pub_input):
             e = dom.element(i)
             pi_eval = (pi_eval + vdn * e % p * pow((zeta - e) % p, -1, p) % p * val) % p
-    # compute_lin_poly_constant_term
+    # compute_lin_poly_constant_term (verifier.rs:340-418)
     tmp = (pi_eval - alpha2 * lagrange_1) % p
-    acc = alpha * pne % p * ((gamma + we[4]) % p) % p
-    for j in range(4):
+    acc = alpha * pne % p * ((gamma + we[nw - 1]) % p) % p
+    for j in range(nw - 1):
         acc = acc * ((gamma + we[j] + beta * se[j]) % p) % p
     lin_const = (tmp - acc) % p
-    # linearization_scalars_and_bases
+    if lp is not None:
+        ev_ = lp["poly_evals"]
+        pc = (lagrange_n * ((ev_["h_1_eval"] - ev_["h_2_next_eval"] - alpha2) % p) - alpha * lagrange_1
+              - alpha3 * ((zeta - g_inv) % p) % p * ev_["prod_next_eval"] % p
+              * ((gb + ev_["h_1_eval"] + beta * ev_["h_1_next_eval"]) % p) % p * ((gb + beta * ev_["h_2_next_eval"]) % p)) % p
+        lin_const = (lin_const + alpha3 * pc) % p
+    # linearization_scalars_and_bases (verifier.rs:513-670)
     sb: List[Tuple[int, object]] = []
     coeff = alpha2 * lagrange_1 % p
     c = alpha
-    for j in range(5):
+    for j in range(nw):
         c = c * ((beta * k[j] % p * zeta + gamma + we[j]) % p) % p
     sb.append(((coeff + c) % p, proof["prod_perm_poly_comm"]))
     c = alpha * beta % p * pne % p
-    for j in range(4):
+    for j in range(nw - 1):
         c = c * ((beta * se[j] + gamma + we[j]) % p) % p
-    sb.append(((-c) % p, vk["sigma_comms"][4]))
+    sb.append(((-c) % p, vk["sigma_comms"][nw - 1]))
     qs = [we[0], we[1], we[2], we[3], we[0] * we[1] % p, we[2] * we[3] % p, pow(we[0], 5, p), pow(we[1], 5, p),
           pow(we[2], 5, p), pow(we[3], 5, p), (-we[4]) % p, 1, we[0] * we[1] * we[2] * we[3] * we[4] % p]
-    for s, cm in zip(qs, vk["selector_comms"]):
-        sb.append((s, cm))
+    for s_, cm in zip(qs, vk["selector_comms"]):   # 13 scalars: the q_lookup commitment (14th) is not part of [D]
+        sb.append((s_, cm))
+    if lp is not None:
+        ev_ = lp["poly_evals"]
+        ml = _merged_lookup(p, tau, we[5], we[0], we[1], we[2], ev_["q_lookup_eval"], ev_["q_dom_sep_eval"])
+        mt = _merged_table(p, tau, ev_["range_table_eval"], ev_["key_table_eval"], ev_["q_lookup_eval"], we[3], we[4], ev_["table_dom_sep_eval"])
+        mtn = _merged_table(p, tau, ev_["range_table_next_eval"], ev_["key_table_next_eval"], ev_["q_lookup_next_eval"], ev_["w_3_next_eval"],
+                            ev_["w_4_next_eval"], ev_["table_dom_sep_next_eval"])
+        cpl = (alpha4 * lagrange_1 + alpha5 * lagrange_n
+               + alpha6 * ((zeta - g_inv) % p) % p * bp1 % p * ((gamma + ml) % p) % p * ((gb + mt + beta * mtn) % p)) % p
+        sb.append((cpl, lp["prod_lookup_poly_comm"]))
+        ch2 = alpha6 * ((g_inv - zeta) % p) % p * ev_["prod_next_eval"] % p * ((gb + ev_["h_1_eval"] + beta * ev_["h_1_next_eval"]) % p) % p
+        sb.append((ch2, lp["h_poly_comms"][1]))
     zeta_n2 = (1 + vanish) * zeta % p * zeta % p
     coeff = (-vanish) % p
     sb.append((coeff, proof["split_quot_poly_comms"][0]))
     for cm in proof["split_quot_poly_comms"][1:]:
         coeff = coeff * zeta_n2 % p
         sb.append((coeff, cm))
-    # aggregate_poly_commitments / aggregate_evaluations
+    # aggregate_poly_commitments / aggregate_evaluations (verifier.rs:421-511,673-745)
     v_base, uv_base = v, u
     buf = []
     for cm in proof["wires_poly_comms"]:
         buf.append(v_base); sb.append((v_base, cm)); v_base = v_base * v % p
-    for cm in vk["sigma_comms"][:4]:
+    for cm in vk["sigma_comms"][:nw - 1]:
         buf.append(v_base); sb.append((v_base, cm)); v_base = v_base * v % p
     buf.append(uv_base); sb.append((uv_base, proof["prod_perm_poly_comm"])); uv_base = uv_base * v % p
+    evals = list(we) + list(se) + [pne]
+    if lp is not None:
+        lvk = vk["plookup"]
+        for cm in (lvk["range_table_comm"], lvk["key_table_comm"], lp["h_poly_comms"][0], vk["selector_comms"][N_SELECTORS],
+                   lvk["table_dom_sep_comm"], lvk["q_dom_sep_comm"]):
+            buf.append(v_base); sb.append((v_base, cm)); v_base = v_base * v % p
+        for cm in (lp["prod_lookup_poly_comm"], lvk["range_table_comm"], lvk["key_table_comm"], lp["h_poly_comms"][0], lp["h_poly_comms"][1],
+                   vk["selector_comms"][N_SELECTORS], proof["wires_poly_comms"][3], proof["wires_poly_comms"][4], lvk["table_dom_sep_comm"]):
+            buf.append(uv_base); sb.append((uv_base, cm)); uv_base = uv_base * v % p
+        evals += _plookup_evals_vec(lp["poly_evals"]) + _plookup_next_evals_vec(lp["poly_evals"])
     ev = (-lin_const) % p
-    for b_, e in zip(buf, list(we) + list(se) + [pne]):
+    assert len(buf) == len(evals)
+    for b_, e in zip(buf, evals):
         ev = (ev + e * b_) % p
     # batch_verify_opening_proofs with one instance (r = 1)
     A = curve.add(proof["opening_proof"], curve.mul(u, proof["shifted_opening_proof"]))
     B = None
-    for s, cm in sb:
-        B = curve.add(B, curve.mul(s % p, cm))
+    for s_, cm in sb:
+        B = curve.add(B, curve.mul(s_ % p, cm))
     B = curve.add(B, curve.mul(zeta, proof["opening_proof"]))
     B = curve.add(B, curve.mul(u * (zeta * g % p) % p, proof["shifted_opening_proof"]))
     B = curve.add(B, curve.mul((-ev) % p, curve.gen))
