@@ -250,6 +250,55 @@ int jf_plonk_prove(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *witness, const 
 /* ark-serialize `serialize_compressed` of the proof; returns the byte count (769 for BN254) or < 0. */
 long jf_plonk_proof_serialize(const jf_plonk_proof *proof, uint8_t *out, size_t cap);
 
+/* ---- UltraPlonk: the same prover with the Plookup argument (6 wire types) ---------------------------------------------------
+ * `PlonkCircuit::new_ultra_plonk(range_bit_len)` circuits (relation/src/constraint_system.rs:234-240): range gates on a sixth
+ * wire, key-value tables (`create_table_and_lookup_variables`), the q_lookup selector.  The caller passes what the
+ * `Arithmetization` impl exposes after `finalize_for_arithmetization`: `all_selectors()` (14 x n: the 13 above, then q_lookup),
+ * the extended permutation (6 x n), k (6), `wire_variables` (6 x n, the range wire last) and the three per-gate columns
+ * `table_key_vec()`, `table_dom_sep_vec()`, `q_dom_sep()` (n each; :873-888); the range table {0 .. 2^range_bit_len - 1, 0 ..}
+ * is built on the device.  jf_plonk_vk_commitments then yields 14 selector, 6 sigma and the 4 `PlookupVerifyingKey`
+ * commitments (range table, key table, table dom sep, q dom sep; snark.rs:573-594), in that order.
+ * Round 3 uses the reference's 8n-point coset (the quotient has degree 6 n + 8); flags: bit 1 (skip zero selectors) only. */
+int jf_ultraplonk_preprocess(jf_ctx *ctx, const jf_srs *srs, unsigned log_n, const uint64_t *selector_evals,
+                             const uint64_t *sigma_evals, const uint64_t *k, const uint32_t *wire_variables, size_t num_vars,
+                             const uint32_t *pub_input_gate_ids, size_t num_inputs, unsigned range_bit_len,
+                             const uint64_t *table_key_evals, const uint64_t *table_dom_sep_evals, const uint64_t *q_dom_sep_evals,
+                             int flags, jf_plonk_pk **out);
+
+/* `Proof<E>` with `plookup_proof: Some(PlookupProof)` (structs.rs:62-84,255-265,496-541) */
+typedef struct {
+    int curve;
+    uint64_t wires_poly_comms[6 * 12];
+    int wires_inf[6];
+    uint64_t prod_perm_poly_comm[12];
+    int prod_perm_inf;
+    uint64_t split_quot_poly_comms[6 * 12];
+    int split_inf[6];
+    uint64_t opening_proof[12];
+    int opening_inf;
+    uint64_t shifted_opening_proof[12];
+    int shifted_opening_inf;
+    uint64_t wires_evals[6 * 4];
+    uint64_t wire_sigma_evals[5 * 4];
+    uint64_t perm_next_eval[4];
+    uint64_t h_poly_comms[2 * 12];      /* PlookupProof */
+    int h_inf[2];
+    uint64_t prod_lookup_poly_comm[12];
+    int prod_lookup_inf;
+    uint64_t plookup_evals[15 * 4];     /* PlookupEvaluations in declaration order: range_table, key_table, table_dom_sep, q_dom_sep,
+                                           h_1, q_lookup, prod_next, range_table_next, key_table_next, table_dom_sep_next, h_1_next,
+                                           h_2_next, q_lookup_next, w_3_next, w_4_next */
+    uint64_t challenges[6 * 4];         /* tau, beta, gamma, alpha, zeta, v (Montgomery): diagnostics */
+} jf_ultraplonk_proof;
+
+/* == `PlonkKzgSnark::prove` for one UltraPlonk instance.  blinders: the 29 field elements the reference draws, in its order:
+ * 6 x 2 wire masks, 3 + 3 for h1 / h2 (`mask_polynomial(.., 2)`, prover.rs:113-114), 3 for the permutation product, 3 for the
+ * lookup product, 5 split-quotient randomizers.  JF_ERR_INVALID_ARG when a lookup value is not in the table
+ * ("The sorted vector has wrong length", constraint_system.rs:1411-1413), JF_ERR_QUOTIENT_DEGREE for an unsatisfied gate. */
+int jf_ultraplonk_prove(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *witness, const uint64_t *blinders, int transcript_kind,
+                        const uint8_t *extra_msg, size_t extra_len, jf_ultraplonk_proof *out);
+long jf_ultraplonk_proof_serialize(const jf_ultraplonk_proof *proof, uint8_t *out, size_t cap);
+
 /* Host-only pieces of the transcripts (no GPU needed): sha3 `Keccak256`, and `PlonkTranscript`
  * new / append_message / get_and_append_challenge (plonk/src/transcript/{solidity,standard}.rs). */
 void jf_keccak256(const uint8_t *data, size_t len, uint8_t out[32]);

@@ -51,6 +51,23 @@ class PlonkProofStruct(ctypes.Structure):
     ]
 
 
+class UltraPlonkProofStruct(ctypes.Structure):
+    """`jf_ultraplonk_proof` of include/jf_b200.h."""
+    _fields_ = [
+        ("curve", ctypes.c_int),
+        ("wires_poly_comms", ctypes.c_uint64 * 72), ("wires_inf", ctypes.c_int * 6),
+        ("prod_perm_poly_comm", ctypes.c_uint64 * 12), ("prod_perm_inf", ctypes.c_int),
+        ("split_quot_poly_comms", ctypes.c_uint64 * 72), ("split_inf", ctypes.c_int * 6),
+        ("opening_proof", ctypes.c_uint64 * 12), ("opening_inf", ctypes.c_int),
+        ("shifted_opening_proof", ctypes.c_uint64 * 12), ("shifted_opening_inf", ctypes.c_int),
+        ("wires_evals", ctypes.c_uint64 * 24), ("wire_sigma_evals", ctypes.c_uint64 * 20),
+        ("perm_next_eval", ctypes.c_uint64 * 4),
+        ("h_poly_comms", ctypes.c_uint64 * 24), ("h_inf", ctypes.c_int * 2),
+        ("prod_lookup_poly_comm", ctypes.c_uint64 * 12), ("prod_lookup_inf", ctypes.c_int),
+        ("plookup_evals", ctypes.c_uint64 * 60), ("challenges", ctypes.c_uint64 * 24),
+    ]
+
+
 # name -> (restype, argtypes); must list every function of include/jf_b200.h
 SIGNATURES = {
     "jf_ctx_create": (ctypes.c_int, [ctypes.c_int, c_void_pp]),
@@ -119,6 +136,12 @@ SIGNATURES = {
     "jf_microbench": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "jf_plonk_preprocess": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint, c_u64p, c_u64p, c_u64p, c_u32p,
                                            ctypes.c_size_t, c_u32p, ctypes.c_size_t, ctypes.c_int, c_void_pp]),
+    "jf_ultraplonk_preprocess": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint, c_u64p, c_u64p, c_u64p, c_u32p,
+                                                ctypes.c_size_t, c_u32p, ctypes.c_size_t, ctypes.c_uint, c_u64p, c_u64p, c_u64p,
+                                                ctypes.c_int, c_void_pp]),
+    "jf_ultraplonk_prove": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64p, c_u64p, ctypes.c_int, ctypes.c_char_p,
+                                           ctypes.c_size_t, ctypes.POINTER(UltraPlonkProofStruct)]),
+    "jf_ultraplonk_proof_serialize": (ctypes.c_long, [ctypes.POINTER(UltraPlonkProofStruct), ctypes.c_char_p, ctypes.c_size_t]),
     "jf_plonk_vk_commitments": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64p, ctypes.POINTER(ctypes.c_int)]),
     "jf_plonk_pk_free": (None, [ctypes.c_void_p, ctypes.c_void_p]),
     "jf_plonk_prove": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64p, c_u64p, ctypes.c_int, ctypes.c_char_p,

@@ -1,7 +1,15 @@
-// plonk.cu -- device-resident TurboPlonk prover rounds around the MSM / NTT kernels
+// plonk.cu -- device-resident TurboPlonk / UltraPlonk prover rounds around the MSM / NTT kernels
 // (the "next" rows either side of the hot path).
 //
-// Replaces, for one TurboPlonk instance with 5 wire types and no Plookup:
+// UltraPlonk (6 wire types, Plookup; `Plonk<C, 6>`) adds, on top of everything below:
+//   PlonkCircuit::compute_{merged_lookup_table,lookup_sorted_vec_polynomials,lookup_prod_polynomial,range_table,key_table,
+//   table_dom_sep,q_dom_sep}_polynomial        relation/src/constraint_system.rs:1261-1492
+//   Prover::run_plookup_1st/2nd_round, compute_plookup_evaluations, compute_quotient_plookup_contribution,
+//   compute_lin_poly_plookup_contribution, plookup_(shifted_)open_polys_ref
+//                                          plonk/src/proof_system/prover.rs:98-123,150-190,239-297,427-460,773-888,1037-1113
+// The quotient of an UltraPlonk instance has degree 6 n + 8, so round 3 runs on the reference's full 8n-point coset.
+//
+// Replaces, for one TurboPlonk instance with 5 wire types and no Plookup (`Plonk<C, 5>`):
 //   PlonkKzgSnark::preprocess              plonk/src/proof_system/snark.rs:529-611
 //   PlonkKzgSnark::batch_prove_internal    plonk/src/proof_system/snark.rs:201-469
 //   Prover::run_1st..3rd_round, compute_evaluations, compute_(non_)quotient_component_for_lin_poly,
@@ -27,16 +35,29 @@
 //                      (prover.rs:504-506; ark-poly's `/` drops the remainder)
 #include <string.h>
 #include <algorithm>
+#include <unordered_map>
 #include "common.cuh"
 #include "ec.cuh"
 #include "transcript.hpp"
 
 namespace jf {
 
-static constexpr int NW = 5;      // wire types (GATE_WIDTH + 1)
-static constexpr int NSEL = 13;   // q_lc[4], q_mul[2], q_hash[4], q_o, q_c, q_ecc
-static constexpr int NBLIND = 17; // 5 x 2 (wires) + 3 (z) + 4 (split quotient)
+static constexpr int NW_TURBO = 5, NW_ULTRA = 6;  // wire types: GATE_WIDTH + 1 (+ the range / lookup wire)
+static constexpr int NW_MAX = 6;
 static constexpr int PAD = 8;     // room above n for the masking coefficients
+// sizes that depend on the Plonk type
+template <int NWT> struct Dim {
+    static constexpr int NW = NWT;
+    static constexpr bool ULTRA = NWT == NW_ULTRA;
+    static constexpr int NSEL = 13 + (ULTRA ? 1 : 0);  // q_lc[4], q_mul[2], q_hash[4], q_o, q_c, q_ecc [, q_lookup]
+    // field elements drawn from the prng: 2 per wire polynomial, [3 + 3 for h1, h2,] 3 for z, [3 for the lookup product,]
+    // NW - 1 split-quotient randomizers (prover.rs:463-486,946-957): 17 / 29
+    static constexpr int NBLIND = 2 * NWT + 3 + (NWT - 1) + (ULTRA ? 9 : 0);
+    static constexpr int BL_H = 2 * NWT;                 // h1 (3), h2 (3)       [Ultra]
+    static constexpr int BL_Z = 2 * NWT + (ULTRA ? 6 : 0);
+    static constexpr int BL_PL = BL_Z + 3;               // lookup product (3)   [Ultra]
+    static constexpr int BL_SPLIT = BL_Z + 3 + (ULTRA ? 3 : 0);
+};
 
 template <class F> __device__ __forceinline__ Fp<F> ldf(const Fp<F> *p) {
     const uint4 *q = reinterpret_cast<const uint4 *>(p);
@@ -181,7 +202,7 @@ __global__ void copy_rows_kernel(const Fp<F> *src, size_t src_stride, Fp<F> *dst
 }
 
 // ---- round 2: numerators / denominators of the grand product ---------------------------------------
-template <class F> struct PermArgs {
+template <class F, int NW> struct PermArgs {
     const Fp<F> *wv;       // NW x n wire values
     const Fp<F> *sigma;    // NW x n extended permutation values
     Fp<F> beta_k[NW];      // beta * k_j
@@ -190,7 +211,7 @@ template <class F> struct PermArgs {
     uint32_t n;
 };
 static constexpr int PERM_I = 8;
-template <class F> __global__ void perm_ab_kernel(const __grid_constant__ PermArgs<F> p) {
+template <class F, int NW> __global__ void perm_ab_kernel(const __grid_constant__ PermArgs<F, NW> p) {
     using E = Fp<F>;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t start = (uint64_t)t * PERM_I;
@@ -253,16 +274,23 @@ template <class F> __global__ void pow_tab_kernel(Fp<F> *table, Fp<F> base, Fp<F
 }
 
 // ---- round 3: the quotient on the 8n coset -----------------------------------------------------------
-template <class F> struct QuotArgs {
+// Plookup terms of the quotient (prover.rs:773-888): coset evaluations of the four table polynomials, h1, h2 and the lookup product
+template <class F> struct LookupQuot {
+    const Fp<F> *range, *key, *tds, *qds, *h1, *h2, *pl;  // m each; q_lookup is selector 13
+    Fp<F> tau, bp1, gb, alpha3;                           // 1 + beta, gamma (1 + beta)
+};
+template <class F, int NW> struct QuotArgs {
     const Fp<F> *sel;    // NSEL x m coset evaluations
     const Fp<F> *sig;    // NW x m
     const Fp<F> *w;      // NW x m
     const Fp<F> *z, *pi; // m each
+    LookupQuot<F> lk;    // UltraPlonk only
     const Fp<F> *inv_nx1;  // 1 / (n (x_i - 1))
     const Fp<F> *x_lo, *x_hi;
     int lo_bits;
     Fp<F> beta_k[NW], beta, gamma, alpha, alpha2;
     Fp<F> zh_inv[8];
+    Fp<F> omega_inv;    // w_n^-1 (UltraPlonk)
     Fp<F> *out;
     uint32_t m, ratio;  // m: evaluation points per polynomial (8n, or 6n by sub-cosets)
     uint32_t zero_sel;  // bit s set: selector s is the zero polynomial (its term and its loads are skipped)
@@ -274,7 +302,17 @@ template <class F> __device__ __forceinline__ Fp<F> pow5(const Fp<F> &x) {
     Fp<F> x2 = Fp<F>::sqr(x);
     return Fp<F>::mul(x, Fp<F>::sqr(x2));
 }
-template <class F> __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ QuotArgs<F> q) {
+// eval_merged_table / eval_merged_lookup_witness (structs.rs:926-956): a + q tau (b + tau (c + tau (d + tau e)))
+template <class F>
+__device__ __forceinline__ Fp<F> merged5(const Fp<F> &tau, const Fp<F> &a, const Fp<F> &q, const Fp<F> &b, const Fp<F> &c, const Fp<F> &d,
+                                         const Fp<F> &e) {
+    using E = Fp<F>;
+    E t = E::add(d, E::mul(tau, e));
+    t = E::add(c, E::mul(tau, t));
+    t = E::add(b, E::mul(tau, t));
+    return E::add(a, E::mul(E::mul(q, tau), t));
+}
+template <class F, int NW> __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ QuotArgs<F, NW> q) {
     using E = Fp<F>;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= q.m) return;
@@ -322,6 +360,31 @@ template <class F> __global__ void __launch_bounds__(128) quotient_kernel(const 
     }
     t = E::add(t, E::mul(q.alpha, E::sub(r1, r2)));
     E t2 = E::mul(E::mul(q.alpha2, E::sub(zx, E::one())), ldf(q.inv_nx1 + i));
+    if constexpr (NW == NW_ULTRA) {
+        // Plookup (prover.rs:773-888).  L_1 / Z_H = 1 / (n (x - 1)) = inv_nx1[i]; L_n / Z_H = w^-1 / (n (x - w^-1)) = 1 / (n (w x - 1))
+        // = inv_nx1[inext], because w x is the point one domain step further on the coset.
+        const LookupQuot<F> &k = q.lk;
+        const E lag1 = ldf(q.inv_nx1 + i), lagn = ldf(q.inv_nx1 + inext);
+        const E ql = S(13), ql_n = ldf(q.sel + 13 * m + inext);
+        const E h1x = ldf(k.h1 + i), h1n = ldf(k.h1 + inext), h2x = ldf(k.h2 + i), h2n = ldf(k.h2 + inext);
+        const E px = ldf(k.pl + i), pn = ldf(k.pl + inext);
+        const E mt_x = merged5(k.tau, ldf(k.range + i), ql, ldf(k.tds + i), ldf(k.key + i), w[3], w[4]);
+        const E mt_n = merged5(k.tau, ldf(k.range + inext), ql_n, ldf(k.tds + inext), ldf(k.key + inext), ldf(q.w + 3 * m + inext),
+                               ldf(q.w + 4 * m + inext));
+        const E ml_x = merged5(k.tau, w[5], ql, ldf(k.qds + i), w[0], w[1], w[2]);
+        E ap = k.alpha3;
+        t2 = E::add(t2, E::mul(ap, E::mul(E::sub(h1x, h2n), lagn)));
+        ap = E::mul(ap, q.alpha);
+        const E pm1 = E::sub(px, E::one());
+        t2 = E::add(t2, E::mul(ap, E::mul(pm1, lag1)));
+        ap = E::mul(ap, q.alpha);
+        t2 = E::add(t2, E::mul(ap, E::mul(pm1, lagn)));
+        ap = E::mul(ap, q.alpha);
+        // (x - w^-1) = (w x - 1) / w; with lagn = 1 / (n (w x - 1)) it is cheaper to rebuild x - w^-1 from x and the constant
+        const E a = E::mul(E::mul(E::mul(px, k.bp1), E::add(q.gamma, ml_x)), E::add(E::add(k.gb, mt_x), E::mul(q.beta, mt_n)));
+        const E b = E::mul(E::mul(pn, E::add(E::add(k.gb, h1x), E::mul(q.beta, h1n))), E::add(E::add(k.gb, h2x), E::mul(q.beta, h2n)));
+        t = E::add(t, E::mul(ap, E::mul(E::sub(x, q.omega_inv), E::sub(a, b))));
+    }
     stf(q.out + i, E::add(E::mul(t, q.zh_inv[row]), t2));
 }
 // WrongQuotientPolyDegree (prover.rs:916-919): coefficient `deg` must be non-zero, all above zero
@@ -357,7 +420,7 @@ template <class F> __global__ void __launch_bounds__(128) subcoset_solve_kernel(
     }
 }
 // split_quotient_polynomial (prover.rs:902-960): part i = t[i (n+2) .. ] with the masking edits
-template <class F>
+template <class F, int NW>
 __global__ void split_kernel(const Fp<F> *t, size_t n, size_t total_len, const Fp<F> *b, Fp<F> *parts, size_t stride) {
     const int part = blockIdx.y;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -368,6 +431,46 @@ __global__ void split_kernel(const Fp<F> *t, size_t n, size_t total_len, const F
     if (i == 0 && part > 0) v = Fp<F>::sub(v, ldf(b + part - 1));
     if (i == n + 2 && part < NW - 1) v = ldf(b + part);
     if (i < stride) stf(parts + part * stride + i, v);
+}
+
+// ---- Plookup (UltraPlonk) -----------------------------------------------------------------------------------
+// range table column: i for i < range_size, else 0 (compute_range_table, constraint_system.rs:1423-1439), Montgomery form
+template <class F> __global__ void range_table_kernel(Fp<F> *out, uint32_t n, uint32_t range_size) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) stf(out + i, i < range_size ? Fp<F>::from_u32(i) : Fp<F>::zero());
+}
+// merged table value and merged lookup-wire value of every gate (merged_table_value / merged_lookup_wire_value,
+// constraint_system.rs:1441-1491).  lk: range | key | table dom sep | q dom sep | q_lookup evaluation columns (n each);
+// wv: 6 x n wire values (0 key, 1-2 lookup values, 3-4 table values, 5 range wire)
+template <class F>
+__global__ void merged_values_kernel(const Fp<F> *lk, const Fp<F> *wv, Fp<F> tau, uint32_t n, Fp<F> *mt, Fp<F> *ml) {
+    using E = Fp<F>;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t N = n;
+    const E ql = ldf(lk + 4 * N + i);
+    stf(mt + i, merged5(tau, ldf(lk + i), ql, ldf(lk + 2 * N + i), ldf(lk + N + i), ldf(wv + 3 * N + i), ldf(wv + 4 * N + i)));
+    stf(ml + i, merged5(tau, ldf(wv + 5 * N + i), ql, ldf(lk + 3 * N + i), ldf(wv + i), ldf(wv + N + i), ldf(wv + 2 * N + i)));
+}
+// numerators / denominators of the lookup product (compute_lookup_prod_polynomial, constraint_system.rs:1311-1368):
+// a_j = (1+beta)(gamma + ml_j)(gamma(1+beta) + mt_j + beta mt_(j+1)),  b_j = (gb + s_j + beta s_(j+1))(gb + s_(n-1+j) + beta s_(n+j)), j < n - 2
+template <class F>
+__global__ void lookup_ab_kernel(const Fp<F> *mt, const Fp<F> *ml, const Fp<F> *sorted, Fp<F> beta, Fp<F> gamma, Fp<F> bp1, Fp<F> gb,
+                                 uint32_t n, Fp<F> *a, Fp<F> *b) {
+    using E = Fp<F>;
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    E av = E::one(), bv = E::one();
+    if (j + 2 < n) {
+        av = E::mul(E::mul(bp1, E::add(gamma, ldf(ml + j))), E::add(E::add(gb, ldf(mt + j)), E::mul(beta, ldf(mt + j + 1))));
+        bv = E::mul(E::add(E::add(gb, ldf(sorted + j)), E::mul(beta, ldf(sorted + j + 1))),
+                    E::add(E::add(gb, ldf(sorted + (size_t)n - 1 + j)), E::mul(beta, ldf(sorted + (size_t)n + j))));
+    }
+    stf(a + j, av);
+    stf(b + j, bv);
+}
+template <class F> __global__ void set_one_kernel(Fp<F> *p) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) stf(p, Fp<F>::one());
 }
 
 // ---- round 4: evaluation -------------------------------------------------------------------------------
@@ -405,7 +508,7 @@ template <class F> __global__ void __launch_bounds__(EV_T) sum_kernel(const Fp<F
 }
 
 // ---- round 5: linear combination, division by a linear factor ------------------------------------------
-static constexpr int LC_MAX = 32;
+static constexpr int LC_MAX = 48;
 template <class F> struct LinArgs {
     const Fp<F> *p[LC_MAX];
     uint32_t len[LC_MAX];
@@ -446,6 +549,13 @@ using namespace jf;
 
 struct jf_plonk_pk {
     int curve = JF_BN254;
+    int nw = jf::NW_TURBO;  // 5: TurboPlonk, 6: UltraPlonk (jf_ultraplonk_preprocess)
+    // UltraPlonk only: the four Plookup table polynomials (range, key, table dom sep, q dom sep; 4 x n coefficients), their
+    // evaluation columns (+ q_lookup's: 5 x n values), and the per-proof h1 / h2 / lookup-product polynomials (3 x np)
+    unsigned range_bit_len = 0;
+    void *d_lk = nullptr, *d_lk_evals = nullptr, *d_hp = nullptr;
+    void *d_mt = nullptr, *d_ml = nullptr, *d_sorted = nullptr;  // merged table (n), merged lookup values (n), sorted vector (2n)
+    std::vector<uint64_t> h_mt, h_ml, h_sorted;                  // host copies for the table-order merge
     const jf_srs *srs = nullptr;
     unsigned log_n = 0, log_m = 0;
     size_t n = 0, m = 0, np = 0;  // np = n + PAD: stride of the n-sized polynomial buffers
@@ -471,7 +581,7 @@ struct jf_plonk_pk {
     void *d_bp = nullptr, *d_t = nullptr, *d_s = nullptr, *d_wz = nullptr, *d_small = nullptr, *d_res = nullptr;
     void *d_side = nullptr;  // scratch of the side stream's division (3 np + scan temporaries)
     // host constants (Montgomery)
-    uint32_t k[NW][8], omega_n[8], omega_m[8], gen[8], zh_inv[8][8];
+    uint32_t k[jf::NW_MAX][8], omega_n[8], omega_n_inv[8], omega_m[8], gen[8], zh_inv[8][8];
     uint64_t gen_limbs[4];
     // verifying-key commitments (affine Montgomery x || y) and their transcript serialisation
     std::vector<uint64_t> vk_xy;
@@ -576,13 +686,18 @@ static int dalloc(jf_ctx *ctx, jf_plonk_pk *pk, size_t bytes, void **out) {
     return JF_OK;
 }
 
-template <class C> struct Plonk {
+template <class C, int NWT = NW_TURBO> struct Plonk {
     using Fr = typename C::Fr;
     using Fq = typename C::Fq;
     using E = Fp<Fr>;
     using H = HostCurve<C>;
+    using D = Dim<NWT>;
     static constexpr int L = H::L;
     static constexpr size_t PT = sizeof(XYZZ<Fq>);
+    static constexpr int NW = D::NW, NSEL = D::NSEL, NBLIND = D::NBLIND;
+    static constexpr bool ULTRA = D::ULTRA;
+    static constexpr int NVK = NSEL + NW + (ULTRA ? 4 : 0);  // verifying-key commitments
+    static constexpr int NROWS = NSEL + 2 * NW + 2 + (ULTRA ? 7 : 0);  // coset-evaluation rows of round 3
 
     static E kf(const jf_plonk_pk *pk, int j) {
         E r;
@@ -609,7 +724,7 @@ template <class C> struct Plonk {
     // latency for 1 or 18 bucket sets).
     struct CommitJob { const void *poly; size_t len; int slot; };
     static int commit_many(jf_ctx *ctx, jf_plonk_pk *pk, const CommitJob *jobs, int count) {
-        MsmJob mj[NSEL + NW];
+        MsmJob mj[NVK];
         for (int i = 0; i < count; i++) mj[i] = MsmJob{0, jobs[i].poly, jobs[i].len, 1, (char *)pk->d_res + PT * jobs[i].slot};
         return msm_run_many(ctx, pk->srs, mj, count);
     }
@@ -683,15 +798,23 @@ template <class C> struct Plonk {
     }
 
     // ------------------------------------------------------------------------------------------
+    // the three per-gate Plookup columns of an UltraPlonk circuit (null for TurboPlonk)
+    struct LookupCols { unsigned range_bit_len; const uint64_t *table_key, *table_dom_sep, *q_dom_sep; };
     static int preprocess(jf_ctx *ctx, const jf_srs *srs, unsigned log_n, const uint64_t *selector_evals,
                           const uint64_t *sigma_evals, const uint64_t *k, const uint32_t *wire_variables, size_t num_vars,
-                          const uint32_t *pub_gate_ids, size_t num_inputs, int flags, jf_plonk_pk **out) {
-        if (log_n < 2 || log_n + 3 > (unsigned)Fr::TWO_ADICITY || log_n > 26)  // n = 2: the quotient (degree 17) does not fit 8n
+                          const uint32_t *pub_gate_ids, size_t num_inputs, int flags, jf_plonk_pk **out,
+                          const LookupCols *lc = nullptr) {
+        // n = 2: the TurboPlonk quotient (degree 17) does not fit 8n; UltraPlonk: 6 n + 9 coefficients need n >= 8 to fit 8n
+        if (log_n < (ULTRA ? 3u : 2u) || log_n + 3 > (unsigned)Fr::TWO_ADICITY || log_n > 26)
             return fail(ctx, JF_ERR_DOMAIN_TOO_LARGE, "preprocess: unsupported domain size");
+        if (ULTRA && (!lc || lc->range_bit_len > log_n))
+            return fail(ctx, JF_ERR_INVALID_ARG, "preprocess: Domain size < range size (constraint_system.rs:1428-1434)");
         const size_t n = (size_t)1 << log_n, m = n * 8, np = n + PAD;
         if (srs->n < n + 3) return fail(ctx, JF_ERR_INVALID_ARG, "preprocess: the commit key needs n + 3 points (srs_size = n + 2)");
         jf_plonk_pk *pk = new jf_plonk_pk();
         pk->curve = srs->curve;
+        pk->nw = NW;
+        pk->range_bit_len = lc ? lc->range_bit_len : 0;
         pk->srs = srs;
         pk->log_n = log_n;
         pk->log_m = log_n + 3;
@@ -700,11 +823,12 @@ template <class C> struct Plonk {
         pk->np = np;
         pk->num_vars = num_vars;
         pk->num_inputs = (uint32_t)num_inputs;
-        pk->cache_coset = flags & 1;
+        pk->cache_coset = ULTRA ? 0 : (flags & 1);
         pk->skip_zero = (flags & 2) ? 1 : 0;
         // 6 n >= 5 n + 8 coefficients needs n >= 8; n >= 16 also leaves n - 8 >= 8 coefficients above the quotient's degree
         // for the WrongQuotientPolyDegree check (at n = 8 the six-row interpolant has no coefficient above degree 47 at all)
-        pk->sub = (log_n >= 4 && !(flags & 4)) ? SUB : 0;
+        // (UltraPlonk: the quotient has 6 n + 9 coefficients: the full 8n coset, as in the reference)
+        pk->sub = (!ULTRA && log_n >= 4 && !(flags & 4)) ? SUB : 0;
         pk->mq = pk->sub ? (size_t)pk->sub * n : m;
         if (flags & 2) {
             for (int sel = 0; sel < NSEL; sel++) {
@@ -713,6 +837,7 @@ template <class C> struct Plonk {
                 for (size_t i = 0; i < 4 * n; i++) acc |= col[i];
                 if (!acc) pk->zero_sel |= 1u << sel;
             }
+            pk->zero_sel &= 0x1FFFu;  // q_lookup (selector 13) is read unconditionally by the Plookup terms
         }
         int prio_least = 0, prio_greatest = 0;
         cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
@@ -722,7 +847,7 @@ template <class C> struct Plonk {
             release_pk(pk);
             return fail(ctx, JF_ERR_CUDA, "preprocess: cannot create the side stream");
         }
-        int rc = preprocess_inner(ctx, pk, selector_evals, sigma_evals, k, wire_variables, pub_gate_ids);
+        int rc = preprocess_inner(ctx, pk, selector_evals, sigma_evals, k, wire_variables, pub_gate_ids, lc);
         if (rc != JF_OK) {
             cudaStreamSynchronize(ctx->stream);
             cudaStreamSynchronize(pk->side);
@@ -734,14 +859,14 @@ template <class C> struct Plonk {
     }
 
     static int preprocess_inner(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *selector_evals, const uint64_t *sigma_evals,
-                                const uint64_t *k, const uint32_t *wire_variables, const uint32_t *pub_gate_ids) {
+                                const uint64_t *k, const uint32_t *wire_variables, const uint32_t *pub_gate_ids, const LookupCols *lc) {
         const size_t n = pk->n, m = pk->m, np = pk->np, mq = pk->mq;
         cudaStream_t st = ctx->stream;
         for (size_t i = 0; i < (size_t)NW * n; i++)
             if (wire_variables[i] >= pk->num_vars) return fail(ctx, JF_ERR_INVALID_ARG, "preprocess: wire variable out of range");
         for (size_t i = 0; i < pk->num_inputs; i++) {
             if (pub_gate_ids[i] >= n) return fail(ctx, JF_ERR_INVALID_ARG, "preprocess: io gate id out of range");
-            pk->pub_vars.push_back(wire_variables[(size_t)(NW - 1) * n + pub_gate_ids[i]]);
+            pk->pub_vars.push_back(wire_variables[(size_t)4 * n + pub_gate_ids[i]]);  // output wire (GATE_WIDTH)
         }
         // ---- host constants ----
         for (int j = 0; j < NW; j++) {
@@ -764,6 +889,10 @@ template <class C> struct Plonk {
         for (int s = 0; s < 3; s++) wn = E::sqr(wn);
         memcpy(pk->omega_m, wm.v, 32);
         memcpy(pk->omega_n, wn.v, 32);
+        {
+            const E wni = E::inv(wn);
+            memcpy(pk->omega_n_inv, wni.v, 32);
+        }
         for (int r = 0; r < 8; r++) {  // 1 / ((g w_m^r)^n - 1)   (prover.rs:530-537)
             E x = E::mul(g, pow_small(wm, r));
             E zh = E::sub(pow_small(x, n), E::one());
@@ -820,7 +949,7 @@ template <class C> struct Plonk {
         JF_TRY(dalloc(ctx, pk, fe * m, &pk->d_a));   // scan inputs / outputs (m-sized for the inversion table)
         JF_TRY(dalloc(ctx, pk, fe * m, &pk->d_b));
         JF_TRY(dalloc(ctx, pk, fe * (m / 256 + 4096), &pk->d_tmp));
-        const int ne = pk->cache_coset ? NW + 2 : NSEL + 2 * NW + 2;
+        const int ne = pk->cache_coset ? NW + 2 : NROWS;
         JF_TRY(dalloc(ctx, pk, fe * (size_t)ne * mq, &pk->d_e));
         JF_TRY(dalloc(ctx, pk, fe * m, &pk->d_q));
         JF_TRY(dalloc(ctx, pk, fe * NW * np, &pk->d_split));
@@ -831,6 +960,14 @@ template <class C> struct Plonk {
         JF_TRY(dalloc(ctx, pk, fe * (3 * np + np / 256 + 4096), &pk->d_side));
         JF_TRY(dalloc(ctx, pk, fe * 64, &pk->d_small));
         JF_TRY(dalloc(ctx, pk, PT * 32, &pk->d_res));
+        if (ULTRA) {
+            JF_TRY(dalloc(ctx, pk, fe * 4 * n, &pk->d_lk));
+            JF_TRY(dalloc(ctx, pk, fe * 5 * n, &pk->d_lk_evals));
+            JF_TRY(dalloc(ctx, pk, fe * 3 * np, &pk->d_hp));
+            JF_TRY(dalloc(ctx, pk, fe * n, &pk->d_mt));
+            JF_TRY(dalloc(ctx, pk, fe * n, &pk->d_ml));
+            JF_TRY(dalloc(ctx, pk, fe * 2 * n, &pk->d_sorted));
+        }
         if (pk->cache_coset) JF_TRY(dalloc(ctx, pk, fe * (size_t)(NSEL + NW) * mq, &pk->d_cached));
         JF_CUDA(ctx, cudaMemcpyAsync(pk->d_sel, selector_evals, fe * NSEL * n, cudaMemcpyHostToDevice, st));
         JF_CUDA(ctx, cudaMemcpyAsync(pk->d_sig, sigma_evals, fe * NW * n, cudaMemcpyHostToDevice, st));
@@ -851,18 +988,31 @@ template <class C> struct Plonk {
             JF_LAUNCH(ctx, "inv_one", inv_one_kernel<Fr><<<1, 32, 0, st>>>(sp, small));
             JF_LAUNCH(ctx, "inv_combine", inv_combine_kernel<Fr><<<(unsigned)((mq + 255) / 256), 256, 0, st>>>(pp, sp, small, (E *)pk->d_inv_nx1, mq));
         }
-        // selector / sigma polynomials (ifft) and the 18 verifying-key commitments
+        if (ULTRA) {
+            // Plookup columns: evaluation copies (range | key | table dom sep | q dom sep | q_lookup) for round 1.5, and the four
+            // table polynomials (snark.rs:541-556; constraint_system.rs:1263-1288)
+            E *lke = (E *)pk->d_lk_evals;
+            JF_LAUNCH(ctx, "range_table", range_table_kernel<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(lke, (uint32_t)n, 1u << lc->range_bit_len));
+            JF_CUDA(ctx, cudaMemcpyAsync(lke + n, lc->table_key, fe * n, cudaMemcpyHostToDevice, st));
+            JF_CUDA(ctx, cudaMemcpyAsync(lke + 2 * n, lc->table_dom_sep, fe * n, cudaMemcpyHostToDevice, st));
+            JF_CUDA(ctx, cudaMemcpyAsync(lke + 3 * n, lc->q_dom_sep, fe * n, cudaMemcpyHostToDevice, st));
+            JF_CUDA(ctx, cudaMemcpyAsync(lke + 4 * n, (const E *)pk->d_sel + (size_t)(NSEL - 1) * n, fe * n, cudaMemcpyDeviceToDevice, st));
+            JF_CUDA(ctx, cudaMemcpyAsync(pk->d_lk, lke, fe * 4 * n, cudaMemcpyDeviceToDevice, st));
+            JF_TRY(intt_n(ctx, pk, pk->d_lk, 4, n));
+        }
+        // selector / sigma polynomials (ifft) and the verifying-key commitments (18; UltraPlonk: 14 + 6 + 4)
         JF_TRY(intt_n(ctx, pk, pk->d_sel, NSEL, n));
         JF_TRY(intt_n(ctx, pk, pk->d_sig, NW, n));
         {
-            CommitJob jobs[NSEL + NW];
+            CommitJob jobs[NVK];
             for (int i = 0; i < NSEL; i++) jobs[i] = {(E *)pk->d_sel + (size_t)i * n, n, i};
             for (int i = 0; i < NW; i++) jobs[NSEL + i] = {(E *)pk->d_sig + (size_t)i * n, n, NSEL + i};
-            JF_TRY(commit_many(ctx, pk, jobs, NSEL + NW));
+            for (int i = NSEL + NW; i < NVK; i++) jobs[i] = {(E *)pk->d_lk + (size_t)(i - NSEL - NW) * n, n, i};
+            JF_TRY(commit_many(ctx, pk, jobs, NVK));
         }
-        pk->vk_xy.resize((size_t)(NSEL + NW) * 2 * L);
-        pk->vk_inf.resize(NSEL + NW);
-        JF_TRY(fetch_commits(ctx, pk, 0, NSEL + NW, pk->vk_xy.data(), pk->vk_inf.data()));
+        pk->vk_xy.resize((size_t)NVK * 2 * L);
+        pk->vk_inf.resize(NVK);
+        JF_TRY(fetch_commits(ctx, pk, 0, NVK, pk->vk_xy.data(), pk->vk_inf.data()));
         if (pk->cache_coset) {
             JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sel, n, n, NSEL, (E *)pk->d_cached, pk->zero_sel));
             JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sig, n, n, NW, (E *)pk->d_cached + (size_t)NSEL * mq));
@@ -930,6 +1080,7 @@ template <class C> struct Plonk {
     }
 
     static void append_vk_and_pub_input(Transcript &tr, const jf_plonk_pk *pk, const E *pub, size_t npub) {
+        // transcript/mod.rs:45-102: the PlookupVerifyingKey commitments are NOT part of it
         const uint32_t bits = Fr::BITS;
         const uint64_t dom = pk->n, nin = pk->num_inputs;
         tr.append_message("field size in bits", (const uint8_t *)&bits, 4);
@@ -942,19 +1093,79 @@ template <class C> struct Plonk {
         for (size_t i = 0; i < npub; i++) tr_fr(tr, "public input", pub[i]);
     }
 
+    // compute_lookup_sorted_vec_polynomials (constraint_system.rs:1370-1418): the lookup values merged into the table, in
+    // table order.  The merge is keyed by field VALUE (a hash map in the reference); it runs on the host over the two
+    // n-element vectors the device just computed -- 2 x 32 n bytes down, 64 n bytes up -- and is the only part of an
+    // UltraPlonk proof that is not a device kernel.
+    static int sorted_vector(jf_ctx *ctx, jf_plonk_pk *pk) {
+        const size_t n = pk->n, fe = sizeof(E);
+        pk->h_mt.resize(4 * n);
+        pk->h_ml.resize(4 * n);
+        pk->h_sorted.resize(4 * (2 * n));
+        JF_CUDA(ctx, cudaMemcpyAsync(pk->h_mt.data(), pk->d_mt, fe * n, cudaMemcpyDeviceToHost, ctx->stream));
+        JF_CUDA(ctx, cudaMemcpyAsync(pk->h_ml.data(), pk->d_ml, fe * n, cudaMemcpyDeviceToHost, ctx->stream));
+        JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        struct Key {
+            uint64_t l[4];
+            bool operator==(const Key &o) const { return l[0] == o.l[0] && l[1] == o.l[1] && l[2] == o.l[2] && l[3] == o.l[3]; }
+        };
+        struct KeyHash {
+            size_t operator()(const Key &k) const {
+                uint64_t h = k.l[0] * 0x9E3779B97F4A7C15ull ^ (k.l[1] + 0xBF58476D1CE4E5B9ull) * 0x94D049BB133111EBull;
+                h ^= (k.l[2] + (h << 6) + (h >> 2)) * 0xD6E8FEB86659FD93ull ^ k.l[3] * 0xFF51AFD7ED558CCDull;
+                return (size_t)(h ^ (h >> 29));
+            }
+        };
+        std::unordered_map<Key, size_t, KeyHash> counts;
+        counts.reserve(1024);
+        // only the first n - 1 gates look up (the last slot never holds a lookup gate)
+        for (size_t i = 0; i + 1 < n; i++) {
+            Key k;
+            memcpy(k.l, pk->h_ml.data() + 4 * i, 32);
+            counts[k]++;
+        }
+        uint64_t *out = pk->h_sorted.data();
+        size_t len = 0;
+        const size_t cap = 2 * n - 1;
+        for (size_t i = 0; i < n; i++) {
+            Key k;
+            memcpy(k.l, pk->h_mt.data() + 4 * i, 32);
+            size_t reps = 1;
+            auto it = counts.find(k);
+            if (it != counts.end()) {
+                reps += it->second;
+                counts.erase(it);
+            }
+            if (len + reps > cap) {
+                len = cap + 1;
+                break;
+            }
+            for (size_t r = 0; r < reps; r++) memcpy(out + 4 * (len + r), k.l, 32);
+            len += reps;
+        }
+        if (len != cap)
+            return fail(ctx, JF_ERR_INVALID_ARG, "prove: The sorted vector has wrong length, some lookup variables might be outside the table");
+        JF_CUDA(ctx, cudaMemcpyAsync(pk->d_sorted, out, fe * cap, cudaMemcpyHostToDevice, ctx->stream));
+        return JF_OK;
+    }
+
     // ------------------------------------------------------------------------------------------
+    template <class ProofT>
     static int prove(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *witness, const uint64_t *blinders, int kind,
-                     const uint8_t *extra, size_t extra_len, jf_plonk_proof *out) {
+                     const uint8_t *extra, size_t extra_len, ProofT *out) {
         const size_t n = pk->n, m = pk->mq, np = pk->np;  // m: evaluation points per polynomial in round 3
         const size_t fe = sizeof(E);
         cudaStream_t st = ctx->stream;
         E *W = (E *)pk->d_w, *PI = W + (size_t)NW * np, *Z = (E *)pk->d_z, *WV = (E *)pk->d_wv;
         E *bl = (E *)pk->d_bl, *small = (E *)pk->d_small;
+        E *H1 = (E *)pk->d_hp, *H2 = H1 + np, *PL = H1 + 2 * np;                       // UltraPlonk
+        const E *LK = (const E *)pk->d_lk;                                             // range | key | table dom sep | q dom sep
+        const E *QL = (const E *)pk->d_sel + (size_t)(NSEL - 1) * n;                   // q_lookup polynomial (UltraPlonk)
         memset(out, 0, sizeof *out);
 
         JF_CUDA(ctx, cudaMemcpyAsync(pk->d_wit, witness, fe * pk->num_vars, cudaMemcpyHostToDevice, st));
         JF_CUDA(ctx, cudaMemcpyAsync(bl, blinders, fe * NBLIND, cudaMemcpyHostToDevice, st));
-        // coset-evaluation slots (8n each): selectors, sigmas (or the resident copies), wires, z, PI
+        // coset-evaluation slots: selectors, sigmas (or the resident copies), wires, z, PI [, range, key, tds, qds, h1, h2, pl]
         E *Ev = (E *)pk->d_e;
         const E *sel_c, *sig_c;
         E *w_c, *z_c, *pi_c;
@@ -974,6 +1185,9 @@ template <class C> struct Plonk {
         }
         z_c = w_c + (size_t)NW * m;
         pi_c = z_c + m;
+        E *lk_c = pi_c + m;  // UltraPlonk: 7 more rows
+        if (ULTRA)
+            JF_TRY(on_side(ctx, pk, [&]() -> int { return coset_fft_rows(ctx, pk, LK, n, n, 4, lk_c); }));
         Transcript tr(kind, "PlonkProof");
         if (extra) tr.append_message("extra info", extra, extra_len);
         {
@@ -981,14 +1195,14 @@ template <class C> struct Plonk {
             for (size_t i = 0; i < pk->num_inputs; i++) pub[i] = H::fr_from_limbs(witness + 4 * (size_t)pk->pub_vars[i]);
             append_vk_and_pub_input(tr, pk, pub.data(), pub.size());
         }
-        // ---- round 1 (prover.rs:72-87): wire polynomials, masking, 5 commitments, PI polynomial ----
+        // ---- round 1 (prover.rs:72-87): wire polynomials, masking, NW commitments, PI polynomial ----
         JF_LAUNCH(ctx, "gather_wires", gather_wires_kernel<Fr><<<(unsigned)((NW * n + 255) / 256), 256, 0, st>>>(
             (const E *)pk->d_wit, pk->d_wire_vars, (size_t)NW * n, WV));
         JF_CUDA(ctx, cudaMemsetAsync(W, 0, fe * (NW + 1) * np, st));
         JF_CUDA(ctx, cudaMemcpy2DAsync(W, fe * np, WV, fe * n, fe * n, NW, cudaMemcpyDeviceToDevice, st));
         if (pk->num_inputs)
             JF_LAUNCH(ctx, "pub_input", pub_input_kernel<Fr><<<(pk->num_inputs + 127) / 128, 128, 0, st>>>(
-                (const E *)pk->d_wit, pk->d_wire_vars + (size_t)(NW - 1) * n, pk->d_gate_ids, pk->num_inputs, PI));
+                (const E *)pk->d_wit, pk->d_wire_vars + (size_t)4 * n, pk->d_gate_ids, pk->num_inputs, PI));
         JF_TRY(intt_n(ctx, pk, W, NW + 1, np));
         for (int j = 0; j < NW; j++) JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(W + (size_t)j * np, n, bl + 2 * j, 2));
         // the wire / PI polynomials are final: their coset NTTs run beside the commitments
@@ -1004,11 +1218,28 @@ template <class C> struct Plonk {
         }
         JF_TRY(fetch_commits(ctx, pk, 0, NW, out->wires_poly_comms, out->wires_inf));
         for (int j = 0; j < NW; j++) tr_g1(tr, "witness_poly_comms", out->wires_poly_comms + 2 * L * j, out->wires_inf[j]);
-        (void)challenge(tr, "tau");  // squeezed even without Plookup (snark.rs:293)
+        const E tau = challenge(tr, "tau");  // squeezed even without Plookup (snark.rs:293)
+        // ---- round 1.5 (Plookup; prover.rs:98-123, constraint_system.rs:1290-1309,1370-1418) ----
+        if constexpr (ULTRA) {
+            JF_LAUNCH(ctx, "merged_values", merged_values_kernel<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+                (const E *)pk->d_lk_evals, WV, tau, (uint32_t)n, (E *)pk->d_mt, (E *)pk->d_ml));
+            JF_TRY(sorted_vector(ctx, pk));
+            JF_CUDA(ctx, cudaMemsetAsync(H1, 0, fe * 3 * np, st));
+            JF_CUDA(ctx, cudaMemcpyAsync(H1, pk->d_sorted, fe * n, cudaMemcpyDeviceToDevice, st));
+            JF_CUDA(ctx, cudaMemcpyAsync(H2, (const E *)pk->d_sorted + (n - 1), fe * n, cudaMemcpyDeviceToDevice, st));
+            JF_TRY(intt_n(ctx, pk, H1, 2, np));
+            JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(H1, n, bl + D::BL_H, 3));
+            JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(H2, n, bl + D::BL_H + 3, 3));
+            JF_TRY(on_side(ctx, pk, [&]() -> int { return coset_fft_rows(ctx, pk, H1, np, n + 3, 2, lk_c + 4 * m); }));
+            CommitJob jobs[2] = {{H1, n + 3, 0}, {H2, n + 3, 1}};
+            JF_TRY(commit_many(ctx, pk, jobs, 2));
+            JF_TRY(fetch_commits(ctx, pk, 0, 2, out->h_poly_comms, out->h_inf));
+            for (int j = 0; j < 2; j++) tr_g1(tr, "h_poly_comms", out->h_poly_comms + 2 * L * j, out->h_inf[j]);
+        }
         // ---- round 2 (prover.rs:125-141; constraint_system.rs:1197-1223) ----
         const E beta = challenge(tr, "beta"), gamma = challenge(tr, "gamma");
         {
-            PermArgs<Fr> pa;
+            PermArgs<Fr, NW> pa;
             pa.wv = WV;
             pa.sigma = (const E *)pk->d_sig_evals;
             for (int j = 0; j < NW; j++) pa.beta_k[j] = E::mul(beta, kf(pk, j));
@@ -1019,7 +1250,7 @@ template <class C> struct Plonk {
             pa.b = (E *)pk->d_b;
             pa.n = (uint32_t)n;
             const unsigned threads = (unsigned)((n + PERM_I - 1) / PERM_I);
-            JF_LAUNCH(ctx, "perm_ab", perm_ab_kernel<Fr><<<(threads + 127) / 128, 128, 0, st>>>(pa));
+            JF_LAUNCH(ctx, "perm_ab", perm_ab_kernel<Fr, NW><<<(threads + 127) / 128, 128, 0, st>>>(pa));
             E *PA = (E *)pk->d_t, *SB = (E *)pk->d_s;
             JF_TRY((fscan<Fr, OpMul, false>(ctx, pa.a, PA, n, (E *)pk->d_tmp)));
             JF_TRY((fscan<Fr, OpMul, true>(ctx, pa.b, SB, n, (E *)pk->d_tmp)));
@@ -1027,17 +1258,37 @@ template <class C> struct Plonk {
             JF_CUDA(ctx, cudaMemsetAsync(Z, 0, fe * np, st));
             JF_LAUNCH(ctx, "z_combine", z_combine_kernel<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(PA, SB, small, Z, (uint32_t)n));
             JF_TRY(intt_n(ctx, pk, Z, 1, np));
-            JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(Z, n, bl + 10, 3));
+            JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(Z, n, bl + D::BL_Z, 3));
             JF_TRY(on_side(ctx, pk, [&]() -> int { return coset_fft_rows(ctx, pk, Z, np, n + 3, 1, z_c); }));
             JF_TRY(commit_dev(ctx, pk, Z, n + 3, 0));
             JF_TRY(fetch_commits(ctx, pk, 0, 1, out->prod_perm_poly_comm, &out->prod_perm_inf));
             tr_g1(tr, "perm_poly_comms", out->prod_perm_poly_comm, out->prod_perm_inf);
         }
-        // ---- round 3 (prover.rs:192-209, 512-673, 902-960) ----
+        const E bp1 = E::add(E::one(), beta), gb = E::mul(gamma, bp1);
+        // ---- round 2.5 (Plookup product; prover.rs:150-190, constraint_system.rs:1311-1368) ----
+        if constexpr (ULTRA) {
+            E *A = (E *)pk->d_a, *B = (E *)pk->d_b, *PA = (E *)pk->d_t, *SB = (E *)pk->d_s;
+            JF_LAUNCH(ctx, "lookup_ab", lookup_ab_kernel<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+                (const E *)pk->d_mt, (const E *)pk->d_ml, (const E *)pk->d_sorted, beta, gamma, bp1, gb, (uint32_t)n, A, B));
+            JF_TRY((fscan<Fr, OpMul, false>(ctx, A, PA, n, (E *)pk->d_tmp)));
+            JF_TRY((fscan<Fr, OpMul, true>(ctx, B, SB, n, (E *)pk->d_tmp)));
+            JF_LAUNCH(ctx, "inv_one", inv_one_kernel<Fr><<<1, 32, 0, st>>>(SB, small));
+            JF_LAUNCH(ctx, "z_combine", z_combine_kernel<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(PA, SB, small, PL, (uint32_t)n));
+            JF_LAUNCH(ctx, "set_one", set_one_kernel<Fr><<<1, 32, 0, st>>>(PL + (n - 1)));  // the reference pushes 1 as the last value
+            JF_TRY(intt_n(ctx, pk, PL, 1, np));
+            JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(PL, n, bl + D::BL_PL, 3));
+            JF_TRY(on_side(ctx, pk, [&]() -> int { return coset_fft_rows(ctx, pk, PL, np, n + 3, 1, lk_c + 6 * m); }));
+            JF_TRY(commit_dev(ctx, pk, PL, n + 3, 0));
+            JF_TRY(fetch_commits(ctx, pk, 0, 1, out->prod_lookup_poly_comm, &out->prod_lookup_inf));
+            tr_g1(tr, "plookup_poly_comms", out->prod_lookup_poly_comm, out->prod_lookup_inf);
+        }
+        // ---- round 3 (prover.rs:192-209, 512-673, 773-888, 902-960) ----
         const E alpha = challenge(tr, "alpha");
+        const size_t deg = NW * (n + 1) + 2;  // quotient_polynomial_degree (prover.rs:1126-1128)
+        const size_t last_len = deg + 1 - (size_t)(NW - 1) * (n + 2);
         {
-            JF_TRY(join_side(ctx, pk));  // all 25 coset evaluation vectors are in place
-            QuotArgs<Fr> q;
+            JF_TRY(join_side(ctx, pk));  // all coset evaluation vectors are in place
+            QuotArgs<Fr, NW> q;
             q.sel = sel_c;
             q.sig = sig_c;
             q.w = w_c;
@@ -1053,13 +1304,27 @@ template <class C> struct Plonk {
             q.alpha = alpha;
             q.alpha2 = E::sqr(alpha);
             for (int r = 0; r < 8; r++) q.zh_inv[r] = lf(pk->zh_inv[r]);
+            q.omega_inv = lf(pk->omega_n_inv);
+            if (ULTRA) {
+                q.lk.range = lk_c;
+                q.lk.key = lk_c + m;
+                q.lk.tds = lk_c + 2 * m;
+                q.lk.qds = lk_c + 3 * m;
+                q.lk.h1 = lk_c + 4 * m;
+                q.lk.h2 = lk_c + 5 * m;
+                q.lk.pl = lk_c + 6 * m;
+                q.lk.tau = tau;
+                q.lk.bp1 = bp1;
+                q.lk.gb = gb;
+                q.lk.alpha3 = E::mul(q.alpha2, alpha);
+            }
             q.out = (E *)pk->d_q;
             q.m = (uint32_t)m;
             q.ratio = 8;
             q.zero_sel = pk->zero_sel;
             q.sub = (uint32_t)pk->sub;
             q.log_n = pk->log_n;
-            JF_LAUNCH(ctx, "quotient", quotient_kernel<Fr><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(q));
+            JF_LAUNCH(ctx, "quotient", quotient_kernel<Fr, NW><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(q));
             const E *T = (const E *)pk->d_q;  // quotient coefficients
             if (pk->sub) {
                 JF_TRY(ntt_run_cosets(ctx, C::FR_ID, pk->d_q, n, n, pk->d_q, pk->log_n, 1, pk->sub_off, pk->sub, 1));
@@ -1073,37 +1338,65 @@ template <class C> struct Plonk {
             } else {
                 JF_TRY(ntt_run(ctx, C::FR_ID, pk->d_q, pk->d_q, m, pk->log_m, 1, pk->gen_limbs, 1, m));
             }
-            const size_t deg = NW * (n + 1) + 2;  // quotient_polynomial_degree (prover.rs:1126-1128)
             JF_LAUNCH(ctx, "degree_check", degree_check_kernel<Fr><<<(unsigned)((m - deg + 255) / 256), 256, 0, st>>>(T, deg, m, ctx->d_err + 1));
             dim3 grid((unsigned)((np + 255) / 256), NW);
-            JF_LAUNCH(ctx, "split", split_kernel<Fr><<<grid, 256, 0, st>>>(T, n, deg + 1, bl + 13, (E *)pk->d_split, np));
+            JF_LAUNCH(ctx, "split", split_kernel<Fr, NW><<<grid, 256, 0, st>>>(T, n, deg + 1, bl + D::BL_SPLIT, (E *)pk->d_split, np));
             CommitJob jobs[NW];
-            for (int i = 0; i < NW; i++)
-                jobs[i] = {(E *)pk->d_split + (size_t)i * np, i < NW - 1 ? n + 3 : deg + 1 - (size_t)(NW - 1) * (n + 2), i};
+            for (int i = 0; i < NW; i++) jobs[i] = {(E *)pk->d_split + (size_t)i * np, i < NW - 1 ? n + 3 : last_len, i};
             JF_TRY(commit_many(ctx, pk, jobs, NW));
             JF_TRY(fetch_commits(ctx, pk, 0, NW, out->split_quot_poly_comms, out->split_inf));
             for (int i = 0; i < NW; i++) tr_g1(tr, "quot_poly_comms", out->split_quot_poly_comms + 2 * L * i, out->split_inf[i]);
         }
-        // ---- round 4 (prover.rs:216-235) ----
+        // ---- round 4 (prover.rs:216-235) and 4.5 (Plookup evaluations, :239-297) ----
         const E zeta = challenge(tr, "zeta");
         const E omega = lf(pk->omega_n);
         const E zeta_w = E::mul(zeta, omega);
-        E ev[10];
+        constexpr int NEV = 2 * NW;  // NW wires, NW - 1 sigmas, z(zeta w)
+        E ev[NEV + 15];
+        // Plookup evaluations in `PlookupEvaluations` declaration order (structs.rs:496-541)
+        enum { P_RANGE, P_KEY, P_TDS, P_QDS, P_H1, P_QL, P_PLN, P_RANGEN, P_KEYN, P_TDSN, P_H1N, P_H2N, P_QLN, P_W3N, P_W4N };
         {
             for (int j = 0; j < NW; j++) JF_TRY(eval_dev(ctx, pk, W + (size_t)j * np, n + 2, zeta, small + j));
             for (int j = 0; j < NW - 1; j++) JF_TRY(eval_dev(ctx, pk, (const E *)pk->d_sig + (size_t)j * n, n, zeta, small + NW + j));
-            JF_TRY(eval_dev(ctx, pk, Z, n + 3, zeta_w, small + 9));
-            JF_CUDA(ctx, cudaMemcpyAsync(ev, small, fe * 10, cudaMemcpyDeviceToHost, st));
+            JF_TRY(eval_dev(ctx, pk, Z, n + 3, zeta_w, small + NEV - 1));
+            if (ULTRA) {
+                E *pe = small + NEV;
+                JF_TRY(eval_dev(ctx, pk, LK, n, zeta, pe + P_RANGE));
+                JF_TRY(eval_dev(ctx, pk, LK + n, n, zeta, pe + P_KEY));
+                JF_TRY(eval_dev(ctx, pk, LK + 2 * n, n, zeta, pe + P_TDS));
+                JF_TRY(eval_dev(ctx, pk, LK + 3 * n, n, zeta, pe + P_QDS));
+                JF_TRY(eval_dev(ctx, pk, H1, n + 3, zeta, pe + P_H1));
+                JF_TRY(eval_dev(ctx, pk, QL, n, zeta, pe + P_QL));
+                JF_TRY(eval_dev(ctx, pk, PL, n + 3, zeta_w, pe + P_PLN));
+                JF_TRY(eval_dev(ctx, pk, LK, n, zeta_w, pe + P_RANGEN));
+                JF_TRY(eval_dev(ctx, pk, LK + n, n, zeta_w, pe + P_KEYN));
+                JF_TRY(eval_dev(ctx, pk, LK + 2 * n, n, zeta_w, pe + P_TDSN));
+                JF_TRY(eval_dev(ctx, pk, H1, n + 3, zeta_w, pe + P_H1N));
+                JF_TRY(eval_dev(ctx, pk, H2, n + 3, zeta_w, pe + P_H2N));
+                JF_TRY(eval_dev(ctx, pk, QL, n, zeta_w, pe + P_QLN));
+                JF_TRY(eval_dev(ctx, pk, W + 3 * np, n + 2, zeta_w, pe + P_W3N));
+                JF_TRY(eval_dev(ctx, pk, W + 4 * np, n + 2, zeta_w, pe + P_W4N));
+            }
+            JF_CUDA(ctx, cudaMemcpyAsync(ev, small, fe * (NEV + (ULTRA ? 15 : 0)), cudaMemcpyDeviceToHost, st));
             JF_CUDA(ctx, cudaStreamSynchronize(st));
             for (int j = 0; j < NW; j++) tr_fr(tr, "wire_evals", ev[j]);
             for (int j = 0; j < NW - 1; j++) tr_fr(tr, "wire_sigma_evals", ev[NW + j]);
-            tr_fr(tr, "perm_next_eval", ev[9]);
+            tr_fr(tr, "perm_next_eval", ev[NEV - 1]);
+            if (ULTRA) {  // append_plookup_evaluations (transcript/mod.rs:168-201): six of the fifteen
+                const E *pe = ev + NEV;
+                tr_fr(tr, "lookup_table_eval", pe[P_RANGE]);
+                tr_fr(tr, "h_1_eval", pe[P_H1]);
+                tr_fr(tr, "prod_next_eval", pe[P_PLN]);
+                tr_fr(tr, "lookup_table_next_eval", pe[P_RANGEN]);
+                tr_fr(tr, "h_1_next_eval", pe[P_H1N]);
+                tr_fr(tr, "h_2_next_eval", pe[P_H2N]);
+            }
         }
-        // ---- round 5 (snark.rs:419-449; prover.rs:302-360, 362-419, 490-509, 963-1034) ----
+        // ---- round 5 (snark.rs:419-449; prover.rs:302-360, 362-460, 490-509, 963-1113) ----
         const E v = challenge(tr, "v");
         {
-            const E *we = ev, *se = ev + NW;
-            const E pne = ev[9];
+            const E *we = ev, *se = ev + NW, *pe = ev + NEV;
+            const E pne = ev[NEV - 1];
             const E one = E::one();
             const E vanish = E::sub(pow_small(zeta, n), one);
             const E zeta_n2 = E::mul(E::mul(E::add(vanish, one), zeta), zeta);
@@ -1121,16 +1414,15 @@ template <class C> struct Plonk {
             // quotient part: -Z_H(zeta) * sum_i zeta^(i (n+2)) t_i
             E coeff = E::neg(vanish);
             for (int i = 0; i < NW; i++) {
-                const size_t len = i < NW - 1 ? n + 3 : NW * (n + 1) + 3 - (size_t)(NW - 1) * (n + 2);
-                push((const E *)pk->d_split + (size_t)i * np, len, coeff);
+                push((const E *)pk->d_split + (size_t)i * np, i < NW - 1 ? n + 3 : last_len, coeff);
                 coeff = E::mul(coeff, zeta_n2);
             }
-            // circuit part
+            // circuit part: the 13 arithmetic selectors (q_lookup is not part of it)
             const E *sel = (const E *)pk->d_sel;
             const E w01 = E::mul(we[0], we[1]), w23 = E::mul(we[2], we[3]);
-            const E qs[NSEL] = {we[0], we[1], we[2], we[3], w01, w23, pow_small(we[0], 5), pow_small(we[1], 5), pow_small(we[2], 5),
-                                pow_small(we[3], 5), E::neg(we[4]), one, E::mul(E::mul(w01, w23), we[4])};
-            for (int s = 0; s < NSEL; s++)
+            const E qs[13] = {we[0], we[1], we[2], we[3], w01, w23, pow_small(we[0], 5), pow_small(we[1], 5), pow_small(we[2], 5),
+                              pow_small(we[3], 5), E::neg(we[4]), one, E::mul(E::mul(w01, w23), we[4])};
+            for (int s = 0; s < 13; s++)
                 if (!((pk->zero_sel >> s) & 1u)) push(sel + (size_t)s * n, n, qs[s]);
             // permutation part
             E c1 = alpha;
@@ -1138,27 +1430,72 @@ template <class C> struct Plonk {
             c1 = E::add(c1, E::mul(alpha2, lagrange_1));
             E c2 = E::mul(E::mul(alpha, beta), pne);
             for (int j = 0; j < NW - 1; j++) c2 = E::mul(c2, E::add(E::add(we[j], E::mul(beta, se[j])), gamma));
-            // the opening batch: lin + v w_0 + .. + v^5 w_4 + v^6 sigma_0 + .. + v^9 sigma_3; z appears in lin only
             push(Z, n + 3, c1);
+            const E *sig = (const E *)pk->d_sig;
+            push(sig + (size_t)(NW - 1) * n, n, E::neg(c2));
+            if (ULTRA) {  // compute_lin_poly_plookup_contribution (prover.rs:1037-1113)
+                const E alpha4 = E::sqr(alpha2), alpha5 = E::mul(alpha4, alpha), alpha6 = E::mul(alpha4, alpha2);
+                const E g_inv = lf(pk->omega_n_inv), zmg = E::sub(zeta, g_inv);
+                const E lagrange_n = E::mul(E::mul(vanish, g_inv), E::inv(E::mul(nf, zmg)));
+                auto merged = [&](const E &a, const E &qv, const E &b, const E &cc, const E &d, const E &e) {
+                    E t = E::add(d, E::mul(tau, e));
+                    t = E::add(cc, E::mul(tau, t));
+                    t = E::add(b, E::mul(tau, t));
+                    return E::add(a, E::mul(E::mul(qv, tau), t));
+                };
+                const E mt = merged(pe[P_RANGE], pe[P_QL], pe[P_TDS], pe[P_KEY], we[3], we[4]);
+                const E mtn = merged(pe[P_RANGEN], pe[P_QLN], pe[P_TDSN], pe[P_KEYN], pe[P_W3N], pe[P_W4N]);
+                const E ml = merged(we[5], pe[P_QL], pe[P_QDS], we[0], we[1], we[2]);
+                E cpl = E::mul(E::mul(E::mul(E::mul(alpha6, zmg), bp1), E::add(gamma, ml)), E::add(E::add(gb, mt), E::mul(beta, mtn)));
+                cpl = E::add(cpl, E::add(E::mul(alpha4, lagrange_1), E::mul(alpha5, lagrange_n)));
+                push(PL, n + 3, cpl);
+                const E ch2 = E::neg(E::mul(E::mul(E::mul(alpha6, zmg), pe[P_PLN]), E::add(E::add(gb, pe[P_H1]), E::mul(beta, pe[P_H1N]))));
+                push(H2, n + 3, ch2);
+            }
+            // the opening batch: lin + v w_0 + .. + v^NW w_(NW-1) + v^(NW+1) sigma_0 + .. [+ range, key, h1, q_lookup, tds, qds]
             E vp = v;
             for (int j = 0; j < NW; j++) {
                 push(W + (size_t)j * np, n + 2, vp);
                 vp = E::mul(vp, v);
             }
-            const E *sig = (const E *)pk->d_sig;
             for (int j = 0; j < NW - 1; j++) {
                 push(sig + (size_t)j * n, n, vp);
                 vp = E::mul(vp, v);
             }
-            push(sig + (size_t)(NW - 1) * n, n, E::neg(c2));
+            if (ULTRA) {  // plookup_open_polys_ref (prover.rs:427-442)
+                const E *ps[6] = {LK, LK + n, H1, QL, LK + 2 * n, LK + 3 * n};
+                const size_t ls[6] = {n, n, n + 3, n, n, n};
+                for (int j = 0; j < 6; j++) {
+                    push(ps[j], ls[j], vp);
+                    vp = E::mul(vp, v);
+                }
+            }
             la.count = c;
             la.out = (E *)pk->d_bp;
             la.out_len = (uint32_t)(n + 3);
             JF_LAUNCH(ctx, "lincomb", lincomb_kernel<Fr><<<(unsigned)((n + 3 + 127) / 128), 128, 0, st>>>(la));
-            // the shifted opening z / (X - zeta w) is independent of the batch polynomial: side stream, own scratch
+            // the shifted opening is independent of the batch polynomial: side stream, own scratch
             E *side_buf = (E *)pk->d_side;  // t, s, quotient (np each), scan temporaries
             JF_TRY(on_side(ctx, pk, [&]() -> int {
-                JF_TRY(div_linear_dev(ctx, side_buf, side_buf + np, side_buf + 3 * np, Z, n + 3, zeta_w, side_buf + 2 * np));
+                const E *shifted = Z;
+                if (ULTRA) {  // z + v pl + v^2 range + .. (plookup_shifted_open_polys_ref, prover.rs:444-460)
+                    LinArgs<Fr> ls;
+                    const E *ps[10] = {Z, PL, LK, LK + n, H1, H2, QL, W + 3 * np, W + 4 * np, LK + 2 * n};
+                    const size_t lens[10] = {n + 3, n + 3, n, n, n + 3, n + 3, n, n + 2, n + 2, n};
+                    E sp = one;
+                    for (int j = 0; j < 10; j++) {
+                        ls.p[j] = ps[j];
+                        ls.len[j] = (uint32_t)lens[j];
+                        ls.s[j] = sp;
+                        sp = E::mul(sp, v);
+                    }
+                    ls.count = 10;
+                    ls.out = PI;  // the PI slot of W is free after round 3 (its coset evaluations were taken in round 1)
+                    ls.out_len = (uint32_t)(n + 3);
+                    JF_LAUNCH(ctx, "lincomb", lincomb_kernel<Fr><<<(unsigned)((n + 3 + 127) / 128), 128, 0, ctx->stream>>>(ls));
+                    shifted = PI;
+                }
+                JF_TRY(div_linear_dev(ctx, side_buf, side_buf + np, side_buf + 3 * np, shifted, n + 3, zeta_w, side_buf + 2 * np));
                 return commit_dev(ctx, pk, side_buf + 2 * np, n + 2, 1);
             }));
             E *WZ = (E *)pk->d_wz;
@@ -1175,12 +1512,22 @@ template <class C> struct Plonk {
         }
         for (int j = 0; j < NW; j++) H::fr_to_limbs(ev[j], out->wires_evals + 4 * j);
         for (int j = 0; j < NW - 1; j++) H::fr_to_limbs(ev[NW + j], out->wire_sigma_evals + 4 * j);
-        H::fr_to_limbs(ev[9], out->perm_next_eval);
-        H::fr_to_limbs(beta, out->challenges + 0);
-        H::fr_to_limbs(gamma, out->challenges + 4);
-        H::fr_to_limbs(alpha, out->challenges + 8);
-        H::fr_to_limbs(zeta, out->challenges + 12);
-        H::fr_to_limbs(v, out->challenges + 16);
+        H::fr_to_limbs(ev[NEV - 1], out->perm_next_eval);
+        if constexpr (ULTRA) {
+            for (int j = 0; j < 15; j++) H::fr_to_limbs(ev[NEV + j], out->plookup_evals + 4 * j);
+            H::fr_to_limbs(tau, out->challenges + 0);
+            H::fr_to_limbs(beta, out->challenges + 4);
+            H::fr_to_limbs(gamma, out->challenges + 8);
+            H::fr_to_limbs(alpha, out->challenges + 12);
+            H::fr_to_limbs(zeta, out->challenges + 16);
+            H::fr_to_limbs(v, out->challenges + 20);
+        } else {
+            H::fr_to_limbs(beta, out->challenges + 0);
+            H::fr_to_limbs(gamma, out->challenges + 4);
+            H::fr_to_limbs(alpha, out->challenges + 8);
+            H::fr_to_limbs(zeta, out->challenges + 12);
+            H::fr_to_limbs(v, out->challenges + 16);
+        }
         out->curve = pk->curve;
         return JF_OK;
     }
@@ -1255,8 +1602,8 @@ template <class C> struct Plonk {
         return JF_OK;
     }
 
-    // `Proof<E>` CanonicalSerialize, compressed (structs.rs:62-84)
-    static size_t serialize(const jf_plonk_proof *p, uint8_t *out) {
+    // `Proof<E>` CanonicalSerialize, compressed (structs.rs:62-84; PlookupProof :255-265, PlookupEvaluations :496-541)
+    template <class ProofT> static size_t serialize(const ProofT *p, uint8_t *out) {
         uint8_t *o = out;
         auto u64 = [&](uint64_t v) { memcpy(o, &v, 8); o += 8; };
         auto g1 = [&](const uint64_t *xy, int inf) { H::g1_bytes(xy, inf, o); o += 8 * L; };
@@ -1273,7 +1620,15 @@ template <class C> struct Plonk {
         u64(NW - 1);
         for (int j = 0; j < NW - 1; j++) fr(p->wire_sigma_evals + 4 * j);
         fr(p->perm_next_eval);
-        *o++ = 0;  // plookup_proof: None
+        if constexpr (ULTRA) {
+            *o++ = 1;  // plookup_proof: Some
+            u64(2);
+            for (int j = 0; j < 2; j++) g1(p->h_poly_comms + 2 * L * j, p->h_inf[j]);
+            g1(p->prod_lookup_poly_comm, p->prod_lookup_inf);
+            for (int j = 0; j < 15; j++) fr(p->plookup_evals + 4 * j);
+        } else {
+            *o++ = 0;  // plookup_proof: None
+        }
         return (size_t)(o - out);
     }
 };
@@ -1308,6 +1663,51 @@ int jf_plonk_preprocess(jf_ctx *ctx, const jf_srs *srs, unsigned log_n, const ui
                                             pub_input_gate_ids, num_inputs, flags, out);
 }
 
+int jf_ultraplonk_preprocess(jf_ctx *ctx, const jf_srs *srs, unsigned log_n, const uint64_t *selector_evals, const uint64_t *sigma_evals,
+                             const uint64_t *k, const uint32_t *wire_variables, size_t num_vars, const uint32_t *pub_input_gate_ids,
+                             size_t num_inputs, unsigned range_bit_len, const uint64_t *table_key_evals,
+                             const uint64_t *table_dom_sep_evals, const uint64_t *q_dom_sep_evals, int flags, jf_plonk_pk **out) {
+    JF_GUARD(ctx);
+    if (!srs || !selector_evals || !sigma_evals || !k || !wire_variables || !out || (num_inputs && !pub_input_gate_ids) ||
+        !table_key_evals || !table_dom_sep_evals || !q_dom_sep_evals)
+        return fail(ctx, JF_ERR_INVALID_ARG, "ultraplonk_preprocess: null argument");
+    *out = nullptr;
+    if (srs->curve == JF_BN254) {
+        Plonk<Bn254Plonk, NW_ULTRA>::LookupCols lc{range_bit_len, table_key_evals, table_dom_sep_evals, q_dom_sep_evals};
+        return Plonk<Bn254Plonk, NW_ULTRA>::preprocess(ctx, srs, log_n, selector_evals, sigma_evals, k, wire_variables, num_vars,
+                                                       pub_input_gate_ids, num_inputs, flags & 2, out, &lc);
+    }
+    Plonk<Bls12381Plonk, NW_ULTRA>::LookupCols lc{range_bit_len, table_key_evals, table_dom_sep_evals, q_dom_sep_evals};
+    return Plonk<Bls12381Plonk, NW_ULTRA>::preprocess(ctx, srs, log_n, selector_evals, sigma_evals, k, wire_variables, num_vars,
+                                                      pub_input_gate_ids, num_inputs, flags & 2, out, &lc);
+}
+
+int jf_ultraplonk_prove(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *witness, const uint64_t *blinders, int transcript_kind,
+                        const uint8_t *extra_msg, size_t extra_len, jf_ultraplonk_proof *out) {
+    JF_GUARD(ctx);
+    if (!pk || !witness || !blinders || !out) return fail(ctx, JF_ERR_INVALID_ARG, "ultraplonk_prove: null argument");
+    if (pk->nw != NW_ULTRA) return fail(ctx, JF_ERR_INVALID_ARG, "ultraplonk_prove: the proving key is a TurboPlonk key (use jf_plonk_prove)");
+    if (transcript_kind != 0 && transcript_kind != 1) return fail(ctx, JF_ERR_INVALID_ARG, "ultraplonk_prove: unknown transcript");
+    const int rc = pk->curve == JF_BN254
+                       ? Plonk<Bn254Plonk, NW_ULTRA>::prove(ctx, pk, witness, blinders, transcript_kind, extra_msg, extra_len, out)
+                       : Plonk<Bls12381Plonk, NW_ULTRA>::prove(ctx, pk, witness, blinders, transcript_kind, extra_msg, extra_len, out);
+    if (rc != JF_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        if (pk->side) cudaStreamSynchronize(pk->side);
+    }
+    return rc;
+}
+
+long jf_ultraplonk_proof_serialize(const jf_ultraplonk_proof *proof, uint8_t *out, size_t cap) {
+    if (!proof || !out) return JF_ERR_INVALID_ARG;
+    const bool bn = proof->curve == JF_BN254;
+    if (!bn && proof->curve != JF_BLS12_381) return JF_ERR_INVALID_ARG;
+    const size_t L = bn ? 4 : 6;
+    const size_t need = 8 + 6 * 8 * L + 8 * L + 8 + 6 * 8 * L + 2 * 8 * L + 8 + 6 * 32 + 8 + 5 * 32 + 32 + 1 + 8 + 2 * 8 * L + 8 * L + 15 * 32;
+    if (cap < need) return JF_ERR_INVALID_ARG;
+    return (long)(bn ? Plonk<Bn254Plonk, NW_ULTRA>::serialize(proof, out) : Plonk<Bls12381Plonk, NW_ULTRA>::serialize(proof, out));
+}
+
 int jf_plonk_vk_commitments(jf_ctx *ctx, const jf_plonk_pk *pk, uint64_t *out_xy, int *out_inf) {
     JF_GUARD(ctx);
     if (!pk || !out_xy || !out_inf) return fail(ctx, JF_ERR_INVALID_ARG, "plonk_vk_commitments: null argument");
@@ -1331,6 +1731,7 @@ int jf_plonk_prove(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *witness, const 
                    const uint8_t *extra_msg, size_t extra_len, jf_plonk_proof *out) {
     JF_GUARD(ctx);
     if (!pk || !witness || !blinders || !out) return fail(ctx, JF_ERR_INVALID_ARG, "plonk_prove: null argument");
+    if (pk->nw != NW_TURBO) return fail(ctx, JF_ERR_INVALID_ARG, "plonk_prove: the proving key is an UltraPlonk key (use jf_ultraplonk_prove)");
     if (transcript_kind != 0 && transcript_kind != 1) return fail(ctx, JF_ERR_INVALID_ARG, "plonk_prove: unknown transcript");
     const int rc = pk->curve == JF_BN254
                        ? Plonk<Bn254Plonk>::prove(ctx, pk, witness, blinders, transcript_kind, extra_msg, extra_len, out)

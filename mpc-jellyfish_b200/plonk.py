@@ -24,6 +24,14 @@ TRANSCRIPT_KINDS = {"solidity": 0, "standard": 1}
 NUM_WIRE_TYPES = 5
 NUM_SELECTORS = 13
 NUM_BLINDERS = 17
+# UltraPlonk: the range / lookup wire, the q_lookup selector, 3 + 3 + 3 more masking scalars (h1, h2, lookup product) and one
+# more split-quotient randomizer
+ULTRA_WIRE_TYPES = 6
+ULTRA_SELECTORS = 14
+ULTRA_BLINDERS = 29
+PLOOKUP_EVAL_FIELDS = ["range_table_eval", "key_table_eval", "table_dom_sep_eval", "q_dom_sep_eval", "h_1_eval", "q_lookup_eval",
+                       "prod_next_eval", "range_table_next_eval", "key_table_next_eval", "table_dom_sep_next_eval", "h_1_next_eval",
+                       "h_2_next_eval", "q_lookup_next_eval", "w_3_next_eval", "w_4_next_eval"]  # structs.rs:496-541
 
 
 def keccak256(data: bytes) -> bytes:
@@ -80,12 +88,19 @@ class Proof:
     wires_evals: np.ndarray
     wire_sigma_evals: np.ndarray
     perm_next_eval: np.ndarray
-    challenges: np.ndarray  # beta, gamma, alpha, zeta, v
+    challenges: np.ndarray  # beta, gamma, alpha, zeta, v  (UltraPlonk: tau first)
     _raw: object = None
+    # `plookup_proof: Some(PlookupProof)` of an UltraPlonk proof (structs.rs:255-265): None for TurboPlonk
+    h_poly_comms: Optional[np.ndarray] = None
+    h_inf: Optional[List[bool]] = None
+    prod_lookup_poly_comm: Optional[np.ndarray] = None
+    prod_lookup_inf: bool = False
+    plookup_evals: Optional[np.ndarray] = None  # (15, 4), `PlookupEvaluations` in declaration order
 
     def serialize_compressed(self) -> bytes:
-        buf = ctypes.create_string_buffer(1024)
-        n = _ffi.lib().jf_plonk_proof_serialize(ctypes.byref(self._raw), buf, len(buf))
+        buf = ctypes.create_string_buffer(4096)
+        fn = _ffi.lib().jf_plonk_proof_serialize if self.h_poly_comms is None else _ffi.lib().jf_ultraplonk_proof_serialize
+        n = fn(ctypes.byref(self._raw), buf, len(buf))
         if n < 0:
             raise InvalidParameters("proof serialization failed (%d)" % n)
         return buf.raw[:n]
@@ -94,15 +109,21 @@ class Proof:
 class ProvingKey:
     """`ProvingKey<E>` resident on the GPU (selector / sigma polynomials, commit key, vk commitments)."""
 
-    def __init__(self, ctx: Context, key: CommitKey, handle, n: int, num_vars: int, num_inputs: int, k: np.ndarray):
+    def __init__(self, ctx: Context, key: CommitKey, handle, n: int, num_vars: int, num_inputs: int, k: np.ndarray, ultra: bool = False):
         self.ctx, self.key, self._h, self.n, self.num_vars, self.num_inputs, self.k = ctx, key, handle, n, num_vars, num_inputs, k
+        self.ultra = ultra
         L = _ffi.CURVE_FQ_LIMBS[key.curve]
-        xy = np.zeros((NUM_SELECTORS + NUM_WIRE_TYPES, 2 * L), dtype=np.uint64)
-        inf = (ctypes.c_int * (NUM_SELECTORS + NUM_WIRE_TYPES))()
+        ns, nw = (ULTRA_SELECTORS, ULTRA_WIRE_TYPES) if ultra else (NUM_SELECTORS, NUM_WIRE_TYPES)
+        total = ns + nw + (4 if ultra else 0)
+        xy = np.zeros((total, 2 * L), dtype=np.uint64)
+        inf = (ctypes.c_int * total)()
         ctx._check(ctx._lib.jf_plonk_vk_commitments(ctx._h, handle, xy.ctypes.data_as(_ffi.c_u64p), inf))
-        self.selector_comms, self.sigma_comms = xy[:NUM_SELECTORS], xy[NUM_SELECTORS:]
-        self.selector_inf = [bool(v) for v in inf[:NUM_SELECTORS]]
-        self.sigma_inf = [bool(v) for v in inf[NUM_SELECTORS:]]
+        self.selector_comms, self.sigma_comms = xy[:ns], xy[ns:ns + nw]
+        self.selector_inf = [bool(v) for v in inf[:ns]]
+        self.sigma_inf = [bool(v) for v in inf[ns:ns + nw]]
+        # PlookupVerifyingKey: range table, key table, table dom sep, q dom sep (snark.rs:573-594)
+        self.plookup_comms = xy[ns + nw:] if ultra else None
+        self.plookup_inf = [bool(v) for v in inf[ns + nw:]] if ultra else None
 
     def free(self):
         if self._h is not None and self.ctx._h:
@@ -171,3 +192,66 @@ class PlonkKzgSnark:
             wire_sigma_evals=np.array(raw.wire_sigma_evals, dtype=np.uint64).reshape(4, 4),
             perm_next_eval=np.array(raw.perm_next_eval, dtype=np.uint64),
             challenges=np.array(raw.challenges, dtype=np.uint64).reshape(5, 4), _raw=raw)
+
+    # ---- UltraPlonk (`PlonkCircuit::new_ultra_plonk`; Plookup argument) ----------------------------------------------------
+    @staticmethod
+    def preprocess_ultra(ctx: Context, key: CommitKey, selector_evals: np.ndarray, sigma_evals: np.ndarray, k: np.ndarray,
+                         wire_variables: np.ndarray, num_vars: int, pub_input_gate_ids: Sequence[int], range_bit_len: int,
+                         table_key_evals: np.ndarray, table_dom_sep_evals: np.ndarray, q_dom_sep_evals: np.ndarray,
+                         skip_zero_selectors: bool = False) -> ProvingKey:
+        """selector_evals (14, n, 4) = `all_selectors()` with q_lookup last, sigma_evals (6, n, 4), k (6, 4), wire_variables (6, n)
+        with the range wire last; table_key / table_dom_sep / q_dom_sep: (n, 4) per-gate columns (constraint_system.rs:873-888)."""
+        sel = np.ascontiguousarray(selector_evals, dtype=np.uint64)
+        sig = np.ascontiguousarray(sigma_evals, dtype=np.uint64)
+        kk = np.ascontiguousarray(k, dtype=np.uint64)
+        wv = np.ascontiguousarray(wire_variables, dtype=np.uint32)
+        if sel.ndim != 3 or sel.shape[0] != ULTRA_SELECTORS or sel.shape[2] != 4:
+            raise InvalidParameters("selector_evals must be (14, n, 4)")
+        n = sel.shape[1]
+        cols = [np.ascontiguousarray(c, dtype=np.uint64) for c in (table_key_evals, table_dom_sep_evals, q_dom_sep_evals)]
+        if n & (n - 1) or sig.shape != (ULTRA_WIRE_TYPES, n, 4) or kk.shape != (ULTRA_WIRE_TYPES, 4) or wv.shape != (ULTRA_WIRE_TYPES, n) \
+                or any(c.shape != (n, 4) for c in cols):
+            raise InvalidParameters("inconsistent proving-key shapes")
+        gids = np.ascontiguousarray(list(pub_input_gate_ids), dtype=np.uint32)
+        h = ctypes.c_void_p()
+        ctx._check(ctx._lib.jf_ultraplonk_preprocess(
+            ctx._h, key._h, n.bit_length() - 1, sel.ctypes.data_as(_ffi.c_u64p), sig.ctypes.data_as(_ffi.c_u64p),
+            kk.ctypes.data_as(_ffi.c_u64p), wv.ctypes.data_as(_ffi.c_u32p), num_vars,
+            gids.ctypes.data_as(_ffi.c_u32p) if len(gids) else None, len(gids), range_bit_len,
+            cols[0].ctypes.data_as(_ffi.c_u64p), cols[1].ctypes.data_as(_ffi.c_u64p), cols[2].ctypes.data_as(_ffi.c_u64p),
+            2 if skip_zero_selectors else 0, ctypes.byref(h)))
+        return ProvingKey(ctx, key, h, n, num_vars, len(gids), kk, ultra=True)
+
+    @staticmethod
+    def prove_ultra(pk: ProvingKey, witness: np.ndarray, blinders: np.ndarray, transcript: str = "solidity",
+                    extra_transcript_init_msg: Optional[bytes] = None) -> Proof:
+        """witness (num_vars, 4), blinders (29, 4): Montgomery limbs."""
+        ctx = pk.ctx
+        w = np.ascontiguousarray(witness, dtype=np.uint64)
+        b = np.ascontiguousarray(blinders, dtype=np.uint64)
+        if w.shape != (pk.num_vars, 4) or b.shape != (ULTRA_BLINDERS, 4):
+            raise InvalidParameters("witness must be (num_vars, 4) and blinders (29, 4)")
+        raw = _ffi.UltraPlonkProofStruct()
+        ctx._check(ctx._lib.jf_ultraplonk_prove(ctx._h, pk._h, w.ctypes.data_as(_ffi.c_u64p), b.ctypes.data_as(_ffi.c_u64p),
+                                                TRANSCRIPT_KINDS[transcript], extra_transcript_init_msg,
+                                                len(extra_transcript_init_msg) if extra_transcript_init_msg else 0,
+                                                ctypes.byref(raw)))
+        L = _ffi.CURVE_FQ_LIMBS[pk.key.curve]
+
+        def pts(arr, count):
+            return np.array(arr[: count * 2 * L], dtype=np.uint64).reshape(count, 2 * L)
+
+        return Proof(
+            curve=pk.key.curve,
+            wires_poly_comms=pts(raw.wires_poly_comms, 6), wires_inf=[bool(v) for v in raw.wires_inf],
+            prod_perm_poly_comm=pts(raw.prod_perm_poly_comm, 1)[0], prod_perm_inf=bool(raw.prod_perm_inf),
+            split_quot_poly_comms=pts(raw.split_quot_poly_comms, 6), split_inf=[bool(v) for v in raw.split_inf],
+            opening_proof=pts(raw.opening_proof, 1)[0], opening_inf=bool(raw.opening_inf),
+            shifted_opening_proof=pts(raw.shifted_opening_proof, 1)[0], shifted_opening_inf=bool(raw.shifted_opening_inf),
+            wires_evals=np.array(raw.wires_evals, dtype=np.uint64).reshape(6, 4),
+            wire_sigma_evals=np.array(raw.wire_sigma_evals, dtype=np.uint64).reshape(5, 4),
+            perm_next_eval=np.array(raw.perm_next_eval, dtype=np.uint64),
+            challenges=np.array(raw.challenges, dtype=np.uint64).reshape(6, 4), _raw=raw,
+            h_poly_comms=pts(raw.h_poly_comms, 2), h_inf=[bool(v) for v in raw.h_inf],
+            prod_lookup_poly_comm=pts(raw.prod_lookup_poly_comm, 1)[0], prod_lookup_inf=bool(raw.prod_lookup_inf),
+            plookup_evals=np.array(raw.plookup_evals, dtype=np.uint64).reshape(15, 4))

@@ -38,6 +38,23 @@ pub struct jf_plonk_proof {
     pub challenges: [u64; 20],
 }
 
+/// `jf_ultraplonk_proof`: an UltraPlonk `Proof<E>` with `plookup_proof: Some(..)`.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct jf_ultraplonk_proof {
+    pub curve: c_int,
+    pub wires_poly_comms: [u64; 72], pub wires_inf: [c_int; 6],
+    pub prod_perm_poly_comm: [u64; 12], pub prod_perm_inf: c_int,
+    pub split_quot_poly_comms: [u64; 72], pub split_inf: [c_int; 6],
+    pub opening_proof: [u64; 12], pub opening_inf: c_int,
+    pub shifted_opening_proof: [u64; 12], pub shifted_opening_inf: c_int,
+    pub wires_evals: [u64; 24], pub wire_sigma_evals: [u64; 20], pub perm_next_eval: [u64; 4],
+    pub h_poly_comms: [u64; 24], pub h_inf: [c_int; 2],
+    pub prod_lookup_poly_comm: [u64; 12], pub prod_lookup_inf: c_int,
+    pub plookup_evals: [u64; 60],
+    pub challenges: [u64; 24],
+}
+
 extern "C" {
     pub fn jf_ctx_create(device: c_int, out: *mut *mut jf_ctx) -> c_int;
     pub fn jf_ctx_destroy(ctx: *mut jf_ctx);
@@ -104,6 +121,15 @@ extern "C" {
                                sigma_evals: *const u64, k: *const u64, wire_variables: *const u32, num_vars: usize,
                                pub_input_gate_ids: *const u32, num_inputs: usize, flags: c_int,
                                out: *mut *mut jf_plonk_pk) -> c_int;
+    pub fn jf_ultraplonk_preprocess(ctx: *mut jf_ctx, srs: *const jf_srs, log_n: c_uint, selector_evals: *const u64,
+                                    sigma_evals: *const u64, k: *const u64, wire_variables: *const u32, num_vars: usize,
+                                    pub_input_gate_ids: *const u32, num_inputs: usize, range_bit_len: c_uint,
+                                    table_key_evals: *const u64, table_dom_sep_evals: *const u64, q_dom_sep_evals: *const u64,
+                                    flags: c_int, out: *mut *mut jf_plonk_pk) -> c_int;
+    pub fn jf_ultraplonk_prove(ctx: *mut jf_ctx, pk: *mut jf_plonk_pk, witness: *const u64, blinders: *const u64,
+                               transcript_kind: c_int, extra_msg: *const u8, extra_len: usize,
+                               out: *mut jf_ultraplonk_proof) -> c_int;
+    pub fn jf_ultraplonk_proof_serialize(proof: *const jf_ultraplonk_proof, out: *mut u8, cap: usize) -> c_long;
     pub fn jf_plonk_vk_commitments(ctx: *mut jf_ctx, pk: *const jf_plonk_pk, out_xy: *mut u64, out_inf: *mut c_int) -> c_int;
     pub fn jf_plonk_pk_free(ctx: *mut jf_ctx, pk: *mut jf_plonk_pk);
     pub fn jf_plonk_prove(ctx: *mut jf_ctx, pk: *mut jf_plonk_pk, witness: *const u64, blinders: *const u64,

@@ -91,3 +91,45 @@ def test_unsatisfied_witness_fails_quotient_degree(P, py):
     assert not cs.check_satisfiability()
     with pytest.raises(ValueError, match="WrongQuotientPolyDegree"):
         P.prove(cv, cs, pk, list(range(1, 18)), "solidity")
+
+
+@pytest.mark.parametrize("kind", ["solidity", "standard"])
+@pytest.mark.parametrize("which", ["ultra_test_m2", "ultra_test_m6", "ultra_bench_100"])
+def test_ultraplonk_oracle_prover_satisfies_oracle_verifier(P, py, kind, which):
+    """UltraPlonk (Plookup): prover restated from prover.rs:98-190,239-297,773-888,1037-1113 and constraint_system.rs:1261-1492,
+    verifier from verifier.rs:340-418,591-650,707-745 -- written from different reference files, they must agree."""
+    cv = py.BN254
+    cs = {"ultra_test_m2": lambda: P.gen_circuit_for_test(2, 3, ultra=True), "ultra_test_m6": lambda: P.gen_circuit_for_test(6, 1, ultra=True),
+          "ultra_bench_100": lambda: P.gen_circuit_for_bench(100, ultra=True)}[which]()
+    assert cs.check_satisfiability() and cs.nw == 6 and len(cs.selector_evals()) == 14
+    beta = 0xABCDEF0123456789 % cv.fr.p
+    pk = P.preprocess(cv, P.gen_srs(cv, beta, cs.n + 2), cs)
+    rnd = random.Random(4)
+    bl = [rnd.randrange(cv.fr.p) for _ in range(P.num_blinders(cs))]
+    assert len(bl) == 29
+    proof = P.prove(cv, cs, pk, bl, kind)
+    assert P.verify(cv, pk["vk"], cs.public_input(), proof, beta, kind)
+    assert len(P.serialize_proof(cv, proof)) == 1481
+    # tampering with any Plookup evaluation, the lookup product commitment or a sorted-vector commitment is rejected
+    for field in P.PLOOKUP_EVAL_FIELDS:
+        lp = dict(proof["plookup_proof"])
+        pe = dict(lp["poly_evals"])
+        pe[field] = (pe[field] + 1) % cv.fr.p
+        lp["poly_evals"] = pe
+        assert not P.verify(cv, pk["vk"], cs.public_input(), dict(proof, plookup_proof=lp), beta, kind), field
+    lp = dict(proof["plookup_proof"], prod_lookup_poly_comm=cv.gen)
+    assert not P.verify(cv, pk["vk"], cs.public_input(), dict(proof, plookup_proof=lp), beta, kind)
+    lp = dict(proof["plookup_proof"], h_poly_comms=[proof["plookup_proof"]["h_poly_comms"][1], proof["plookup_proof"]["h_poly_comms"][0]])
+    assert not P.verify(cv, pk["vk"], cs.public_input(), dict(proof, plookup_proof=lp), beta, kind)
+    # a TurboPlonk proof against an UltraPlonk key (and vice versa) is refused outright
+    assert not P.verify(cv, pk["vk"], cs.public_input(), dict(proof, plookup_proof=None), beta, kind)
+
+
+def test_ultraplonk_lookup_outside_the_table_is_refused(P, py):
+    cv = py.BN254
+    cs = P.gen_circuit_for_test(2, 3, ultra=True)
+    pk = P.preprocess(cv, P.gen_srs(cv, 31337, cs.n + 2), cs)
+    cs.witness[cs.wire_variables[5][0]] = 1000   # range-checked variable outside [0, 32)
+    assert not cs.check_satisfiability()
+    with pytest.raises(ValueError, match="sorted vector has wrong length"):
+        P.prove(cv, cs, pk, list(range(1, 30)), "solidity")
