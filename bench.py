@@ -414,6 +414,41 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
     prove16_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
     pk16.free()
     key16.free()
+    # UltraPlonk (Plookup) on the same bench circuit (`gen_circuit_for_bench(2^20, PlonkType::UltraPlonk)`, bench.rs:29-46; the
+    # reference publishes 33 701 ns/constraint for BN254 at 2^15, bench.md:25): 6 wire types, 35 polynomials on the full 8n coset
+    ultra = None
+    if not args.no_sweep:
+        arrU = B.bench_circuit_arrays(ctx, PROVE_LOG_N, ultra=True)
+        keyU = ctx.generate_srs_for_testing("bn254", BETA % co_modulus(), n + 3)
+        pkU = jf_mod().PlonkKzgSnark.preprocess_ultra(ctx, keyU, arrU["selectors"], arrU["sigmas"], arrU["k"], arrU["wire_vars"],
+                                                      arrU["num_vars"], [], arrU["range_bit_len"], arrU["table_key"],
+                                                      arrU["table_dom_sep"], arrU["q_dom_sep"])
+        blU = rng.integers(0, 1 << 60, size=(29, 4), dtype=np.uint64)
+        witU = torch.from_numpy(arrU["witness"].view(np.int64)).pin_memory().numpy().view(np.uint64)
+        proofU = jf_mod().PlonkKzgSnark.prove_ultra(pkU, witU, blU, "solidity")
+        if rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import plonk_ref as P
+            import plonk_util as U
+            import pyref
+            cv = pyref.BN254
+            vkU = U.vk_from_product(co, cv, pkU, B.BN254_K + [B.BN254_K5])
+            if not P.verify(cv, vkU, [], U.proof_to_oracle(co, cv, proofU), BETA % co_modulus(), "solidity"):
+                raise SystemExit("bench.py: the 2^20 UltraPlonk proof is rejected by the restated verifier; refusing to time it")
+        for _ in range(2):
+            jf_mod().PlonkKzgSnark.prove_ultra(pkU, witU, blU, "solidity")
+        barrier()
+        l0 = ctx.launch_count
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            jf_mod().PlonkKzgSnark.prove_ultra(pkU, witU, blU, "solidity")
+        barrier()
+        ultra = {"value": max_over_ranks((time.perf_counter() - t0) * 1e3 / steps), "unit": "ms",
+                 "gpu_launches": int((ctx.launch_count - l0) // steps),
+                 "note": "UltraPlonk (Plookup) proof of the 2^20-gate bench circuit, SolidityTranscript, accepted by the restated verifier; "
+                         "round 3 on the reference's full 8n coset (35 polynomials); the sorted lookup vector is merged on the host"}
+        pkU.free()
+        keyU.free()
     if rank != 0:
         return None
     cpu = None
@@ -439,6 +474,7 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
         "with_cached_selector_sigma_coset_evals": alt((True, True, False), "additionally the selector / sigma coset evaluations stay "
                                                       "resident (+3.4 GiB): only 7 polynomials are transformed per proof; same proof bytes"),
         "prove_2^16_gates_ms": prove16_ms,
+        "ultraplonk_2^20_gates": ultra,
         "cpu_baseline": cpu,
         "e2e": {"value": base["wall_ms"], "unit": "ms", "h2d_bytes_per_step": int(arr["witness"].nbytes + 17 * 32),
                 "d2h_bytes_per_step": 13 * 128 + 10 * 32},

@@ -2,7 +2,9 @@
 the CPU restatement (oracle/plonk_ref.py, whose prover satisfies its restated verifier: tests/test_plonk_oracle.py) on the
 reference's own UltraPlonk test circuit (plonk/src/proof_system/snark.rs:681-744: range gates, one key-value table, two lookups)
 and on the bench circuit (plonk/benches/bench.rs:29-46 with `new_ultra_plonk(8)`), both transcripts, both curves."""
+import os
 import random
+import sys
 
 import numpy as np
 import pytest
@@ -10,6 +12,8 @@ import pytest
 import plonk_util as U
 
 pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -111,5 +115,42 @@ def test_ultraplonk_errors(ctx, co, py, P):
     # key types do not mix
     with pytest.raises(jf.InvalidParameters):
         jf.PlonkKzgSnark.prove(pk, arr["witness"], bl[:17])
+    pk.free()
+    key.free()
+
+
+def test_numpy_ultra_bench_circuit_matches_the_restated_circuit(ctx, co, py, P):
+    import bench_circuit as B
+    cs = P.gen_circuit_for_bench(1 << 9, ultra=True)
+    want = U.arrays_from_oracle_circuit(co, py, cs)
+    got = B.bench_circuit_arrays(ctx, 9, ultra=True)
+    assert cs.k == B.BN254_K + [B.BN254_K5] and cs.n == 512
+    for f in ("selectors", "sigmas", "k", "witness", "table_key", "table_dom_sep", "q_dom_sep"):
+        assert np.array_equal(got[f], want[f]), f
+    assert np.array_equal(got["wire_vars"], want["wire_vars"]) and got["num_vars"] == want["num_vars"]
+    assert got["range_bit_len"] == want["range_bit_len"] == 8
+
+
+@pytest.mark.parametrize("log_n,kind", [(14, "solidity"), (18, "standard"), (20, "solidity")])
+def test_large_ultraplonk_proofs_are_accepted_by_the_restated_verifier(ctx, co, py, P, log_n, kind):
+    """the reference's UltraPlonk bench shape (plonk/benches/bench.rs with PlonkType::UltraPlonk) up to 2^20 gates"""
+    import mpc_jellyfish_b200 as jf
+    import bench_circuit as B
+    cv, fr = py.BN254, py.BN254_FR
+    arr = B.bench_circuit_arrays(ctx, log_n, ultra=True)
+    beta = 0x1D3C7A5B9E8F60412B7A6C5D4E3F20198A7B6C5D4E3F2A1B0C9D8E7F6A5B4C3 % fr.p
+    key = ctx.generate_srs_for_testing("bn254", beta, arr["n"] + 3)
+    pk = jf.PlonkKzgSnark.preprocess_ultra(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"], [],
+                                           arr["range_bit_len"], arr["table_key"], arr["table_dom_sep"], arr["q_dom_sep"])
+    bl = np.random.default_rng(log_n).integers(0, 1 << 60, size=(29, 4), dtype=np.uint64)
+    proof = jf.PlonkKzgSnark.prove_ultra(pk, arr["witness"], bl, kind)
+    got = U.proof_to_oracle(co, cv, proof)
+    vk = U.vk_from_product(co, cv, pk, B.BN254_K + [B.BN254_K5])
+    assert P.verify(cv, vk, [], got, beta, kind)
+    lp = dict(got["plookup_proof"])
+    pe = dict(lp["poly_evals"])
+    pe["h_1_next_eval"] = (pe["h_1_next_eval"] + 1) % fr.p
+    lp["poly_evals"] = pe
+    assert not P.verify(cv, vk, [], dict(got, plookup_proof=lp), beta, kind)
     pk.free()
     key.free()

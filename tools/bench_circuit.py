@@ -17,6 +17,9 @@ BN254_K = [1,
            0x1ee678a0470a75a6eaa8fe837060498ba828a3703b311d0f77f010424afeb025,
            0x2042a587a90c187b0a087c03e29c968b950b1db26d5c82d666905a6895790c0a,
            0x2e2b91456103698adf57b799969dea1c8f739da5d8d40dd3eb9222db7c81e881]
+# sixth representative of compute_coset_representatives::<ark_bn254::Fr>(6, _): the same ChaCha20 stream, one more draw
+# (oracle/plonk_ref.py computes it; no published constant exists for it)
+BN254_K5 = 0x1f20f5b0adb417179d42df7ddd4410a330afdb03e5c28949665b55adf7d7922d
 NW, NSEL = 5, 13
 
 
@@ -47,9 +50,10 @@ def wire_permutation(wire_vars: np.ndarray) -> np.ndarray:
 
 
 def arrays_from_columns(ctx, field, log_n, selector_cols_small, wire_vars, witness_small, pub_gate_ids, k_ints, p):
-    """selector_cols_small: (13, n) int64 with negative values meaning p - |v|; witness_small: int64 values.
-    Everything is converted to Montgomery limbs with the library's kernels."""
+    """selector_cols_small: (13 or 14, n) int64 with negative values meaning p - |v|; witness_small: int64 values;
+    wire_vars: (5 or 6, n).  Everything is converted to Montgomery limbs with the library's kernels."""
     n = 1 << log_n
+    NSEL, NW = selector_cols_small.shape[0], wire_vars.shape[0]
     to_mont = lambda a: ctx.field_op(field, "to_mont", np.ascontiguousarray(a))  # noqa: E731
     sel = np.zeros((NSEL, n, 4), dtype=np.uint64)
     for s in range(NSEL):
@@ -75,13 +79,19 @@ def arrays_from_columns(ctx, field, log_n, selector_cols_small, wire_vars, witne
             "witness": witness, "pub_gate_ids": list(pub_gate_ids), "num_vars": len(witness_small), "n": n, "log_n": log_n}
 
 
-def bench_circuit_arrays(ctx, log_n, field="bn254_fr", k_ints=BN254_K, p=BN254_FR_P):
-    """gen_circuit_for_bench(num_gates = 2^log_n, TurboPlonk): two constant gates (variables 0 and 1), then
-    2^log_n - 10 additions a <- a + 1; padded with PaddingGate / variable 0."""
+def bench_circuit_arrays(ctx, log_n, field="bn254_fr", k_ints=BN254_K, p=BN254_FR_P, ultra=False):
+    """gen_circuit_for_bench(num_gates = 2^log_n, TurboPlonk | UltraPlonk): two constant gates (variables 0 and 1), then
+    2^log_n - 10 additions a <- a + 1; padded with PaddingGate / variable 0.  UltraPlonk
+    (`new_ultra_plonk(8)`, bench.rs:33-37): a sixth wire column (all variable 0: the circuit has no range gates), an all-zero
+    q_lookup selector and all-zero table columns; the domain is max(gates, 2^8 + 1) rounded up = 2^log_n for log_n >= 9."""
     n = 1 << log_n
     adds = n - 10
-    wire_vars = np.zeros((NW, n), dtype=np.int64)
-    sel = np.zeros((NSEL, n), dtype=np.int64)
+    nw, nsel = (6, 14) if ultra else (NW, NSEL)
+    if ultra:
+        assert log_n >= 9 and k_ints is BN254_K
+        k_ints = BN254_K + [BN254_K5]
+    wire_vars = np.zeros((nw, n), dtype=np.int64)
+    sel = np.zeros((nsel, n), dtype=np.int64)
     # gates 0, 1: ConstantGate on wires [0,0,0,0,var] with q_c = value, q_o = 1
     wire_vars[4, 0], wire_vars[4, 1] = 0, 1
     sel[10, 0] = sel[10, 1] = 1
@@ -95,4 +105,8 @@ def bench_circuit_arrays(ctx, log_n, field="bn254_fr", k_ints=BN254_K, p=BN254_F
     sel[1, g] = 1
     sel[10, g] = 1
     witness = np.concatenate(([0, 1], t + 1)).astype(np.int64)
-    return arrays_from_columns(ctx, field, log_n, sel, wire_vars, witness, [], k_ints, p)
+    arr = arrays_from_columns(ctx, field, log_n, sel, wire_vars, witness, [], k_ints, p)
+    if ultra:
+        zero = np.zeros((n, 4), dtype=np.uint64)
+        arr.update({"range_bit_len": 8, "table_key": zero, "table_dom_sep": zero, "q_dom_sep": zero})
+    return arr
