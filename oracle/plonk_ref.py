@@ -858,13 +858,40 @@ def _append_plookup_evals(tr, fr, e):
 
 def prove(curve: Curve, cs: PlonkCircuit, pk: dict, blinders: Sequence[int], transcript: str = "solidity",
           extra_msg: Optional[bytes] = None) -> dict:
-    """batch_prove_internal for ONE instance (snark.rs:201-469), TurboPlonk or UltraPlonk.  `blinders`: the field elements the
-    reference draws from its prng, in consumption order: nw x (b0, b1) for the wire polynomials, [3 for h1,
-    3 for h2,] 3 for z, [3 for the lookup product,] nw - 1 split-quotient randomizers: 17 for TurboPlonk, 29 for UltraPlonk."""
+    """`PlonkKzgSnark::prove` = batch_prove_internal for ONE instance (snark.rs:624-651), TurboPlonk or UltraPlonk.  `blinders`: the
+    field elements the reference draws from its prng, in consumption order: nw x (b0, b1) for the wire
+    polynomials, [3 for h1, 3 for h2,] 3 for z, [3 for the lookup product,] nw - 1 split-quotient randomizers: 17 / 29."""
+    bp = batch_prove(curve, [cs], [pk], blinders, transcript, extra_msg)
+    return {   # `From<BatchProof> for Proof` (structs.rs:302-317)
+        "wires_poly_comms": bp["wires_poly_comms_vec"][0], "prod_perm_poly_comm": bp["prod_perm_poly_comms_vec"][0],
+        "split_quot_poly_comms": bp["split_quot_poly_comms"], "opening_proof": bp["opening_proof"],
+        "shifted_opening_proof": bp["shifted_opening_proof"], "wires_evals": bp["poly_evals_vec"][0]["wires_evals"],
+        "wire_sigma_evals": bp["poly_evals_vec"][0]["wire_sigma_evals"], "perm_next_eval": bp["poly_evals_vec"][0]["perm_next_eval"],
+        "plookup_proof": bp["plookup_proofs_vec"][0], "challenges": bp["challenges"]}
+
+
+def batch_num_blinders(circuits) -> int:
+    nw, ultra = circuits[0].nw, circuits[0].ultra
+    return len(circuits) * (2 * nw + 3 + (9 if ultra else 0)) + (nw - 1)
+
+
+def batch_prove(curve: Curve, circuits: Sequence[PlonkCircuit], pks: Sequence[dict], blinders: Sequence[int],
+                transcript: str = "solidity", extra_msg: Optional[bytes] = None) -> dict:
+    """batch_prove_internal (snark.rs:201-469): several instances over the same domain share one transcript, ONE quotient
+    polynomial (instance i enters with alpha_base_i = (alpha^3 | alpha^7)^i) and ONE pair of opening proofs.  `blinders` in the
+    order the reference's single prng is consumed: the wire masks of every instance, [the h1 / h2 masks of every instance,] the z
+    masks of every instance, [the lookup-product masks,] then the nw - 1 split-quotient randomizers."""
     fr, p = curve.fr, curve.fr.p
     be = _Backend(curve)
-    n = pk["n"]
-    nw, ultra = cs.nw, cs.ultra
+    ninst = len(circuits)
+    assert ninst >= 1 and len(pks) == ninst
+    n = pks[0]["n"]
+    nw, ultra = circuits[0].nw, circuits[0].ultra
+    for cs, pk in zip(circuits, pks):   # snark.rs:226-260
+        if cs.n != n or pk["n"] != n:
+            raise ValueError("circuit / proving key domain size differs from the expected domain size")
+        if cs.nw != nw or cs.ultra != ultra or (pk["plookup"] is not None) != ultra:
+            raise ValueError("inconsistent plonk circuit types")
     log_n = n.bit_length() - 1
     m = quotient_domain_size(n, nw)
     log_m = m.bit_length() - 1
@@ -873,11 +900,9 @@ def prove(curve: Curve, cs: PlonkCircuit, pk: dict, blinders: Sequence[int], tra
     qdom = Radix2Domain(fr, m)
     g = dom.group_gen
     g_inv = pow(g, -1, p)
-    srs_limbs, srs_points = pk["srs"]
-    vk = pk["vk"]
-    k = vk["k"]
+    srs_limbs, srs_points = pks[0]["srs"]
     bl = list(blinders)
-    assert len(bl) == num_blinders(nw, ultra)
+    assert len(bl) == batch_num_blinders(circuits)
 
     def commit(c):
         return be.commit(srs_limbs, srs_points, c)
@@ -894,111 +919,123 @@ def prove(curve: Curve, cs: PlonkCircuit, pk: dict, blinders: Sequence[int], tra
     tr = TRANSCRIPTS[transcript](b"PlonkProof")
     if extra_msg is not None:
         tr.append_message(b"extra info", extra_msg)
-    pub_input = cs.public_input()
-    append_vk_and_pub_input(tr, curve, vk, pub_input)
+    for cs, pk in zip(circuits, pks):
+        append_vk_and_pub_input(tr, curve, pk["vk"], cs.public_input())
+    I = [dict() for _ in range(ninst)]   # per-instance oracles
 
     # ---- round 1 ---------------------------------------------------------------------------------
-    wvals = cs.wire_values()
-    wire_polys = [mask(_strip(be.ntt(w, log_n, True)), 1) for w in wvals]
-    wires_comms = [commit(wp) for wp in wire_polys]
-    pi_vec = [0] * n
-    for gid in cs.pub_input_gate_ids:
-        pi_vec[gid] = cs.witness[cs.wire_variables[GATE_WIDTH][gid]]
-    pi_poly = _strip(be.ntt(pi_vec, log_n, True))
-    for c in wires_comms:
-        tr.append_message(b"witness_poly_comms", ser_g1(curve, c))
+    for cs, st in zip(circuits, I):
+        st["wvals"] = cs.wire_values()
+        st["wire_polys"] = [mask(_strip(be.ntt(w, log_n, True)), 1) for w in st["wvals"]]
+        st["wires_comms"] = [commit(wp) for wp in st["wire_polys"]]
+        pi_vec = [0] * n
+        for gid in cs.pub_input_gate_ids:
+            pi_vec[gid] = cs.witness[cs.wire_variables[GATE_WIDTH][gid]]
+        st["pi_poly"] = _strip(be.ntt(pi_vec, log_n, True))
+        for c in st["wires_comms"]:
+            tr.append_message(b"witness_poly_comms", ser_g1(curve, c))
 
     # ---- round 1.5 (Plookup; the challenge is squeezed even without it) -------------------------------
     tau = tr.get_and_append_challenge(fr, b"tau")
     if ultra:
-        merged_table = cs.merged_lookup_table(tau)
-        sorted_vec = cs.lookup_sorted_vec(tau, merged_table)
-        h_polys = [mask(_strip(be.ntt(sorted_vec[:n], log_n, True)), 2), mask(_strip(be.ntt(sorted_vec[n - 1:], log_n, True)), 2)]
-        h_comms = [commit(h) for h in h_polys]
-        for c in h_comms:
-            tr.append_message(b"h_poly_comms", ser_g1(curve, c))
+        for cs, st in zip(circuits, I):
+            st["merged_table"] = cs.merged_lookup_table(tau)
+            st["sorted_vec"] = cs.lookup_sorted_vec(tau, st["merged_table"])
+            sv = st["sorted_vec"]
+            st["h_polys"] = [mask(_strip(be.ntt(sv[:n], log_n, True)), 2), mask(_strip(be.ntt(sv[n - 1:], log_n, True)), 2)]
+            st["h_comms"] = [commit(h) for h in st["h_polys"]]
+            for c in st["h_comms"]:
+                tr.append_message(b"h_poly_comms", ser_g1(curve, c))
 
     # ---- round 2 ---------------------------------------------------------------------------------
     beta = tr.get_and_append_challenge(fr, b"beta")
     gamma = tr.get_and_append_challenge(fr, b"gamma")
-    ext_id, wperm = cs.extended_id_permutation, cs.wire_permutation
-    prod = [1]
-    for j in range(n - 1):
-        a = b = 1
-        for i in range(nw):
-            tmp = (wvals[i][j] + gamma) % p
-            a = a * (tmp + beta * ext_id[i * n + j]) % p
-            pi_, pj_ = wperm[i * n + j]
-            b = b * (tmp + beta * ext_id[pi_ * n + pj_]) % p
-        prod.append(prod[-1] * a % p * pow(b, -1, p) % p)
-    z_poly = mask(_strip(be.ntt(prod, log_n, True)), 2)
-    z_comm = commit(z_poly)
-    tr.append_message(b"perm_poly_comms", ser_g1(curve, z_comm))
+    for cs, st in zip(circuits, I):
+        ext_id, wperm, wvals = cs.extended_id_permutation, cs.wire_permutation, st["wvals"]
+        prod = [1]
+        for j in range(n - 1):
+            a = b = 1
+            for i in range(nw):
+                tmp = (wvals[i][j] + gamma) % p
+                a = a * (tmp + beta * ext_id[i * n + j]) % p
+                pi_, pj_ = wperm[i * n + j]
+                b = b * (tmp + beta * ext_id[pi_ * n + pj_]) % p
+            prod.append(prod[-1] * a % p * pow(b, -1, p) % p)
+        st["z_poly"] = mask(_strip(be.ntt(prod, log_n, True)), 2)
+        st["z_comm"] = commit(st["z_poly"])
+        tr.append_message(b"perm_poly_comms", ser_g1(curve, st["z_comm"]))
 
     # ---- round 2.5 (Plookup product) -------------------------------------------------------------------
     if ultra:
-        pl_poly = mask(_strip(be.ntt(cs.lookup_prod_vec(tau, beta, gamma, merged_table, sorted_vec), log_n, True)), 2)
-        pl_comm = commit(pl_poly)
-        tr.append_message(b"plookup_poly_comms", ser_g1(curve, pl_comm))
+        for cs, st in zip(circuits, I):
+            st["pl_poly"] = mask(_strip(be.ntt(cs.lookup_prod_vec(tau, beta, gamma, st["merged_table"], st["sorted_vec"]), log_n, True)), 2)
+            st["pl_comm"] = commit(st["pl_poly"])
+            tr.append_message(b"plookup_poly_comms", ser_g1(curve, st["pl_comm"]))
 
     # ---- round 3 ---------------------------------------------------------------------------------
     alpha = tr.get_and_append_challenge(fr, b"alpha")
     G = fr.generator
     z_h_inv = [pow((pow(G * qdom.element(i) % p, n, p) - 1) % p, -1, p) for i in range(ratio)]
     cfft = lambda poly: be.ntt(poly, log_m, False, G)  # noqa: E731  coset.fft
-    sel_c = [cfft(s) for s in pk["selectors"]]
-    sig_c = [cfft(s) for s in pk["sigmas"]]
-    w_c = [cfft(wp) for wp in wire_polys]
-    z_c = cfft(z_poly)
-    pi_c = cfft(pi_poly)
-    if ultra:
-        lk = pk["plookup"]
-        tds_c, qds_c = cfft(lk["table_dom_sep_poly"]), cfft(lk["q_dom_sep_poly"])
-        rng_c, key_c = cfft(lk["range_table_poly"]), cfft(lk["key_table_poly"])
-        h1_c, h2_c, pl_c = cfft(h_polys[0]), cfft(h_polys[1]), cfft(pl_poly)
-        ql_c = sel_c[N_SELECTORS]
     alpha2 = alpha * alpha % p
     alpha3 = alpha2 * alpha % p
+    alpha7 = alpha3 * alpha3 % p * alpha % p
+    alpha_step = alpha7 if ultra else alpha3
     n_f = n % p
     bp1 = (1 + beta) % p
     gb = gamma * bp1 % p
     quot = [0] * m
     wq = qdom.group_gen
-    x = G  # eval point g * w_m^i
-    for i in range(m):
-        inx = (i + ratio) % m
-        w = [w_c[j][i] for j in range(nw)]
-        q = [sel_c[s][i] for s in range(N_SELECTORS)]
-        t_circ = (q[11] + pi_c[i] + q[0] * w[0] + q[1] * w[1] + q[2] * w[2] + q[3] * w[3]
-                  + q[4] * w[0] * w[1] + q[5] * w[2] * w[3] + q[12] * w[0] * w[1] * w[2] * w[3] * w[4]
-                  + q[6] * pow(w[0], 5, p) + q[7] * pow(w[1], 5, p) + q[8] * pow(w[2], 5, p) + q[9] * pow(w[3], 5, p)
-                  - q[10] * w[4]) % p
-        zx, zxw = z_c[i], z_c[inx]
-        r1 = zx
-        r2 = zxw
-        for j in range(nw):
-            r1 = r1 * (w[j] + k[j] * x % p * beta + gamma) % p
-            r2 = r2 * (w[j] + sig_c[j][i] * beta + gamma) % p
-        t1 = (t_circ + alpha * (r1 - r2)) % p
-        t2 = alpha2 * (zx - 1) % p * pow(n_f * (x - 1) % p, -1, p) % p
-        if ultra:  # compute_quotient_plookup_contribution (prover.rs:773-888)
-            lag_n = g_inv * pow(n_f * (x - g_inv) % p, -1, p) % p
-            lag_1 = pow(n_f * (x - 1) % p, -1, p)
-            mt_x = _merged_table(p, tau, rng_c[i], key_c[i], ql_c[i], w[3], w[4], tds_c[i])
-            mt_xw = _merged_table(p, tau, rng_c[inx], key_c[inx], ql_c[inx], w_c[3][inx], w_c[4][inx], tds_c[inx])
-            ml_x = _merged_lookup(p, tau, w[5], w[0], w[1], w[2], ql_c[i], qds_c[i])
-            ap = alpha3
-            t2 = (t2 + ap * ((h1_c[i] - h2_c[inx]) * lag_n % p)) % p
-            ap = ap * alpha % p
-            t2 = (t2 + ap * ((pl_c[i] - 1) * lag_1 % p)) % p
-            ap = ap * alpha % p
-            t2 = (t2 + ap * ((pl_c[i] - 1) * lag_n % p)) % p
-            ap = ap * alpha % p
-            term = (x - g_inv) * (pl_c[i] * bp1 % p * ((gamma + ml_x) % p) % p * ((gb + mt_x + beta * mt_xw) % p)
-                                  - pl_c[inx] * ((gb + h1_c[i] + beta * h1_c[inx]) % p) % p * ((gb + h2_c[i] + beta * h2_c[inx]) % p)) % p
-            t1 = (t1 + ap * term) % p
-        quot[i] = (t1 * z_h_inv[i % ratio] + t2) % p
-        x = x * wq % p
+    alpha_base = 1
+    for cs, pk, st in zip(circuits, pks, I):
+        k = pk["vk"]["k"]
+        sel_c = [cfft(s_) for s_ in pk["selectors"]]
+        sig_c = [cfft(s_) for s_ in pk["sigmas"]]
+        w_c = [cfft(wp) for wp in st["wire_polys"]]
+        z_c = cfft(st["z_poly"])
+        pi_c = cfft(st["pi_poly"])
+        if ultra:
+            lk = pk["plookup"]
+            tds_c, qds_c = cfft(lk["table_dom_sep_poly"]), cfft(lk["q_dom_sep_poly"])
+            rng_c, key_c = cfft(lk["range_table_poly"]), cfft(lk["key_table_poly"])
+            h1_c, h2_c, pl_c = cfft(st["h_polys"][0]), cfft(st["h_polys"][1]), cfft(st["pl_poly"])
+            ql_c = sel_c[N_SELECTORS]
+        x = G  # eval point g * w_m^i
+        for i in range(m):
+            inx = (i + ratio) % m
+            w = [w_c[j][i] for j in range(nw)]
+            q = [sel_c[s_][i] for s_ in range(N_SELECTORS)]
+            t_circ = (q[11] + pi_c[i] + q[0] * w[0] + q[1] * w[1] + q[2] * w[2] + q[3] * w[3]
+                      + q[4] * w[0] * w[1] + q[5] * w[2] * w[3] + q[12] * w[0] * w[1] * w[2] * w[3] * w[4]
+                      + q[6] * pow(w[0], 5, p) + q[7] * pow(w[1], 5, p) + q[8] * pow(w[2], 5, p) + q[9] * pow(w[3], 5, p)
+                      - q[10] * w[4]) % p
+            zx, zxw = z_c[i], z_c[inx]
+            r1 = zx
+            r2 = zxw
+            for j in range(nw):
+                r1 = r1 * (w[j] + k[j] * x % p * beta + gamma) % p
+                r2 = r2 * (w[j] + sig_c[j][i] * beta + gamma) % p
+            t1 = (t_circ + alpha * (r1 - r2)) % p
+            t2 = alpha2 * (zx - 1) % p * pow(n_f * (x - 1) % p, -1, p) % p
+            if ultra:  # compute_quotient_plookup_contribution (prover.rs:773-888)
+                lag_n = g_inv * pow(n_f * (x - g_inv) % p, -1, p) % p
+                lag_1 = pow(n_f * (x - 1) % p, -1, p)
+                mt_x = _merged_table(p, tau, rng_c[i], key_c[i], ql_c[i], w[3], w[4], tds_c[i])
+                mt_xw = _merged_table(p, tau, rng_c[inx], key_c[inx], ql_c[inx], w_c[3][inx], w_c[4][inx], tds_c[inx])
+                ml_x = _merged_lookup(p, tau, w[5], w[0], w[1], w[2], ql_c[i], qds_c[i])
+                ap = alpha3
+                t2 = (t2 + ap * ((h1_c[i] - h2_c[inx]) * lag_n % p)) % p
+                ap = ap * alpha % p
+                t2 = (t2 + ap * ((pl_c[i] - 1) * lag_1 % p)) % p
+                ap = ap * alpha % p
+                t2 = (t2 + ap * ((pl_c[i] - 1) * lag_n % p)) % p
+                ap = ap * alpha % p
+                term = (x - g_inv) * (pl_c[i] * bp1 % p * ((gamma + ml_x) % p) % p * ((gb + mt_x + beta * mt_xw) % p)
+                                      - pl_c[inx] * ((gb + h1_c[i] + beta * h1_c[inx]) % p) % p * ((gb + h2_c[i] + beta * h2_c[inx]) % p)) % p
+                t1 = (t1 + ap * term) % p
+            quot[i] = (quot[i] + alpha_base * ((t1 * z_h_inv[i % ratio] + t2) % p)) % p
+            x = x * wq % p
+        alpha_base = alpha_base * alpha_step % p
     quot_poly = _strip(be.ntt(quot, log_m, True, G))
     expected_degree = nw * (n + 1) + 2
     if len(quot_poly) - 1 != expected_degree:
@@ -1022,29 +1059,32 @@ def prove(curve: Curve, cs: PlonkCircuit, pk: dict, blinders: Sequence[int], tra
     # ---- round 4 ---------------------------------------------------------------------------------
     zeta = tr.get_and_append_challenge(fr, b"zeta")
     zg = zeta * g % p
-    wires_evals = [_poly_eval(p, wp, zeta) for wp in wire_polys]
-    sigma_evals = [_poly_eval(p, sg, zeta) for sg in pk["sigmas"][:nw - 1]]
-    perm_next_eval = _poly_eval(p, z_poly, zg)
-    for e in wires_evals:
-        tr.append_message(b"wire_evals", ser_fr(fr, e))
-    for e in sigma_evals:
-        tr.append_message(b"wire_sigma_evals", ser_fr(fr, e))
-    tr.append_message(b"perm_next_eval", ser_fr(fr, perm_next_eval))
-    plookup_evals = None
-    if ultra:  # round 4.5: compute_plookup_evaluations (prover.rs:239-297)
-        qlp = pk["selectors"][N_SELECTORS]
-        plookup_evals = {
-            "range_table_eval": _poly_eval(p, lk["range_table_poly"], zeta), "key_table_eval": _poly_eval(p, lk["key_table_poly"], zeta),
-            "h_1_eval": _poly_eval(p, h_polys[0], zeta), "q_lookup_eval": _poly_eval(p, qlp, zeta),
-            "table_dom_sep_eval": _poly_eval(p, lk["table_dom_sep_poly"], zeta), "q_dom_sep_eval": _poly_eval(p, lk["q_dom_sep_poly"], zeta),
-            "prod_next_eval": _poly_eval(p, pl_poly, zg), "range_table_next_eval": _poly_eval(p, lk["range_table_poly"], zg),
-            "key_table_next_eval": _poly_eval(p, lk["key_table_poly"], zg), "h_1_next_eval": _poly_eval(p, h_polys[0], zg),
-            "h_2_next_eval": _poly_eval(p, h_polys[1], zg), "q_lookup_next_eval": _poly_eval(p, qlp, zg),
-            "w_3_next_eval": _poly_eval(p, wire_polys[3], zg), "w_4_next_eval": _poly_eval(p, wire_polys[4], zg),
-            "table_dom_sep_next_eval": _poly_eval(p, lk["table_dom_sep_poly"], zg)}
-        _append_plookup_evals(tr, fr, plookup_evals)
+    for pk, st in zip(pks, I):
+        st["wires_evals"] = [_poly_eval(p, wp, zeta) for wp in st["wire_polys"]]
+        st["sigma_evals"] = [_poly_eval(p, sg, zeta) for sg in pk["sigmas"][:nw - 1]]
+        st["perm_next_eval"] = _poly_eval(p, st["z_poly"], zg)
+        for e in st["wires_evals"]:
+            tr.append_message(b"wire_evals", ser_fr(fr, e))
+        for e in st["sigma_evals"]:
+            tr.append_message(b"wire_sigma_evals", ser_fr(fr, e))
+        tr.append_message(b"perm_next_eval", ser_fr(fr, st["perm_next_eval"]))
+    for pk, st in zip(pks, I):
+        st["plookup_evals"] = None
+        if ultra:  # round 4.5: compute_plookup_evaluations (prover.rs:239-297)
+            lk, h_polys, pl_poly, wire_polys = pk["plookup"], st["h_polys"], st["pl_poly"], st["wire_polys"]
+            qlp = pk["selectors"][N_SELECTORS]
+            st["plookup_evals"] = {
+                "range_table_eval": _poly_eval(p, lk["range_table_poly"], zeta), "key_table_eval": _poly_eval(p, lk["key_table_poly"], zeta),
+                "h_1_eval": _poly_eval(p, h_polys[0], zeta), "q_lookup_eval": _poly_eval(p, qlp, zeta),
+                "table_dom_sep_eval": _poly_eval(p, lk["table_dom_sep_poly"], zeta), "q_dom_sep_eval": _poly_eval(p, lk["q_dom_sep_poly"], zeta),
+                "prod_next_eval": _poly_eval(p, pl_poly, zg), "range_table_next_eval": _poly_eval(p, lk["range_table_poly"], zg),
+                "key_table_next_eval": _poly_eval(p, lk["key_table_poly"], zg), "h_1_next_eval": _poly_eval(p, h_polys[0], zg),
+                "h_2_next_eval": _poly_eval(p, h_polys[1], zg), "q_lookup_next_eval": _poly_eval(p, qlp, zg),
+                "w_3_next_eval": _poly_eval(p, wire_polys[3], zg), "w_4_next_eval": _poly_eval(p, wire_polys[4], zg),
+                "table_dom_sep_next_eval": _poly_eval(p, lk["table_dom_sep_poly"], zg)}
+            _append_plookup_evals(tr, fr, st["plookup_evals"])
 
-    # linearization polynomial (snark.rs:419-440; prover.rs:302-360,963-1113)
+    # linearization polynomial (snark.rs:403-428; prover.rs:302-360,963-1113)
     vanish = (pow(zeta, n, p) - 1) % p
     zeta_n2 = (vanish + 1) * zeta % p * zeta % p
     r_quot = list(split[0])
@@ -1053,42 +1093,46 @@ def prove(curve: Curve, cs: PlonkCircuit, pk: dict, blinders: Sequence[int], tra
         coeff = coeff * zeta_n2 % p
         r_quot = _poly_add(p, r_quot, _poly_scale(p, sp, coeff))
     lin = _poly_scale(p, r_quot, (-vanish) % p)
-    we = wires_evals
-    sel = pk["selectors"]
-    r_circ = []
-    for s_idx, sc in ((0, we[0]), (1, we[1]), (2, we[2]), (3, we[3]), (4, we[0] * we[1]), (5, we[2] * we[3]),
-                      (6, pow(we[0], 5, p)), (7, pow(we[1], 5, p)), (8, pow(we[2], 5, p)), (9, pow(we[3], 5, p)),
-                      (12, we[0] * we[1] * we[2] * we[3] * we[4]), (10, -we[4])):
-        r_circ = _poly_add(p, r_circ, _poly_scale(p, sel[s_idx], sc % p))
-    r_circ = _poly_add(p, r_circ, sel[11])
     lagrange_1 = vanish * pow(n_f * (zeta - 1) % p, -1, p) % p
-    c1 = alpha
-    for j in range(nw):
-        c1 = c1 * (we[j] + beta * k[j] % p * zeta + gamma) % p
-    c1 = (c1 + alpha2 * lagrange_1) % p
-    r_perm = _poly_scale(p, z_poly, c1)
-    c2 = alpha * beta % p * perm_next_eval % p
-    for j in range(nw - 1):
-        c2 = c2 * (we[j] + beta * sigma_evals[j] + gamma) % p
-    r_perm = _poly_add(p, r_perm, _poly_scale(p, pk["sigmas"][nw - 1], (-c2) % p))
-    non_quot = _poly_add(p, r_circ, r_perm)
-    if ultra:  # compute_lin_poly_plookup_contribution (prover.rs:1037-1113)
-        pe = plookup_evals
-        alpha4 = alpha2 * alpha2 % p
-        alpha5, alpha6 = alpha4 * alpha % p, alpha4 * alpha2 % p
-        lagrange_n = vanish * g_inv % p * pow(n_f * (zeta - g_inv) % p, -1, p) % p
-        mt = _merged_table(p, tau, pe["range_table_eval"], pe["key_table_eval"], pe["q_lookup_eval"], we[3], we[4], pe["table_dom_sep_eval"])
-        mtn = _merged_table(p, tau, pe["range_table_next_eval"], pe["key_table_next_eval"], pe["q_lookup_next_eval"], pe["w_3_next_eval"],
-                            pe["w_4_next_eval"], pe["table_dom_sep_next_eval"])
-        ml = _merged_lookup(p, tau, we[5], we[0], we[1], we[2], pe["q_lookup_eval"], pe["q_dom_sep_eval"])
-        zmg = (zeta - g_inv) % p
-        cpl = (alpha4 * lagrange_1 + alpha5 * lagrange_n
-               + alpha6 * zmg % p * bp1 % p * ((gamma + ml) % p) % p * ((gb + mt + beta * mtn) % p)) % p
-        r_lookup = _poly_scale(p, pl_poly, cpl)
-        ch2 = (-alpha6) % p * zmg % p * pe["prod_next_eval"] % p * ((gb + pe["h_1_eval"] + beta * pe["h_1_next_eval"]) % p) % p
-        r_lookup = _poly_add(p, r_lookup, _poly_scale(p, h_polys[1], ch2))
-        non_quot = _poly_add(p, non_quot, r_lookup)
-    lin = _poly_add(p, lin, _poly_scale(p, non_quot, 1))  # alpha_base = 1 for the first (only) instance
+    alpha_base = 1
+    for pk, st in zip(pks, I):
+        k = pk["vk"]["k"]
+        we, sigma_evals, perm_next_eval = st["wires_evals"], st["sigma_evals"], st["perm_next_eval"]
+        sel = pk["selectors"]
+        r_circ = []
+        for s_idx, sc in ((0, we[0]), (1, we[1]), (2, we[2]), (3, we[3]), (4, we[0] * we[1]), (5, we[2] * we[3]),
+                          (6, pow(we[0], 5, p)), (7, pow(we[1], 5, p)), (8, pow(we[2], 5, p)), (9, pow(we[3], 5, p)),
+                          (12, we[0] * we[1] * we[2] * we[3] * we[4]), (10, -we[4])):
+            r_circ = _poly_add(p, r_circ, _poly_scale(p, sel[s_idx], sc % p))
+        r_circ = _poly_add(p, r_circ, sel[11])
+        c1 = alpha
+        for j in range(nw):
+            c1 = c1 * (we[j] + beta * k[j] % p * zeta + gamma) % p
+        c1 = (c1 + alpha2 * lagrange_1) % p
+        r_perm = _poly_scale(p, st["z_poly"], c1)
+        c2 = alpha * beta % p * perm_next_eval % p
+        for j in range(nw - 1):
+            c2 = c2 * (we[j] + beta * sigma_evals[j] + gamma) % p
+        r_perm = _poly_add(p, r_perm, _poly_scale(p, pk["sigmas"][nw - 1], (-c2) % p))
+        non_quot = _poly_add(p, r_circ, r_perm)
+        if ultra:  # compute_lin_poly_plookup_contribution (prover.rs:1037-1113)
+            pe = st["plookup_evals"]
+            alpha4 = alpha2 * alpha2 % p
+            alpha5, alpha6 = alpha4 * alpha % p, alpha4 * alpha2 % p
+            lagrange_n = vanish * g_inv % p * pow(n_f * (zeta - g_inv) % p, -1, p) % p
+            mt = _merged_table(p, tau, pe["range_table_eval"], pe["key_table_eval"], pe["q_lookup_eval"], we[3], we[4], pe["table_dom_sep_eval"])
+            mtn = _merged_table(p, tau, pe["range_table_next_eval"], pe["key_table_next_eval"], pe["q_lookup_next_eval"], pe["w_3_next_eval"],
+                                pe["w_4_next_eval"], pe["table_dom_sep_next_eval"])
+            ml = _merged_lookup(p, tau, we[5], we[0], we[1], we[2], pe["q_lookup_eval"], pe["q_dom_sep_eval"])
+            zmg = (zeta - g_inv) % p
+            cpl = (alpha4 * lagrange_1 + alpha5 * lagrange_n
+                   + alpha6 * zmg % p * bp1 % p * ((gamma + ml) % p) % p * ((gb + mt + beta * mtn) % p)) % p
+            r_lookup = _poly_scale(p, st["pl_poly"], cpl)
+            ch2 = (-alpha6) % p * zmg % p * pe["prod_next_eval"] % p * ((gb + pe["h_1_eval"] + beta * pe["h_1_next_eval"]) % p) % p
+            r_lookup = _poly_add(p, r_lookup, _poly_scale(p, st["h_polys"][1], ch2))
+            non_quot = _poly_add(p, non_quot, r_lookup)
+        lin = _poly_add(p, lin, _poly_scale(p, non_quot, alpha_base))
+        alpha_base = alpha_base * alpha_step % p
 
     # ---- round 5 ---------------------------------------------------------------------------------
     v = tr.get_and_append_challenge(fr, b"v")
@@ -1100,25 +1144,74 @@ def prove(curve: Curve, cs: PlonkCircuit, pk: dict, blinders: Sequence[int], tra
             coeff = coeff * r % p
         return commit(_div_linear(p, acc, point))
 
-    open_polys = [lin] + wire_polys + pk["sigmas"][:nw - 1]
-    shifted_polys = [z_poly]
-    if ultra:  # plookup_open_polys_ref / plookup_shifted_open_polys_ref (prover.rs:427-460)
-        open_polys += [lk["range_table_poly"], lk["key_table_poly"], h_polys[0], pk["selectors"][N_SELECTORS], lk["table_dom_sep_poly"],
-                       lk["q_dom_sep_poly"]]
-        shifted_polys += [pl_poly, lk["range_table_poly"], lk["key_table_poly"], h_polys[0], h_polys[1], pk["selectors"][N_SELECTORS],
-                          wire_polys[3], wire_polys[4], lk["table_dom_sep_poly"]]
+    open_polys = [lin]
+    shifted_polys = []
+    for pk, st in zip(pks, I):
+        open_polys += st["wire_polys"] + pk["sigmas"][:nw - 1]
+        shifted_polys += [st["z_poly"]]
+        if ultra:  # plookup_open_polys_ref / plookup_shifted_open_polys_ref (prover.rs:427-460)
+            lk, h_polys = pk["plookup"], st["h_polys"]
+            open_polys += [lk["range_table_poly"], lk["key_table_poly"], h_polys[0], pk["selectors"][N_SELECTORS], lk["table_dom_sep_poly"],
+                           lk["q_dom_sep_poly"]]
+            shifted_polys += [st["pl_poly"], lk["range_table_poly"], lk["key_table_poly"], h_polys[0], h_polys[1], pk["selectors"][N_SELECTORS],
+                              st["wire_polys"][3], st["wire_polys"][4], lk["table_dom_sep_poly"]]
     opening = batched_witness(open_polys, v, zeta)
     shifted = batched_witness(shifted_polys, v, zg)
-    proof = {
-        "wires_poly_comms": wires_comms, "prod_perm_poly_comm": z_comm, "split_quot_poly_comms": split_comms,
-        "opening_proof": opening, "shifted_opening_proof": shifted,
-        "wires_evals": wires_evals, "wire_sigma_evals": sigma_evals, "perm_next_eval": perm_next_eval,
-        "plookup_proof": None,
+    return {
+        "wires_poly_comms_vec": [st["wires_comms"] for st in I], "prod_perm_poly_comms_vec": [st["z_comm"] for st in I],
+        "poly_evals_vec": [{"wires_evals": st["wires_evals"], "wire_sigma_evals": st["sigma_evals"], "perm_next_eval": st["perm_next_eval"]}
+                           for st in I],
+        "plookup_proofs_vec": [({"h_poly_comms": st["h_comms"], "prod_lookup_poly_comm": st["pl_comm"], "poly_evals": st["plookup_evals"]}
+                                if ultra else None) for st in I],
+        "split_quot_poly_comms": split_comms, "opening_proof": opening, "shifted_opening_proof": shifted,
         "challenges": {"tau": tau, "beta": beta, "gamma": gamma, "alpha": alpha, "zeta": zeta, "v": v},
     }
-    if ultra:
-        proof["plookup_proof"] = {"h_poly_comms": h_comms, "prod_lookup_poly_comm": pl_comm, "poly_evals": plookup_evals}
-    return proof
+
+
+def _ser_plookup_proof(curve, fr, lp) -> bytes:
+    out = bytearray()
+    if lp is None:
+        return b"\x00"
+    out += b"\x01"
+    out += struct.pack("<Q", len(lp["h_poly_comms"]))
+    for c in lp["h_poly_comms"]:
+        out += ser_g1(curve, c)
+    out += ser_g1(curve, lp["prod_lookup_poly_comm"])
+    for name in PLOOKUP_EVAL_FIELDS:
+        out += ser_fr(fr, lp["poly_evals"][name])
+    return bytes(out)
+
+
+def serialize_batch_proof(curve: Curve, bp: dict) -> bytes:
+    """`BatchProof<E>` CanonicalSerialize (compressed), field order of structs.rs:271-292."""
+    fr = curve.fr
+    out = bytearray()
+    out += struct.pack("<Q", len(bp["wires_poly_comms_vec"]))
+    for comms in bp["wires_poly_comms_vec"]:
+        out += struct.pack("<Q", len(comms))
+        for c in comms:
+            out += ser_g1(curve, c)
+    out += struct.pack("<Q", len(bp["prod_perm_poly_comms_vec"]))
+    for c in bp["prod_perm_poly_comms_vec"]:
+        out += ser_g1(curve, c)
+    out += struct.pack("<Q", len(bp["poly_evals_vec"]))
+    for pe in bp["poly_evals_vec"]:
+        out += struct.pack("<Q", len(pe["wires_evals"]))
+        for e in pe["wires_evals"]:
+            out += ser_fr(fr, e)
+        out += struct.pack("<Q", len(pe["wire_sigma_evals"]))
+        for e in pe["wire_sigma_evals"]:
+            out += ser_fr(fr, e)
+        out += ser_fr(fr, pe["perm_next_eval"])
+    out += struct.pack("<Q", len(bp["plookup_proofs_vec"]))
+    for lp in bp["plookup_proofs_vec"]:
+        out += _ser_plookup_proof(curve, fr, lp)
+    out += struct.pack("<Q", len(bp["split_quot_poly_comms"]))
+    for c in bp["split_quot_poly_comms"]:
+        out += ser_g1(curve, c)
+    out += ser_g1(curve, bp["opening_proof"])
+    out += ser_g1(curve, bp["shifted_opening_proof"])
+    return bytes(out)
 
 
 def serialize_proof(curve: Curve, proof: dict) -> bytes:
@@ -1157,141 +1250,176 @@ def serialize_proof(curve: Curve, proof: dict) -> bytes:
 
 def verify(curve: Curve, vk: dict, pub_input: Sequence[int], proof: dict, beta_srs: int, transcript: str = "solidity",
            extra_msg: Optional[bytes] = None) -> bool:
-    """verifier.rs (prepare_pcs_info + batch_verify_opening_proofs for one proof, TurboPlonk or UltraPlonk); the pairing check
-    e(A,[x]_2) == e(B,[1]_2) is evaluated as x*A == B with the known trapdoor x = beta_srs."""
+    """`PlonkKzgSnark::verify` (one instance): `From<Proof> for BatchProof` (structs.rs:319-331), then `batch_verify`."""
+    bp = {"wires_poly_comms_vec": [proof["wires_poly_comms"]], "prod_perm_poly_comms_vec": [proof["prod_perm_poly_comm"]],
+          "poly_evals_vec": [{"wires_evals": proof["wires_evals"], "wire_sigma_evals": proof["wire_sigma_evals"],
+                              "perm_next_eval": proof["perm_next_eval"]}],
+          "plookup_proofs_vec": [proof.get("plookup_proof")], "split_quot_poly_comms": proof["split_quot_poly_comms"],
+          "opening_proof": proof["opening_proof"], "shifted_opening_proof": proof["shifted_opening_proof"]}
+    return batch_verify(curve, [vk], [pub_input], bp, beta_srs, transcript, extra_msg)
+
+
+def batch_verify(curve: Curve, vks: Sequence[dict], pub_inputs: Sequence[Sequence[int]], bp: dict, beta_srs: int,
+                 transcript: str = "solidity", extra_msg: Optional[bytes] = None) -> bool:
+    """verifier.rs: prepare_pcs_info (:68-193) + batch_verify_opening_proofs (:195-254) for ONE batch proof over several instances,
+    TurboPlonk or UltraPlonk; the pairing check e(A,[x]_2) == e(B,[1]_2) is evaluated as x*A == B with the known trapdoor
+    x = beta_srs."""
     fr, p = curve.fr, curve.fr.p
-    n = vk["domain_size"]
+    ninst = len(vks)
+    if ninst == 0 or len(pub_inputs) != ninst or len(bp["prod_perm_poly_comms_vec"]) != ninst:
+        return False
+    n = vks[0]["domain_size"]
     dom = Radix2Domain(fr, n)
     g = dom.group_gen
     g_inv = pow(g, -1, p)
-    k = vk["k"]
-    lp = proof.get("plookup_proof")
-    if (vk.get("plookup") is not None) != (lp is not None):   # verifier.rs:97
-        return False
-    nw = len(proof["wires_poly_comms"])
-    if len(pub_input) != vk["num_inputs"] or nw != len(k):
-        return False
-    # compute_challenges (verifier.rs:257-318)
+    for vk, pi, lp, wc in zip(vks, pub_inputs, bp["plookup_proofs_vec"], bp["wires_poly_comms_vec"]):
+        if (vk.get("plookup") is not None) != (lp is not None):   # verifier.rs:97
+            return False
+        if vk["domain_size"] != n or len(pi) != vk["num_inputs"] or len(wc) != len(vk["k"]):
+            return False
+    # compute_challenges (verifier.rs:256-318)
     tr = TRANSCRIPTS[transcript](b"PlonkProof")
     if extra_msg is not None:
         tr.append_message(b"extra info", extra_msg)
-    append_vk_and_pub_input(tr, curve, vk, pub_input)
-    for c in proof["wires_poly_comms"]:
-        tr.append_message(b"witness_poly_comms", ser_g1(curve, c))
+    for vk, pi in zip(vks, pub_inputs):
+        append_vk_and_pub_input(tr, curve, vk, pi)
+    for comms in bp["wires_poly_comms_vec"]:
+        for c in comms:
+            tr.append_message(b"witness_poly_comms", ser_g1(curve, c))
     tau = tr.get_and_append_challenge(fr, b"tau")
-    if lp is not None:
-        for c in lp["h_poly_comms"]:
-            tr.append_message(b"h_poly_comms", ser_g1(curve, c))
+    for lp in bp["plookup_proofs_vec"]:
+        if lp is not None:
+            for c in lp["h_poly_comms"]:
+                tr.append_message(b"h_poly_comms", ser_g1(curve, c))
     beta = tr.get_and_append_challenge(fr, b"beta")
     gamma = tr.get_and_append_challenge(fr, b"gamma")
-    tr.append_message(b"perm_poly_comms", ser_g1(curve, proof["prod_perm_poly_comm"]))
-    if lp is not None:
-        tr.append_message(b"plookup_poly_comms", ser_g1(curve, lp["prod_lookup_poly_comm"]))
+    for c in bp["prod_perm_poly_comms_vec"]:
+        tr.append_message(b"perm_poly_comms", ser_g1(curve, c))
+    for lp in bp["plookup_proofs_vec"]:
+        if lp is not None:
+            tr.append_message(b"plookup_poly_comms", ser_g1(curve, lp["prod_lookup_poly_comm"]))
     alpha = tr.get_and_append_challenge(fr, b"alpha")
-    for c in proof["split_quot_poly_comms"]:
+    for c in bp["split_quot_poly_comms"]:
         tr.append_message(b"quot_poly_comms", ser_g1(curve, c))
     zeta = tr.get_and_append_challenge(fr, b"zeta")
-    for e in proof["wires_evals"]:
-        tr.append_message(b"wire_evals", ser_fr(fr, e))
-    for e in proof["wire_sigma_evals"]:
-        tr.append_message(b"wire_sigma_evals", ser_fr(fr, e))
-    tr.append_message(b"perm_next_eval", ser_fr(fr, proof["perm_next_eval"]))
-    if lp is not None:
-        _append_plookup_evals(tr, fr, lp["poly_evals"])
+    for pe in bp["poly_evals_vec"]:
+        for e in pe["wires_evals"]:
+            tr.append_message(b"wire_evals", ser_fr(fr, e))
+        for e in pe["wire_sigma_evals"]:
+            tr.append_message(b"wire_sigma_evals", ser_fr(fr, e))
+        tr.append_message(b"perm_next_eval", ser_fr(fr, pe["perm_next_eval"]))
+    for lp in bp["plookup_proofs_vec"]:
+        if lp is not None:
+            _append_plookup_evals(tr, fr, lp["poly_evals"])
     v = tr.get_and_append_challenge(fr, b"v")
-    tr.append_message(b"open_proof", ser_g1(curve, proof["opening_proof"]))
-    tr.append_message(b"shifted_open_proof", ser_g1(curve, proof["shifted_opening_proof"]))
+    tr.append_message(b"open_proof", ser_g1(curve, bp["opening_proof"]))
+    tr.append_message(b"shifted_open_proof", ser_g1(curve, bp["shifted_opening_proof"]))
     u = tr.get_and_append_challenge(fr, b"u")
 
     alpha2 = alpha * alpha % p
     alpha3, alpha4 = alpha2 * alpha % p, alpha2 * alpha2 % p
     alpha5, alpha6 = alpha4 * alpha % p, alpha4 * alpha2 % p
+    alpha7 = alpha6 * alpha % p
+    step = alpha7 if vks[0].get("plookup") is not None else alpha3   # verifier.rs:131-138
+    alpha_bases = [1]
+    for _ in range(ninst - 1):
+        alpha_bases.append(alpha_bases[-1] * step % p)
     vanish = (pow(zeta, n, p) - 1) % p
     n_f = n % p
     lagrange_1 = vanish * pow(n_f * (zeta - 1) % p, -1, p) % p
     lagrange_n = vanish * g_inv % p * pow(n_f * (zeta - g_inv) % p, -1, p) % p
     bp1 = (1 + beta) % p
     gb = gamma * bp1 % p
-    we, se, pne = proof["wires_evals"], proof["wire_sigma_evals"], proof["perm_next_eval"]
-    # evaluate_pi_poly (verifier.rs:765-805)
-    pi_eval = 0
-    if vanish:
-        vdn = pow(n_f, -1, p) * vanish % p
-        for i, val in enumerate(pub_input):
-            e = dom.element(i)
-            pi_eval = (pi_eval + vdn * e % p * pow((zeta - e) % p, -1, p) % p * val) % p
-    # compute_lin_poly_constant_term (verifier.rs:340-418)
-    tmp = (pi_eval - alpha2 * lagrange_1) % p
-    acc = alpha * pne % p * ((gamma + we[nw - 1]) % p) % p
-    for j in range(nw - 1):
-        acc = acc * ((gamma + we[j] + beta * se[j]) % p) % p
-    lin_const = (tmp - acc) % p
-    if lp is not None:
-        ev_ = lp["poly_evals"]
-        pc = (lagrange_n * ((ev_["h_1_eval"] - ev_["h_2_next_eval"] - alpha2) % p) - alpha * lagrange_1
-              - alpha3 * ((zeta - g_inv) % p) % p * ev_["prod_next_eval"] % p
-              * ((gb + ev_["h_1_eval"] + beta * ev_["h_1_next_eval"]) % p) % p * ((gb + beta * ev_["h_2_next_eval"]) % p)) % p
-        lin_const = (lin_const + alpha3 * pc) % p
-    # linearization_scalars_and_bases (verifier.rs:513-670)
+
+    lin_const = 0
     sb: List[Tuple[int, object]] = []
-    coeff = alpha2 * lagrange_1 % p
-    c = alpha
-    for j in range(nw):
-        c = c * ((beta * k[j] % p * zeta + gamma + we[j]) % p) % p
-    sb.append(((coeff + c) % p, proof["prod_perm_poly_comm"]))
-    c = alpha * beta % p * pne % p
-    for j in range(nw - 1):
-        c = c * ((beta * se[j] + gamma + we[j]) % p) % p
-    sb.append(((-c) % p, vk["sigma_comms"][nw - 1]))
-    qs = [we[0], we[1], we[2], we[3], we[0] * we[1] % p, we[2] * we[3] % p, pow(we[0], 5, p), pow(we[1], 5, p),
-          pow(we[2], 5, p), pow(we[3], 5, p), (-we[4]) % p, 1, we[0] * we[1] * we[2] * we[3] * we[4] % p]
-    for s_, cm in zip(qs, vk["selector_comms"]):   # 13 scalars: the q_lookup commitment (14th) is not part of [D]
-        sb.append((s_, cm))
-    if lp is not None:
-        ev_ = lp["poly_evals"]
-        ml = _merged_lookup(p, tau, we[5], we[0], we[1], we[2], ev_["q_lookup_eval"], ev_["q_dom_sep_eval"])
-        mt = _merged_table(p, tau, ev_["range_table_eval"], ev_["key_table_eval"], ev_["q_lookup_eval"], we[3], we[4], ev_["table_dom_sep_eval"])
-        mtn = _merged_table(p, tau, ev_["range_table_next_eval"], ev_["key_table_next_eval"], ev_["q_lookup_next_eval"], ev_["w_3_next_eval"],
-                            ev_["w_4_next_eval"], ev_["table_dom_sep_next_eval"])
-        cpl = (alpha4 * lagrange_1 + alpha5 * lagrange_n
-               + alpha6 * ((zeta - g_inv) % p) % p * bp1 % p * ((gamma + ml) % p) % p * ((gb + mt + beta * mtn) % p)) % p
-        sb.append((cpl, lp["prod_lookup_poly_comm"]))
-        ch2 = alpha6 * ((g_inv - zeta) % p) % p * ev_["prod_next_eval"] % p * ((gb + ev_["h_1_eval"] + beta * ev_["h_1_next_eval"]) % p) % p
-        sb.append((ch2, lp["h_poly_comms"][1]))
+    for vk, pub_input, pe, lp, z_comm, ab in zip(vks, pub_inputs, bp["poly_evals_vec"], bp["plookup_proofs_vec"],
+                                                  bp["prod_perm_poly_comms_vec"], alpha_bases):
+        k = vk["k"]
+        nw = len(k)
+        we, se, pne = pe["wires_evals"], pe["wire_sigma_evals"], pe["perm_next_eval"]
+        # evaluate_pi_poly (verifier.rs:845-881)
+        pi_eval = 0
+        if vanish:
+            vdn = pow(n_f, -1, p) * vanish % p
+            for i, val in enumerate(pub_input):
+                e = dom.element(i)
+                pi_eval = (pi_eval + vdn * e % p * pow((zeta - e) % p, -1, p) % p * val) % p
+        # compute_lin_poly_constant_term (verifier.rs:340-418)
+        tmp = (pi_eval - alpha2 * lagrange_1) % p
+        acc = alpha * pne % p * ((gamma + we[nw - 1]) % p) % p
+        for j in range(nw - 1):
+            acc = acc * ((gamma + we[j] + beta * se[j]) % p) % p
+        tmp = (tmp - acc) % p
+        if lp is not None:
+            ev_ = lp["poly_evals"]
+            pc = (lagrange_n * ((ev_["h_1_eval"] - ev_["h_2_next_eval"] - alpha2) % p) - alpha * lagrange_1
+                  - alpha3 * ((zeta - g_inv) % p) % p * ev_["prod_next_eval"] % p
+                  * ((gb + ev_["h_1_eval"] + beta * ev_["h_1_next_eval"]) % p) % p * ((gb + beta * ev_["h_2_next_eval"]) % p)) % p
+            tmp = (tmp + alpha3 * pc) % p
+        lin_const = (lin_const + ab * tmp) % p
+        # linearization_scalars_and_bases (verifier.rs:513-656)
+        coeff = alpha2 * lagrange_1 % p
+        c = alpha
+        for j in range(nw):
+            c = c * ((beta * k[j] % p * zeta + gamma + we[j]) % p) % p
+        sb.append(((coeff + c) * ab % p, z_comm))
+        c = alpha * beta % p * pne % p
+        for j in range(nw - 1):
+            c = c * ((beta * se[j] + gamma + we[j]) % p) % p
+        sb.append(((-c * ab) % p, vk["sigma_comms"][nw - 1]))
+        qs = [we[0], we[1], we[2], we[3], we[0] * we[1] % p, we[2] * we[3] % p, pow(we[0], 5, p), pow(we[1], 5, p),
+              pow(we[2], 5, p), pow(we[3], 5, p), (-we[4]) % p, 1, we[0] * we[1] * we[2] * we[3] * we[4] % p]
+        for s_, cm in zip(qs, vk["selector_comms"]):   # 13 scalars: the q_lookup commitment (14th) is not part of [D]
+            sb.append((s_ * ab % p, cm))
+        if lp is not None:
+            ev_ = lp["poly_evals"]
+            ml = _merged_lookup(p, tau, we[5], we[0], we[1], we[2], ev_["q_lookup_eval"], ev_["q_dom_sep_eval"])
+            mt = _merged_table(p, tau, ev_["range_table_eval"], ev_["key_table_eval"], ev_["q_lookup_eval"], we[3], we[4], ev_["table_dom_sep_eval"])
+            mtn = _merged_table(p, tau, ev_["range_table_next_eval"], ev_["key_table_next_eval"], ev_["q_lookup_next_eval"], ev_["w_3_next_eval"],
+                                ev_["w_4_next_eval"], ev_["table_dom_sep_next_eval"])
+            cpl = (alpha4 * lagrange_1 + alpha5 * lagrange_n
+                   + alpha6 * ((zeta - g_inv) % p) % p * bp1 % p * ((gamma + ml) % p) % p * ((gb + mt + beta * mtn) % p)) % p
+            sb.append((cpl * ab % p, lp["prod_lookup_poly_comm"]))
+            ch2 = alpha6 * ((g_inv - zeta) % p) % p * ev_["prod_next_eval"] % p * ((gb + ev_["h_1_eval"] + beta * ev_["h_1_next_eval"]) % p) % p
+            sb.append((ch2 * ab % p, lp["h_poly_comms"][1]))
     zeta_n2 = (1 + vanish) * zeta % p * zeta % p
     coeff = (-vanish) % p
-    sb.append((coeff, proof["split_quot_poly_comms"][0]))
-    for cm in proof["split_quot_poly_comms"][1:]:
+    sb.append((coeff, bp["split_quot_poly_comms"][0]))
+    for cm in bp["split_quot_poly_comms"][1:]:
         coeff = coeff * zeta_n2 % p
         sb.append((coeff, cm))
-    # aggregate_poly_commitments / aggregate_evaluations (verifier.rs:421-511,673-745)
+    # aggregate_poly_commitments / aggregate_evaluations (verifier.rs:421-511,673-745): the powers of v run on across the instances
     v_base, uv_base = v, u
-    buf = []
-    for cm in proof["wires_poly_comms"]:
-        buf.append(v_base); sb.append((v_base, cm)); v_base = v_base * v % p
-    for cm in vk["sigma_comms"][:nw - 1]:
-        buf.append(v_base); sb.append((v_base, cm)); v_base = v_base * v % p
-    buf.append(uv_base); sb.append((uv_base, proof["prod_perm_poly_comm"])); uv_base = uv_base * v % p
-    evals = list(we) + list(se) + [pne]
-    if lp is not None:
-        lvk = vk["plookup"]
-        for cm in (lvk["range_table_comm"], lvk["key_table_comm"], lp["h_poly_comms"][0], vk["selector_comms"][N_SELECTORS],
-                   lvk["table_dom_sep_comm"], lvk["q_dom_sep_comm"]):
+    buf, evals = [], []
+    for vk, wires, pe, lp, z_comm in zip(vks, bp["wires_poly_comms_vec"], bp["poly_evals_vec"], bp["plookup_proofs_vec"],
+                                         bp["prod_perm_poly_comms_vec"]):
+        nw = len(wires)
+        for cm in wires:
             buf.append(v_base); sb.append((v_base, cm)); v_base = v_base * v % p
-        for cm in (lp["prod_lookup_poly_comm"], lvk["range_table_comm"], lvk["key_table_comm"], lp["h_poly_comms"][0], lp["h_poly_comms"][1],
-                   vk["selector_comms"][N_SELECTORS], proof["wires_poly_comms"][3], proof["wires_poly_comms"][4], lvk["table_dom_sep_comm"]):
-            buf.append(uv_base); sb.append((uv_base, cm)); uv_base = uv_base * v % p
-        evals += _plookup_evals_vec(lp["poly_evals"]) + _plookup_next_evals_vec(lp["poly_evals"])
+        for cm in vk["sigma_comms"][:nw - 1]:
+            buf.append(v_base); sb.append((v_base, cm)); v_base = v_base * v % p
+        buf.append(uv_base); sb.append((uv_base, z_comm)); uv_base = uv_base * v % p
+        evals += list(pe["wires_evals"]) + list(pe["wire_sigma_evals"]) + [pe["perm_next_eval"]]
+        if lp is not None:
+            lvk = vk["plookup"]
+            for cm in (lvk["range_table_comm"], lvk["key_table_comm"], lp["h_poly_comms"][0], vk["selector_comms"][N_SELECTORS],
+                       lvk["table_dom_sep_comm"], lvk["q_dom_sep_comm"]):
+                buf.append(v_base); sb.append((v_base, cm)); v_base = v_base * v % p
+            for cm in (lp["prod_lookup_poly_comm"], lvk["range_table_comm"], lvk["key_table_comm"], lp["h_poly_comms"][0], lp["h_poly_comms"][1],
+                       vk["selector_comms"][N_SELECTORS], wires[3], wires[4], lvk["table_dom_sep_comm"]):
+                buf.append(uv_base); sb.append((uv_base, cm)); uv_base = uv_base * v % p
+            evals += _plookup_evals_vec(lp["poly_evals"]) + _plookup_next_evals_vec(lp["poly_evals"])
     ev = (-lin_const) % p
     assert len(buf) == len(evals)
     for b_, e in zip(buf, evals):
         ev = (ev + e * b_) % p
-    # batch_verify_opening_proofs with one instance (r = 1)
-    A = curve.add(proof["opening_proof"], curve.mul(u, proof["shifted_opening_proof"]))
+    # batch_verify_opening_proofs with one batch proof (r = 1)
+    A = curve.add(bp["opening_proof"], curve.mul(u, bp["shifted_opening_proof"]))
     B = None
     for s_, cm in sb:
         B = curve.add(B, curve.mul(s_ % p, cm))
-    B = curve.add(B, curve.mul(zeta, proof["opening_proof"]))
-    B = curve.add(B, curve.mul(u * (zeta * g % p) % p, proof["shifted_opening_proof"]))
+    B = curve.add(B, curve.mul(zeta, bp["opening_proof"]))
+    B = curve.add(B, curve.mul(u * (zeta * g % p) % p, bp["shifted_opening_proof"]))
     B = curve.add(B, curve.mul((-ev) % p, curve.gen))
     return curve.mul(beta_srs % p, A) == B

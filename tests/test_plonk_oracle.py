@@ -133,3 +133,38 @@ def test_ultraplonk_lookup_outside_the_table_is_refused(P, py):
     assert not cs.check_satisfiability()
     with pytest.raises(ValueError, match="sorted vector has wrong length"):
         P.prove(cv, cs, pk, list(range(1, 30)), "solidity")
+
+
+@pytest.mark.parametrize("kind", ["solidity", "standard"])
+@pytest.mark.parametrize("ultra", [False, True], ids=["turbo", "ultra"])
+def test_batch_prove_several_instances(P, py, kind, ultra):
+    """`batch_prove` (snark.rs:201-469): three instances over one domain, one transcript, ONE quotient (alpha bases 1, a, a^2 with
+    a = alpha^3 | alpha^7) and one pair of opening proofs; the batch verifier restated from verifier.rs:68-254 accepts."""
+    cv = py.BN254
+    css = [P.gen_circuit_for_test(3, 2, ultra=ultra), P.gen_circuit_for_test(3, 1, ultra=ultra),
+           P.gen_circuit_for_test(5, 3, ultra=ultra) if ultra else P.gen_circuit_for_bench(32)]
+    assert len({cs.n for cs in css}) == 1
+    beta = 0x7777777777777777777 % cv.fr.p
+    srs = P.gen_srs(cv, beta, css[0].n + 2)
+    pks = [P.preprocess(cv, srs, cs) for cs in css]
+    rnd = random.Random(6)
+    bl = [rnd.randrange(cv.fr.p) for _ in range(P.batch_num_blinders(css))]
+    bp = P.batch_prove(cv, css, pks, bl, kind)
+    vks, pis = [pk["vk"] for pk in pks], [cs.public_input() for cs in css]
+    assert P.batch_verify(cv, vks, pis, bp, beta, kind)
+    # instance order matters; every instance's evaluations are bound
+    assert not P.batch_verify(cv, [vks[1], vks[0], vks[2]], [pis[1], pis[0], pis[2]], bp, beta, kind)
+    for i in range(3):
+        pe = [dict(x) for x in bp["poly_evals_vec"]]
+        pe[i]["wires_evals"] = [(pe[i]["wires_evals"][0] + 1) % cv.fr.p] + pe[i]["wires_evals"][1:]
+        assert not P.batch_verify(cv, vks, pis, dict(bp, poly_evals_vec=pe), beta, kind)
+    # a batch of one is `prove` (structs.rs:302-331)
+    one = P.batch_prove(cv, css[:1], pks[:1], bl[:2 * css[0].nw] + bl[2 * css[0].nw * 3:][:0] + [7] * (P.batch_num_blinders(css[:1]) - 2 * css[0].nw), kind)
+    single = P.prove(cv, css[0], pks[0], bl[:2 * css[0].nw] + [7] * (P.num_blinders(css[0]) - 2 * css[0].nw), kind)
+    assert single["wires_poly_comms"] == one["wires_poly_comms_vec"][0] and single["opening_proof"] == one["opening_proof"]
+    assert P.verify(cv, vks[0], pis[0], single, beta, kind)
+    # instances over different domains are refused (snark.rs:228-236)
+    other = P.gen_circuit_for_bench(200, ultra=ultra)
+    with pytest.raises(ValueError, match="domain size"):
+        P.batch_prove(cv, [css[0], other], [pks[0], P.preprocess(cv, P.gen_srs(cv, beta, other.n + 2), other)],
+                      [1] * P.batch_num_blinders([css[0], other]), kind)
