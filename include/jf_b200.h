@@ -299,6 +299,24 @@ int jf_ultraplonk_prove(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *witness, c
                         const uint8_t *extra_msg, size_t extra_len, jf_ultraplonk_proof *out);
 long jf_ultraplonk_proof_serialize(const jf_ultraplonk_proof *proof, uint8_t *out, size_t cap);
 
+/* ---- several instances in one proof -----------------------------------------------------------------------------------------
+ * == `PlonkKzgSnark::batch_prove` -> `batch_prove_internal` (snark.rs:201-469): `count` instances over the same domain size and the
+ * same commit key share one transcript, ONE quotient polynomial (instance i enters with alpha_base_i = (alpha^3 | alpha^7)^i,
+ * prover.rs:661-669) and ONE pair of opening proofs.  pks: one proving key per instance (each key owns its device workspace, so
+ * the same circuit twice needs two keys; all built with the same flags).  blinders, in the order the reference's single prng is
+ * consumed: the wire masks of every instance (2 x 5|6 each), [UltraPlonk: the h1 / h2 masks of every instance (6 each),] the
+ * permutation-product masks (3 each), [the lookup-product masks (3 each),] then the 4|5 split-quotient randomizers:
+ * count x 13 + 4 (TurboPlonk) or count x 24 + 5 (UltraPlonk) field elements.  out: `count` proof records; record i holds instance
+ * i's commitments and evaluations, the shared parts (split quotient commitments, opening proofs) are written to every record.
+ * The batch serialisers emit `BatchProof<E>` (structs.rs:271-292); a batch of one equals jf_plonk_prove. */
+int jf_plonk_batch_prove(jf_ctx *ctx, jf_plonk_pk *const *pks, size_t count, const uint64_t *const *witnesses, const uint64_t *blinders,
+                         int transcript_kind, const uint8_t *extra_msg, size_t extra_len, jf_plonk_proof *out);
+int jf_ultraplonk_batch_prove(jf_ctx *ctx, jf_plonk_pk *const *pks, size_t count, const uint64_t *const *witnesses,
+                              const uint64_t *blinders, int transcript_kind, const uint8_t *extra_msg, size_t extra_len,
+                              jf_ultraplonk_proof *out);
+long jf_plonk_batch_proof_serialize(const jf_plonk_proof *proofs, size_t count, uint8_t *out, size_t cap);
+long jf_ultraplonk_batch_proof_serialize(const jf_ultraplonk_proof *proofs, size_t count, uint8_t *out, size_t cap);
+
 /* Host-only pieces of the transcripts (no GPU needed): sha3 `Keccak256`, and `PlonkTranscript`
  * new / append_message / get_and_append_challenge (plonk/src/transcript/{solidity,standard}.rs). */
 void jf_keccak256(const uint8_t *data, size_t len, uint8_t out[32]);

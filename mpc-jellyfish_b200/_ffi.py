@@ -142,6 +142,13 @@ SIGNATURES = {
     "jf_ultraplonk_prove": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64p, c_u64p, ctypes.c_int, ctypes.c_char_p,
                                            ctypes.c_size_t, ctypes.POINTER(UltraPlonkProofStruct)]),
     "jf_ultraplonk_proof_serialize": (ctypes.c_long, [ctypes.POINTER(UltraPlonkProofStruct), ctypes.c_char_p, ctypes.c_size_t]),
+    "jf_plonk_batch_prove": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, ctypes.c_size_t, ctypes.POINTER(c_u64p), c_u64p, ctypes.c_int,
+                                            ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(PlonkProofStruct)]),
+    "jf_ultraplonk_batch_prove": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, ctypes.c_size_t, ctypes.POINTER(c_u64p), c_u64p, ctypes.c_int,
+                                                 ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(UltraPlonkProofStruct)]),
+    "jf_plonk_batch_proof_serialize": (ctypes.c_long, [ctypes.POINTER(PlonkProofStruct), ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]),
+    "jf_ultraplonk_batch_proof_serialize": (ctypes.c_long, [ctypes.POINTER(UltraPlonkProofStruct), ctypes.c_size_t, ctypes.c_char_p,
+                                                            ctypes.c_size_t]),
     "jf_plonk_vk_commitments": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64p, ctypes.POINTER(ctypes.c_int)]),
     "jf_plonk_pk_free": (None, [ctypes.c_void_p, ctypes.c_void_p]),
     "jf_plonk_prove": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64p, c_u64p, ctypes.c_int, ctypes.c_char_p,

@@ -291,6 +291,8 @@ template <class F, int NW> struct QuotArgs {
     Fp<F> beta_k[NW], beta, gamma, alpha, alpha2;
     Fp<F> zh_inv[8];
     Fp<F> omega_inv;    // w_n^-1 (UltraPlonk)
+    Fp<F> scale;        // batch_prove: instance i enters the ONE quotient with alpha_base_i (prover.rs:661-669)
+    uint32_t acc_mode;  // 0: out = t;  1: out += scale * t
     Fp<F> *out;
     uint32_t m, ratio;  // m: evaluation points per polynomial (8n, or 6n by sub-cosets)
     uint32_t zero_sel;  // bit s set: selector s is the zero polynomial (its term and its loads are skipped)
@@ -385,7 +387,9 @@ template <class F, int NW> __global__ void __launch_bounds__(128) quotient_kerne
         const E b = E::mul(E::mul(pn, E::add(E::add(k.gb, h1x), E::mul(q.beta, h1n))), E::add(E::add(k.gb, h2x), E::mul(q.beta, h2n)));
         t = E::add(t, E::mul(ap, E::mul(E::sub(x, q.omega_inv), E::sub(a, b))));
     }
-    stf(q.out + i, E::add(E::mul(t, q.zh_inv[row]), t2));
+    E res = E::add(E::mul(t, q.zh_inv[row]), t2);
+    if (q.acc_mode) res = E::add(ldf(q.out + i), E::mul(q.scale, res));
+    stf(q.out + i, res);
 }
 // WrongQuotientPolyDegree (prover.rs:916-919): coefficient `deg` must be non-zero, all above zero
 template <class F> __global__ void degree_check_kernel(const Fp<F> *c, size_t deg, size_t m, int *err) {
@@ -514,6 +518,7 @@ template <class F> struct LinArgs {
     uint32_t len[LC_MAX];
     Fp<F> s[LC_MAX];
     int count;
+    int accumulate;  // != 0: out += (a batch proof has more (scalar, polynomial) pairs than one launch carries)
     Fp<F> *out;
     uint32_t out_len;
 };
@@ -521,7 +526,7 @@ template <class F> __global__ void lincomb_kernel(const __grid_constant__ LinArg
     using E = Fp<F>;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.out_len) return;
-    E acc = E::zero();
+    E acc = a.accumulate ? ldf(a.out + i) : E::zero();
     for (int k = 0; k < a.count; k++)
         if (i < a.len[k]) acc = E::add(acc, E::mul(a.s[k], ldf(a.p[k] + i)));
     stf(a.out + i, acc);
@@ -1150,97 +1155,178 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
     }
 
     // ------------------------------------------------------------------------------------------
+    // one (scalar, polynomial) pair of a linear combination; `lincomb_many` issues as many launches as the list needs
+    struct Term { const E *p; size_t len; E s; };
+    static int lincomb_many(jf_ctx *ctx, const std::vector<Term> &terms, E *out, size_t out_len) {
+        size_t done = 0;
+        do {
+            LinArgs<Fr> la;
+            const size_t cnt = std::min<size_t>(LC_MAX, terms.size() - done);
+            for (size_t c = 0; c < cnt; c++) {
+                la.p[c] = terms[done + c].p;
+                la.len[c] = (uint32_t)terms[done + c].len;
+                la.s[c] = terms[done + c].s;
+            }
+            la.count = (int)cnt;
+            la.accumulate = done ? 1 : 0;
+            la.out = out;
+            la.out_len = (uint32_t)out_len;
+            JF_LAUNCH(ctx, "lincomb", lincomb_kernel<Fr><<<(unsigned)((out_len + 127) / 128), 128, 0, ctx->stream>>>(la));
+            done += cnt;
+        } while (done < terms.size());
+        return JF_OK;
+    }
+
     template <class ProofT>
     static int prove(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *witness, const uint64_t *blinders, int kind,
                      const uint8_t *extra, size_t extra_len, ProofT *out) {
-        const size_t n = pk->n, m = pk->mq, np = pk->np;  // m: evaluation points per polynomial in round 3
+        return batch_prove(ctx, &pk, 1, &witness, blinders, kind, extra, extra_len, out);
+    }
+
+    // `PlonkKzgSnark::batch_prove` -> batch_prove_internal (snark.rs:201-469): `count` instances over one domain and one commit
+    // key share the transcript, ONE quotient polynomial (instance i enters with alpha_base_i = (alpha^3 | alpha^7)^i) and ONE pair
+    // of opening proofs.  Every instance has its own proving key (and so its own device workspace).  outs[i] receives
+    // instance i's commitments and evaluations; the shared parts (split quotient, opening proofs) are written to every entry.
+    // blinders, in the order the reference's single prng is consumed: the wire masks of every instance, [the h1 / h2 masks,] the
+    // z masks, [the lookup-product masks,] then the NW - 1 split-quotient randomizers.
+    template <class ProofT>
+    static int batch_prove(jf_ctx *ctx, jf_plonk_pk *const *pks, size_t count, const uint64_t *const *witnesses,
+                           const uint64_t *blinders, int kind, const uint8_t *extra, size_t extra_len, ProofT *outs) {
+        // The side-stream work of EVERY instance goes to the first key's side stream: the context keeps one set of scratch
+        // buffers per lane (main / side), so two side streams working at once would share them.
+        jf_plonk_pk *pk0 = pks[0];
+        const size_t n = pk0->n, m = pk0->mq, np = pk0->np;  // m: evaluation points per polynomial in round 3
         const size_t fe = sizeof(E);
         cudaStream_t st = ctx->stream;
-        E *W = (E *)pk->d_w, *PI = W + (size_t)NW * np, *Z = (E *)pk->d_z, *WV = (E *)pk->d_wv;
-        E *bl = (E *)pk->d_bl, *small = (E *)pk->d_small;
-        E *H1 = (E *)pk->d_hp, *H2 = H1 + np, *PL = H1 + 2 * np;                       // UltraPlonk
-        const E *LK = (const E *)pk->d_lk;                                             // range | key | table dom sep | q dom sep
-        const E *QL = (const E *)pk->d_sel + (size_t)(NSEL - 1) * n;                   // q_lookup polynomial (UltraPlonk)
-        memset(out, 0, sizeof *out);
-
-        JF_CUDA(ctx, cudaMemcpyAsync(pk->d_wit, witness, fe * pk->num_vars, cudaMemcpyHostToDevice, st));
-        JF_CUDA(ctx, cudaMemcpyAsync(bl, blinders, fe * NBLIND, cudaMemcpyHostToDevice, st));
-        // coset-evaluation slots: selectors, sigmas (or the resident copies), wires, z, PI [, range, key, tds, qds, h1, h2, pl]
-        E *Ev = (E *)pk->d_e;
-        const E *sel_c, *sig_c;
-        E *w_c, *z_c, *pi_c;
-        if (pk->cache_coset) {
-            sel_c = (const E *)pk->d_cached;
-            sig_c = sel_c + (size_t)NSEL * m;
-            w_c = Ev;
-        } else {
-            sel_c = Ev;
-            sig_c = Ev + (size_t)NSEL * m;
-            w_c = Ev + (size_t)(NSEL + NW) * m;
-            // independent of this proof's challenges: runs on the side stream beside rounds 1 and 2
-            JF_TRY(on_side(ctx, pk, [&]() -> int {
-                JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sel, n, n, NSEL, Ev, pk->zero_sel));
-                return coset_fft_rows(ctx, pk, (const E *)pk->d_sig, n, n, NW, Ev + (size_t)NSEL * m);
-            }));
+        for (size_t i = 0; i < count; i++) {  // snark.rs:226-260
+            const jf_plonk_pk *pk = pks[i];
+            if (pk->nw != NW || pk->curve != pk0->curve) return fail(ctx, JF_ERR_INVALID_ARG, "batch_prove: inconsistent plonk circuit types");
+            if (pk->n != n || pk->sub != pk0->sub) return fail(ctx, JF_ERR_INVALID_ARG, "batch_prove: proving key domain size differs from the expected domain size");
+            if (pk->srs != pk0->srs) return fail(ctx, JF_ERR_INVALID_ARG, "batch_prove: the instances must share one commit key");
+            for (size_t j = 0; j < i; j++)
+                if (pks[j] == pk) return fail(ctx, JF_ERR_INVALID_ARG, "batch_prove: every instance needs its own proving key (workspace)");
+            memset(&outs[i], 0, sizeof outs[i]);
         }
-        z_c = w_c + (size_t)NW * m;
-        pi_c = z_c + m;
-        E *lk_c = pi_c + m;  // UltraPlonk: 7 more rows
-        if (ULTRA)
-            JF_TRY(on_side(ctx, pk, [&]() -> int { return coset_fft_rows(ctx, pk, LK, n, n, 4, lk_c); }));
+        // blinders: one device copy for the whole batch
+        constexpr int PER = NBLIND - (NW - 1);  // per-instance masks
+        const size_t nbl = count * PER + (NW - 1);
+        E *bl;
+        {
+            void *p;
+            JF_TRY(scratch(ctx, "batch_blinders", fe * nbl, &p));
+            bl = (E *)p;
+        }
+        JF_CUDA(ctx, cudaMemcpyAsync(bl, blinders, fe * nbl, cudaMemcpyHostToDevice, st));
+        const E *bl_w = bl, *bl_h = bl + count * 2 * NW, *bl_z = bl_h + (ULTRA ? count * 6 : 0), *bl_pl = bl_z + count * 3,
+                *bl_split = bl_pl + (ULTRA ? count * 3 : 0);
+        // per-instance views
+        struct Inst {
+            jf_plonk_pk *pk;
+            E *W, *PI, *Z, *WV, *H1, *H2, *PL, *small;
+            const E *LK, *QL, *sel_c, *sig_c;
+            E *w_c, *z_c, *pi_c, *lk_c;
+            E ev[2 * NW + 15];
+        };
+        std::vector<Inst> I(count);
         Transcript tr(kind, "PlonkProof");
         if (extra) tr.append_message("extra info", extra, extra_len);
-        {
+        for (size_t i = 0; i < count; i++) {
+            jf_plonk_pk *pk = pks[i];
+            Inst &s = I[i];
+            s.pk = pk;
+            s.W = (E *)pk->d_w;
+            s.PI = s.W + (size_t)NW * np;
+            s.Z = (E *)pk->d_z;
+            s.WV = (E *)pk->d_wv;
+            s.small = (E *)pk->d_small;
+            s.H1 = (E *)pk->d_hp;                                            // UltraPlonk
+            s.H2 = s.H1 + np;
+            s.PL = s.H1 + 2 * np;
+            s.LK = (const E *)pk->d_lk;                                      // range | key | table dom sep | q dom sep
+            s.QL = (const E *)pk->d_sel + (size_t)(NSEL - 1) * n;            // q_lookup polynomial (UltraPlonk)
+            JF_CUDA(ctx, cudaMemcpyAsync(pk->d_wit, witnesses[i], fe * pk->num_vars, cudaMemcpyHostToDevice, st));
+            // coset-evaluation slots: selectors, sigmas (or the resident copies), wires, z, PI [, range, key, tds, qds, h1, h2, pl]
+            E *Ev = (E *)pk->d_e;
+            if (pk->cache_coset) {
+                s.sel_c = (const E *)pk->d_cached;
+                s.sig_c = s.sel_c + (size_t)NSEL * m;
+                s.w_c = Ev;
+            } else {
+                s.sel_c = Ev;
+                s.sig_c = Ev + (size_t)NSEL * m;
+                s.w_c = Ev + (size_t)(NSEL + NW) * m;
+                // independent of this proof's challenges: runs on the side stream beside rounds 1 and 2
+                JF_TRY(on_side(ctx, pk0, [&]() -> int {
+                    JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sel, n, n, NSEL, Ev, pk->zero_sel));
+                    return coset_fft_rows(ctx, pk, (const E *)pk->d_sig, n, n, NW, Ev + (size_t)NSEL * m);
+                }));
+            }
+            s.z_c = s.w_c + (size_t)NW * m;
+            s.pi_c = s.z_c + m;
+            s.lk_c = s.pi_c + m;  // UltraPlonk: 7 more rows
+            if (ULTRA) JF_TRY(on_side(ctx, pk0, [&]() -> int { return coset_fft_rows(ctx, pk, s.LK, n, n, 4, s.lk_c); }));
             std::vector<E> pub(pk->num_inputs);
-            for (size_t i = 0; i < pk->num_inputs; i++) pub[i] = H::fr_from_limbs(witness + 4 * (size_t)pk->pub_vars[i]);
+            for (size_t k = 0; k < pk->num_inputs; k++) pub[k] = H::fr_from_limbs(witnesses[i] + 4 * (size_t)pk->pub_vars[k]);
             append_vk_and_pub_input(tr, pk, pub.data(), pub.size());
         }
         // ---- round 1 (prover.rs:72-87): wire polynomials, masking, NW commitments, PI polynomial ----
-        JF_LAUNCH(ctx, "gather_wires", gather_wires_kernel<Fr><<<(unsigned)((NW * n + 255) / 256), 256, 0, st>>>(
-            (const E *)pk->d_wit, pk->d_wire_vars, (size_t)NW * n, WV));
-        JF_CUDA(ctx, cudaMemsetAsync(W, 0, fe * (NW + 1) * np, st));
-        JF_CUDA(ctx, cudaMemcpy2DAsync(W, fe * np, WV, fe * n, fe * n, NW, cudaMemcpyDeviceToDevice, st));
-        if (pk->num_inputs)
-            JF_LAUNCH(ctx, "pub_input", pub_input_kernel<Fr><<<(pk->num_inputs + 127) / 128, 128, 0, st>>>(
-                (const E *)pk->d_wit, pk->d_wire_vars + (size_t)4 * n, pk->d_gate_ids, pk->num_inputs, PI));
-        JF_TRY(intt_n(ctx, pk, W, NW + 1, np));
-        for (int j = 0; j < NW; j++) JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(W + (size_t)j * np, n, bl + 2 * j, 2));
-        // the wire / PI polynomials are final: their coset NTTs run beside the commitments
-        JF_TRY(on_side(ctx, pk, [&]() -> int {
-            JF_TRY(coset_fft_rows(ctx, pk, W, np, n + 2, NW, w_c));
-            if (pk->num_inputs == 0 && pk->skip_zero) return JF_OK;  // PI(X) = 0: nothing to transform
-            return coset_fft_rows(ctx, pk, PI, np, n, 1, pi_c);
-        }));
-        {
+        for (size_t i = 0; i < count; i++) {
+            Inst &s = I[i];
+            jf_plonk_pk *pk = s.pk;
+            ProofT *out = &outs[i];
+            JF_LAUNCH(ctx, "gather_wires", gather_wires_kernel<Fr><<<(unsigned)((NW * n + 255) / 256), 256, 0, st>>>(
+                (const E *)pk->d_wit, pk->d_wire_vars, (size_t)NW * n, s.WV));
+            JF_CUDA(ctx, cudaMemsetAsync(s.W, 0, fe * (NW + 1) * np, st));
+            JF_CUDA(ctx, cudaMemcpy2DAsync(s.W, fe * np, s.WV, fe * n, fe * n, NW, cudaMemcpyDeviceToDevice, st));
+            if (pk->num_inputs)
+                JF_LAUNCH(ctx, "pub_input", pub_input_kernel<Fr><<<(pk->num_inputs + 127) / 128, 128, 0, st>>>(
+                    (const E *)pk->d_wit, pk->d_wire_vars + (size_t)4 * n, pk->d_gate_ids, pk->num_inputs, s.PI));
+            JF_TRY(intt_n(ctx, pk, s.W, NW + 1, np));
+            for (int j = 0; j < NW; j++)
+                JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(s.W + (size_t)j * np, n, bl_w + i * 2 * NW + 2 * j, 2));
+            // the wire / PI polynomials are final: their coset NTTs run beside the commitments
+            JF_TRY(on_side(ctx, pk0, [&]() -> int {
+                JF_TRY(coset_fft_rows(ctx, pk, s.W, np, n + 2, NW, s.w_c));
+                if (pk->num_inputs == 0 && pk->skip_zero) return JF_OK;  // PI(X) = 0: nothing to transform
+                return coset_fft_rows(ctx, pk, s.PI, np, n, 1, s.pi_c);
+            }));
             CommitJob jobs[NW];
-            for (int j = 0; j < NW; j++) jobs[j] = {W + (size_t)j * np, n + 2, j};
+            for (int j = 0; j < NW; j++) jobs[j] = {s.W + (size_t)j * np, n + 2, j};
             JF_TRY(commit_many(ctx, pk, jobs, NW));
+            JF_TRY(fetch_commits(ctx, pk, 0, NW, out->wires_poly_comms, out->wires_inf));
+            for (int j = 0; j < NW; j++) tr_g1(tr, "witness_poly_comms", out->wires_poly_comms + 2 * L * j, out->wires_inf[j]);
         }
-        JF_TRY(fetch_commits(ctx, pk, 0, NW, out->wires_poly_comms, out->wires_inf));
-        for (int j = 0; j < NW; j++) tr_g1(tr, "witness_poly_comms", out->wires_poly_comms + 2 * L * j, out->wires_inf[j]);
         const E tau = challenge(tr, "tau");  // squeezed even without Plookup (snark.rs:293)
         // ---- round 1.5 (Plookup; prover.rs:98-123, constraint_system.rs:1290-1309,1370-1418) ----
         if constexpr (ULTRA) {
-            JF_LAUNCH(ctx, "merged_values", merged_values_kernel<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-                (const E *)pk->d_lk_evals, WV, tau, (uint32_t)n, (E *)pk->d_mt, (E *)pk->d_ml));
-            JF_TRY(sorted_vector(ctx, pk));
-            JF_CUDA(ctx, cudaMemsetAsync(H1, 0, fe * 3 * np, st));
-            JF_CUDA(ctx, cudaMemcpyAsync(H1, pk->d_sorted, fe * n, cudaMemcpyDeviceToDevice, st));
-            JF_CUDA(ctx, cudaMemcpyAsync(H2, (const E *)pk->d_sorted + (n - 1), fe * n, cudaMemcpyDeviceToDevice, st));
-            JF_TRY(intt_n(ctx, pk, H1, 2, np));
-            JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(H1, n, bl + D::BL_H, 3));
-            JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(H2, n, bl + D::BL_H + 3, 3));
-            JF_TRY(on_side(ctx, pk, [&]() -> int { return coset_fft_rows(ctx, pk, H1, np, n + 3, 2, lk_c + 4 * m); }));
-            CommitJob jobs[2] = {{H1, n + 3, 0}, {H2, n + 3, 1}};
-            JF_TRY(commit_many(ctx, pk, jobs, 2));
-            JF_TRY(fetch_commits(ctx, pk, 0, 2, out->h_poly_comms, out->h_inf));
-            for (int j = 0; j < 2; j++) tr_g1(tr, "h_poly_comms", out->h_poly_comms + 2 * L * j, out->h_inf[j]);
+            for (size_t i = 0; i < count; i++) {
+                Inst &s = I[i];
+                jf_plonk_pk *pk = s.pk;
+                ProofT *out = &outs[i];
+                JF_LAUNCH(ctx, "merged_values", merged_values_kernel<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+                    (const E *)pk->d_lk_evals, s.WV, tau, (uint32_t)n, (E *)pk->d_mt, (E *)pk->d_ml));
+                JF_TRY(sorted_vector(ctx, pk));
+                JF_CUDA(ctx, cudaMemsetAsync(s.H1, 0, fe * 3 * np, st));
+                JF_CUDA(ctx, cudaMemcpyAsync(s.H1, pk->d_sorted, fe * n, cudaMemcpyDeviceToDevice, st));
+                JF_CUDA(ctx, cudaMemcpyAsync(s.H2, (const E *)pk->d_sorted + (n - 1), fe * n, cudaMemcpyDeviceToDevice, st));
+                JF_TRY(intt_n(ctx, pk, s.H1, 2, np));
+                JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(s.H1, n, bl_h + i * 6, 3));
+                JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(s.H2, n, bl_h + i * 6 + 3, 3));
+                JF_TRY(on_side(ctx, pk0, [&]() -> int { return coset_fft_rows(ctx, pk, s.H1, np, n + 3, 2, s.lk_c + 4 * m); }));
+                CommitJob jobs[2] = {{s.H1, n + 3, 0}, {s.H2, n + 3, 1}};
+                JF_TRY(commit_many(ctx, pk, jobs, 2));
+                JF_TRY(fetch_commits(ctx, pk, 0, 2, out->h_poly_comms, out->h_inf));
+                for (int j = 0; j < 2; j++) tr_g1(tr, "h_poly_comms", out->h_poly_comms + 2 * L * j, out->h_inf[j]);
+            }
         }
         // ---- round 2 (prover.rs:125-141; constraint_system.rs:1197-1223) ----
         const E beta = challenge(tr, "beta"), gamma = challenge(tr, "gamma");
-        {
+        for (size_t i = 0; i < count; i++) {
+            Inst &s = I[i];
+            jf_plonk_pk *pk = s.pk;
+            ProofT *out = &outs[i];
             PermArgs<Fr, NW> pa;
-            pa.wv = WV;
+            pa.wv = s.WV;
             pa.sigma = (const E *)pk->d_sig_evals;
             for (int j = 0; j < NW; j++) pa.beta_k[j] = E::mul(beta, kf(pk, j));
             pa.beta = beta;
@@ -1254,77 +1340,94 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
             E *PA = (E *)pk->d_t, *SB = (E *)pk->d_s;
             JF_TRY((fscan<Fr, OpMul, false>(ctx, pa.a, PA, n, (E *)pk->d_tmp)));
             JF_TRY((fscan<Fr, OpMul, true>(ctx, pa.b, SB, n, (E *)pk->d_tmp)));
-            JF_LAUNCH(ctx, "inv_one", inv_one_kernel<Fr><<<1, 32, 0, st>>>(SB, small));
-            JF_CUDA(ctx, cudaMemsetAsync(Z, 0, fe * np, st));
-            JF_LAUNCH(ctx, "z_combine", z_combine_kernel<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(PA, SB, small, Z, (uint32_t)n));
-            JF_TRY(intt_n(ctx, pk, Z, 1, np));
-            JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(Z, n, bl + D::BL_Z, 3));
-            JF_TRY(on_side(ctx, pk, [&]() -> int { return coset_fft_rows(ctx, pk, Z, np, n + 3, 1, z_c); }));
-            JF_TRY(commit_dev(ctx, pk, Z, n + 3, 0));
+            JF_LAUNCH(ctx, "inv_one", inv_one_kernel<Fr><<<1, 32, 0, st>>>(SB, s.small));
+            JF_CUDA(ctx, cudaMemsetAsync(s.Z, 0, fe * np, st));
+            JF_LAUNCH(ctx, "z_combine", z_combine_kernel<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(PA, SB, s.small, s.Z, (uint32_t)n));
+            JF_TRY(intt_n(ctx, pk, s.Z, 1, np));
+            JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(s.Z, n, bl_z + i * 3, 3));
+            JF_TRY(on_side(ctx, pk0, [&]() -> int { return coset_fft_rows(ctx, pk, s.Z, np, n + 3, 1, s.z_c); }));
+            JF_TRY(commit_dev(ctx, pk, s.Z, n + 3, 0));
             JF_TRY(fetch_commits(ctx, pk, 0, 1, out->prod_perm_poly_comm, &out->prod_perm_inf));
             tr_g1(tr, "perm_poly_comms", out->prod_perm_poly_comm, out->prod_perm_inf);
         }
         const E bp1 = E::add(E::one(), beta), gb = E::mul(gamma, bp1);
         // ---- round 2.5 (Plookup product; prover.rs:150-190, constraint_system.rs:1311-1368) ----
         if constexpr (ULTRA) {
-            E *A = (E *)pk->d_a, *B = (E *)pk->d_b, *PA = (E *)pk->d_t, *SB = (E *)pk->d_s;
-            JF_LAUNCH(ctx, "lookup_ab", lookup_ab_kernel<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-                (const E *)pk->d_mt, (const E *)pk->d_ml, (const E *)pk->d_sorted, beta, gamma, bp1, gb, (uint32_t)n, A, B));
-            JF_TRY((fscan<Fr, OpMul, false>(ctx, A, PA, n, (E *)pk->d_tmp)));
-            JF_TRY((fscan<Fr, OpMul, true>(ctx, B, SB, n, (E *)pk->d_tmp)));
-            JF_LAUNCH(ctx, "inv_one", inv_one_kernel<Fr><<<1, 32, 0, st>>>(SB, small));
-            JF_LAUNCH(ctx, "z_combine", z_combine_kernel<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(PA, SB, small, PL, (uint32_t)n));
-            JF_LAUNCH(ctx, "set_one", set_one_kernel<Fr><<<1, 32, 0, st>>>(PL + (n - 1)));  // the reference pushes 1 as the last value
-            JF_TRY(intt_n(ctx, pk, PL, 1, np));
-            JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(PL, n, bl + D::BL_PL, 3));
-            JF_TRY(on_side(ctx, pk, [&]() -> int { return coset_fft_rows(ctx, pk, PL, np, n + 3, 1, lk_c + 6 * m); }));
-            JF_TRY(commit_dev(ctx, pk, PL, n + 3, 0));
-            JF_TRY(fetch_commits(ctx, pk, 0, 1, out->prod_lookup_poly_comm, &out->prod_lookup_inf));
-            tr_g1(tr, "plookup_poly_comms", out->prod_lookup_poly_comm, out->prod_lookup_inf);
+            for (size_t i = 0; i < count; i++) {
+                Inst &s = I[i];
+                jf_plonk_pk *pk = s.pk;
+                ProofT *out = &outs[i];
+                E *A = (E *)pk->d_a, *B = (E *)pk->d_b, *PA = (E *)pk->d_t, *SB = (E *)pk->d_s;
+                JF_LAUNCH(ctx, "lookup_ab", lookup_ab_kernel<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+                    (const E *)pk->d_mt, (const E *)pk->d_ml, (const E *)pk->d_sorted, beta, gamma, bp1, gb, (uint32_t)n, A, B));
+                JF_TRY((fscan<Fr, OpMul, false>(ctx, A, PA, n, (E *)pk->d_tmp)));
+                JF_TRY((fscan<Fr, OpMul, true>(ctx, B, SB, n, (E *)pk->d_tmp)));
+                JF_LAUNCH(ctx, "inv_one", inv_one_kernel<Fr><<<1, 32, 0, st>>>(SB, s.small));
+                JF_LAUNCH(ctx, "z_combine", z_combine_kernel<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(PA, SB, s.small, s.PL, (uint32_t)n));
+                JF_LAUNCH(ctx, "set_one", set_one_kernel<Fr><<<1, 32, 0, st>>>(s.PL + (n - 1)));  // the reference pushes 1 as the last value
+                JF_TRY(intt_n(ctx, pk, s.PL, 1, np));
+                JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(s.PL, n, bl_pl + i * 3, 3));
+                JF_TRY(on_side(ctx, pk0, [&]() -> int { return coset_fft_rows(ctx, pk, s.PL, np, n + 3, 1, s.lk_c + 6 * m); }));
+                JF_TRY(commit_dev(ctx, pk, s.PL, n + 3, 0));
+                JF_TRY(fetch_commits(ctx, pk, 0, 1, out->prod_lookup_poly_comm, &out->prod_lookup_inf));
+                tr_g1(tr, "plookup_poly_comms", out->prod_lookup_poly_comm, out->prod_lookup_inf);
+            }
         }
-        // ---- round 3 (prover.rs:192-209, 512-673, 773-888, 902-960) ----
+        // ---- round 3 (prover.rs:192-209, 512-673, 773-888, 902-960): ONE quotient for the whole batch ----
         const E alpha = challenge(tr, "alpha");
+        const E alpha2 = E::sqr(alpha), alpha3 = E::mul(alpha2, alpha);
+        const E alpha_step = ULTRA ? E::mul(E::sqr(alpha3), alpha) : alpha3;  // alpha^7 | alpha^3 (prover.rs:665-669)
         const size_t deg = NW * (n + 1) + 2;  // quotient_polynomial_degree (prover.rs:1126-1128)
         const size_t last_len = deg + 1 - (size_t)(NW - 1) * (n + 2);
+        const E *split = (const E *)pk0->d_split;
         {
-            JF_TRY(join_side(ctx, pk));  // all coset evaluation vectors are in place
-            QuotArgs<Fr, NW> q;
-            q.sel = sel_c;
-            q.sig = sig_c;
-            q.w = w_c;
-            q.z = z_c;
-            q.pi = (pk->num_inputs == 0 && pk->skip_zero) ? nullptr : pi_c;
-            q.inv_nx1 = (const E *)pk->d_inv_nx1;
-            q.x_lo = (const E *)pk->d_xlo;
-            q.x_hi = (const E *)pk->d_xhi;
-            q.lo_bits = pk->lo_bits;
-            for (int j = 0; j < NW; j++) q.beta_k[j] = E::mul(beta, kf(pk, j));
-            q.beta = beta;
-            q.gamma = gamma;
-            q.alpha = alpha;
-            q.alpha2 = E::sqr(alpha);
-            for (int r = 0; r < 8; r++) q.zh_inv[r] = lf(pk->zh_inv[r]);
-            q.omega_inv = lf(pk->omega_n_inv);
-            if (ULTRA) {
-                q.lk.range = lk_c;
-                q.lk.key = lk_c + m;
-                q.lk.tds = lk_c + 2 * m;
-                q.lk.qds = lk_c + 3 * m;
-                q.lk.h1 = lk_c + 4 * m;
-                q.lk.h2 = lk_c + 5 * m;
-                q.lk.pl = lk_c + 6 * m;
-                q.lk.tau = tau;
-                q.lk.bp1 = bp1;
-                q.lk.gb = gb;
-                q.lk.alpha3 = E::mul(q.alpha2, alpha);
+            E alpha_base = E::one();
+            for (size_t i = 0; i < count; i++) {
+                Inst &s = I[i];
+                jf_plonk_pk *pk = s.pk;
+                JF_TRY(join_side(ctx, pk0));  // this instance's coset evaluation vectors are in place
+                QuotArgs<Fr, NW> q;
+                q.sel = s.sel_c;
+                q.sig = s.sig_c;
+                q.w = s.w_c;
+                q.z = s.z_c;
+                q.pi = (pk->num_inputs == 0 && pk->skip_zero) ? nullptr : s.pi_c;
+                q.inv_nx1 = (const E *)pk->d_inv_nx1;
+                q.x_lo = (const E *)pk->d_xlo;
+                q.x_hi = (const E *)pk->d_xhi;
+                q.lo_bits = pk->lo_bits;
+                for (int j = 0; j < NW; j++) q.beta_k[j] = E::mul(beta, kf(pk, j));
+                q.beta = beta;
+                q.gamma = gamma;
+                q.alpha = alpha;
+                q.alpha2 = alpha2;
+                for (int r = 0; r < 8; r++) q.zh_inv[r] = lf(pk->zh_inv[r]);
+                q.omega_inv = lf(pk->omega_n_inv);
+                if (ULTRA) {
+                    q.lk.range = s.lk_c;
+                    q.lk.key = s.lk_c + m;
+                    q.lk.tds = s.lk_c + 2 * m;
+                    q.lk.qds = s.lk_c + 3 * m;
+                    q.lk.h1 = s.lk_c + 4 * m;
+                    q.lk.h2 = s.lk_c + 5 * m;
+                    q.lk.pl = s.lk_c + 6 * m;
+                    q.lk.tau = tau;
+                    q.lk.bp1 = bp1;
+                    q.lk.gb = gb;
+                    q.lk.alpha3 = alpha3;
+                }
+                q.scale = alpha_base;
+                q.acc_mode = i ? 1u : 0u;
+                q.out = (E *)pk0->d_q;
+                q.m = (uint32_t)m;
+                q.ratio = 8;
+                q.zero_sel = pk->zero_sel;
+                q.sub = (uint32_t)pk->sub;
+                q.log_n = pk->log_n;
+                JF_LAUNCH(ctx, "quotient", quotient_kernel<Fr, NW><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(q));
+                alpha_base = E::mul(alpha_base, alpha_step);
             }
-            q.out = (E *)pk->d_q;
-            q.m = (uint32_t)m;
-            q.ratio = 8;
-            q.zero_sel = pk->zero_sel;
-            q.sub = (uint32_t)pk->sub;
-            q.log_n = pk->log_n;
-            JF_LAUNCH(ctx, "quotient", quotient_kernel<Fr, NW><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(q));
+            jf_plonk_pk *pk = pk0;
             const E *T = (const E *)pk->d_q;  // quotient coefficients
             if (pk->sub) {
                 JF_TRY(ntt_run_cosets(ctx, C::FR_ID, pk->d_q, n, n, pk->d_q, pk->log_n, 1, pk->sub_off, pk->sub, 1));
@@ -1340,50 +1443,59 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
             }
             JF_LAUNCH(ctx, "degree_check", degree_check_kernel<Fr><<<(unsigned)((m - deg + 255) / 256), 256, 0, st>>>(T, deg, m, ctx->d_err + 1));
             dim3 grid((unsigned)((np + 255) / 256), NW);
-            JF_LAUNCH(ctx, "split", split_kernel<Fr, NW><<<grid, 256, 0, st>>>(T, n, deg + 1, bl + D::BL_SPLIT, (E *)pk->d_split, np));
+            JF_LAUNCH(ctx, "split", split_kernel<Fr, NW><<<grid, 256, 0, st>>>(T, n, deg + 1, bl_split, (E *)pk->d_split, np));
             CommitJob jobs[NW];
             for (int i = 0; i < NW; i++) jobs[i] = {(E *)pk->d_split + (size_t)i * np, i < NW - 1 ? n + 3 : last_len, i};
             JF_TRY(commit_many(ctx, pk, jobs, NW));
+            ProofT *out = &outs[0];
             JF_TRY(fetch_commits(ctx, pk, 0, NW, out->split_quot_poly_comms, out->split_inf));
             for (int i = 0; i < NW; i++) tr_g1(tr, "quot_poly_comms", out->split_quot_poly_comms + 2 * L * i, out->split_inf[i]);
         }
         // ---- round 4 (prover.rs:216-235) and 4.5 (Plookup evaluations, :239-297) ----
         const E zeta = challenge(tr, "zeta");
-        const E omega = lf(pk->omega_n);
+        const E omega = lf(pk0->omega_n);
         const E zeta_w = E::mul(zeta, omega);
         constexpr int NEV = 2 * NW;  // NW wires, NW - 1 sigmas, z(zeta w)
-        E ev[NEV + 15];
         // Plookup evaluations in `PlookupEvaluations` declaration order (structs.rs:496-541)
         enum { P_RANGE, P_KEY, P_TDS, P_QDS, P_H1, P_QL, P_PLN, P_RANGEN, P_KEYN, P_TDSN, P_H1N, P_H2N, P_QLN, P_W3N, P_W4N };
-        {
-            for (int j = 0; j < NW; j++) JF_TRY(eval_dev(ctx, pk, W + (size_t)j * np, n + 2, zeta, small + j));
+        for (size_t i = 0; i < count; i++) {
+            Inst &s = I[i];
+            jf_plonk_pk *pk = s.pk;
+            E *small = s.small;
+            for (int j = 0; j < NW; j++) JF_TRY(eval_dev(ctx, pk, s.W + (size_t)j * np, n + 2, zeta, small + j));
             for (int j = 0; j < NW - 1; j++) JF_TRY(eval_dev(ctx, pk, (const E *)pk->d_sig + (size_t)j * n, n, zeta, small + NW + j));
-            JF_TRY(eval_dev(ctx, pk, Z, n + 3, zeta_w, small + NEV - 1));
+            JF_TRY(eval_dev(ctx, pk, s.Z, n + 3, zeta_w, small + NEV - 1));
             if (ULTRA) {
                 E *pe = small + NEV;
+                const E *LK = s.LK;
                 JF_TRY(eval_dev(ctx, pk, LK, n, zeta, pe + P_RANGE));
                 JF_TRY(eval_dev(ctx, pk, LK + n, n, zeta, pe + P_KEY));
                 JF_TRY(eval_dev(ctx, pk, LK + 2 * n, n, zeta, pe + P_TDS));
                 JF_TRY(eval_dev(ctx, pk, LK + 3 * n, n, zeta, pe + P_QDS));
-                JF_TRY(eval_dev(ctx, pk, H1, n + 3, zeta, pe + P_H1));
-                JF_TRY(eval_dev(ctx, pk, QL, n, zeta, pe + P_QL));
-                JF_TRY(eval_dev(ctx, pk, PL, n + 3, zeta_w, pe + P_PLN));
+                JF_TRY(eval_dev(ctx, pk, s.H1, n + 3, zeta, pe + P_H1));
+                JF_TRY(eval_dev(ctx, pk, s.QL, n, zeta, pe + P_QL));
+                JF_TRY(eval_dev(ctx, pk, s.PL, n + 3, zeta_w, pe + P_PLN));
                 JF_TRY(eval_dev(ctx, pk, LK, n, zeta_w, pe + P_RANGEN));
                 JF_TRY(eval_dev(ctx, pk, LK + n, n, zeta_w, pe + P_KEYN));
                 JF_TRY(eval_dev(ctx, pk, LK + 2 * n, n, zeta_w, pe + P_TDSN));
-                JF_TRY(eval_dev(ctx, pk, H1, n + 3, zeta_w, pe + P_H1N));
-                JF_TRY(eval_dev(ctx, pk, H2, n + 3, zeta_w, pe + P_H2N));
-                JF_TRY(eval_dev(ctx, pk, QL, n, zeta_w, pe + P_QLN));
-                JF_TRY(eval_dev(ctx, pk, W + 3 * np, n + 2, zeta_w, pe + P_W3N));
-                JF_TRY(eval_dev(ctx, pk, W + 4 * np, n + 2, zeta_w, pe + P_W4N));
+                JF_TRY(eval_dev(ctx, pk, s.H1, n + 3, zeta_w, pe + P_H1N));
+                JF_TRY(eval_dev(ctx, pk, s.H2, n + 3, zeta_w, pe + P_H2N));
+                JF_TRY(eval_dev(ctx, pk, s.QL, n, zeta_w, pe + P_QLN));
+                JF_TRY(eval_dev(ctx, pk, s.W + 3 * np, n + 2, zeta_w, pe + P_W3N));
+                JF_TRY(eval_dev(ctx, pk, s.W + 4 * np, n + 2, zeta_w, pe + P_W4N));
             }
-            JF_CUDA(ctx, cudaMemcpyAsync(ev, small, fe * (NEV + (ULTRA ? 15 : 0)), cudaMemcpyDeviceToHost, st));
-            JF_CUDA(ctx, cudaStreamSynchronize(st));
+            JF_CUDA(ctx, cudaMemcpyAsync(s.ev, small, fe * (NEV + (ULTRA ? 15 : 0)), cudaMemcpyDeviceToHost, st));
+        }
+        JF_CUDA(ctx, cudaStreamSynchronize(st));
+        for (size_t i = 0; i < count; i++) {  // append_proof_evaluations for every instance ...
+            const E *ev = I[i].ev;
             for (int j = 0; j < NW; j++) tr_fr(tr, "wire_evals", ev[j]);
             for (int j = 0; j < NW - 1; j++) tr_fr(tr, "wire_sigma_evals", ev[NW + j]);
             tr_fr(tr, "perm_next_eval", ev[NEV - 1]);
-            if (ULTRA) {  // append_plookup_evaluations (transcript/mod.rs:168-201): six of the fifteen
-                const E *pe = ev + NEV;
+        }
+        if (ULTRA) {  // ... then append_plookup_evaluations for every instance (transcript/mod.rs:168-201): six of the fifteen
+            for (size_t i = 0; i < count; i++) {
+                const E *pe = I[i].ev + NEV;
                 tr_fr(tr, "lookup_table_eval", pe[P_RANGE]);
                 tr_fr(tr, "h_1_eval", pe[P_H1]);
                 tr_fr(tr, "prod_next_eval", pe[P_PLN]);
@@ -1392,108 +1504,101 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
                 tr_fr(tr, "h_2_next_eval", pe[P_H2N]);
             }
         }
-        // ---- round 5 (snark.rs:419-449; prover.rs:302-360, 362-460, 490-509, 963-1113) ----
+        // ---- round 5 (snark.rs:403-449; prover.rs:302-360, 362-460, 490-509, 963-1113) ----
         const E v = challenge(tr, "v");
         {
-            const E *we = ev, *se = ev + NW, *pe = ev + NEV;
-            const E pne = ev[NEV - 1];
             const E one = E::one();
             const E vanish = E::sub(pow_small(zeta, n), one);
             const E zeta_n2 = E::mul(E::mul(E::add(vanish, one), zeta), zeta);
-            const E alpha2 = E::sqr(alpha);
             const E nf = E::from_u32((uint32_t)n);
             const E lagrange_1 = E::mul(vanish, E::inv(E::mul(nf, E::sub(zeta, one))));
-            LinArgs<Fr> la;
-            int c = 0;
-            auto push = [&](const E *p, size_t len, const E &s) {
-                la.p[c] = p;
-                la.len[c] = (uint32_t)len;
-                la.s[c] = s;
-                c++;
-            };
+            std::vector<Term> terms, shifted_terms;
             // quotient part: -Z_H(zeta) * sum_i zeta^(i (n+2)) t_i
             E coeff = E::neg(vanish);
             for (int i = 0; i < NW; i++) {
-                push((const E *)pk->d_split + (size_t)i * np, i < NW - 1 ? n + 3 : last_len, coeff);
+                terms.push_back({split + (size_t)i * np, i < NW - 1 ? n + 3 : last_len, coeff});
                 coeff = E::mul(coeff, zeta_n2);
             }
-            // circuit part: the 13 arithmetic selectors (q_lookup is not part of it)
-            const E *sel = (const E *)pk->d_sel;
-            const E w01 = E::mul(we[0], we[1]), w23 = E::mul(we[2], we[3]);
-            const E qs[13] = {we[0], we[1], we[2], we[3], w01, w23, pow_small(we[0], 5), pow_small(we[1], 5), pow_small(we[2], 5),
-                              pow_small(we[3], 5), E::neg(we[4]), one, E::mul(E::mul(w01, w23), we[4])};
-            for (int s = 0; s < 13; s++)
-                if (!((pk->zero_sel >> s) & 1u)) push(sel + (size_t)s * n, n, qs[s]);
-            // permutation part
-            E c1 = alpha;
-            for (int j = 0; j < NW; j++) c1 = E::mul(c1, E::add(E::add(we[j], E::mul(E::mul(beta, kf(pk, j)), zeta)), gamma));
-            c1 = E::add(c1, E::mul(alpha2, lagrange_1));
-            E c2 = E::mul(E::mul(alpha, beta), pne);
-            for (int j = 0; j < NW - 1; j++) c2 = E::mul(c2, E::add(E::add(we[j], E::mul(beta, se[j])), gamma));
-            push(Z, n + 3, c1);
-            const E *sig = (const E *)pk->d_sig;
-            push(sig + (size_t)(NW - 1) * n, n, E::neg(c2));
-            if (ULTRA) {  // compute_lin_poly_plookup_contribution (prover.rs:1037-1113)
-                const E alpha4 = E::sqr(alpha2), alpha5 = E::mul(alpha4, alpha), alpha6 = E::mul(alpha4, alpha2);
-                const E g_inv = lf(pk->omega_n_inv), zmg = E::sub(zeta, g_inv);
-                const E lagrange_n = E::mul(E::mul(vanish, g_inv), E::inv(E::mul(nf, zmg)));
-                auto merged = [&](const E &a, const E &qv, const E &b, const E &cc, const E &d, const E &e) {
-                    E t = E::add(d, E::mul(tau, e));
-                    t = E::add(cc, E::mul(tau, t));
-                    t = E::add(b, E::mul(tau, t));
-                    return E::add(a, E::mul(E::mul(qv, tau), t));
-                };
-                const E mt = merged(pe[P_RANGE], pe[P_QL], pe[P_TDS], pe[P_KEY], we[3], we[4]);
-                const E mtn = merged(pe[P_RANGEN], pe[P_QLN], pe[P_TDSN], pe[P_KEYN], pe[P_W3N], pe[P_W4N]);
-                const E ml = merged(we[5], pe[P_QL], pe[P_QDS], we[0], we[1], we[2]);
-                E cpl = E::mul(E::mul(E::mul(E::mul(alpha6, zmg), bp1), E::add(gamma, ml)), E::add(E::add(gb, mt), E::mul(beta, mtn)));
-                cpl = E::add(cpl, E::add(E::mul(alpha4, lagrange_1), E::mul(alpha5, lagrange_n)));
-                push(PL, n + 3, cpl);
-                const E ch2 = E::neg(E::mul(E::mul(E::mul(alpha6, zmg), pe[P_PLN]), E::add(E::add(gb, pe[P_H1]), E::mul(beta, pe[P_H1N]))));
-                push(H2, n + 3, ch2);
-            }
-            // the opening batch: lin + v w_0 + .. + v^NW w_(NW-1) + v^(NW+1) sigma_0 + .. [+ range, key, h1, q_lookup, tds, qds]
-            E vp = v;
-            for (int j = 0; j < NW; j++) {
-                push(W + (size_t)j * np, n + 2, vp);
-                vp = E::mul(vp, v);
-            }
-            for (int j = 0; j < NW - 1; j++) {
-                push(sig + (size_t)j * n, n, vp);
-                vp = E::mul(vp, v);
-            }
-            if (ULTRA) {  // plookup_open_polys_ref (prover.rs:427-442)
-                const E *ps[6] = {LK, LK + n, H1, QL, LK + 2 * n, LK + 3 * n};
-                const size_t ls[6] = {n, n, n + 3, n, n, n};
-                for (int j = 0; j < 6; j++) {
-                    push(ps[j], ls[j], vp);
+            // the non-quotient parts enter with alpha_base_i; the opening batch continues the powers of v across the instances:
+            // lin + v w_0 + .. + v^NW w_(NW-1) + v^(NW+1) sigma_0 + .. [+ range, key, h1, q_lookup, tds, qds] + (next instance) ..
+            E alpha_base = one, vp = v, sp = one;
+            for (size_t i = 0; i < count; i++) {
+                Inst &s = I[i];
+                jf_plonk_pk *pk = s.pk;
+                const E *we = s.ev, *se = s.ev + NW, *pe = s.ev + NEV;
+                const E pne = s.ev[NEV - 1];
+                // circuit part: the 13 arithmetic selectors (q_lookup is not part of it)
+                const E *sel = (const E *)pk->d_sel;
+                const E w01 = E::mul(we[0], we[1]), w23 = E::mul(we[2], we[3]);
+                const E qs[13] = {we[0], we[1], we[2], we[3], w01, w23, pow_small(we[0], 5), pow_small(we[1], 5), pow_small(we[2], 5),
+                                  pow_small(we[3], 5), E::neg(we[4]), one, E::mul(E::mul(w01, w23), we[4])};
+                for (int k = 0; k < 13; k++)
+                    if (!((pk->zero_sel >> k) & 1u)) terms.push_back({sel + (size_t)k * n, n, E::mul(alpha_base, qs[k])});
+                // permutation part
+                E c1 = alpha;
+                for (int j = 0; j < NW; j++) c1 = E::mul(c1, E::add(E::add(we[j], E::mul(E::mul(beta, kf(pk, j)), zeta)), gamma));
+                c1 = E::add(c1, E::mul(alpha2, lagrange_1));
+                E c2 = E::mul(E::mul(alpha, beta), pne);
+                for (int j = 0; j < NW - 1; j++) c2 = E::mul(c2, E::add(E::add(we[j], E::mul(beta, se[j])), gamma));
+                terms.push_back({s.Z, n + 3, E::mul(alpha_base, c1)});
+                const E *sig = (const E *)pk->d_sig;
+                terms.push_back({sig + (size_t)(NW - 1) * n, n, E::mul(alpha_base, E::neg(c2))});
+                if (ULTRA) {  // compute_lin_poly_plookup_contribution (prover.rs:1037-1113)
+                    const E alpha4 = E::sqr(alpha2), alpha5 = E::mul(alpha4, alpha), alpha6 = E::mul(alpha4, alpha2);
+                    const E g_inv = lf(pk->omega_n_inv), zmg = E::sub(zeta, g_inv);
+                    const E lagrange_n = E::mul(E::mul(vanish, g_inv), E::inv(E::mul(nf, zmg)));
+                    auto merged = [&](const E &a, const E &qv, const E &b, const E &cc, const E &d, const E &e) {
+                        E t = E::add(d, E::mul(tau, e));
+                        t = E::add(cc, E::mul(tau, t));
+                        t = E::add(b, E::mul(tau, t));
+                        return E::add(a, E::mul(E::mul(qv, tau), t));
+                    };
+                    const E mt = merged(pe[P_RANGE], pe[P_QL], pe[P_TDS], pe[P_KEY], we[3], we[4]);
+                    const E mtn = merged(pe[P_RANGEN], pe[P_QLN], pe[P_TDSN], pe[P_KEYN], pe[P_W3N], pe[P_W4N]);
+                    const E ml = merged(we[5], pe[P_QL], pe[P_QDS], we[0], we[1], we[2]);
+                    E cpl = E::mul(E::mul(E::mul(E::mul(alpha6, zmg), bp1), E::add(gamma, ml)), E::add(E::add(gb, mt), E::mul(beta, mtn)));
+                    cpl = E::add(cpl, E::add(E::mul(alpha4, lagrange_1), E::mul(alpha5, lagrange_n)));
+                    terms.push_back({s.PL, n + 3, E::mul(alpha_base, cpl)});
+                    const E ch2 = E::neg(E::mul(E::mul(E::mul(alpha6, zmg), pe[P_PLN]), E::add(E::add(gb, pe[P_H1]), E::mul(beta, pe[P_H1N]))));
+                    terms.push_back({s.H2, n + 3, E::mul(alpha_base, ch2)});
+                }
+                for (int j = 0; j < NW; j++) {
+                    terms.push_back({s.W + (size_t)j * np, n + 2, vp});
                     vp = E::mul(vp, v);
                 }
-            }
-            la.count = c;
-            la.out = (E *)pk->d_bp;
-            la.out_len = (uint32_t)(n + 3);
-            JF_LAUNCH(ctx, "lincomb", lincomb_kernel<Fr><<<(unsigned)((n + 3 + 127) / 128), 128, 0, st>>>(la));
-            // the shifted opening is independent of the batch polynomial: side stream, own scratch
-            E *side_buf = (E *)pk->d_side;  // t, s, quotient (np each), scan temporaries
-            JF_TRY(on_side(ctx, pk, [&]() -> int {
-                const E *shifted = Z;
-                if (ULTRA) {  // z + v pl + v^2 range + .. (plookup_shifted_open_polys_ref, prover.rs:444-460)
-                    LinArgs<Fr> ls;
-                    const E *ps[10] = {Z, PL, LK, LK + n, H1, H2, QL, W + 3 * np, W + 4 * np, LK + 2 * n};
-                    const size_t lens[10] = {n + 3, n + 3, n, n, n + 3, n + 3, n, n + 2, n + 2, n};
-                    E sp = one;
-                    for (int j = 0; j < 10; j++) {
-                        ls.p[j] = ps[j];
-                        ls.len[j] = (uint32_t)lens[j];
-                        ls.s[j] = sp;
+                for (int j = 0; j < NW - 1; j++) {
+                    terms.push_back({sig + (size_t)j * n, n, vp});
+                    vp = E::mul(vp, v);
+                }
+                shifted_terms.push_back({s.Z, n + 3, sp});
+                sp = E::mul(sp, v);
+                if (ULTRA) {  // plookup_open_polys_ref / plookup_shifted_open_polys_ref (prover.rs:427-460)
+                    const E *LK = s.LK;
+                    const E *ps[6] = {LK, LK + n, s.H1, s.QL, LK + 2 * n, LK + 3 * n};
+                    const size_t ls[6] = {n, n, n + 3, n, n, n};
+                    for (int j = 0; j < 6; j++) {
+                        terms.push_back({ps[j], ls[j], vp});
+                        vp = E::mul(vp, v);
+                    }
+                    const E *qs2[9] = {s.PL, LK, LK + n, s.H1, s.H2, s.QL, s.W + 3 * np, s.W + 4 * np, LK + 2 * n};
+                    const size_t ls2[9] = {n + 3, n, n, n + 3, n + 3, n, n + 2, n + 2, n};
+                    for (int j = 0; j < 9; j++) {
+                        shifted_terms.push_back({qs2[j], ls2[j], sp});
                         sp = E::mul(sp, v);
                     }
-                    ls.count = 10;
-                    ls.out = PI;  // the PI slot of W is free after round 3 (its coset evaluations were taken in round 1)
-                    ls.out_len = (uint32_t)(n + 3);
-                    JF_LAUNCH(ctx, "lincomb", lincomb_kernel<Fr><<<(unsigned)((n + 3 + 127) / 128), 128, 0, ctx->stream>>>(ls));
-                    shifted = PI;
+                }
+                alpha_base = E::mul(alpha_base, alpha_step);
+            }
+            jf_plonk_pk *pk = pk0;
+            JF_TRY(lincomb_many(ctx, terms, (E *)pk->d_bp, n + 3));
+            // the shifted opening is independent of the batch polynomial: side stream, own scratch
+            E *side_buf = (E *)pk->d_side;  // t, s, quotient (np each), scan temporaries
+            JF_TRY(on_side(ctx, pk0, [&]() -> int {
+                const E *shifted = I[0].Z;
+                if (shifted_terms.size() > 1) {
+                    // the PI slot of W is free after round 3 (its coset evaluations were taken in round 1)
+                    JF_TRY(lincomb_many(ctx, shifted_terms, I[0].PI, n + 3));
+                    shifted = I[0].PI;
                 }
                 JF_TRY(div_linear_dev(ctx, side_buf, side_buf + np, side_buf + 3 * np, shifted, n + 3, zeta_w, side_buf + 2 * np));
                 return commit_dev(ctx, pk, side_buf + 2 * np, n + 2, 1);
@@ -1501,34 +1606,47 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
             E *WZ = (E *)pk->d_wz;
             JF_TRY(div_linear_dev(ctx, pk, (const E *)pk->d_bp, n + 3, zeta, WZ));
             JF_TRY(commit_dev(ctx, pk, WZ, n + 2, 0));
-            JF_TRY(join_side(ctx, pk));
+            JF_TRY(join_side(ctx, pk0));
             uint64_t xy[2 * 2 * 6];
             int inf[2];
             JF_TRY(fetch_commits(ctx, pk, 0, 2, xy, inf));
+            ProofT *out = &outs[0];
             memcpy(out->opening_proof, xy, sizeof(uint64_t) * 2 * L);
             memcpy(out->shifted_opening_proof, xy + 2 * L, sizeof(uint64_t) * 2 * L);
             out->opening_inf = inf[0];
             out->shifted_opening_inf = inf[1];
         }
-        for (int j = 0; j < NW; j++) H::fr_to_limbs(ev[j], out->wires_evals + 4 * j);
-        for (int j = 0; j < NW - 1; j++) H::fr_to_limbs(ev[NW + j], out->wire_sigma_evals + 4 * j);
-        H::fr_to_limbs(ev[NEV - 1], out->perm_next_eval);
-        if constexpr (ULTRA) {
-            for (int j = 0; j < 15; j++) H::fr_to_limbs(ev[NEV + j], out->plookup_evals + 4 * j);
-            H::fr_to_limbs(tau, out->challenges + 0);
-            H::fr_to_limbs(beta, out->challenges + 4);
-            H::fr_to_limbs(gamma, out->challenges + 8);
-            H::fr_to_limbs(alpha, out->challenges + 12);
-            H::fr_to_limbs(zeta, out->challenges + 16);
-            H::fr_to_limbs(v, out->challenges + 20);
-        } else {
-            H::fr_to_limbs(beta, out->challenges + 0);
-            H::fr_to_limbs(gamma, out->challenges + 4);
-            H::fr_to_limbs(alpha, out->challenges + 8);
-            H::fr_to_limbs(zeta, out->challenges + 12);
-            H::fr_to_limbs(v, out->challenges + 16);
+        for (size_t i = 0; i < count; i++) {
+            ProofT *out = &outs[i];
+            const E *ev = I[i].ev;
+            if (i) {  // the shared parts of the batch proof, replicated
+                memcpy(out->split_quot_poly_comms, outs[0].split_quot_poly_comms, sizeof out->split_quot_poly_comms);
+                memcpy(out->split_inf, outs[0].split_inf, sizeof out->split_inf);
+                memcpy(out->opening_proof, outs[0].opening_proof, sizeof out->opening_proof);
+                memcpy(out->shifted_opening_proof, outs[0].shifted_opening_proof, sizeof out->shifted_opening_proof);
+                out->opening_inf = outs[0].opening_inf;
+                out->shifted_opening_inf = outs[0].shifted_opening_inf;
+            }
+            for (int j = 0; j < NW; j++) H::fr_to_limbs(ev[j], out->wires_evals + 4 * j);
+            for (int j = 0; j < NW - 1; j++) H::fr_to_limbs(ev[NW + j], out->wire_sigma_evals + 4 * j);
+            H::fr_to_limbs(ev[NEV - 1], out->perm_next_eval);
+            if constexpr (ULTRA) {
+                for (int j = 0; j < 15; j++) H::fr_to_limbs(ev[NEV + j], out->plookup_evals + 4 * j);
+                H::fr_to_limbs(tau, out->challenges + 0);
+                H::fr_to_limbs(beta, out->challenges + 4);
+                H::fr_to_limbs(gamma, out->challenges + 8);
+                H::fr_to_limbs(alpha, out->challenges + 12);
+                H::fr_to_limbs(zeta, out->challenges + 16);
+                H::fr_to_limbs(v, out->challenges + 20);
+            } else {
+                H::fr_to_limbs(beta, out->challenges + 0);
+                H::fr_to_limbs(gamma, out->challenges + 4);
+                H::fr_to_limbs(alpha, out->challenges + 8);
+                H::fr_to_limbs(zeta, out->challenges + 12);
+                H::fr_to_limbs(v, out->challenges + 16);
+            }
+            out->curve = pk0->curve;
         }
-        out->curve = pk->curve;
         return JF_OK;
     }
 
@@ -1631,6 +1749,52 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
         }
         return (size_t)(o - out);
     }
+
+    // `BatchProof<E>` CanonicalSerialize, compressed (structs.rs:271-292): per-instance vectors first, then the shared parts
+    template <class ProofT> static size_t serialize_batch(const ProofT *ps, size_t count, uint8_t *out) {
+        uint8_t *o = out;
+        auto u64 = [&](uint64_t v) { memcpy(o, &v, 8); o += 8; };
+        auto g1 = [&](const uint64_t *xy, int inf) { H::g1_bytes(xy, inf, o); o += 8 * L; };
+        auto fr = [&](const uint64_t *l) { H::fr_bytes(H::fr_from_limbs(l), o); o += 32; };
+        u64(count);  // wires_poly_comms_vec
+        for (size_t i = 0; i < count; i++) {
+            u64(NW);
+            for (int j = 0; j < NW; j++) g1(ps[i].wires_poly_comms + 2 * L * j, ps[i].wires_inf[j]);
+        }
+        u64(count);  // prod_perm_poly_comms_vec
+        for (size_t i = 0; i < count; i++) g1(ps[i].prod_perm_poly_comm, ps[i].prod_perm_inf);
+        u64(count);  // poly_evals_vec
+        for (size_t i = 0; i < count; i++) {
+            u64(NW);
+            for (int j = 0; j < NW; j++) fr(ps[i].wires_evals + 4 * j);
+            u64(NW - 1);
+            for (int j = 0; j < NW - 1; j++) fr(ps[i].wire_sigma_evals + 4 * j);
+            fr(ps[i].perm_next_eval);
+        }
+        u64(count);  // plookup_proofs_vec
+        for (size_t i = 0; i < count; i++) {
+            if constexpr (ULTRA) {
+                *o++ = 1;
+                u64(2);
+                for (int j = 0; j < 2; j++) g1(ps[i].h_poly_comms + 2 * L * j, ps[i].h_inf[j]);
+                g1(ps[i].prod_lookup_poly_comm, ps[i].prod_lookup_inf);
+                for (int j = 0; j < 15; j++) fr(ps[i].plookup_evals + 4 * j);
+            } else {
+                *o++ = 0;
+            }
+        }
+        u64(NW);  // split_quot_poly_comms
+        for (int j = 0; j < NW; j++) g1(ps[0].split_quot_poly_comms + 2 * L * j, ps[0].split_inf[j]);
+        g1(ps[0].opening_proof, ps[0].opening_inf);
+        g1(ps[0].shifted_opening_proof, ps[0].shifted_opening_inf);
+        return (size_t)(o - out);
+    }
+    static size_t batch_size(size_t count) {
+        const size_t pt = 8 * L;
+        size_t per = 8 + NW * pt + pt + 8 + NW * 32 + 8 + (NW - 1) * 32 + 32 + 1;
+        if (ULTRA) per += 8 + 2 * pt + pt + 15 * 32;
+        return 4 * 8 + count * per + 8 + NW * pt + 2 * pt;
+    }
 };
 
 struct Bn254Plonk : Bn254G1 {
@@ -1646,6 +1810,27 @@ struct Bls12381Plonk : Bls12381G1 {
     if (!(ctx)) return JF_ERR_INVALID_ARG;        \
     std::lock_guard<std::mutex> lock_((ctx)->mu); \
     cudaSetDevice((ctx)->device)
+
+// shared argument checks and the error drain of the two batch entry points
+template <int NWT, class ProofT>
+static int batch_prove_entry(jf_ctx *ctx, jf_plonk_pk *const *pks, size_t count, const uint64_t *const *witnesses, const uint64_t *blinders,
+                             int transcript_kind, const uint8_t *extra_msg, size_t extra_len, ProofT *out) {
+    if (!pks || !witnesses || !blinders || !out || count == 0)
+        return fail(ctx, JF_ERR_INVALID_ARG, "batch_prove: zero number of circuits/proving keys or a null argument");
+    if (count > 64) return fail(ctx, JF_ERR_INVALID_ARG, "batch_prove: at most 64 instances");
+    for (size_t i = 0; i < count; i++)
+        if (!pks[i] || !witnesses[i]) return fail(ctx, JF_ERR_INVALID_ARG, "batch_prove: null proving key or witness");
+    if (transcript_kind != 0 && transcript_kind != 1) return fail(ctx, JF_ERR_INVALID_ARG, "batch_prove: unknown transcript");
+    const int rc = pks[0]->curve == JF_BN254
+                       ? Plonk<Bn254Plonk, NWT>::batch_prove(ctx, pks, count, witnesses, blinders, transcript_kind, extra_msg, extra_len, out)
+                       : Plonk<Bls12381Plonk, NWT>::batch_prove(ctx, pks, count, witnesses, blinders, transcript_kind, extra_msg, extra_len, out);
+    if (rc != JF_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        for (size_t i = 0; i < count; i++)
+            if (pks[i]->side) cudaStreamSynchronize(pks[i]->side);
+    }
+    return rc;
+}
 
 extern "C" {
 
@@ -1696,6 +1881,36 @@ int jf_ultraplonk_prove(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *witness, c
         if (pk->side) cudaStreamSynchronize(pk->side);
     }
     return rc;
+}
+
+int jf_plonk_batch_prove(jf_ctx *ctx, jf_plonk_pk *const *pks, size_t count, const uint64_t *const *witnesses, const uint64_t *blinders,
+                         int transcript_kind, const uint8_t *extra_msg, size_t extra_len, jf_plonk_proof *out) {
+    JF_GUARD(ctx);
+    return batch_prove_entry<NW_TURBO>(ctx, pks, count, witnesses, blinders, transcript_kind, extra_msg, extra_len, out);
+}
+
+int jf_ultraplonk_batch_prove(jf_ctx *ctx, jf_plonk_pk *const *pks, size_t count, const uint64_t *const *witnesses,
+                              const uint64_t *blinders, int transcript_kind, const uint8_t *extra_msg, size_t extra_len,
+                              jf_ultraplonk_proof *out) {
+    JF_GUARD(ctx);
+    return batch_prove_entry<NW_ULTRA>(ctx, pks, count, witnesses, blinders, transcript_kind, extra_msg, extra_len, out);
+}
+
+long jf_plonk_batch_proof_serialize(const jf_plonk_proof *proofs, size_t count, uint8_t *out, size_t cap) {
+    if (!proofs || !out || count == 0) return JF_ERR_INVALID_ARG;
+    const bool bn = proofs[0].curve == JF_BN254;
+    if (!bn && proofs[0].curve != JF_BLS12_381) return JF_ERR_INVALID_ARG;
+    if (cap < (bn ? Plonk<Bn254Plonk>::batch_size(count) : Plonk<Bls12381Plonk>::batch_size(count))) return JF_ERR_INVALID_ARG;
+    return (long)(bn ? Plonk<Bn254Plonk>::serialize_batch(proofs, count, out) : Plonk<Bls12381Plonk>::serialize_batch(proofs, count, out));
+}
+
+long jf_ultraplonk_batch_proof_serialize(const jf_ultraplonk_proof *proofs, size_t count, uint8_t *out, size_t cap) {
+    if (!proofs || !out || count == 0) return JF_ERR_INVALID_ARG;
+    const bool bn = proofs[0].curve == JF_BN254;
+    if (!bn && proofs[0].curve != JF_BLS12_381) return JF_ERR_INVALID_ARG;
+    if (cap < (bn ? Plonk<Bn254Plonk, NW_ULTRA>::batch_size(count) : Plonk<Bls12381Plonk, NW_ULTRA>::batch_size(count))) return JF_ERR_INVALID_ARG;
+    return (long)(bn ? Plonk<Bn254Plonk, NW_ULTRA>::serialize_batch(proofs, count, out)
+                     : Plonk<Bls12381Plonk, NW_ULTRA>::serialize_batch(proofs, count, out));
 }
 
 long jf_ultraplonk_proof_serialize(const jf_ultraplonk_proof *proof, uint8_t *out, size_t cap) {

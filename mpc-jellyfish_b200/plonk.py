@@ -137,7 +137,81 @@ class ProvingKey:
             pass
 
 
+def _proof_from_raw(curve: str, raw, ultra: bool) -> Proof:
+    L = _ffi.CURVE_FQ_LIMBS[curve]
+    nw = ULTRA_WIRE_TYPES if ultra else NUM_WIRE_TYPES
+
+    def pts(arr, count):
+        return np.array(arr[: count * 2 * L], dtype=np.uint64).reshape(count, 2 * L)
+
+    pr = Proof(
+        curve=curve,
+        wires_poly_comms=pts(raw.wires_poly_comms, nw), wires_inf=[bool(v) for v in raw.wires_inf],
+        prod_perm_poly_comm=pts(raw.prod_perm_poly_comm, 1)[0], prod_perm_inf=bool(raw.prod_perm_inf),
+        split_quot_poly_comms=pts(raw.split_quot_poly_comms, nw), split_inf=[bool(v) for v in raw.split_inf],
+        opening_proof=pts(raw.opening_proof, 1)[0], opening_inf=bool(raw.opening_inf),
+        shifted_opening_proof=pts(raw.shifted_opening_proof, 1)[0], shifted_opening_inf=bool(raw.shifted_opening_inf),
+        wires_evals=np.array(raw.wires_evals, dtype=np.uint64).reshape(nw, 4),
+        wire_sigma_evals=np.array(raw.wire_sigma_evals, dtype=np.uint64).reshape(nw - 1, 4),
+        perm_next_eval=np.array(raw.perm_next_eval, dtype=np.uint64),
+        challenges=np.array(raw.challenges, dtype=np.uint64).reshape(-1, 4), _raw=raw)
+    if ultra:
+        pr.h_poly_comms = pts(raw.h_poly_comms, 2)
+        pr.h_inf = [bool(v) for v in raw.h_inf]
+        pr.prod_lookup_poly_comm = pts(raw.prod_lookup_poly_comm, 1)[0]
+        pr.prod_lookup_inf = bool(raw.prod_lookup_inf)
+        pr.plookup_evals = np.array(raw.plookup_evals, dtype=np.uint64).reshape(15, 4)
+    return pr
+
+
+@dataclass
+class BatchProof:
+    """`BatchProof<E>` (structs.rs:271-292): per-instance records plus the shared split-quotient commitments and opening
+    proofs (present in every record)."""
+    proofs: List[Proof]
+    _raw: object = None
+    ultra: bool = False
+
+    def __len__(self):
+        return len(self.proofs)
+
+    def serialize_compressed(self) -> bytes:
+        buf = ctypes.create_string_buffer(4096 * (len(self.proofs) + 1))
+        fn = _ffi.lib().jf_ultraplonk_batch_proof_serialize if self.ultra else _ffi.lib().jf_plonk_batch_proof_serialize
+        n = fn(self._raw, len(self.proofs), buf, len(buf))
+        if n < 0:
+            raise InvalidParameters("batch proof serialization failed (%d)" % n)
+        return buf.raw[:n]
+
+
 class PlonkKzgSnark:
+    @staticmethod
+    def batch_prove(pks: Sequence["ProvingKey"], witnesses: Sequence[np.ndarray], blinders: np.ndarray, transcript: str = "solidity",
+                    extra_transcript_init_msg: Optional[bytes] = None) -> BatchProof:
+        """`PlonkKzgSnark::batch_prove` (snark.rs:201-469).  blinders: (count * 13 + 4, 4) for TurboPlonk, (count * 24 + 5, 4) for
+        UltraPlonk, in the reference's prng order (all wire masks, [all h masks,] all z masks, [all lookup-product masks,] split)."""
+        if not pks or len(pks) != len(witnesses):
+            raise InvalidParameters("the number of circuits != the number of proving keys (or zero)")
+        ctx, ultra, count = pks[0].ctx, pks[0].ultra, len(pks)
+        nw = ULTRA_WIRE_TYPES if ultra else NUM_WIRE_TYPES
+        per = 2 * nw + 3 + (9 if ultra else 0)
+        b = np.ascontiguousarray(blinders, dtype=np.uint64)
+        if b.shape != (count * per + nw - 1, 4):
+            raise InvalidParameters("blinders must be (%d, 4)" % (count * per + nw - 1))
+        ws = [np.ascontiguousarray(w, dtype=np.uint64) for w in witnesses]
+        for pk, w in zip(pks, ws):
+            if pk.ultra != ultra:
+                raise InvalidParameters("inconsistent plonk circuit types")
+            if w.shape != (pk.num_vars, 4):
+                raise InvalidParameters("witness must be (num_vars, 4)")
+        handles = (ctypes.c_void_p * count)(*[pk._h for pk in pks])
+        wptrs = (_ffi.c_u64p * count)(*[w.ctypes.data_as(_ffi.c_u64p) for w in ws])
+        raw = ((_ffi.UltraPlonkProofStruct if ultra else _ffi.PlonkProofStruct) * count)()
+        fn = ctx._lib.jf_ultraplonk_batch_prove if ultra else ctx._lib.jf_plonk_batch_prove
+        ctx._check(fn(ctx._h, handles, count, wptrs, b.ctypes.data_as(_ffi.c_u64p), TRANSCRIPT_KINDS[transcript],
+                      extra_transcript_init_msg, len(extra_transcript_init_msg) if extra_transcript_init_msg else 0, raw))
+        return BatchProof([_proof_from_raw(pks[0].key.curve, raw[i], ultra) for i in range(count)], raw, ultra)
+
     @staticmethod
     def preprocess(ctx: Context, key: CommitKey, selector_evals: np.ndarray, sigma_evals: np.ndarray, k: np.ndarray,
                    wire_variables: np.ndarray, num_vars: int, pub_input_gate_ids: Sequence[int] = (),

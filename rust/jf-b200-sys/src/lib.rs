@@ -130,6 +130,14 @@ extern "C" {
                                transcript_kind: c_int, extra_msg: *const u8, extra_len: usize,
                                out: *mut jf_ultraplonk_proof) -> c_int;
     pub fn jf_ultraplonk_proof_serialize(proof: *const jf_ultraplonk_proof, out: *mut u8, cap: usize) -> c_long;
+    pub fn jf_plonk_batch_prove(ctx: *mut jf_ctx, pks: *const *mut jf_plonk_pk, count: usize, witnesses: *const *const u64,
+                                blinders: *const u64, transcript_kind: c_int, extra_msg: *const u8, extra_len: usize,
+                                out: *mut jf_plonk_proof) -> c_int;
+    pub fn jf_ultraplonk_batch_prove(ctx: *mut jf_ctx, pks: *const *mut jf_plonk_pk, count: usize, witnesses: *const *const u64,
+                                     blinders: *const u64, transcript_kind: c_int, extra_msg: *const u8, extra_len: usize,
+                                     out: *mut jf_ultraplonk_proof) -> c_int;
+    pub fn jf_plonk_batch_proof_serialize(proofs: *const jf_plonk_proof, count: usize, out: *mut u8, cap: usize) -> c_long;
+    pub fn jf_ultraplonk_batch_proof_serialize(proofs: *const jf_ultraplonk_proof, count: usize, out: *mut u8, cap: usize) -> c_long;
     pub fn jf_plonk_vk_commitments(ctx: *mut jf_ctx, pk: *const jf_plonk_pk, out_xy: *mut u64, out_inf: *mut c_int) -> c_int;
     pub fn jf_plonk_pk_free(ctx: *mut jf_ctx, pk: *mut jf_plonk_pk);
     pub fn jf_plonk_prove(ctx: *mut jf_ctx, pk: *mut jf_plonk_pk, witness: *const u64, blinders: *const u64,
