@@ -392,3 +392,54 @@ impl<E: GpuCurve> GpuProvingKey<E> {
     }
 }
 impl<E: GpuCurve> Drop for GpuProvingKey<E> { fn drop(&mut self) { unsafe { sys::jf_plonk_pk_free(self.key.gpu.ctx, self.pk) } } }
+
+impl<E: GpuCurve> GpuProvingKey<E> {
+    /// `PlonkKzgSnark::batch_prove` (snark.rs:201-469) for TurboPlonk keys: one transcript, ONE quotient, one pair of opening
+    /// proofs.  `blinders`: `keys.len() * 13 + 4` elements in the reference's prng order (all wire masks, all z masks, split).
+    /// Record i of the result holds instance i's parts; the shared parts are replicated in every record.
+    pub fn batch_prove(keys: &[&Self], witnesses: &[&[E::ScalarField]], blinders: &[E::ScalarField], solidity_transcript: bool,
+                       extra: Option<&[u8]>) -> Result<Vec<sys::jf_plonk_proof>, GpuError> {
+        assert!(!keys.is_empty() && keys.len() == witnesses.len() && blinders.len() == keys.len() * 13 + 4);
+        let pks: Vec<*mut sys::jf_plonk_pk> = keys.iter().map(|k| k.pk).collect();
+        let ws: Vec<*const u64> = witnesses.iter().map(|w| w.as_ptr() as *const u64).collect();
+        let mut out: Vec<MaybeUninit<sys::jf_plonk_proof>> = (0..keys.len()).map(|_| MaybeUninit::uninit()).collect();
+        keys[0].key.gpu.check(unsafe {
+            sys::jf_plonk_batch_prove(keys[0].key.gpu.ctx, pks.as_ptr(), pks.len(), ws.as_ptr(), blinders.as_ptr() as *const u64,
+                                      if solidity_transcript { 0 } else { 1 }, extra.map_or(ptr::null(), |e| e.as_ptr()),
+                                      extra.map_or(0, |e| e.len()), out.as_mut_ptr() as *mut sys::jf_plonk_proof)
+        })?;
+        Ok(out.into_iter().map(|p| unsafe { p.assume_init() }).collect())
+    }
+}
+
+/// UltraPlonk (`PlonkCircuit::new_ultra_plonk`): the same key type on the C side, built from 14 selector columns, 6 sigma rows,
+/// 6 `k`, 6 wire rows and the three per-gate Plookup columns; proofs carry the `PlookupProof`.
+pub struct GpuUltraProvingKey<E: GpuCurve> { key: Arc<GpuCommitKey<E>>, pk: *mut sys::jf_plonk_pk }
+impl<E: GpuCurve> GpuUltraProvingKey<E> {
+    #[allow(clippy::too_many_arguments)]
+    pub fn preprocess(key: Arc<GpuCommitKey<E>>, log_n: u32, selectors: &[E::ScalarField], extended_perm: &[E::ScalarField],
+                      k: &[E::ScalarField; 6], wire_variables: &[u32], num_vars: usize, io_gate_ids: &[u32], range_bit_len: u32,
+                      table_key: &[E::ScalarField], table_dom_sep: &[E::ScalarField], q_dom_sep: &[E::ScalarField], flags: i32)
+                      -> Result<Self, GpuError> {
+        let mut pk = ptr::null_mut();
+        key.gpu.check(unsafe {
+            sys::jf_ultraplonk_preprocess(key.gpu.ctx, key.srs, log_n, selectors.as_ptr() as *const u64, extended_perm.as_ptr() as *const u64,
+                                          k.as_ptr() as *const u64, wire_variables.as_ptr(), num_vars, io_gate_ids.as_ptr(),
+                                          io_gate_ids.len(), range_bit_len, table_key.as_ptr() as *const u64,
+                                          table_dom_sep.as_ptr() as *const u64, q_dom_sep.as_ptr() as *const u64, flags, &mut pk)
+        })?;
+        Ok(Self { key, pk })
+    }
+    /// `blinders`: 29 elements in the reference's order (6 x 2 wires, 3 + 3 for h1 / h2, 3 for z, 3 for the lookup product, 5 split).
+    pub fn prove(&self, witness: &[E::ScalarField], blinders: &[E::ScalarField; 29], solidity_transcript: bool, extra: Option<&[u8]>)
+                 -> Result<sys::jf_ultraplonk_proof, GpuError> {
+        let mut out = MaybeUninit::<sys::jf_ultraplonk_proof>::uninit();
+        self.key.gpu.check(unsafe {
+            sys::jf_ultraplonk_prove(self.key.gpu.ctx, self.pk, witness.as_ptr() as *const u64, blinders.as_ptr() as *const u64,
+                                     if solidity_transcript { 0 } else { 1 }, extra.map_or(ptr::null(), |e| e.as_ptr()),
+                                     extra.map_or(0, |e| e.len()), out.as_mut_ptr())
+        })?;
+        Ok(unsafe { out.assume_init() })
+    }
+}
+impl<E: GpuCurve> Drop for GpuUltraProvingKey<E> { fn drop(&mut self) { unsafe { sys::jf_plonk_pk_free(self.key.gpu.ctx, self.pk) } } }
