@@ -415,7 +415,7 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
     pk16.free()
     key16.free()
     # UltraPlonk (Plookup) on the same bench circuit (`gen_circuit_for_bench(2^20, PlonkType::UltraPlonk)`, bench.rs:29-46; the
-    # reference publishes 33 701 ns/constraint for BN254 at 2^15, bench.md:25): 6 wire types, 35 polynomials on the full 8n coset
+    # reference publishes 33 701 ns/constraint for BN254 at 2^15, bench.md:25): 6 wire types, 35 polynomials on seven sub-cosets
     ultra = None
     if not args.no_sweep:
         arrU = B.bench_circuit_arrays(ctx, PROVE_LOG_N, ultra=True)
@@ -446,7 +446,8 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
         ultra = {"value": max_over_ranks((time.perf_counter() - t0) * 1e3 / steps), "unit": "ms",
                  "gpu_launches": int((ctx.launch_count - l0) // steps),
                  "note": "UltraPlonk (Plookup) proof of the 2^20-gate bench circuit, SolidityTranscript, accepted by the restated verifier; "
-                         "round 3 on the reference's full 8n coset (35 polynomials); the sorted lookup vector is merged on the host"}
+                         "round 3 on seven sub-cosets of n points (35 polynomials; the reference's 8n coset gives the same bytes, "
+                         "tests/test_gpu_ultraplonk.py); the sorted lookup vector is merged on the host"}
         pkU.free()
         keyU.free()
     if rank != 0:

@@ -258,7 +258,8 @@ long jf_plonk_proof_serialize(const jf_plonk_proof *proof, uint8_t *out, size_t 
  * `table_key_vec()`, `table_dom_sep_vec()`, `q_dom_sep()` (n each; :873-888); the range table {0 .. 2^range_bit_len - 1, 0 ..}
  * is built on the device.  jf_plonk_vk_commitments then yields 14 selector, 6 sigma and the 4 `PlookupVerifyingKey`
  * commitments (range table, key table, table dom sep, q dom sep; snark.rs:573-594), in that order.
- * Round 3 uses the reference's 8n-point coset (the quotient has degree 6 n + 8); flags: bit 1 (skip zero selectors) only. */
+ * Round 3 evaluates the quotient (degree 6 n + 8) on SEVEN sub-cosets of n points (from n = 16), like the six of the TurboPlonk
+ * prover; flags: 2 (skip zero selectors) and 4 (the reference's 8n-point coset instead) as for jf_plonk_preprocess. */
 int jf_ultraplonk_preprocess(jf_ctx *ctx, const jf_srs *srs, unsigned log_n, const uint64_t *selector_evals,
                              const uint64_t *sigma_evals, const uint64_t *k, const uint32_t *wire_variables, size_t num_vars,
                              const uint32_t *pub_input_gate_ids, size_t num_inputs, unsigned range_bit_len,

@@ -7,7 +7,7 @@
 //   Prover::run_plookup_1st/2nd_round, compute_plookup_evaluations, compute_quotient_plookup_contribution,
 //   compute_lin_poly_plookup_contribution, plookup_(shifted_)open_polys_ref
 //                                          plonk/src/proof_system/prover.rs:98-123,150-190,239-297,427-460,773-888,1037-1113
-// The quotient of an UltraPlonk instance has degree 6 n + 8, so round 3 runs on the reference's full 8n-point coset.
+// The quotient of an UltraPlonk instance has degree 6 n + 8: round 3 runs on seven sub-cosets of n points (six for TurboPlonk).
 //
 // Replaces, for one TurboPlonk instance with 5 wire types and no Plookup (`Plonk<C, 5>`):
 //   PlonkKzgSnark::preprocess              plonk/src/proof_system/snark.rs:529-611
@@ -401,14 +401,16 @@ template <class F> __global__ void degree_check_kernel(const Fp<F> *c, size_t de
 // Quotient coefficients from its interpolants on the sub-cosets: with t = sum_k X^(k n) t_k (deg t_k < n) and
 // X^n = c_r on coset r, the interpolant there is T_r = sum_k c_r^k t_k, so t_k[j] = sum_r Vinv[k][r] T_r[j] where
 // V[r][k] = c_r^k is a SUB x SUB Vandermonde matrix (inverted once per proving key on the host).
-static constexpr int SUB = 6;  // 6 n points determine the quotient (degree 5 n + 7) for every n >= 8 (used from n = 16)
-template <class F> struct SolveArgs {
+// SUB = 6: 6 n points determine the TurboPlonk quotient (degree 5 n + 7) for every n >= 8; SUB = 7: 7 n points the UltraPlonk
+// quotient (degree 6 n + 8) for every n >= 9 (both used from n = 16, which leaves coefficients above the degree to check)
+static constexpr int SUB_MAX = 7;
+template <class F, int SUB> struct SolveArgs {
     const Fp<F> *T;  // SUB rows of n
     Fp<F> *t;        // SUB * n coefficients
     uint32_t n;
     Fp<F> vinv[SUB][SUB];
 };
-template <class F> __global__ void __launch_bounds__(128) subcoset_solve_kernel(const __grid_constant__ SolveArgs<F> a) {
+template <class F, int SUB> __global__ void __launch_bounds__(128) subcoset_solve_kernel(const __grid_constant__ SolveArgs<F, SUB> a) {
     using E = Fp<F>;
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= a.n) return;
@@ -564,10 +566,10 @@ struct jf_plonk_pk {
     const jf_srs *srs = nullptr;
     unsigned log_n = 0, log_m = 0;
     size_t n = 0, m = 0, np = 0;  // np = n + PAD: stride of the n-sized polynomial buffers
-    int sub = 0;                  // SUB: the quotient is evaluated on 6 of the 8 sub-cosets (n points each); 0: all 8n points
+    int sub = 0;                  // 6 | 7: the quotient is evaluated on that many of the 8 sub-cosets (n points each); 0: all 8n points
     size_t mq = 0;                // evaluation points per polynomial: sub ? sub * n : m
-    uint64_t sub_off[6 * 4];      // offsets g w_8n^r of the sub-cosets (Montgomery limbs)
-    uint32_t vinv[6][6][8];       // inverse Vandermonde matrix of subcoset_solve_kernel
+    uint64_t sub_off[jf::SUB_MAX * 4];               // offsets g w_8n^r of the sub-cosets (Montgomery limbs)
+    uint32_t vinv[jf::SUB_MAX * jf::SUB_MAX][8];     // inverse Vandermonde matrix of subcoset_solve_kernel, row-major sub x sub
     size_t num_vars = 0;
     uint32_t num_inputs = 0;
     int cache_coset = 0;
@@ -703,6 +705,7 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
     static constexpr bool ULTRA = D::ULTRA;
     static constexpr int NVK = NSEL + NW + (ULTRA ? 4 : 0);  // verifying-key commitments
     static constexpr int NROWS = NSEL + 2 * NW + 2 + (ULTRA ? 7 : 0);  // coset-evaluation rows of round 3
+    static constexpr int SUB = ULTRA ? 7 : 6;  // sub-cosets of n points that determine the quotient (degree NW (n + 1) + 2)
 
     static E kf(const jf_plonk_pk *pk, int j) {
         E r;
@@ -832,8 +835,8 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
         pk->skip_zero = (flags & 2) ? 1 : 0;
         // 6 n >= 5 n + 8 coefficients needs n >= 8; n >= 16 also leaves n - 8 >= 8 coefficients above the quotient's degree
         // for the WrongQuotientPolyDegree check (at n = 8 the six-row interpolant has no coefficient above degree 47 at all)
-        // (UltraPlonk: the quotient has 6 n + 9 coefficients: the full 8n coset, as in the reference)
-        pk->sub = (!ULTRA && log_n >= 4 && !(flags & 4)) ? SUB : 0;
+        // (UltraPlonk: 7 n >= 6 n + 9 coefficients needs n >= 9; n >= 16 leaves n - 9 >= 7 coefficients above the degree)
+        pk->sub = (log_n >= 4 && !(flags & 4)) ? SUB : 0;
         pk->mq = pk->sub ? (size_t)pk->sub * n : m;
         if (flags & 2) {
             for (int sel = 0; sel < NSEL; sel++) {
@@ -932,7 +935,7 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
                 }
             }
             for (int r = 0; r < SUB; r++)
-                for (int kk = 0; kk < SUB; kk++) memcpy(pk->vinv[r][kk], V[r][SUB + kk].v, 32);
+                for (int kk = 0; kk < SUB; kk++) memcpy(pk->vinv[r * SUB + kk], V[r][SUB + kk].v, 32);
         }
         // ---- device buffers ----
         const size_t fe = sizeof(E);
@@ -1431,12 +1434,12 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
             const E *T = (const E *)pk->d_q;  // quotient coefficients
             if (pk->sub) {
                 JF_TRY(ntt_run_cosets(ctx, C::FR_ID, pk->d_q, n, n, pk->d_q, pk->log_n, 1, pk->sub_off, pk->sub, 1));
-                SolveArgs<Fr> sa;
+                SolveArgs<Fr, SUB> sa;
                 sa.T = (const E *)pk->d_q;
                 sa.t = (E *)pk->d_a;  // free since round 2
                 sa.n = (uint32_t)n;
-                memcpy(sa.vinv, pk->vinv, sizeof sa.vinv);
-                JF_LAUNCH(ctx, "subcoset_solve", subcoset_solve_kernel<Fr><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sa));
+                memcpy(sa.vinv, pk->vinv, sizeof sa.vinv);  // row-major SUB x SUB on both sides
+                JF_LAUNCH(ctx, "subcoset_solve", subcoset_solve_kernel<Fr, SUB><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sa));
                 T = (const E *)pk->d_a;
             } else {
                 JF_TRY(ntt_run(ctx, C::FR_ID, pk->d_q, pk->d_q, m, pk->log_m, 1, pk->gen_limbs, 1, m));
@@ -1860,11 +1863,11 @@ int jf_ultraplonk_preprocess(jf_ctx *ctx, const jf_srs *srs, unsigned log_n, con
     if (srs->curve == JF_BN254) {
         Plonk<Bn254Plonk, NW_ULTRA>::LookupCols lc{range_bit_len, table_key_evals, table_dom_sep_evals, q_dom_sep_evals};
         return Plonk<Bn254Plonk, NW_ULTRA>::preprocess(ctx, srs, log_n, selector_evals, sigma_evals, k, wire_variables, num_vars,
-                                                       pub_input_gate_ids, num_inputs, flags & 2, out, &lc);
+                                                       pub_input_gate_ids, num_inputs, flags & 6, out, &lc);
     }
     Plonk<Bls12381Plonk, NW_ULTRA>::LookupCols lc{range_bit_len, table_key_evals, table_dom_sep_evals, q_dom_sep_evals};
     return Plonk<Bls12381Plonk, NW_ULTRA>::preprocess(ctx, srs, log_n, selector_evals, sigma_evals, k, wire_variables, num_vars,
-                                                      pub_input_gate_ids, num_inputs, flags & 2, out, &lc);
+                                                      pub_input_gate_ids, num_inputs, flags & 6, out, &lc);
 }
 
 int jf_ultraplonk_prove(jf_ctx *ctx, jf_plonk_pk *pk, const uint64_t *witness, const uint64_t *blinders, int transcript_kind,

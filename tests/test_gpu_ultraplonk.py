@@ -22,13 +22,13 @@ def P():
     return plonk_ref
 
 
-def _setup(ctx, co, py, P, cv, cs, beta, skip=False):
+def _setup(ctx, co, py, P, cv, cs, beta, skip=False, full=False):
     import mpc_jellyfish_b200 as jf
     arr = U.arrays_from_oracle_circuit(co, py, cs)
     key = ctx.generate_srs_for_testing(cv.name, beta, cs.n + 3)
     pk = jf.PlonkKzgSnark.preprocess_ultra(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"],
                                            arr["pub_gate_ids"], arr["range_bit_len"], arr["table_key"], arr["table_dom_sep"],
-                                           arr["q_dom_sep"], skip_zero_selectors=skip)
+                                           arr["q_dom_sep"], skip_zero_selectors=skip, full_quotient_coset=full)
     return arr, key, pk
 
 
@@ -80,10 +80,11 @@ def test_ultraplonk_bls12_381_and_zero_selector_skip(ctx, co, py, P):
     ints = [rnd.randrange(fr.p) for _ in range(29)]
     bl = co.ints_to_limbs([fr.to_mont(v) for v in ints], 4)
     want = P.serialize_proof(cv, P.prove(cv, cs, opk, ints, "solidity"))
-    for skip in (False, True):
-        arr, key, pk = _setup(ctx, co, py, P, cv, cs, beta, skip=skip)
+    for skip, full in ((False, False), (True, False), (False, True), (True, True)):
+        # seven sub-cosets of n points (default) and the reference's literal 8n coset give the same quotient polynomial
+        arr, key, pk = _setup(ctx, co, py, P, cv, cs, beta, skip=skip, full=full)
         proof = jf.PlonkKzgSnark.prove_ultra(pk, arr["witness"], bl, "solidity")
-        assert proof.serialize_compressed() == want, "skip=%s" % skip
+        assert proof.serialize_compressed() == want, "skip=%s full=%s" % (skip, full)
         assert P.verify(cv, U.vk_from_product(co, cv, pk, cs.k), cs.public_input(), U.proof_to_oracle(co, cv, proof), beta, "solidity")
         pk.free()
         key.free()
