@@ -447,7 +447,7 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
                  "gpu_launches": int((ctx.launch_count - l0) // steps),
                  "note": "UltraPlonk (Plookup) proof of the 2^20-gate bench circuit, SolidityTranscript, accepted by the restated verifier; "
                          "round 3 on seven sub-cosets of n points (35 polynomials; the reference's 8n coset gives the same bytes, "
-                         "tests/test_gpu_ultraplonk.py); the sorted lookup vector is merged on the host"}
+                         "tests/test_gpu_ultraplonk.py); the sorted lookup vector is built on the device (hash set of the table values, counts, prefix sum, expansion)"}
         pkU.free()
         keyU.free()
     if rank != 0:

@@ -35,7 +35,6 @@
 //                      (prover.rs:504-506; ark-poly's `/` drops the remainder)
 #include <string.h>
 #include <algorithm>
-#include <unordered_map>
 #include "common.cuh"
 #include "ec.cuh"
 #include "transcript.hpp"
@@ -475,6 +474,155 @@ __global__ void lookup_ab_kernel(const Fp<F> *mt, const Fp<F> *ml, const Fp<F> *
     stf(a + j, av);
     stf(b + j, bv);
 }
+// ---- sorted lookup vector (compute_lookup_sorted_vec_polynomials, constraint_system.rs:1370-1418) ---------------
+// The reference walks the merged table in order and emits every entry once plus, at the FIRST row that holds a value, once per
+// lookup of that value; a lookup value absent from the table leaves the vector short (its error).  On the device:
+//   sv_insert : open-addressing set over the table VALUES; a slot holds the smallest row index with that value
+//   sv_count  : every lookup finds its value's slot and bumps that row's count (a miss raises `flag`)
+//   sv_block / sv_carry / sv_offsets : exclusive prefix sum of (1 + count) -> the row's first position in the vector
+//   sv_expand : every output position finds its row by bisection of the offsets and copies that row's value
+static constexpr uint32_t SV_EMPTY = 0xFFFFFFFFu;
+static constexpr int SV_T = 256, SV_I = 4;  // rows per block of the prefix sum: SV_T * SV_I
+template <class F> __device__ __forceinline__ uint32_t sv_hash(const Fp<F> &k) {
+    uint32_t h = 0x811C9DC5u;
+#pragma unroll
+    for (int i = 0; i < F::N; i++) h = (h ^ k.v[i]) * 0x01000193u + (h >> 15);
+    h ^= h >> 16;
+    h *= 0x7FEB352Du;
+    return h ^ (h >> 15);
+}
+template <class F> __device__ __forceinline__ bool sv_eq(const Fp<F> &a, const Fp<F> &b) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < F::N; i++) d |= a.v[i] ^ b.v[i];
+    return d == 0;
+}
+template <class F> __global__ void sv_insert_kernel(const Fp<F> *mt, uint32_t n, uint32_t *slots, uint32_t mask) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Fp<F> key = ldf(mt + i);
+    uint32_t h = sv_hash(key) & mask;
+    for (;;) {
+        uint32_t cur = *(volatile uint32_t *)(slots + h);
+        if (cur == SV_EMPTY) {
+            cur = atomicCAS(slots + h, SV_EMPTY, i);
+            if (cur == SV_EMPTY) return;
+        }
+        // an occupied slot keeps its value for good (only the row index may still fall)
+        if (sv_eq(ldf(mt + cur), key)) {
+            if (cur > i) atomicMin(slots + h, i);
+            return;
+        }
+        h = (h + 1) & mask;
+    }
+}
+template <class F>
+__global__ void sv_count_kernel(const Fp<F> *mt, const Fp<F> *ml, uint32_t n_lookups, const uint32_t *slots, uint32_t mask, uint32_t *cnt,
+                                uint32_t *flag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t row = SV_EMPTY;
+    if (i < n_lookups) {
+        const Fp<F> key = ldf(ml + i);
+        uint32_t h = sv_hash(key) & mask;
+        for (;;) {
+            const uint32_t cur = slots[h];
+            if (cur == SV_EMPTY) break;
+            if (sv_eq(ldf(mt + cur), key)) {
+                row = cur;
+                break;
+            }
+            h = (h + 1) & mask;
+        }
+        if (row == SV_EMPTY) *flag = 1;
+    }
+    // circuits look the same few values up over and over: one atomic per distinct row and warp
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, row);
+    if (row != SV_EMPTY && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(cnt + row, (uint32_t)__popc(peers));
+}
+__global__ void __launch_bounds__(SV_T) sv_block_kernel(const uint32_t *cnt, uint32_t n, uint32_t *bsum) {
+    __shared__ uint32_t sh[SV_T / 32];
+    const uint32_t base = (blockIdx.x * SV_T + threadIdx.x) * SV_I;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < SV_I; k++)
+        if (base + k < n) v += 1 + cnt[base + k];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < SV_T / 32; w++) t += sh[w];
+        bsum[blockIdx.x] = t;
+    }
+}
+// exclusive prefix sum of the block totals, in place, by one block; bsum[blocks] = the length of the vector
+__global__ void __launch_bounds__(1024) sv_carry_kernel(uint32_t *bsum, uint32_t blocks) {
+    __shared__ uint32_t sh[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < blocks; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < blocks ? bsum[i] : 0;
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if ((threadIdx.x & 31) >= (uint32_t)o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = sh[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+                if (threadIdx.x >= (uint32_t)o) w += y;
+            }
+            sh[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const uint32_t before = carry + (threadIdx.x >= 32 ? sh[(threadIdx.x >> 5) - 1] : 0) + x - v;
+        if (i < blocks) bsum[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bsum[blocks] = carry;
+}
+__global__ void __launch_bounds__(SV_T) sv_offsets_kernel(const uint32_t *cnt, uint32_t n, const uint32_t *bsum, uint32_t *off) {
+    __shared__ uint32_t sh[SV_T / 32];
+    const uint32_t base = (blockIdx.x * SV_T + threadIdx.x) * SV_I;
+    uint32_t r[SV_I], v = 0;
+#pragma unroll
+    for (int k = 0; k < SV_I; k++) {
+        r[k] = base + k < n ? 1 + cnt[base + k] : 0;
+        v += r[k];
+    }
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if ((threadIdx.x & 31) >= (uint32_t)o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = x;
+    __syncthreads();
+    uint32_t before = bsum[blockIdx.x] + x - v;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) before += sh[w];
+#pragma unroll
+    for (int k = 0; k < SV_I; k++) {
+        if (base + k < n) off[base + k] = before;
+        before += r[k];
+    }
+}
+template <class F> __global__ void sv_expand_kernel(const Fp<F> *mt, const uint32_t *off, uint32_t n, uint32_t len, Fp<F> *out) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= len) return;
+    uint32_t lo = 0, hi = n;  // the last row with off[row] <= p
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= p) lo = mid;
+        else hi = mid;
+    }
+    stf(out + p, ldf(mt + lo));
+}
 template <class F> __global__ void set_one_kernel(Fp<F> *p) {
     if (threadIdx.x == 0 && blockIdx.x == 0) stf(p, Fp<F>::one());
 }
@@ -562,7 +710,8 @@ struct jf_plonk_pk {
     unsigned range_bit_len = 0;
     void *d_lk = nullptr, *d_lk_evals = nullptr, *d_hp = nullptr;
     void *d_mt = nullptr, *d_ml = nullptr, *d_sorted = nullptr;  // merged table (n), merged lookup values (n), sorted vector (2n)
-    std::vector<uint64_t> h_mt, h_ml, h_sorted;                  // host copies for the table-order merge
+    uint32_t *d_sv = nullptr;  // scratch of the sorted vector: flag | counts (n) | offsets (n) | block sums | slots (sv_slots)
+    uint32_t sv_slots = 0;     // power of two >= 4 n
     const jf_srs *srs = nullptr;
     unsigned log_n = 0, log_m = 0;
     size_t n = 0, m = 0, np = 0;  // np = n + PAD: stride of the n-sized polynomial buffers
@@ -975,6 +1124,8 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
             JF_TRY(dalloc(ctx, pk, fe * n, &pk->d_mt));
             JF_TRY(dalloc(ctx, pk, fe * n, &pk->d_ml));
             JF_TRY(dalloc(ctx, pk, fe * 2 * n, &pk->d_sorted));
+            pk->sv_slots = (uint32_t)(4 * n);
+            JF_TRY(dalloc(ctx, pk, sizeof(uint32_t) * (16 + 2 * n + (n / (SV_T * SV_I) + 2) + pk->sv_slots), (void **)&pk->d_sv));
         }
         if (pk->cache_coset) JF_TRY(dalloc(ctx, pk, fe * (size_t)(NSEL + NW) * mq, &pk->d_cached));
         JF_CUDA(ctx, cudaMemcpyAsync(pk->d_sel, selector_evals, fe * NSEL * n, cudaMemcpyHostToDevice, st));
@@ -1106,54 +1257,27 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
     // n-element vectors the device just computed -- 2 x 32 n bytes down, 64 n bytes up -- and is the only part of an
     // UltraPlonk proof that is not a device kernel.
     static int sorted_vector(jf_ctx *ctx, jf_plonk_pk *pk) {
-        const size_t n = pk->n, fe = sizeof(E);
-        pk->h_mt.resize(4 * n);
-        pk->h_ml.resize(4 * n);
-        pk->h_sorted.resize(4 * (2 * n));
-        JF_CUDA(ctx, cudaMemcpyAsync(pk->h_mt.data(), pk->d_mt, fe * n, cudaMemcpyDeviceToHost, ctx->stream));
-        JF_CUDA(ctx, cudaMemcpyAsync(pk->h_ml.data(), pk->d_ml, fe * n, cudaMemcpyDeviceToHost, ctx->stream));
-        JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        struct Key {
-            uint64_t l[4];
-            bool operator==(const Key &o) const { return l[0] == o.l[0] && l[1] == o.l[1] && l[2] == o.l[2] && l[3] == o.l[3]; }
-        };
-        struct KeyHash {
-            size_t operator()(const Key &k) const {
-                uint64_t h = k.l[0] * 0x9E3779B97F4A7C15ull ^ (k.l[1] + 0xBF58476D1CE4E5B9ull) * 0x94D049BB133111EBull;
-                h ^= (k.l[2] + (h << 6) + (h >> 2)) * 0xD6E8FEB86659FD93ull ^ k.l[3] * 0xFF51AFD7ED558CCDull;
-                return (size_t)(h ^ (h >> 29));
-            }
-        };
-        std::unordered_map<Key, size_t, KeyHash> counts;
-        counts.reserve(1024);
+        const size_t n = pk->n;
+        cudaStream_t st = ctx->stream;
+        const uint32_t blocks = (uint32_t)((n + SV_T * SV_I - 1) / (SV_T * SV_I)), mask = pk->sv_slots - 1, cap = (uint32_t)(2 * n - 1);
+        uint32_t *flag = pk->d_sv, *cnt = flag + 16, *off = cnt + n, *bsum = off + n, *slots = bsum + blocks + 1;
+        const E *mt = (const E *)pk->d_mt, *ml = (const E *)pk->d_ml;
+        JF_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(uint32_t) * (16 + n), st));
+        JF_CUDA(ctx, cudaMemsetAsync(slots, 0xFF, sizeof(uint32_t) * pk->sv_slots, st));
+        const unsigned g = (unsigned)((n + 255) / 256);
+        JF_LAUNCH(ctx, "sv_insert", sv_insert_kernel<Fr><<<g, 256, 0, st>>>(mt, (uint32_t)n, slots, mask));
         // only the first n - 1 gates look up (the last slot never holds a lookup gate)
-        for (size_t i = 0; i + 1 < n; i++) {
-            Key k;
-            memcpy(k.l, pk->h_ml.data() + 4 * i, 32);
-            counts[k]++;
-        }
-        uint64_t *out = pk->h_sorted.data();
-        size_t len = 0;
-        const size_t cap = 2 * n - 1;
-        for (size_t i = 0; i < n; i++) {
-            Key k;
-            memcpy(k.l, pk->h_mt.data() + 4 * i, 32);
-            size_t reps = 1;
-            auto it = counts.find(k);
-            if (it != counts.end()) {
-                reps += it->second;
-                counts.erase(it);
-            }
-            if (len + reps > cap) {
-                len = cap + 1;
-                break;
-            }
-            for (size_t r = 0; r < reps; r++) memcpy(out + 4 * (len + r), k.l, 32);
-            len += reps;
-        }
-        if (len != cap)
+        JF_LAUNCH(ctx, "sv_count", sv_count_kernel<Fr><<<g, 256, 0, st>>>(mt, ml, (uint32_t)(n - 1), slots, mask, cnt, flag));
+        JF_LAUNCH(ctx, "sv_block", sv_block_kernel<<<blocks, SV_T, 0, st>>>(cnt, (uint32_t)n, bsum));
+        JF_LAUNCH(ctx, "sv_carry", sv_carry_kernel<<<1, 1024, 0, st>>>(bsum, blocks));
+        JF_LAUNCH(ctx, "sv_offsets", sv_offsets_kernel<<<blocks, SV_T, 0, st>>>(cnt, (uint32_t)n, bsum, off));
+        JF_LAUNCH(ctx, "sv_expand", sv_expand_kernel<Fr><<<(cap + 255) / 256, 256, 0, st>>>(mt, off, (uint32_t)n, cap, (E *)pk->d_sorted));
+        void *h;
+        JF_TRY(pinned(ctx, 64, &h));
+        JF_CUDA(ctx, cudaMemcpyAsync(h, flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        JF_CUDA(ctx, cudaStreamSynchronize(st));
+        if (*(const uint32_t *)h)
             return fail(ctx, JF_ERR_INVALID_ARG, "prove: The sorted vector has wrong length, some lookup variables might be outside the table");
-        JF_CUDA(ctx, cudaMemcpyAsync(pk->d_sorted, out, fe * cap, cudaMemcpyHostToDevice, ctx->stream));
         return JF_OK;
     }
 

@@ -207,6 +207,27 @@ def test_msm_large_known_beta_identity(ctx, co, py, log_n):
     key.free()
 
 
+def test_msm_two_half_split_of_large_copied_scalars(ctx, co, py):
+    """jf_msm cuts an MSM of >= 2^21 scalars that must be staged (pageable source) into two halves over consecutive base ranges
+    (api.cu: jf_msm); a one-vector jf_msm_batch never splits.  Both must give the same point, also for an odd length with an
+    offset, and the known-beta identity commit(p) == p(beta) G must hold."""
+    cv = py.BN254
+    n = (1 << 21) + 5
+    beta = py.random_field_elems(cv.fr, 1, seed=123)[0]
+    key = ctx.generate_srs_for_testing("bn254", beta, n)
+    coeffs = co.random_field_elems("bn254_fr", n, 17, True)
+    xy, inf = ctx.msm(key, coeffs, montgomery=True)
+    one, one_inf = ctx.msm_batch(key, [coeffs], montgomery=True)
+    assert not inf and not one_inf[0] and np.array_equal(xy, one[0])
+    ev = co.poly_eval("bn254_fr", coeffs, co.ints_to_limbs([cv.fr.to_mont(beta)], 4)[0])
+    want_pt = co.fixed_base_mul("bn254", co.field_op("bn254_fr", "from_mont", ev[None, :]))[0]
+    assert np.array_equal(xy, want_pt)
+    xy2, inf2 = ctx.msm(key, coeffs[: n - 8], montgomery=True, base_offset=3)
+    one2, one2_inf = ctx.msm_batch(key, [coeffs[: n - 8]], base_offsets=[3], montgomery=True)
+    assert inf2 == one2_inf[0] and np.array_equal(xy2, one2[0])
+    key.free()
+
+
 def test_msm_2_20_random_points_vs_oracle_pippenger(ctx, co):
     """BASELINE config-2 size with random (non-KZG) points: the GPU result against the C restatement of
     ark-ec's Pippenger on all 2^20 + 3 pairs (the known-beta identity above only covers KZG-shaped keys)."""
