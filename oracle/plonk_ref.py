@@ -338,9 +338,54 @@ def ConstantAdditionGate(c): return Gate("const_add", q_lc=(1, 0, 0, 0), q_c=c, 
 def LookupGate(q_dom_sep, table_dom_sep, table_key):
     return Gate("lookup", q_lookup=1, q_dom_sep=q_dom_sep, table_dom_sep=table_dom_sep, table_key=table_key)
 def PaddingGate(): return Gate("pad")  # all selectors zero in this fork (relation/src/gates/mod.rs)
+def ProofLinkingGate(): return Gate("link", q_mul=(1, 0))  # a * 0 = 0 (relation/src/gates/mod.rs:86-99)
+
+
+PROOF_LINK_WIRE_IDX = 0  # relation/src/proof_linking/linkable_circuit.rs:22
+
+
+class GroupLayout:
+    """relation/src/proof_linking/mod.rs:17-53: `size` proof-linking gates on the 2^alignment-th roots of unity, from `offset`."""
+
+    def __init__(self, alignment: int, offset: int, size: int):
+        self.alignment, self.offset, self.size = alignment, offset, size
+
+    def range_in_nth_roots(self, n: int) -> Tuple[int, int]:
+        assert n >= self.alignment, "Group alignment must be <= n"
+        spacing = 1 << (n - self.alignment)
+        start = self.offset * spacing
+        return start, start + max(self.size - 1, 0) * spacing
+
+    def domain_generator(self, field: Field) -> int:
+        return Radix2Domain(field, 1 << self.alignment).group_gen
+
+    def __eq__(self, o): return (self.alignment, self.offset, self.size) == (o.alignment, o.offset, o.size)
+    def __repr__(self): return "GroupLayout(alignment=%d, offset=%d, size=%d)" % (self.alignment, self.offset, self.size)
 
 
 RANGE_WIRE_ID = 5  # relation/src/constraint_system.rs:77-85
+
+
+def _next_pow2(x: int) -> int:
+    n = 1
+    while n < x:
+        n <<= 1
+    return n
+
+
+def _place_group(size: int, n_inputs: int, alignment: int, gid: str, placed: list) -> bool:
+    """place_group_with_alignment (linkable_circuit.rs:251-290): the first gap behind the public inputs that takes the group"""
+    ranges = sorted(l.range_in_nth_roots(alignment) for _, l in placed)
+    offset = n_inputs
+    for idx, (start, end) in enumerate(ranges):
+        if offset + size <= start:
+            placed.insert(idx, (gid, GroupLayout(alignment, offset, size)))
+            return True
+        offset = end + 1
+    if offset + size < (1 << alignment):
+        placed.append((gid, GroupLayout(alignment, offset, size)))
+        return True
+    return False
 
 
 class PlonkCircuit:
@@ -359,8 +404,104 @@ class PlonkCircuit:
         self.num_table_elems = 0
         self.table_gate_ids: List[Tuple[int, int]] = []
         self.n = 1  # eval domain size; 1 == not finalized
+        self.link_groups: dict = {}         # id -> member variables, in allocation order (constraint_system.rs:166)
+        self.link_group_layouts: dict = {}  # id -> GroupLayout, where one is fixed (:172)
         self.enforce_constant(0, 0)
         self.enforce_constant(1, 1)
+
+    # -- proof linking (constraint_system.rs:283-298,514-595; TurboPlonk only) ------------------------------
+    def create_link_group(self, gid: str, layout: Optional["GroupLayout"] = None) -> str:
+        assert not self.ultra, "only TurboPlonk supports link groups"
+        self.link_groups[gid] = []
+        if layout is not None:
+            self.link_group_layouts[gid] = layout
+        return gid
+
+    def create_variable_with_link_groups(self, val: int, groups: Sequence[str]) -> int:
+        assert self.n == 1
+        v = self.create_variable(val)
+        for g in groups:
+            if g not in self.link_groups:
+                raise ValueError("link group %s not found" % g)
+            self.link_groups[g].append(v)
+        return v
+
+    def get_link_group_layout(self, gid: str) -> Optional["GroupLayout"]:
+        return self.link_group_layouts.get(gid)
+
+    def num_links(self) -> int:
+        return sum(len(g) for g in self.link_groups.values())
+
+    def _generate_layout(self):
+        """`LinkableCircuit::generate_layout` (linkable_circuit.rs:136-178) -> (group layouts sorted by range, circuit size).
+        Groups without a layout are placed in creation order (the reference walks a HashMap: any order with one such group)."""
+        placed = [(g, l) for g, l in self.link_group_layouts.items() if g in self.link_groups]
+        unplaced = [g for g in self.link_groups if g not in self.link_group_layouts]
+        n_links = self.num_links()
+        alignment = max([l.alignment for _, l in placed] + [(_next_pow2(n_links)).bit_length() - 1])   # min_alignment (:104-118)
+        placed.sort(key=lambda t: t[1].range_in_nth_roots(alignment))
+        inputs = self.num_inputs()
+        for gid in unplaced:
+            size = len(self.link_groups[gid])
+            while not _place_group(size, inputs, alignment, gid, placed):
+                alignment += 1
+        layouts = dict(placed)
+        # CircuitLayout::circuit_size / circuit_alignment (mod.rs:74-93)
+        max_alignment = max(l.alignment for l in layouts.values()) if layouts else 1
+        link_gates = sum(l.size for l in layouts.values())
+        size = max(_next_pow2(self.num_gates() + link_gates), 1 << max_alignment)
+        log_size = size.bit_length() - 1
+        # validate_layout (linkable_circuit.rs:352-399)
+        for gid, l in layouts.items():
+            if l.size == 0:
+                raise ValueError("Link group %s (layout = %r) is empty" % (gid, l))
+            if l.offset + l.size >= (1 << l.alignment):
+                raise ValueError("Link group %s (layout = %r) exceeds its alignment" % (gid, l))
+            if l.range_in_nth_roots(log_size)[0] < inputs:
+                raise ValueError("Link group %s (layout = %r) would mangle public inputs" % (gid, l))
+        order = sorted(layouts.items(), key=lambda t: t[1].range_in_nth_roots(max_alignment))
+        for (g1, l1), (g2, l2) in zip(order, order[1:]):
+            r1, r2 = l1.range_in_nth_roots(log_size), l2.range_in_nth_roots(log_size)
+            if max(r1[0], r2[0]) <= min(r1[1], r2[1]):
+                raise ValueError("Link group %s (layout = %r) overlaps with group %s (layout = %r)" % (g1, l1, g2, l2))
+        self.link_group_layouts.update(layouts)
+        return order, size
+
+    def _apply_layout(self, order, size):
+        """`LinkableCircuit::apply_layout` (linkable_circuit.rs:184-238): inputs first, the proof-linking gates at their rows with
+        the circuit's own gates in between, padding to `size`."""
+        old_gates = iter(self.gates)
+        old_vars = [iter(w) for w in self.wire_variables[:NUM_WIRE_TYPES]]
+        gates: List[Gate] = []
+        wires: List[List[int]] = [[] for _ in range(NUM_WIRE_TYPES)]
+
+        def place(cnt):   # place_gates (:296-318)
+            for _ in range(cnt):
+                gates.append(next(old_gates, None) or PaddingGate())
+                for j in range(NUM_WIRE_TYPES):
+                    wires[j].append(next(old_vars[j], 0))
+
+        place(self.num_inputs())
+        log_size = size.bit_length() - 1
+        for gid, l in order:
+            start, _ = l.range_in_nth_roots(log_size)
+            if start < len(gates):
+                raise ValueError("link group %s does not fit behind the gates placed before it" % gid)
+            place(start - len(gates))
+            spacing = 1 << (log_size - l.alignment)
+            for var in self.link_groups[gid]:   # append_group (:322-345)
+                gates.append(ProofLinkingGate())
+                for j in range(NUM_WIRE_TYPES):
+                    wires[j].append(var if j == PROOF_LINK_WIRE_IDX else 0)
+                place(spacing - 1)
+        if len(gates) > size:
+            raise ValueError("the circuit's gates do not fit its layout")
+        place(size - len(gates))
+        if next(old_gates, None) is not None:
+            raise ValueError("the circuit's gates do not fit its layout")
+        self.gates = gates
+        for j in range(NUM_WIRE_TYPES):
+            self.wire_variables[j] = wires[j]
 
     # -- UltraPlonk construction -----------------------------------------------------------------------
     def range_size(self) -> int:
@@ -434,6 +575,28 @@ class PlonkCircuit:
         self.mul_gate(a, b, c)
         return c
 
+    def lc_gate(self, wires: Sequence[int], coeffs: Sequence[int]):
+        """LinCombGate (relation/src/traits.rs:258-276): q_lc = coeffs, q_o = 1"""
+        self.insert_gate(list(wires), Gate("lc", q_lc=tuple(c % self.f.p for c in coeffs), q_o=1))
+
+    def lc(self, wires_in: Sequence[int], coeffs: Sequence[int]) -> int:
+        y = self.create_variable(sum(self.witness[v] * c for v, c in zip(wires_in, coeffs)))
+        self.lc_gate(list(wires_in) + [y], coeffs)
+        return y
+
+    def sum(self, elems: Sequence[int]) -> int:
+        """relation/src/traits.rs:369-408: z_0 = x_0, z_i = z_{i-1} + x_{3i-2} + x_{3i-1} + x_{3i}, the last step lands on `sum`"""
+        assert elems
+        total = self.create_variable(sum(self.witness[v] for v in elems))
+        rate = GATE_WIDTH - 1
+        padded_len = -(-(len(elems) - 1) // rate) * rate + 1
+        padded = list(elems) + [0] * (padded_len - len(elems))
+        accum = padded[0]
+        for i in range(1, padded_len // rate):
+            accum = self.lc([accum, padded[rate * i - 2], padded[rate * i - 1], padded[rate * i]], [1, 1, 1, 1])
+        self.lc_gate([accum, padded[padded_len - 3], padded[padded_len - 2], padded[padded_len - 1], total], [1, 1, 1, 1])
+        return total
+
     def public_input(self) -> List[int]:
         return [self.witness[self.wire_variables[GATE_WIDTH][g]] for g in self.pub_input_gate_ids]
 
@@ -441,8 +604,10 @@ class PlonkCircuit:
     def finalize_for_arithmetization(self):
         if self.n != 1:
             return
+        order = []
         if not self.ultra:
-            n_gates = self.num_gates()  # CircuitLayout::circuit_size: next_power_of_two(n_gates)
+            # generate_layout + apply_layout (constraint_system.rs:972-980); without link groups: next_power_of_two(n_gates)
+            order, n_gates = self._generate_layout()
         else:  # range gates and lookup gates need separate slots (constraint_system.rs:981-987)
             n_gates = max(self.num_gates(),
                           max(self.range_size(), len(self.wire_variables[RANGE_WIRE_ID])) + self.num_table_elems + 1)
@@ -476,11 +641,8 @@ class PlonkCircuit:
                             w[gate_id], w[cur] = w[cur], w[gate_id]
                         cur -= 1
         else:
-            # pad with PaddingGate / variable 0 (linkable_circuit.rs:294-314)
-            while len(self.gates) < n:
-                self.gates.append(PaddingGate())
-                for j in range(NUM_WIRE_TYPES):
-                    self.wire_variables[j].append(0)
+            # proof-linking gates at their rows; pad with PaddingGate / variable 0 (linkable_circuit.rs:184-238,294-314)
+            self._apply_layout(order, n)
         self.n = n
         self.domain = Radix2Domain(self.f, n)
         self._compute_wire_permutation()
@@ -870,6 +1032,159 @@ def prove(curve: Curve, cs: PlonkCircuit, pk: dict, blinders: Sequence[int], tra
         "plookup_proof": bp["plookup_proofs_vec"][0], "challenges": bp["challenges"]}
 
 
+def prove_with_link_hint(curve: Curve, cs: PlonkCircuit, pk: dict, blinders: Sequence[int], transcript: str = "solidity"):
+    """`PlonkKzgSnark::prove_with_link_hint` (snark.rs:81-114) -> (proof, LinkingHint): the hint is the first wire polynomial
+    (after masking) and its commitment (structs.rs:88-97)."""
+    bp = batch_prove(curve, [cs], [pk], blinders, transcript, None)
+    proof = {
+        "wires_poly_comms": bp["wires_poly_comms_vec"][0], "prod_perm_poly_comm": bp["prod_perm_poly_comms_vec"][0],
+        "split_quot_poly_comms": bp["split_quot_poly_comms"], "opening_proof": bp["opening_proof"],
+        "shifted_opening_proof": bp["shifted_opening_proof"], "wires_evals": bp["poly_evals_vec"][0]["wires_evals"],
+        "wire_sigma_evals": bp["poly_evals_vec"][0]["wire_sigma_evals"], "perm_next_eval": bp["poly_evals_vec"][0]["perm_next_eval"],
+        "plookup_proof": bp["plookup_proofs_vec"][0], "challenges": bp["challenges"]}
+    hint = {"linking_wire_poly": list(bp["wire_polys_vec"][0][PROOF_LINK_WIRE_IDX]),
+            "linking_wire_comm": bp["wires_poly_comms_vec"][0][PROOF_LINK_WIRE_IDX]}
+    return proof, hint
+
+
+# ======================================================================================
+# Proof linking (plonk/src/proof_system/proof_linking.rs)
+# ======================================================================================
+def _link_roots(fr: Field, layout: GroupLayout) -> List[int]:
+    """the roots of the linking domain's vanishing polynomial: g^offset .. g^(offset + size - 1), g the 2^alignment-th root of
+    unity (proof_linking.rs:137-160)"""
+    g = layout.domain_generator(fr)
+    r = pow(g, layout.offset, fr.p)
+    out = []
+    for _ in range(layout.size):
+        out.append(r)
+        r = r * g % fr.p
+    return out
+
+
+def _poly_sub(p: int, a: Sequence[int], b: Sequence[int]) -> List[int]:
+    return _poly_add(p, a, [(-x) % p for x in b])
+
+
+def linking_quotient(fr: Field, a1: Sequence[int], a2: Sequence[int], layout: GroupLayout) -> List[int]:
+    """compute_linking_quotient (proof_linking.rs:116-135): (a1 - a2) / Z_D, remainder dropped.  ark-poly's `/` is schoolbook long
+    division; dividing by the linear factors of Z_D one after the other yields the same quotient (the remainders of the steps
+    combine to one of degree < size)."""
+    p = fr.p
+    if _strip(a1) == _strip(a2):
+        return []
+    q = _poly_sub(p, a1, a2)
+    for r in _link_roots(fr, layout):
+        q = _div_linear(p, q, r)
+    return q
+
+
+def linking_quotient_schoolbook(fr: Field, a1: Sequence[int], a2: Sequence[int], layout: GroupLayout) -> List[int]:
+    """the literal form (test only): build Z_D by multiplying its monomials (:137-160), then long division"""
+    p = fr.p
+    z = [1]
+    for r in _link_roots(fr, layout):
+        nz = [0] * (len(z) + 1)
+        for i, c in enumerate(z):
+            nz[i] = (nz[i] - c * r) % p
+            nz[i + 1] = (nz[i + 1] + c) % p
+        z = nz
+    rem = _poly_sub(p, a1, a2)
+    if len(rem) < len(z):
+        return []
+    q = [0] * (len(rem) - len(z) + 1)
+    for k in range(len(q) - 1, -1, -1):   # Z_D is monic
+        c = rem[k + len(z) - 1]
+        q[k] = c
+        if c:
+            for i, zc in enumerate(z):
+                rem[k + i] = (rem[k + i] - c * zc) % p
+    return _strip(q)
+
+
+def _link_challenge(curve: Curve, a1_comm, a2_comm, q_comm, transcript: str) -> int:
+    """compute_quotient_challenge (:171-191): a fresh transcript over the two wire commitments and the quotient commitment"""
+    tr = TRANSCRIPTS[transcript](b"PlonkLinkingProof")
+    for c in (a1_comm, a2_comm):
+        tr.append_message(b"linking_wire_comms", ser_g1(curve, c))
+    tr.append_message(b"quotient_comm", ser_g1(curve, q_comm))
+    return tr.get_and_append_challenge(curve.fr, b"eta")
+
+
+def _link_vanishing_eval(fr: Field, eta: int, layout: GroupLayout) -> int:
+    ev = 1
+    for r in _link_roots(fr, layout):   # compute_vanishing_poly_eval (:162-177)
+        ev = ev * (eta - r) % fr.p
+    return ev
+
+
+def link_proofs(curve: Curve, lhs_hint: dict, rhs_hint: dict, layout: GroupLayout, srs, transcript: str = "solidity") -> dict:
+    """`PlonkKzgSnark::link_proofs` (proof_linking.rs:79-112) -> LinkingProof {quotient_commitment, opening_proof}.
+    srs: (limb array | None, python points | None) as returned by gen_srs."""
+    fr, p = curve.fr, curve.fr.p
+    be = _Backend(curve)
+    srs_limbs, srs_points = srs
+    a1, a2 = lhs_hint["linking_wire_poly"], rhs_hint["linking_wire_poly"]
+    quotient = linking_quotient(fr, a1, a2, layout)
+    q_comm = be.commit(srs_limbs, srs_points, quotient)
+    eta = _link_challenge(curve, lhs_hint["linking_wire_comm"], rhs_hint["linking_wire_comm"], q_comm, transcript)
+    # compute_identity_opening (:193-216): a1 - a2 - q * Z_D(eta), opened at eta (`UnivariateKzgPCS::open`, mod.rs:135-161)
+    zd = _link_vanishing_eval(fr, eta, layout)
+    identity = _poly_sub(p, _poly_sub(p, a1, a2), _poly_scale(p, quotient, zd))
+    opening = be.commit(srs_limbs, srs_points, _div_linear(p, identity, eta))
+    return {"quotient_commitment": q_comm, "opening_proof": opening, "eta": eta}
+
+
+def verify_link_proof(curve: Curve, proof1: dict, proof2: dict, link_proof: dict, layout: GroupLayout, beta_srs: int,
+                      transcript: str = "solidity") -> bool:
+    """`verify_link_proof` (proof_linking.rs:233-283); `UnivariateKzgPCS::verify` (mod.rs:218-243) e(C - v g, h) == e(pi, [beta - z] h)
+    is evaluated in G1 with the known trapdoor: C - v g == (beta - z) pi, here with v = 0, z = eta."""
+    fr, p = curve.fr, curve.fr.p
+    a1c, a2c = proof1["wires_poly_comms"][PROOF_LINK_WIRE_IDX], proof2["wires_poly_comms"][PROOF_LINK_WIRE_IDX]
+    qc = link_proof["quotient_commitment"]
+    eta = _link_challenge(curve, a1c, a2c, qc, transcript)
+    zd = _link_vanishing_eval(fr, eta, layout)
+    # compute_identity_commitment (:285-299)
+    ident = curve.add(curve.add(a1c, curve.neg(a2c)), curve.neg(curve.mul(zd, qc)))
+    return ident == curve.mul((beta_srs - eta) % p, link_proof["opening_proof"])
+
+
+def serialize_link_proof(curve: Curve, lp: dict) -> bytes:
+    """`LinkingProof<E>` CanonicalSerialize, compressed (proof_linking.rs:32-39): the quotient commitment, then the opening proof"""
+    return ser_g1(curve, lp["quotient_commitment"]) + ser_g1(curve, lp["opening_proof"])
+
+
+LINK_GROUP_NAME = "test_group"  # proof_linking.rs:310
+
+
+def gen_link_test_circuit(which: int, witness: Sequence[int], layout: Optional[GroupLayout], field: Field = pyref.BN254_FR) -> PlonkCircuit:
+    """`gen_test_circuit1` (a sum) / `gen_test_circuit2` (a product) of proof_linking.rs:330-407, finalized."""
+    cs = PlonkCircuit(field)
+    p = field.p
+    if which == 1:
+        expected = cs.create_public_variable(sum(witness) % p)
+    else:
+        prod = 1
+        for w in witness:
+            prod = prod * w % p
+        expected = cs.create_public_variable(prod)
+    for w in witness:               # a few public inputs, for spacing
+        cs.create_public_variable(w)
+    group = cs.create_link_group(LINK_GROUP_NAME, layout)
+    wvars = [cs.create_variable_with_link_groups(w, [group]) for w in witness]
+    for w in witness:               # a few witnesses that are not linked
+        cs.create_variable(w * w)
+    if which == 1:
+        cs.enforce_equal(cs.sum(wvars), expected)
+    else:
+        prod = cs.one()
+        for v in wvars:
+            prod = cs.mul(prod, v)
+        cs.enforce_equal(prod, expected)
+    cs.finalize_for_arithmetization()
+    return cs
+
+
 def batch_num_blinders(circuits) -> int:
     nw, ultra = circuits[0].nw, circuits[0].ultra
     return len(circuits) * (2 * nw + 3 + (9 if ultra else 0)) + (nw - 1)
@@ -1165,6 +1480,7 @@ def batch_prove(curve: Curve, circuits: Sequence[PlonkCircuit], pks: Sequence[di
                                 if ultra else None) for st in I],
         "split_quot_poly_comms": split_comms, "opening_proof": opening, "shifted_opening_proof": shifted,
         "challenges": {"tau": tau, "beta": beta, "gamma": gamma, "alpha": alpha, "zeta": zeta, "v": v},
+        "wire_polys_vec": [st["wire_polys"] for st in I],   # `Oracles::wire_polys` (snark.rs:466-468): not part of the proof
     }
 
 
