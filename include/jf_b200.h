@@ -318,6 +318,41 @@ int jf_ultraplonk_batch_prove(jf_ctx *ctx, jf_plonk_pk *const *pks, size_t count
 long jf_plonk_batch_proof_serialize(const jf_plonk_proof *proofs, size_t count, uint8_t *out, size_t cap);
 long jf_ultraplonk_batch_proof_serialize(const jf_ultraplonk_proof *proofs, size_t count, uint8_t *out, size_t cap);
 
+/* ---- proof linking ------------------------------------------------------------------------------------------------------------
+ * `PlonkKzgSnark::link_proofs` (plonk/src/proof_system/proof_linking.rs:79-216): two TurboPlonk proofs whose circuits placed the
+ * same link group (`GroupLayout { alignment, offset, size }`, relation/src/proof_linking/mod.rs:17-53) carry the group's values in
+ * their first wire polynomial at the points g^(offset + i), g the 2^alignment-th root of unity.  The linking proof is the commitment
+ * of q = (a1 - a2) / Z_D (Z_D the vanishing polynomial of those points; remainder dropped like ark-poly's `/`) and a KZG opening
+ * (`UnivariateKzgPCS::open`, mod.rs:135-161) of a1 - a2 - q Z_D(eta) at the challenge eta squeezed from a fresh transcript over
+ * (a1's commitment, a2's commitment, q's commitment).  On the device: a1 - a2 is evaluated on the 2^alignment-th roots of unity; when
+ * it vanishes on the link domain the quotient is a pointwise ratio on a coset (three transforms, independent of `size`), otherwise
+ * -- the two proofs are NOT linked and the verifier will reject -- the same floor quotient is obtained from `size` divisions by a
+ * linear factor.  flags & 1 forces the second form.  The circuit-side layout (`LinkableCircuit`) stays with the caller. */
+typedef struct {
+    int curve;
+    uint64_t quotient_commitment[12];  /* `LinkingProof::quotient_commitment` (proof_linking.rs:32-39) */
+    int quotient_inf;
+    uint64_t opening_proof[12];        /* `LinkingProof::opening_proof` */
+    int opening_inf;
+    uint64_t eta[4];                   /* the opening challenge (Montgomery): diagnostics */
+    int path;                          /* 0: exact division on a coset, 1: successive linear divisions: diagnostics */
+} jf_link_proof;
+/* `LinkingHint::linking_wire_poly` (structs.rs:88-97; snark.rs:96-100) of the LAST proof made with `pk`: the first wire polynomial
+ * after masking, n + 2 Montgomery coefficients (cap >= n + 2 elements).  The hint's commitment is wires_poly_comms[0] of that proof. */
+int jf_plonk_link_hint(jf_ctx *ctx, const jf_plonk_pk *pk, uint64_t *out_poly, size_t cap, size_t *out_len);
+/* == `link_proofs(lhs_link_hint, rhs_link_hint, group_layout, commit_key)` with the hints in host memory: a1 / a2 Montgomery
+ * coefficients (low degree first), their commitments as affine x || y (+ infinity flag).  transcript_kind as jf_plonk_prove. */
+int jf_plonk_link_proofs(jf_ctx *ctx, const jf_srs *srs, const uint64_t *a1, size_t len1, const uint64_t *a1_comm_xy, int a1_inf,
+                         const uint64_t *a2, size_t len2, const uint64_t *a2_comm_xy, int a2_inf, unsigned alignment, size_t offset,
+                         size_t size, int transcript_kind, int flags, jf_link_proof *out);
+/* The same with both wire polynomials still in HBM: the workspaces of the two proving keys hold them after jf_plonk_prove
+ * (the keys must share one commit key; no polynomial crosses PCIe). */
+int jf_plonk_link_proofs_resident(jf_ctx *ctx, const jf_plonk_pk *lhs, const jf_plonk_proof *lhs_proof, const jf_plonk_pk *rhs,
+                                  const jf_plonk_proof *rhs_proof, unsigned alignment, size_t offset, size_t size, int transcript_kind,
+                                  int flags, jf_link_proof *out);
+/* ark-serialize `serialize_compressed` of `LinkingProof<E>`: 64 bytes (BN254) / 96 (BLS12-381); returns the count or < 0 */
+long jf_link_proof_serialize(const jf_link_proof *proof, uint8_t *out, size_t cap);
+
 /* Host-only pieces of the transcripts (no GPU needed): sha3 `Keccak256`, and `PlonkTranscript`
  * new / append_message / get_and_append_challenge (plonk/src/transcript/{solidity,standard}.rs). */
 void jf_keccak256(const uint8_t *data, size_t len, uint8_t out[32]);

@@ -12,14 +12,15 @@ from .errors import (DomainCreationError, InvalidParameters, PCSError, PlonkErro
                      WrongQuotientPolyDegree)
 from .multiprover import (AuthenticatedDensePoly, AuthenticatedPointShare, MultiproverKZG, fft_with_domain,
                           ifft_with_domain)
-from .plonk import BatchProof, PlonkKzgSnark, Proof, ProvingKey, Transcript, keccak256
+from .plonk import (BatchProof, GroupLayout, LinkingHint, LinkingProof, PlonkKzgSnark, Proof, ProvingKey, Transcript,
+                    keccak256)
 from .sharded import Comm, Group, GroupKey, ShardedMsm, combine_partials, poly_owner, shard_range
 from .pcs import Commitment, DensePolynomial, UnivariateKzgPCS, UnivariateProverParam
 
 __all__ = [
     "Context", "CommitKey", "Radix2EvaluationDomain", "UnivariateKzgPCS", "UnivariateProverParam",
     "DensePolynomial", "Commitment", "PCSError", "InvalidParameters", "UpstreamError", "PlonkError",
-    "DomainCreationError", "WrongQuotientPolyDegree", "PlonkKzgSnark", "Proof", "BatchProof", "ProvingKey", "Transcript", "keccak256",
+    "DomainCreationError", "WrongQuotientPolyDegree", "PlonkKzgSnark", "Proof", "BatchProof", "GroupLayout", "LinkingHint", "LinkingProof", "ProvingKey", "Transcript", "keccak256",
     "MultiproverKZG", "AuthenticatedDensePoly", "AuthenticatedPointShare", "fft_with_domain", "ifft_with_domain",
     "ShardedMsm", "Comm", "Group", "GroupKey", "combine_partials", "poly_owner", "shard_range",
 ]

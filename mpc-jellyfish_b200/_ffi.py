@@ -68,6 +68,16 @@ class UltraPlonkProofStruct(ctypes.Structure):
     ]
 
 
+class LinkProofStruct(ctypes.Structure):
+    """`jf_link_proof` of include/jf_b200.h."""
+    _fields_ = [
+        ("curve", ctypes.c_int),
+        ("quotient_commitment", ctypes.c_uint64 * 12), ("quotient_inf", ctypes.c_int),
+        ("opening_proof", ctypes.c_uint64 * 12), ("opening_inf", ctypes.c_int),
+        ("eta", ctypes.c_uint64 * 4), ("path", ctypes.c_int),
+    ]
+
+
 # name -> (restype, argtypes); must list every function of include/jf_b200.h
 SIGNATURES = {
     "jf_ctx_create": (ctypes.c_int, [ctypes.c_int, c_void_pp]),
@@ -154,6 +164,14 @@ SIGNATURES = {
     "jf_plonk_prove": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64p, c_u64p, ctypes.c_int, ctypes.c_char_p,
                                       ctypes.c_size_t, ctypes.POINTER(PlonkProofStruct)]),
     "jf_plonk_proof_serialize": (ctypes.c_long, [ctypes.POINTER(PlonkProofStruct), ctypes.c_char_p, ctypes.c_size_t]),
+    "jf_plonk_link_hint": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+    "jf_plonk_link_proofs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64p, ctypes.c_size_t, c_u64p, ctypes.c_int, c_u64p,
+                                            ctypes.c_size_t, c_u64p, ctypes.c_int, ctypes.c_uint, ctypes.c_size_t, ctypes.c_size_t,
+                                            ctypes.c_int, ctypes.c_int, ctypes.POINTER(LinkProofStruct)]),
+    "jf_plonk_link_proofs_resident": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(PlonkProofStruct), ctypes.c_void_p,
+                                                     ctypes.POINTER(PlonkProofStruct), ctypes.c_uint, ctypes.c_size_t, ctypes.c_size_t,
+                                                     ctypes.c_int, ctypes.c_int, ctypes.POINTER(LinkProofStruct)]),
+    "jf_link_proof_serialize": (ctypes.c_long, [ctypes.POINTER(LinkProofStruct), ctypes.c_char_p, ctypes.c_size_t]),
     "jf_keccak256": (None, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]),
     "jf_transcript_new": (ctypes.c_void_p, [ctypes.c_int, ctypes.c_char_p]),
     "jf_transcript_free": (None, [ctypes.c_void_p]),

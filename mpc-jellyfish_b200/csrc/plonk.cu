@@ -695,6 +695,33 @@ __global__ void mulpow_kernel(const Fp<F> *in, Fp<F> *out, size_t len, uint32_t 
     }
 }
 
+// ---- proof linking (plonk/src/proof_system/proof_linking.rs) ---------------------------------------------
+// out[j] = sum_k in[j + k N] c^k, j < N: `in` (len coefficients) reduced mod X^N - c
+template <class F> __global__ void fold_kernel(const Fp<F> *in, size_t len, size_t N, Fp<F> c, Fp<F> *out) {
+    using E = Fp<F>;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    E acc = E::zero();
+    for (size_t k = (len + N - 1) / N; k-- > 0;) {
+        const size_t idx = j + k * N;
+        acc = E::mul(acc, c);
+        if (idx < len) acc = E::add(acc, ldf(in + idx));
+    }
+    stf(out + j, acc);
+}
+// vals: a polynomial's values on the N-th roots of unity (natural order).  *flag = 1 unless it vanishes on the linking domain
+// {g^(offset + i), i < size}, g the 2^alignment-th root of unity = w_N^stride.
+template <class F>
+__global__ void link_roots_check_kernel(const Fp<F> *vals, uint32_t stride, uint32_t mask, uint32_t offset, uint32_t size, int *flag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= size) return;
+    if (!ldf(vals + (size_t)((offset + i) & mask) * stride).is_zero()) *flag = 1;
+}
+template <class F> __global__ void vmul_kernel(const Fp<F> *a, const Fp<F> *b, Fp<F> *out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) stf(out + i, Fp<F>::mul(ldf(a + i), ldf(b + i)));
+}
+
 }  // namespace jf
 
 // ================================================================================================
@@ -722,6 +749,7 @@ struct jf_plonk_pk {
     size_t num_vars = 0;
     uint32_t num_inputs = 0;
     int cache_coset = 0;
+    int proofs_done = 0;    // batch_prove calls that left their wire polynomials in d_w (jf_plonk_link_hint, proof linking)
     uint32_t zero_sel = 0;  // selectors that are identically zero (flags & 2)
     int skip_zero = 0;      // flags & 2: zero polynomials (such selectors; PI without public inputs) are not transformed
     std::vector<uint32_t> pub_vars;  // variable index of every public input, in io-gate order
@@ -1773,6 +1801,7 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
                 H::fr_to_limbs(v, out->challenges + 16);
             }
             out->curve = pk0->curve;
+            I[i].pk->proofs_done++;
         }
         return JF_OK;
     }
@@ -1844,6 +1873,214 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
         for (size_t i = 0; i < batch; i++)
             JF_TRY(msm_finish_host(ctx, srs->curve, (const uint64_t *)((const char *)h + PT * i), 1, out_xy + (size_t)2 * L * i, out_inf + i));
         memcpy(out_evals, (const char *)h + PT * batch, fe * batch);
+        return JF_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // `PlonkKzgSnark::link_proofs` (plonk/src/proof_system/proof_linking.rs:79-216): quotient (a1 - a2) / Z_D over the linking
+    // domain D = {g^(offset + i), i < size} (g the 2^alignment-th root of unity), its commitment, the challenge eta from a fresh
+    // transcript, and the KZG opening at eta of a1 - a2 - q Z_D(eta).  d_a1 / d_a2: the two first-wire polynomials in HBM.
+    //
+    // The reference builds Z_D by `size` polynomial multiplications and divides by schoolbook long division.  Here:
+    //  * a1 - a2 is evaluated on the 2^alignment-th roots of unity (one fold mod X^N - 1, one size-N transform).  When it
+    //    vanishes on D (every honestly linked pair of proofs) the division is exact, and the quotient is the pointwise ratio on the
+    //    coset GENERATOR <w_N> -- three size-N transforms and one batch inversion, whatever `size` is; Z_D's coefficients follow from
+    //    the q-binomial theorem in O(size) host multiplications (its roots are consecutive powers of g).
+    //  * otherwise (the pair is NOT linked: the proof will be rejected, but the reference still produces bytes) ark-poly's `/`
+    //    drops a non-zero remainder; dividing by the `size` linear factors one after the other (scan division each) yields that
+    //    same floor quotient.  flags & 1 forces this form; the tests compare the two.
+    static E root_of_unity(unsigned log) {
+        uint32_t e[8];
+        Limbs<Fr>::p(e);
+        e[0] -= 1;
+        for (int s = 0; s < Fr::TWO_ADICITY; s++)
+            for (int i = 0; i < 8; i++) e[i] = (e[i] >> 1) | (i < 7 ? e[i + 1] << 31 : 0);
+        E w = E::pow(E::from_u32(Fr::GENERATOR), e, 8);
+        for (unsigned s = 0; s < Fr::TWO_ADICITY - log; s++) w = E::sqr(w);
+        return w;
+    }
+    // coefficients (low degree first, size + 1 of them) of Z_D = prod_{i < size} (X - g^(offset + i)):
+    // prod_{i<s} (y - g^i) = sum_k (-1)^k g^(k(k-1)/2) [s; k]_g y^(s-k)  with  [s; k]_g = [s; k-1]_g (1 - g^(s-k+1)) / (1 - g^k),
+    // and Z_D(X) = g^(offset s) P(X / g^offset).  1 - g^k != 0 because size < 2^alignment.
+    static std::vector<E> vanishing_coeffs(const E &g, size_t offset, size_t size) {
+        const size_t s = size;
+        std::vector<E> gp(s + 1), den(s + 1), pre(s + 1);
+        gp[0] = E::one();
+        for (size_t k = 1; k <= s; k++) gp[k] = E::mul(gp[k - 1], g);
+        E run = E::one();
+        for (size_t k = 1; k <= s; k++) {  // batch inversion of 1 - g^k
+            den[k] = E::sub(E::one(), gp[k]);
+            pre[k] = run;
+            run = E::mul(run, den[k]);
+        }
+        E inv = E::inv(run);
+        std::vector<E> dinv(s + 1);
+        for (size_t k = s; k >= 1; k--) {
+            dinv[k] = E::mul(inv, pre[k]);
+            inv = E::mul(inv, den[k]);
+        }
+        std::vector<E> z(s + 1);
+        E binom = E::one(), e = E::one();            // [s; k]_g and g^(k(k-1)/2 + offset k)
+        E step = pow_small(g, (uint64_t)offset);     // g^(offset + k)
+        z[s] = E::one();
+        for (size_t k = 1; k <= s; k++) {
+            binom = E::mul(E::mul(binom, den[s - k + 1]), dinv[k]);
+            e = E::mul(e, step);
+            step = E::mul(step, g);
+            const E c = E::mul(binom, e);
+            z[s - k] = (k & 1) ? E::neg(c) : c;
+        }
+        return z;
+    }
+
+    struct LinkOut {
+        uint64_t q_xy[12], open_xy[12], eta[4];
+        int q_inf, open_inf, path;
+    };
+    static int link_proofs(jf_ctx *ctx, const jf_srs *srs, const E *d_a1, size_t len1, const uint64_t *a1_comm, int a1_inf,
+                           const E *d_a2, size_t len2, const uint64_t *a2_comm, int a2_inf, unsigned alignment, size_t offset,
+                           size_t size, int kind, int flags, LinkOut *out) {
+        if (alignment > (unsigned)Fr::TWO_ADICITY || alignment > 30)
+            return fail(ctx, JF_ERR_DOMAIN_TOO_LARGE, "link_proofs: the group alignment exceeds the field's two-adicity");
+        if (size == 0 || offset + size >= ((size_t)1 << alignment))  // validate_layout (linkable_circuit.rs:352-370)
+            return fail(ctx, JF_ERR_INVALID_ARG, "link_proofs: the link group is empty or exceeds its alignment");
+        const size_t max_len = std::max(len1, len2);
+        if (max_len > srs->n + 1) return fail(ctx, JF_ERR_INVALID_ARG, "link_proofs: polynomial degree exceeds the commit key");
+        const size_t fe = sizeof(E);
+        cudaStream_t st = ctx->stream;
+        const E g = root_of_unity(alignment);
+        const E r0 = pow_small(g, (uint64_t)offset);
+        memset(out, 0, sizeof *out);
+        const size_t qlen = max_len > size ? max_len - size : 0;
+        unsigned log_N = alignment;
+        while (((size_t)1 << log_N) < std::max(qlen, size + 1)) log_N++;
+        const size_t N = (size_t)1 << log_N;
+        bool fast = !(flags & 1) && qlen > 0 && log_N <= (unsigned)Fr::TWO_ADICITY && log_N <= 27;
+        const size_t cap = std::max(max_len, fast ? N : (size_t)0) + 8;
+        void *p_diff, *p_a, *p_b, *p_t, *p_s, *p_tmp, *p_res, *p_flag;
+        JF_TRY(scratch(ctx, "link_diff", fe * cap, &p_diff));
+        JF_TRY(scratch(ctx, "link_a", fe * cap, &p_a));
+        JF_TRY(scratch(ctx, "link_b", fe * cap, &p_b));
+        JF_TRY(scratch(ctx, "link_t", fe * cap, &p_t));
+        JF_TRY(scratch(ctx, "link_s", fe * cap, &p_s));
+        JF_TRY(scratch(ctx, "link_tmp", fe * (cap / 256 + 4096), &p_tmp));
+        JF_TRY(scratch(ctx, "link_res", 2 * PT + fe, &p_res));
+        JF_TRY(scratch(ctx, "link_flag", 64, &p_flag));
+        E *diff = (E *)p_diff, *A = (E *)p_a, *B = (E *)p_b, *T = (E *)p_t, *S = (E *)p_s, *tmp = (E *)p_tmp;
+        E *small = (E *)((char *)p_res + 2 * PT);
+        int *d_flag = (int *)p_flag;
+        // a1 - a2
+        if (max_len) {
+            std::vector<Term> terms = {{d_a1, len1, E::one()}, {d_a2, len2, E::neg(E::one())}};
+            JF_TRY(lincomb_many(ctx, terms, diff, max_len));
+        }
+        const E gen = E::from_u32(Fr::GENERATOR);
+        uint64_t gen_limbs[4];
+        H::fr_to_limbs(gen, gen_limbs);
+        if (fast) {  // does a1 - a2 vanish on the linking domain?
+            JF_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+            JF_LAUNCH(ctx, "fold", fold_kernel<Fr><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(diff, max_len, N, E::one(), A));
+            JF_TRY(ntt_run(ctx, C::FR_ID, A, A, N, log_N, 0, nullptr, 1, N));
+            JF_LAUNCH(ctx, "link_roots_check", link_roots_check_kernel<Fr><<<(unsigned)((size + 255) / 256), 256, 0, st>>>(
+                A, (uint32_t)(N >> alignment), (uint32_t)(((size_t)1 << alignment) - 1), (uint32_t)offset, (uint32_t)size, d_flag));
+            int flag = 0;
+            JF_CUDA(ctx, cudaMemcpyAsync(&flag, d_flag, sizeof flag, cudaMemcpyDeviceToHost, st));
+            JF_CUDA(ctx, cudaStreamSynchronize(st));
+            fast = flag == 0;
+        }
+        E *Q = A;  // quotient coefficients
+        size_t q_len = qlen;
+        if (fast) {
+            out->path = 0;
+            const std::vector<E> z = vanishing_coeffs(g, offset, size);
+            JF_LAUNCH(ctx, "fold", fold_kernel<Fr><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(diff, max_len, N, pow_small(gen, (uint64_t)N), A));
+            JF_TRY(ntt_run(ctx, C::FR_ID, A, A, N, log_N, 0, gen_limbs, 1, N));
+            void *hz;
+            JF_TRY(pinned(ctx, fe * (size + 1), &hz));
+            memcpy(hz, z.data(), fe * (size + 1));
+            JF_CUDA(ctx, cudaMemcpyAsync(B, hz, fe * (size + 1), cudaMemcpyHostToDevice, st));
+            JF_TRY(ntt_run(ctx, C::FR_ID, B, B, size + 1, log_N, 0, gen_limbs, 1, N));
+            JF_TRY((fscan<Fr, OpMul, false>(ctx, B, T, N, tmp)));
+            JF_TRY((fscan<Fr, OpMul, true>(ctx, B, S, N, tmp)));
+            JF_LAUNCH(ctx, "inv_one", inv_one_kernel<Fr><<<1, 32, 0, st>>>(S, small));
+            JF_LAUNCH(ctx, "inv_combine", inv_combine_kernel<Fr><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(T, S, small, B, N));
+            JF_LAUNCH(ctx, "vmul", vmul_kernel<Fr><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(A, B, A, N));
+            JF_TRY(ntt_run(ctx, C::FR_ID, A, A, N, log_N, 1, gen_limbs, 1, N));
+        } else {
+            out->path = 1;
+            // floor((a1 - a2) / Z_D) as `size` divisions by a linear factor
+            const E *cur = diff;
+            size_t len = max_len;
+            E r = r0, rinv = E::inv(r0);
+            const E ginv = E::inv(g);
+            E *bufs[2] = {A, B};
+            int which = 0;
+            for (size_t i = 0; i < size && len; i++) {
+                if (len < 2) {
+                    len = 0;
+                    break;
+                }
+                E *nxt = bufs[which];
+                const unsigned b1 = (unsigned)((len + 256 * MP_I - 1) / (256 * MP_I));
+                JF_LAUNCH(ctx, "mulpow", mulpow_kernel<Fr><<<b1, 256, 0, st>>>(cur, T, len, 0, 0, r));
+                JF_TRY((fscan<Fr, OpAdd, true>(ctx, T, S, len, tmp)));
+                JF_LAUNCH(ctx, "mulpow", mulpow_kernel<Fr><<<b1, 256, 0, st>>>(S, nxt, len - 1, 1, 1, rinv));
+                cur = nxt;
+                which ^= 1;
+                len--;
+                r = E::mul(r, g);
+                rinv = E::mul(rinv, ginv);
+            }
+            q_len = len;
+            Q = const_cast<E *>(cur);
+            if (q_len == 0) Q = A;
+        }
+        // quotient commitment (`UnivariateKzgPCS::commit`, mod.rs:90-116)
+        JF_TRY(msm_run(ctx, srs, 0, Q, q_len, 1, p_res));
+        void *h;
+        JF_TRY(pinned(ctx, 2 * PT + 64, &h));
+        JF_CUDA(ctx, cudaMemcpyAsync(h, p_res, PT, cudaMemcpyDeviceToHost, st));
+        int herr = 0;
+        JF_CUDA(ctx, cudaMemcpyAsync(&herr, ctx->d_err, sizeof herr, cudaMemcpyDeviceToHost, st));
+        JF_CUDA(ctx, cudaStreamSynchronize(st));
+        if (herr) {
+            cudaMemsetAsync(ctx->d_err, 0, sizeof herr, st);
+            return fail(ctx, herr, "link_proofs: a coefficient is not a reduced field element");
+        }
+        JF_TRY(msm_finish_host(ctx, srs->curve, (const uint64_t *)h, 1, out->q_xy, &out->q_inf));
+        // compute_quotient_challenge (:171-191)
+        Transcript tr(kind, "PlonkLinkingProof");
+        tr_g1(tr, "linking_wire_comms", a1_comm, a1_inf);
+        tr_g1(tr, "linking_wire_comms", a2_comm, a2_inf);
+        tr_g1(tr, "quotient_comm", out->q_xy, out->q_inf);
+        const E eta = challenge(tr, "eta");
+        H::fr_to_limbs(eta, out->eta);
+        E zd = E::one(), r = r0;  // compute_vanishing_poly_eval (:162-177)
+        for (size_t i = 0; i < size; i++) {
+            zd = E::mul(zd, E::sub(eta, r));
+            r = E::mul(r, g);
+        }
+        // compute_identity_opening (:193-216): (a1 - a2 - q Z_D(eta)) / (X - eta), committed
+        E *ident = (Q == A) ? B : A;
+        size_t wlen = 0;
+        if (max_len >= 2) {
+            std::vector<Term> terms = {{diff, max_len, E::one()}, {Q, q_len, E::neg(zd)}};
+            JF_TRY(lincomb_many(ctx, terms, ident, max_len));
+            E *wit = diff;  // a1 - a2 is not needed any more
+            JF_TRY(div_linear_dev(ctx, T, S, tmp, ident, max_len, eta, wit));
+            wlen = max_len - 1;
+            JF_TRY(msm_run(ctx, srs, 0, wit, wlen, 1, (char *)p_res + PT));
+        } else {
+            JF_TRY(msm_run(ctx, srs, 0, diff, 0, 1, (char *)p_res + PT));
+        }
+        JF_CUDA(ctx, cudaMemcpyAsync(h, (char *)p_res + PT, PT, cudaMemcpyDeviceToHost, st));
+        JF_CUDA(ctx, cudaMemcpyAsync(&herr, ctx->d_err, sizeof herr, cudaMemcpyDeviceToHost, st));
+        JF_CUDA(ctx, cudaStreamSynchronize(st));
+        if (herr) {
+            cudaMemsetAsync(ctx->d_err, 0, sizeof herr, st);
+            return fail(ctx, herr, "link_proofs: a coefficient is not a reduced field element");
+        }
+        JF_TRY(msm_finish_host(ctx, srs->curve, (const uint64_t *)h, 1, out->open_xy, &out->open_inf));
         return JF_OK;
     }
 
@@ -1937,6 +2174,30 @@ struct Bls12381Plonk : Bls12381G1 {
     if (!(ctx)) return JF_ERR_INVALID_ARG;        \
     std::lock_guard<std::mutex> lock_((ctx)->mu); \
     cudaSetDevice((ctx)->device)
+
+// entry of the two proof-linking forms (host hints / resident polynomials)
+template <class P>
+static int link_entry(jf_ctx *ctx, const jf_srs *srs, const void *d_a1, size_t len1, const uint64_t *a1_comm, int a1_inf, const void *d_a2,
+                      size_t len2, const uint64_t *a2_comm, int a2_inf, unsigned alignment, size_t offset, size_t size, int kind, int flags,
+                      jf_link_proof *out) {
+    using PL = Plonk<P>;
+    typename PL::LinkOut lo;
+    int rc = PL::link_proofs(ctx, srs, (const typename PL::E *)d_a1, len1, a1_comm, a1_inf, (const typename PL::E *)d_a2, len2, a2_comm,
+                             a2_inf, alignment, offset, size, kind, flags, &lo);
+    if (rc != JF_OK) {
+        cudaStreamSynchronize(ctx->stream);  // nothing of this call may still be in flight when the caller reuses its buffers
+        return rc;
+    }
+    memset(out, 0, sizeof *out);
+    out->curve = srs->curve;
+    memcpy(out->quotient_commitment, lo.q_xy, sizeof lo.q_xy);
+    out->quotient_inf = lo.q_inf;
+    memcpy(out->opening_proof, lo.open_xy, sizeof lo.open_xy);
+    out->opening_inf = lo.open_inf;
+    memcpy(out->eta, lo.eta, sizeof lo.eta);
+    out->path = lo.path;
+    return JF_OK;
+}
 
 // shared argument checks and the error drain of the two batch entry points
 template <int NWT, class ProofT>
@@ -2097,6 +2358,75 @@ int jf_kzg_open(jf_ctx *ctx, const jf_srs *srs, const uint64_t *const *polys, co
     if (batch == 0) return JF_OK;
     if (srs->curve == JF_BN254) return Plonk<Bn254Plonk>::kzg_open(ctx, srs, polys, lens, batch, points, out_proof_xy, out_infinity, out_evals);
     return Plonk<Bls12381Plonk>::kzg_open(ctx, srs, polys, lens, batch, points, out_proof_xy, out_infinity, out_evals);
+}
+
+// ---- proof linking ----------------------------------------------------------------------------------
+int jf_plonk_link_hint(jf_ctx *ctx, const jf_plonk_pk *pk, uint64_t *out_poly, size_t cap, size_t *out_len) {
+    JF_GUARD(ctx);
+    if (!pk || !out_poly || !out_len) return fail(ctx, JF_ERR_INVALID_ARG, "link_hint: null argument");
+    if (!pk->proofs_done) return fail(ctx, JF_ERR_INVALID_ARG, "link_hint: no proof has been made with this key yet");
+    const size_t len = pk->n + 2;  // the masked first wire polynomial (prover.rs:82)
+    if (cap < len) return fail(ctx, JF_ERR_INVALID_ARG, "link_hint: the buffer holds fewer than n + 2 coefficients");
+    JF_CUDA(ctx, cudaMemcpyAsync(out_poly, pk->d_w, 32 * len, cudaMemcpyDeviceToHost, ctx->stream));
+    JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out_len = len;
+    return JF_OK;
+}
+
+int jf_plonk_link_proofs(jf_ctx *ctx, const jf_srs *srs, const uint64_t *a1, size_t len1, const uint64_t *a1_comm_xy, int a1_inf,
+                         const uint64_t *a2, size_t len2, const uint64_t *a2_comm_xy, int a2_inf, unsigned alignment, size_t offset,
+                         size_t size, int transcript_kind, int flags, jf_link_proof *out) {
+    JF_GUARD(ctx);
+    if (!srs || !out || !a1_comm_xy || !a2_comm_xy || (len1 && !a1) || (len2 && !a2)) return fail(ctx, JF_ERR_INVALID_ARG, "link_proofs: null argument");
+    if (transcript_kind != 0 && transcript_kind != 1) return fail(ctx, JF_ERR_INVALID_ARG, "link_proofs: unknown transcript kind");
+    // DensePolynomial semantics: trailing (high-degree) zero coefficients do not count
+    auto trim = [](const uint64_t *p, size_t len) {
+        while (len && !(p[4 * (len - 1)] | p[4 * (len - 1) + 1] | p[4 * (len - 1) + 2] | p[4 * (len - 1) + 3])) len--;
+        return len;
+    };
+    len1 = trim(a1, len1);
+    len2 = trim(a2, len2);
+    void *d1, *d2;
+    JF_TRY(scratch(ctx, "link_in1", 32 * (len1 + 1), &d1));
+    JF_TRY(scratch(ctx, "link_in2", 32 * (len2 + 1), &d2));
+    if (len1) JF_CUDA(ctx, cudaMemcpyAsync(d1, a1, 32 * len1, cudaMemcpyHostToDevice, ctx->stream));
+    if (len2) JF_CUDA(ctx, cudaMemcpyAsync(d2, a2, 32 * len2, cudaMemcpyHostToDevice, ctx->stream));
+    if (srs->curve == JF_BN254)
+        return link_entry<Bn254Plonk>(ctx, srs, d1, len1, a1_comm_xy, a1_inf, d2, len2, a2_comm_xy, a2_inf, alignment, offset, size,
+                                      transcript_kind, flags, out);
+    return link_entry<Bls12381Plonk>(ctx, srs, d1, len1, a1_comm_xy, a1_inf, d2, len2, a2_comm_xy, a2_inf, alignment, offset, size,
+                                     transcript_kind, flags, out);
+}
+
+int jf_plonk_link_proofs_resident(jf_ctx *ctx, const jf_plonk_pk *lhs, const jf_plonk_proof *lhs_proof, const jf_plonk_pk *rhs,
+                                  const jf_plonk_proof *rhs_proof, unsigned alignment, size_t offset, size_t size, int transcript_kind,
+                                  int flags, jf_link_proof *out) {
+    JF_GUARD(ctx);
+    if (!lhs || !rhs || !lhs_proof || !rhs_proof || !out) return fail(ctx, JF_ERR_INVALID_ARG, "link_proofs: null argument");
+    if (transcript_kind != 0 && transcript_kind != 1) return fail(ctx, JF_ERR_INVALID_ARG, "link_proofs: unknown transcript kind");
+    if (lhs->nw != jf::NW_TURBO || rhs->nw != jf::NW_TURBO) return fail(ctx, JF_ERR_INVALID_ARG, "link_proofs: only TurboPlonk supports link groups");
+    if (!lhs->proofs_done || !rhs->proofs_done) return fail(ctx, JF_ERR_INVALID_ARG, "link_proofs: no proof has been made with one of the keys");
+    if (lhs->srs != rhs->srs) return fail(ctx, JF_ERR_INVALID_ARG, "link_proofs: the two proofs must share one commit key");
+    const jf_srs *srs = lhs->srs;
+    if (srs->curve == JF_BN254)
+        return link_entry<Bn254Plonk>(ctx, srs, lhs->d_w, lhs->n + 2, lhs_proof->wires_poly_comms, lhs_proof->wires_inf[0], rhs->d_w, rhs->n + 2,
+                                      rhs_proof->wires_poly_comms, rhs_proof->wires_inf[0], alignment, offset, size, transcript_kind, flags, out);
+    return link_entry<Bls12381Plonk>(ctx, srs, lhs->d_w, lhs->n + 2, lhs_proof->wires_poly_comms, lhs_proof->wires_inf[0], rhs->d_w, rhs->n + 2,
+                                     rhs_proof->wires_poly_comms, rhs_proof->wires_inf[0], alignment, offset, size, transcript_kind, flags, out);
+}
+
+long jf_link_proof_serialize(const jf_link_proof *proof, uint8_t *out, size_t cap) {
+    if (!proof || !out) return JF_ERR_INVALID_ARG;
+    const size_t pt = proof->curve == JF_BN254 ? 32 : 48;
+    if (cap < 2 * pt) return JF_ERR_INVALID_ARG;
+    if (proof->curve == JF_BN254) {
+        HostCurve<Bn254Plonk>::g1_bytes(proof->quotient_commitment, proof->quotient_inf, out);
+        HostCurve<Bn254Plonk>::g1_bytes(proof->opening_proof, proof->opening_inf, out + pt);
+    } else {
+        HostCurve<Bls12381Plonk>::g1_bytes(proof->quotient_commitment, proof->quotient_inf, out);
+        HostCurve<Bls12381Plonk>::g1_bytes(proof->opening_proof, proof->opening_inf, out + pt);
+    }
+    return (long)(2 * pt);
 }
 
 long jf_plonk_proof_serialize(const jf_plonk_proof *proof, uint8_t *out, size_t cap) {

@@ -106,6 +106,50 @@ class Proof:
         return buf.raw[:n]
 
 
+@dataclass
+class GroupLayout:
+    """`GroupLayout` (relation/src/proof_linking/mod.rs:17-53): `size` proof-linking gates on the 2^alignment-th roots of unity,
+    starting at `offset`."""
+    alignment: int
+    offset: int
+    size: int
+
+
+@dataclass
+class LinkingHint:
+    """`LinkingHint<E>` (structs.rs:88-97): the first wire polynomial after masking ((n + 2, 4) Montgomery limbs) and its commitment."""
+    linking_wire_poly: np.ndarray
+    linking_wire_comm: np.ndarray
+    linking_wire_inf: bool = False
+
+
+@dataclass
+class LinkingProof:
+    """`LinkingProof<E>` (proof_linking.rs:32-39)."""
+    curve: str
+    quotient_commitment: np.ndarray
+    quotient_inf: bool
+    opening_proof: np.ndarray
+    opening_inf: bool
+    eta: np.ndarray   # the opening challenge, Montgomery limbs (diagnostics)
+    path: int         # 0: exact division on a coset, 1: successive linear divisions (diagnostics)
+    _raw: object = None
+
+    def serialize_compressed(self) -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        n = _ffi.lib().jf_link_proof_serialize(ctypes.byref(self._raw), buf, len(buf))
+        if n < 0:
+            raise InvalidParameters("linking proof serialization failed (%d)" % n)
+        return buf.raw[:n]
+
+
+def _link_proof_from_raw(curve: str, raw) -> LinkingProof:
+    L = _ffi.CURVE_FQ_LIMBS[curve]
+    return LinkingProof(curve, np.array(raw.quotient_commitment[:2 * L], dtype=np.uint64), bool(raw.quotient_inf),
+                        np.array(raw.opening_proof[:2 * L], dtype=np.uint64), bool(raw.opening_inf),
+                        np.array(raw.eta, dtype=np.uint64), int(raw.path), raw)
+
+
 class ProvingKey:
     """`ProvingKey<E>` resident on the GPU (selector / sigma polynomials, commit key, vk commitments)."""
 
@@ -266,6 +310,46 @@ class PlonkKzgSnark:
             wire_sigma_evals=np.array(raw.wire_sigma_evals, dtype=np.uint64).reshape(4, 4),
             perm_next_eval=np.array(raw.perm_next_eval, dtype=np.uint64),
             challenges=np.array(raw.challenges, dtype=np.uint64).reshape(5, 4), _raw=raw)
+
+    # ---- proof linking (plonk/src/proof_system/proof_linking.rs) --------------------------------------------------------------
+    @staticmethod
+    def prove_with_link_hint(pk: ProvingKey, witness: np.ndarray, blinders: np.ndarray, transcript: str = "solidity"):
+        """`PlonkKzgSnark::prove_with_link_hint` (snark.rs:81-114) -> (Proof, LinkingHint); TurboPlonk only."""
+        if pk.ultra:
+            raise InvalidParameters("only TurboPlonk supports link groups")
+        proof = PlonkKzgSnark.prove(pk, witness, blinders, transcript)
+        ctx = pk.ctx
+        poly = np.zeros((pk.n + 2, 4), dtype=np.uint64)
+        got = ctypes.c_size_t(0)
+        ctx._check(ctx._lib.jf_plonk_link_hint(ctx._h, pk._h, poly.ctypes.data_as(_ffi.c_u64p), pk.n + 2, ctypes.byref(got)))
+        return proof, LinkingHint(poly[:got.value], proof.wires_poly_comms[0].copy(), proof.wires_inf[0])
+
+    @staticmethod
+    def link_proofs(ctx: Context, key: CommitKey, lhs: LinkingHint, rhs: LinkingHint, layout: GroupLayout,
+                    transcript: str = "solidity", sequential_division: bool = False) -> LinkingProof:
+        """`PlonkKzgSnark::link_proofs` (proof_linking.rs:79-112) from two hints in host memory."""
+        a1 = np.ascontiguousarray(lhs.linking_wire_poly, dtype=np.uint64).reshape(-1, 4)
+        a2 = np.ascontiguousarray(rhs.linking_wire_poly, dtype=np.uint64).reshape(-1, 4)
+        c1 = np.ascontiguousarray(lhs.linking_wire_comm, dtype=np.uint64)
+        c2 = np.ascontiguousarray(rhs.linking_wire_comm, dtype=np.uint64)
+        raw = _ffi.LinkProofStruct()
+        ctx._check(ctx._lib.jf_plonk_link_proofs(
+            ctx._h, key._h, a1.ctypes.data_as(_ffi.c_u64p), len(a1), c1.ctypes.data_as(_ffi.c_u64p), int(lhs.linking_wire_inf),
+            a2.ctypes.data_as(_ffi.c_u64p), len(a2), c2.ctypes.data_as(_ffi.c_u64p), int(rhs.linking_wire_inf),
+            layout.alignment, layout.offset, layout.size, TRANSCRIPT_KINDS[transcript], int(sequential_division), ctypes.byref(raw)))
+        return _link_proof_from_raw(key.curve, raw)
+
+    @staticmethod
+    def link_proofs_resident(lhs_pk: ProvingKey, lhs_proof: Proof, rhs_pk: ProvingKey, rhs_proof: Proof, layout: GroupLayout,
+                             transcript: str = "solidity", sequential_division: bool = False) -> LinkingProof:
+        """The same with both wire polynomials still in the workspaces of the two proving keys (no polynomial crosses PCIe):
+        `lhs_proof` / `rhs_proof` must be the LAST proofs made with those keys."""
+        ctx = lhs_pk.ctx
+        raw = _ffi.LinkProofStruct()
+        ctx._check(ctx._lib.jf_plonk_link_proofs_resident(
+            ctx._h, lhs_pk._h, ctypes.byref(lhs_proof._raw), rhs_pk._h, ctypes.byref(rhs_proof._raw), layout.alignment, layout.offset,
+            layout.size, TRANSCRIPT_KINDS[transcript], int(sequential_division), ctypes.byref(raw)))
+        return _link_proof_from_raw(lhs_pk.key.curve, raw)
 
     # ---- UltraPlonk (`PlonkCircuit::new_ultra_plonk`; Plookup argument) ----------------------------------------------------
     @staticmethod

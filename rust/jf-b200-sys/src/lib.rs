@@ -38,6 +38,17 @@ pub struct jf_plonk_proof {
     pub challenges: [u64; 20],
 }
 
+/// `jf_link_proof`: `LinkingProof<E>` (plonk/src/proof_system/proof_linking.rs:32-39) plus diagnostics.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct jf_link_proof {
+    pub curve: c_int,
+    pub quotient_commitment: [u64; 12], pub quotient_inf: c_int,
+    pub opening_proof: [u64; 12], pub opening_inf: c_int,
+    pub eta: [u64; 4],
+    pub path: c_int,
+}
+
 /// `jf_ultraplonk_proof`: an UltraPlonk `Proof<E>` with `plookup_proof: Some(..)`.
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -143,6 +154,15 @@ extern "C" {
     pub fn jf_plonk_prove(ctx: *mut jf_ctx, pk: *mut jf_plonk_pk, witness: *const u64, blinders: *const u64,
                           transcript_kind: c_int, extra_msg: *const u8, extra_len: usize, out: *mut jf_plonk_proof) -> c_int;
     pub fn jf_plonk_proof_serialize(proof: *const jf_plonk_proof, out: *mut u8, cap: usize) -> c_long;
+
+    pub fn jf_plonk_link_hint(ctx: *mut jf_ctx, pk: *const jf_plonk_pk, out_poly: *mut u64, cap: usize, out_len: *mut usize) -> c_int;
+    pub fn jf_plonk_link_proofs(ctx: *mut jf_ctx, srs: *const jf_srs, a1: *const u64, len1: usize, a1_comm_xy: *const u64, a1_inf: c_int,
+                                a2: *const u64, len2: usize, a2_comm_xy: *const u64, a2_inf: c_int, alignment: c_uint, offset: usize,
+                                size: usize, transcript_kind: c_int, flags: c_int, out: *mut jf_link_proof) -> c_int;
+    pub fn jf_plonk_link_proofs_resident(ctx: *mut jf_ctx, lhs: *const jf_plonk_pk, lhs_proof: *const jf_plonk_proof,
+                                         rhs: *const jf_plonk_pk, rhs_proof: *const jf_plonk_proof, alignment: c_uint, offset: usize,
+                                         size: usize, transcript_kind: c_int, flags: c_int, out: *mut jf_link_proof) -> c_int;
+    pub fn jf_link_proof_serialize(proof: *const jf_link_proof, out: *mut u8, cap: usize) -> c_long;
 
     pub fn jf_keccak256(data: *const u8, len: usize, out: *mut u8);
     pub fn jf_transcript_new(kind: c_int, label: *const c_char) -> *mut c_void;

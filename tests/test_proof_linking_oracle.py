@@ -198,3 +198,37 @@ def test_invalid_proof_links(P, py, link_srs):
         except ValueError:
             continue   # the moved group collides with the public inputs: the reference fails in finalize as well
         assert not _link_and_verify(P, cv, link_srs, h1, h4, p1, p4, bad, "solidity")[0]
+
+
+def _vanishing_coeffs_model(p, g, offset, s):
+    """the recurrences of `Plonk::vanishing_coeffs` (csrc/plonk.cu) in exact integers: q-binomial theorem,
+    prod_{i<s} (X - g^(offset+i)) = sum_k (-1)^k [s;k]_g g^(k(k-1)/2 + offset k) X^(s-k)"""
+    gp = [1] * (s + 1)
+    for k in range(1, s + 1):
+        gp[k] = gp[k - 1] * g % p
+    den = [0] + [(1 - gp[k]) % p for k in range(1, s + 1)]
+    z = [0] * (s + 1)
+    z[s] = 1
+    binom, e, step = 1, 1, pow(g, offset, p)
+    for k in range(1, s + 1):
+        binom = binom * den[s - k + 1] % p * pow(den[k], -1, p) % p
+        e = e * step % p
+        step = step * g % p
+        z[s - k] = (-binom * e if k & 1 else binom * e) % p
+    return z
+
+
+@pytest.mark.parametrize("alignment,offset,size", [(4, 0, 1), (4, 3, 2), (5, 11, 10), (8, 20, 10), (8, 1, 254), (10, 700, 300)])
+def test_vanishing_polynomial_closed_form(P, py, alignment, offset, size):
+    fr = py.BN254_FR
+    p = fr.p
+    lay = P.GroupLayout(alignment, offset, size)
+    g = lay.domain_generator(fr)
+    z = [1]
+    for r in P._link_roots(fr, lay):   # the reference's product of monomials (proof_linking.rs:137-160)
+        nz = [0] * (len(z) + 1)
+        for i, c in enumerate(z):
+            nz[i] = (nz[i] - c * r) % p
+            nz[i + 1] = (nz[i + 1] + c) % p
+        z = nz
+    assert _vanishing_coeffs_model(p, g, offset, size) == z
