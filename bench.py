@@ -483,6 +483,63 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
     }
 
 
+def link_leg(ctx, co, torch, args):
+    """Proof linking (plonk/src/proof_system/proof_linking.rs:79-216) at the prover bench's size: two first-wire polynomials of
+    2^20 + 2 coefficients that agree on a link group of 1024 values (GroupLayout { alignment 19, offset 100, size 1024 }) -> the
+    quotient commitment and the opening proof through `jf_plonk_link_proofs` (hints in host memory: 2 x 32 MiB H2D inside).  The
+    hints are synthetic (a2 = a1 + c X^7 (X^(2^19) - 1), which vanishes on every 2^19-th root of unity); the result is checked
+    with the restated verifier's equation in G1 (known beta).  Rank 0 only."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import plonk_ref as P
+    import plonk_util as U
+    import pyref
+    jf = jf_mod()
+    cv, fr = pyref.BN254, pyref.BN254_FR
+    log_n, align, offset = PROVE_LOG_N, PROVE_LOG_N - 1, 100
+    n = 1 << log_n
+    beta = BETA % co_modulus()
+    key = ctx.generate_srs_for_testing("bn254", beta, n + 3)
+    rng = np.random.default_rng(SEED % (1 << 32) + 77)
+    a1 = rng.integers(0, 1 << 62, size=(n + 2, 4), dtype=np.uint64)   # < 2^254: valid Montgomery representations
+    a1[:, 3] >>= 2
+    a2 = a1.copy()
+    c = np.array([[5, 0, 0, 0]], dtype=np.uint64)
+    a2[7:8] = ctx.field_op("bn254_fr", "sub", a1[7:8], c)
+    a2[7 + (1 << align):8 + (1 << align)] = ctx.field_op("bn254_fr", "add", a1[7 + (1 << align):8 + (1 << align)], c)
+    pin = lambda a: torch.from_numpy(a.view(np.int64)).pin_memory().numpy().view(np.uint64)  # noqa: E731
+    a1, a2 = pin(a1), pin(a2)
+    c1, i1 = ctx.msm(key, a1, montgomery=True)
+    c2, i2 = ctx.msm(key, a2, montgomery=True)
+    h1, h2 = jf.LinkingHint(a1, c1, bool(i1)), jf.LinkingHint(a2, c2, bool(i2))
+    out = {}
+    steps = max(1, min(args.steps, 5))
+    for size, seq in ((1024, False), (64, False), (64, True)):
+        lay = jf.GroupLayout(align, offset, size)
+        lp = jf.PlonkKzgSnark.link_proofs(ctx, key, h1, h2, lay, "solidity", sequential_division=seq)
+        if lp.path != (1 if seq else 0):
+            raise SystemExit("bench.py: link_proofs took the wrong division path")
+        o1 = {"wires_poly_comms": [U.point_to_affine(co, cv, c1, i1)]}
+        o2 = {"wires_poly_comms": [U.point_to_affine(co, cv, c2, i2)]}
+        olp = {"quotient_commitment": U.point_to_affine(co, cv, lp.quotient_commitment, lp.quotient_inf),
+               "opening_proof": U.point_to_affine(co, cv, lp.opening_proof, lp.opening_inf)}
+        if not P.verify_link_proof(cv, o1, o2, olp, P.GroupLayout(align, offset, size), beta, "solidity"):
+            raise SystemExit("bench.py: the linking proof is rejected by the restated verifier; refusing to time it")
+        l0 = ctx.launch_count
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            jf.PlonkKzgSnark.link_proofs(ctx, key, h1, h2, lay, "solidity", sequential_division=seq)
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        out["size_%d_%s" % (size, "linear_divisions" if seq else "coset_division")] = {
+            "value": round(ms, 3), "unit": "ms", "gpu_launches": int((ctx.launch_count - l0) // steps)}
+    key.free()
+    return {"metric": "link_proofs ms, two 2^20-gate proofs (BN254, SolidityTranscript, host hints, accepted by the restated verifier)",
+            **out,
+            "note": "coset_division: a1 - a2 vanishes on the link domain, so the quotient is a pointwise ratio on a coset (4 transforms "
+                    "of 2^20 + one batch inversion, independent of the group size) + 2 MSMs; linear_divisions: the reference-literal floor "
+                    "quotient as `size` scan divisions (the path taken for pairs that are NOT linked); both give the same bytes "
+                    "(tests/test_gpu_proof_linking.py)"}
+
+
 def jf_mod():
     import mpc_jellyfish_b200 as jf
     return jf
@@ -879,6 +936,7 @@ def run_cuda(args):
             cpu_ntt = ntt["cpu_baseline"]["value"] if ntt and ntt.get("cpu_baseline") else None
         prove = prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream, cpu_msm_ms, cpu_ntt)
     mpc = None if args.no_mpc else mpc_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream)
+    link = link_leg(ctx, co, torch, args) if (rank == 0 and not args.no_prove and not args.no_sweep) else None
     stop.set()
     sampler.join(timeout=2)
     clocks = _clock_summary(rows)
@@ -962,6 +1020,7 @@ def run_cuda(args):
         "ntt": ntt,
         "prove": prove,
         "mpc": mpc,
+        "link_proofs": link,
     }
     _emit(line)
     if world > 1:

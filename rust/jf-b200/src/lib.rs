@@ -36,6 +36,8 @@ pub trait GpuCurve: Pairing {
     const FR: c_int;      // JF_BN254_FR / JF_BLS12_381_FR
     const L: usize;       // u64 limbs per base-field element (4 / 6)
     fn point_from_mont(xy: &[u64], infinity: bool) -> Self::G1Affine;
+    /// x || y Montgomery limbs (2 L of the 12 words used) and the infinity flag: the form commitments cross the ABI in
+    fn point_to_mont(p: &Self::G1Affine) -> ([u64; 12], bool);
     fn fr_from_mont(limbs: [u64; 4]) -> Self::ScalarField;
     /// (size_of::<G1Affine>(), byte offset of `infinity` inside it)
     fn affine_layout() -> (usize, usize);
@@ -53,6 +55,14 @@ macro_rules! impl_gpu_curve {
                 x.copy_from_slice(&xy[..$l]);
                 y.copy_from_slice(&xy[$l..2 * $l]);
                 <$aff>::new_unchecked(<$fq>::new_unchecked(BigInt::<$l>(x)), <$fq>::new_unchecked(BigInt::<$l>(y)))
+            }
+            fn point_to_mont(p: &$aff) -> ([u64; 12], bool) {
+                let mut xy = [0u64; 12];
+                if !p.infinity {
+                    xy[..$l].copy_from_slice(&(p.x.0).0);      // Fp(BigInt<N>): the Montgomery representation as stored
+                    xy[$l..2 * $l].copy_from_slice(&(p.y.0).0);
+                }
+                (xy, p.infinity)
             }
             fn fr_from_mont(limbs: [u64; 4]) -> $fr { <$fr>::new_unchecked(BigInt::<4>(limbs)) }
             fn affine_layout() -> (usize, usize) {
@@ -193,6 +203,23 @@ impl<E: GpuCurve> GpuCommitKey<E> {
         let zs = vec![*z; components.len()];
         self.batch_open(components, &zs)
     }
+    /// `PlonkKzgSnark::link_proofs` (plonk/src/proof_system/proof_linking.rs:79-112) from the two hints' wire polynomials and
+    /// commitments: -> (quotient commitment, opening proof).  `layout` = (alignment, offset, size) of the `GroupLayout`.
+    #[allow(clippy::too_many_arguments)]
+    pub fn link_proofs(&self, a1: &[E::ScalarField], a1_comm: &E::G1Affine, a2: &[E::ScalarField], a2_comm: &E::G1Affine,
+                       layout: (usize, usize, usize), solidity_transcript: bool) -> Result<(E::G1Affine, E::G1Affine), GpuError> {
+        let (c1, i1) = E::point_to_mont(a1_comm);
+        let (c2, i2) = E::point_to_mont(a2_comm);
+        let mut out = MaybeUninit::<sys::jf_link_proof>::uninit();
+        self.gpu.check(unsafe {
+            sys::jf_plonk_link_proofs(self.gpu.ctx, self.srs, a1.as_ptr() as *const u64, a1.len(), c1.as_ptr(), i1 as c_int,
+                                      a2.as_ptr() as *const u64, a2.len(), c2.as_ptr(), i2 as c_int, layout.0 as u32, layout.1, layout.2,
+                                      if solidity_transcript { 0 } else { 1 }, 0, out.as_mut_ptr())
+        })?;
+        let lp = unsafe { out.assume_init() };
+        let w = 2 * E::L;
+        Ok((E::point_from_mont(&lp.quotient_commitment[..w], lp.quotient_inf != 0), E::point_from_mont(&lp.opening_proof[..w], lp.opening_inf != 0)))
+    }
 }
 impl<E: GpuCurve> Drop for GpuCommitKey<E> { fn drop(&mut self) { unsafe { sys::jf_srs_free(self.gpu.ctx, self.srs) } } }
 
@@ -271,6 +298,22 @@ pub fn try_commit_authenticated<E: Pairing>(powers_of_g: &[E::G1Affine], compone
     dispatch!(E, powers_of_g, |C, pts| {
         let cs: Vec<&[<C as Pairing>::ScalarField]> = components.iter().map(|p| same::<E, C, E::ScalarField, _>(p).unwrap()).collect();
         cached_commit_key::<C>(pts).and_then(|k| k.commit_authenticated(&cs)).map(back::<Vec<<C as Pairing>::G1Affine>, Vec<E::G1Affine>>)
+    })
+}
+
+/// `link_proofs` for the patched `PlonkKzgSnark::<E>::link_proofs`: quotient, its commitment, the challenge and the opening in
+/// one call.  `solidity_transcript`: T is `SolidityTranscript` (else `StandardTranscript`).
+#[allow(clippy::too_many_arguments, clippy::type_complexity)]
+pub fn try_link_proofs<E: Pairing>(powers_of_g: &[E::G1Affine], a1: &[E::ScalarField], a1_comm: &E::G1Affine, a2: &[E::ScalarField],
+                                   a2_comm: &E::G1Affine, layout: (usize, usize, usize), solidity_transcript: bool)
+                                   -> Option<Result<(E::G1Affine, E::G1Affine), GpuError>> {
+    dispatch!(E, powers_of_g, |C, pts| {
+        let p1 = same::<E, C, E::ScalarField, <C as Pairing>::ScalarField>(a1).unwrap();
+        let p2 = same::<E, C, E::ScalarField, <C as Pairing>::ScalarField>(a2).unwrap();
+        let c1 = same::<E, C, E::G1Affine, <C as Pairing>::G1Affine>(core::slice::from_ref(a1_comm)).unwrap();
+        let c2 = same::<E, C, E::G1Affine, <C as Pairing>::G1Affine>(core::slice::from_ref(a2_comm)).unwrap();
+        cached_commit_key::<C>(pts).and_then(|k| k.link_proofs(p1, &c1[0], p2, &c2[0], layout, solidity_transcript))
+            .map(back::<(<C as Pairing>::G1Affine, <C as Pairing>::G1Affine), (E::G1Affine, E::G1Affine)>)
     })
 }
 
