@@ -341,7 +341,7 @@ def ntt_leg(env):
 PROVE_LOG_N = 20
 
 
-def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream, cpu_msm_ms, cpu_ntt_melems):
+def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream, cpu_msm_ms, cpu_ntt_melems, comm=None):
     """First metric of BASELINE.json: "BN254 2^20-gate PLONK prove ms" (configs[3]).  One step = one
     `PlonkKzgSnark::prove` of the reference's own bench circuit (plonk/benches/bench.rs:29-46, 2^20 gates,
     TurboPlonk, SolidityTranscript) through the C-ABI call `jf_plonk_prove`: witness in host memory
@@ -398,6 +398,27 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
         out[(cache, skip, full)] = {"wall_ms": max_over_ranks(wall), "device_ms": max_over_ranks(dev), "launches": int(launches),
                       "preprocess_s": round(t_pre, 3),
                       "kernels_ms": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}}
+        if comm is not None and not cache and not skip and not full:
+            # ONE proof on all the GPUs (strong scaling of the prove metric): every rank runs the same call -- same witness, same
+            # blinders -- and commits only its slice of every polynomial (jf_plonk_pk_shard_commits); the 13 MSMs split by point
+            # range, the transforms are replicated.  Refuses to time unless the bytes equal the one-GPU proof of this rank.
+            from mpc_jellyfish_b200.sharded import shard_range
+            bl0 = np.random.default_rng(SEED % (1 << 32)).integers(0, 1 << 60, size=(17, 4), dtype=np.uint64)
+            ref_bytes = jf_mod().PlonkKzgSnark.prove(pk, wit, bl0, "solidity").serialize_compressed()
+            a, b = shard_range(n + 3, world, rank)
+            key_slice = ctx.generate_srs_for_testing("bn254", BETA % co_modulus(), b - a, first_power=a)
+            pk.shard_commits(comm, key_slice, a)
+            if jf_mod().PlonkKzgSnark.prove(pk, wit, bl0, "solidity").serialize_compressed() != ref_bytes:
+                raise SystemExit("bench.py: the proof with sharded commitments differs from the one-GPU proof; refusing to time it")
+            jf_mod().PlonkKzgSnark.prove(pk, wit, bl0, "solidity")
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                jf_mod().PlonkKzgSnark.prove(pk, wit, bl0, "solidity")
+            barrier()
+            out["sharded"] = max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+            pk.shard_commits(None, None)
+            key_slice.free()
         pk.free()
     key.free()
     # BASELINE configs[0] shape (2^16 gates, the size the reference's own bench can run): one data point
@@ -475,6 +496,11 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
         "with_cached_selector_sigma_coset_evals": alt((True, True, False), "additionally the selector / sigma coset evaluations stay "
                                                       "resident (+3.4 GiB): only 7 polynomials are transformed per proof; same proof bytes"),
         "prove_2^16_gates_ms": prove16_ms,
+        "one_proof_on_all_gpus": ({"value": out["sharded"], "unit": "ms", "n_gpus": world, "scaling": "strong",
+                                   "note": "every rank runs the same jf_plonk_prove call and commits 1/%d of every polynomial "
+                                           "(jf_plonk_pk_shard_commits: the 13 MSMs split by point range, partials over %s; transforms "
+                                           "and polynomial algebra replicated); bytes equal the one-GPU proof" % (world, comm.transport)}
+                                  if "sharded" in out else None),
         "ultraplonk_2^20_gates": ultra,
         "cpu_baseline": cpu,
         "e2e": {"value": base["wall_ms"], "unit": "ms", "h2d_bytes_per_step": int(arr["witness"].nbytes + 17 * 32),
@@ -934,7 +960,7 @@ def run_cuda(args):
             cpu_msm_ms = (time.perf_counter() - t0) * 1e3 * (n / ns)
             env.gpu_leg()
             cpu_ntt = ntt["cpu_baseline"]["value"] if ntt and ntt.get("cpu_baseline") else None
-        prove = prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream, cpu_msm_ms, cpu_ntt)
+        prove = prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream, cpu_msm_ms, cpu_ntt, env.comm)
     mpc = None if args.no_mpc else mpc_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream)
     link = link_leg(ctx, co, torch, args) if (rank == 0 and not args.no_prove and not args.no_sweep) else None
     stop.set()

@@ -318,6 +318,17 @@ int jf_ultraplonk_batch_prove(jf_ctx *ctx, jf_plonk_pk *const *pks, size_t count
 long jf_plonk_batch_proof_serialize(const jf_plonk_proof *proofs, size_t count, uint8_t *out, size_t cap);
 long jf_ultraplonk_batch_proof_serialize(const jf_ultraplonk_proof *proofs, size_t count, uint8_t *out, size_t cap);
 
+/* ---- ONE proof on several GPUs (one process per GPU, jf_comm) ----------------------------------------------------------------
+ * Every commitment of a proof is a sum over (coefficient, key point) pairs, so it splits by point range like jf_msm_sharded.  After
+ * jf_plonk_pk_shard_commits every rank runs the SAME jf_plonk_prove / jf_plonk_batch_prove / jf_ultraplonk_prove call (same circuit,
+ * witness, blinders, transcript: the polynomial algebra and the transforms are replicated, they hold identical polynomials in HBM),
+ * but commits only coefficients [slice_start, slice_start + jf_srs_len(key_slice)) against its slice of the key; the XYZZ partials
+ * cross NVLink (peer-memory mailboxes or ncclAllGather) before each commitment is normalised, so every rank sees the same
+ * commitments, squeezes the same challenges and returns the same proof.  The 13 MSMs of a TurboPlonk proof then cost 1/nranks of
+ * their accumulation each.  `pk` was built with the FULL key (jf_plonk_preprocess is not collective); comm == NULL returns the key to
+ * one-GPU operation.  Calls are collective: the ranks must issue them in the same order. */
+int jf_plonk_pk_shard_commits(jf_ctx *ctx, jf_plonk_pk *pk, jf_comm *comm, const jf_srs *key_slice, size_t slice_start);
+
 /* ---- proof linking ------------------------------------------------------------------------------------------------------------
  * `PlonkKzgSnark::link_proofs` (plonk/src/proof_system/proof_linking.rs:79-216): two TurboPlonk proofs whose circuits placed the
  * same link group (`GroupLayout { alignment, offset, size }`, relation/src/proof_linking/mod.rs:17-53) carry the group's values in

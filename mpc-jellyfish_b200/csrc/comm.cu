@@ -236,18 +236,23 @@ static int msm_partial_to_host(jf_ctx *ctx, const jf_srs *srs, size_t off, const
     return JF_OK;
 }
 
-static int comm_exchange(jf_ctx *ctx, jf_comm *c, size_t pt, void *d_out_parts) {
+// every rank's `d_part` (pt bytes: one XYZZ point) -> d_out_parts (nranks x pt, rank order) on every rank; ctx->stream.
+// Calls must be issued in the same order on every rank and on ONE stream (the mailbox parities rely on it).
+int comm_exchange_from(jf_ctx *ctx, jf_comm *c, const void *d_part, size_t pt, void *d_out_parts) {
     if (c->transport == 2) {
         c->seq++;
-        JF_LAUNCH(ctx, "msm_exchange", msm_exchange_kernel<<<1, 256, 0, ctx->stream>>>((const uint4 *)c->d_part, (int)(pt / 16), c->peers, c->rank,
+        JF_LAUNCH(ctx, "msm_exchange", msm_exchange_kernel<<<1, 256, 0, ctx->stream>>>((const uint4 *)d_part, (int)(pt / 16), c->peers, c->rank,
                                                                           c->nranks, c->seq, (uint4 *)d_out_parts, ctx->d_err));
         return JF_OK;
     }
     NcclApi *api = nccl_api();
     if (!api) return fail(ctx, JF_ERR_COMM, "NCCL is not available");
-    JF_NCCL(ctx, api, api->AllGather(c->d_part, d_out_parts, pt, ncclChar, c->nccl, ctx->stream));
+    JF_NCCL(ctx, api, api->AllGather(d_part, d_out_parts, pt, ncclChar, c->nccl, ctx->stream));
     return JF_OK;  // NCCL's kernel, not ours: not counted in jf_ctx_launch_count
 }
+int comm_size(const jf_comm *c) { return c->nranks; }
+jf_ctx *comm_ctx(const jf_comm *c) { return c->ctx; }
+static int comm_exchange(jf_ctx *ctx, jf_comm *c, size_t pt, void *d_out_parts) { return comm_exchange_from(ctx, c, c->d_part, pt, d_out_parts); }
 
 }  // namespace jf
 

@@ -184,6 +184,10 @@ bool msm_reads_scalars_once(const jf_srs *srs, size_t n);
 bool zero_copy_enabled();                          // JF_MSM_ZEROCOPY != 0
 const void *pinned_device_view(const void *host);  // device-visible alias of a page-locked host buffer, nullptr for pageable memory
 int msm_finish_host(jf_ctx *ctx, int curve, const uint64_t *xyzz_parts, size_t parts, uint64_t *out_xy, int *out_inf);
+// comm.cu: all-gather of one XYZZ partial per rank (mailboxes over peer memory, or ncclAllGather); see comm_exchange_from there
+int comm_exchange_from(jf_ctx *ctx, jf_comm *c, const void *d_part, size_t pt, void *d_out_parts);
+int comm_size(const jf_comm *c);
+jf_ctx *comm_ctx(const jf_comm *c);
 int srs_build(jf_ctx *ctx, int curve, const void *d_base_points /* n affine, device */, size_t n, int window_bits,
               int precompute, jf_srs **out);
 int srs_generate(jf_ctx *ctx, int curve, const uint64_t *beta, size_t first_power, size_t n, void *d_out_points);

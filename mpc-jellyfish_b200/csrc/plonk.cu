@@ -749,6 +749,12 @@ struct jf_plonk_pk {
     size_t num_vars = 0;
     uint32_t num_inputs = 0;
     int cache_coset = 0;
+    // one proof on several GPUs (jf_plonk_pk_shard_commits): this rank commits coefficients [shard_start, shard_start + len(srs_slice))
+    // against its slice of the key; the XYZZ partials of all ranks are exchanged before a commitment is normalised
+    jf_comm *comm = nullptr;
+    const jf_srs *srs_slice = nullptr;
+    size_t shard_start = 0;
+    void *d_parts = nullptr;  // 32 slots x nranks partials
     int proofs_done = 0;    // batch_prove calls that left their wire polynomials in d_w (jf_plonk_link_hint, proof linking)
     uint32_t zero_sel = 0;  // selectors that are identically zero (flags & 2)
     int skip_zero = 0;      // flags & 2: zero polynomials (such selectors; PI without public inputs) are not transformed
@@ -902,6 +908,11 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
 
     // commitments of `count` device polynomials (Montgomery coefficients) -> d_res[slot..]
     static int commit_dev(jf_ctx *ctx, const jf_plonk_pk *pk, const void *d_poly, size_t len, int slot) {
+        if (pk->comm) {  // this rank's slice of the sum; fetch_commits exchanges the partials
+            const size_t a = pk->shard_start;
+            return msm_run(ctx, pk->srs_slice, 0, (const char *)d_poly + sizeof(E) * std::min(a, len), len > a ? len - a : 0, 1,
+                           (char *)pk->d_res + PT * slot);
+        }
         return msm_run(ctx, pk->srs, 0, d_poly, len, 1, (char *)pk->d_res + PT * slot);
     }
     // `count` commitments on the main stream: every MSM runs its bulk phases (digits, sort, bucket accumulation) into
@@ -910,24 +921,41 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
     struct CommitJob { const void *poly; size_t len; int slot; };
     static int commit_many(jf_ctx *ctx, jf_plonk_pk *pk, const CommitJob *jobs, int count) {
         MsmJob mj[NVK];
+        if (pk->comm) {
+            const size_t a = pk->shard_start;
+            for (int i = 0; i < count; i++)
+                mj[i] = MsmJob{0, (const char *)jobs[i].poly + sizeof(E) * std::min(a, jobs[i].len), jobs[i].len > a ? jobs[i].len - a : 0, 1,
+                               (char *)pk->d_res + PT * jobs[i].slot};
+            return msm_run_many(ctx, pk->srs_slice, mj, count);
+        }
         for (int i = 0; i < count; i++) mj[i] = MsmJob{0, jobs[i].poly, jobs[i].len, 1, (char *)pk->d_res + PT * jobs[i].slot};
         return msm_run_many(ctx, pk->srs, mj, count);
     }
     // bring `count` XYZZ results back and normalise (into_affine)
     static int fetch_commits(jf_ctx *ctx, const jf_plonk_pk *pk, int slot, int count, uint64_t *xy, int *inf) {
         void *h;
-        JF_TRY(pinned(ctx, PT * count + 64, &h));
-        JF_CUDA(ctx, cudaMemcpyAsync(h, (char *)pk->d_res + PT * slot, PT * count, cudaMemcpyDeviceToHost, ctx->stream));
+        const int parts = pk->comm ? comm_size(pk->comm) : 1;
+        JF_TRY(pinned(ctx, PT * parts * count + 64, &h));
+        const char *src = (const char *)pk->d_res + PT * slot;
+        if (pk->comm) {
+            // always on the main stream, in program order: the mailbox protocol of the exchange needs one ordered stream
+            for (int i = 0; i < count; i++)
+                JF_TRY(comm_exchange_from(ctx, pk->comm, (const char *)pk->d_res + PT * (slot + i), PT,
+                                          (char *)pk->d_parts + PT * parts * (slot + i)));
+            src = (const char *)pk->d_parts + PT * parts * slot;
+        }
+        JF_CUDA(ctx, cudaMemcpyAsync(h, src, PT * parts * count, cudaMemcpyDeviceToHost, ctx->stream));
         int herr[2] = {0, 0};
         JF_CUDA(ctx, cudaMemcpyAsync(herr, ctx->d_err, sizeof herr, cudaMemcpyDeviceToHost, ctx->stream));
         JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (herr[0] || herr[1]) {
             cudaMemsetAsync(ctx->d_err, 0, sizeof herr, ctx->stream);
             if (herr[1]) return fail(ctx, herr[1], "prove: WrongQuotientPolyDegree (the witness does not satisfy the circuit)");
+            if (herr[0] == JF_ERR_COMM) return fail(ctx, herr[0], "prove: a peer did not deliver its partial commitment in time");
             return fail(ctx, herr[0], "prove: a scalar is not below the group order");
         }
         for (int i = 0; i < count; i++)
-            JF_TRY(msm_finish_host(ctx, pk->curve, (const uint64_t *)((const char *)h + PT * i), 1, xy + (size_t)2 * L * i, inf + i));
+            JF_TRY(msm_finish_host(ctx, pk->curve, (const uint64_t *)((const char *)h + PT * parts * i), parts, xy + (size_t)2 * L * i, inf + i));
         return JF_OK;
     }
 
@@ -2361,6 +2389,28 @@ int jf_kzg_open(jf_ctx *ctx, const jf_srs *srs, const uint64_t *const *polys, co
 }
 
 // ---- proof linking ----------------------------------------------------------------------------------
+int jf_plonk_pk_shard_commits(jf_ctx *ctx, jf_plonk_pk *pk, jf_comm *comm, const jf_srs *key_slice, size_t slice_start) {
+    JF_GUARD(ctx);
+    if (!pk) return fail(ctx, JF_ERR_INVALID_ARG, "shard_commits: null proving key");
+    if (!comm) {  // back to one GPU
+        pk->comm = nullptr;
+        pk->srs_slice = nullptr;
+        pk->shard_start = 0;
+        return JF_OK;
+    }
+    if (!key_slice || comm_ctx(comm) != ctx) return fail(ctx, JF_ERR_INVALID_ARG, "shard_commits: null key slice or a comm of another context");
+    if (key_slice->curve != pk->curve) return fail(ctx, JF_ERR_INVALID_ARG, "shard_commits: the key slice is over another curve");
+    if (comm_size(comm) > 16) return fail(ctx, JF_ERR_INVALID_ARG, "shard_commits: at most 16 ranks");
+    if (!pk->d_parts) {
+        const size_t pt = (size_t)key_slice->limbs64 * 32;
+        JF_TRY(dalloc(ctx, pk, pt * 32 * 16, &pk->d_parts));
+    }
+    pk->comm = comm;
+    pk->srs_slice = key_slice;
+    pk->shard_start = slice_start;
+    return JF_OK;
+}
+
 int jf_plonk_link_hint(jf_ctx *ctx, const jf_plonk_pk *pk, uint64_t *out_poly, size_t cap, size_t *out_len) {
     JF_GUARD(ctx);
     if (!pk || !out_poly || !out_len) return fail(ctx, JF_ERR_INVALID_ARG, "link_hint: null argument");

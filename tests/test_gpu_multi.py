@@ -122,3 +122,47 @@ def test_sharded_msm_one_process_per_gpu_nccl_and_p2p():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     for k in range(world):
         assert "rank %d ok" % k in r.stdout
+
+
+def test_sharded_prover_single_rank(ctx, co, py):
+    """`jf_plonk_pk_shard_commits` with one rank (slice == the whole key): the exchange path runs, the proof is unchanged"""
+    import random
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import mpc_jellyfish_b200 as jf
+    import plonk_ref as P
+    import plonk_util as U
+    cv, fr = py.BN254, py.BN254_FR
+    cs = P.gen_circuit_for_test(20, 1)
+    arr = U.arrays_from_oracle_circuit(co, py, cs)
+    key = ctx.generate_srs_for_testing("bn254", BETA, cs.n + 3)
+    pk = jf.PlonkKzgSnark.preprocess(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"], arr["pub_gate_ids"])
+    rnd = random.Random(5)
+    bl = co.ints_to_limbs([fr.to_mont(rnd.randrange(fr.p)) for _ in range(17)], 4)
+    want = jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, "solidity").serialize_compressed()
+    for transport in ("p2p", "nccl"):
+        comm = jf.Comm(ctx, 0, 1, jf.Comm.unique_id(), transport)
+        pk.shard_commits(comm, key, 0)
+        for _ in range(2):
+            assert jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, "solidity").serialize_compressed() == want
+        pk.shard_commits(None, None)
+        comm.close()
+    assert jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, "solidity").serialize_compressed() == want
+    pk.free()
+    key.free()
+
+
+def test_sharded_prover_one_process_per_gpu():
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2 if n < 4 else 4
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world,
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(ROOT, "tests", "multi", "prove_worker.py")],
+                       capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    for k in range(world):
+        assert "rank %d ok" % k in r.stdout
