@@ -407,16 +407,17 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
             ref_bytes = jf_mod().PlonkKzgSnark.prove(pk, wit, bl0, "solidity").serialize_compressed()
             a, b = shard_range(n + 3, world, rank)
             key_slice = ctx.generate_srs_for_testing("bn254", BETA % co_modulus(), b - a, first_power=a)
-            pk.shard_commits(comm, key_slice, a)
-            if jf_mod().PlonkKzgSnark.prove(pk, wit, bl0, "solidity").serialize_compressed() != ref_bytes:
-                raise SystemExit("bench.py: the proof with sharded commitments differs from the one-GPU proof; refusing to time it")
-            jf_mod().PlonkKzgSnark.prove(pk, wit, bl0, "solidity")
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(steps):
+            for rows, slot in ((False, "sharded_commits_only"), (True, "sharded")):
+                pk.shard_commits(comm, key_slice, a, shard_round3=rows)
+                if jf_mod().PlonkKzgSnark.prove(pk, wit, bl0, "solidity").serialize_compressed() != ref_bytes:
+                    raise SystemExit("bench.py: the sharded proof differs from the one-GPU proof; refusing to time it")
                 jf_mod().PlonkKzgSnark.prove(pk, wit, bl0, "solidity")
-            barrier()
-            out["sharded"] = max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    jf_mod().PlonkKzgSnark.prove(pk, wit, bl0, "solidity")
+                barrier()
+                out[slot] = max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
             pk.shard_commits(None, None)
             key_slice.free()
         pk.free()
@@ -497,9 +498,13 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
                                                       "resident (+3.4 GiB): only 7 polynomials are transformed per proof; same proof bytes"),
         "prove_2^16_gates_ms": prove16_ms,
         "one_proof_on_all_gpus": ({"value": out["sharded"], "unit": "ms", "n_gpus": world, "scaling": "strong",
-                                   "note": "every rank runs the same jf_plonk_prove call and commits 1/%d of every polynomial "
-                                           "(jf_plonk_pk_shard_commits: the 13 MSMs split by point range, partials over %s; transforms "
-                                           "and polynomial algebra replicated); bytes equal the one-GPU proof" % (world, comm.transport)}
+                                   "commitments_only_ms": out["sharded_commits_only"],
+                                   "note": "every rank runs the same jf_plonk_prove call, commits 1/%d of every polynomial "
+                                           "(jf_plonk_pk_shard_commits: the 13 MSMs split by point range, partials over %s) and handles "
+                                           "the sub-cosets r = rank mod %d of round 3 (25 transforms, the quotient kernel and the inverse "
+                                           "transform per sub-coset; the six n-coefficient interpolants are broadcast over NVLink before the "
+                                           "solve); rounds 1, 2, 4, 5 are replicated; bytes equal the one-GPU proof.  commitments_only_ms: "
+                                           "without the round-3 split" % (world, comm.transport, world)}
                                   if "sharded" in out else None),
         "ultraplonk_2^20_gates": ultra,
         "cpu_baseline": cpu,

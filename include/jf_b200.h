@@ -326,8 +326,13 @@ long jf_ultraplonk_batch_proof_serialize(const jf_ultraplonk_proof *proofs, size
  * cross NVLink (peer-memory mailboxes or ncclAllGather) before each commitment is normalised, so every rank sees the same
  * commitments, squeezes the same challenges and returns the same proof.  The 13 MSMs of a TurboPlonk proof then cost 1/nranks of
  * their accumulation each.  `pk` was built with the FULL key (jf_plonk_preprocess is not collective); comm == NULL returns the key to
- * one-GPU operation.  Calls are collective: the ranks must issue them in the same order. */
-int jf_plonk_pk_shard_commits(jf_ctx *ctx, jf_plonk_pk *pk, jf_comm *comm, const jf_srs *key_slice, size_t slice_start);
+ * one-GPU operation.  Calls are collective: the ranks must issue them in the same order.
+ * shard_round3 != 0 additionally deals out round 3 by sub-coset: the quotient is evaluated on 6 (UltraPlonk: 7) cosets of n points
+ * that do not interact until the final Vandermonde solve, so rank r mod nranks transforms the 25 (35) polynomials onto coset r only,
+ * evaluates the quotient there and transforms it back; the n-coefficient interpolants of the rows are then broadcast (NCCL over
+ * NVLink: 32 n bytes per row) and every rank solves for the same quotient polynomial.  Ignored for keys built with flags & 1
+ * (resident coset evaluations) or flags & 4 / n < 16 (8n-point coset). */
+int jf_plonk_pk_shard_commits(jf_ctx *ctx, jf_plonk_pk *pk, jf_comm *comm, const jf_srs *key_slice, size_t slice_start, int shard_round3);
 
 /* ---- proof linking ------------------------------------------------------------------------------------------------------------
  * `PlonkKzgSnark::link_proofs` (plonk/src/proof_system/proof_linking.rs:79-216): two TurboPlonk proofs whose circuits placed the

@@ -164,7 +164,8 @@ SIGNATURES = {
     "jf_plonk_prove": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64p, c_u64p, ctypes.c_int, ctypes.c_char_p,
                                       ctypes.c_size_t, ctypes.POINTER(PlonkProofStruct)]),
     "jf_plonk_proof_serialize": (ctypes.c_long, [ctypes.POINTER(PlonkProofStruct), ctypes.c_char_p, ctypes.c_size_t]),
-    "jf_plonk_pk_shard_commits": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "jf_plonk_pk_shard_commits": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                 ctypes.c_int]),
     "jf_plonk_link_hint": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     "jf_plonk_link_proofs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_u64p, ctypes.c_size_t, c_u64p, ctypes.c_int, c_u64p,
                                             ctypes.c_size_t, c_u64p, ctypes.c_int, ctypes.c_uint, ctypes.c_size_t, ctypes.c_size_t,

@@ -31,6 +31,9 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     std::string err;
 };
@@ -55,8 +58,12 @@ static NcclApi *nccl_api() {
         api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
         api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
         api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
+        api.Broadcast = (decltype(api.Broadcast))dlsym(api.handle, "ncclBroadcast");
+        api.GroupStart = (decltype(api.GroupStart))dlsym(api.handle, "ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.handle, "ncclGroupEnd");
         api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
-        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GetErrorString) {
+        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GetErrorString || !api.Broadcast ||
+            !api.GroupStart || !api.GroupEnd) {
             api.err = "libnccl.so.2 lacks an expected symbol";
             api.handle = nullptr;
         }
@@ -251,6 +258,22 @@ int comm_exchange_from(jf_ctx *ctx, jf_comm *c, const void *d_part, size_t pt, v
     return JF_OK;  // NCCL's kernel, not ours: not counted in jf_ctx_launch_count
 }
 int comm_size(const jf_comm *c) { return c->nranks; }
+int comm_rank(const jf_comm *c) { return c->rank; }
+// Rows dealt out round-robin (row r lives on rank r mod nranks, as that rank's local row r / nranks) -> all `rows` rows, in order,
+// on every rank: one grouped NCCL broadcast per row over NVLink (bulk data: the mailboxes only carry 192-byte partials).
+int comm_bcast_rows(jf_ctx *ctx, jf_comm *c, const void *d_local_rows, void *d_all_rows, size_t row_bytes, int rows) {
+    NcclApi *api = nccl_api();
+    if (!api) return fail(ctx, JF_ERR_COMM, "NCCL is not available");
+    JF_NCCL(ctx, api, api->GroupStart());
+    for (int r = 0; r < rows; r++) {
+        const int root = r % c->nranks;
+        char *dst = (char *)d_all_rows + (size_t)r * row_bytes;
+        const void *src = root == c->rank ? (const char *)d_local_rows + (size_t)(r / c->nranks) * row_bytes : dst;
+        JF_NCCL(ctx, api, api->Broadcast(src, dst, row_bytes, ncclChar, root, c->nccl, ctx->stream));
+    }
+    JF_NCCL(ctx, api, api->GroupEnd());
+    return JF_OK;
+}
 jf_ctx *comm_ctx(const jf_comm *c) { return c->ctx; }
 static int comm_exchange(jf_ctx *ctx, jf_comm *c, size_t pt, void *d_out_parts) { return comm_exchange_from(ctx, c, c->d_part, pt, d_out_parts); }
 

@@ -187,6 +187,8 @@ int msm_finish_host(jf_ctx *ctx, int curve, const uint64_t *xyzz_parts, size_t p
 // comm.cu: all-gather of one XYZZ partial per rank (mailboxes over peer memory, or ncclAllGather); see comm_exchange_from there
 int comm_exchange_from(jf_ctx *ctx, jf_comm *c, const void *d_part, size_t pt, void *d_out_parts);
 int comm_size(const jf_comm *c);
+int comm_rank(const jf_comm *c);
+int comm_bcast_rows(jf_ctx *ctx, jf_comm *c, const void *d_local_rows, void *d_all_rows, size_t row_bytes, int rows);
 jf_ctx *comm_ctx(const jf_comm *c);
 int srs_build(jf_ctx *ctx, int curve, const void *d_base_points /* n affine, device */, size_t n, int window_bits,
               int precompute, jf_srs **out);

@@ -298,6 +298,9 @@ template <class F, int NW> struct QuotArgs {
     // sub != 0: the evaluations are laid out by sub-coset, position r n + j <-> the point g w_8n^(8 j + r), r < sub.
     // Within a row the domain generator w_n is a shift by one, and X^n - 1 is the constant 1 / zh_inv[r].
     uint32_t sub, log_n;
+    // row_map[l]: the sub-coset held in local row l.  Identity unless round 3 is dealt out over several GPUs
+    // (jf_plonk_pk_shard_commits), where a rank holds only some of the rows; inv_nx1 always covers all of them.
+    uint32_t row_map[8];
 };
 template <class F> __device__ __forceinline__ Fp<F> pow5(const Fp<F> &x) {
     Fp<F> x2 = Fp<F>::sqr(x);
@@ -340,15 +343,18 @@ template <class F, int NW> __global__ void __launch_bounds__(128) quotient_kerne
     if (on(9)) t = E::add(t, E::mul(S(9), pow5(w[3])));
     if (on(10)) t = E::sub(t, E::mul(S(10), w[4]));
     // copy constraints (prover.rs:743-756)
-    uint32_t xi = i, inext = i + q.ratio, row = 0;
+    uint32_t xi = i, inext = i + q.ratio, row = 0, gi = i, ginext;
     if (q.sub) {
         const uint32_t nmask = (1u << q.log_n) - 1, jj = i & nmask;
-        row = i >> q.log_n;
+        row = q.row_map[i >> q.log_n];
         xi = (jj << 3) | row;
         inext = (i & ~nmask) | ((jj + 1) & nmask);
+        gi = (row << q.log_n) | jj;  // position in the per-key table, which holds every sub-coset
+        ginext = (row << q.log_n) | ((jj + 1) & nmask);
     } else {
         if (inext >= q.m) inext -= q.m;
         row = i % q.ratio;
+        ginext = inext;
     }
     const E x = E::mul(ldf(q.x_lo + (xi & ((1u << q.lo_bits) - 1))), ldf(q.x_hi + (xi >> q.lo_bits)));
     const E zx = ldf(q.z + i);
@@ -360,12 +366,12 @@ template <class F, int NW> __global__ void __launch_bounds__(128) quotient_kerne
         r2 = E::mul(r2, E::add(wg, E::mul(q.beta, ldf(q.sig + j * m + i))));
     }
     t = E::add(t, E::mul(q.alpha, E::sub(r1, r2)));
-    E t2 = E::mul(E::mul(q.alpha2, E::sub(zx, E::one())), ldf(q.inv_nx1 + i));
+    E t2 = E::mul(E::mul(q.alpha2, E::sub(zx, E::one())), ldf(q.inv_nx1 + gi));
     if constexpr (NW == NW_ULTRA) {
         // Plookup (prover.rs:773-888).  L_1 / Z_H = 1 / (n (x - 1)) = inv_nx1[i]; L_n / Z_H = w^-1 / (n (x - w^-1)) = 1 / (n (w x - 1))
         // = inv_nx1[inext], because w x is the point one domain step further on the coset.
         const LookupQuot<F> &k = q.lk;
-        const E lag1 = ldf(q.inv_nx1 + i), lagn = ldf(q.inv_nx1 + inext);
+        const E lag1 = ldf(q.inv_nx1 + gi), lagn = ldf(q.inv_nx1 + ginext);
         const E ql = S(13), ql_n = ldf(q.sel + 13 * m + inext);
         const E h1x = ldf(k.h1 + i), h1n = ldf(k.h1 + inext), h2x = ldf(k.h2 + i), h2n = ldf(k.h2 + inext);
         const E px = ldf(k.pl + i), pn = ldf(k.pl + inext);
@@ -755,6 +761,11 @@ struct jf_plonk_pk {
     const jf_srs *srs_slice = nullptr;
     size_t shard_start = 0;
     void *d_parts = nullptr;  // 32 slots x nranks partials
+    // ... and round 3 dealt out by sub-coset: this rank transforms / evaluates only rows_local of the `sub` rows (row r lives on
+    // rank r mod nranks); the rows' interpolants are broadcast before the Vandermonde solve
+    int shard_rows = 0, rows_local = 0;
+    int row_map[jf::SUB_MAX] = {0};
+    uint64_t sub_off_local[jf::SUB_MAX * 4];
     int proofs_done = 0;    // batch_prove calls that left their wire polynomials in d_w (jf_plonk_link_hint, proof linking)
     uint32_t zero_sel = 0;  // selectors that are identically zero (flags & 2)
     int skip_zero = 0;      // flags & 2: zero polynomials (such selectors; PI without public inputs) are not transformed
@@ -1237,6 +1248,11 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
         return JF_OK;
     }
 
+    // sub-coset rows this GPU holds (all of them unless round 3 is dealt out over several GPUs)
+    static int rows_eff(const jf_plonk_pk *pk) { return pk->shard_rows ? pk->rows_local : pk->sub; }
+    static size_t mq_eff(const jf_plonk_pk *pk) { return pk->shard_rows ? (size_t)pk->rows_local * pk->n : pk->mq; }
+    static const uint64_t *offs_eff(const jf_plonk_pk *pk) { return pk->shard_rows ? pk->sub_off_local : pk->sub_off; }
+
     // rows of coefficients (`len` valid, `stride` apart) -> rows of m coset evaluations in `dst`
     // Rows whose bit is set in `skip` are zero polynomials: their (all-zero) evaluations are never read.
     static int coset_fft_rows(jf_ctx *ctx, const jf_plonk_pk *pk, const E *src, size_t stride, size_t len, int rows, E *dst,
@@ -1245,6 +1261,7 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
         if (pk->sub) {
             // sub-coset form: row r of the result holds the polynomial on the cosets (g w_m^s) <w_n>, s < sub, n points each;
             // the transform reads the coefficients where they are (reduced mod X^n - c_s on the way in)
+            if (rows_eff(pk) == 0) return JF_OK;  // round 3 dealt out over more GPUs than there are sub-cosets: nothing here
             int r = 0;
             while (r < rows) {
                 if ((skip >> r) & 1u) {
@@ -1253,8 +1270,8 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
                 }
                 int b = 1;
                 while (b < 5 && r + b < rows && !((skip >> (r + b)) & 1u)) b++;
-                JF_TRY(ntt_run_cosets(ctx, C::FR_ID, src + (size_t)r * stride, stride, len, dst + (size_t)r * pk->mq, pk->log_n, 0,
-                                      pk->sub_off, pk->sub, b));
+                JF_TRY(ntt_run_cosets(ctx, C::FR_ID, src + (size_t)r * stride, stride, len, dst + (size_t)r * mq_eff(pk), pk->log_n, 0,
+                                      offs_eff(pk), rows_eff(pk), b));
                 r += b;
             }
             return JF_OK;
@@ -1378,13 +1395,15 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
         // The side-stream work of EVERY instance goes to the first key's side stream: the context keeps one set of scratch
         // buffers per lane (main / side), so two side streams working at once would share them.
         jf_plonk_pk *pk0 = pks[0];
-        const size_t n = pk0->n, m = pk0->mq, np = pk0->np;  // m: evaluation points per polynomial in round 3
+        const size_t n = pk0->n, m = mq_eff(pk0), np = pk0->np;  // m: evaluation points per polynomial in round 3 (on this GPU)
         const size_t fe = sizeof(E);
         cudaStream_t st = ctx->stream;
         for (size_t i = 0; i < count; i++) {  // snark.rs:226-260
             const jf_plonk_pk *pk = pks[i];
             if (pk->nw != NW || pk->curve != pk0->curve) return fail(ctx, JF_ERR_INVALID_ARG, "batch_prove: inconsistent plonk circuit types");
             if (pk->n != n || pk->sub != pk0->sub) return fail(ctx, JF_ERR_INVALID_ARG, "batch_prove: proving key domain size differs from the expected domain size");
+            if (pk->comm != pk0->comm || pk->shard_rows != pk0->shard_rows || pk->shard_start != pk0->shard_start || pk->srs_slice != pk0->srs_slice)
+                return fail(ctx, JF_ERR_INVALID_ARG, "batch_prove: the instances must be sharded alike (jf_plonk_pk_shard_commits)");
             if (pk->srs != pk0->srs) return fail(ctx, JF_ERR_INVALID_ARG, "batch_prove: the instances must share one commit key");
             for (size_t j = 0; j < i; j++)
                 if (pks[j] == pk) return fail(ctx, JF_ERR_INVALID_ARG, "batch_prove: every instance needs its own proving key (workspace)");
@@ -1607,15 +1626,22 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
                 q.zero_sel = pk->zero_sel;
                 q.sub = (uint32_t)pk->sub;
                 q.log_n = pk->log_n;
-                JF_LAUNCH(ctx, "quotient", quotient_kernel<Fr, NW><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(q));
+                for (int r = 0; r < 8; r++) q.row_map[r] = pk->shard_rows ? (uint32_t)pk->row_map[r < SUB_MAX ? r : 0] : (uint32_t)r;
+                if (m) JF_LAUNCH(ctx, "quotient", quotient_kernel<Fr, NW><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(q));
                 alpha_base = E::mul(alpha_base, alpha_step);
             }
             jf_plonk_pk *pk = pk0;
             const E *T = (const E *)pk->d_q;  // quotient coefficients
+            const size_t m_full = pk->mq;
             if (pk->sub) {
-                JF_TRY(ntt_run_cosets(ctx, C::FR_ID, pk->d_q, n, n, pk->d_q, pk->log_n, 1, pk->sub_off, pk->sub, 1));
+                if (rows_eff(pk)) JF_TRY(ntt_run_cosets(ctx, C::FR_ID, pk->d_q, n, n, pk->d_q, pk->log_n, 1, offs_eff(pk), rows_eff(pk), 1));
                 SolveArgs<Fr, SUB> sa;
                 sa.T = (const E *)pk->d_q;
+                if (pk->shard_rows) {
+                    // every rank needs every row's interpolant: row r travels from rank r mod nranks (NVLink, one grouped broadcast)
+                    JF_TRY(comm_bcast_rows(ctx, pk->comm, pk->d_q, pk->d_b, fe * n, pk->sub));
+                    sa.T = (const E *)pk->d_b;  // free since round 2.5
+                }
                 sa.t = (E *)pk->d_a;  // free since round 2
                 sa.n = (uint32_t)n;
                 memcpy(sa.vinv, pk->vinv, sizeof sa.vinv);  // row-major SUB x SUB on both sides
@@ -1624,7 +1650,7 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
             } else {
                 JF_TRY(ntt_run(ctx, C::FR_ID, pk->d_q, pk->d_q, m, pk->log_m, 1, pk->gen_limbs, 1, m));
             }
-            JF_LAUNCH(ctx, "degree_check", degree_check_kernel<Fr><<<(unsigned)((m - deg + 255) / 256), 256, 0, st>>>(T, deg, m, ctx->d_err + 1));
+            JF_LAUNCH(ctx, "degree_check", degree_check_kernel<Fr><<<(unsigned)((m_full - deg + 255) / 256), 256, 0, st>>>(T, deg, m_full, ctx->d_err + 1));
             dim3 grid((unsigned)((np + 255) / 256), NW);
             JF_LAUNCH(ctx, "split", split_kernel<Fr, NW><<<grid, 256, 0, st>>>(T, n, deg + 1, bl_split, (E *)pk->d_split, np));
             CommitJob jobs[NW];
@@ -2389,13 +2415,14 @@ int jf_kzg_open(jf_ctx *ctx, const jf_srs *srs, const uint64_t *const *polys, co
 }
 
 // ---- proof linking ----------------------------------------------------------------------------------
-int jf_plonk_pk_shard_commits(jf_ctx *ctx, jf_plonk_pk *pk, jf_comm *comm, const jf_srs *key_slice, size_t slice_start) {
+int jf_plonk_pk_shard_commits(jf_ctx *ctx, jf_plonk_pk *pk, jf_comm *comm, const jf_srs *key_slice, size_t slice_start, int shard_round3) {
     JF_GUARD(ctx);
     if (!pk) return fail(ctx, JF_ERR_INVALID_ARG, "shard_commits: null proving key");
     if (!comm) {  // back to one GPU
         pk->comm = nullptr;
         pk->srs_slice = nullptr;
         pk->shard_start = 0;
+        pk->shard_rows = pk->rows_local = 0;
         return JF_OK;
     }
     if (!key_slice || comm_ctx(comm) != ctx) return fail(ctx, JF_ERR_INVALID_ARG, "shard_commits: null key slice or a comm of another context");
@@ -2408,6 +2435,16 @@ int jf_plonk_pk_shard_commits(jf_ctx *ctx, jf_plonk_pk *pk, jf_comm *comm, const
     pk->comm = comm;
     pk->srs_slice = key_slice;
     pk->shard_start = slice_start;
+    pk->shard_rows = pk->rows_local = 0;
+    // round 3 by sub-coset: only in the sub-coset form, and not with resident coset evaluations (they are laid out for all rows)
+    if (shard_round3 && pk->sub && !pk->cache_coset && comm_size(comm) > 1) {
+        pk->shard_rows = 1;
+        for (int r = comm_rank(comm); r < pk->sub; r += comm_size(comm)) {
+            pk->row_map[pk->rows_local] = r;
+            memcpy(pk->sub_off_local + 4 * pk->rows_local, pk->sub_off + 4 * r, 32);
+            pk->rows_local++;
+        }
+    }
     return JF_OK;
 }
 

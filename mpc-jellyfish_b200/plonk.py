@@ -169,13 +169,14 @@ class ProvingKey:
         self.plookup_comms = xy[ns + nw:] if ultra else None
         self.plookup_inf = [bool(v) for v in inf[ns + nw:]] if ultra else None
 
-    def shard_commits(self, comm, key_slice: Optional[CommitKey], slice_start: int = 0):
+    def shard_commits(self, comm, key_slice: Optional[CommitKey], slice_start: int = 0, shard_round3: bool = True):
         """ONE proof on several GPUs (`jf_plonk_pk_shard_commits`): from now on every rank runs the same prove call and commits
-        only coefficients [slice_start, slice_start + len(key_slice)); comm = None returns to one-GPU operation.  `comm`:
-        `mpc_jellyfish_b200.sharded.Comm`."""
+        only coefficients [slice_start, slice_start + len(key_slice)); with shard_round3 the sub-cosets of round 3 are dealt out over
+        the ranks as well.  comm = None returns to one-GPU operation.  `comm`: `mpc_jellyfish_b200.sharded.Comm`."""
         self._comm, self._key_slice = comm, key_slice   # keep them alive
         self.ctx._check(self.ctx._lib.jf_plonk_pk_shard_commits(self.ctx._h, self._h, comm._h if comm is not None else None,
-                                                                key_slice._h if key_slice is not None else None, slice_start))
+                                                                key_slice._h if key_slice is not None else None, slice_start,
+                                                                int(shard_round3)))
 
     def free(self):
         if self._h is not None and self.ctx._h:

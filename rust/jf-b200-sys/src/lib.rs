@@ -156,7 +156,7 @@ extern "C" {
     pub fn jf_plonk_proof_serialize(proof: *const jf_plonk_proof, out: *mut u8, cap: usize) -> c_long;
 
     pub fn jf_plonk_pk_shard_commits(ctx: *mut jf_ctx, pk: *mut jf_plonk_pk, comm: *mut jf_comm, key_slice: *const jf_srs,
-                                     slice_start: usize) -> c_int;
+                                     slice_start: usize, shard_round3: c_int) -> c_int;
     pub fn jf_plonk_link_hint(ctx: *mut jf_ctx, pk: *const jf_plonk_pk, out_poly: *mut u64, cap: usize, out_len: *mut usize) -> c_int;
     pub fn jf_plonk_link_proofs(ctx: *mut jf_ctx, srs: *const jf_srs, a1: *const u64, len1: usize, a1_comm_xy: *const u64, a1_inf: c_int,
                                 a2: *const u64, len2: usize, a2_comm_xy: *const u64, a2_inf: c_int, alignment: c_uint, offset: usize,

@@ -3,7 +3,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port P tests/multi/prove_worker.py
 
 `jf_plonk_pk_shard_commits`: every rank runs the same prove call and commits only its slice of every polynomial against its slice
-of the key.  Checked on EVERY rank: the proof bytes equal the CPU restatement's (TurboPlonk, UltraPlonk, a batch of two, both
+of the key; with shard_round3 the sub-cosets of round 3 are dealt out over the ranks too (interpolants broadcast before the solve).  Checked on EVERY rank: the proof bytes equal the CPU restatement's (TurboPlonk, UltraPlonk, a batch of two, both
 transports, ragged slices incl. an empty one), and equal the one-GPU proof of the same key after un-sharding.
 """
 import os
@@ -66,10 +66,11 @@ def main():
             prove = jf.PlonkKzgSnark.prove_ultra if ultra else jf.PlonkKzgSnark.prove
             for kind in ("solidity", "standard"):
                 want = P.serialize_proof(cv, P.prove(cv, cs, opk, ints, kind))
-                pk.shard_commits(comm, key_slice, a)
-                for it in range(3):                       # back-to-back: both mailbox parities
-                    got = prove(pk, arr["witness"], bl, kind).serialize_compressed()
-                    assert got == want, "%s %s %s sharded proof differs (call %d)" % (transport, name, kind, it)
+                for rows in (False, True):                    # commitments only / commitments + round 3 by sub-coset
+                    pk.shard_commits(comm, key_slice, a, shard_round3=rows)
+                    for it in range(3):                       # back-to-back: both mailbox parities
+                        got = prove(pk, arr["witness"], bl, kind).serialize_compressed()
+                        assert got == want, "%s %s %s sharded proof differs (rows=%s, call %d)" % (transport, name, kind, rows, it)
                 pk.shard_commits(None, None)
                 assert prove(pk, arr["witness"], bl, kind).serialize_compressed() == want, "one-GPU proof after un-sharding"
             if name == "test_m20":                        # a batch of two instances through the sharded commitments
