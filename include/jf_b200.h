@@ -366,6 +366,13 @@ int jf_plonk_link_proofs(jf_ctx *ctx, const jf_srs *srs, const uint64_t *a1, siz
 int jf_plonk_link_proofs_resident(jf_ctx *ctx, const jf_plonk_pk *lhs, const jf_plonk_proof *lhs_proof, const jf_plonk_pk *rhs,
                                   const jf_plonk_proof *rhs_proof, unsigned alignment, size_t offset, size_t size, int transcript_kind,
                                   int flags, jf_link_proof *out);
+/* floor(p / Z_D) for `batch` polynomials (host memory, lens[i] Montgomery coefficients; out_quotients[i] receives
+ * max(lens[i] - size, 0)).  Division by the PUBLIC vanishing polynomial is linear, so the collaborative prover's
+ * `compute_linking_quotient` (plonk/src/multiprover/proof_system/proof_linking.rs:127-138) is this call on the share, the MAC and the
+ * public-modifier vector of a1 - a2; the shares' remainders do not vanish one by one, so they take the linear-division path unless
+ * the polynomial happens to vanish on the group.  flags as jf_plonk_link_proofs.  field: JF_BN254_FR / JF_BLS12_381_FR. */
+int jf_poly_div_link_domain(jf_ctx *ctx, int field, const uint64_t *const *polys, const size_t *lens, size_t batch, unsigned alignment,
+                            size_t offset, size_t size, int flags, uint64_t *const *out_quotients);
 /* ark-serialize `serialize_compressed` of `LinkingProof<E>`: 64 bytes (BN254) / 96 (BLS12-381); returns the count or < 0 */
 long jf_link_proof_serialize(const jf_link_proof *proof, uint8_t *out, size_t cap);
 

@@ -10,8 +10,8 @@ from .context import CommitKey, Context
 from .domain import Radix2EvaluationDomain
 from .errors import (DomainCreationError, InvalidParameters, PCSError, PlonkError, UpstreamError,
                      WrongQuotientPolyDegree)
-from .multiprover import (AuthenticatedDensePoly, AuthenticatedPointShare, MultiproverKZG, fft_with_domain,
-                          ifft_with_domain)
+from .multiprover import (AuthenticatedDensePoly, AuthenticatedPointShare, MpcLinkingHint, MultiproverKZG, MultiproverLinking,
+                          fft_with_domain, ifft_with_domain)
 from .plonk import (BatchProof, GroupLayout, LinkingHint, LinkingProof, PlonkKzgSnark, Proof, ProvingKey, Transcript,
                     keccak256)
 from .sharded import Comm, Group, GroupKey, ShardedMsm, combine_partials, poly_owner, shard_range
@@ -21,6 +21,6 @@ __all__ = [
     "Context", "CommitKey", "Radix2EvaluationDomain", "UnivariateKzgPCS", "UnivariateProverParam",
     "DensePolynomial", "Commitment", "PCSError", "InvalidParameters", "UpstreamError", "PlonkError",
     "DomainCreationError", "WrongQuotientPolyDegree", "PlonkKzgSnark", "Proof", "BatchProof", "GroupLayout", "LinkingHint", "LinkingProof", "ProvingKey", "Transcript", "keccak256",
-    "MultiproverKZG", "AuthenticatedDensePoly", "AuthenticatedPointShare", "fft_with_domain", "ifft_with_domain",
+    "MultiproverKZG", "MultiproverLinking", "MpcLinkingHint", "AuthenticatedDensePoly", "AuthenticatedPointShare", "fft_with_domain", "ifft_with_domain",
     "ShardedMsm", "Comm", "Group", "GroupKey", "combine_partials", "poly_owner", "shard_range",
 ]

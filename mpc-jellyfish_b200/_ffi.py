@@ -173,6 +173,9 @@ SIGNATURES = {
     "jf_plonk_link_proofs_resident": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(PlonkProofStruct), ctypes.c_void_p,
                                                      ctypes.POINTER(PlonkProofStruct), ctypes.c_uint, ctypes.c_size_t, ctypes.c_size_t,
                                                      ctypes.c_int, ctypes.c_int, ctypes.POINTER(LinkProofStruct)]),
+    "jf_poly_div_link_domain": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(c_u64p), ctypes.POINTER(ctypes.c_size_t),
+                                               ctypes.c_size_t, ctypes.c_uint, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
+                                               ctypes.POINTER(c_u64p)]),
     "jf_link_proof_serialize": (ctypes.c_long, [ctypes.POINTER(LinkProofStruct), ctypes.c_char_p, ctypes.c_size_t]),
     "jf_keccak256": (None, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]),
     "jf_transcript_new": (ctypes.c_void_p, [ctypes.c_int, ctypes.c_char_p]),

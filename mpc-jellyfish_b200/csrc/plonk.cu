@@ -1987,47 +1987,47 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
         return z;
     }
 
-    struct LinkOut {
-        uint64_t q_xy[12], open_xy[12], eta[4];
-        int q_inf, open_inf, path;
+    // scratch of the linking quotient: diff = the dividend (max_len coefficients), A / B ping-pong or transform buffers, T / S scan
+    // buffers, each max(max_len, N) + 8 elements
+    struct LinkBufs {
+        E *diff, *A, *B, *T, *S, *tmp, *small;
+        int *flag;
     };
-    static int link_proofs(jf_ctx *ctx, const jf_srs *srs, const E *d_a1, size_t len1, const uint64_t *a1_comm, int a1_inf,
-                           const E *d_a2, size_t len2, const uint64_t *a2_comm, int a2_inf, unsigned alignment, size_t offset,
-                           size_t size, int kind, int flags, LinkOut *out) {
-        if (alignment > (unsigned)Fr::TWO_ADICITY || alignment > 30)
-            return fail(ctx, JF_ERR_DOMAIN_TOO_LARGE, "link_proofs: the group alignment exceeds the field's two-adicity");
-        if (size == 0 || offset + size >= ((size_t)1 << alignment))  // validate_layout (linkable_circuit.rs:352-370)
-            return fail(ctx, JF_ERR_INVALID_ARG, "link_proofs: the link group is empty or exceeds its alignment");
-        const size_t max_len = std::max(len1, len2);
-        if (max_len > srs->n + 1) return fail(ctx, JF_ERR_INVALID_ARG, "link_proofs: polynomial degree exceeds the commit key");
-        const size_t fe = sizeof(E);
-        cudaStream_t st = ctx->stream;
-        const E g = root_of_unity(alignment);
-        const E r0 = pow_small(g, (uint64_t)offset);
-        memset(out, 0, sizeof *out);
+    static unsigned link_log_N(size_t max_len, unsigned alignment, size_t size) {
         const size_t qlen = max_len > size ? max_len - size : 0;
         unsigned log_N = alignment;
         while (((size_t)1 << log_N) < std::max(qlen, size + 1)) log_N++;
-        const size_t N = (size_t)1 << log_N;
-        bool fast = !(flags & 1) && qlen > 0 && log_N <= (unsigned)Fr::TWO_ADICITY && log_N <= 27;
-        const size_t cap = std::max(max_len, fast ? N : (size_t)0) + 8;
-        void *p_diff, *p_a, *p_b, *p_t, *p_s, *p_tmp, *p_res, *p_flag;
+        return log_N;
+    }
+    static int link_bufs(jf_ctx *ctx, size_t max_len, unsigned alignment, size_t size, int flags, LinkBufs *lb) {
+        const size_t fe = sizeof(E);
+        const unsigned log_N = link_log_N(max_len, alignment, size);
+        const bool may_be_fast = !(flags & 1) && max_len > size && log_N <= (unsigned)Fr::TWO_ADICITY && log_N <= 27;
+        const size_t cap = std::max(max_len, may_be_fast ? (size_t)1 << log_N : (size_t)0) + 8;
+        void *p_diff, *p_a, *p_b, *p_t, *p_s, *p_tmp, *p_small;
         JF_TRY(scratch(ctx, "link_diff", fe * cap, &p_diff));
         JF_TRY(scratch(ctx, "link_a", fe * cap, &p_a));
         JF_TRY(scratch(ctx, "link_b", fe * cap, &p_b));
         JF_TRY(scratch(ctx, "link_t", fe * cap, &p_t));
         JF_TRY(scratch(ctx, "link_s", fe * cap, &p_s));
         JF_TRY(scratch(ctx, "link_tmp", fe * (cap / 256 + 4096), &p_tmp));
-        JF_TRY(scratch(ctx, "link_res", 2 * PT + fe, &p_res));
-        JF_TRY(scratch(ctx, "link_flag", 64, &p_flag));
-        E *diff = (E *)p_diff, *A = (E *)p_a, *B = (E *)p_b, *T = (E *)p_t, *S = (E *)p_s, *tmp = (E *)p_tmp;
-        E *small = (E *)((char *)p_res + 2 * PT);
-        int *d_flag = (int *)p_flag;
-        // a1 - a2
-        if (max_len) {
-            std::vector<Term> terms = {{d_a1, len1, E::one()}, {d_a2, len2, E::neg(E::one())}};
-            JF_TRY(lincomb_many(ctx, terms, diff, max_len));
-        }
+        JF_TRY(scratch(ctx, "link_small", fe + 64, &p_small));
+        *lb = LinkBufs{(E *)p_diff, (E *)p_a, (E *)p_b, (E *)p_t, (E *)p_s, (E *)p_tmp, (E *)p_small, (int *)((char *)p_small + fe)};
+        return JF_OK;
+    }
+    // *Q (one of lb.A / lb.B, *q_len coefficients) = floor(lb.diff / Z_D); *path: 0 exact division on a coset, 1 linear divisions
+    static int link_quotient(jf_ctx *ctx, const LinkBufs &lb, size_t max_len, unsigned alignment, size_t offset, size_t size, int flags,
+                             E **Q_out, size_t *q_len_out, int *path) {
+        const size_t fe = sizeof(E);
+        cudaStream_t st = ctx->stream;
+        E *diff = lb.diff, *A = lb.A, *B = lb.B, *T = lb.T, *S = lb.S, *tmp = lb.tmp, *small = lb.small;
+        int *d_flag = lb.flag;
+        const E g = root_of_unity(alignment);
+        const E r0 = pow_small(g, (uint64_t)offset);
+        const size_t qlen = max_len > size ? max_len - size : 0;
+        const unsigned log_N = link_log_N(max_len, alignment, size);
+        const size_t N = (size_t)1 << log_N;
+        bool fast = !(flags & 1) && qlen > 0 && log_N <= (unsigned)Fr::TWO_ADICITY && log_N <= 27;
         const E gen = E::from_u32(Fr::GENERATOR);
         uint64_t gen_limbs[4];
         H::fr_to_limbs(gen, gen_limbs);
@@ -2045,7 +2045,7 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
         E *Q = A;  // quotient coefficients
         size_t q_len = qlen;
         if (fast) {
-            out->path = 0;
+            *path = 0;
             const std::vector<E> z = vanishing_coeffs(g, offset, size);
             JF_LAUNCH(ctx, "fold", fold_kernel<Fr><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(diff, max_len, N, pow_small(gen, (uint64_t)N), A));
             JF_TRY(ntt_run(ctx, C::FR_ID, A, A, N, log_N, 0, gen_limbs, 1, N));
@@ -2061,7 +2061,7 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
             JF_LAUNCH(ctx, "vmul", vmul_kernel<Fr><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(A, B, A, N));
             JF_TRY(ntt_run(ctx, C::FR_ID, A, A, N, log_N, 1, gen_limbs, 1, N));
         } else {
-            out->path = 1;
+            *path = 1;
             // floor((a1 - a2) / Z_D) as `size` divisions by a linear factor
             const E *cur = diff;
             size_t len = max_len;
@@ -2089,6 +2089,72 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
             Q = const_cast<E *>(cur);
             if (q_len == 0) Q = A;
         }
+        *Q_out = Q;
+        *q_len_out = q_len;
+        return JF_OK;
+    }
+
+    // floor(p / Z_D) for `batch` polynomials in host memory (division by the PUBLIC vanishing polynomial of a link group is linear,
+    // so the collaborative prover applies it to every component of its shares: multiprover/proof_system/proof_linking.rs:127-138).
+    // outs[i] receives max(lens[i] - size, 0) coefficients.
+    static int div_link_domain(jf_ctx *ctx, const uint64_t *const *polys, const size_t *lens, size_t batch, unsigned alignment,
+                               size_t offset, size_t size, int flags, uint64_t *const *outs) {
+        if (alignment > (unsigned)Fr::TWO_ADICITY || alignment > 30)
+            return fail(ctx, JF_ERR_DOMAIN_TOO_LARGE, "div_link_domain: the group alignment exceeds the field's two-adicity");
+        if (size == 0 || offset + size >= ((size_t)1 << alignment))
+            return fail(ctx, JF_ERR_INVALID_ARG, "div_link_domain: the link group is empty or exceeds its alignment");
+        const size_t fe = sizeof(E);
+        size_t max_len = 0;
+        for (size_t i = 0; i < batch; i++) max_len = std::max(max_len, lens[i]);
+        if (max_len >> 27) return fail(ctx, JF_ERR_INVALID_ARG, "div_link_domain: polynomial too long");
+        LinkBufs lb;
+        JF_TRY(link_bufs(ctx, max_len, alignment, size, flags, &lb));
+        for (size_t i = 0; i < batch; i++) {
+            const size_t want = lens[i] > size ? lens[i] - size : 0;
+            if (!want) continue;
+            JF_CUDA(ctx, cudaMemcpyAsync(lb.diff, polys[i], fe * lens[i], cudaMemcpyHostToDevice, ctx->stream));
+            E *Q = lb.A;
+            size_t q_len = 0;
+            int path = 0;
+            JF_TRY(link_quotient(ctx, lb, lens[i], alignment, offset, size, flags, &Q, &q_len, &path));
+            if (q_len < want) memset(outs[i] + 4 * q_len, 0, fe * (want - q_len));
+            if (q_len) JF_CUDA(ctx, cudaMemcpyAsync(outs[i], Q, fe * std::min(q_len, want), cudaMemcpyDeviceToHost, ctx->stream));
+            JF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // lb is reused by the next polynomial
+        }
+        return JF_OK;
+    }
+
+    struct LinkOut {
+        uint64_t q_xy[12], open_xy[12], eta[4];
+        int q_inf, open_inf, path;
+    };
+    static int link_proofs(jf_ctx *ctx, const jf_srs *srs, const E *d_a1, size_t len1, const uint64_t *a1_comm, int a1_inf,
+                           const E *d_a2, size_t len2, const uint64_t *a2_comm, int a2_inf, unsigned alignment, size_t offset,
+                           size_t size, int kind, int flags, LinkOut *out) {
+        if (alignment > (unsigned)Fr::TWO_ADICITY || alignment > 30)
+            return fail(ctx, JF_ERR_DOMAIN_TOO_LARGE, "link_proofs: the group alignment exceeds the field's two-adicity");
+        if (size == 0 || offset + size >= ((size_t)1 << alignment))  // validate_layout (linkable_circuit.rs:352-370)
+            return fail(ctx, JF_ERR_INVALID_ARG, "link_proofs: the link group is empty or exceeds its alignment");
+        const size_t max_len = std::max(len1, len2);
+        if (max_len > srs->n + 1) return fail(ctx, JF_ERR_INVALID_ARG, "link_proofs: polynomial degree exceeds the commit key");
+        const size_t fe = sizeof(E);
+        cudaStream_t st = ctx->stream;
+        const E g = root_of_unity(alignment);
+        const E r0 = pow_small(g, (uint64_t)offset);
+        memset(out, 0, sizeof *out);
+        LinkBufs lb;
+        JF_TRY(link_bufs(ctx, max_len, alignment, size, flags, &lb));
+        void *p_res;
+        JF_TRY(scratch(ctx, "link_res", 2 * PT, &p_res));
+        E *diff = lb.diff, *A = lb.A, *B = lb.B, *T = lb.T, *S = lb.S, *tmp = lb.tmp;
+        // a1 - a2
+        if (max_len) {
+            std::vector<Term> terms = {{d_a1, len1, E::one()}, {d_a2, len2, E::neg(E::one())}};
+            JF_TRY(lincomb_many(ctx, terms, diff, max_len));
+        }
+        E *Q = A;
+        size_t q_len = 0;
+        JF_TRY(link_quotient(ctx, lb, max_len, alignment, offset, size, flags, &Q, &q_len, &out->path));
         // quotient commitment (`UnivariateKzgPCS::commit`, mod.rs:90-116)
         JF_TRY(msm_run(ctx, srs, 0, Q, q_len, 1, p_res));
         void *h;
@@ -2500,6 +2566,20 @@ int jf_plonk_link_proofs_resident(jf_ctx *ctx, const jf_plonk_pk *lhs, const jf_
                                       rhs_proof->wires_poly_comms, rhs_proof->wires_inf[0], alignment, offset, size, transcript_kind, flags, out);
     return link_entry<Bls12381Plonk>(ctx, srs, lhs->d_w, lhs->n + 2, lhs_proof->wires_poly_comms, lhs_proof->wires_inf[0], rhs->d_w, rhs->n + 2,
                                      rhs_proof->wires_poly_comms, rhs_proof->wires_inf[0], alignment, offset, size, transcript_kind, flags, out);
+}
+
+int jf_poly_div_link_domain(jf_ctx *ctx, int field, const uint64_t *const *polys, const size_t *lens, size_t batch, unsigned alignment,
+                            size_t offset, size_t size, int flags, uint64_t *const *out_quotients) {
+    JF_GUARD(ctx);
+    if (batch && (!polys || !lens || !out_quotients)) return fail(ctx, JF_ERR_INVALID_ARG, "div_link_domain: null argument");
+    for (size_t i = 0; i < batch; i++)
+        if (lens[i] && (!polys[i] || (lens[i] > size && !out_quotients[i]))) return fail(ctx, JF_ERR_INVALID_ARG, "div_link_domain: null polynomial");
+    int rc;
+    if (field == JF_BN254_FR) rc = Plonk<Bn254Plonk>::div_link_domain(ctx, polys, lens, batch, alignment, offset, size, flags, out_quotients);
+    else if (field == JF_BLS12_381_FR) rc = Plonk<Bls12381Plonk>::div_link_domain(ctx, polys, lens, batch, alignment, offset, size, flags, out_quotients);
+    else return fail(ctx, JF_ERR_INVALID_ARG, "div_link_domain: field must be a scalar field");
+    if (rc != JF_OK) cudaStreamSynchronize(ctx->stream);
+    return rc;
 }
 
 long jf_link_proof_serialize(const jf_link_proof *proof, uint8_t *out, size_t cap) {

@@ -142,3 +142,100 @@ def fft_with_domain(domain: Radix2EvaluationDomain, poly: AuthenticatedDensePoly
 
 def ifft_with_domain(domain: Radix2EvaluationDomain, evals: AuthenticatedDensePoly) -> AuthenticatedDensePoly:
     return fft_with_domain(domain, evals, inverse=True)
+
+
+# ---- collaborative proof linking (plonk/src/multiprover/proof_system/proof_linking.rs:96-246) --------------------------------
+@dataclass
+class MpcLinkingHint:
+    """`MpcLinkingHint` (multiprover/proof_system/structs.rs:206-230): this party's share of the first wire polynomial and of its
+    commitment."""
+    linking_wire_poly: AuthenticatedDensePoly
+    linking_wire_comm: AuthenticatedPointShare
+
+
+class MultiproverLinking:
+    """The party-local arithmetic of `MultiproverPlonkKzgSnark::link_proofs`.  The protocol opens the quotient commitment before the
+    challenge eta exists, so it comes in two steps around that opening (ark-mpc's network; here the tests add the parties' points):
+
+        q, q_comm = MultiproverLinking.quotient(params, lhs_hint, rhs_hint, layout)          # every party
+        eta = MultiproverLinking.challenge(ctx, curve, a1_comm, a2_comm, opened_q_comm)      # public points -> public scalar
+        proof = MultiproverLinking.identity_opening(params, lhs_hint, rhs_hint, q, eta, layout)
+
+    The opened (quotient commitment, opening proof) equal the single prover's `LinkingProof` under `SolidityTranscript`
+    (`MpcTranscript` wraps it: multiprover/primitives/mpc_transcript.rs:27-52)."""
+
+    @staticmethod
+    def _sub(ctx: Context, field: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        n = max(len(a), len(b))
+        pa, pb = np.zeros((n, 4), dtype=np.uint64), np.zeros((n, 4), dtype=np.uint64)
+        pa[: len(a)], pb[: len(b)] = a, b
+        return ctx.field_op(field, "sub", pa, pb) if n else pa
+
+    @staticmethod
+    def quotient(prover_params: UnivariateProverParam, lhs: MpcLinkingHint, rhs: MpcLinkingHint, layout
+                 ) -> Tuple[AuthenticatedDensePoly, AuthenticatedPointShare]:
+        """compute_linking_quotient (:127-138) share-wise -- division by the public Z_D is linear -- and `MultiproverKZG::commit`."""
+        import ctypes
+        from . import _ffi
+        ctx = prover_params.ctx
+        field = _ffi.CURVE_FR[prover_params.key.curve]
+        c1, c2 = lhs.linking_wire_poly.components(), rhs.linking_wire_poly.components()
+        if len(c1) != len(c2):
+            raise InvalidParameters("the two hints carry different share forms")
+        diffs = [MultiproverLinking._sub(ctx, field, a, b) for a, b in zip(c1, c2)]
+        k = len(diffs)
+        outs = [np.zeros((max(len(d) - layout.size, 0), 4), dtype=np.uint64) for d in diffs]
+        ptrs = (_ffi.c_u64p * k)(*[d.ctypes.data_as(_ffi.c_u64p) for d in diffs])
+        optrs = (_ffi.c_u64p * k)(*[o.ctypes.data_as(_ffi.c_u64p) for o in outs])
+        lens = (ctypes.c_size_t * k)(*[len(d) for d in diffs])
+        ctx._check(ctx._lib.jf_poly_div_link_domain(ctx._h, _ffi.FIELDS[field], ptrs, lens, k, layout.alignment, layout.offset,
+                                                    layout.size, 0, optrs))
+        q = AuthenticatedDensePoly(outs[0], outs[1], outs[2] if k == 3 else None)
+        return q, MultiproverKZG.commit(prover_params, q)
+
+    @staticmethod
+    def challenge(curve: str, a1_comm, a2_comm, quotient_comm) -> np.ndarray:
+        """compute_quotient_challenge (:176-195) on the OPENED commitments: (xy, is_infinity) each -> eta, 4 Montgomery limbs."""
+        from .plonk import Transcript
+        from . import _ffi
+        tr = Transcript("solidity", b"MpcPlonkLinkingProof")
+        for label, (xy, inf) in ((b"linking_wire_comms", a1_comm), (b"linking_wire_comms", a2_comm), (b"quotient_comm", quotient_comm)):
+            tr.append_message(label, g1_serialize_compressed(curve, xy, inf))
+        return tr.get_and_append_challenge(_ffi.CURVE_FR[curve], b"eta")
+
+    @staticmethod
+    def identity_opening(prover_params: UnivariateProverParam, lhs: MpcLinkingHint, rhs: MpcLinkingHint, quotient: AuthenticatedDensePoly,
+                         eta: np.ndarray, vanishing_eval: np.ndarray) -> AuthenticatedPointShare:
+        """compute_identity_opening (:203-220): a1 - a2 - q Z_D(eta), opened at the public eta.  `vanishing_eval` = Z_D(eta)
+        (4 Montgomery limbs; public, O(size) host products: compute_vanishing_poly_eval, :155-170)."""
+        from . import _ffi
+        ctx = prover_params.ctx
+        field = _ffi.CURVE_FR[prover_params.key.curve]
+        comps = []
+        for a, b, q in zip(lhs.linking_wire_poly.components(), rhs.linking_wire_poly.components(), quotient.components()):
+            d = MultiproverLinking._sub(ctx, field, a, b)
+            if len(q):
+                zq = ctx.field_op(field, "mul", q, np.broadcast_to(np.asarray(vanishing_eval, dtype=np.uint64), q.shape).copy())
+                d = MultiproverLinking._sub(ctx, field, d, zq)
+            comps.append(d)
+        ident = AuthenticatedDensePoly(comps[0], comps[1], comps[2] if len(comps) == 3 else None)
+        proof, _ = MultiproverKZG.open(prover_params, ident, eta)
+        return proof
+
+
+def g1_serialize_compressed(curve: str, xy: np.ndarray, inf: bool) -> bytes:
+    """`to_bytes!` of a commitment (the library's host serialiser: ark-ec's form for BN254, the ZCash form for BLS12-381)."""
+    import ctypes
+    from . import _ffi
+    raw = _ffi.LinkProofStruct()
+    raw.curve = _ffi.CURVES[curve]
+    L = _ffi.CURVE_FQ_LIMBS[curve]
+    for i in range(2 * L):
+        raw.quotient_commitment[i] = int(xy[i]) if not inf else 0
+    raw.quotient_inf = int(bool(inf))
+    raw.opening_inf = 1
+    buf = ctypes.create_string_buffer(128)
+    n = _ffi.lib().jf_link_proof_serialize(ctypes.byref(raw), buf, len(buf))
+    if n < 0:
+        raise InvalidParameters("point serialization failed (%d)" % n)
+    return buf.raw[: n // 2]

@@ -164,6 +164,8 @@ extern "C" {
     pub fn jf_plonk_link_proofs_resident(ctx: *mut jf_ctx, lhs: *const jf_plonk_pk, lhs_proof: *const jf_plonk_proof,
                                          rhs: *const jf_plonk_pk, rhs_proof: *const jf_plonk_proof, alignment: c_uint, offset: usize,
                                          size: usize, transcript_kind: c_int, flags: c_int, out: *mut jf_link_proof) -> c_int;
+    pub fn jf_poly_div_link_domain(ctx: *mut jf_ctx, field: c_int, polys: *const *const u64, lens: *const usize, batch: usize,
+                                   alignment: c_uint, offset: usize, size: usize, flags: c_int, out_quotients: *const *mut u64) -> c_int;
     pub fn jf_link_proof_serialize(proof: *const jf_link_proof, out: *mut u8, cap: usize) -> c_long;
 
     pub fn jf_keccak256(data: *const u8, len: usize, out: *mut u8);

@@ -190,3 +190,72 @@ def test_config5_size_commit_and_sharewise_coset_ntt(ctx, co, py, three):
     ev = co.field_op(field, "add", pr[0][1][0][0][None, :], pr[1][1][0][0][None, :])[0]
     assert fr.from_mont(co.limbs_to_ints(ev[None, :])[0]) == ev_single
     pp.key.free()
+
+
+@pytest.mark.parametrize("three", [False, True])
+def test_collaborative_proof_linking_matches_the_single_prover(ctx, co, py, three):
+    """multiprover/proof_system/proof_linking.rs (its own tests open the collaborative linking proof and verify it like a single
+    prover's): two parties hold additive shares (+ MAC shares [+ public modifiers]) of two first-wire polynomials that agree on a
+    link group; quotient shares, commitment shares, the challenge from the opened commitments, opening shares.  The opened
+    (quotient commitment, opening proof) must be the single prover's `LinkingProof` bytes, and the MAC points must check."""
+    import mpc_jellyfish_b200 as jf
+    cv, fr = py.BN254, py.BN254_FR
+    p = fr.p
+    beta, mac_key = 0xFEEDFACE1234567, 0x2468ACE
+    n, align, offset, size = 256, 7, 9, 20
+    pp = jf.UnivariateProverParam(ctx.generate_srs_for_testing("bn254", beta, n + 3))
+    a1 = py.random_field_elems(fr, n + 2, seed=91)
+    a2 = list(a1)
+    for j in (3, 40):                         # a2 = a1 + c_j X^j (X^(2^align) - 1): equal on every 2^align-th root of unity
+        c = 1000 + j
+        a2[j] = (a2[j] - c) % p
+        a2[j + (1 << align)] = (a2[j + (1 << align)] + c) % p
+    mont = lambda xs: co.ints_to_limbs([fr.to_mont(x) for x in xs], 4)  # noqa: E731
+    pt = lambda xy, inf: _pt(co, cv, xy, inf)                           # noqa: E731
+    # single prover
+    key = pp.key
+    c1 = ctx.msm(key, mont(a1), montgomery=True)
+    c2 = ctx.msm(key, mont(a2), montgomery=True)
+    layout = jf.GroupLayout(align, offset, size)
+    single = jf.PlonkKzgSnark.link_proofs(ctx, key, jf.LinkingHint(mont(a1), c1[0], bool(c1[1])), jf.LinkingHint(mont(a2), c2[0], bool(c2[1])),
+                                          layout, "solidity")
+    assert single.path == 0
+    # two parties
+    def hints(vals, seed):
+        out = []
+        for s, m in _share(co, py, fr, vals, mac_key, seed):
+            mod = None
+            if three:   # public modifiers: zero vectors on both parties except one public constant folded into party 0's view
+                mod = np.zeros_like(s)
+            poly = jf.AuthenticatedDensePoly(s, m, mod)
+            out.append(jf.MpcLinkingHint(poly, jf.MultiproverKZG.commit(pp, poly)))
+        return out
+    h1, h2 = hints(a1, 300), hints(a2, 400)
+    opened = lambda shares, which: cv.add(*[pt(getattr(s, which), getattr(s, which + "_inf")) for s in shares])  # noqa: E731
+    a1c, a2c = opened([h.linking_wire_comm for h in h1], "share"), opened([h.linking_wire_comm for h in h2], "share")
+    assert a1c == pt(*c1) and a2c == pt(*c2)
+    qs = [jf.MultiproverLinking.quotient(pp, h1[i], h2[i], layout) for i in range(2)]
+    assert len(qs[0][0].share) == n + 2 - size
+    qc, qc_mac = opened([q[1] for q in qs], "share"), opened([q[1] for q in qs], "mac")
+    assert qc == pt(single.quotient_commitment, single.quotient_inf)
+    assert qc_mac == cv.mul(mac_key, qc)
+    # the shares of the quotient do not vanish on the group one by one, their sum does: check the opened polynomial too
+    qsum = [(x + y) % p for x, y in zip(*[[fr.from_mont(v) for v in co.limbs_to_ints(q[0].share)] for q in qs])]
+    import plonk_ref as P
+    assert P._strip(qsum) == P.linking_quotient(fr, a1, a2, P.GroupLayout(align, offset, size))
+    # public challenge from the opened points, then the opening shares
+    to_xy = lambda P_: (np.concatenate([co.ints_to_limbs([cv.fq.to_mont(P_[0])], 4)[0], co.ints_to_limbs([cv.fq.to_mont(P_[1])], 4)[0]]), False)  # noqa: E731
+    eta = jf.MultiproverLinking.challenge("bn254", to_xy(a1c), to_xy(a2c), to_xy(qc))
+    assert np.array_equal(eta, single.eta)
+    eta_i = fr.from_mont(co.limbs_to_ints(eta.reshape(1, 4))[0])
+    zd = P._link_vanishing_eval(fr, eta_i, P.GroupLayout(align, offset, size))
+    zd_l = co.ints_to_limbs([fr.to_mont(zd)], 4)[0]
+    proofs = [jf.MultiproverLinking.identity_opening(pp, h1[i], h2[i], qs[i][0], eta, zd_l) for i in range(2)]
+    w, w_mac = opened(proofs, "share"), opened(proofs, "mac")
+    assert w == pt(single.opening_proof, single.opening_inf)
+    assert w_mac == cv.mul(mac_key, w)
+    # ... and the restated verifier accepts the opened proof
+    ok = P.verify_link_proof(cv, {"wires_poly_comms": [a1c]}, {"wires_poly_comms": [a2c]},
+                             {"quotient_commitment": qc, "opening_proof": w}, P.GroupLayout(align, offset, size), beta, "solidity")
+    assert ok
+    pp.key.free()
