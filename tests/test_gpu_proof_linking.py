@@ -206,3 +206,65 @@ def test_large_link_groups(ctx, co, py, P, log_n, size):
     for s in (a, b, c):
         s.free()
     key.free()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_hints_and_layouts_match_the_cpu_restatement(ctx, co, py, P, seed):
+    """hints that do not come from circuits: unequal lengths, groups longer than a polynomial, size 1, alignments above and below the
+    polynomial length, pairs that vanish on the group and pairs that do not -- quotient commitment, eta and opening == oracle"""
+    import mpc_jellyfish_b200 as jf
+    import plonk_util as U
+    cv, fr = py.BN254, py.BN254_FR
+    p = fr.p
+    beta = BETA % p
+    rnd = random.Random(1000 + seed)
+    key = ctx.generate_srs_for_testing("bn254", beta, 700)
+    osrs = P.gen_srs(cv, beta, 699)
+    mont = lambda xs: co.ints_to_limbs([fr.to_mont(x) for x in xs], 4) if xs else np.zeros((0, 4), dtype=np.uint64)  # noqa: E731
+    for case in range(6):
+        align = rnd.randrange(1, 11)
+        size = rnd.randrange(1, max(2, min(1 << align, 200) - 1))
+        offset = rnd.randrange(0, (1 << align) - size)
+        if offset + size >= (1 << align):
+            continue
+        lay = P.GroupLayout(align, offset, size)
+        len1 = rnd.choice([0, 1, size, size + 1, rnd.randrange(1, 600), rnd.randrange(300, 690)])
+        a1 = [rnd.randrange(p) for _ in range(len1)]
+        mode = rnd.choice(["linked", "linked_longer", "unrelated", "equal", "shorter"])
+        if mode == "equal":
+            a2 = list(a1)
+        elif mode == "unrelated":
+            a2 = [rnd.randrange(p) for _ in range(rnd.randrange(0, 690))]
+        elif mode == "shorter":
+            a2 = a1[: len(a1) // 2]
+        else:   # a2 = a1 + Z_D * r for a random r: equal on the group, different elsewhere
+            z = [1]
+            for r_ in P._link_roots(fr, lay):
+                nz = [0] * (len(z) + 1)
+                for i, c in enumerate(z):
+                    nz[i] = (nz[i] - c * r_) % p
+                    nz[i + 1] = (nz[i + 1] + c) % p
+                z = nz
+            rl = rnd.randrange(1, 40) if mode == "linked" else max(1, 680 - size - 1)
+            rpoly = [rnd.randrange(p) for _ in range(rl)]
+            prod = [0] * (len(z) + rl - 1)
+            for i, zc in enumerate(z):
+                for j, rc in enumerate(rpoly):
+                    prod[i + j] = (prod[i + j] + zc * rc) % p
+            a2 = P._poly_add(p, a1, prod)
+        if max(len(a1), len(a2)) > 690:
+            continue
+        c1, c2 = ctx.msm(key, mont(a1), montgomery=True) if a1 else (np.zeros(8, dtype=np.uint64), True), \
+            ctx.msm(key, mont(a2), montgomery=True) if a2 else (np.zeros(8, dtype=np.uint64), True)
+        h1 = jf.LinkingHint(mont(a1), c1[0], bool(c1[1]))
+        h2 = jf.LinkingHint(mont(a2), c2[0], bool(c2[1]))
+        oh1 = {"linking_wire_poly": P._strip(a1), "linking_wire_comm": U.point_to_affine(co, cv, c1[0], c1[1])}
+        oh2 = {"linking_wire_poly": P._strip(a2), "linking_wire_comm": U.point_to_affine(co, cv, c2[0], c2[1])}
+        want = P.link_proofs(cv, oh1, oh2, lay, osrs, "solidity")
+        jl = jf.GroupLayout(align, offset, size)
+        for seq in (False, True):
+            got = jf.PlonkKzgSnark.link_proofs(ctx, key, h1, h2, jl, "solidity", sequential_division=seq)
+            assert got.serialize_compressed() == P.serialize_link_proof(cv, want), (seed, case, mode, lay, len(a1), len(a2), seq)
+        if mode in ("linked", "linked_longer", "equal") and max(len(a1), len(a2)) > size:
+            assert jf.PlonkKzgSnark.link_proofs(ctx, key, h1, h2, jl, "solidity").path == 0
+    key.free()
