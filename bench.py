@@ -360,14 +360,15 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
     wit = torch.from_numpy(arr["witness"].view(np.int64)).pin_memory().numpy().view(np.uint64)
     out = {}
     steps = max(1, min(args.steps, 5))
-    for cache, skip, full in ((False, False, False), (False, True, False), (True, True, False), (False, False, True)):
+    for cache, skip, full, lag in ((False, False, False, False), (False, True, False, False), (True, True, False, False),
+                                  (False, False, True, False), (False, False, False, True), (True, True, False, True)):
         t0 = time.time()
         pk = jf_mod().PlonkKzgSnark.preprocess(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"],
                                                arr["num_vars"], [], cache_coset_evals=cache, skip_zero_selectors=skip,
-                                               full_quotient_coset=full)
+                                               full_quotient_coset=full, lagrange_wire_commitments=lag)
         t_pre = time.time() - t0
         proof = jf_mod().PlonkKzgSnark.prove(pk, wit, bl, "solidity")
-        if rank == 0 and not cache and not skip and not full:
+        if rank == 0 and not cache and not skip and not full and not lag:
             # checker: the restated jellyfish verifier (known-beta G1 form) must accept the proof
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import plonk_ref as P
@@ -395,10 +396,10 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
         jf_mod().PlonkKzgSnark.prove(pk, wit, bl, "solidity")
         prof = ctx.profile_collect()
         ctx.profile(False)
-        out[(cache, skip, full)] = {"wall_ms": max_over_ranks(wall), "device_ms": max_over_ranks(dev), "launches": int(launches),
+        out[(cache, skip, full, lag)] = {"wall_ms": max_over_ranks(wall), "device_ms": max_over_ranks(dev), "launches": int(launches),
                       "preprocess_s": round(t_pre, 3),
                       "kernels_ms": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}}
-        if comm is not None and not cache and not skip and not full:
+        if comm is not None and not cache and not skip and not full and not lag:
             # ONE proof on all the GPUs (strong scaling of the prove metric): every rank runs the same call -- same witness, same
             # blinders -- and commits only its slice of every polynomial (jf_plonk_pk_shard_commits); the 13 MSMs split by point
             # range, the transforms are replicated.  Refuses to time unless the bytes equal the one-GPU proof of this rank.
@@ -481,21 +482,28 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
                "sample": "component sum of the CPU restatement timed in this run: 13 MSM(2^20) + 26 coset NTT(2^23) + "
                          "7 iNTT(2^20) (App. A workload); pointwise / Horner / division terms not included. The reference's "
                          "only published figure extrapolates to ~24 s on a 5900X (bench.md:17, 2^15 gates x 32)"}
-    base = out[(False, False, False)]
+    base = out[(False, False, False, False)]
     alt = lambda k, note: {"value": out[k]["wall_ms"], "unit": "ms", "device_ms": out[k]["device_ms"],  # noqa: E731
-                           "gpu_launches": out[k]["launches"], "note": note}
+                           "gpu_launches": out[k]["launches"], "preprocess_s": out[k]["preprocess_s"], "note": note}
     return {
         "metric": "BN254 2^20-gate TurboPlonk prove ms (bench.rs circuit, SolidityTranscript, proof accepted by the restated verifier)",
         "value": base["wall_ms"] / 1.0, "unit": "ms", "ms_per_step": base["wall_ms"], "higher_is_better": False,
         "proofs_per_s": world * 1e3 / base["wall_ms"], "device_ms": base["device_ms"], "gpu_launches": base["launches"],
         "kernels_ms_per_proof": base["kernels_ms"], "setup_s": round(t_setup, 2), "preprocess_s": base["preprocess_s"],
-        "with_full_8n_quotient_coset": alt((False, False, True), "round 3 in the reference's literal form: one 8n-point coset NTT per "
+        "with_full_8n_quotient_coset": alt((False, False, True, False), "round 3 in the reference's literal form: one 8n-point coset NTT per "
                                            "polynomial (prover.rs:552-567) instead of six sub-cosets of n points; same proof bytes"),
-        "with_zero_selector_skip": alt((False, True, False), "selector columns that are identically zero (9 of 13 in this circuit: "
+        "with_zero_selector_skip": alt((False, True, False, False), "selector columns that are identically zero (9 of 13 in this circuit: "
                                        "q_lc2-3, q_mul, q_hash, q_ecc) are recognised at preprocess; their coset NTTs and "
                                        "quotient terms are skipped; same proof bytes (tests/test_gpu_plonk.py)"),
-        "with_cached_selector_sigma_coset_evals": alt((True, True, False), "additionally the selector / sigma coset evaluations stay "
+        "with_cached_selector_sigma_coset_evals": alt((True, True, False, False), "additionally the selector / sigma coset evaluations stay "
                                                       "resident (+3.4 GiB): only 7 polynomials are transformed per proof; same proof bytes"),
+        "with_lagrange_wire_commitments": alt((False, False, False, True), "the five wire polynomials are committed in the Lagrange basis "
+                                              "(jf_srs_lagrange once per key: an inverse DFT of the commit key in the group, see preprocess_s): "
+                                              "their MSMs run over the witness VALUES, which in this circuit are the integers 0 .. 2^20 "
+                                              "(two non-zero digits per scalar instead of 15; random-looking witnesses gain nothing); same "
+                                              "proof bytes (tests/test_gpu_lagrange.py)"),
+        "with_all_key_side_options": alt((True, True, False, True), "zero-selector skip + resident selector / sigma coset evaluations + "
+                                         "Lagrange-basis wire commitments; same proof bytes"),
         "prove_2^16_gates_ms": prove16_ms,
         "one_proof_on_all_gpus": ({"value": out["sharded"], "unit": "ms", "n_gpus": world, "scaling": "strong",
                                    "commitments_only_ms": out["sharded_commits_only"],

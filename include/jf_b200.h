@@ -75,6 +75,12 @@ int jf_srs_load(jf_ctx *ctx, int curve, const void *affine_pts, size_t n, size_t
  * (first_power > 0 yields the slice of the key one GPU holds in a range-sharded MSM). */
 int jf_srs_generate_for_testing(jf_ctx *ctx, int curve, const uint64_t *beta, size_t first_power, size_t n,
                                 int window_bits, int precompute, jf_srs **out);
+/* The commit key in the LAGRANGE basis of the size-2^log_n domain: out[j] = [L_j(beta)] G, so that
+ * `commit(p) = sum_j p(w^j) * out[j]` is an MSM over a polynomial's VALUES on the domain (zero and small values then cost nothing or
+ * little).  Computed from `srs` alone -- beta stays unknown -- as the inverse DFT of its first 2^log_n points taken in the group
+ * (n/2 log n scalar multiplications: about a second at 2^20, once per key and domain).  mask_points != 0 appends P_n - P_0 and
+ * P_(n+1) - P_1, the commit-key side of the prover's masking terms (b_0 + b_1 X)(X^n - 1) (prover.rs:463-486). */
+int jf_srs_lagrange(jf_ctx *ctx, const jf_srs *srs, unsigned log_n, int mask_points, jf_srs **out);
 /* Copy `count` affine points starting at `first` back to the host (x || y each). */
 int jf_srs_read(jf_ctx *ctx, const jf_srs *srs, size_t first, size_t count, uint64_t *out_xy);
 size_t jf_srs_len(const jf_srs *srs);
@@ -207,7 +213,9 @@ int jf_ntt_cosets(jf_ctx *ctx, int field, const uint64_t *polys_in, size_t in_le
  * quotient terms are skipped; the proof is unchanged.  Round 3 evaluates the quotient on six sub-cosets
  * (g w_8n^r)<w_n>, r < 6, of the reference's 8n-point coset (6n points determine a polynomial of degree 5n + 7;
  * the coefficients follow from six size-n inverse transforms and a 6 x 6 Vandermonde solve per index), which
- * yields the same quotient polynomial with 29 % less transform work; flags & 4 keeps the reference's form (one
+ * yields the same quotient polynomial with 29 % less transform work; flags & 8: the wire polynomials are committed in the Lagrange
+ * basis (jf_srs_lagrange is run once for this key: the five wire commitments of a proof become MSMs over the witness values; same
+ * commitments; ignored while the key is sharded over several GPUs); flags & 4 keeps the reference's form (one
  * 8n-point coset transform per polynomial, prover.rs:552-567,672), as do domains below 16 (at n = 8 six rows hold
  * exactly the quotient's 48 coefficients and nothing would be left for the WrongQuotientPolyDegree check).  `srs` must outlive the key and hold >= n + 3 points.  2 <= log_n and
  * log_n + 3 <= two-adicity (JF_ERR_DOMAIN_TOO_LARGE otherwise: `Prover::new`, prover.rs:54-62). */

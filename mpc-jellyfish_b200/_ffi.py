@@ -90,6 +90,7 @@ SIGNATURES = {
                                    ctypes.c_long, ctypes.c_int, ctypes.c_int, c_void_pp]),
     "jf_srs_generate_for_testing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64p, ctypes.c_size_t, ctypes.c_size_t,
                                                    ctypes.c_int, ctypes.c_int, c_void_pp]),
+    "jf_srs_lagrange": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint, ctypes.c_int, c_void_pp]),
     "jf_srs_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, c_u64p]),
     "jf_srs_len": (ctypes.c_size_t, [ctypes.c_void_p]),
     "jf_srs_window_bits": (ctypes.c_int, [ctypes.c_void_p]),

@@ -265,6 +265,13 @@ class CommitKey:
         self.ctx._check(self.ctx._lib.jf_srs_read(self.ctx._h, self._h, first, count, _u64p(out)))
         return out
 
+    def lagrange(self, log_n: int, mask_points: bool = False) -> "CommitKey":
+        """The key in the Lagrange basis of the size-2^log_n domain: out[j] = [L_j(beta)] G (`jf_srs_lagrange`), so that a
+        commitment is an MSM over a polynomial's values on the domain."""
+        h = ctypes.c_void_p()
+        self.ctx._check(self.ctx._lib.jf_srs_lagrange(self.ctx._h, self._h, log_n, int(mask_points), ctypes.byref(h)))
+        return CommitKey(self.ctx, self.curve, h)
+
     def free(self):
         if self._h is not None and self.ctx._h:
             self.ctx._lib.jf_srs_free(self.ctx._h, self._h)

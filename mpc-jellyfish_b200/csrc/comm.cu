@@ -269,7 +269,11 @@ int comm_bcast_rows(jf_ctx *ctx, jf_comm *c, const void *d_local_rows, void *d_a
         const int root = r % c->nranks;
         char *dst = (char *)d_all_rows + (size_t)r * row_bytes;
         const void *src = root == c->rank ? (const char *)d_local_rows + (size_t)(r / c->nranks) * row_bytes : dst;
-        JF_NCCL(ctx, api, api->Broadcast(src, dst, row_bytes, ncclChar, root, c->nccl, ctx->stream));
+        const ncclResult_t r_ = api->Broadcast(src, dst, row_bytes, ncclChar, root, c->nccl, ctx->stream);
+        if (r_ != ncclSuccess) {
+            api->GroupEnd();  // do not leave the library inside a group
+            return fail(ctx, JF_ERR_COMM, std::string("ncclBroadcast: ") + api->GetErrorString(r_));
+        }
     }
     JF_NCCL(ctx, api, api->GroupEnd());
     return JF_OK;

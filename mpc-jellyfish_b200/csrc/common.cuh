@@ -193,6 +193,8 @@ jf_ctx *comm_ctx(const jf_comm *c);
 int srs_build(jf_ctx *ctx, int curve, const void *d_base_points /* n affine, device */, size_t n, int window_bits,
               int precompute, jf_srs **out);
 int srs_generate(jf_ctx *ctx, int curve, const uint64_t *beta, size_t first_power, size_t n, void *d_out_points);
+// lagrange.cu: [L_j(beta)] G, j < 2^log_n, from the monomial key (inverse DFT in the group); mask_points: + P_n - P_0, P_(n+1) - P_1
+int srs_lagrange(jf_ctx *ctx, const jf_srs *mono, unsigned log_n, int mask_points, jf_srs **out);
 int microbench(jf_ctx *ctx, int kind, double *out_rate);
 int fixed_base_mul(jf_ctx *ctx, int curve, const void *d_scalars, size_t n, void *d_out_points);
 int field_op(jf_ctx *ctx, int field, int op, const void *d_a, const void *d_b, void *d_out, size_t n);

@@ -766,6 +766,10 @@ struct jf_plonk_pk {
     int shard_rows = 0, rows_local = 0;
     int row_map[jf::SUB_MAX] = {0};
     uint64_t sub_off_local[jf::SUB_MAX * 4];
+    // flags & 8: the key in the Lagrange basis of this domain (+ the two masking points), and the scalar vectors of a round's wire
+    // commitments: NW x (n + 2) = the wire's values on the domain, then its two masking scalars
+    jf_srs *lag = nullptr;
+    void *d_lagsc = nullptr;
     int proofs_done = 0;    // batch_prove calls that left their wire polynomials in d_w (jf_plonk_link_hint, proof linking)
     uint32_t zero_sel = 0;  // selectors that are identically zero (flags & 2)
     int skip_zero = 0;      // flags & 2: zero polynomials (such selectors; PI without public inputs) are not transformed
@@ -875,6 +879,10 @@ template <class C> struct HostCurve {
 // frees everything a (possibly half-built) proving key owns; the caller has synchronised the streams that used it
 static void release_pk(jf_plonk_pk *pk) {
     for (void *p : pk->allocs) cudaFree(p);
+    if (pk->lag) {
+        cudaFree(pk->lag->d_points);
+        delete pk->lag;
+    }
     if (pk->ev_main) cudaEventDestroy(pk->ev_main);
     if (pk->ev_side) cudaEventDestroy(pk->ev_side);
     if (pk->side) cudaStreamDestroy(pk->side);
@@ -1072,6 +1080,10 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
             return fail(ctx, JF_ERR_CUDA, "preprocess: cannot create the side stream");
         }
         int rc = preprocess_inner(ctx, pk, selector_evals, sigma_evals, k, wire_variables, pub_gate_ids, lc);
+        if (rc == JF_OK && (flags & 8)) {  // Lagrange-basis key for the wire commitments (lagrange.cu), once per proving key
+            rc = srs_lagrange(ctx, srs, log_n, 1, &pk->lag);
+            if (rc == JF_OK) rc = dalloc(ctx, pk, sizeof(E) * NW * (n + 2), &pk->d_lagsc);
+        }
         if (rc != JF_OK) {
             cudaStreamSynchronize(ctx->stream);
             cudaStreamSynchronize(pk->side);
@@ -1492,9 +1504,20 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
                 if (pk->num_inputs == 0 && pk->skip_zero) return JF_OK;  // PI(X) = 0: nothing to transform
                 return coset_fft_rows(ctx, pk, s.PI, np, n, 1, s.pi_c);
             }));
-            CommitJob jobs[NW];
-            for (int j = 0; j < NW; j++) jobs[j] = {s.W + (size_t)j * np, n + 2, j};
-            JF_TRY(commit_many(ctx, pk, jobs, NW));
+            if (pk->lag && !pk->comm) {
+                // Lagrange basis: commit(wire j) = sum_i value_i [L_i(beta)] G + b_0 (P_n - P_0) + b_1 (P_(n+1) - P_1): an MSM over the
+                // witness values (zeros are skipped, small values have few digits) and the two masking scalars; same point
+                E *sc = (E *)pk->d_lagsc;
+                JF_CUDA(ctx, cudaMemcpy2DAsync(sc, fe * (n + 2), s.WV, fe * n, fe * n, NW, cudaMemcpyDeviceToDevice, st));
+                JF_CUDA(ctx, cudaMemcpy2DAsync(sc + n, fe * (n + 2), bl_w + i * 2 * NW, fe * 2, fe * 2, NW, cudaMemcpyDeviceToDevice, st));
+                MsmJob mj[NW];
+                for (int j = 0; j < NW; j++) mj[j] = MsmJob{0, sc + (size_t)j * (n + 2), n + 2, 1, (char *)pk->d_res + PT * j};
+                JF_TRY(msm_run_many(ctx, pk->lag, mj, NW));
+            } else {
+                CommitJob jobs[NW];
+                for (int j = 0; j < NW; j++) jobs[j] = {s.W + (size_t)j * np, n + 2, j};
+                JF_TRY(commit_many(ctx, pk, jobs, NW));
+            }
             JF_TRY(fetch_commits(ctx, pk, 0, NW, out->wires_poly_comms, out->wires_inf));
             for (int j = 0; j < NW; j++) tr_g1(tr, "witness_poly_comms", out->wires_poly_comms + 2 * L * j, out->wires_inf[j]);
         }
@@ -2144,8 +2167,11 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
         memset(out, 0, sizeof *out);
         LinkBufs lb;
         JF_TRY(link_bufs(ctx, max_len, alignment, size, flags, &lb));
-        void *p_res;
+        void *p_res, *h;
         JF_TRY(scratch(ctx, "link_res", 2 * PT, &p_res));
+        // one pinned staging area for the whole call (Z_D's coefficients go up through it, the two results come down): reserved
+        // here at its largest so that no later request re-allocates it under a copy in flight
+        JF_TRY(pinned(ctx, std::max(fe * (size + 1), 2 * PT + 64), &h));
         E *diff = lb.diff, *A = lb.A, *B = lb.B, *T = lb.T, *S = lb.S, *tmp = lb.tmp;
         // a1 - a2
         if (max_len) {
@@ -2157,8 +2183,6 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
         JF_TRY(link_quotient(ctx, lb, max_len, alignment, offset, size, flags, &Q, &q_len, &out->path));
         // quotient commitment (`UnivariateKzgPCS::commit`, mod.rs:90-116)
         JF_TRY(msm_run(ctx, srs, 0, Q, q_len, 1, p_res));
-        void *h;
-        JF_TRY(pinned(ctx, 2 * PT + 64, &h));
         JF_CUDA(ctx, cudaMemcpyAsync(h, p_res, PT, cudaMemcpyDeviceToHost, st));
         int herr = 0;
         JF_CUDA(ctx, cudaMemcpyAsync(&herr, ctx->d_err, sizeof herr, cudaMemcpyDeviceToHost, st));

@@ -269,7 +269,7 @@ class PlonkKzgSnark:
     def preprocess(ctx: Context, key: CommitKey, selector_evals: np.ndarray, sigma_evals: np.ndarray, k: np.ndarray,
                    wire_variables: np.ndarray, num_vars: int, pub_input_gate_ids: Sequence[int] = (),
                    cache_coset_evals: bool = False, skip_zero_selectors: bool = False,
-                   full_quotient_coset: bool = False) -> ProvingKey:
+                   full_quotient_coset: bool = False, lagrange_wire_commitments: bool = False) -> ProvingKey:
         """selector_evals (13, n, 4), sigma_evals (5, n, 4) = the extended permutation, k (5, 4):
         Montgomery limbs; wire_variables (5, n) uint32."""
         sel = np.ascontiguousarray(selector_evals, dtype=np.uint64)
@@ -286,7 +286,8 @@ class PlonkKzgSnark:
         ctx._check(ctx._lib.jf_plonk_preprocess(
             ctx._h, key._h, n.bit_length() - 1, sel.ctypes.data_as(_ffi.c_u64p), sig.ctypes.data_as(_ffi.c_u64p),
             kk.ctypes.data_as(_ffi.c_u64p), wv.ctypes.data_as(_ffi.c_u32p), num_vars,
-            gids.ctypes.data_as(_ffi.c_u32p) if len(gids) else None, len(gids), int(cache_coset_evals) | (2 if skip_zero_selectors else 0) | (4 if full_quotient_coset else 0), ctypes.byref(h)))
+            gids.ctypes.data_as(_ffi.c_u32p) if len(gids) else None, len(gids), int(cache_coset_evals) | (2 if skip_zero_selectors else 0) | (4 if full_quotient_coset else 0)
+            | (8 if lagrange_wire_commitments else 0), ctypes.byref(h)))
         return ProvingKey(ctx, key, h, n, num_vars, len(gids), kk)
 
     @staticmethod
@@ -365,7 +366,8 @@ class PlonkKzgSnark:
     def preprocess_ultra(ctx: Context, key: CommitKey, selector_evals: np.ndarray, sigma_evals: np.ndarray, k: np.ndarray,
                          wire_variables: np.ndarray, num_vars: int, pub_input_gate_ids: Sequence[int], range_bit_len: int,
                          table_key_evals: np.ndarray, table_dom_sep_evals: np.ndarray, q_dom_sep_evals: np.ndarray,
-                         skip_zero_selectors: bool = False, full_quotient_coset: bool = False) -> ProvingKey:
+                         skip_zero_selectors: bool = False, full_quotient_coset: bool = False,
+                         lagrange_wire_commitments: bool = False) -> ProvingKey:
         """selector_evals (14, n, 4) = `all_selectors()` with q_lookup last, sigma_evals (6, n, 4), k (6, 4), wire_variables (6, n)
         with the range wire last; table_key / table_dom_sep / q_dom_sep: (n, 4) per-gate columns (constraint_system.rs:873-888)."""
         sel = np.ascontiguousarray(selector_evals, dtype=np.uint64)
@@ -386,7 +388,7 @@ class PlonkKzgSnark:
             kk.ctypes.data_as(_ffi.c_u64p), wv.ctypes.data_as(_ffi.c_u32p), num_vars,
             gids.ctypes.data_as(_ffi.c_u32p) if len(gids) else None, len(gids), range_bit_len,
             cols[0].ctypes.data_as(_ffi.c_u64p), cols[1].ctypes.data_as(_ffi.c_u64p), cols[2].ctypes.data_as(_ffi.c_u64p),
-            (2 if skip_zero_selectors else 0) | (4 if full_quotient_coset else 0), ctypes.byref(h)))
+            (2 if skip_zero_selectors else 0) | (4 if full_quotient_coset else 0) | (8 if lagrange_wire_commitments else 0), ctypes.byref(h)))
         return ProvingKey(ctx, key, h, n, num_vars, len(gids), kk, ultra=True)
 
     @staticmethod

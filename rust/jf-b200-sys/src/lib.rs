@@ -78,6 +78,7 @@ extern "C" {
                        inf_flag_offset: c_long, window_bits: c_int, precompute: c_int, out: *mut *mut jf_srs) -> c_int;
     pub fn jf_srs_generate_for_testing(ctx: *mut jf_ctx, curve: c_int, beta: *const u64, first_power: usize, n: usize,
                                        window_bits: c_int, precompute: c_int, out: *mut *mut jf_srs) -> c_int;
+    pub fn jf_srs_lagrange(ctx: *mut jf_ctx, srs: *const jf_srs, log_n: c_uint, mask_points: c_int, out: *mut *mut jf_srs) -> c_int;
     pub fn jf_srs_read(ctx: *mut jf_ctx, srs: *const jf_srs, first: usize, count: usize, out_xy: *mut u64) -> c_int;
     pub fn jf_srs_len(srs: *const jf_srs) -> usize;
     pub fn jf_srs_window_bits(srs: *const jf_srs) -> c_int;
