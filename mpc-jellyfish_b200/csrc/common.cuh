@@ -59,6 +59,8 @@ struct jf_srs {
     int windows = 16;      // W
     int tables = 1;        // T: 1 (no precompute) or W
     void *d_points = nullptr;  // tables * n affine points, table-major
+    int skew = 0;  // scalars against this key are expected to pile onto few buckets (a Lagrange-basis key meets witness VALUES:
+                   // constant columns, small integers): compact sort with warp-aggregated atomics from the start
 };
 
 namespace jf {

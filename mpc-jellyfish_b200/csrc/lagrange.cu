@@ -122,7 +122,9 @@ template <class C> static int srs_lagrange_t(jf_ctx *ctx, const jf_srs *mono, un
     JF_LAUNCH(ctx, "lag_finish", lag_finish_kernel<Fq><<<(unsigned)((n + 63) / 64), 64, 0, st>>>(X, (Affine<Fq> *)dout, (uint32_t)n, (int)log_n));
     if (mask_points) JF_LAUNCH(ctx, "lag_mask_points", lag_mask_points_kernel<Fq><<<1, 32, 0, st>>>(pts, (Affine<Fq> *)dout + n, (uint32_t)n));
     // same window as the monomial key: the two keys then share the MSM's bucket geometry
-    return srs_build(ctx, mono->curve, dout, total, mono->window_bits, mono->tables > 1 ? 1 : 0, out);
+    JF_TRY(srs_build(ctx, mono->curve, dout, total, mono->window_bits, mono->tables > 1 ? 1 : 0, out));
+    (*out)->skew = 1;  // witness values, not random-looking coefficients, meet this key
+    return JF_OK;
 }
 
 int srs_lagrange(jf_ctx *ctx, const jf_srs *mono, unsigned log_n, int mask_points, jf_srs **out) {

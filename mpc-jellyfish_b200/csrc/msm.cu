@@ -39,6 +39,7 @@ struct MsmGeom {
     int c, W, T, S;        // window bits, windows, tables, bucket sets
     uint32_t NB;           // buckets per set = 2^(c-1)
     int mont;              // scalars arrive in Montgomery form
+    int skew;              // jf_srs::skew: merge the atomics of lanes that hit the same bucket, in every window
 };
 
 // ---- 1. digits -------------------------------------------------------------------------
@@ -111,7 +112,7 @@ __global__ void msm_count_kernel(const uint32_t *scalars, MsmGeom g, uint32_t *c
     for_each_digit(s, g.c, g.W, [&](int w, int32_t d) {
         uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
         uint32_t bucket = (uint32_t)(w / g.T) * g.NB + (mag - 1);
-        if (agg_top && w == g.W - 1) agg_atomic_add(counts, bucket);
+        if (g.skew || (agg_top && w == g.W - 1)) agg_atomic_add(counts, bucket);
         else atomicAdd(&counts[bucket], 1u);
     });
 }
@@ -156,7 +157,7 @@ __global__ void msm_scatter_kernel(const uint32_t *__restrict__ scalars, MsmGeom
         }
 #pragma unroll
         for (int k = 0; k < 8; k++)
-            if (on[k]) pos[k] = (agg_top && w0 + k == g.W - 1) ? agg_atomic_add(cursor, bucket[k]) : atomicAdd(&cursor[bucket[k]], 1u);
+            if (on[k]) pos[k] = (g.skew || (agg_top && w0 + k == g.W - 1)) ? agg_atomic_add(cursor, bucket[k]) : atomicAdd(&cursor[bucket[k]], 1u);
 #pragma unroll
         for (int k = 0; k < 8; k++)
             if (on[k]) sorted[pos[k]] = payload[k];
@@ -391,17 +392,33 @@ __device__ __forceinline__ bool bucket_slots(const uint32_t *off, uint32_t b, ui
     return true;
 }
 
+// A heavy bucket's partials are cut into segments of HEAVY_SEG; every (bucket, segment) pair is one CTA's work item, so a bucket
+// that holds most of an MSM (all scalars equal; a column of small witness values against a Lagrange-basis key) is summed by the
+// whole GPU in two short steps instead of by one CTA walking tens of thousands of partials.
+static constexpr uint32_t HEAVY_SEG = HEAVY_THREADS * 8;
+struct HeavyQueues {
+    uint32_t *count;      // [0] heavy buckets, [1] segments
+    uint32_t *list;       // heavy bucket ids
+    uint32_t *base;       // first segment of each heavy bucket
+    uint2 *seg_desc;      // (bucket, segment index)
+};
+
 template <class Fq>
 __global__ void bucket_sum_kernel(const XYZZ<Fq> *partials, const uint32_t *off, uint32_t total_buckets, uint32_t acc_threads,
-                                  XYZZ<Fq> *X, uint32_t *heavy_count, uint32_t *heavy_list) {
+                                  XYZZ<Fq> *X, HeavyQueues hq) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= total_buckets) return;
     const uint32_t E = chunk_len(off[total_buckets], acc_threads);
     uint32_t s0, s1;
     XYZZ<Fq> acc = XYZZ<Fq>::inf();
     if (bucket_slots(off, b, E, s0, s1)) {
-        if (s1 - s0 + 1 > HEAVY_PARTS) {
-            heavy_list[atomicAdd(heavy_count, 1u)] = b;
+        const uint32_t parts = s1 - s0 + 1;
+        if (parts > HEAVY_PARTS) {
+            const uint32_t nseg = (parts + HEAVY_SEG - 1) / HEAVY_SEG;
+            const uint32_t k = atomicAdd(hq.count, 1u), base = atomicAdd(hq.count + 1, nseg);
+            hq.list[k] = b;
+            hq.base[k] = base;
+            for (uint32_t j = 0; j < nseg; j++) hq.seg_desc[base + j] = make_uint2(b, j);
             return;
         }
         for (uint32_t s = s0; s <= s1; s++) acc.add(load_xyzz(partials + s));
@@ -409,28 +426,56 @@ __global__ void bucket_sum_kernel(const XYZZ<Fq> *partials, const uint32_t *off,
     store_xyzz(X + b, acc);
 }
 
+// sum of in[lo .. hi] by one CTA: strided partial sums, then a tree in shared memory; the result is valid in thread 0
+template <class Fq>
+__device__ __forceinline__ XYZZ<Fq> cta_sum(const XYZZ<Fq> *in, uint32_t lo, uint32_t hi, XYZZ<Fq> *sh) {
+    XYZZ<Fq> acc = XYZZ<Fq>::inf();
+    for (uint32_t s = lo + threadIdx.x; s <= hi; s += HEAVY_THREADS) acc.add(load_xyzz(in + s));
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = HEAVY_THREADS / 2; d >= 1; d >>= 1) {
+        if ((int)threadIdx.x < d) {
+            acc.add(sh[threadIdx.x + d]);
+            sh[threadIdx.x] = acc;
+        }
+        __syncthreads();
+    }
+    return acc;
+}
+
+// step 1: every segment of every heavy bucket -> seg_out
 template <class Fq>
 __global__ void __launch_bounds__(HEAVY_THREADS)
-bucket_sum_heavy_kernel(const XYZZ<Fq> *partials, const uint32_t *off, uint32_t total_buckets, uint32_t acc_threads,
-                        XYZZ<Fq> *X, const uint32_t *heavy_count, const uint32_t *heavy_list) {
+bucket_sum_heavy_kernel(const XYZZ<Fq> *partials, const uint32_t *off, uint32_t total_buckets, uint32_t acc_threads, HeavyQueues hq,
+                        XYZZ<Fq> *seg_out) {
     __shared__ XYZZ<Fq> sh[HEAVY_THREADS];
-    const uint32_t nheavy = *heavy_count;
+    const uint32_t nseg = hq.count[1];
+    const uint32_t E = chunk_len(off[total_buckets], acc_threads);
+    for (uint32_t i = blockIdx.x; i < nseg; i += gridDim.x) {
+        const uint2 d = hq.seg_desc[i];
+        uint32_t s0, s1;
+        bucket_slots(off, d.x, E, s0, s1);
+        const uint32_t lo = s0 + d.y * HEAVY_SEG, hi = min(s1, lo + HEAVY_SEG - 1);
+        XYZZ<Fq> acc = cta_sum<Fq>(partials, lo, hi, sh);
+        if (threadIdx.x == 0) store_xyzz(seg_out + i, acc);
+        __syncthreads();
+    }
+}
+
+// step 2: the segment sums of a heavy bucket -> its bucket
+template <class Fq>
+__global__ void __launch_bounds__(HEAVY_THREADS)
+bucket_sum_heavy_join_kernel(const uint32_t *off, uint32_t total_buckets, uint32_t acc_threads, HeavyQueues hq, const XYZZ<Fq> *seg_out,
+                             XYZZ<Fq> *X) {
+    __shared__ XYZZ<Fq> sh[HEAVY_THREADS];
+    const uint32_t nheavy = hq.count[0];
     const uint32_t E = chunk_len(off[total_buckets], acc_threads);
     for (uint32_t i = blockIdx.x; i < nheavy; i += gridDim.x) {
-        const uint32_t b = heavy_list[i];
+        const uint32_t b = hq.list[i], base = hq.base[i];
         uint32_t s0, s1;
         bucket_slots(off, b, E, s0, s1);
-        XYZZ<Fq> acc = XYZZ<Fq>::inf();
-        for (uint32_t s = s0 + threadIdx.x; s <= s1; s += HEAVY_THREADS) acc.add(load_xyzz(partials + s));
-        sh[threadIdx.x] = acc;
-        __syncthreads();
-        for (int d = HEAVY_THREADS / 2; d >= 1; d >>= 1) {
-            if ((int)threadIdx.x < d) {
-                acc.add(sh[threadIdx.x + d]);
-                sh[threadIdx.x] = acc;
-            }
-            __syncthreads();
-        }
+        const uint32_t nseg = (s1 - s0 + 1 + HEAVY_SEG - 1) / HEAVY_SEG;
+        XYZZ<Fq> acc = cta_sum<Fq>(seg_out, base, base + nseg - 1, sh);
         if (threadIdx.x == 0) store_xyzz(X + b, acc);
         __syncthreads();
     }
@@ -517,7 +562,7 @@ bool msm_reads_scalars_once(const jf_srs *srs, size_t n) {
     const int bits = srs->curve == JF_BLS12_381 ? 255 : 254;
     const int S = (srs->windows + srs->tables - 1) / srs->tables;
     const uint32_t total = (uint32_t)S << (srs->window_bits - 1);
-    return n != 0 && direct_cap_log(bits, srs->window_bits, srs->windows, total, n * (size_t)srs->windows) != 0;
+    return n != 0 && !srs->skew && direct_cap_log(bits, srs->window_bits, srs->windows, total, n * (size_t)srs->windows) != 0;
 }
 
 template <class C>
@@ -546,6 +591,7 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     g.S = (g.W + g.T - 1) / g.T;
     g.NB = 1u << (g.c - 1);
     g.mont = mont;
+    g.skew = srs->skew;
     const uint32_t total = (uint32_t)g.S * g.NB;
     const size_t max_entries = n * (size_t)g.W;
     if (max_entries >= (1ull << 32)) return fail(ctx, JF_ERR_INVALID_ARG, "msm: n * windows must stay below 2^32");
@@ -585,9 +631,19 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     P *const XA0 = XA;
     XA += (size_t)ji * total;  // this member's buckets
     err = ctx->d_err;
+    // heavy buckets: counters, bucket ids, first segment of each; then the overflow flag of the direct sort; then the segment
+    // descriptors and the segment sums.  Every heavy bucket has more than HEAVY_PARTS partials, and its segments are full but the last
+    const size_t max_heavy = max_partials / HEAVY_PARTS + 1, max_segs = max_partials / HEAVY_SEG + max_heavy + 1;
     uint32_t *heavy;
-    JF_TRY(scratch(ctx, "msm_heavy", sizeof(uint32_t) * ((size_t)total + 8), &p));
-    heavy = (uint32_t *)p;  // [0] = count, [1..] = bucket ids
+    JF_TRY(scratch(ctx, "msm_heavy", sizeof(uint32_t) * (2 * max_heavy + 16) + sizeof(uint2) * max_segs, &p));
+    heavy = (uint32_t *)p;
+    HeavyQueues hq;
+    hq.count = heavy;
+    hq.list = heavy + 8;
+    hq.base = hq.list + max_heavy;
+    hq.seg_desc = (uint2 *)(hq.base + max_heavy + 2);
+    JF_TRY(scratch(ctx, "msm_heavy_seg", sizeof(P) * max_segs, &p));
+    P *seg_out = (P *)p;
 
     if (n == 0) {  // empty member of a group: all buckets are the identity (all-zero words)
         JF_CUDA(ctx, cudaMemsetAsync(XA, 0, sizeof(P) * total, st));
@@ -601,8 +657,8 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
     // Direct sort when every bucket is expected to stay far below its slot capacity (uniform digits, no narrow
     // top window): one pass over the scalars instead of two.  A bucket that overflows anyway (skewed scalars)
     // raises a device-side flag and the compact path below takes over; no host round trip either way.
-    const uint32_t cap_log = direct_cap_log(Fr::BITS, g.c, g.W, total, max_entries);
-    int *flag = (int *)(heavy + total + 2);
+    const uint32_t cap_log = srs->skew ? 0u : direct_cap_log(Fr::BITS, g.c, g.W, total, max_entries);
+    int *flag = (int *)(heavy + 4);
     if (cap_log) {
         uint32_t *slots;
         JF_TRY(scratch(ctx, "msm_slots", sizeof(uint32_t) * ((size_t)total << cap_log), &p));
@@ -627,9 +683,10 @@ static int msm_run_t(jf_ctx *ctx, const jf_srs *srs, size_t base_offset, const v
         JF_LAUNCH(ctx, "msm_accumulate", msm_accumulate_kernel<Fq, false><<<acc_blocks, ACC_THREADS, 0, st>>>(
             (const Affine<Fq> *)srs->d_points, g.srs_n, sorted, 0u, off, total, partials, (const int *)nullptr, 0));
     }
-    JF_CUDA(ctx, cudaMemsetAsync(heavy, 0, sizeof(uint32_t), st));
-    JF_LAUNCH(ctx, "bucket_sum", bucket_sum_kernel<Fq><<<(total + 127) / 128, 128, 0, st>>>(partials, off, total, acc_threads, XA, heavy, heavy + 1));
-    JF_LAUNCH(ctx, "bucket_sum_heavy", bucket_sum_heavy_kernel<Fq><<<(unsigned)ctx->sm_count * 4, HEAVY_THREADS, 0, st>>>(partials, off, total, acc_threads, XA, heavy, heavy + 1));
+    JF_CUDA(ctx, cudaMemsetAsync(heavy, 0, 2 * sizeof(uint32_t), st));
+    JF_LAUNCH(ctx, "bucket_sum", bucket_sum_kernel<Fq><<<(total + 127) / 128, 128, 0, st>>>(partials, off, total, acc_threads, XA, hq));
+    JF_LAUNCH(ctx, "bucket_sum_heavy", bucket_sum_heavy_kernel<Fq><<<(unsigned)ctx->sm_count * 4, HEAVY_THREADS, 0, st>>>(partials, off, total, acc_threads, hq, seg_out));
+    JF_LAUNCH(ctx, "bucket_sum_heavy_join", bucket_sum_heavy_join_kernel<Fq><<<(unsigned)ctx->sm_count, HEAVY_THREADS, 0, st>>>(off, total, acc_threads, hq, seg_out, XA));
     }  // bulk
     if (ji + 1 < jc) return JF_OK;  // the group's last member reduces every member's buckets
     {
