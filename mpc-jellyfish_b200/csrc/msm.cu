@@ -319,6 +319,21 @@ __device__ __forceinline__ uint32_t chunk_len(uint32_t entries, uint32_t nthread
     return e < ACC_MIN_CHUNK ? ACC_MIN_CHUNK : e;
 }
 
+// the bucket that holds entry `pos`: the largest b with off[b] <= pos (empty buckets have off[b] == off[b + 1] and are skipped).
+// Out of line: it runs once per long gap, and the accumulation loop around its call site has no register to spare.
+__device__ __noinline__ void seek_bucket(const uint32_t *off, uint32_t total_buckets, uint32_t pos, uint32_t &fb, uint32_t &foff,
+                                         uint32_t &fnext) {
+    uint32_t lo = fb, hi = total_buckets;  // off[lo] <= pos < off[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= pos) lo = mid;
+        else hi = mid;
+    }
+    fb = lo;
+    foff = off[lo];
+    fnext = off[lo + 1];
+}
+
 // Thread t owns entries [t*E, (t+1)*E) of the bucket-ordered list.  It emits one partial per bucket it touches,
 // into slot t + bucket: slots are unique (consecutive threads touch non-decreasing buckets) and the partials of
 // one bucket are consecutive, so no task list or second scan is needed.
@@ -345,10 +360,13 @@ msm_accumulate_kernel(const Affine<Fq> *points, uint32_t srs_n, const uint32_t *
     // fetch cursor: bucket fb holds entries [foff, fnext)
     uint32_t fb = lo, foff = off[lo], fnext = off[lo + 1];
     auto fetch = [&](uint32_t pos) -> uint32_t {
-        while (pos >= fnext) {
+        if (pos >= fnext) {
             fb++;
             foff = fnext;
             fnext = off[fb + 1];
+            // more than one step: the list is sparse here (skewed scalars leave runs of thousands of empty buckets between two
+            // entries); search instead of walking them one dependent load at a time
+            if (pos >= fnext) seek_bucket(off, total_buckets, pos, fb, foff, fnext);
         }
         return SLOTTED ? list[((size_t)fb << cap_log) + (pos - foff)] : list[pos];
     };
