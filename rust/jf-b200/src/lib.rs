@@ -203,6 +203,29 @@ impl<E: GpuCurve> GpuCommitKey<E> {
         let zs = vec![*z; components.len()];
         self.batch_open(components, &zs)
     }
+    /// The key in the Lagrange basis of the size-2^log_n domain (`jf_srs_lagrange`): `commit` over it takes a polynomial's VALUES on
+    /// the domain (zero / small values cost nothing / little).  About a second at 2^20, once per key and domain.
+    pub fn lagrange(&self, log_n: u32, mask_points: bool) -> Result<Self, GpuError> {
+        let mut srs = ptr::null_mut();
+        self.gpu.check(unsafe { sys::jf_srs_lagrange(self.gpu.ctx, self.srs, log_n, mask_points as c_int, &mut srs) })?;
+        Ok(Self { gpu: self.gpu, srs, len: (1usize << log_n) + if mask_points { 2 } else { 0 }, _e: PhantomData })
+    }
+    /// floor(p / Z_D) for the component vectors of a share (`compute_linking_quotient` of the collaborative prover,
+    /// multiprover/proof_system/proof_linking.rs:127-138): division by the public vanishing polynomial of a link group is linear.
+    pub fn div_link_domain(&self, polys: &[&[E::ScalarField]], layout: (usize, usize, usize)) -> Result<Vec<Vec<E::ScalarField>>, GpuError> {
+        let lens: Vec<usize> = polys.iter().map(|p| p.len()).collect();
+        let ptrs: Vec<*const u64> = polys.iter().map(|p| p.as_ptr() as *const u64).collect();
+        let mut outs: Vec<Vec<u64>> = lens.iter().map(|&l| vec![0u64; 4 * l.saturating_sub(layout.2).max(1)]).collect();
+        let optrs: Vec<*mut u64> = outs.iter_mut().map(|o| o.as_mut_ptr()).collect();
+        self.gpu.check(unsafe {
+            sys::jf_poly_div_link_domain(self.gpu.ctx, E::FR, ptrs.as_ptr(), lens.as_ptr(), polys.len(), layout.0 as u32, layout.1, layout.2,
+                                         0, optrs.as_ptr())
+        })?;
+        Ok(outs.iter().zip(&lens).map(|(o, &l)| {
+            (0..l.saturating_sub(layout.2)).map(|i| E::fr_from_mont([o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]])).collect()
+        }).collect())
+    }
+
     /// `PlonkKzgSnark::link_proofs` (plonk/src/proof_system/proof_linking.rs:79-112) from the two hints' wire polynomials and
     /// commitments: -> (quotient commitment, opening proof).  `layout` = (alignment, offset, size) of the `GroupLayout`.
     #[allow(clippy::too_many_arguments)]
@@ -435,6 +458,40 @@ impl<E: GpuCurve> GpuProvingKey<E> {
     }
 }
 impl<E: GpuCurve> Drop for GpuProvingKey<E> { fn drop(&mut self) { unsafe { sys::jf_plonk_pk_free(self.key.gpu.ctx, self.pk) } } }
+
+impl<E: GpuCurve> GpuProvingKey<E> {
+    /// `LinkingHint::linking_wire_poly` of the last proof made with this key (snark.rs:96-100): n + 2 coefficients.
+    pub fn link_hint(&self, n: usize) -> Result<Vec<E::ScalarField>, GpuError> {
+        let mut buf = vec![0u64; 4 * (n + 2)];
+        let mut len = 0usize;
+        self.key.gpu.check(unsafe { sys::jf_plonk_link_hint(self.key.gpu.ctx, self.pk, buf.as_mut_ptr(), n + 2, &mut len) })?;
+        Ok((0..len).map(|i| E::fr_from_mont([buf[4 * i], buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3]])).collect())
+    }
+    /// `link_proofs` with both wire polynomials still in HBM (the last proofs made with `self` and `rhs`).
+    pub fn link_proofs_resident(&self, lhs_proof: &sys::jf_plonk_proof, rhs: &Self, rhs_proof: &sys::jf_plonk_proof,
+                                layout: (usize, usize, usize), solidity_transcript: bool) -> Result<(E::G1Affine, E::G1Affine), GpuError> {
+        let mut out = MaybeUninit::<sys::jf_link_proof>::uninit();
+        self.key.gpu.check(unsafe {
+            sys::jf_plonk_link_proofs_resident(self.key.gpu.ctx, self.pk, lhs_proof, rhs.pk, rhs_proof, layout.0 as u32, layout.1, layout.2,
+                                               if solidity_transcript { 0 } else { 1 }, 0, out.as_mut_ptr())
+        })?;
+        let lp = unsafe { out.assume_init() };
+        let w = 2 * E::L;
+        Ok((E::point_from_mont(&lp.quotient_commitment[..w], lp.quotient_inf != 0), E::point_from_mont(&lp.opening_proof[..w], lp.opening_inf != 0)))
+    }
+    /// ONE proof on several GPUs (one process per GPU): every rank calls `prove` with the same witness and blinders afterwards;
+    /// commitments are split by point range and round 3 by sub-coset (`jf_plonk_pk_shard_commits`).  `comm` and `key_slice` must
+    /// outlive the sharded use of the key; `unshard` returns to one-GPU operation.
+    ///
+    /// # Safety
+    /// `comm` must be a live `jf_comm` created on this key's context.
+    pub unsafe fn shard(&self, comm: *mut sys::jf_comm, key_slice: &GpuCommitKey<E>, slice_start: usize, shard_round3: bool) -> Result<(), GpuError> {
+        self.key.gpu.check(sys::jf_plonk_pk_shard_commits(self.key.gpu.ctx, self.pk, comm, key_slice.srs, slice_start, shard_round3 as c_int))
+    }
+    pub fn unshard(&self) -> Result<(), GpuError> {
+        self.key.gpu.check(unsafe { sys::jf_plonk_pk_shard_commits(self.key.gpu.ctx, self.pk, ptr::null_mut(), ptr::null(), 0, 0) })
+    }
+}
 
 impl<E: GpuCurve> GpuProvingKey<E> {
     /// `PlonkKzgSnark::batch_prove` (snark.rs:201-469) for TurboPlonk keys: one transcript, ONE quotient, one pair of opening

@@ -163,3 +163,21 @@ def test_lagrange_wire_commitments_at_2_pow_16(ctx, co, py, P):
         pk.free()
     assert proofs[0].serialize_compressed() == proofs[1].serialize_compressed()
     key.free()
+
+
+def test_bls12_381_proof_with_lagrange_wire_commitments(ctx, co, py, P):
+    import mpc_jellyfish_b200 as jf
+    import plonk_util as U
+    cv, fr = py.BLS12_381, py.BLS12_381_FR
+    cs = P.gen_circuit_for_test(20, 1, fr)
+    beta = BETA % fr.p
+    arr = U.arrays_from_oracle_circuit(co, py, cs)
+    key = ctx.generate_srs_for_testing("bls12_381", beta, cs.n + 3)
+    pk = jf.PlonkKzgSnark.preprocess(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"],
+                                     arr["pub_gate_ids"], lagrange_wire_commitments=True)
+    opk = P.preprocess(cv, P.gen_srs(cv, beta, cs.n + 2), cs)
+    ints, bl = _blinders(co, fr, 17, 17)
+    assert jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, "standard").serialize_compressed() == \
+        P.serialize_proof(cv, P.prove(cv, cs, opk, ints, "standard"))
+    pk.free()
+    key.free()
