@@ -349,9 +349,10 @@ int jf_plonk_pk_shard_commits(jf_ctx *ctx, jf_plonk_pk *pk, jf_comm *comm, const
  * of q = (a1 - a2) / Z_D (Z_D the vanishing polynomial of those points; remainder dropped like ark-poly's `/`) and a KZG opening
  * (`UnivariateKzgPCS::open`, mod.rs:135-161) of a1 - a2 - q Z_D(eta) at the challenge eta squeezed from a fresh transcript over
  * (a1's commitment, a2's commitment, q's commitment).  On the device: a1 - a2 is evaluated on the 2^alignment-th roots of unity; when
- * it vanishes on the link domain the quotient is a pointwise ratio on a coset (three transforms, independent of `size`), otherwise
- * -- the two proofs are NOT linked and the verifier will reject -- the same floor quotient is obtained from `size` divisions by a
- * linear factor.  flags & 1 forces the second form.  The circuit-side layout (`LinkableCircuit`) stays with the caller. */
+ * it vanishes on the link domain the quotient is a pointwise ratio on a coset (three transforms, independent of `size`); otherwise
+ * -- the two proofs are NOT linked and the verifier will reject -- the remainder (a1 - a2) mod Z_D is taken off first (Z_D divides
+ * X^(2^alignment) - 1, so it is a fold and a short schoolbook reduction) and the same division yields the floor quotient; groups
+ * aligned above 2^12 fall back to `size` divisions by a linear factor.  flags & 1 forces that last form.  The circuit-side layout (`LinkableCircuit`) stays with the caller. */
 typedef struct {
     int curve;
     uint64_t quotient_commitment[12];  /* `LinkingProof::quotient_commitment` (proof_linking.rs:32-39) */
@@ -359,7 +360,8 @@ typedef struct {
     uint64_t opening_proof[12];        /* `LinkingProof::opening_proof` */
     int opening_inf;
     uint64_t eta[4];                   /* the opening challenge (Montgomery): diagnostics */
-    int path;                          /* 0: exact division on a coset, 1: successive linear divisions: diagnostics */
+    int path;                          /* 0: exact division on a coset, 2: the same after taking the remainder off, 1: successive linear
+                                          divisions: diagnostics */
 } jf_link_proof;
 /* `LinkingHint::linking_wire_poly` (structs.rs:88-97; snark.rs:96-100) of the LAST proof made with `pk`: the first wire polynomial
  * after masking, n + 2 Montgomery coefficients (cap >= n + 2 elements).  The hint's commitment is wires_poly_comms[0] of that proof. */
@@ -377,8 +379,7 @@ int jf_plonk_link_proofs_resident(jf_ctx *ctx, const jf_plonk_pk *lhs, const jf_
 /* floor(p / Z_D) for `batch` polynomials (host memory, lens[i] Montgomery coefficients; out_quotients[i] receives
  * max(lens[i] - size, 0)).  Division by the PUBLIC vanishing polynomial is linear, so the collaborative prover's
  * `compute_linking_quotient` (plonk/src/multiprover/proof_system/proof_linking.rs:127-138) is this call on the share, the MAC and the
- * public-modifier vector of a1 - a2; the shares' remainders do not vanish one by one, so they take the linear-division path unless
- * the polynomial happens to vanish on the group.  flags as jf_plonk_link_proofs.  field: JF_BN254_FR / JF_BLS12_381_FR. */
+ * public-modifier vector of a1 - a2; the shares' remainders do not vanish one by one, so they go through the remainder step above.  flags as jf_plonk_link_proofs.  field: JF_BN254_FR / JF_BLS12_381_FR. */
 int jf_poly_div_link_domain(jf_ctx *ctx, int field, const uint64_t *const *polys, const size_t *lens, size_t batch, unsigned alignment,
                             size_t offset, size_t size, int flags, uint64_t *const *out_quotients);
 /* ark-serialize `serialize_compressed` of `LinkingProof<E>`: 64 bytes (BN254) / 96 (BLS12-381); returns the count or < 0 */

@@ -723,6 +723,26 @@ __global__ void link_roots_check_kernel(const Fp<F> *vals, uint32_t stride, uint
     if (i >= size) return;
     if (!ldf(vals + (size_t)((offset + i) & mask) * stride).is_zero()) *flag = 1;
 }
+// rem = p mod z for a MONIC z of degree s and a p of m coefficients held in shared memory: schoolbook, one CTA, m - s dependent
+// steps of s independent products each.  (Proof linking: p = (a1 - a2) mod (X^(2^a) - 1), z = Z_D, which divides X^(2^a) - 1.)
+template <class F> __global__ void __launch_bounds__(1024) poly_mod_monic_kernel(const Fp<F> *p, uint32_t m, const Fp<F> *z, uint32_t s, Fp<F> *rem) {
+    extern __shared__ uint4 poly_mod_smem[];
+    Fp<F> *r = reinterpret_cast<Fp<F> *>(poly_mod_smem);
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) r[i] = ldf(p + i);
+    __syncthreads();
+    for (uint32_t k = m; k-- > s;) {
+        const Fp<F> c = r[k];  // not written in this step
+        if (!c.is_zero())
+            for (uint32_t j = threadIdx.x; j < s; j += blockDim.x) r[k - s + j] = Fp<F>::sub(r[k - s + j], Fp<F>::mul(c, ldf(z + j)));
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < s; i += blockDim.x) stf(rem + i, r[i]);
+}
+// a[j] -= b[j], j < n
+template <class F> __global__ void vsub_kernel(Fp<F> *a, const Fp<F> *b, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) stf(a + i, Fp<F>::sub(ldf(a + i), ldf(b + i)));
+}
 template <class F> __global__ void vmul_kernel(const Fp<F> *a, const Fp<F> *b, Fp<F> *out, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) stf(out + i, Fp<F>::mul(ldf(a + i), ldf(b + i)));
@@ -2050,7 +2070,7 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
         const size_t qlen = max_len > size ? max_len - size : 0;
         const unsigned log_N = link_log_N(max_len, alignment, size);
         const size_t N = (size_t)1 << log_N;
-        bool fast = !(flags & 1) && qlen > 0 && log_N <= (unsigned)Fr::TWO_ADICITY && log_N <= 27;
+        bool fast = !(flags & 1) && qlen > 0 && log_N <= (unsigned)Fr::TWO_ADICITY && log_N <= 27, vanishes = false;
         const E gen = E::from_u32(Fr::GENERATOR);
         uint64_t gen_limbs[4];
         H::fr_to_limbs(gen, gen_limbs);
@@ -2063,19 +2083,32 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
             int flag = 0;
             JF_CUDA(ctx, cudaMemcpyAsync(&flag, d_flag, sizeof flag, cudaMemcpyDeviceToHost, st));
             JF_CUDA(ctx, cudaStreamSynchronize(st));
-            fast = flag == 0;
+            // A non-zero remainder (the pair is not linked; or the dividend is one party's SHARE of a1 - a2): the floor quotient is
+            // (p - p mod Z_D) / Z_D, and because Z_D divides X^(2^a) - 1, p mod Z_D = (p mod (X^(2^a) - 1)) mod Z_D: one fold to 2^a
+            // coefficients and a schoolbook reduction of those in shared memory.  With the remainder taken off the exact division
+            // applies.  (2^a coefficients must fit one CTA's shared memory: alignments up to 12.)
+            vanishes = flag == 0;
+            fast = vanishes || alignment <= 12;
         }
         E *Q = A;  // quotient coefficients
         size_t q_len = qlen;
         if (fast) {
-            *path = 0;
+            *path = vanishes ? 0 : 2;
             const std::vector<E> z = vanishing_coeffs(g, offset, size);
-            JF_LAUNCH(ctx, "fold", fold_kernel<Fr><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(diff, max_len, N, pow_small(gen, (uint64_t)N), A));
-            JF_TRY(ntt_run(ctx, C::FR_ID, A, A, N, log_N, 0, gen_limbs, 1, N));
             void *hz;
             JF_TRY(pinned(ctx, fe * (size + 1), &hz));
             memcpy(hz, z.data(), fe * (size + 1));
             JF_CUDA(ctx, cudaMemcpyAsync(B, hz, fe * (size + 1), cudaMemcpyHostToDevice, st));
+            JF_LAUNCH(ctx, "fold", fold_kernel<Fr><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(diff, max_len, N, pow_small(gen, (uint64_t)N), A));
+            if (!vanishes) {
+                const uint32_t m = 1u << alignment;
+                const size_t smem = fe * m;
+                JF_CUDA(ctx, cudaFuncSetAttribute(poly_mod_monic_kernel<Fr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                JF_LAUNCH(ctx, "fold", fold_kernel<Fr><<<(m + 255) / 256, 256, 0, st>>>(diff, max_len, (size_t)m, E::one(), T));
+                JF_LAUNCH(ctx, "poly_mod_monic", poly_mod_monic_kernel<Fr><<<1, 1024, smem, st>>>(T, m, B, (uint32_t)size, S));
+                JF_LAUNCH(ctx, "vsub", vsub_kernel<Fr><<<(unsigned)((size + 255) / 256), 256, 0, st>>>(A, S, size));
+            }
+            JF_TRY(ntt_run(ctx, C::FR_ID, A, A, N, log_N, 0, gen_limbs, 1, N));
             JF_TRY(ntt_run(ctx, C::FR_ID, B, B, size + 1, log_N, 0, gen_limbs, 1, N));
             JF_TRY((fscan<Fr, OpMul, false>(ctx, B, T, N, tmp)));
             JF_TRY((fscan<Fr, OpMul, true>(ctx, B, S, N, tmp)));

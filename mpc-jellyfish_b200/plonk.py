@@ -132,7 +132,7 @@ class LinkingProof:
     opening_proof: np.ndarray
     opening_inf: bool
     eta: np.ndarray   # the opening challenge, Montgomery limbs (diagnostics)
-    path: int         # 0: exact division on a coset, 1: successive linear divisions (diagnostics)
+    path: int         # 0: exact division on a coset, 2: the same after taking the remainder off, 1: successive linear divisions
     _raw: object = None
 
     def serialize_compressed(self) -> bytes:
