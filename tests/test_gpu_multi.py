@@ -166,3 +166,61 @@ def test_sharded_prover_one_process_per_gpu():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     for k in range(world):
         assert "rank %d ok" % k in r.stdout
+
+
+def test_sharded_prover_one_process_one_thread_per_gpu(co, py):
+    """The form a single Rust prover process needs: ONE process, one thread (context + `jf_comm` over NCCL) per GPU, every thread
+    calling the same prove with the same inputs.  (The peer-memory mailboxes need one process per GPU -- CUDA IPC -- so the
+    transport falls back to NCCL here.)  Bytes == the CPU restatement on every thread."""
+    import random
+    import threading
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import mpc_jellyfish_b200 as jf
+    import plonk_ref as P
+    import plonk_util as U
+    from mpc_jellyfish_b200.sharded import shard_range
+    cv, fr = py.BN254, py.BN254_FR
+    world = 2
+    cs = P.gen_circuit_for_bench(1 << 10)
+    arr = U.arrays_from_oracle_circuit(co, py, cs)
+    beta = BETA % fr.p
+    opk = P.preprocess(cv, P.gen_srs(cv, beta, cs.n + 2), cs)
+    rnd = random.Random(9)
+    ints = [rnd.randrange(fr.p) for _ in range(17)]
+    bl = co.ints_to_limbs([fr.to_mont(v) for v in ints], 4)
+    want = P.serialize_proof(cv, P.prove(cv, cs, opk, ints, "solidity"))
+    uid = jf.Comm.unique_id()
+    results, errors = [None] * world, []
+
+    def worker(rank):
+        try:
+            ctx = jf.Context(rank)
+            comm = jf.Comm(ctx, rank, world, uid, "auto")
+            key = ctx.generate_srs_for_testing("bn254", beta, cs.n + 3)
+            a, b = shard_range(cs.n + 3, world, rank)
+            key_slice = ctx.generate_srs_for_testing("bn254", beta, b - a, first_power=a)
+            pk = jf.PlonkKzgSnark.preprocess(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"],
+                                             arr["pub_gate_ids"])
+            pk.shard_commits(comm, key_slice, a)
+            out = [jf.PlonkKzgSnark.prove(pk, arr["witness"], bl, "solidity").serialize_compressed() for _ in range(3)]
+            results[rank] = (comm.transport, out)
+            pk.shard_commits(None, None)
+            pk.free()
+            key_slice.free()
+            key.free()
+            comm.close()
+            ctx.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append((rank, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    assert not errors, errors
+    for r in range(world):
+        assert results[r] is not None and results[r][0] == "nccl"
+        assert all(o == want for o in results[r][1]), "rank %d: sharded proof differs" % r
