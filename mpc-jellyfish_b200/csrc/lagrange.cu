@@ -33,15 +33,34 @@ template <class Fr> __global__ void lag_twiddle_kernel(uint32_t *tw, Fp<Fr> w_mo
     for (int i = 0; i < 8; i++) tw[8 * (size_t)t + i] = c.v[i];
 }
 
-// k * P for a point in XYZZ form, left to right from the scalar's top bit
+// k * P for a point in XYZZ form: fixed 4-bit windows, left to right.  Every lane of a warp carries its own scalar, so a
+// bit-by-bit double-and-add pays for an addition at almost every bit (some lane always has the bit set); with a 15-entry table
+// (local memory, 128 B per entry) the warp does 254 doublings and 64 additions whatever the scalars are.
 template <class Fq> __device__ XYZZ<Fq> xyzz_mul(const XYZZ<Fq> &p, const uint32_t *k) {
     XYZZ<Fq> acc = XYZZ<Fq>::inf();
     if (p.is_inf()) return acc;
-    int top = 255;
-    while (top >= 0 && !((k[top >> 5] >> (top & 31)) & 1u)) top--;
-    for (int i = top; i >= 0; i--) {
-        acc = acc.dbl();
-        if ((k[i >> 5] >> (i & 31)) & 1u) acc.add(p);
+    XYZZ<Fq> tab[15];  // tab[i] = (i + 1) P
+    tab[0] = p;
+#pragma unroll 1
+    for (int i = 1; i < 15; i++) {
+        if (i & 1) tab[i] = tab[i >> 1].dbl();  // (i + 1) even: 2 * ((i + 1) / 2) P
+        else {
+            tab[i] = tab[i - 1];
+            tab[i].add(p);
+        }
+    }
+    int w = 63;
+    while (w >= 0 && !((k[w >> 3] >> ((w & 7) * 4)) & 15u)) w--;
+#pragma unroll 1
+    for (; w >= 0; w--) {
+        if (!acc.is_inf()) {
+            acc = acc.dbl();
+            acc = acc.dbl();
+            acc = acc.dbl();
+            acc = acc.dbl();
+        }
+        const uint32_t d = (k[w >> 3] >> ((w & 7) * 4)) & 15u;
+        if (d) acc.add(tab[d - 1]);
     }
     return acc;
 }
