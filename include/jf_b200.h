@@ -131,7 +131,7 @@ int jf_msm_combine(jf_ctx *ctx, int curve, const uint64_t *xyzz_parts, size_t pa
  *     128 bytes to the other ranks by whatever channel the caller has; every rank then calls jf_comm_init (collective).
  *     NCCL (libnccl.so.2, loaded at run time: single-GPU users need not have it) bootstraps the group and is one of the two
  *     transports.  transport: 1 = `ncclAllGather` of the partials; 2 = peer-memory mailboxes: every rank maps the other
- *     ranks' mailbox through CUDA IPC, and ONE kernel at the tail of the MSM stores its partial into all peers' HBM over
+ *     ranks' mailbox through CUDA IPC (ranks that are threads of ONE process: through peer access), and ONE kernel at the tail of the MSM stores its partial into all peers' HBM over
  *     NVLink and waits for theirs (no collective launch; the wait gives up after 2 s with JF_ERR_COMM); 0 = 2 when all peers
  *     are reachable, else 1 (env JF_COMM_TRANSPORT=nccl|p2p overrides).
  *     jf_msm_sharded(_device) are collective: every rank calls them in the same order with its own key slice and scalar

@@ -19,6 +19,7 @@
 #include <condition_variable>
 #include <functional>
 #include <thread>
+#include <unistd.h>
 #include "common.cuh"
 #include "ec.cuh"
 
@@ -144,6 +145,7 @@ struct jf_comm {
     unsigned long long seq = 0;
     void *d_part = nullptr;   // this rank's partial (XYZZ)
     void *d_parts = nullptr;  // nranks partials
+    bool via_ipc[jf::MAX_RANKS] = {};  // peers.p[r] was opened with cudaIpcOpenMemHandle (a rank of the SAME process is mapped directly)
 };
 
 // ---- the one-process form ------------------------------------------------------------------------------------------
@@ -304,7 +306,7 @@ void jf_comm_destroy(jf_comm *c) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int r = 0; r < c->nranks; r++)
-        if (r != c->rank && c->peers.p[r]) cudaIpcCloseMemHandle(c->peers.p[r]);
+        if (r != c->rank && c->peers.p[r] && c->via_ipc[r]) cudaIpcCloseMemHandle(c->peers.p[r]);
     NcclApi *api = nccl_api();
     if (api && c->nccl) api->CommDestroy(c->nccl);
     if (c->mbox) cudaFree(c->mbox);
@@ -346,12 +348,18 @@ int jf_comm_init(jf_ctx *ctx, int rank, int nranks, const uint8_t id[JF_COMM_ID_
         struct Rec {
             cudaIpcMemHandle_t h;
             int ok;
-            int pad[15];
+            int pid, device;  // a rank of the same process (one thread per GPU) is reached through its pointer, not through IPC
+            int pad0;
+            unsigned long long ptr;
+            int pad[10];
         };
         static_assert(sizeof(Rec) == 128, "Rec");
         Rec mine = {};
         mine.ok = cudaIpcGetMemHandle(&mine.h, c->mbox) == cudaSuccess ? 1 : 0;
         cudaGetLastError();
+        mine.pid = (int)getpid();
+        mine.device = ctx->device;
+        mine.ptr = (unsigned long long)(uintptr_t)c->mbox;
         Rec *d_all;
         std::vector<Rec> all(nranks);
         JF_CUDA(ctx, cudaMalloc((void **)&d_all, sizeof(Rec) * (nranks + 1)));
@@ -372,12 +380,29 @@ int jf_comm_init(jf_ctx *ctx, int rank, int nranks, const uint8_t id[JF_COMM_ID_
                     continue;
                 }
                 void *p = nullptr;
+                if (all[r].pid == mine.pid) {
+                    // same process: CUDA IPC cannot map it; the pointer is valid here once peer access is on
+                    if (all[r].device != ctx->device) {
+                        int can = 0;
+                        cudaDeviceCanAccessPeer(&can, ctx->device, all[r].device);
+                        cudaError_t e = can ? cudaDeviceEnablePeerAccess(all[r].device, 0) : cudaErrorInvalidDevice;
+                        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                            cudaGetLastError();
+                            p2p_ok = false;
+                            break;
+                        }
+                        cudaGetLastError();
+                    }
+                    c->peers.p[r] = (unsigned char *)(uintptr_t)all[r].ptr;
+                    continue;
+                }
                 if (cudaIpcOpenMemHandle(&p, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                     cudaGetLastError();
                     p2p_ok = false;
                     break;
                 }
                 c->peers.p[r] = (unsigned char *)p;
+                c->via_ipc[r] = true;
             }
         }
         // second round: p2p only if EVERY rank could map every mailbox
@@ -392,8 +417,9 @@ int jf_comm_init(jf_ctx *ctx, int rank, int nranks, const uint8_t id[JF_COMM_ID_
         c->transport = p2p_ok ? 2 : 1;
         if (!p2p_ok)
             for (int r = 0; r < nranks; r++) {
-                if (r != rank && c->peers.p[r]) cudaIpcCloseMemHandle(c->peers.p[r]);
+                if (r != rank && c->peers.p[r] && c->via_ipc[r]) cudaIpcCloseMemHandle(c->peers.p[r]);
                 c->peers.p[r] = nullptr;
+                c->via_ipc[r] = false;
             }
         return JF_OK;
     }();

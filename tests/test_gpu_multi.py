@@ -170,8 +170,9 @@ def test_sharded_prover_one_process_per_gpu():
 
 def test_sharded_prover_one_process_one_thread_per_gpu(co, py):
     """The form a single Rust prover process needs: ONE process, one thread (context + `jf_comm` over NCCL) per GPU, every thread
-    calling the same prove with the same inputs.  (The peer-memory mailboxes need one process per GPU -- CUDA IPC -- so the
-    transport falls back to NCCL here.)  Bytes == the CPU restatement on every thread."""
+    calling the same prove with the same inputs.  Ranks of one process reach each other's mailbox through peer access (CUDA IPC
+    only maps memory of ANOTHER process), so the peer-memory transport is available here too; both transports are run.
+    Bytes == the CPU restatement on every thread."""
     import random
     import threading
     if _ngpu() < 2:
@@ -191,13 +192,12 @@ def test_sharded_prover_one_process_one_thread_per_gpu(co, py):
     ints = [rnd.randrange(fr.p) for _ in range(17)]
     bl = co.ints_to_limbs([fr.to_mont(v) for v in ints], 4)
     want = P.serialize_proof(cv, P.prove(cv, cs, opk, ints, "solidity"))
-    uid = jf.Comm.unique_id()
     results, errors = [None] * world, []
 
-    def worker(rank):
+    def worker(rank, uid, transport):
         try:
             ctx = jf.Context(rank)
-            comm = jf.Comm(ctx, rank, world, uid, "auto")
+            comm = jf.Comm(ctx, rank, world, uid, transport)
             key = ctx.generate_srs_for_testing("bn254", beta, cs.n + 3)
             a, b = shard_range(cs.n + 3, world, rank)
             key_slice = ctx.generate_srs_for_testing("bn254", beta, b - a, first_power=a)
@@ -215,12 +215,15 @@ def test_sharded_prover_one_process_one_thread_per_gpu(co, py):
         except Exception as e:  # noqa: BLE001
             errors.append((rank, repr(e)))
 
-    threads = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join(timeout=600)
-    assert not errors, errors
-    for r in range(world):
-        assert results[r] is not None and results[r][0] == "nccl"
-        assert all(o == want for o in results[r][1]), "rank %d: sharded proof differs" % r
+    for transport, expect in (("auto", "p2p"), ("nccl", "nccl")):
+        uid = jf.Comm.unique_id()
+        threads = [threading.Thread(target=worker, args=(r, uid, transport)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=600)
+        assert not errors, errors
+        for r in range(world):
+            assert results[r] is not None and results[r][0] == expect, (transport, results[r] and results[r][0])
+            assert all(o == want for o in results[r][1]), "rank %d: sharded proof differs (%s)" % (r, transport)
+            results[r] = None
