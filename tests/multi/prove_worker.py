@@ -57,8 +57,9 @@ def main():
                                                        arr["pub_gate_ids"], arr["range_bit_len"], arr["table_key"], arr["table_dom_sep"],
                                                        arr["q_dom_sep"])
             else:
+                # one key also carries the Lagrange-basis form: it is switched off while the key is sharded and back on afterwards
                 pk = jf.PlonkKzgSnark.preprocess(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"],
-                                                 arr["pub_gate_ids"])
+                                                 arr["pub_gate_ids"], lagrange_wire_commitments=(name == "bench_2^10"))
             opk = P.preprocess(cv, P.gen_srs(cv, beta, n + 2), cs)
             rnd = random.Random(31)
             ints = [rnd.randrange(fr.p) for _ in range(P.num_blinders(cs))]
