@@ -99,3 +99,43 @@ def test_product_serializer_emits_the_published_g1_encodings(py):
         else:
             assert pts[2] == g["generator_compressed"][:-2] + "80"   # -G: same x, "negative" flag in the last byte
         assert pts[1] == cv.serialize_compressed(G2).hex() and pts[2] == cv.serialize_compressed(cv.neg(G)).hex()
+
+
+def test_link_proof_serializer_and_linking_challenge_on_the_host(py):
+    """`jf_link_proof_serialize` and the collaborative mirror's `MultiproverLinking.challenge` are host code: `LinkingProof` bytes
+    are the two compressed points in order (published encodings of G / identity), and the challenge over three points equals the
+    restated SolidityTranscript's (proof_linking.rs:171-191)."""
+    import ctypes
+    import numpy as np
+    import plonk_ref as P
+    from mpc_jellyfish_b200 import _ffi
+    from mpc_jellyfish_b200.multiprover import MultiproverLinking, g1_serialize_compressed
+    consts = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "constants.json")))
+    for curve_id, name, cv, key, L in ((0, "bn254", py.BN254, "bn254_g1", 4), (1, "bls12_381", py.BLS12_381, "bls12_381_g1", 6)):
+        g = consts[key]
+        fq = cv.fq
+
+        def limbs(Pt):
+            out = []
+            for v in (fq.to_mont(Pt[0]), fq.to_mont(Pt[1])):
+                out += [(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(L)]
+            return out
+
+        raw = _ffi.LinkProofStruct()
+        raw.curve = curve_id
+        for i, v in enumerate(limbs(cv.gen)):
+            raw.quotient_commitment[i] = v
+        raw.opening_inf = 1
+        buf = ctypes.create_string_buffer(128)
+        n = _ffi.lib().jf_link_proof_serialize(ctypes.byref(raw), buf, len(buf))
+        assert n == 16 * L
+        assert buf.raw[:8 * L].hex() == g["generator_compressed"] and buf.raw[8 * L:n].hex() == g["identity_compressed"]
+        assert _ffi.lib().jf_link_proof_serialize(ctypes.byref(raw), buf, 16 * L - 1) < 0
+        # the three-point challenge
+        pts = [cv.gen, cv.mul(2, cv.gen), None]
+        xy = [(np.array(limbs(Q), dtype=np.uint64), False) if Q is not None else (np.zeros(2 * L, dtype=np.uint64), True) for Q in pts]
+        assert g1_serialize_compressed(name, *xy[1]) == P.ser_g1(cv, pts[1])
+        eta = MultiproverLinking.challenge(name, xy[0], xy[1], xy[2])
+        want = P._link_challenge(cv, pts[0], pts[1], pts[2], "solidity")
+        got = sum(int(eta[i]) << (64 * i) for i in range(4))
+        assert cv.fr.from_mont(got) == want
