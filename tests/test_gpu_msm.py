@@ -240,3 +240,51 @@ def test_msm_2_20_random_points_vs_oracle_pippenger(ctx, co):
     key.free()
     wxy, winf = co.msm("bn254", pts, s)
     assert inf == winf and np.array_equal(xy, wxy)
+
+
+@pytest.mark.parametrize("shape", ["all_ones", "all_equal", "zeros_but_two", "small_integers", "constant_plus_random_tail"])
+@pytest.mark.parametrize("skew_key", [False, True])
+def test_msm_piled_up_and_sparse_scalars_at_2_17(ctx, co, py, shape, skew_key):
+    """Scalars as a Lagrange-basis key meets them (witness VALUES): one bucket holding the whole MSM (several segments of the heavy
+    bucket sums), a handful of entries scattered over 65536 buckets (a thread's chunk spans thousands of empty buckets), small
+    integers (eight buckets of the second window hold an eighth of the MSM each).  Checked with the known-beta identity
+    commit(p) == p(beta) G on a plain key and on a key marked as skewed (the Lagrange-basis key of the same size: then the
+    scalars are read as values on the domain, and the identity becomes commit == p_interp(beta) G)."""
+    fr = py.BN254_FR
+    p = fr.p
+    log_n = 17
+    n = 1 << log_n
+    beta = 0x5DEECE66D1234567890ABCDEF % p
+    key = ctx.generate_srs_for_testing("bn254", beta, n + 3)
+    use = key.lagrange(log_n) if skew_key else key
+    rng = np.random.default_rng(7)
+    s = np.zeros((n, 4), dtype=np.uint64)
+    if shape == "all_ones":
+        s[:, 0] = 1
+    elif shape == "all_equal":
+        s[:] = co.random_field_elems("bn254_fr", 1, 5, False)[0]
+    elif shape == "zeros_but_two":
+        s[[17, n - 3]] = co.random_field_elems("bn254_fr", 2, 6, False)
+    elif shape == "small_integers":
+        s[:, 0] = np.arange(n, dtype=np.uint64)
+    else:
+        s[:, 0] = 3
+        s[n - 2:] = co.random_field_elems("bn254_fr", 2, 8, False)
+    xy, inf = ctx.msm(use, s)
+    vals = co.limbs_to_ints(s)
+    if skew_key:   # the scalars are values on H: p_interp(beta) = sum_j v_j L_j(beta), L_j(beta) = w^j (beta^n - 1) / (n (beta - w^j))
+        w = py.Radix2Domain(fr, n).group_gen
+        c = (pow(beta, n, p) - 1) * pow(n, -1, p) % p
+        acc, wj = 0, 1
+        for v in vals:
+            if v:
+                acc = (acc + v * wj % p * pow((beta - wj) % p, -1, p)) % p
+            wj = wj * w % p
+        want_scalar = acc * c % p
+    else:
+        want_scalar = py.poly_eval(fr, vals, beta)
+    want = co.fixed_base_mul("bn254", co.ints_to_limbs([want_scalar], 4))[0]
+    assert not inf and np.array_equal(xy, want), (shape, skew_key)
+    if skew_key:
+        use.free()
+    key.free()
