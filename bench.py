@@ -472,6 +472,22 @@ def prove_leg(ctx, co, torch, args, world, rank, barrier, max_over_ranks, stream
                          "round 3 on seven sub-cosets of n points (35 polynomials; the reference's 8n coset gives the same bytes, "
                          "tests/test_gpu_ultraplonk.py); the sorted lookup vector is built on the device (hash set of the table values, counts, prefix sum, expansion)"}
         pkU.free()
+        # ... and with every key-side option (resident selector / sigma / table coset evaluations, zero-selector skip,
+        # Lagrange-basis wire commitments): same proof bytes
+        pkU = jf_mod().PlonkKzgSnark.preprocess_ultra(ctx, keyU, arrU["selectors"], arrU["sigmas"], arrU["k"], arrU["wire_vars"],
+                                                      arrU["num_vars"], [], arrU["range_bit_len"], arrU["table_key"],
+                                                      arrU["table_dom_sep"], arrU["q_dom_sep"], skip_zero_selectors=True,
+                                                      lagrange_wire_commitments=True, cache_coset_evals=True)
+        if jf_mod().PlonkKzgSnark.prove_ultra(pkU, witU, blU, "solidity").serialize_compressed() != proofU.serialize_compressed():
+            raise SystemExit("bench.py: the key-side options changed the UltraPlonk proof; refusing to time it")
+        jf_mod().PlonkKzgSnark.prove_ultra(pkU, witU, blU, "solidity")
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            jf_mod().PlonkKzgSnark.prove_ultra(pkU, witU, blU, "solidity")
+        barrier()
+        ultra["with_all_key_side_options_ms"] = max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+        pkU.free()
         keyU.free()
     if rank != 0:
         return None

@@ -267,7 +267,8 @@ long jf_plonk_proof_serialize(const jf_plonk_proof *proof, uint8_t *out, size_t 
  * is built on the device.  jf_plonk_vk_commitments then yields 14 selector, 6 sigma and the 4 `PlookupVerifyingKey`
  * commitments (range table, key table, table dom sep, q dom sep; snark.rs:573-594), in that order.
  * Round 3 evaluates the quotient (degree 6 n + 8) on SEVEN sub-cosets of n points (from n = 16), like the six of the TurboPlonk
- * prover; flags: 2 (skip zero selectors) and 4 (the reference's 8n-point coset instead) as for jf_plonk_preprocess. */
+ * prover; flags as for jf_plonk_preprocess: 1 (resident coset evaluations of the 14 selector, 6 sigma and 4 table polynomials),
+ * 2 (skip zero selectors), 4 (the reference's 8n-point coset instead), 8 (Lagrange-basis wire commitments). */
 int jf_ultraplonk_preprocess(jf_ctx *ctx, const jf_srs *srs, unsigned log_n, const uint64_t *selector_evals,
                              const uint64_t *sigma_evals, const uint64_t *k, const uint32_t *wire_variables, size_t num_vars,
                              const uint32_t *pub_input_gate_ids, size_t num_inputs, unsigned range_bit_len,

@@ -1075,7 +1075,7 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
         pk->np = np;
         pk->num_vars = num_vars;
         pk->num_inputs = (uint32_t)num_inputs;
-        pk->cache_coset = ULTRA ? 0 : (flags & 1);
+        pk->cache_coset = flags & 1;
         pk->skip_zero = (flags & 2) ? 1 : 0;
         // 6 n >= 5 n + 8 coefficients needs n >= 8; n >= 16 also leaves n - 8 >= 8 coefficients above the quotient's degree
         // for the WrongQuotientPolyDegree check (at n = 8 the six-row interpolant has no coefficient above degree 47 at all)
@@ -1205,7 +1205,7 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
         JF_TRY(dalloc(ctx, pk, fe * m, &pk->d_a));   // scan inputs / outputs (m-sized for the inversion table)
         JF_TRY(dalloc(ctx, pk, fe * m, &pk->d_b));
         JF_TRY(dalloc(ctx, pk, fe * (m / 256 + 4096), &pk->d_tmp));
-        const int ne = pk->cache_coset ? NW + 2 : NROWS;
+        const int ne = pk->cache_coset ? NW + 2 + (ULTRA ? 3 : 0) : NROWS;  // resident: selectors, sigmas [, the four table polynomials]
         JF_TRY(dalloc(ctx, pk, fe * (size_t)ne * mq, &pk->d_e));
         JF_TRY(dalloc(ctx, pk, fe * m, &pk->d_q));
         JF_TRY(dalloc(ctx, pk, fe * NW * np, &pk->d_split));
@@ -1226,7 +1226,7 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
             pk->sv_slots = (uint32_t)(4 * n);
             JF_TRY(dalloc(ctx, pk, sizeof(uint32_t) * (16 + 2 * n + (n / (SV_T * SV_I) + 2) + pk->sv_slots), (void **)&pk->d_sv));
         }
-        if (pk->cache_coset) JF_TRY(dalloc(ctx, pk, fe * (size_t)(NSEL + NW) * mq, &pk->d_cached));
+        if (pk->cache_coset) JF_TRY(dalloc(ctx, pk, fe * (size_t)(NSEL + NW + (ULTRA ? 4 : 0)) * mq, &pk->d_cached));
         JF_CUDA(ctx, cudaMemcpyAsync(pk->d_sel, selector_evals, fe * NSEL * n, cudaMemcpyHostToDevice, st));
         JF_CUDA(ctx, cudaMemcpyAsync(pk->d_sig, sigma_evals, fe * NW * n, cudaMemcpyHostToDevice, st));
         JF_CUDA(ctx, cudaMemcpyAsync(pk->d_sig_evals, sigma_evals, fe * NW * n, cudaMemcpyHostToDevice, st));
@@ -1274,6 +1274,7 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
         if (pk->cache_coset) {
             JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sel, n, n, NSEL, (E *)pk->d_cached, pk->zero_sel));
             JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_sig, n, n, NW, (E *)pk->d_cached + (size_t)NSEL * mq));
+            if (ULTRA) JF_TRY(coset_fft_rows(ctx, pk, (const E *)pk->d_lk, n, n, 4, (E *)pk->d_cached + (size_t)(NSEL + NW) * mq));
         }
         // transcript prefix (transcript/mod.rs:45-88): sizes, k, selector and sigma commitments
         JF_CUDA(ctx, cudaStreamSynchronize(st));
@@ -1458,7 +1459,8 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
             jf_plonk_pk *pk;
             E *W, *PI, *Z, *WV, *H1, *H2, *PL, *small;
             const E *LK, *QL, *sel_c, *sig_c;
-            E *w_c, *z_c, *pi_c, *lk_c;
+            E *w_c, *z_c, *pi_c, *lk_c;   // lk_c: h1, h2, lookup product (UltraPlonk)
+            const E *lkt_c;               // range, key, table dom sep, q dom sep: per proof, or the resident copies
             E ev[2 * NW + 15];
         };
         std::vector<Inst> I(count);
@@ -1497,8 +1499,15 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
             }
             s.z_c = s.w_c + (size_t)NW * m;
             s.pi_c = s.z_c + m;
-            s.lk_c = s.pi_c + m;  // UltraPlonk: 7 more rows
-            if (ULTRA) JF_TRY(on_side(ctx, pk0, [&]() -> int { return coset_fft_rows(ctx, pk, s.LK, n, n, 4, s.lk_c); }));
+            if (ULTRA && pk->cache_coset) {
+                s.lkt_c = s.sig_c + (size_t)NW * m;
+                s.lk_c = s.pi_c + m;  // 3 more rows
+            } else {
+                E *t = s.pi_c + m;    // UltraPlonk: 7 more rows
+                s.lkt_c = t;
+                s.lk_c = t + 4 * m;
+                if (ULTRA) JF_TRY(on_side(ctx, pk0, [&]() -> int { return coset_fft_rows(ctx, pk, s.LK, n, n, 4, t); }));
+            }
             std::vector<E> pub(pk->num_inputs);
             for (size_t k = 0; k < pk->num_inputs; k++) pub[k] = H::fr_from_limbs(witnesses[i] + 4 * (size_t)pk->pub_vars[k]);
             append_vk_and_pub_input(tr, pk, pub.data(), pub.size());
@@ -1557,7 +1566,7 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
                 JF_TRY(intt_n(ctx, pk, s.H1, 2, np));
                 JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(s.H1, n, bl_h + i * 6, 3));
                 JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(s.H2, n, bl_h + i * 6 + 3, 3));
-                JF_TRY(on_side(ctx, pk0, [&]() -> int { return coset_fft_rows(ctx, pk, s.H1, np, n + 3, 2, s.lk_c + 4 * m); }));
+                JF_TRY(on_side(ctx, pk0, [&]() -> int { return coset_fft_rows(ctx, pk, s.H1, np, n + 3, 2, s.lk_c); }));
                 CommitJob jobs[2] = {{s.H1, n + 3, 0}, {s.H2, n + 3, 1}};
                 JF_TRY(commit_many(ctx, pk, jobs, 2));
                 JF_TRY(fetch_commits(ctx, pk, 0, 2, out->h_poly_comms, out->h_inf));
@@ -1612,7 +1621,7 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
                 JF_LAUNCH(ctx, "set_one", set_one_kernel<Fr><<<1, 32, 0, st>>>(s.PL + (n - 1)));  // the reference pushes 1 as the last value
                 JF_TRY(intt_n(ctx, pk, s.PL, 1, np));
                 JF_LAUNCH(ctx, "blind", blind_kernel<Fr><<<1, 32, 0, st>>>(s.PL, n, bl_pl + i * 3, 3));
-                JF_TRY(on_side(ctx, pk0, [&]() -> int { return coset_fft_rows(ctx, pk, s.PL, np, n + 3, 1, s.lk_c + 6 * m); }));
+                JF_TRY(on_side(ctx, pk0, [&]() -> int { return coset_fft_rows(ctx, pk, s.PL, np, n + 3, 1, s.lk_c + 2 * m); }));
                 JF_TRY(commit_dev(ctx, pk, s.PL, n + 3, 0));
                 JF_TRY(fetch_commits(ctx, pk, 0, 1, out->prod_lookup_poly_comm, &out->prod_lookup_inf));
                 tr_g1(tr, "plookup_poly_comms", out->prod_lookup_poly_comm, out->prod_lookup_inf);
@@ -1649,13 +1658,13 @@ template <class C, int NWT = NW_TURBO> struct Plonk {
                 for (int r = 0; r < 8; r++) q.zh_inv[r] = lf(pk->zh_inv[r]);
                 q.omega_inv = lf(pk->omega_n_inv);
                 if (ULTRA) {
-                    q.lk.range = s.lk_c;
-                    q.lk.key = s.lk_c + m;
-                    q.lk.tds = s.lk_c + 2 * m;
-                    q.lk.qds = s.lk_c + 3 * m;
-                    q.lk.h1 = s.lk_c + 4 * m;
-                    q.lk.h2 = s.lk_c + 5 * m;
-                    q.lk.pl = s.lk_c + 6 * m;
+                    q.lk.range = s.lkt_c;
+                    q.lk.key = s.lkt_c + m;
+                    q.lk.tds = s.lkt_c + 2 * m;
+                    q.lk.qds = s.lkt_c + 3 * m;
+                    q.lk.h1 = s.lk_c;
+                    q.lk.h2 = s.lk_c + m;
+                    q.lk.pl = s.lk_c + 2 * m;
                     q.lk.tau = tau;
                     q.lk.bp1 = bp1;
                     q.lk.gb = gb;

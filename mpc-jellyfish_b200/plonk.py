@@ -367,7 +367,7 @@ class PlonkKzgSnark:
                          wire_variables: np.ndarray, num_vars: int, pub_input_gate_ids: Sequence[int], range_bit_len: int,
                          table_key_evals: np.ndarray, table_dom_sep_evals: np.ndarray, q_dom_sep_evals: np.ndarray,
                          skip_zero_selectors: bool = False, full_quotient_coset: bool = False,
-                         lagrange_wire_commitments: bool = False) -> ProvingKey:
+                         lagrange_wire_commitments: bool = False, cache_coset_evals: bool = False) -> ProvingKey:
         """selector_evals (14, n, 4) = `all_selectors()` with q_lookup last, sigma_evals (6, n, 4), k (6, 4), wire_variables (6, n)
         with the range wire last; table_key / table_dom_sep / q_dom_sep: (n, 4) per-gate columns (constraint_system.rs:873-888)."""
         sel = np.ascontiguousarray(selector_evals, dtype=np.uint64)
@@ -388,7 +388,8 @@ class PlonkKzgSnark:
             kk.ctypes.data_as(_ffi.c_u64p), wv.ctypes.data_as(_ffi.c_u32p), num_vars,
             gids.ctypes.data_as(_ffi.c_u32p) if len(gids) else None, len(gids), range_bit_len,
             cols[0].ctypes.data_as(_ffi.c_u64p), cols[1].ctypes.data_as(_ffi.c_u64p), cols[2].ctypes.data_as(_ffi.c_u64p),
-            (2 if skip_zero_selectors else 0) | (4 if full_quotient_coset else 0) | (8 if lagrange_wire_commitments else 0), ctypes.byref(h)))
+            int(cache_coset_evals) | (2 if skip_zero_selectors else 0) | (4 if full_quotient_coset else 0)
+            | (8 if lagrange_wire_commitments else 0), ctypes.byref(h)))
         return ProvingKey(ctx, key, h, n, num_vars, len(gids), kk, ultra=True)
 
     @staticmethod

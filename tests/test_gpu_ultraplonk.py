@@ -155,3 +155,31 @@ def test_large_ultraplonk_proofs_are_accepted_by_the_restated_verifier(ctx, co, 
     assert not P.verify(cv, vk, [], dict(got, plookup_proof=lp), beta, kind)
     pk.free()
     key.free()
+
+
+@pytest.mark.parametrize("which", ["test_m12", "bench_3000"])
+def test_ultraplonk_resident_coset_evaluations_give_the_same_proof(ctx, co, py, P, which):
+    """flags & 1 for UltraPlonk keys: the coset evaluations of the 14 selector, 6 sigma and 4 table polynomials stay resident
+    (24 of the 35 polynomials of round 3 are transformed once per key); alone and with the other key-side options, on the seven
+    sub-cosets and on the 8n coset: byte-identical proofs, several in a row."""
+    import mpc_jellyfish_b200 as jf
+    cv, fr = py.BN254, py.BN254_FR
+    cs = {"test_m12": lambda: P.gen_circuit_for_test(12, 1, ultra=True), "bench_3000": lambda: P.gen_circuit_for_bench(3000, ultra=True)}[which]()
+    beta = 0xABCDEF1234567 % fr.p
+    opk = P.preprocess(cv, P.gen_srs(cv, beta, cs.n + 2), cs)
+    import plonk_util as U2
+    arr = U2.arrays_from_oracle_circuit(co, py, cs)
+    key = ctx.generate_srs_for_testing("bn254", beta, cs.n + 3)
+    rnd = random.Random(15)
+    for opts in (dict(cache_coset_evals=True), dict(cache_coset_evals=True, skip_zero_selectors=True, lagrange_wire_commitments=True),
+                 dict(cache_coset_evals=True, full_quotient_coset=True)):
+        pk = jf.PlonkKzgSnark.preprocess_ultra(ctx, key, arr["selectors"], arr["sigmas"], arr["k"], arr["wire_vars"], arr["num_vars"],
+                                               arr["pub_gate_ids"], arr["range_bit_len"], arr["table_key"], arr["table_dom_sep"],
+                                               arr["q_dom_sep"], **opts)
+        for kind in ("solidity", "standard"):
+            ints = [rnd.randrange(fr.p) for _ in range(29)]
+            bl = co.ints_to_limbs([fr.to_mont(v) for v in ints], 4)
+            want = P.serialize_proof(cv, P.prove(cv, cs, opk, ints, kind))
+            assert jf.PlonkKzgSnark.prove_ultra(pk, arr["witness"], bl, kind).serialize_compressed() == want, (opts, kind)
+        pk.free()
+    key.free()
