@@ -93,3 +93,27 @@ def test_host_mirror_logic_without_gpu():
         assert rs[0][0] == 0 and rs[-1][1] == n and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
         assert max(e - s for s, e in rs) - min(e - s for s, e in rs) <= 1
     assert [poly_owner(i, 4) for i in range(6)] == [0, 1, 2, 3, 0, 1]
+
+
+def test_rust_patches_apply_to_the_reference_tree(tmp_path):
+    """rust/patches/*.diff are unified diffs against the reference as surveyed; where the reference tree is present (the build
+    container, not the GPU box) each one must still apply cleanly to a scratch copy of its target file."""
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present")
+    patches = sorted(f for f in os.listdir(os.path.join(ROOT, "rust", "patches")) if f.endswith(".diff"))
+    assert len(patches) >= 3
+    for name in patches:
+        text = open(os.path.join(ROOT, "rust", "patches", name)).read()
+        targets = re.findall(r"^\+\+\+ b/(\S+)", text, flags=re.M)
+        assert targets, name
+        work = tmp_path / name
+        for t in targets:
+            dst = work / t
+            dst.parent.mkdir(parents=True, exist_ok=True)
+            dst.write_bytes(open(os.path.join(ref, t), "rb").read())
+        r = subprocess.run(["patch", "-p1", "--batch", "-i", os.path.join(ROOT, "rust", "patches", name)], cwd=work,
+                           capture_output=True, text=True)
+        assert r.returncode == 0 and "FAILED" not in r.stdout, name + ": " + r.stdout + r.stderr
+        for t in targets:
+            assert "jf_b200::" in (work / t).read_text(), "%s does not route %s through the B200 library" % (name, t)
