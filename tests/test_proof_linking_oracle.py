@@ -232,3 +232,39 @@ def test_vanishing_polynomial_closed_form(P, py, alignment, offset, size):
             nz[i + 1] = (nz[i + 1] + c) % p
         z = nz
     assert _vanishing_coeffs_model(p, g, offset, size) == z
+
+
+@pytest.mark.parametrize("alignment,offset,size,plen", [(4, 3, 5, 40), (5, 11, 10, 34), (6, 2, 50, 300), (8, 20, 10, 258), (3, 1, 6, 9)])
+def test_remainder_through_the_fold_then_exact_division(P, py, alignment, offset, size, plen):
+    """the algebra of the device's path for dividends that do not vanish on the group (csrc/plonk.cu: `fold`, `poly_mod_monic`):
+    Z_D divides X^(2^a) - 1, so p mod Z_D = (p mod (X^(2^a) - 1)) mod Z_D, and floor(p / Z_D) = (p - p mod Z_D) / Z_D exactly."""
+    fr = py.BN254_FR
+    p = fr.p
+    rnd = random.Random(alignment * 1000 + size)
+    lay = P.GroupLayout(alignment, offset, size)
+    poly = [rnd.randrange(p) for _ in range(plen)]
+    z = _vanishing_coeffs_model(p, lay.domain_generator(fr), offset, size)
+    m = 1 << alignment
+    folded = [0] * m
+    for i, c in enumerate(poly):                 # p mod (X^m - 1)
+        folded[i % m] = (folded[i % m] + c) % p
+    rem = list(folded)
+    for k in range(m - 1, size - 1, -1):         # schoolbook reduction mod the monic Z_D, top coefficient first
+        c = rem[k]
+        if c:
+            for j in range(size):
+                rem[k - size + j] = (rem[k - size + j] - c * z[j]) % p
+    rem = rem[:size]
+    # the remainder interpolates p on the group ...
+    for r in P._link_roots(fr, lay):
+        assert P._poly_eval(p, rem, r) == P._poly_eval(p, poly, r)
+    # ... and taking it off makes the division exact, with the floor quotient as its result
+    exact = P._poly_add(p, poly, [(-c) % p for c in rem])
+    want = P.linking_quotient(fr, poly, [], lay)
+    assert want == P.linking_quotient_schoolbook(fr, poly, [], lay)
+    assert P.linking_quotient(fr, exact, [], lay) == want
+    back = [0] * (len(want) + size)
+    for i, a in enumerate(want):
+        for j, b in enumerate(z):
+            back[i + j] = (back[i + j] + a * b) % p
+    assert P._strip(back) == P._strip(exact)
